@@ -1,0 +1,94 @@
+"""The oracle (numpy restatement) against golden vectors produced by the REAL reference
+(oracle/make_golden.py, run in the build container).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle import codec_oracle as O
+from tests.helpers import cases, load_case
+
+TOL_AUDIO = 2e-6      # fp32 vs fp32, different summation orders (observed <= 2.2e-7)
+TOL_FEAT = 2e-5       # intermediates have magnitudes of a few units (observed <= 4.3e-6)
+
+
+@pytest.mark.parametrize("case", cases("offline") + cases("reference_init"), ids=lambda c: c["name"])
+def test_offline_decode_matches_reference(case):
+    cfg, sd, g = load_case(case)
+    taps = {}
+    y = O.decode(sd, g["tokens"], cfg.num_heads, cfg.hop_length, taps=taps)
+    assert y.shape == g["audio"].shape == (case["B"], case["L"] * cfg.samples_per_token)
+    assert np.abs(y - g["audio"]).max() < TOL_AUDIO
+    assert O.snr_db(g["audio"], y) > 100.0
+    for k in ("z", "x50", "prior", "layer0", "final"):
+        if k in g.files:
+            assert np.abs(taps[k] - g[k]).max() < TOL_FEAT, k
+    if "up_full" in g.files:  # reference keeps 3 extra frames before the trim (decoder.py:615)
+        up = taps["up"]
+        assert np.abs(up - g["up_full"][:, :up.shape[1]]).max() < TOL_FEAT
+
+
+@pytest.mark.parametrize("case", cases("stream"), ids=lambda c: c["name"])
+def test_streaming_decode_matches_reference(case):
+    cfg, sd, g = load_case(case)
+    tok, chunks = g["tokens"], list(g["chunks"])
+    st, pos, outs = None, 0, []
+    for i, lc in enumerate(chunks):
+        y, st = O.decode_chunk(sd, tok[:, :, pos:pos + lc], st, i == len(chunks) - 1, cfg.num_heads, cfg.hop_length)
+        ref = g[f"audio_{i}"]
+        first, last = i == 0, i == len(chunks) - 1
+        n = cfg.samples_per_token * lc - cfg.istft_pad * first + cfg.istft_pad * last
+        assert y.shape == ref.shape == (case["B"], n)
+        assert np.abs(y - ref).max() < TOL_AUDIO
+        outs.append(y)
+        pos += lc
+    for k, v in st.to_reference_layout(cfg.num_heads).items():
+        ref = g["cache_" + k]
+        assert v.shape == ref.shape, k
+        assert np.abs(v - ref).max() < TOL_FEAT, k
+    # one token per call == offline (block of 8 frames == one token); multi-token chunks are unmasked
+    # inside the chunk (whisper.py:107-113) and legitimately differ from offline.
+    cat = np.concatenate(outs, axis=1)
+    if all(c == 1 for c in chunks):
+        assert np.abs(cat - g["offline"]).max() < TOL_AUDIO
+    assert cat.shape == g["offline"].shape
+
+
+def test_identity_projection_sum_is_index_ordered():
+    case = [c for c in cases("offline") if c["name"] == "tiny_ident_offline"][0]
+    cfg, sd, g = load_case(case)
+    rows = O.rvq_gather(sd, g["tokens"])
+    emb, _ = O.rvq_decode_codes(sd, g["tokens"])
+    acc = np.zeros_like(rows[:, :, 0, :])
+    for i in range(cfg.num_quantizers):
+        acc = acc + rows[:, :, i, :]
+    assert np.array_equal(acc, emb)
+    for i in range(cfg.num_quantizers):
+        cb = sd[f"rvq.quantizers.{i}.codebook"]
+        assert np.array_equal(rows[:, :, i, :], cb[g["tokens"][:, i, :]])
+
+
+def test_out_of_range_index_raises():
+    case = cases("offline")[0]
+    cfg, sd, g = load_case(case)
+    tok = g["tokens"].copy()
+    tok[0, 1, 2] = cfg.codebook_size
+    with pytest.raises(IndexError):
+        O.decode(sd, tok, cfg.num_heads)
+    tok[0, 1, 2] = -1
+    with pytest.raises(IndexError):
+        O.decode(sd, tok, cfg.num_heads)
+
+
+def test_prefix_codebooks_allowed():
+    # quantizers[:nq] — fewer codebooks than configured are accepted (rvq.py:160)
+    case = cases("offline")[0]
+    cfg, sd, g = load_case(case)
+    y = O.decode(sd, g["tokens"][:, :2, :], cfg.num_heads)
+    assert y.shape == g["audio"].shape and np.isfinite(y).all()
+
+
+def test_batch_row_equals_single():
+    case = cases("offline")[0]
+    cfg, sd, g = load_case(case)
+    y = O.decode(sd, g["tokens"], cfg.num_heads)
+    y0 = O.decode(sd, g["tokens"][1:2], cfg.num_heads)
+    assert np.abs(y[1:2] - y0).max() < TOL_AUDIO
