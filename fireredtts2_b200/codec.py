@@ -1,0 +1,259 @@
+"""Drop-in replacement for the reference's codec decode entry points.
+
+``RedCodecB200`` duck-types what ``FireRedTTS2`` uses of ``RedCodecInfer`` (reference
+``fireredtts2/codec/model.py:197-376``; call sites ``fireredtts2/fireredtts2.py:51-53,96,196,441``):
+
+* ``decode(tokens (B,nq,L) int32|int64, any strides) -> (B, 1920*L) float32``
+* ``decode_one_token(token (B,nq,Lc), cache_dict, last_token) -> (audio (B,n), new_cache_dict)``
+* ``encode(...)`` — delegated to a wrapped reference module when one is given (encode is out of scope).
+
+All compute runs in libfrt2_b200.so (hand-written sm_100a CUDA) through the C ABI in ``include/frt2.h``;
+PyTorch only provides device memory and the current CUDA stream.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as N
+from .config import CodecConfig
+from .weights import decode_keys, normalise_state_dict
+
+_STATE_KEY = "frt2_state"
+_REF_CACHE_KEYS = ("up_conv_cache", "bb_conv_cache1", "bb_conv_cache2", "bb_kv_cache", "is_cache")
+
+
+class _NativeStream:
+    """Owns a frt2_stream (the in-HBM equivalent of the reference's cache_dict)."""
+
+    def __init__(self, codec: "RedCodecB200", batch: int, max_tokens: int):
+        self.codec = codec
+        self.batch = batch
+        self.max_tokens = max_tokens
+        self.ptr = C.c_void_p()
+        N.check(codec._lib.frt2_stream_create(codec._h, batch, max_tokens, C.byref(self.ptr)))
+        self.finished = False
+
+    @property
+    def n_tokens(self) -> int:
+        return int(self.codec._lib.frt2_stream_tokens(self.ptr))
+
+    def close(self):
+        if self.ptr:
+            self.codec._lib.frt2_stream_destroy(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RedCodecB200(torch.nn.Module):
+    def __init__(self, cfg: CodecConfig, state_dict, device="cuda:0", encoder: Optional[torch.nn.Module] = None,
+                 stream_max_tokens: int = 1200, check_indices: bool = True):
+        super().__init__()
+        self._lib = N.load()   # raises if the CUDA extension is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("RedCodecB200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("RedCodecB200 runs on CUDA devices only")
+        self.device_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.stream_max_tokens = stream_max_tokens
+        self.check_indices = check_indices
+        self._encoder = [encoder]  # list: keep the reference module out of nn.Module registration
+        self._h = C.c_void_p()
+        c = N.Frt2Config(cfg.rvq_dim, cfg.output_dim, cfg.num_quantizers, cfg.codebook_size, cfg.codebook_dim,
+                         cfg.embed_dim, cfg.num_layers, cfg.num_heads, cfg.hop_length, cfg.upconv_stride)
+        N.check(self._lib.frt2_create(C.byref(c), self.device_index, C.byref(self._h)))
+        sd = normalise_state_dict(state_dict)
+        for key in decode_keys(cfg):
+            if key not in sd:
+                raise KeyError(f"state_dict is missing decode-path tensor {key!r}")
+            a = np.ascontiguousarray(sd[key], dtype=np.float32)
+            shape = (C.c_int64 * a.ndim)(*a.shape)
+            N.check(self._lib.frt2_load_tensor(self._h, key.encode(), a.ctypes.data_as(C.c_void_p), a.ndim, shape, 0))
+        N.check(self._lib.frt2_finalize(self._h))
+
+    # ------------------------------------------------------------------ constructors
+    @classmethod
+    def from_reference(cls, ref: torch.nn.Module, num_heads: Optional[int] = None, **kw) -> "RedCodecB200":
+        """Build from a live reference ``RedCodecInfer`` (weights copied once; ``encode`` delegates to it)."""
+        ad = ref.acoustic_decoder
+        q0 = ref.rvq.quantizers[0]
+        cfg = CodecConfig(rvq_dim=ref.rvq.rvq_dim, output_dim=ad.embed_dim, num_quantizers=len(ref.rvq.quantizers),
+                          codebook_size=q0.codebook.shape[0], codebook_dim=q0.codebook.shape[1],
+                          embed_dim=ad.embed_dim, num_layers=ad.num_layers,
+                          num_heads=num_heads or ad.num_heads, hop_length=ad.hop_length)
+        if not getattr(ad, "causal", True):
+            raise AssertionError("Only AcousticDecoder with causal=True supports forward_chunk method.")
+        return cls(cfg, ref.state_dict(), encoder=ref, **kw)
+
+    @classmethod
+    def from_pretrained(cls, conf_path: str, ckpt_path: str, **kw) -> "RedCodecB200":
+        """Same arguments as ``RedCodecInfer.from_pretrained`` (reference model.py:210-216); decode-only."""
+        with open(conf_path, "r") as f:
+            cfg = CodecConfig.from_reference_dict(json.load(f))
+        ckpt = torch.load(ckpt_path, map_location="cpu")["generator"]
+        return cls(cfg, ckpt, **kw)
+
+    # ------------------------------------------------------------------ nn.Module compatibility
+    def to(self, *args, **kwargs):  # weights live in the native handle on self.device
+        return self
+
+    def __del__(self):
+        try:
+            if self._h:
+                self._lib.frt2_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _cuda_stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.device_index).cuda_stream)
+
+    def _prep_tokens(self, tokens: torch.Tensor) -> torch.Tensor:
+        if tokens.dim() != 3:
+            raise ValueError(f"tokens must be (B, nq, L), got {tuple(tokens.shape)}")
+        if tokens.dtype not in (torch.int32, torch.int64):
+            if tokens.dtype.is_floating_point or tokens.dtype == torch.bool:
+                raise TypeError(f"tokens must be an integer tensor, got {tokens.dtype}")
+            tokens = tokens.long()
+        if tokens.device.type != "cuda" or tokens.device.index != self.device_index:
+            tokens = tokens.to(torch.device("cuda", self.device_index))
+        return tokens
+
+    def _maybe_check(self):
+        if self.check_indices:
+            N.check(self._lib.frt2_check_error(self._h, self._cuda_stream()))
+
+    # ------------------------------------------------------------------ reference API
+    @torch.inference_mode()
+    def decode(self, tokens: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """RedCodecInfer.decode (reference model.py:307-324).  ``lengths`` (B,) int32 token counts is an
+        extension for ragged batches: item b equals a standalone decode of its first lengths[b] tokens."""
+        tokens = self._prep_tokens(tokens)
+        B, nq, L = tokens.shape
+        if L == 0 or B == 0:
+            return torch.zeros((B, 0), dtype=torch.float32, device=tokens.device)
+        with torch.cuda.device(self.device_index):
+            audio = torch.empty((B, self.cfg.samples_per_token * L), dtype=torch.float32, device=tokens.device)
+            lptr = None
+            if lengths is not None:
+                lengths = lengths.to(device=tokens.device, dtype=torch.int32).contiguous()
+                if lengths.numel() != B:
+                    raise ValueError("lengths must have B entries")
+                lptr = C.c_void_p(lengths.data_ptr())
+            sB, sQ, sL = tokens.stride()
+            N.check(self._lib.frt2_decode(self._h, C.c_void_p(tokens.data_ptr()), tokens.element_size(), sB, sQ, sL,
+                                          B, nq, L, lptr, C.c_void_p(audio.data_ptr()), audio.stride(0),
+                                          self._cuda_stream()))
+            self._maybe_check()
+        return audio
+
+    @torch.inference_mode()
+    def decode_one_token(self, token: torch.Tensor, cache_dict: Dict[str, object], last_token: bool
+                         ) -> Tuple[torch.Tensor, Dict[str, object]]:
+        """RedCodecInfer.decode_one_token (reference model.py:326-376).
+
+        ``cache_dict`` is ``{}`` on the first call.  The returned dict carries the opaque in-HBM state under
+        ``"frt2_state"`` (updated in place — re-using an *old* dict to fork a stream is not supported; use
+        ``export_cache`` / a reference-layout dict for that).  A dict holding the reference's five tensors
+        (hand-off from the reference implementation) is imported."""
+        token = self._prep_tokens(token)
+        B, nq, Lc = token.shape
+        if Lc < 1:
+            raise ValueError("decode_one_token needs at least one token")
+        with torch.cuda.device(self.device_index):
+            st = cache_dict.get(_STATE_KEY) if cache_dict else None
+            if st is None:
+                st = _NativeStream(self, B, self.stream_max_tokens)
+                if cache_dict and all(k in cache_dict for k in _REF_CACHE_KEYS):
+                    self._import_reference_cache(st, cache_dict)
+            if st.batch != B:
+                raise ValueError(f"stream was created for batch {st.batch}, got {B}")
+            if st.finished:
+                raise ValueError("stream already received its last token")
+            first = st.n_tokens == 0
+            n = self.cfg.samples_per_token * Lc - self.cfg.istft_pad * first + self.cfg.istft_pad * bool(last_token)
+            audio = torch.empty((B, n), dtype=torch.float32, device=token.device)
+            n_out = C.c_int(0)
+            sB, sQ, sL = token.stride()
+            N.check(self._lib.frt2_decode_chunk(self._h, st.ptr, C.c_void_p(token.data_ptr()), token.element_size(),
+                                                sB, sQ, sL, nq, Lc, int(bool(last_token)),
+                                                C.c_void_p(audio.data_ptr()), audio.stride(0), C.byref(n_out),
+                                                self._cuda_stream()))
+            assert n_out.value == n
+            self._maybe_check()
+            st.finished = bool(last_token)
+        return audio, {_STATE_KEY: st}
+
+    def export_cache(self, cache_dict: Dict[str, object]) -> Dict[str, torch.Tensor]:
+        """The state in the reference's own cache_dict layouts (model.py:346-375), for parity / hand-off."""
+        st: _NativeStream = cache_dict[_STATE_KEY]
+        c, B, E = self.cfg, st.batch, self.cfg.embed_dim
+        T = 8 * st.n_tokens
+        dev = torch.device("cuda", self.device_index)
+        out = {
+            "up_conv_cache": torch.empty((B, E, 3), device=dev),
+            "bb_conv_cache1": torch.empty((B, E, 6), device=dev),
+            "bb_conv_cache2": torch.empty((B, 8 * E, 2), device=dev),
+            "bb_kv_cache": torch.empty((B, c.num_layers, c.num_heads, T, 2 * c.head_dim), device=dev),
+            "is_cache": torch.empty((B, c.n_fft, 3), device=dev),
+        }
+        with torch.cuda.device(self.device_index):
+            N.check(self._lib.frt2_export_state(self._h, st.ptr, *[C.c_void_p(out[k].data_ptr()) for k in _REF_CACHE_KEYS],
+                                                self._cuda_stream()))
+        return out
+
+    def _import_reference_cache(self, st: _NativeStream, cache: Dict[str, torch.Tensor]):
+        dev = torch.device("cuda", self.device_index)
+        ts = [cache[k].to(device=dev, dtype=torch.float32).contiguous() for k in _REF_CACHE_KEYS]
+        T = ts[3].shape[3]
+        if T % 8:
+            raise ValueError("bb_kv_cache length must be a multiple of 8 frames (whole tokens)")
+        N.check(self._lib.frt2_import_state(self._h, st.ptr, T // 8, *[C.c_void_p(t.data_ptr()) for t in ts],
+                                            self._cuda_stream()))
+        torch.cuda.current_stream(self.device_index).synchronize()
+
+    def encode(self, *args, **kwargs):
+        """Out of scope for this path: delegated to the wrapped reference module."""
+        enc = self._encoder[0]
+        if enc is None:
+            raise NotImplementedError("encode() needs the reference RedCodecInfer (use RedCodecB200.from_reference)")
+        return enc.encode(*args, **kwargs)
+
+    # ------------------------------------------------------------------ parity hooks
+    def rvq_gather(self, tokens: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Raw codebook rows (B,L,nq,cd) and their index-ordered sum (B,L,cd), bit-exact with F.embedding."""
+        tokens = self._prep_tokens(tokens)
+        B, nq, L = tokens.shape
+        with torch.cuda.device(self.device_index):
+            rows = torch.empty((B, L, nq, self.cfg.codebook_dim), dtype=torch.float32, device=tokens.device)
+            s = torch.empty((B, L, self.cfg.codebook_dim), dtype=torch.float32, device=tokens.device)
+            sB, sQ, sL = tokens.stride()
+            N.check(self._lib.frt2_rvq_gather(self._h, C.c_void_p(tokens.data_ptr()), tokens.element_size(), sB, sQ, sL,
+                                              B, nq, L, C.c_void_p(rows.data_ptr()), C.c_void_p(s.data_ptr()),
+                                              self._cuda_stream()))
+            N.check(self._lib.frt2_check_error(self._h, self._cuda_stream()))
+        return rows, s
+
+    def set_debug(self, flags: int):
+        N.check(self._lib.frt2_set_debug(self._h, flags))
+
+    def get_tap(self, name: str, shape) -> torch.Tensor:
+        out = torch.empty(tuple(shape), dtype=torch.float32, device=torch.device("cuda", self.device_index))
+        n = C.c_int64(0)
+        N.check(self._lib.frt2_get_tap(self._h, name.encode(), C.c_void_p(out.data_ptr()), out.numel(), C.byref(n),
+                                       self._cuda_stream()))
+        if n.value != out.numel():
+            raise ValueError(f"tap {name} has {n.value} elements, expected {out.numel()}")
+        return out

@@ -122,11 +122,11 @@ C1 = dataclasses.replace(C0, rvq_dim=256, codebook_dim=256)
 # Small configs for fast CPU/GPU parity tests (same architecture, reduced widths).
 TINY = CodecConfig(rvq_dim=64, output_dim=128, num_quantizers=4, codebook_size=64, codebook_dim=32,
                    embed_dim=128, num_layers=2, num_heads=2)
-TINY_IDENT = dataclasses.replace(TINY, rvq_dim=32, codebook_dim=32)
+TINY_IDENT = dataclasses.replace(TINY, rvq_dim=64, codebook_dim=64)
 SMALL = CodecConfig(rvq_dim=128, output_dim=256, num_quantizers=8, codebook_size=256, codebook_dim=64,
                     embed_dim=256, num_layers=3, num_heads=4)
 
-MICRO = CodecConfig(rvq_dim=32, output_dim=64, num_quantizers=2, codebook_size=16, codebook_dim=16,
+MICRO = CodecConfig(rvq_dim=64, output_dim=64, num_quantizers=2, codebook_size=16, codebook_dim=16,
                     embed_dim=64, num_layers=1, num_heads=1)
 
 PRESETS = {"MICRO": MICRO, "C0": C0, "C1": C1, "TINY": TINY, "TINY_IDENT": TINY_IDENT, "SMALL": SMALL}

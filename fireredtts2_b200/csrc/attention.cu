@@ -1,0 +1,475 @@
+// K3 — attention of the causal Vocos backbone (reference whisper.py:49-118, mask utils.py:19-38).
+//
+//   offline : block-causal, key j visible to query i  iff  j <= (i | 7)   (8-frame blocks == one codec token);
+//             the dense (b,t,t) bool mask the reference builds on the host is replaced by this predicate.
+//   chunked : queries are the new frames at absolute positions q_pos0.., keys = KV state ++ chunk, no mask
+//             inside the chunk (reference forward_chunk passes attn_mask=None).
+//
+// attention_tc   : tcgen05 flash attention, hd = 64.  One CTA per (128-query tile, head, item), 64-key tiles.
+//                  S = Q K^T and P V on the tensor cores with fp32 accumulators in TMEM; softmax in fp32 with
+//                  one thread per query row (tcgen05.ld gives a thread its whole row: no shuffles);
+//                  P goes back through shared memory in the SWIZZLE_128B K-major layout; V is consumed
+//                  straight from its natural (key, d) layout as an MN-major operand.  Two CTAs per SM so one
+//                  CTA's exponentials overlap the other's MMAs.
+// attention_warp : CUDA-core kernel, one warp per 8-query block (all 8 rows of a block see the same keys).
+//                  Used for the short-query streaming step and as the on-device check for attention_tc.
+#include <math_constants.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace frt2 {
+
+// =====================================================================================================
+// attention_warp
+// =====================================================================================================
+namespace {
+
+template <int HD>
+__global__ void __launch_bounds__(128) attention_warp_kernel(AttnDesc a) {
+  constexpr int DPL = HD / 32;  // output dims per lane
+  __shared__ float sq[4][8][HD];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nblk = a.Tq >> 3;
+  const long long wid = static_cast<long long>(blockIdx.x) * 4 + warp;
+  if (wid >= static_cast<long long>(a.B) * a.H * nblk) return;
+  const int qb = static_cast<int>(wid % nblk);
+  const int h = static_cast<int>((wid / nblk) % a.H);
+  const int b = static_cast<int>(wid / (static_cast<long long>(nblk) * a.H));
+  const float scale_log2 = a.scale * 1.4426950408889634f;
+
+  const __half* qp = a.q + b * a.q_batch_pitch + static_cast<long long>(qb * 8) * a.q_row_pitch + h * HD;
+  for (int e = lane; e < 8 * HD; e += 32) {
+    const int r = e / HD, d = e - r * HD;
+    sq[warp][r][d] = __half2float(qp[r * a.q_row_pitch + d]) * scale_log2;
+  }
+  __syncwarp();
+
+  int kend = a.Tk - 1;
+  if (a.block_causal) kend = min(kend, (a.q_pos0 + qb * 8) | 7);
+  const __half* kp = a.k + b * a.kv_batch_pitch + h * HD;
+  const __half* vp = a.v + b * a.kv_batch_pitch + h * HD;
+
+  float m[8], l[8], acc[8][DPL];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    m[r] = -CUDART_INF_F;
+    l[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) acc[r][i] = 0.f;
+  }
+  for (int j0 = 0; j0 <= kend; j0 += 32) {
+    const int j = j0 + lane;
+    const bool valid = j <= kend;
+    float s[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s[r] = 0.f;
+    {
+      const uint4* krow = reinterpret_cast<const uint4*>(kp + static_cast<long long>(valid ? j : kend) * a.kv_row_pitch);
+#pragma unroll
+      for (int c = 0; c < HD / 8; ++c) {
+        const uint4 kv = __ldg(krow + c);
+        const __half2* k2 = reinterpret_cast<const __half2*>(&kv);
+        float kf[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(k2[i]);
+          kf[2 * i] = f.x;
+          kf[2 * i + 1] = f.y;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float4 q0 = *reinterpret_cast<const float4*>(&sq[warp][r][c * 8]);
+          const float4 q1 = *reinterpret_cast<const float4*>(&sq[warp][r][c * 8 + 4]);
+          s[r] += q0.x * kf[0] + q0.y * kf[1] + q0.z * kf[2] + q0.w * kf[3] + q1.x * kf[4] + q1.y * kf[5] +
+                  q1.z * kf[6] + q1.w * kf[7];
+        }
+      }
+    }
+    float p[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      float sv = valid ? s[r] : -CUDART_INF_F;
+      float mx = sv;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float m_new = fmaxf(m[r], mx);
+      const float alpha = exp2f(m[r] - m_new);
+      p[r] = valid ? exp2f(sv - m_new) : 0.f;
+      float ps = p[r];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+      l[r] = l[r] * alpha + ps;
+      m[r] = m_new;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) acc[r][i] *= alpha;
+    }
+    const int nk = min(32, kend - j0 + 1);
+    for (int jj = 0; jj < nk; ++jj) {
+      const __half* vrow = vp + static_cast<long long>(j0 + jj) * a.kv_row_pitch + lane * DPL;
+      float vf[DPL];
+      if (DPL == 2) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(vrow));
+        vf[0] = f.x;
+        vf[DPL - 1] = f.y;
+      } else {
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) vf[i] = __half2float(vrow[i]);
+      }
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float pj = __shfl_sync(0xffffffffu, p[r], jj);
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) acc[r][i] = fmaf(pj, vf[i], acc[r][i]);
+      }
+    }
+  }
+  __half* op = a.out + b * a.o_batch_pitch + static_cast<long long>(qb * 8) * a.o_row_pitch + h * HD + lane * DPL;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const float inv = 1.0f / l[r];
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) op[r * a.o_row_pitch + i] = __float2half_rn(acc[r][i] * inv);
+  }
+}
+
+}  // namespace
+
+int attention_warp(const AttnDesc& a, cudaStream_t stream) {
+  FRT2_REQUIRE(a.Tq % 8 == 0 && a.q_pos0 % 8 == 0, FRT2_ERR_BAD_ARG, "attention: Tq and q_pos0 must be multiples of 8");
+  FRT2_REQUIRE(a.kv_row_pitch % 8 == 0, FRT2_ERR_BAD_ARG, "attention: K/V row pitch must be a multiple of 8");
+  const long long warps = static_cast<long long>(a.B) * a.H * (a.Tq / 8);
+  if (warps == 0) return FRT2_OK;
+  const unsigned grid = static_cast<unsigned>((warps + 3) / 4);
+  switch (a.hd) {
+    case 32: attention_warp_kernel<32><<<grid, 128, 0, stream>>>(a); break;
+    case 64: attention_warp_kernel<64><<<grid, 128, 0, stream>>>(a); break;
+    case 128: attention_warp_kernel<128><<<grid, 128, 0, stream>>>(a); break;
+    default:
+      set_error("attention: head_dim must be 32, 64 or 128");
+      return FRT2_ERR_BAD_ARG;
+  }
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
+
+// =====================================================================================================
+// attention_tc  (hd = 64)
+// =====================================================================================================
+namespace {
+
+constexpr int AT_BQ = 128;      // query rows per CTA == TMEM lanes
+constexpr int AT_BK = 64;       // keys per tile
+constexpr int AT_HD = 64;
+constexpr int AT_STAGES = 3;
+constexpr int AT_THREADS = 192; // warps 0-3 softmax (thread == query row), warp 4 TMA, warp 5 MMA + TMEM alloc
+constexpr int AT_Q_BYTES = AT_BQ * AT_HD * 2;   // 16 KB
+constexpr int AT_KV_BYTES = AT_BK * AT_HD * 2;  // 8 KB
+constexpr int AT_P_BYTES = AT_BQ * AT_BK * 2;   // 16 KB
+constexpr int AT_TMEM_COLS = 128;               // S: cols [0,64), PV: cols [64,128)
+constexpr int AT_SMEM_BYTES = AT_Q_BYTES + AT_P_BYTES + 2 * AT_STAGES * AT_KV_BYTES + 1024 + 256;
+
+struct AttnKParams {
+  int Tq, Tk, q_pos0, block_causal, H;
+  float scale_log2;
+  __half* out;
+  long long o_row_pitch, o_batch_pitch;
+  int q_col0, k_col0, v_col0;  // column of head 0 inside the respective tensor map
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sP = sQ + AT_Q_BYTES;
+  uint8_t* sK = sP + AT_P_BYTES;
+  uint8_t* sV = sK + AT_STAGES * AT_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_STAGES * AT_KV_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + AT_STAGES;
+  uint64_t* v_full = k_empty + AT_STAGES;
+  uint64_t* v_empty = v_full + AT_STAGES;
+  uint64_t* s_full = v_empty + AT_STAGES;
+  uint64_t* s_empty = s_full + 1;
+  uint64_t* p_full = s_empty + 1;
+  uint64_t* pv_full = p_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = gridDim.x - 1 - blockIdx.x;  // heaviest (latest) query tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qt * AT_BQ;
+
+  // number of 64-key tiles this query tile needs
+  int kmax = p.Tk - 1;
+  if (p.block_causal) kmax = min(kmax, (p.q_pos0 + min(q0 + AT_BQ, p.Tq) - 1) | 7);
+  const int ntiles = kmax / AT_BK + 1;
+
+  if (warp == 4 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+  }
+  if (warp == 5 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < AT_STAGES; ++s) {
+      ptx::mbar_init(&k_full[s], 1);
+      ptx::mbar_init(&k_empty[s], 1);
+      ptx::mbar_init(&v_full[s], 1);
+      ptx::mbar_init(&v_empty[s], 1);
+    }
+    ptx::mbar_init(s_full, 1);
+    ptx::mbar_init(s_empty, 4);
+    ptx::mbar_init(p_full, 4);
+    ptx::mbar_init(pv_full, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 5) {
+    ptx::tmem_alloc(tmem_slot, AT_TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;
+  const uint32_t tmem_pv = tmem_base + AT_BK;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(q_full, AT_Q_BYTES);
+      ptx::tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + h * AT_HD, q0, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        ptx::mbar_wait(&k_empty[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&k_full[stage], AT_KV_BYTES);
+        ptx::tma_load_3d(sK + stage * AT_KV_BYTES, &tmK, &k_full[stage], p.k_col0 + h * AT_HD, j * AT_BK, b);
+        ptx::mbar_wait(&v_empty[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&v_full[stage], AT_KV_BYTES);
+        ptx::tma_load_3d(sV + stage * AT_KV_BYTES, &tmV, &v_full[stage], p.v_col0 + h * AT_HD, j * AT_BK, b);
+        if (++stage == AT_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_s = ptx::make_idesc_f16(AT_BQ, AT_BK, 0, 0);   // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(AT_BQ, AT_HD, 0, 1);  // P (K-major) x V (MN-major)
+      const uint64_t dq = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sQ));
+      const uint64_t dp = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sP));
+      ptx::mbar_wait(q_full, 0);
+      auto issue_pv = [&](int j) {
+        const int st = j % AT_STAGES;
+        ptx::mbar_wait(p_full, j & 1);
+        ptx::mbar_wait(&v_full[st], (j / AT_STAGES) & 1);
+        ptx::tc_fence_after();
+        const uint32_t vaddr = ptx::smem_u32(sV + st * AT_KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < AT_BK / 16; ++k) {
+          // 16 keys = 16 rows of 128 B: MN-major operand advances 2048 B per K step; P advances 32 B
+          const uint64_t dv = ptx::make_desc_mnmajor_sw128(vaddr + k * 2048, 1024, 1024);
+          ptx::mma_f16_ss(tmem_pv, dp + 2 * k, dv, idesc_pv, k != 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(pv_full);
+        ptx::mma_commit(&v_empty[st]);
+      };
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % AT_STAGES;
+        ptx::mbar_wait(&k_full[st], (j / AT_STAGES) & 1);
+        if (j > 0) ptx::mbar_wait(s_empty, (j - 1) & 1);
+        ptx::tc_fence_after();
+        const uint64_t dk = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sK + st * AT_KV_BYTES));
+#pragma unroll
+        for (int k = 0; k < AT_HD / 16; ++k) ptx::mma_f16_ss(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        ptx::mma_commit(s_full);
+        ptx::mma_commit(&k_empty[st]);
+        if (j > 0) issue_pv(j - 1);
+      }
+      issue_pv(ntiles - 1);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ softmax / output (thread == query row)
+    const int r = threadIdx.x;  // 0..127 == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const int qi = q0 + r;                 // row inside this item's query block
+    const int qabs = p.q_pos0 + qi;        // absolute position
+    int limit = p.Tk - 1;
+    if (p.block_causal) limit = min(limit, qabs | 7);
+    float m = -CUDART_INF_F, l = 0.f;
+    float o[AT_HD];
+#pragma unroll
+    for (int c = 0; c < AT_HD; ++c) o[c] = 0.f;
+    uint8_t* prow = sP + r * 128;
+    const int sw = r & 7;
+
+    for (int j = 0; j < ntiles; ++j) {
+      ptx::mbar_wait(s_full, j & 1);
+      ptx::tc_fence_after();
+      uint32_t sa[32], sb[32];
+      ptx::tmem_ld32(tmem_s + lane_off, sa);
+      ptx::tmem_ld32(tmem_s + lane_off + 32, sb);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(s_empty);
+
+      const int lim = limit - j * AT_BK;  // columns c <= lim are visible
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float v0 = __uint_as_float(sa[c]) * p.scale_log2;
+        float v1 = __uint_as_float(sb[c]) * p.scale_log2;
+        if (c > lim) v0 = -CUDART_INF_F;
+        if (c + 32 > lim) v1 = -CUDART_INF_F;
+        sa[c] = __float_as_uint(v0);
+        sb[c] = __float_as_uint(v1);
+        mx = fmaxf(mx, fmaxf(v0, v1));
+      }
+      const float m_new = fmaxf(m, mx);
+      // a row whose visible keys all lie in later tiles keeps m = -inf; use 0 as the exponent base then
+      const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
+      const float alpha = exp2f(m - m_use);
+      float rs = 0.f;
+      uint32_t ph[32];  // 64 probabilities packed as half2
+#pragma unroll
+      for (int c = 0; c < 32; c += 2) {
+        const float p0 = exp2f(__uint_as_float(sa[c]) - m_use);
+        const float p1 = exp2f(__uint_as_float(sa[c + 1]) - m_use);
+        const float p2 = exp2f(__uint_as_float(sb[c]) - m_use);
+        const float p3 = exp2f(__uint_as_float(sb[c + 1]) - m_use);
+        rs += (p0 + p1) + (p2 + p3);
+        ph[c >> 1] = pack_half2(p0, p1);
+        ph[16 + (c >> 1)] = pack_half2(p2, p3);
+      }
+      l = l * alpha + rs;
+      m = m_new;
+
+      if (j > 0) {
+        // fold in P_{j-1} V_{j-1} (computed relative to the previous max), then rescale to the new max
+        ptx::mbar_wait(pv_full, (j - 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint32_t t[32];
+          ptx::tmem_ld32(tmem_pv + lane_off + half * 32, t);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[half * 32 + c] = (o[half * 32 + c] + __uint_as_float(t[c])) * alpha;
+        }
+        ptx::tc_fence_before();
+      }
+      // P tile -> shared memory, K-major SWIZZLE_128B: row r at r*128 B, 16-byte chunk c at (c ^ (r & 7))
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 q;
+        q.x = ph[4 * c + 0]; q.y = ph[4 * c + 1]; q.z = ph[4 * c + 2]; q.w = ph[4 * c + 3];
+        *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = q;
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(p_full);
+    }
+    ptx::mbar_wait(pv_full, (ntiles - 1) & 1);
+    ptx::tc_fence_after();
+    const float inv = 1.0f / l;
+    __half* op = p.out + b * p.o_batch_pitch + static_cast<long long>(qi) * p.o_row_pitch + h * AT_HD;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t t[32];
+      ptx::tmem_ld32(tmem_pv + lane_off + half * 32, t);
+      ptx::tmem_ld_wait();
+      if (qi < p.Tq) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 q;
+          q.x = pack_half2((o[half * 32 + c + 0] + __uint_as_float(t[c + 0])) * inv,
+                           (o[half * 32 + c + 1] + __uint_as_float(t[c + 1])) * inv);
+          q.y = pack_half2((o[half * 32 + c + 2] + __uint_as_float(t[c + 2])) * inv,
+                           (o[half * 32 + c + 3] + __uint_as_float(t[c + 3])) * inv);
+          q.z = pack_half2((o[half * 32 + c + 4] + __uint_as_float(t[c + 4])) * inv,
+                           (o[half * 32 + c + 5] + __uint_as_float(t[c + 5])) * inv);
+          q.w = pack_half2((o[half * 32 + c + 6] + __uint_as_float(t[c + 6])) * inv,
+                           (o[half * 32 + c + 7] + __uint_as_float(t[c + 7])) * inv);
+          *reinterpret_cast<uint4*>(op + half * 32 + c) = q;
+        }
+      }
+    }
+    ptx::tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 5) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, AT_TMEM_COLS);
+  }
+}
+
+std::once_flag g_attn_once;
+int g_attn_status = FRT2_OK;
+
+}  // namespace
+
+int attention_tc_init() {
+  std::call_once(g_attn_once, [] {
+    g_attn_status = gemm_tc_init();
+    if (g_attn_status != FRT2_OK) return;
+    cudaError_t e =
+        cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error(std::string("cudaFuncSetAttribute(attention_tc_kernel): ") + cudaGetErrorString(e));
+      g_attn_status = FRT2_ERR_CUDA;
+    }
+  });
+  return g_attn_status;
+}
+
+int attention_tc(const AttnDesc& a, cudaStream_t stream) {
+  FRT2_TRY(attention_tc_init());
+  FRT2_REQUIRE(a.hd == AT_HD, FRT2_ERR_BAD_ARG, "attention_tc: head_dim must be 64");
+  FRT2_REQUIRE(a.Tq >= 1 && a.Tk >= 1, FRT2_ERR_BAD_ARG, "attention_tc: empty sequence");
+  FRT2_REQUIRE(a.q_row_pitch % 8 == 0 && a.kv_row_pitch % 8 == 0 && a.q_batch_pitch % 8 == 0 &&
+                   a.kv_batch_pitch % 8 == 0 && a.o_row_pitch % 8 == 0 && a.o_batch_pitch % 8 == 0,
+               FRT2_ERR_BAD_ARG, "attention_tc: pitches must be multiples of 8 elements");
+  CUtensorMap tmQ, tmK, tmV;
+  const uint64_t cols = static_cast<uint64_t>(a.H) * a.hd;
+  {
+    uint64_t dims[3] = {cols, static_cast<uint64_t>(a.Tq), static_cast<uint64_t>(a.B)};
+    uint64_t strides[2] = {static_cast<uint64_t>(a.q_row_pitch) * 2,
+                           static_cast<uint64_t>(a.B > 1 ? a.q_batch_pitch : a.q_row_pitch * a.Tq) * 2};
+    uint32_t box[3] = {AT_HD, AT_BQ, 1};
+    FRT2_TRY(tma_encode_fp16(&tmQ, a.q, 3, dims, strides, box));
+  }
+  {
+    uint64_t dims[3] = {cols, static_cast<uint64_t>(a.Tk), static_cast<uint64_t>(a.B)};
+    uint64_t strides[2] = {static_cast<uint64_t>(a.kv_row_pitch) * 2,
+                           static_cast<uint64_t>(a.B > 1 ? a.kv_batch_pitch : a.kv_row_pitch * a.Tk) * 2};
+    uint32_t box[3] = {AT_HD, AT_BK, 1};
+    FRT2_TRY(tma_encode_fp16(&tmK, a.k, 3, dims, strides, box));
+    FRT2_TRY(tma_encode_fp16(&tmV, a.v, 3, dims, strides, box));
+  }
+  AttnKParams p;
+  p.Tq = a.Tq;
+  p.Tk = a.Tk;
+  p.q_pos0 = a.q_pos0;
+  p.block_causal = a.block_causal;
+  p.H = a.H;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.out = a.out;
+  p.o_row_pitch = a.o_row_pitch;
+  p.o_batch_pitch = a.o_batch_pitch;
+  p.q_col0 = p.k_col0 = p.v_col0 = 0;
+  dim3 grid((a.Tq + AT_BQ - 1) / AT_BQ, a.H, a.B);
+  attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
+
+}  // namespace frt2

@@ -1,0 +1,138 @@
+// Shared declarations for the libfrt2_b200 kernels and host engine.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/frt2.h"
+
+namespace frt2 {
+
+// ---- thread-local last-error string (frt2_last_error) ----
+void set_error(const std::string& msg);
+const char* get_error();
+
+#define FRT2_CUDA_OK(expr)                                                                     \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::frt2::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                        ":" + std::to_string(__LINE__) + ")");                                 \
+      return FRT2_ERR_CUDA;                                                                    \
+    }                                                                                          \
+  } while (0)
+
+#define FRT2_TRY(expr)            \
+  do {                            \
+    int _s = (expr);              \
+    if (_s != FRT2_OK) return _s; \
+  } while (0)
+
+#define FRT2_REQUIRE(cond, code, msg)                  \
+  do {                                                 \
+    if (!(cond)) {                                     \
+      ::frt2::set_error(std::string(msg));             \
+      return (code);                                   \
+    }                                                  \
+  } while (0)
+
+// Device-side error word bits (always-on checks; read back by frt2_check_error / at sync points)
+enum : unsigned int { DEV_ERR_INDEX_OOR = 1u };
+
+// ---- device math helpers ----
+__device__ __forceinline__ float gelu_erf(float x) {  // exact erf GELU (reference F.gelu / nn.GELU default)
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---- GEMM (tcgen05) ----
+enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_POLAR = 2 };
+
+struct GemmDesc {
+  // A operand: fp16, logical (batches, rows_a, Kc) with element pitches; K of the GEMM = ntaps*Kc.
+  const __half* A;
+  int64_t a_row_pitch;    // elements between consecutive rows (time steps)
+  int64_t a_batch_pitch;  // elements between batch items
+  int rows_a;             // addressable rows per batch item (TMA zero-fills outside [0, rows_a))
+  int batches;
+  int Kc;                 // channels per tap (multiple of 64)
+  int ntaps;              // causal taps (1 = plain GEMM); weight K index = tap*Kc + c
+  int row_shift;          // A row for output row m, tap j is  m + j + row_shift
+  // B operand: fp16 weights (N, ntaps*Kc) row-major (K contiguous)
+  const __half* W;
+  int N;
+  // output: rows_out rows per batch item; element address = b*pitchX + m*ldX + n
+  int rows_out;
+  int64_t pitch32;        // batch pitch (elements) of out32 / resid
+  int64_t pitch16;        // batch pitch (elements) of out16
+  float alpha;            // acc *= alpha before bias
+  const float* bias;      // (N) or null
+  int act;                // GemmAct
+  const float* resid;     // fp32 (.., ld32) added after activation, may alias out32
+  float* out32;           // fp32 output or null
+  int64_t ld32;
+  __half* out16;          // fp16 output or null
+  int64_t ld16;
+};
+
+int gemm_tc(const GemmDesc& g, cudaStream_t stream);    // tcgen05 / TMEM / TMA path (product)
+int gemm_ref(const GemmDesc& g, cudaStream_t stream);   // plain SIMT fp32-accumulate check kernel (tests only)
+int gemm_tc_init();                                      // resolves cuTensorMapEncodeTiled, sets smem attrs
+
+// ---- attention ----
+struct AttnDesc {
+  const __half* q;   // (B, Tq, *) rows, head h at column h*hd
+  int64_t q_row_pitch, q_batch_pitch;
+  const __half* k;   // (B, Tk, *)
+  const __half* v;
+  int64_t kv_row_pitch, kv_batch_pitch;
+  __half* out;       // (B, Tq, H*hd)
+  int64_t o_row_pitch, o_batch_pitch;
+  int B, H, hd, Tq, Tk;
+  int q_pos0;        // absolute position of query row 0 (== Tk - Tq in streaming)
+  int block_causal;  // 1: key j visible iff j <= ((q_pos0+i) | 7); 0: all Tk keys visible
+  float scale;
+};
+int attention_warp(const AttnDesc& a, cudaStream_t stream);  // CUDA-core, one warp per 8-query block
+int attention_tc(const AttnDesc& a, cudaStream_t stream);    // tcgen05 flash attention (hd == 64)
+int attention_tc_init();
+
+// ---- misc kernels ----
+int rvq_gather_sum(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B, int nq, int L,
+                   const float* tables /*(nq,K,D)*/, int K, int D, float* sum32 /*(B*L,D) or null*/,
+                   __half* sum16 /*(B*L,D) or null*/, float* rows /*(B,L,nq,D) or null*/, unsigned int* err_word,
+                   cudaStream_t stream);
+int layer_norm_rows(const float* x, int64_t ldx, int rows, int C, const float* gamma, const float* beta, float eps,
+                    int apply_silu, __half* out16, int64_t ld16, cudaStream_t stream);
+// Overlap-add of windowed frames + window-square envelope normalisation + "same" trimming.
+struct OlaDesc {
+  const float* frames;   // (B, T, n_fft) windowed frames of this call
+  int64_t frames_batch_pitch;
+  const float* tail;     // (B, 3, n_fft) carried windowed frames (streaming) or null
+  const float* window;   // (n_fft)
+  const int* lengths;    // per-item length (offline var-len) or null; valid frames = lengths[b]*len_mul
+  int len_mul;
+  float* audio;          // (B, *)
+  int64_t audio_pitch;
+  int B, T, n_fft, hop;
+  int first, last;       // streaming flags; offline == first && last
+};
+int istft_overlap_add(const OlaDesc& d, cudaStream_t stream);
+int istft_update_tail(const float* frames, int64_t frames_batch_pitch, float* tail, int B, int T, int n_fft,
+                      cudaStream_t stream);
+int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_per_batch, int C, const float* gamma,
+                            const float* beta, float eps, int apply_silu, __half* out16, int64_t ld16,
+                            int64_t out_batch_pitch, cudaStream_t stream);
+int tma_encode_fp16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box);
+int num_sms();
+
+}  // namespace frt2

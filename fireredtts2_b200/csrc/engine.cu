@@ -1,0 +1,1086 @@
+// Host engine of libfrt2_b200: weight import / one-time repack, workspace, the offline decode pipeline
+// (reference RedCodecInfer.decode, codec/model.py:307-324) and the in-HBM streaming state
+// (reference RedCodecInfer.decode_one_token + cache_dict, codec/model.py:326-376).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace frt2 {
+
+// ------------------------------------------------------------------ error string
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* get_error() { return g_err.c_str(); }
+
+namespace {
+
+constexpr int DBG_TAPS = 1;       // record intermediates (frt2_get_tap)
+constexpr int DBG_GEMM_REF = 2;   // route every GEMM through the SIMT check kernel (tests only)
+constexpr int DBG_ATTN_WARP = 4;  // route attention through the warp kernel (tests only)
+
+struct HostTensor {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : shape) n *= d;
+    return n;
+  }
+};
+
+struct ResW {
+  float *ln1_g, *ln1_b, *b1, *ln2_g, *ln2_b, *b2;
+  __half *w1, *w2;  // (E, 3E) tap-major
+};
+struct LayerW {
+  float *ln1_g, *ln1_b, *b_qkv, *b_o, *ln2_g, *ln2_b, *b_fc1, *b_fc2;
+  __half *w_qkv, *w_o, *w_fc1, *w_fc2;
+};
+
+// small elementwise helpers -------------------------------------------------------------------------
+__global__ void half_to_float_kernel(const __half* __restrict__ src, long long ld, long long rows, int cols,
+                                     float* __restrict__ dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  const int c = static_cast<int>(i - r * cols);
+  dst[i] = __half2float(src[r * ld + c]);
+}
+
+struct ShiftEntry {
+  __half* p;
+  int hist;
+  int rows;  // chunk rows written by this call
+  long long batch_pitch;
+};
+struct ShiftTable {
+  ShiftEntry e[16];
+  int n;
+};
+// move the last `hist` rows of [hist | chunk] to the head of each streaming conv buffer (the new history)
+__global__ void shift_history_kernel(ShiftTable t, int E, int B) {
+  const int ei = blockIdx.y;
+  const ShiftEntry en = t.e[ei];
+  const int rows = en.rows;
+  const long long total = static_cast<long long>(B) * en.hist * E;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % E);
+    const int r = static_cast<int>((i / E) % en.hist);
+    const int b = static_cast<int>(i / (static_cast<long long>(E) * en.hist));
+    __half* base = en.p + b * en.batch_pitch;
+    // rows >= hist so source (r + rows) never overlaps a not-yet-read destination row of another thread
+    base[static_cast<long long>(r) * E + c] = base[static_cast<long long>(r + rows) * E + c];
+  }
+}
+
+// state export / import in the reference's cache layouts ----------------------------------------------
+// src (B, rows, C) fp16 time-major with pitches  ->  dst (B, C_total, rows) fp32 channel-major at channel offset
+__global__ void export_tm_to_cm_kernel(const __half* src, long long batch_pitch, int rows, int C, float* dst,
+                                       int C_total, int c_off, int t_total, int t_off, int B) {
+  const long long n = static_cast<long long>(B) * rows * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int r = static_cast<int>((i / C) % rows);
+    const int b = static_cast<int>(i / (static_cast<long long>(C) * rows));
+    dst[(static_cast<long long>(b) * C_total + c_off + c) * t_total + t_off + r] =
+        __half2float(src[b * batch_pitch + static_cast<long long>(r) * C + c]);
+  }
+}
+__global__ void import_cm_to_tm_kernel(const float* src, int C_total, int c_off, int t_total, int t_off, __half* dst,
+                                       long long batch_pitch, int rows, int C, int B) {
+  const long long n = static_cast<long long>(B) * rows * C;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % C);
+    const int r = static_cast<int>((i / C) % rows);
+    const int b = static_cast<int>(i / (static_cast<long long>(C) * rows));
+    dst[b * batch_pitch + static_cast<long long>(r) * C + c] =
+        __float2half_rn(src[(static_cast<long long>(b) * C_total + c_off + c) * t_total + t_off + r]);
+  }
+}
+// kv state (B, Tmax, 2E) fp16 [k | v]  <->  reference (B, nl, H, T, 2*hd) fp32 slice of layer `layer`
+__global__ void export_kv_kernel(const __half* kv, long long batch_pitch, int T, int E, int H, int hd, float* dst,
+                                 int nl, int layer, int B) {
+  const long long n = static_cast<long long>(B) * T * 2 * E;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % (2 * E));
+    const int t = static_cast<int>((i / (2 * E)) % T);
+    const int b = static_cast<int>(i / (static_cast<long long>(2 * E) * T));
+    const int isv = c >= E;
+    const int ch = isv ? c - E : c;
+    const int h = ch / hd, d = ch - h * hd;
+    dst[((((static_cast<long long>(b) * nl + layer) * H + h) * T + t) * 2 + isv) * hd + d] =
+        __half2float(kv[b * batch_pitch + static_cast<long long>(t) * 2 * E + c]);
+  }
+}
+__global__ void import_kv_kernel(const float* src, int nl, int layer, __half* kv, long long batch_pitch, int T, int E,
+                                 int H, int hd, int B) {
+  const long long n = static_cast<long long>(B) * T * 2 * E;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % (2 * E));
+    const int t = static_cast<int>((i / (2 * E)) % T);
+    const int b = static_cast<int>(i / (static_cast<long long>(2 * E) * T));
+    const int isv = c >= E;
+    const int ch = isv ? c - E : c;
+    const int h = ch / hd, d = ch - h * hd;
+    kv[b * batch_pitch + static_cast<long long>(t) * 2 * E + c] =
+        __float2half_rn(src[((((static_cast<long long>(b) * nl + layer) * H + h) * T + t) * 2 + isv) * hd + d]);
+  }
+}
+// is_cache (B, n_fft, 3) fp32 channel-major <-> tail (B, 3, n_fft) fp32
+__global__ void transpose_tail_kernel(const float* src, float* dst, int B, int n_fft, int to_reference) {
+  const int n = B * 3 * n_fft;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = i % n_fft, t = (i / n_fft) % 3, b = i / (3 * n_fft);
+  const long long tm = (static_cast<long long>(b) * 3 + t) * n_fft + k;
+  const long long cm = (static_cast<long long>(b) * n_fft + k) * 3 + t;
+  if (to_reference) dst[cm] = src[tm];
+  else dst[tm] = src[cm];
+}
+
+inline unsigned grid_for(long long n, int block = 256, unsigned cap = 148 * 16) {
+  long long g = (n + block - 1) / block;
+  return static_cast<unsigned>(std::max<long long>(1, std::min<long long>(g, cap)));
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+}  // namespace
+
+// =====================================================================================================
+struct Stream;
+
+struct Handle {
+  frt2_config cfg{};
+  int device = 0;
+  bool finalized = false;
+  int debug = 0;
+  std::map<std::string, HostTensor> raw;
+  std::vector<void*> owned;  // device allocations of packed weights
+  std::mutex mu;
+
+  // derived
+  int E = 0, H = 0, hd = 0, nl = 0, nq = 0, K = 0, cd = 0, rd = 0, hop = 0, n_fft = 0, n_bins = 0, spec_ld = 0;
+  bool has_out_project = false, has_output_proj = false;
+
+  // packed weights
+  float* codebooks = nullptr;  // (nq,K,cd) raw
+  float* tables = nullptr;     // (nq,K,rd) folded with out_project (== codebooks when Identity)
+  __half* w_outproj = nullptr; float* b_outproj = nullptr;
+  __half* w_up_in = nullptr;   float* b_up_in = nullptr;
+  __half* w_up_conv = nullptr;
+  __half* w_us0 = nullptr;     float* b_us0 = nullptr;
+  __half* w_us2 = nullptr;     float* b_us2 = nullptr;
+  __half* w_inproj = nullptr;  float* b_inproj = nullptr;
+  ResW res[4]{};
+  std::vector<LayerW> layers;
+  float *fn_g = nullptr, *fn_b = nullptr;
+  __half* w_head = nullptr;    float* b_head = nullptr;
+  __half* w_idft = nullptr;
+  float* window = nullptr;
+  unsigned int* err_word = nullptr;
+
+  // workspace arena (grow-only)
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
+  std::map<std::string, std::pair<float*, int64_t>> taps;
+  int tap_B = 0, tap_L = 0;
+
+  ~Handle() {
+    cudaSetDevice(device);
+    for (void* p : owned) cudaFree(p);
+    if (ws) cudaFree(ws);
+    for (auto& kv : taps) cudaFree(kv.second.first);
+  }
+
+  int dev_alloc(void** p, size_t bytes) {
+    FRT2_CUDA_OK(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+    owned.push_back(*p);
+    return FRT2_OK;
+  }
+  int upload_f32(const std::vector<float>& v, float** out) {
+    FRT2_TRY(dev_alloc(reinterpret_cast<void**>(out), v.size() * 4));
+    FRT2_CUDA_OK(cudaMemcpy(*out, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+    return FRT2_OK;
+  }
+  int upload_f16(const std::vector<float>& v, __half** out) {
+    std::vector<__half> hbuf(v.size());
+    const long long n = static_cast<long long>(v.size());
+#pragma omp parallel for schedule(static)
+    for (long long i = 0; i < n; ++i) hbuf[i] = __float2half_rn(v[i]);
+    FRT2_TRY(dev_alloc(reinterpret_cast<void**>(out), hbuf.size() * 2));
+    FRT2_CUDA_OK(cudaMemcpy(*out, hbuf.data(), hbuf.size() * 2, cudaMemcpyHostToDevice));
+    return FRT2_OK;
+  }
+
+  const HostTensor* find(const std::string& key) const {
+    auto it = raw.find(key);
+    return it == raw.end() ? nullptr : &it->second;
+  }
+  int need(const std::string& key, const HostTensor** out, std::initializer_list<int64_t> shape) {
+    const HostTensor* t = find(key);
+    if (t == nullptr) {
+      set_error("missing tensor: " + key);
+      return FRT2_ERR_MISSING_TENSOR;
+    }
+    std::vector<int64_t> want(shape);
+    if (t->shape != want) {
+      std::string got, exp;
+      for (auto d : t->shape) got += std::to_string(d) + ",";
+      for (auto d : want) exp += std::to_string(d) + ",";
+      set_error("tensor " + key + " has shape (" + got + ") expected (" + exp + ")");
+      return FRT2_ERR_BAD_ARG;
+    }
+    *out = t;
+    return FRT2_OK;
+  }
+
+  int finalize();
+  int ensure_ws(size_t bytes);
+  int run_gemm(const GemmDesc& g, cudaStream_t st) { return (debug & DBG_GEMM_REF) ? gemm_ref(g, st) : gemm_tc(g, st); }
+  int run_attn(const AttnDesc& a, cudaStream_t st) {
+    if ((debug & DBG_ATTN_WARP) || a.hd != 64 || a.Tq < 32) return attention_warp(a, st);
+    return attention_tc(a, st);
+  }
+  int tap_f32(const char* name, const float* src, int64_t n, cudaStream_t st);
+  int tap_f16(const char* name, const __half* src, int64_t ld, int64_t rows, int cols, cudaStream_t st);
+
+  int pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B, int nq_in, int L,
+               const int32_t* lengths, float* audio, int64_t audio_pitch, Stream* s, int last, cudaStream_t st);
+};
+
+struct Stream {
+  Handle* h = nullptr;
+  int B = 0, max_tokens = 0, n_tokens = 0, chunk_cap = 0;
+  // conv input buffers [hist | chunk], fp16: x50 (hist 1, 4 rows/token), a (hist 2), in_proj in (hist 6), 8 x res (hist 2)
+  __half* conv[11]{};
+  int conv_hist[11] = {1, 2, 6, 2, 2, 2, 2, 2, 2, 2, 2};
+  int conv_rpt[11] = {4, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8};  // rows per token
+  std::vector<__half*> kv;  // per layer (B, Tmax, 2E)
+  float* tail = nullptr;    // (B, 3, n_fft)
+
+  int64_t conv_pitch(int i) const { return static_cast<int64_t>(conv_hist[i] + conv_rpt[i] * chunk_cap) * h->E; }
+  int64_t kv_pitch() const { return static_cast<int64_t>(max_tokens) * 8 * 2 * h->E; }
+  void free_conv() {
+    for (auto& p : conv) {
+      if (p) cudaFree(p);
+      p = nullptr;
+    }
+  }
+  ~Stream() {
+    cudaSetDevice(h->device);
+    free_conv();
+    for (auto p : kv) cudaFree(p);
+    if (tail) cudaFree(tail);
+  }
+  int ensure_chunk_cap(int Lc, cudaStream_t st);
+  int reset();
+};
+
+// ------------------------------------------------------------------ weight repack (host, once)
+static std::vector<float> weight_norm_host(const HostTensor& g, const HostTensor& v) {
+  // W[o] = g[o] * v[o] / ||v[o]||  (torch weight_norm dim=0, reference rvq.py:8-13)
+  const int64_t out = v.shape[0];
+  const int64_t inner = v.numel() / out;
+  std::vector<float> W(v.data.size());
+#pragma omp parallel for schedule(static)
+  for (long long o = 0; o < out; ++o) {
+    double ss = 0.0;
+    for (int64_t i = 0; i < inner; ++i) ss += static_cast<double>(v.data[o * inner + i]) * v.data[o * inner + i];
+    const float scale = g.data[o] / static_cast<float>(std::sqrt(ss));
+    for (int64_t i = 0; i < inner; ++i) W[o * inner + i] = v.data[o * inner + i] * scale;
+  }
+  return W;
+}
+
+int Handle::finalize() {
+  FRT2_CUDA_OK(cudaSetDevice(device));
+  FRT2_TRY(gemm_tc_init());
+  const HostTensor* t = nullptr;
+  const std::string RVQ = "rvq.", UP = "upsample.", AD = "acoustic_decoder.", BB = "acoustic_decoder.backbone.";
+
+  // ---- RVQ: raw codebooks + tables folded with the weight-normed out_project (+ bias) ----
+  {
+    std::vector<float> cbs(static_cast<size_t>(nq) * K * cd);
+    std::vector<float> tab;
+    if (has_out_project) tab.resize(static_cast<size_t>(nq) * K * rd);
+    for (int i = 0; i < nq; ++i) {
+      const std::string q = RVQ + "quantizers." + std::to_string(i);
+      FRT2_TRY(need(q + ".codebook", &t, {K, cd}));
+      std::memcpy(&cbs[static_cast<size_t>(i) * K * cd], t->data.data(), static_cast<size_t>(K) * cd * 4);
+      if (has_out_project) {
+        const HostTensor *g, *v, *bq;
+        FRT2_TRY(need(q + ".out_project.parametrizations.weight.original0", &g, {rd, 1, 1}));
+        FRT2_TRY(need(q + ".out_project.parametrizations.weight.original1", &v, {rd, cd, 1}));
+        FRT2_TRY(need(q + ".out_project.bias", &bq, {rd}));
+        const std::vector<float> W = weight_norm_host(*g, *v);  // (rd, cd)
+        const float* cb = t->data.data();
+        float* dst = &tab[static_cast<size_t>(i) * K * rd];
+#pragma omp parallel for schedule(static)
+        for (long long k = 0; k < K; ++k) {
+          for (int o = 0; o < rd; ++o) {
+            float acc = 0.f;
+            const float* wr = &W[static_cast<size_t>(o) * cd];
+            const float* cr = &cb[static_cast<size_t>(k) * cd];
+            for (int c = 0; c < cd; ++c) acc += cr[c] * wr[c];
+            dst[static_cast<size_t>(k) * rd + o] = acc + bq->data[o];
+          }
+        }
+      }
+    }
+    FRT2_TRY(upload_f32(cbs, &codebooks));
+    if (has_out_project) FRT2_TRY(upload_f32(tab, &tables));
+    else tables = codebooks;
+  }
+  if (has_output_proj) {
+    const HostTensor *g, *v, *bo;
+    FRT2_TRY(need(RVQ + "output_proj.parametrizations.weight.original0", &g, {E, 1, 1}));
+    FRT2_TRY(need(RVQ + "output_proj.parametrizations.weight.original1", &v, {E, rd, 1}));
+    FRT2_TRY(need(RVQ + "output_proj.bias", &bo, {E}));
+    FRT2_TRY(upload_f16(weight_norm_host(*g, *v), &w_outproj));
+    FRT2_TRY(upload_f32(bo->data, &b_outproj));
+  }
+  // ---- UpConv ----
+  {
+    const HostTensor *w, *b, *wc;
+    FRT2_TRY(need(UP + "in_proj.weight", &w, {4 * E, E}));
+    FRT2_TRY(need(UP + "in_proj.bias", &b, {4 * E}));
+    FRT2_TRY(need(UP + "up_conv.weight", &wc, {4 * E, E, 4}));
+    FRT2_TRY(upload_f16(w->data, &w_up_in));
+    FRT2_TRY(upload_f32(b->data, &b_up_in));
+    // ConvTranspose1d k = s = 4 (in=4E, out=E, k): x50[4t+k, o] = sum_c h[c] Wup[c,o,k]  ->  W[(k*E+o), c]
+    std::vector<float> W(static_cast<size_t>(4) * E * 4 * E);
+    const int64_t Cin = 4 * E;
+#pragma omp parallel for schedule(static)
+    for (long long n = 0; n < 4LL * E; ++n) {
+      const int k = static_cast<int>(n / E), o = static_cast<int>(n % E);
+      for (int64_t c = 0; c < Cin; ++c) W[n * Cin + c] = wc->data[(c * E + o) * 4 + k];
+    }
+    FRT2_TRY(upload_f16(W, &w_up_conv));
+  }
+  // ---- upsample_conv (two ConvTranspose1d k=3) ----
+  {
+    const HostTensor *w0, *b0, *w2, *b2;
+    FRT2_TRY(need(AD + "upsample_conv.0.weight", &w0, {E, E, 3}));
+    FRT2_TRY(need(AD + "upsample_conv.0.bias", &b0, {E}));
+    FRT2_TRY(need(AD + "upsample_conv.2.weight", &w2, {E, E, 3}));
+    FRT2_TRY(need(AD + "upsample_conv.2.bias", &b2, {E}));
+    // stride-2 polyphase (reference decoder.py:572-579): even y[2t] = W[:,:,0]^T x[t] + W[:,:,2]^T x[t-1],
+    // odd y[2t+1] = W[:,:,1]^T x[t].  GEMM over taps (x[t-1], x[t]) with N = 2E: cols [0,E) even, [E,2E) odd.
+    std::vector<float> W(static_cast<size_t>(2) * E * 2 * E, 0.f);
+#pragma omp parallel for schedule(static)
+    for (long long n = 0; n < 2LL * E; ++n) {
+      const int o = static_cast<int>(n % E);
+      const bool odd = n >= E;
+      float* row = &W[static_cast<size_t>(n) * 2 * E];
+      for (int c = 0; c < E; ++c) {
+        row[c] = odd ? 0.f : w0->data[(static_cast<size_t>(c) * E + o) * 3 + 2];          // tap x[t-1]
+        row[E + c] = w0->data[(static_cast<size_t>(c) * E + o) * 3 + (odd ? 1 : 0)];      // tap x[t]
+      }
+    }
+    FRT2_TRY(upload_f16(W, &w_us0));
+    std::vector<float> bb(2 * E);
+    for (int i = 0; i < 2 * E; ++i) bb[i] = b0->data[i % E];
+    FRT2_TRY(upload_f32(bb, &b_us0));
+    // stride-1 ConvTranspose == causal conv with flipped taps: v[j] = sum_k W[:,:,k]^T a[j-k]; tap tau <-> a[j-2+tau]
+    std::vector<float> W2(static_cast<size_t>(E) * 3 * E);
+#pragma omp parallel for schedule(static)
+    for (long long n = 0; n < E; ++n)
+      for (int tau = 0; tau < 3; ++tau)
+        for (int c = 0; c < E; ++c)
+          W2[(static_cast<size_t>(n) * 3 + tau) * E + c] = w2->data[(static_cast<size_t>(c) * E + n) * 3 + (2 - tau)];
+    FRT2_TRY(upload_f16(W2, &w_us2));
+    FRT2_TRY(upload_f32(b2->data, &b_us2));
+  }
+  // causal Conv1d (out,in,k) -> (out, k*in) tap-major: tap tau <-> x[t-(k-1)+tau]  (reference decoder.py:88-91)
+  auto pack_conv = [&](const std::string& key, int k, __half** w, float** b) -> int {
+    const HostTensor *wt, *bt;
+    FRT2_TRY(need(key + ".weight", &wt, {E, E, k}));
+    FRT2_TRY(need(key + ".bias", &bt, {E}));
+    std::vector<float> W(static_cast<size_t>(E) * k * E);
+#pragma omp parallel for schedule(static)
+    for (long long n = 0; n < E; ++n)
+      for (int tau = 0; tau < k; ++tau)
+        for (int c = 0; c < E; ++c)
+          W[(static_cast<size_t>(n) * k + tau) * E + c] = wt->data[(static_cast<size_t>(n) * E + c) * k + tau];
+    FRT2_TRY(upload_f16(W, w));
+    FRT2_TRY(upload_f32(bt->data, b));
+    return FRT2_OK;
+  };
+  auto up_vec = [&](const std::string& key, int n, float** out) -> int {
+    const HostTensor* v;
+    FRT2_TRY(need(key, &v, {n}));
+    return upload_f32(v->data, out);
+  };
+  FRT2_TRY(pack_conv(BB + "in_proj", 7, &w_inproj, &b_inproj));
+  for (int r = 0; r < 4; ++r) {
+    const std::string p = BB + (r < 2 ? "prior_net." : "post_net.") + std::to_string(r % 2) + ".";
+    FRT2_TRY(up_vec(p + "block1.1.weight", E, &res[r].ln1_g));
+    FRT2_TRY(up_vec(p + "block1.1.bias", E, &res[r].ln1_b));
+    FRT2_TRY(pack_conv(p + "block1.4", 3, &res[r].w1, &res[r].b1));
+    FRT2_TRY(up_vec(p + "block2.1.weight", E, &res[r].ln2_g));
+    FRT2_TRY(up_vec(p + "block2.1.bias", E, &res[r].ln2_b));
+    FRT2_TRY(pack_conv(p + "block2.5", 3, &res[r].w2, &res[r].b2));
+  }
+  layers.resize(nl);
+  for (int i = 0; i < nl; ++i) {
+    const std::string p = BB + "transformers." + std::to_string(i) + ".";
+    LayerW& lw = layers[i];
+    const HostTensor *wq, *bq, *wk, *wv, *bv, *wo, *w1, *w2;
+    FRT2_TRY(need(p + "self_attn.q_proj.weight", &wq, {E, E}));
+    FRT2_TRY(need(p + "self_attn.q_proj.bias", &bq, {E}));
+    FRT2_TRY(need(p + "self_attn.k_proj.weight", &wk, {E, E}));
+    FRT2_TRY(need(p + "self_attn.v_proj.weight", &wv, {E, E}));
+    FRT2_TRY(need(p + "self_attn.v_proj.bias", &bv, {E}));
+    FRT2_TRY(need(p + "self_attn.out_proj.weight", &wo, {E, E}));
+    FRT2_TRY(need(p + "fc1.weight", &w1, {4 * E, E}));
+    FRT2_TRY(need(p + "fc2.weight", &w2, {E, 4 * E}));
+    std::vector<float> wqkv(static_cast<size_t>(3) * E * E), bqkv(3 * E, 0.f);  // k_proj has no bias (whisper.py:37)
+    std::memcpy(&wqkv[0], wq->data.data(), static_cast<size_t>(E) * E * 4);
+    std::memcpy(&wqkv[static_cast<size_t>(E) * E], wk->data.data(), static_cast<size_t>(E) * E * 4);
+    std::memcpy(&wqkv[static_cast<size_t>(2) * E * E], wv->data.data(), static_cast<size_t>(E) * E * 4);
+    std::memcpy(&bqkv[0], bq->data.data(), E * 4);
+    std::memcpy(&bqkv[2 * E], bv->data.data(), E * 4);
+    FRT2_TRY(upload_f16(wqkv, &lw.w_qkv));
+    FRT2_TRY(upload_f32(bqkv, &lw.b_qkv));
+    FRT2_TRY(upload_f16(wo->data, &lw.w_o));
+    FRT2_TRY(up_vec(p + "self_attn.out_proj.bias", E, &lw.b_o));
+    FRT2_TRY(upload_f16(w1->data, &lw.w_fc1));
+    FRT2_TRY(up_vec(p + "fc1.bias", 4 * E, &lw.b_fc1));
+    FRT2_TRY(upload_f16(w2->data, &lw.w_fc2));
+    FRT2_TRY(up_vec(p + "fc2.bias", E, &lw.b_fc2));
+    FRT2_TRY(up_vec(p + "self_attn_layer_norm.weight", E, &lw.ln1_g));
+    FRT2_TRY(up_vec(p + "self_attn_layer_norm.bias", E, &lw.ln1_b));
+    FRT2_TRY(up_vec(p + "final_layer_norm.weight", E, &lw.ln2_g));
+    FRT2_TRY(up_vec(p + "final_layer_norm.bias", E, &lw.ln2_b));
+  }
+  FRT2_TRY(up_vec(BB + "final_norm.weight", E, &fn_g));
+  FRT2_TRY(up_vec(BB + "final_norm.bias", E, &fn_b));
+  // ---- iSTFT head: Linear(E -> 2*n_bins) with rows interleaved (log-mag f, phase f) so the GEMM epilogue
+  //      sees both halves of a bin in one thread (reference decoder.py:503-518) ----
+  {
+    const HostTensor *w, *b, *win;
+    FRT2_TRY(need(AD + "isift.out.weight", &w, {2 * n_bins, E}));
+    FRT2_TRY(need(AD + "isift.out.bias", &b, {2 * n_bins}));
+    FRT2_TRY(need(AD + "isift.istft.window", &win, {n_fft}));
+    std::vector<float> W(static_cast<size_t>(2) * n_bins * E), bb(2 * n_bins);
+    for (int f = 0; f < n_bins; ++f) {
+      std::memcpy(&W[static_cast<size_t>(2 * f) * E], &w->data[static_cast<size_t>(f) * E], E * 4);
+      std::memcpy(&W[static_cast<size_t>(2 * f + 1) * E], &w->data[static_cast<size_t>(n_bins + f) * E], E * 4);
+      bb[2 * f] = b->data[f];
+      bb[2 * f + 1] = b->data[n_bins + f];
+    }
+    FRT2_TRY(upload_f16(W, &w_head));
+    FRT2_TRY(upload_f32(bb, &b_head));
+    FRT2_TRY(upload_f32(win->data, &window));
+    // windowed inverse real DFT as a (n_fft x spec_ld) matrix over interleaved (Re, Im) columns:
+    // fr[n] = (1/N) [Re S0 + (-1)^n Re S_{N/2} + 2 sum_f (Re S_f cos(2 pi f n/N) - Im S_f sin(2 pi f n/N))]
+    // (irfft, norm="backward"; Im of DC / Nyquist ignored) times window[n] (reference decoder.py:380-381).
+    // The 1/N is applied as the GEMM's fp32 alpha so the fp16 basis entries stay in [-2, 2].
+    std::vector<float> Bm(static_cast<size_t>(n_fft) * spec_ld, 0.f);
+#pragma omp parallel for schedule(static)
+    for (long long n = 0; n < n_fft; ++n) {
+      const double wn = win->data[n];
+      for (int f = 0; f < n_bins; ++f) {
+        const bool edge = (f == 0) || (f == n_fft / 2);
+        const double cf = edge ? 1.0 : 2.0;
+        const double ang = 2.0 * M_PI * static_cast<double>((static_cast<long long>(f) * n) % n_fft) / n_fft;
+        Bm[n * spec_ld + 2 * f] = static_cast<float>(wn * cf * std::cos(ang));
+        Bm[n * spec_ld + 2 * f + 1] = edge ? 0.f : static_cast<float>(-wn * cf * std::sin(ang));
+      }
+    }
+    FRT2_TRY(upload_f16(Bm, &w_idft));
+  }
+  FRT2_TRY(dev_alloc(reinterpret_cast<void**>(&err_word), 4));
+  FRT2_CUDA_OK(cudaMemset(err_word, 0, 4));
+  raw.clear();
+  finalized = true;
+  return FRT2_OK;
+}
+
+int Handle::ensure_ws(size_t bytes) {
+  if (bytes <= ws_bytes) return FRT2_OK;
+  if (ws) {
+    FRT2_CUDA_OK(cudaDeviceSynchronize());
+    FRT2_CUDA_OK(cudaFree(ws));
+    ws = nullptr;
+    ws_bytes = 0;
+  }
+  FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ws), bytes));
+  ws_bytes = bytes;
+  return FRT2_OK;
+}
+
+int Handle::tap_f32(const char* name, const float* src, int64_t n, cudaStream_t st) {
+  if (!(debug & DBG_TAPS)) return FRT2_OK;
+  auto& e = taps[name];
+  if (e.second < n) {
+    if (e.first) cudaFree(e.first);
+    FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e.first), n * 4));
+  }
+  e.second = n;
+  FRT2_CUDA_OK(cudaMemcpyAsync(e.first, src, n * 4, cudaMemcpyDeviceToDevice, st));
+  return FRT2_OK;
+}
+int Handle::tap_f16(const char* name, const __half* src, int64_t ld, int64_t rows, int cols, cudaStream_t st) {
+  if (!(debug & DBG_TAPS)) return FRT2_OK;
+  const int64_t n = rows * cols;
+  auto& e = taps[name];
+  if (e.second < n) {
+    if (e.first) cudaFree(e.first);
+    FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&e.first), n * 4));
+  }
+  e.second = n;
+  half_to_float_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(src, ld, rows, cols, e.first);
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
+
+// ------------------------------------------------------------------ the decode pipeline
+// One function serves both entry points.  Offline (s == nullptr): conv inputs have no history rows and the
+// causal left padding comes from TMA out-of-bounds zero fill; attention is block-causal over the whole item.
+// Streaming: every conv input buffer is [history | chunk] owned by the stream, K/V are appended to the HBM
+// state and attention runs unmasked over state ++ chunk.
+int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B, int nq_in, int L,
+                     const int32_t* lengths, float* audio, int64_t audio_pitch, Stream* s, int last, cudaStream_t st) {
+  const int64_t R = static_cast<int64_t>(B) * L;  // tokens
+  const int T50 = 4 * L, T = 8 * L;
+  const int64_t M = static_cast<int64_t>(B) * T;  // 100 Hz frames
+  const bool streaming = s != nullptr;
+  const int pos = streaming ? 8 * s->n_tokens : 0;
+
+  // ---- workspace carve-up ----
+  size_t off = 0;
+  auto carve = [&](size_t bytes) {
+    size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  const size_t o_emb32 = carve(R * rd * 4), o_emb16 = carve(R * rd * 2), o_z16 = carve(R * E * 2);
+  const size_t o_h16 = carve(R * 4 * E * 2);
+  const size_t o_x50 = carve(R * 4 * E * 2), o_a16 = carve(M * E * 2), o_u16 = carve(M * E * 2);
+  const size_t o_x32 = carve(M * E * 4), o_y32 = carve(M * E * 4), o_n16 = carve(M * E * 2);
+  const size_t o_qkv = carve(M * 3 * E * 2), o_o16 = carve(M * E * 2), o_g16 = carve(M * 4 * E * 2);
+  const size_t o_spec = carve(M * spec_ld * 2), o_frames = carve(M * n_fft * 4);
+  FRT2_TRY(ensure_ws(off));
+  float* emb32 = reinterpret_cast<float*>(ws + o_emb32);
+  __half* emb16 = reinterpret_cast<__half*>(ws + o_emb16);
+  __half* z16 = reinterpret_cast<__half*>(ws + o_z16);
+  __half* h16 = reinterpret_cast<__half*>(ws + o_h16);
+  float* x32 = reinterpret_cast<float*>(ws + o_x32);
+  float* y32 = reinterpret_cast<float*>(ws + o_y32);
+  __half* n16 = reinterpret_cast<__half*>(ws + o_n16);
+  __half* qkv16 = reinterpret_cast<__half*>(ws + o_qkv);
+  __half* o16 = reinterpret_cast<__half*>(ws + o_o16);
+  __half* g16 = reinterpret_cast<__half*>(ws + o_g16);
+  __half* spec16 = reinterpret_cast<__half*>(ws + o_spec);
+  float* frames32 = reinterpret_cast<float*>(ws + o_frames);
+
+  // conv input buffers: pointer to row 0 (first history row), history rows present, batch pitch (elements)
+  struct CB { __half* p; int hist; int64_t pitch; };
+  CB cb[11];
+  if (streaming) {
+    for (int i = 0; i < 11; ++i) cb[i] = {s->conv[i], s->conv_hist[i], s->conv_pitch(i)};
+  } else {
+    cb[0] = {reinterpret_cast<__half*>(ws + o_x50), 0, static_cast<int64_t>(T50) * E};
+    cb[1] = {reinterpret_cast<__half*>(ws + o_a16), 0, static_cast<int64_t>(T) * E};
+    cb[2] = {reinterpret_cast<__half*>(ws + o_u16), 0, static_cast<int64_t>(T) * E};
+    for (int i = 3; i < 11; ++i) cb[i] = {n16, 0, static_cast<int64_t>(T) * E};
+  }
+
+  auto flat_gemm = [&](const __half* A, int64_t rows, int Kdim, const __half* W, int N, const float* bias, int act,
+                       const float* resid, float* out32, __half* out16, int64_t ld16, float alpha = 1.0f) {
+    GemmDesc g{};
+    g.A = A; g.a_row_pitch = Kdim; g.a_batch_pitch = 0; g.rows_a = static_cast<int>(rows); g.batches = 1;
+    g.Kc = Kdim; g.ntaps = 1; g.row_shift = 0; g.W = W; g.N = N; g.rows_out = static_cast<int>(rows);
+    g.pitch32 = 0; g.pitch16 = 0; g.alpha = alpha; g.bias = bias; g.act = act; g.resid = resid;
+    g.out32 = out32; g.ld32 = N; g.out16 = out16; g.ld16 = ld16;
+    return run_gemm(g, st);
+  };
+  // causal conv over cb[i] with `taps` taps producing `rows` rows per item
+  auto conv_gemm = [&](const CB& in, int rows, int taps, const __half* W, int N, const float* bias, int act,
+                       const float* resid, float* out32, int64_t pitch32, __half* out16, int64_t ld16,
+                       int64_t pitch16) {
+    GemmDesc g{};
+    g.A = in.p; g.a_row_pitch = E; g.a_batch_pitch = in.pitch; g.rows_a = in.hist + rows; g.batches = B;
+    g.Kc = E; g.ntaps = taps; g.row_shift = in.hist - (taps - 1); g.W = W; g.N = N; g.rows_out = rows;
+    g.pitch32 = pitch32; g.pitch16 = pitch16; g.alpha = 1.0f; g.bias = bias; g.act = act; g.resid = resid;
+    g.out32 = out32; g.ld32 = E; g.out16 = out16; g.ld16 = ld16;
+    return run_gemm(g, st);
+  };
+  auto chunk_ptr = [&](const CB& c) { return c.p + static_cast<int64_t>(c.hist) * E; };
+
+  // ---- K1: RVQ gather-and-sum (+ output projection) ----
+  FRT2_TRY(rvq_gather_sum(tokens, idx_bytes, sB, sQ, sL, B, nq_in, L, tables, K, rd, (debug & DBG_TAPS) ? emb32 : nullptr,
+                          emb16, nullptr, err_word, st));
+  FRT2_TRY(tap_f32("emb", emb32, R * rd, st));
+  const __half* z = emb16;
+  if (has_output_proj) {
+    FRT2_TRY(flat_gemm(emb16, R, rd, w_outproj, E, b_outproj, ACT_NONE, nullptr, nullptr, z16, E));
+    z = z16;
+  }
+  FRT2_TRY(tap_f16("z", z, E, R, E, st));
+  // ---- UpConv: Linear E->4E, ConvTranspose k=s=4 as a GEMM whose (R,4E) output is the (4R,E) 50 Hz sequence ----
+  FRT2_TRY(flat_gemm(z, R, E, w_up_in, 4 * E, b_up_in, ACT_NONE, nullptr, nullptr, h16, 4 * E));
+  {
+    GemmDesc g{};
+    g.A = h16; g.a_row_pitch = 4 * E; g.a_batch_pitch = static_cast<int64_t>(L) * 4 * E; g.rows_a = L; g.batches = B;
+    g.Kc = 4 * E; g.ntaps = 1; g.row_shift = 0; g.W = w_up_conv; g.N = 4 * E; g.rows_out = L;
+    g.alpha = 1.0f; g.bias = nullptr; g.act = ACT_NONE; g.resid = nullptr; g.out32 = nullptr; g.ld32 = 0; g.pitch32 = 0;
+    g.out16 = chunk_ptr(cb[0]); g.ld16 = 4 * E; g.pitch16 = cb[0].pitch;
+    FRT2_TRY(run_gemm(g, st));
+  }
+  if (!streaming) FRT2_TRY(tap_f16("x50", cb[0].p, E, R * 4, E, st));
+  // ---- upsample_conv: ConvT(k3,s2)+GELU as a 2-tap conv with N=2E (even|odd phases), ConvT(k3,s1)+GELU 3-tap ----
+  FRT2_TRY(conv_gemm(cb[0], T50, 2, w_us0, 2 * E, b_us0, ACT_GELU, nullptr, nullptr, 0, chunk_ptr(cb[1]), 2 * E,
+                     cb[1].pitch));
+  FRT2_TRY(conv_gemm(cb[1], T, 3, w_us2, E, b_us2, ACT_GELU, nullptr, nullptr, 0, chunk_ptr(cb[2]), E, cb[2].pitch));
+  if (!streaming) FRT2_TRY(tap_f16("up", cb[2].p, E, M, E, st));
+  // ---- backbone: in_proj k7, 2 resnet blocks ----
+  const int64_t xp = static_cast<int64_t>(T) * E;
+  FRT2_TRY(conv_gemm(cb[2], T, 7, w_inproj, E, b_inproj, ACT_NONE, nullptr, x32, xp, nullptr, 0, 0));
+  auto resblock = [&](int r) -> int {
+    const ResW& w = res[r];
+    const CB& c1 = cb[3 + 2 * r];
+    const CB& c2 = cb[4 + 2 * r];
+    FRT2_TRY(layer_norm_rows_batched(x32, E, M, T, E, w.ln1_g, w.ln1_b, 1e-5f, 1, chunk_ptr(c1), E, c1.pitch, st));
+    FRT2_TRY(conv_gemm(c1, T, 3, w.w1, E, w.b1, ACT_NONE, nullptr, y32, xp, nullptr, 0, 0));
+    FRT2_TRY(layer_norm_rows_batched(y32, E, M, T, E, w.ln2_g, w.ln2_b, 1e-5f, 1, chunk_ptr(c2), E, c2.pitch, st));
+    FRT2_TRY(conv_gemm(c2, T, 3, w.w2, E, w.b2, ACT_NONE, x32, x32, xp, nullptr, 0, 0));
+    return FRT2_OK;
+  };
+  FRT2_TRY(resblock(0));
+  FRT2_TRY(resblock(1));
+  FRT2_TRY(tap_f32("prior", x32, M * E, st));
+  // ---- 12 pre-LN transformer layers ----
+  for (int i = 0; i < nl; ++i) {
+    const LayerW& w = layers[i];
+    FRT2_TRY(layer_norm_rows(x32, E, static_cast<int>(M), E, w.ln1_g, w.ln1_b, 1e-5f, 0, n16, E, st));
+    AttnDesc a{};
+    a.B = B; a.H = H; a.hd = hd; a.Tq = T; a.out = o16; a.o_row_pitch = E; a.o_batch_pitch = xp;
+    a.scale = 1.0f / std::sqrt(static_cast<float>(hd));
+    if (!streaming) {
+      FRT2_TRY(flat_gemm(n16, M, E, w.w_qkv, 3 * E, w.b_qkv, ACT_NONE, nullptr, nullptr, qkv16, 3 * E));
+      a.q = qkv16; a.q_row_pitch = 3 * E; a.q_batch_pitch = static_cast<int64_t>(T) * 3 * E;
+      a.k = qkv16 + E; a.v = qkv16 + 2 * E; a.kv_row_pitch = 3 * E; a.kv_batch_pitch = a.q_batch_pitch;
+      a.Tk = T; a.q_pos0 = 0; a.block_causal = 1;
+    } else {
+      // Q for the chunk; K|V appended in place to the HBM state of this layer (no re-copy: reference
+      // whisper.py:100-104 + decoder.py:306 re-concatenate the whole cache every step)
+      FRT2_TRY(flat_gemm(n16, M, E, w.w_qkv, E, w.b_qkv, ACT_NONE, nullptr, nullptr, qkv16, E));
+      GemmDesc g{};
+      g.A = n16; g.a_row_pitch = E; g.a_batch_pitch = xp; g.rows_a = T; g.batches = B; g.Kc = E; g.ntaps = 1;
+      g.row_shift = 0; g.W = w.w_qkv + static_cast<int64_t>(E) * E; g.N = 2 * E; g.rows_out = T; g.alpha = 1.0f;
+      g.bias = w.b_qkv + E; g.act = ACT_NONE; g.resid = nullptr; g.out32 = nullptr; g.ld32 = 0; g.pitch32 = 0;
+      g.out16 = s->kv[i] + static_cast<int64_t>(pos) * 2 * E; g.ld16 = 2 * E; g.pitch16 = s->kv_pitch();
+      FRT2_TRY(run_gemm(g, st));
+      a.q = qkv16; a.q_row_pitch = E; a.q_batch_pitch = xp;
+      a.k = s->kv[i]; a.v = s->kv[i] + E; a.kv_row_pitch = 2 * E; a.kv_batch_pitch = s->kv_pitch();
+      a.Tk = pos + T; a.q_pos0 = pos; a.block_causal = 0;
+    }
+    FRT2_TRY(run_attn(a, st));
+    FRT2_TRY(flat_gemm(o16, M, E, w.w_o, E, w.b_o, ACT_NONE, x32, x32, nullptr, 0));
+    FRT2_TRY(layer_norm_rows(x32, E, static_cast<int>(M), E, w.ln2_g, w.ln2_b, 1e-5f, 0, n16, E, st));
+    FRT2_TRY(flat_gemm(n16, M, E, w.w_fc1, 4 * E, w.b_fc1, ACT_GELU, nullptr, nullptr, g16, 4 * E));
+    FRT2_TRY(flat_gemm(g16, M, 4 * E, w.w_fc2, E, w.b_fc2, ACT_NONE, x32, x32, nullptr, 0));
+    if (i == 0) FRT2_TRY(tap_f32("layer0", x32, M * E, st));
+  }
+  FRT2_TRY(tap_f32("layers", x32, M * E, st));
+  FRT2_TRY(resblock(2));
+  FRT2_TRY(resblock(3));
+  FRT2_TRY(layer_norm_rows(x32, E, static_cast<int>(M), E, fn_g, fn_b, 1e-6f, 0, n16, E, st));
+  FRT2_TRY(tap_f16("final", n16, E, M, E, st));
+  // ---- K5: head GEMM with polar epilogue -> windowed inverse DFT GEMM -> overlap-add ----
+  if (spec_ld > 2 * n_bins) {
+    FRT2_CUDA_OK(cudaMemset2DAsync(spec16 + 2 * n_bins, static_cast<size_t>(spec_ld) * 2, 0,
+                                   static_cast<size_t>(spec_ld - 2 * n_bins) * 2, M, st));
+  }
+  FRT2_TRY(flat_gemm(n16, M, E, w_head, 2 * n_bins, b_head, ACT_POLAR, nullptr, nullptr, spec16, spec_ld));
+  FRT2_TRY(tap_f16("spec", spec16, spec_ld, M, 2 * n_bins, st));
+  FRT2_TRY(flat_gemm(spec16, M, spec_ld, w_idft, n_fft, nullptr, ACT_NONE, nullptr, frames32, nullptr, 0,
+                     1.0f / static_cast<float>(n_fft)));
+  FRT2_TRY(tap_f32("frames", frames32, M * n_fft, st));
+  OlaDesc od{};
+  od.frames = frames32; od.frames_batch_pitch = static_cast<int64_t>(T) * n_fft; od.window = window;
+  od.lengths = lengths; od.len_mul = 8; od.audio = audio; od.audio_pitch = audio_pitch; od.B = B; od.T = T;
+  od.n_fft = n_fft; od.hop = hop;
+  if (streaming) {
+    od.tail = s->tail; od.first = (s->n_tokens == 0); od.last = last;
+  } else {
+    od.tail = nullptr; od.first = 1; od.last = 1;
+  }
+  FRT2_TRY(istft_overlap_add(od, st));
+  if (streaming) {
+    FRT2_TRY(istft_update_tail(frames32, od.frames_batch_pitch, s->tail, B, T, n_fft, st));
+    ShiftTable tb{};
+    tb.n = 11;
+    for (int i = 0; i < 11; ++i) tb.e[i] = {s->conv[i], s->conv_hist[i], s->conv_rpt[i] * L, s->conv_pitch(i)};
+    shift_history_kernel<<<dim3(8, 11), 256, 0, st>>>(tb, E, B);
+    FRT2_CUDA_OK(cudaGetLastError());
+  }
+  tap_B = B;
+  tap_L = L;
+  return FRT2_OK;
+}
+
+int Stream::ensure_chunk_cap(int Lc, cudaStream_t st) {
+  if (Lc <= chunk_cap) return FRT2_OK;
+  // grow the [history | chunk] conv buffers, preserving the history rows
+  const int old_cap = chunk_cap;
+  __half* old[11];
+  int64_t old_pitch[11];
+  for (int i = 0; i < 11; ++i) {
+    old[i] = conv[i];
+    old_pitch[i] = conv_pitch(i);
+  }
+  chunk_cap = Lc;
+  for (int i = 0; i < 11; ++i) {
+    const size_t bytes = static_cast<size_t>(B) * conv_pitch(i) * 2;
+    FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&conv[i]), bytes));
+    FRT2_CUDA_OK(cudaMemsetAsync(conv[i], 0, bytes, st));
+    if (old_cap > 0) {
+      FRT2_CUDA_OK(cudaMemcpy2DAsync(conv[i], conv_pitch(i) * 2, old[i], old_pitch[i] * 2,
+                                     static_cast<size_t>(conv_hist[i]) * h->E * 2, B, cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  if (old_cap > 0) {
+    FRT2_CUDA_OK(cudaStreamSynchronize(st));
+    for (int i = 0; i < 11; ++i) cudaFree(old[i]);
+  }
+  return FRT2_OK;
+}
+
+int Stream::reset() {
+  n_tokens = 0;
+  for (int i = 0; i < 11; ++i)
+    if (conv[i]) FRT2_CUDA_OK(cudaMemset(conv[i], 0, static_cast<size_t>(B) * conv_pitch(i) * 2));
+  FRT2_CUDA_OK(cudaMemset(tail, 0, static_cast<size_t>(B) * 3 * h->n_fft * 4));
+  return FRT2_OK;
+}
+
+}  // namespace frt2
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+using namespace frt2;
+
+struct frt2_handle { Handle h; };
+struct frt2_stream { Stream s; };
+
+extern "C" {
+
+const char* frt2_last_error(void) { return get_error(); }
+const char* frt2_version(void) { return "frt2_b200 0.1 (sm_100a)"; }
+
+int frt2_create(const frt2_config* cfg, int device, frt2_handle** out) {
+  FRT2_REQUIRE(cfg != nullptr && out != nullptr, FRT2_ERR_BAD_ARG, "frt2_create: null argument");
+  FRT2_REQUIRE(cfg->output_dim == cfg->embed_dim, FRT2_ERR_BAD_ARG, "rvq.output_dim must equal embed_dim");
+  FRT2_REQUIRE(cfg->upconv_stride == 4, FRT2_ERR_BAD_ARG, "only UpConv stride 4 is supported");
+  FRT2_REQUIRE(cfg->embed_dim % 64 == 0 && cfg->rvq_dim % 64 == 0, FRT2_ERR_BAD_ARG,
+               "embed_dim and rvq_dim must be multiples of 64 (tensor-core K blocks)");
+  FRT2_REQUIRE(cfg->codebook_dim % 4 == 0, FRT2_ERR_BAD_ARG, "codebook_dim must be a multiple of 4");
+  FRT2_REQUIRE(cfg->embed_dim % cfg->num_heads == 0, FRT2_ERR_BAD_ARG, "embed_dim must be divisible by num_heads");
+  const int hd = cfg->embed_dim / cfg->num_heads;
+  FRT2_REQUIRE(hd == 32 || hd == 64 || hd == 128, FRT2_ERR_BAD_ARG, "head_dim must be 32, 64 or 128");
+  FRT2_REQUIRE(cfg->num_quantizers >= 1 && cfg->num_quantizers <= 64, FRT2_ERR_BAD_ARG, "num_quantizers out of range");
+  FRT2_REQUIRE(cfg->hop_length >= 1 && cfg->num_layers >= 0 && cfg->codebook_size >= 1, FRT2_ERR_BAD_ARG,
+               "bad config");
+  int ndev = 0;
+  FRT2_CUDA_OK(cudaGetDeviceCount(&ndev));
+  FRT2_REQUIRE(device >= 0 && device < ndev, FRT2_ERR_BAD_ARG, "frt2_create: no such CUDA device");
+  FRT2_CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  FRT2_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  FRT2_REQUIRE(prop.major == 10, FRT2_ERR_CUDA,
+               "libfrt2_b200 needs a Blackwell sm_100 device (tcgen05/TMEM/TMA); there is no fallback path");
+  auto* w = new frt2_handle();
+  Handle& h = w->h;
+  h.cfg = *cfg;
+  h.device = device;
+  h.E = cfg->embed_dim; h.H = cfg->num_heads; h.hd = hd; h.nl = cfg->num_layers; h.nq = cfg->num_quantizers;
+  h.K = cfg->codebook_size; h.cd = cfg->codebook_dim; h.rd = cfg->rvq_dim; h.hop = cfg->hop_length;
+  h.n_fft = 4 * cfg->hop_length; h.n_bins = h.n_fft / 2 + 1;
+  h.spec_ld = (2 * h.n_bins + 63) / 64 * 64;
+  h.has_out_project = cfg->codebook_dim != cfg->rvq_dim;
+  h.has_output_proj = cfg->rvq_dim != cfg->output_dim;
+  *out = w;
+  return FRT2_OK;
+}
+
+int frt2_load_tensor(frt2_handle* hh, const char* key, const float* data, int ndim, const int64_t* shape,
+                     int on_device) {
+  FRT2_REQUIRE(hh && key && data && shape && ndim >= 1 && ndim <= 4, FRT2_ERR_BAD_ARG, "frt2_load_tensor: bad argument");
+  Handle& h = hh->h;
+  FRT2_REQUIRE(!h.finalized, FRT2_ERR_BAD_ARG, "frt2_load_tensor: handle already finalized");
+  const std::string k(key);
+  // encode-only / training-only tensors are not part of the decode path
+  for (const char* skip : {"input_proj", "in_project", "inited", "cluster_size", "embed_avg"})
+    if (k.find(skip) != std::string::npos) return FRT2_OK;
+  if (k.rfind("rvq.", 0) != 0 && k.rfind("upsample.", 0) != 0 && k.rfind("acoustic_decoder.", 0) != 0) return FRT2_OK;
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  const int64_t n = t.numel();
+  FRT2_REQUIRE(n >= 0, FRT2_ERR_BAD_ARG, "frt2_load_tensor: negative dimension");
+  t.data.resize(n);
+  if (on_device) {
+    FRT2_CUDA_OK(cudaSetDevice(h.device));
+    FRT2_CUDA_OK(cudaMemcpy(t.data.data(), data, n * 4, cudaMemcpyDeviceToHost));
+  } else {
+    std::memcpy(t.data.data(), data, n * 4);
+  }
+  std::lock_guard<std::mutex> lk(h.mu);
+  h.raw[k] = std::move(t);
+  return FRT2_OK;
+}
+
+int frt2_finalize(frt2_handle* hh) {
+  FRT2_REQUIRE(hh, FRT2_ERR_BAD_ARG, "null handle");
+  std::lock_guard<std::mutex> lk(hh->h.mu);
+  FRT2_REQUIRE(!hh->h.finalized, FRT2_ERR_BAD_ARG, "already finalized");
+  return hh->h.finalize();
+}
+
+void frt2_destroy(frt2_handle* hh) { delete hh; }
+
+static int check_decode_args(Handle& h, const void* tokens, int idx_bytes, int B, int nq, int L, const float* audio) {
+  FRT2_REQUIRE(h.finalized, FRT2_ERR_NOT_FINALIZED, "handle not finalized");
+  FRT2_REQUIRE(tokens != nullptr && audio != nullptr, FRT2_ERR_BAD_ARG, "null tokens/audio pointer");
+  FRT2_REQUIRE(idx_bytes == 4 || idx_bytes == 8, FRT2_ERR_BAD_DTYPE, "tokens must be int32 or int64");
+  FRT2_REQUIRE(B >= 1 && L >= 1, FRT2_ERR_BAD_ARG, "B and L must be >= 1");
+  FRT2_REQUIRE(nq >= 1 && nq <= h.nq, FRT2_ERR_BAD_ARG, "nq must be in [1, num_quantizers] (quantizers[:nq], rvq.py:160)");
+  return FRT2_OK;
+}
+
+int frt2_decode(frt2_handle* hh, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B, int nq,
+                int L, const int32_t* lengths, float* audio, int64_t audio_pitch, void* cuda_stream) {
+  FRT2_REQUIRE(hh, FRT2_ERR_BAD_ARG, "null handle");
+  Handle& h = hh->h;
+  FRT2_TRY(check_decode_args(h, tokens, idx_bytes, B, nq, L, audio));
+  FRT2_REQUIRE(audio_pitch >= static_cast<int64_t>(8) * h.hop * L, FRT2_ERR_BAD_ARG, "audio_pitch too small");
+  std::lock_guard<std::mutex> lk(h.mu);
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  return h.pipeline(tokens, idx_bytes, sB, sQ, sL, B, nq, L, lengths, audio, audio_pitch, nullptr, 1,
+                    static_cast<cudaStream_t>(cuda_stream));
+}
+
+int frt2_stream_create(frt2_handle* hh, int B, int max_tokens, frt2_stream** out) {
+  FRT2_REQUIRE(hh && out, FRT2_ERR_BAD_ARG, "null argument");
+  Handle& h = hh->h;
+  FRT2_REQUIRE(h.finalized, FRT2_ERR_NOT_FINALIZED, "handle not finalized");
+  FRT2_REQUIRE(B >= 1 && max_tokens >= 1, FRT2_ERR_BAD_ARG, "B and max_tokens must be >= 1");
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  auto* w = new frt2_stream();
+  Stream& s = w->s;
+  s.h = &h; s.B = B; s.max_tokens = max_tokens;
+  s.kv.resize(h.nl, nullptr);
+  int st = FRT2_OK;
+  auto fail = [&](int code) { delete w; return code; };
+  for (int i = 0; i < h.nl; ++i) {
+    if (cudaMalloc(reinterpret_cast<void**>(&s.kv[i]), static_cast<size_t>(B) * s.kv_pitch() * 2) != cudaSuccess) {
+      set_error("frt2_stream_create: out of memory for the KV state");
+      return fail(FRT2_ERR_CUDA);
+    }
+  }
+  if (cudaMalloc(reinterpret_cast<void**>(&s.tail), static_cast<size_t>(B) * 3 * h.n_fft * 4) != cudaSuccess) {
+    set_error("frt2_stream_create: out of memory");
+    return fail(FRT2_ERR_CUDA);
+  }
+  st = s.ensure_chunk_cap(1, nullptr);
+  if (st != FRT2_OK) return fail(st);
+  st = s.reset();
+  if (st != FRT2_OK) return fail(st);
+  *out = w;
+  return FRT2_OK;
+}
+
+int frt2_stream_reset(frt2_stream* ss) {
+  FRT2_REQUIRE(ss, FRT2_ERR_BAD_ARG, "null stream");
+  FRT2_CUDA_OK(cudaSetDevice(ss->s.h->device));
+  FRT2_CUDA_OK(cudaDeviceSynchronize());
+  return ss->s.reset();
+}
+void frt2_stream_destroy(frt2_stream* ss) { delete ss; }
+int frt2_stream_tokens(const frt2_stream* ss) { return ss ? ss->s.n_tokens : 0; }
+
+int frt2_decode_chunk(frt2_handle* hh, frt2_stream* ss, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ,
+                      int64_t sL, int nq, int Lc, int last, float* audio, int64_t audio_pitch, int* n_samples,
+                      void* cuda_stream) {
+  FRT2_REQUIRE(hh && ss, FRT2_ERR_BAD_ARG, "null handle/stream");
+  Handle& h = hh->h;
+  Stream& s = ss->s;
+  FRT2_REQUIRE(s.h == &h, FRT2_ERR_BAD_ARG, "stream belongs to another handle");
+  FRT2_TRY(check_decode_args(h, tokens, idx_bytes, s.B, nq, Lc, audio));
+  FRT2_REQUIRE(s.n_tokens + Lc <= s.max_tokens, FRT2_ERR_STATE_OVERFLOW,
+               "stream state overflow: more tokens than frt2_stream_create reserved");
+  const int pad = (h.n_fft - h.hop) / 2;
+  const int n = 8 * h.hop * Lc - (s.n_tokens == 0 ? pad : 0) + (last ? pad : 0);
+  FRT2_REQUIRE(audio_pitch >= n, FRT2_ERR_BAD_ARG, "audio_pitch too small");
+  std::lock_guard<std::mutex> lk(h.mu);
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  FRT2_TRY(s.ensure_chunk_cap(Lc, st));
+  FRT2_TRY(h.pipeline(tokens, idx_bytes, sB, sQ, sL, s.B, nq, Lc, nullptr, audio, audio_pitch, &s, last, st));
+  s.n_tokens += Lc;
+  if (n_samples) *n_samples = n;
+  return FRT2_OK;
+}
+
+int frt2_export_state(frt2_handle* hh, const frt2_stream* ss, float* up_conv_cache, float* bb_conv_cache1,
+                      float* bb_conv_cache2, float* bb_kv_cache, float* is_cache, void* cuda_stream) {
+  FRT2_REQUIRE(hh && ss, FRT2_ERR_BAD_ARG, "null handle/stream");
+  Handle& h = hh->h;
+  const Stream& s = ss->s;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  const int E = h.E, B = s.B;
+  if (up_conv_cache) {  // (B,E,3) = [last x50 frame | last two post-GELU frames]  (decoder.py:624-655)
+    export_tm_to_cm_kernel<<<grid_for(1LL * B * E), 256, 0, st>>>(s.conv[0], s.conv_pitch(0), 1, E, up_conv_cache, E, 0, 3, 0, B);
+    export_tm_to_cm_kernel<<<grid_for(2LL * B * E), 256, 0, st>>>(s.conv[1], s.conv_pitch(1), 2, E, up_conv_cache, E, 0, 3, 1, B);
+  }
+  if (bb_conv_cache1)  // (B,E,6)
+    export_tm_to_cm_kernel<<<grid_for(6LL * B * E), 256, 0, st>>>(s.conv[2], s.conv_pitch(2), 6, E, bb_conv_cache1, E, 0, 6, 0, B);
+  if (bb_conv_cache2)  // (B,8E,2): 4 blocks x [conv1 input | conv2 input]  (decoder.py:150-171,317-319)
+    for (int i = 0; i < 8; ++i)
+      export_tm_to_cm_kernel<<<grid_for(2LL * B * E), 256, 0, st>>>(s.conv[3 + i], s.conv_pitch(3 + i), 2, E, bb_conv_cache2, 8 * E, i * E, 2, 0, B);
+  if (bb_kv_cache && s.n_tokens > 0)
+    for (int l = 0; l < h.nl; ++l)
+      export_kv_kernel<<<grid_for(2LL * B * 8 * s.n_tokens * E), 256, 0, st>>>(s.kv[l], s.kv_pitch(), 8 * s.n_tokens, E, h.H, h.hd, bb_kv_cache, h.nl, l, B);
+  if (is_cache)
+    transpose_tail_kernel<<<(B * 3 * h.n_fft + 255) / 256, 256, 0, st>>>(s.tail, is_cache, B, h.n_fft, 1);
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
+
+int frt2_import_state(frt2_handle* hh, frt2_stream* ss, int n_tokens, const float* up_conv_cache,
+                      const float* bb_conv_cache1, const float* bb_conv_cache2, const float* bb_kv_cache,
+                      const float* is_cache, void* cuda_stream) {
+  FRT2_REQUIRE(hh && ss, FRT2_ERR_BAD_ARG, "null handle/stream");
+  Handle& h = hh->h;
+  Stream& s = ss->s;
+  FRT2_REQUIRE(n_tokens >= 0 && n_tokens <= s.max_tokens, FRT2_ERR_STATE_OVERFLOW, "n_tokens exceeds the stream capacity");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  const int E = h.E, B = s.B;
+  if (up_conv_cache) {
+    import_cm_to_tm_kernel<<<grid_for(1LL * B * E), 256, 0, st>>>(up_conv_cache, E, 0, 3, 0, s.conv[0], s.conv_pitch(0), 1, E, B);
+    import_cm_to_tm_kernel<<<grid_for(2LL * B * E), 256, 0, st>>>(up_conv_cache, E, 0, 3, 1, s.conv[1], s.conv_pitch(1), 2, E, B);
+  }
+  if (bb_conv_cache1)
+    import_cm_to_tm_kernel<<<grid_for(6LL * B * E), 256, 0, st>>>(bb_conv_cache1, E, 0, 6, 0, s.conv[2], s.conv_pitch(2), 6, E, B);
+  if (bb_conv_cache2)
+    for (int i = 0; i < 8; ++i)
+      import_cm_to_tm_kernel<<<grid_for(2LL * B * E), 256, 0, st>>>(bb_conv_cache2, 8 * E, i * E, 2, 0, s.conv[3 + i], s.conv_pitch(3 + i), 2, E, B);
+  if (bb_kv_cache && n_tokens > 0)
+    for (int l = 0; l < h.nl; ++l)
+      import_kv_kernel<<<grid_for(2LL * B * 8 * n_tokens * E), 256, 0, st>>>(bb_kv_cache, h.nl, l, s.kv[l], s.kv_pitch(), 8 * n_tokens, E, h.H, h.hd, B);
+  if (is_cache)
+    transpose_tail_kernel<<<(B * 3 * h.n_fft + 255) / 256, 256, 0, st>>>(is_cache, s.tail, B, h.n_fft, 0);
+  FRT2_CUDA_OK(cudaGetLastError());
+  s.n_tokens = n_tokens;
+  return FRT2_OK;
+}
+
+int frt2_rvq_gather(frt2_handle* hh, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
+                    int nq, int L, float* rows, float* sum, void* cuda_stream) {
+  FRT2_REQUIRE(hh, FRT2_ERR_BAD_ARG, "null handle");
+  Handle& h = hh->h;
+  FRT2_REQUIRE(h.finalized, FRT2_ERR_NOT_FINALIZED, "handle not finalized");
+  FRT2_REQUIRE(nq >= 1 && nq <= h.nq && B >= 1 && L >= 1 && tokens, FRT2_ERR_BAD_ARG, "bad argument");
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  return rvq_gather_sum(tokens, idx_bytes, sB, sQ, sL, B, nq, L, h.codebooks, h.K, h.cd, sum, nullptr, rows, h.err_word,
+                        static_cast<cudaStream_t>(cuda_stream));
+}
+
+int frt2_set_debug(frt2_handle* hh, int flags) {
+  FRT2_REQUIRE(hh, FRT2_ERR_BAD_ARG, "null handle");
+  hh->h.debug = flags;
+  return FRT2_OK;
+}
+
+int frt2_get_tap(frt2_handle* hh, const char* name, float* out, int64_t capacity, int64_t* n, void* cuda_stream) {
+  FRT2_REQUIRE(hh && name && out && n, FRT2_ERR_BAD_ARG, "bad argument");
+  Handle& h = hh->h;
+  auto it = h.taps.find(name);
+  FRT2_REQUIRE(it != h.taps.end() && it->second.first != nullptr, FRT2_ERR_BAD_ARG,
+               "no such tap recorded (call frt2_set_debug(h, 1) before decoding)");
+  FRT2_REQUIRE(capacity >= it->second.second, FRT2_ERR_BAD_ARG, "tap buffer too small");
+  FRT2_CUDA_OK(cudaMemcpyAsync(out, it->second.first, it->second.second * 4, cudaMemcpyDeviceToDevice,
+                               static_cast<cudaStream_t>(cuda_stream)));
+  *n = it->second.second;
+  return FRT2_OK;
+}
+
+int frt2_check_error(frt2_handle* hh, void* cuda_stream) {
+  FRT2_REQUIRE(hh, FRT2_ERR_BAD_ARG, "null handle");
+  Handle& h = hh->h;
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  unsigned int word = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  FRT2_CUDA_OK(cudaMemcpyAsync(&word, h.err_word, 4, cudaMemcpyDeviceToHost, st));
+  FRT2_CUDA_OK(cudaStreamSynchronize(st));
+  if (word != 0) {
+    FRT2_CUDA_OK(cudaMemsetAsync(h.err_word, 0, 4, st));
+    if (word & DEV_ERR_INDEX_OOR) {
+      set_error("index out of range in self");
+      return FRT2_ERR_INDEX_OUT_OF_RANGE;
+    }
+  }
+  return FRT2_OK;
+}
+
+// ---- single-operator entry points ----
+int frt2_op_gemm(int impl, const void* A16, const void* W16, int batches, int rows_per_batch, int Kc, int ntaps, int N,
+                 float alpha, const float* bias, int act, const float* resid, float* out32, void* out16,
+                 void* cuda_stream) {
+  GemmDesc g{};
+  g.A = static_cast<const __half*>(A16); g.a_row_pitch = Kc; g.a_batch_pitch = static_cast<int64_t>(rows_per_batch) * Kc;
+  g.rows_a = rows_per_batch; g.batches = batches; g.Kc = Kc; g.ntaps = ntaps; g.row_shift = -(ntaps - 1);
+  g.W = static_cast<const __half*>(W16); g.N = N; g.rows_out = rows_per_batch;
+  g.pitch32 = static_cast<int64_t>(rows_per_batch) * N; g.pitch16 = g.pitch32; g.alpha = alpha; g.bias = bias; g.act = act;
+  g.resid = resid; g.out32 = out32; g.ld32 = N; g.out16 = static_cast<__half*>(out16); g.ld16 = N;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  return impl == 0 ? gemm_tc(g, st) : gemm_ref(g, st);
+}
+
+int frt2_op_layer_norm(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,
+                       int apply_silu, void* out16, void* cuda_stream) {
+  return layer_norm_rows(x, C, rows, C, gamma, beta, eps, apply_silu, static_cast<__half*>(out16), C,
+                         static_cast<cudaStream_t>(cuda_stream));
+}
+
+int frt2_op_attention(int impl, const void* q16, const void* k16, const void* v16, void* out16, int B, int H, int hd,
+                      int Tq, int Tk, int q_pos0, int block_causal, void* cuda_stream) {
+  AttnDesc a{};
+  const int64_t E = static_cast<int64_t>(H) * hd;
+  a.q = static_cast<const __half*>(q16); a.q_row_pitch = E; a.q_batch_pitch = E * Tq;
+  a.k = static_cast<const __half*>(k16); a.v = static_cast<const __half*>(v16); a.kv_row_pitch = E; a.kv_batch_pitch = E * Tk;
+  a.out = static_cast<__half*>(out16); a.o_row_pitch = E; a.o_batch_pitch = E * Tq;
+  a.B = B; a.H = H; a.hd = hd; a.Tq = Tq; a.Tk = Tk; a.q_pos0 = q_pos0; a.block_causal = block_causal;
+  a.scale = 1.0f / std::sqrt(static_cast<float>(hd));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  return impl == 0 ? attention_tc(a, st) : attention_warp(a, st);
+}
+
+int frt2_op_overlap_add(const float* frames, const float* tail, const float* window, const int32_t* lengths,
+                        float* audio, int64_t audio_pitch, int B, int T, int n_fft, int hop, int first, int last,
+                        void* cuda_stream) {
+  OlaDesc d{};
+  d.frames = frames; d.frames_batch_pitch = static_cast<int64_t>(T) * n_fft; d.tail = tail; d.window = window;
+  d.lengths = lengths; d.len_mul = 8; d.audio = audio; d.audio_pitch = audio_pitch; d.B = B; d.T = T; d.n_fft = n_fft;
+  d.hop = hop; d.first = first; d.last = last;
+  return istft_overlap_add(d, static_cast<cudaStream_t>(cuda_stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,406 @@
+// K2 — tcgen05 / TMEM / TMA GEMM with a multi-tap causal A operand and fused epilogues.
+//
+//   C[b, m, n] = act(alpha * sum_{tap, c} A[b, m + tap + row_shift, c] * W[n, tap*Kc + c] + bias[n]) (+ resid)
+//
+// One kernel covers every dense contraction of the decode path: the Linear layers (ntaps = 1), the causal
+// Conv1d k=3/7 and both ConvTranspose1d of the upsampler (implicit GEMM: each tap is the same TMA box shifted
+// by one time step on a (C, T, B) tensor map; rows before t = 0 are out of bounds and arrive zero-filled,
+// which IS the causal left padding — reference decoder.py:88-91), the RVQ output projection, the iSTFT head
+// and the windowed inverse DFT.
+//
+// Structure (persistent, one CTA per SM, 256 threads):
+//   warp 0   TMA producer       : cp.async.bulk.tensor (SWIZZLE_128B) A box 64x128, W box 64xBN per k-block
+//   warp 1   MMA issuer         : one elected thread, tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16
+//   warp 2   TMEM allocator     : 2*BN columns = two fp32 accumulators (epilogue of tile i overlaps MMA of i+1)
+//   warps 4-7 epilogue          : tcgen05.ld 32x32b.x32 (thread == output row), bias/GELU/polar/residual,
+//                                 16-byte global stores
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace frt2 {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;          // 64 fp16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 256;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+
+struct GemmKParams {
+  int rows_out;
+  long long pitch32;
+  long long pitch16;
+  int N;
+  int kblocks_per_tap;
+  int num_kblocks;
+  int row_shift;
+  int tiles_m;
+  int tiles_n;
+  int num_tiles;
+  float alpha;
+  const float* bias;
+  int act;
+  const float* resid;
+  float* out32;
+  long long ld32;
+  __half* out16;
+  long long ld16;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void store_chunk(const GemmKParams& p, const uint32_t (&r)[32], long long off32,
+                                            long long off16, int n0, bool full_chunk) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+  if (p.bias != nullptr) {
+    if (full_chunk) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = __ldg(b4 + j);
+        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
+    }
+  }
+  if (p.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (p.act == ACT_POLAR) {
+    // columns come in (log-magnitude, phase) pairs: reference decoder.py:505-518
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      float mag = fminf(expf(v[j]), 100.0f);
+      float s, c;
+      sincosf(v[j + 1], &s, &c);
+      v[j] = mag * c;
+      v[j + 1] = mag * s;
+    }
+  }
+  if (p.resid != nullptr) {
+    const float* rp = p.resid + off32 + n0;
+    if (full_chunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 b = *reinterpret_cast<const float4*>(rp + 4 * j);
+        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) v[j] += rp[j];
+    }
+  }
+  if (p.out32 != nullptr) {
+    float* op = p.out32 + off32 + n0;
+    if (full_chunk) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) op[j] = v[j];
+    }
+  }
+  if (p.out16 != nullptr) {
+    __half* op = p.out16 + off16 + n0;
+    if (full_chunk) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 q;
+        q.x = pack_half2(v[8 * j + 0], v[8 * j + 1]);
+        q.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+        q.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+        q.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(op + 8 * j) = q;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) op[j] = __float2half_rn(v[j]);
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull_bar[s], 1);
+      ptx::mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_idx = tile % p.tiles_n;
+        const int mb = tile / p.tiles_n;
+        const int b = mb / p.tiles_m;
+        const int m0 = (mb % p.tiles_m) * BM;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          const int tap = kb / p.kblocks_per_tap;
+          const int c0 = (kb - tap * p.kblocks_per_tap) * BK;
+          ptx::tma_load_3d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], c0, m0 + tap + p.row_shift, b);
+          ptx::tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_idx * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sA + stage * A_STAGE_BYTES));
+          const uint64_t db = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sB + stage * Cfg::B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 fp16 = 32 B along K inside the 128-B swizzle row: +2 in the (addr >> 4) field
+            ptx::mma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit(&tfull_bar[as]);       // accumulator ready for the epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int wq = warp - 4;  // TMEM lane quarter == warp_id % 4
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_idx = tile % p.tiles_n;
+      const int mb = tile / p.tiles_n;
+      const int b = mb / p.tiles_m;
+      const int row = (mb % p.tiles_m) * BM + wq * 32 + lane;
+      const bool valid_row = row < p.rows_out;
+      const long long off32 = static_cast<long long>(b) * p.pitch32 + static_cast<long long>(row) * p.ld32;
+      const long long off16 = static_cast<long long>(b) * p.pitch16 + static_cast<long long>(row) * p.ld16;
+      ptx::mbar_wait(&tfull_bar[as], aphase);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = n_idx * BN + c * 32;
+        if (n0 >= p.N) break;
+        uint32_t r[32];
+        ptx::tmem_ld32(tmem_base + static_cast<uint32_t>(as * BN + c * 32) + (static_cast<uint32_t>(wq * 32) << 16), r);
+        ptx::tmem_ld_wait();
+        if (valid_row) store_chunk(p, r, off32, off16, n0, n0 + 32 <= p.N);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 0;
+std::once_flag g_once;
+int g_init_status = FRT2_OK;
+
+void do_init() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    g_init_status = FRT2_ERR_CUDA;
+    return;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::SMEM_BYTES);
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute(gemm_tc_kernel): ") + cudaGetErrorString(e));
+    g_init_status = FRT2_ERR_CUDA;
+  }
+}
+
+}  // namespace
+
+int gemm_tc_init() {
+  std::call_once(g_once, do_init);
+  return g_init_status;
+}
+
+int tma_encode_fp16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  FRT2_TRY(gemm_tc_init());
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                        gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) + " (rank " +
+              std::to_string(rank) + ", dims " + std::to_string(dims[0]) + "x" + std::to_string(dims[1]) +
+              ", stride0 " + std::to_string(strides_bytes[0]) + ")");
+    return FRT2_ERR_CUDA;
+  }
+  return FRT2_OK;
+}
+
+int num_sms() {
+  gemm_tc_init();
+  return g_num_sms;
+}
+
+int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
+  FRT2_TRY(gemm_tc_init());
+  FRT2_REQUIRE(g.Kc % BK == 0 && g.Kc > 0, FRT2_ERR_BAD_ARG, "gemm_tc: Kc must be a positive multiple of 64");
+  FRT2_REQUIRE(g.ntaps >= 1 && g.N >= 1 && g.rows_out >= 1 && g.batches >= 1, FRT2_ERR_BAD_ARG, "gemm_tc: bad shape");
+  FRT2_REQUIRE((reinterpret_cast<uintptr_t>(g.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.W) & 15) == 0,
+               FRT2_ERR_BAD_ARG, "gemm_tc: operands must be 16-byte aligned");
+  FRT2_REQUIRE(g.a_row_pitch % 8 == 0 && g.a_batch_pitch % 8 == 0, FRT2_ERR_BAD_ARG,
+               "gemm_tc: A pitches must be multiples of 8 elements");
+  FRT2_REQUIRE((g.out32 == nullptr && g.resid == nullptr) || (g.ld32 % 4 == 0 && g.pitch32 % 4 == 0), FRT2_ERR_BAD_ARG,
+               "gemm_tc: ld32/pitch32 must be multiples of 4");
+  FRT2_REQUIRE(g.out16 == nullptr || (g.ld16 % 8 == 0 && g.pitch16 % 8 == 0), FRT2_ERR_BAD_ARG,
+               "gemm_tc: ld16/pitch16 must be multiples of 8");
+  FRT2_REQUIRE(g.act != ACT_POLAR || (g.N % 2 == 0), FRT2_ERR_BAD_ARG, "gemm_tc: polar epilogue needs even N");
+
+  const int BN = (g.N >= 512) ? 256 : 128;
+  const uint64_t Ktot = static_cast<uint64_t>(g.ntaps) * g.Kc;
+
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(g.Kc), static_cast<uint64_t>(g.rows_a), static_cast<uint64_t>(g.batches)};
+    uint64_t strides[2] = {static_cast<uint64_t>(g.a_row_pitch) * 2,
+                           static_cast<uint64_t>(g.batches > 1 ? g.a_batch_pitch : g.a_row_pitch * g.rows_a) * 2};
+    uint32_t box[3] = {BK, BM, 1};
+    FRT2_TRY(tma_encode_fp16(&tmA, g.A, 3, dims, strides, box));
+  }
+  {
+    uint64_t dims[2] = {Ktot, static_cast<uint64_t>(g.N)};
+    uint64_t strides[1] = {Ktot * 2};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(BN)};
+    FRT2_TRY(tma_encode_fp16(&tmB, g.W, 2, dims, strides, box));
+  }
+
+  GemmKParams p;
+  p.rows_out = g.rows_out;
+  p.pitch32 = g.pitch32;
+  p.pitch16 = g.pitch16;
+  p.N = g.N;
+  p.kblocks_per_tap = g.Kc / BK;
+  p.num_kblocks = g.ntaps * p.kblocks_per_tap;
+  p.row_shift = g.row_shift;
+  p.tiles_m = (g.rows_out + BM - 1) / BM;
+  p.tiles_n = (g.N + BN - 1) / BN;
+  p.num_tiles = g.batches * p.tiles_m * p.tiles_n;
+  p.alpha = g.alpha;
+  p.bias = g.bias;
+  p.act = g.act;
+  p.resid = g.resid;
+  p.out32 = g.out32;
+  p.ld32 = g.ld32;
+  p.out16 = g.out16;
+  p.ld16 = g.ld16;
+
+  const int grid = std::min(p.num_tiles, g_num_sms);
+  if (BN == 256) {
+    gemm_tc_kernel<256><<<grid, GEMM_THREADS, GemmCfg<256>::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  } else {
+    gemm_tc_kernel<128><<<grid, GEMM_THREADS, GemmCfg<128>::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  }
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
+
+}  // namespace frt2

@@ -1,0 +1,323 @@
+// Bandwidth-bound kernels of the decode path: K1 RVQ gather-and-sum, K4 LayerNorm(+SiLU) rows,
+// K5c overlap-add / envelope / trim, plus the SIMT check GEMM used by the unit tests.
+#include "common.cuh"
+
+namespace frt2 {
+
+// =====================================================================================================
+// K1 — RVQ dequantisation: fused gather-and-sum over all codebooks (reference rvq.py:56-60,145-164).
+// One CTA handles TOK tokens; the nq indices of each token are staged in shared memory after an
+// always-on range check; every thread owns float4 columns of the D-wide row, so each codebook row is read
+// with fully coalesced 16-byte loads.  The sum runs in index order from +0.0f (bit-exact with the reference
+// for Identity projections).  `tables` is either the raw codebooks (D = codebook_dim) or the tables
+// pre-folded with the weight-normed out_project (D = rvq_dim), see engine.cu.
+// =====================================================================================================
+constexpr int RVQ_TOK = 4;
+constexpr int RVQ_MAX_NQ = 64;
+
+template <typename IdxT>
+__global__ void __launch_bounds__(128) rvq_gather_sum_kernel(const IdxT* __restrict__ tokens, long long sB, long long sQ,
+                                                             long long sL, int B, int nq, int L,
+                                                             const float* __restrict__ tables, int K, int D,
+                                                             float* __restrict__ sum32, __half* __restrict__ sum16,
+                                                             float* __restrict__ rows, unsigned int* err_word) {
+  __shared__ int s_idx[RVQ_TOK][RVQ_MAX_NQ];
+  const long long R = static_cast<long long>(B) * L;
+  const long long r0 = static_cast<long long>(blockIdx.x) * RVQ_TOK;
+  for (int e = threadIdx.x; e < RVQ_TOK * nq; e += blockDim.x) {
+    const int t = e / nq, i = e - t * nq;
+    const long long r = r0 + t;
+    int idx = 0;
+    if (r < R) {
+      const long long b = r / L, l = r - b * L;
+      const long long raw = static_cast<long long>(tokens[b * sB + i * sQ + l * sL]);
+      if (raw < 0 || raw >= K) {
+        atomicOr(err_word, DEV_ERR_INDEX_OOR);  // surfaced as FRT2_ERR_INDEX_OUT_OF_RANGE / IndexError
+      } else {
+        idx = static_cast<int>(raw);
+      }
+    }
+    s_idx[t][i] = idx;
+  }
+  __syncthreads();
+  const int D4 = D >> 2;
+  const float4* tab4 = reinterpret_cast<const float4*>(tables);
+  for (int t = 0; t < RVQ_TOK; ++t) {
+    const long long r = r0 + t;
+    if (r >= R) break;
+    for (int c = threadIdx.x; c < D4; c += blockDim.x) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < nq; ++i) {
+        const float4 v = __ldg(tab4 + (static_cast<long long>(i) * K + s_idx[t][i]) * D4 + c);
+        if (rows != nullptr) reinterpret_cast<float4*>(rows)[(r * nq + i) * D4 + c] = v;
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      if (sum32 != nullptr) reinterpret_cast<float4*>(sum32)[r * D4 + c] = acc;
+      if (sum16 != nullptr) {
+        uint2 h;
+        h.x = pack_half2(acc.x, acc.y);
+        h.y = pack_half2(acc.z, acc.w);
+        reinterpret_cast<uint2*>(sum16)[r * D4 + c] = h;
+      }
+    }
+  }
+}
+
+int rvq_gather_sum(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B, int nq, int L,
+                   const float* tables, int K, int D, float* sum32, __half* sum16, float* rows,
+                   unsigned int* err_word, cudaStream_t stream) {
+  FRT2_REQUIRE(idx_bytes == 4 || idx_bytes == 8, FRT2_ERR_BAD_DTYPE, "tokens must be int32 or int64");
+  FRT2_REQUIRE(nq >= 1 && nq <= RVQ_MAX_NQ, FRT2_ERR_BAD_ARG, "nq out of range");
+  FRT2_REQUIRE(D % 4 == 0, FRT2_ERR_BAD_ARG, "codebook row width must be a multiple of 4");
+  const long long R = static_cast<long long>(B) * L;
+  if (R == 0) return FRT2_OK;
+  const unsigned grid = static_cast<unsigned>((R + RVQ_TOK - 1) / RVQ_TOK);
+  if (idx_bytes == 4) {
+    rvq_gather_sum_kernel<int><<<grid, 128, 0, stream>>>(static_cast<const int*>(tokens), sB, sQ, sL, B, nq, L, tables,
+                                                         K, D, sum32, sum16, rows, err_word);
+  } else {
+    rvq_gather_sum_kernel<long long><<<grid, 128, 0, stream>>>(static_cast<const long long*>(tokens), sB, sQ, sL, B,
+                                                               nq, L, tables, K, D, sum32, sum16, rows, err_word);
+  }
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
+
+// =====================================================================================================
+// K4 — LayerNorm over channels (+ optional SiLU), one warp per row, warp-shuffle reductions, fp32 in,
+// fp16 out (the next op is always a tensor-core GEMM / conv).  Reference: nn.LayerNorm(eps 1e-5 / 1e-6)
+// decoder.py:119,127,246; whisper.py:134,140; followed by nn.SiLU in the resnet blocks (decoder.py:121,129).
+// Rows are addressed as (batch, t): in = x + (b*in_rows_per_batch + t)*ldx, out = out16 + b*out_batch_pitch + t*ld16
+// so the streaming path can write straight behind the conv history rows.
+// =====================================================================================================
+constexpr int LN_MAX_V4 = 8;  // register cache: up to 32 lanes * 8 float4 = 1024 channels; wider rows re-read
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, long long ldx, long long rows,
+                                                         int rows_per_batch, int C, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float eps, int apply_silu,
+                                                         __half* __restrict__ out16, long long ld16,
+                                                         long long out_batch_pitch) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int C4 = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 cache[LN_MAX_V4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C4) {
+      cache[i] = xr[c];
+      s += (cache[i].x + cache[i].y) + (cache[i].z + cache[i].w);
+    }
+  }
+  for (int c = lane + 32 * LN_MAX_V4; c < C4; c += 32) {
+    const float4 v = xr[c];
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float mean = warp_sum(s) / static_cast<float>(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C4) {
+      const float a = cache[i].x - mean, b = cache[i].y - mean, cc = cache[i].z - mean, d = cache[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  for (int c = lane + 32 * LN_MAX_V4; c < C4; c += 32) {
+    const float4 v = xr[c];
+    const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+    q += (a * a + b * b) + (cc * cc + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(C) + eps);
+  const long long bidx = row / rows_per_batch;
+  const long long t = row - bidx * rows_per_batch;
+  uint2* orow = reinterpret_cast<uint2*>(out16 + bidx * out_batch_pitch + t * ld16);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  auto emit = [&](int c, const float4& v) {
+    const float4 g = __ldg(g4 + c), bb = __ldg(b4 + c);
+    float y0 = (v.x - mean) * rstd * g.x + bb.x;
+    float y1 = (v.y - mean) * rstd * g.y + bb.y;
+    float y2 = (v.z - mean) * rstd * g.z + bb.z;
+    float y3 = (v.w - mean) * rstd * g.w + bb.w;
+    if (apply_silu) { y0 = silu(y0); y1 = silu(y1); y2 = silu(y2); y3 = silu(y3); }
+    uint2 h;
+    h.x = pack_half2(y0, y1);
+    h.y = pack_half2(y2, y3);
+    orow[c] = h;
+  };
+#pragma unroll
+  for (int i = 0; i < LN_MAX_V4; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C4) emit(c, cache[i]);
+  }
+  for (int c = lane + 32 * LN_MAX_V4; c < C4; c += 32) emit(c, xr[c]);
+}
+
+int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_per_batch, int C, const float* gamma,
+                            const float* beta, float eps, int apply_silu, __half* out16, int64_t ld16,
+                            int64_t out_batch_pitch, cudaStream_t stream) {
+  FRT2_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ld16 % 4 == 0 && out_batch_pitch % 4 == 0, FRT2_ERR_BAD_ARG,
+               "layer_norm: C and pitches must be multiples of 4");
+  if (rows == 0) return FRT2_OK;
+  const int warps = 8;
+  const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
+  layer_norm_kernel<<<grid, warps * 32, 0, stream>>>(x, ldx, rows, rows_per_batch, C, gamma, beta, eps, apply_silu,
+                                                     out16, ld16, out_batch_pitch);
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
+
+int layer_norm_rows(const float* x, int64_t ldx, int rows, int C, const float* gamma, const float* beta, float eps,
+                    int apply_silu, __half* out16, int64_t ld16, cudaStream_t stream) {
+  return layer_norm_rows_batched(x, ldx, rows, rows > 0 ? rows : 1, C, gamma, beta, eps, apply_silu, out16, ld16, 0,
+                                 stream);
+}
+
+// =====================================================================================================
+// K5c — overlap-add of windowed frames, window-square envelope normalisation and "same" trimming
+// (reference ISTFT.forward decoder.py:384-405 and ISTFT.forward_chunk decoder.py:431-467) in gather form:
+// every output sample sums the <= n_fft/hop frames that cover it, so there is no scatter / atomics, the
+// envelope is accumulated in the same pass (the reference rebuilds it with a second F.fold every call) and
+// the trim is index arithmetic.  Frame list = [carried tail frames (streaming, not first) | this call's frames].
+// =====================================================================================================
+__global__ void __launch_bounds__(256) overlap_add_kernel(OlaDesc d, int ntail, int start, int n_out_full) {
+  const int b = blockIdx.y;
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= n_out_full) return;
+  int TF = ntail + d.T;
+  int n_out = n_out_full;
+  if (d.lengths != nullptr) {  // offline var-len: item b has lengths[b] tokens == len_mul*lengths[b] frames
+    TF = min(TF, d.lengths[b] * d.len_mul);
+    n_out = TF * d.hop;
+  }
+  float* out = d.audio + static_cast<long long>(b) * d.audio_pitch + n;
+  if (n >= n_out) {
+    *out = 0.f;
+    return;
+  }
+  const int m = n + start;
+  int t_hi = m / d.hop;
+  if (t_hi > TF - 1) t_hi = TF - 1;
+  int t_lo = (m - d.n_fft + d.hop) / d.hop;  // ceil((m - n_fft + 1) / hop) for m - n_fft + 1 > 0
+  if (m - d.n_fft + 1 <= 0) t_lo = 0;
+  float y = 0.f, env = 0.f;
+  for (int t = t_lo; t <= t_hi; ++t) {
+    const int off = m - t * d.hop;
+    const float* fr = (t < ntail)
+                          ? d.tail + (static_cast<long long>(b) * 3 + t) * d.n_fft
+                          : d.frames + static_cast<long long>(b) * d.frames_batch_pitch +
+                                static_cast<long long>(t - ntail) * d.n_fft;
+    const float w = __ldg(d.window + off);
+    y += fr[off];
+    env += w * w;
+  }
+  *out = y / env;
+}
+
+// new tail = last 3 frames of [old tail | frames]; T >= 3 always (a token is 8 frames) so it is a plain copy
+__global__ void update_tail_kernel(const float* __restrict__ frames, long long frames_batch_pitch, float* tail, int T,
+                                   int n_fft) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * n_fft) return;
+  tail[static_cast<long long>(b) * 3 * n_fft + i] =
+      frames[static_cast<long long>(b) * frames_batch_pitch + static_cast<long long>(T - 3) * n_fft + i];
+}
+
+int istft_overlap_add(const OlaDesc& d, cudaStream_t stream) {
+  FRT2_REQUIRE(d.n_fft % d.hop == 0 && d.T >= 1 && d.B >= 1, FRT2_ERR_BAD_ARG, "overlap_add: bad shape");
+  const int pad = (d.n_fft - d.hop) / 2;
+  const int ntail = (d.tail != nullptr && !d.first) ? (d.n_fft / d.hop - 1) : 0;
+  FRT2_REQUIRE(ntail == 0 || ntail == 3, FRT2_ERR_BAD_ARG, "overlap_add: streaming needs n_fft == 4*hop");
+  const int TF = ntail + d.T;
+  const int full = (TF - 1) * d.hop + d.n_fft;
+  const int start = d.first ? pad : (d.n_fft - d.hop);
+  const int n_out = full - start - (d.last ? pad : (d.n_fft - d.hop));
+  if (n_out <= 0) return FRT2_OK;
+  dim3 grid((n_out + 255) / 256, d.B);
+  overlap_add_kernel<<<grid, 256, 0, stream>>>(d, ntail, start, n_out);
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
+
+int istft_update_tail(const float* frames, int64_t frames_batch_pitch, float* tail, int B, int T, int n_fft,
+                      cudaStream_t stream) {
+  FRT2_REQUIRE(T >= 3, FRT2_ERR_BAD_ARG, "update_tail: chunk shorter than the iSTFT carry");
+  dim3 grid((3 * n_fft + 255) / 256, B);
+  update_tail_kernel<<<grid, 256, 0, stream>>>(frames, frames_batch_pitch, tail, T, n_fft);
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
+
+// =====================================================================================================
+// SIMT check GEMM (tests only): same contract as gemm_tc, one thread per output column pair.
+// =====================================================================================================
+__global__ void __launch_bounds__(128) gemm_ref_kernel(GemmDesc g) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  const int m = blockIdx.y;
+  const int b = blockIdx.z;
+  if (n >= g.N) return;
+  const bool has2 = (n + 1) < g.N;
+  const long long Ktot = static_cast<long long>(g.ntaps) * g.Kc;
+  float acc0 = 0.f, acc1 = 0.f;
+  for (int tap = 0; tap < g.ntaps; ++tap) {
+    const int ra = m + tap + g.row_shift;
+    if (ra < 0 || ra >= g.rows_a) continue;
+    const __half* arow = g.A + static_cast<long long>(b) * g.a_batch_pitch + static_cast<long long>(ra) * g.a_row_pitch;
+    const __half* w0 = g.W + static_cast<long long>(n) * Ktot + static_cast<long long>(tap) * g.Kc;
+    const __half* w1 = w0 + Ktot;
+    for (int c = 0; c < g.Kc; ++c) {
+      const float a = __half2float(arow[c]);
+      acc0 = fmaf(a, __half2float(w0[c]), acc0);
+      if (has2) acc1 = fmaf(a, __half2float(w1[c]), acc1);
+    }
+  }
+  float v0 = acc0 * g.alpha, v1 = acc1 * g.alpha;
+  if (g.bias != nullptr) {
+    v0 += g.bias[n];
+    if (has2) v1 += g.bias[n + 1];
+  }
+  if (g.act == ACT_GELU) {
+    v0 = gelu_erf(v0);
+    v1 = gelu_erf(v1);
+  } else if (g.act == ACT_POLAR) {
+    const float mag = fminf(expf(v0), 100.0f);
+    float s, c;
+    sincosf(v1, &s, &c);
+    v0 = mag * c;
+    v1 = mag * s;
+  }
+  const long long o32 = static_cast<long long>(b) * g.pitch32 + static_cast<long long>(m) * g.ld32 + n;
+  const long long o16 = static_cast<long long>(b) * g.pitch16 + static_cast<long long>(m) * g.ld16 + n;
+  if (g.resid != nullptr) {
+    v0 += g.resid[o32];
+    if (has2) v1 += g.resid[o32 + 1];
+  }
+  if (g.out32 != nullptr) {
+    g.out32[o32] = v0;
+    if (has2) g.out32[o32 + 1] = v1;
+  }
+  if (g.out16 != nullptr) {
+    g.out16[o16] = __float2half_rn(v0);
+    if (has2) g.out16[o16 + 1] = __float2half_rn(v1);
+  }
+}
+
+int gemm_ref(const GemmDesc& g, cudaStream_t stream) {
+  dim3 grid((g.N / 2 + 1 + 127) / 128, g.rows_out, g.batches);
+  gemm_ref_kernel<<<grid, 128, 0, stream>>>(g);
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
+
+}  // namespace frt2

@@ -1,0 +1,133 @@
+/*
+ * libfrt2_b200 — C ABI of the B200-native FireRedTTS-2 codec decoder.
+ *
+ * The reference has no FFI: its boundary for this path is the Python attribute
+ * FireRedTTS2._audio_tokenizer (fireredtts2/fireredtts2.py:51-53) and the methods
+ * RedCodecInfer.decode (fireredtts2/codec/model.py:307-324) and
+ * RedCodecInfer.decode_one_token (model.py:326-376).  The entry points below are what a binding of
+ * that boundary needs; fireredtts2_b200/codec.py is the ctypes binding.
+ *
+ * All pointers named "device" are CUDA device pointers on the handle's device.  Calls are
+ * asynchronous on the caller's stream unless stated otherwise.  Return value: FRT2_OK or a negative
+ * frt2_status; frt2_last_error() returns a thread-local message for the last failure.
+ */
+#ifndef FRT2_H_
+#define FRT2_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum frt2_status {
+  FRT2_OK = 0,
+  FRT2_ERR_BAD_ARG = -1,
+  FRT2_ERR_BAD_DTYPE = -2,
+  FRT2_ERR_INDEX_OUT_OF_RANGE = -3, /* reference: IndexError from F.embedding (codec/rvq.py:58) */
+  FRT2_ERR_STATE_OVERFLOW = -4,     /* more tokens than frt2_stream_create reserved */
+  FRT2_ERR_CUDA = -5,
+  FRT2_ERR_MISSING_TENSOR = -6,
+  FRT2_ERR_NOT_FINALIZED = -7
+} frt2_status;
+
+/* Mirrors config_codec.json["codec"]["rvq"|"upsample"|"acoustic_decoder"] (model.py:181-184). */
+typedef struct frt2_config {
+  int32_t rvq_dim;        /* rvq.rvq_dim            (rvq.py:96)  */
+  int32_t output_dim;     /* rvq.output_dim == embed_dim        */
+  int32_t num_quantizers; /* rvq.num_quantizers     (rvq.py:98)  */
+  int32_t codebook_size;  /* rvq.codebook_size      (rvq.py:99)  */
+  int32_t codebook_dim;   /* rvq.codebook_dim       (rvq.py:100) */
+  int32_t embed_dim;      /* upsample / acoustic_decoder embed_dim (model.py:126, decoder.py:553) */
+  int32_t num_layers;     /* acoustic_decoder.num_layers */
+  int32_t num_heads;      /* acoustic_decoder.num_heads  */
+  int32_t hop_length;     /* acoustic_decoder.hop_length (decoder.py:559) */
+  int32_t upconv_stride;  /* upsample.stride (model.py:127), must be 4 */
+} frt2_config;
+
+typedef struct frt2_handle frt2_handle; /* weights + workspace; one per device */
+typedef struct frt2_stream frt2_stream; /* streaming state of B concurrent utterances */
+
+/* ---- lifecycle: replaces RedCodecInfer.from_pretrained + load_state_dict (model.py:210-216) ---- */
+int frt2_create(const frt2_config* cfg, int device, frt2_handle** out);
+/* Hand over one tensor of the reference state_dict by its reference key (e.g.
+ * "acoustic_decoder.backbone.transformers.3.fc1.weight", "rvq.quantizers.0.codebook",
+ * "rvq.output_proj.parametrizations.weight.original0").  fp32, reference layout, contiguous;
+ * host pointer (on_device = 0) or device pointer.  Keys the decode path does not use are ignored. */
+int frt2_load_tensor(frt2_handle* h, const char* key, const float* data, int ndim, const int64_t* shape,
+                     int on_device);
+/* One-time repack on the GPU: weight-norm materialisation (rvq.py:8-13), folded RVQ tables, tap-major
+ * conv weights, fp16 operands, windowed iDFT basis.  Synchronous. */
+int frt2_finalize(frt2_handle* h);
+void frt2_destroy(frt2_handle* h);
+
+/* ---- offline decode: RedCodecInfer.decode (model.py:307-324) ----
+ * tokens: device, (B,nq,L) integers of idx_bytes (4 or 8) with ELEMENT strides sB,sQ,sL (any strides: the
+ * production caller passes a permuted int32 view, fireredtts2.py:196).  audio: device fp32 (B, 8*hop*L) with
+ * row pitch audio_pitch elements.  lengths: optional device int32 (B) of per-item token counts L_b <= L
+ * (extension; item b then equals a standalone decode of its first L_b tokens, remaining samples are 0);
+ * NULL reproduces the reference (every item has L tokens). */
+int frt2_decode(frt2_handle* h, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
+                int nq, int L, const int32_t* lengths, float* audio, int64_t audio_pitch, void* cuda_stream);
+
+/* ---- streaming decode: RedCodecInfer.decode_one_token (model.py:326-376) ----
+ * The stream object owns what the reference keeps in cache_dict (up_conv_cache, bb_conv_cache1/2, bb_kv_cache,
+ * is_cache) in HBM, updated in place. */
+int frt2_stream_create(frt2_handle* h, int B, int max_tokens, frt2_stream** out);
+int frt2_stream_reset(frt2_stream* s);
+void frt2_stream_destroy(frt2_stream* s);
+int frt2_stream_tokens(const frt2_stream* s); /* tokens consumed so far */
+/* One chunk of Lc >= 1 tokens per item.  n_samples (host, written before return) =
+ * 8*hop*Lc - pad*[first chunk] + pad*[last], pad = (n_fft-hop)/2, exactly as ISTFT.forward_chunk slices
+ * (decoder.py:459-467).  Attention inside the chunk is unmasked like the reference's forward_chunk
+ * (whisper.py:107-113); with Lc == 1 it equals the offline block-causal mask. */
+int frt2_decode_chunk(frt2_handle* h, frt2_stream* s, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ,
+                      int64_t sL, int nq, int Lc, int last, float* audio, int64_t audio_pitch, int* n_samples,
+                      void* cuda_stream);
+/* Export / import the state in the reference's cache_dict layouts (fp32, contiguous, device):
+ * up_conv_cache (B,E,3), bb_conv_cache1 (B,E,6), bb_conv_cache2 (B,8E,2), bb_kv_cache (B,layers,H,T,2*hd)
+ * with T = 8*frt2_stream_tokens(s), is_cache (B,n_fft,3).  Any pointer may be NULL (skipped). */
+int frt2_export_state(frt2_handle* h, const frt2_stream* s, float* up_conv_cache, float* bb_conv_cache1,
+                      float* bb_conv_cache2, float* bb_kv_cache, float* is_cache, void* cuda_stream);
+int frt2_import_state(frt2_handle* h, frt2_stream* s, int n_tokens, const float* up_conv_cache,
+                      const float* bb_conv_cache1, const float* bb_conv_cache2, const float* bb_kv_cache,
+                      const float* is_cache, void* cuda_stream);
+
+/* ---- parity hooks ----
+ * Raw codebook rows and their index-ordered fp32 sum, bit-exact with VectorQuantize.decode_code /
+ * ResidualVQ.decode_codes for Identity projections (rvq.py:56-60,145-164).  rows (B,L,nq,cd) / sum (B,L,cd),
+ * either may be NULL. */
+int frt2_rvq_gather(frt2_handle* h, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
+                    int nq, int L, float* rows, float* sum, void* cuda_stream);
+/* Copy an intermediate of the most recent frt2_decode into out (device fp32, time-major (B,T,C)):
+ * "emb" (B,L,rvq_dim), "z" (B,L,E), "x50" (B,4L,E), "up" (B,8L,E), "prior", "layer0", "layers", "final",
+ * "spec" (B,8L,2*n_bins interleaved re,im), "frames" (B,8L,n_fft).  Requires frt2_set_debug(h, 1) before
+ * the decode.  Returns the number of floats written through *n. */
+int frt2_set_debug(frt2_handle* h, int flags);
+int frt2_get_tap(frt2_handle* h, const char* name, float* out, int64_t capacity, int64_t* n, void* cuda_stream);
+/* Synchronise the stream and translate the device-side error word (out-of-range code index) into a status. */
+int frt2_check_error(frt2_handle* h, void* cuda_stream);
+
+/* ---- single-operator entry points (unit parity tests and per-kernel roofline benches) ---- */
+/* C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias) (+ resid); A,W fp16 device, fp32 accumulate.
+ * impl 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT check kernel.  ntaps > 1: causal conv over `batches` items of
+ * rows_per_batch rows, K = ntaps*Kc, zero left padding. */
+int frt2_op_gemm(int impl, const void* A16, const void* W16, int batches, int rows_per_batch, int Kc, int ntaps,
+                 int N, float alpha, const float* bias, int act, const float* resid, float* out32, void* out16,
+                 void* cuda_stream);
+int frt2_op_layer_norm(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,
+                       int apply_silu, void* out16, void* cuda_stream);
+/* q,k,v,out: fp16 (B,T,H*hd) contiguous.  impl 0 = tcgen05 flash kernel, 1 = warp kernel. */
+int frt2_op_attention(int impl, const void* q16, const void* k16, const void* v16, void* out16, int B, int H,
+                      int hd, int Tq, int Tk, int q_pos0, int block_causal, void* cuda_stream);
+int frt2_op_overlap_add(const float* frames, const float* tail, const float* window, const int32_t* lengths,
+                        float* audio, int64_t audio_pitch, int B, int T, int n_fft, int hop, int first, int last,
+                        void* cuda_stream);
+
+const char* frt2_last_error(void);
+const char* frt2_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRT2_H_ */

@@ -1,0 +1,69 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports exactly what
+include/frt2.h declares; the host binding fails loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "frt2.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(frt2_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fireredtts2_b200 import build
+    build.build()
+    from fireredtts2_b200 import _native as N
+    return N.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    from fireredtts2_b200 import _native as N
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/frt2.h but not exported"
+    assert sorted(N.SIGNATURES) == names, "ctypes SIGNATURES and include/frt2.h disagree"
+
+
+def test_version_and_error_string(lib):
+    assert b"sm_100a" in lib.frt2_version()
+    assert isinstance(lib.frt2_last_error(), bytes)
+
+
+def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
+    from fireredtts2_b200 import _native as N
+    h = C.c_void_p()
+    assert lib.frt2_create(None, 0, C.byref(h)) == N.ERR_BAD_ARG
+    cfg = N.Frt2Config(512, 1024, 16, 2048, 256, 1000, 12, 16, 240, 4)   # output_dim != embed_dim
+    assert lib.frt2_create(C.byref(cfg), 0, C.byref(h)) == N.ERR_BAD_ARG
+    cfg = N.Frt2Config(512, 1024, 16, 2048, 256, 1024, 12, 16, 240, 2)   # stride != 4
+    assert lib.frt2_create(C.byref(cfg), 0, C.byref(h)) == N.ERR_BAD_ARG
+    assert lib.frt2_finalize(None) == N.ERR_BAD_ARG
+    assert lib.frt2_decode(None, None, 8, 0, 0, 0, 1, 1, 1, None, None, 0, None) == N.ERR_BAD_ARG
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fireredtts2_b200.codec import RedCodecB200
+    from fireredtts2_b200.config import MICRO
+    from fireredtts2_b200.weights import synthetic_state_dict
+    with pytest.raises(RuntimeError):
+        RedCodecB200(MICRO, synthetic_state_dict(MICRO, 0))
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "fireredtts2_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f

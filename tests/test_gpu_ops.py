@@ -1,0 +1,198 @@
+"""Single-kernel parity tests (GPU): each hand-written kernel through the C ABI against a torch fp32
+reference of the same op on the same fp16-rounded operands, and tcgen05 kernels against the SIMT/warp
+check kernels."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fireredtts2_b200 import _native as N
+    return N.load()
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(lib, status):
+    from fireredtts2_b200 import _native as N
+    N.check(status)
+
+
+def gemm_reference(A, W, taps, bias, act, resid, alpha):
+    """A (b, rows, Kc) fp16, W (N, taps*Kc) fp16 -> fp32 (b, rows, N); causal taps with zero left padding."""
+    b, rows, Kc = A.shape
+    Af = A.float()
+    Wf = W.float()
+    out = torch.zeros(b, rows, W.shape[0], device=A.device)
+    for tap in range(taps):
+        shift = taps - 1 - tap
+        x = torch.zeros_like(Af)
+        if shift < rows:
+            x[:, shift:, :] = Af[:, :rows - shift, :]
+        out += x @ Wf[:, tap * Kc:(tap + 1) * Kc].T
+    out = out * alpha
+    if bias is not None:
+        out = out + bias
+    if act == 1:
+        out = torch.nn.functional.gelu(out)
+    elif act == 2:
+        mag = torch.clamp(torch.exp(out[..., 0::2]), max=100.0)
+        ph = out[..., 1::2]
+        out = torch.stack([mag * torch.cos(ph), mag * torch.sin(ph)], dim=-1).reshape(out.shape)
+    if resid is not None:
+        out = out + resid
+    return out
+
+
+GEMM_CASES = [
+    # batches, rows, Kc, taps, N, bias, act, resid, alpha
+    (1, 128, 64, 1, 128, False, 0, False, 1.0),
+    (1, 300, 128, 1, 256, True, 0, False, 1.0),
+    (1, 1000, 1024, 1, 1024, True, 1, False, 1.0),
+    (1, 777, 1024, 1, 3072, True, 0, False, 1.0),
+    (1, 512, 4096, 1, 1024, True, 0, True, 1.0),
+    (2, 77, 128, 3, 128, True, 0, True, 1.0),
+    (3, 200, 256, 7, 256, True, 0, False, 1.0),
+    (2, 500, 1024, 2, 2048, True, 1, False, 1.0),
+    (1, 1000, 1024, 1, 962, True, 2, False, 1.0),
+    (1, 640, 1024, 1, 960, False, 0, False, 1.0 / 960),
+    (4, 8, 1024, 3, 1024, True, 0, True, 1.0),
+]
+
+
+@pytest.mark.parametrize("case", GEMM_CASES, ids=lambda c: "b%d_m%d_k%d_t%d_n%d_b%d_a%d_r%d" % c[:8])
+def test_gemm_tc(lib, case):
+    batches, rows, Kc, taps, Nn, use_bias, act, use_resid, alpha = case
+    g = torch.Generator(device="cuda").manual_seed(1)
+    A = (torch.randn(batches, rows, Kc, device="cuda", generator=g)).half()
+    W = (torch.randn(Nn, taps * Kc, device="cuda", generator=g) / math.sqrt(taps * Kc)).half()
+    if act == 2:
+        W = W * 0.5
+    bias = torch.randn(Nn, device="cuda", generator=g) * 0.1 if use_bias else None
+    resid = torch.randn(batches, rows, Nn, device="cuda", generator=g) if use_resid else None
+    outs = {}
+    for impl in (0, 1):
+        o32 = torch.full((batches, rows, Nn), float("nan"), device="cuda")
+        o16 = torch.full((batches, rows, Nn), float("nan"), device="cuda", dtype=torch.half) if Nn % 8 == 0 else None
+        _check(lib, lib.frt2_op_gemm(impl, _p(A), _p(W), batches, rows, Kc, taps, Nn, alpha, _p(bias), act,
+                                     _p(resid), _p(o32), _p(o16), _stream()))
+        torch.cuda.synchronize()
+        outs[impl] = (o32, o16)
+    ref = gemm_reference(A, W, taps, bias, act, resid, alpha)
+    scale = ref.abs().max().item() + 1e-6
+    e_ref = (outs[1][0] - ref).abs().max().item() / scale
+    e_tc = (outs[0][0] - ref).abs().max().item() / scale
+    e_tc_vs_simt = (outs[0][0] - outs[1][0]).abs().max().item() / scale
+    print(f"gemm {case}: simt-vs-torch {e_ref:.2e} tc-vs-torch {e_tc:.2e} tc-vs-simt {e_tc_vs_simt:.2e}")
+    assert torch.isfinite(outs[0][0]).all()
+    assert e_ref < 2e-3, "SIMT check kernel disagrees with torch"
+    assert e_tc < 2e-3, "tcgen05 GEMM disagrees with torch"
+    if outs[0][1] is not None:
+        e16 = (outs[0][1].float() - ref).abs().max().item() / scale
+        assert e16 < 3e-3
+
+
+@pytest.mark.parametrize("rows,Cc,silu,eps", [(1000, 1024, 0, 1e-5), (333, 128, 1, 1e-5), (64, 64, 0, 1e-6),
+                                                (17, 2048, 1, 1e-5)])
+def test_layer_norm(lib, rows, Cc, silu, eps):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.randn(rows, Cc, device="cuda", generator=g) * 3 + 0.5
+    gamma = torch.randn(Cc, device="cuda", generator=g)
+    beta = torch.randn(Cc, device="cuda", generator=g)
+    out = torch.empty(rows, Cc, device="cuda", dtype=torch.half)
+    _check(lib, lib.frt2_op_layer_norm(_p(x), rows, Cc, _p(gamma), _p(beta), eps, silu, _p(out), _stream()))
+    ref = torch.nn.functional.layer_norm(x, (Cc,), gamma, beta, eps)
+    if silu:
+        ref = torch.nn.functional.silu(ref)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 4e-3 * max(1.0, ref.abs().max().item()), err   # fp16 output rounding
+
+
+def attention_reference(q, k, v, H, q_pos0, block_causal):
+    B, Tq, E = q.shape
+    Tk = k.shape[1]
+    hd = E // H
+    qh = q.float().view(B, Tq, H, hd).transpose(1, 2)
+    kh = k.float().view(B, Tk, H, hd).transpose(1, 2)
+    vh = v.float().view(B, Tk, H, hd).transpose(1, 2)
+    mask = None
+    if block_causal:
+        qi = torch.arange(Tq, device=q.device) + q_pos0
+        kj = torch.arange(Tk, device=q.device)
+        mask = kj[None, :] <= (qi[:, None] | 7)
+    o = torch.nn.functional.scaled_dot_product_attention(qh, kh, vh, attn_mask=mask)
+    return o.transpose(1, 2).reshape(B, Tq, E)
+
+
+ATTN_CASES = [
+    # B, H, hd, Tq, Tk, q_pos0, block_causal
+    (1, 2, 64, 72, 72, 0, 1),
+    (2, 4, 64, 1000, 1000, 0, 1),
+    (1, 16, 64, 3000, 3000, 0, 1),
+    (2, 2, 64, 32, 232, 200, 0),
+    (1, 2, 64, 8, 8, 0, 0),
+    (3, 2, 64, 8, 808, 800, 0),
+    (1, 2, 64, 128, 128, 0, 1),
+    (1, 1, 64, 64, 320, 256, 0),
+]
+
+
+@pytest.mark.parametrize("case", ATTN_CASES, ids=lambda c: "B%d_H%d_hd%d_q%d_k%d_p%d_bc%d" % c)
+@pytest.mark.parametrize("impl", [1, 0], ids=["warp", "tc"])
+def test_attention(lib, impl, case):
+    B, H, hd, Tq, Tk, q_pos0, bc = case
+    E = H * hd
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q = torch.randn(B, Tq, E, device="cuda", generator=g).half()
+    k = torch.randn(B, Tk, E, device="cuda", generator=g).half()
+    v = torch.randn(B, Tk, E, device="cuda", generator=g).half()
+    out = torch.full((B, Tq, E), float("nan"), device="cuda", dtype=torch.half)
+    _check(lib, lib.frt2_op_attention(impl, _p(q), _p(k), _p(v), _p(out), B, H, hd, Tq, Tk, q_pos0, bc, _stream()))
+    torch.cuda.synchronize()
+    ref = attention_reference(q, k, v, H, q_pos0, bc)
+    err = (out.float() - ref).abs().max().item()
+    print(f"attention impl={impl} {case}: max-abs err {err:.3e}")
+    assert torch.isfinite(out.float()).all()
+    assert err < (2e-3 if impl == 1 else 4e-3), err
+
+
+@pytest.mark.parametrize("B,T,first,last,use_tail", [(2, 24, 1, 1, 0), (1, 8, 1, 0, 1), (2, 8, 0, 0, 1),
+                                                      (1, 16, 0, 1, 1), (1, 8, 1, 1, 1)])
+def test_overlap_add(lib, B, T, first, last, use_tail):
+    from oracle import codec_oracle as O
+    n_fft, hop = 960, 240
+    rng = np.random.default_rng(5)
+    frames = rng.standard_normal((B, T, n_fft)).astype(np.float32)
+    tail = rng.standard_normal((B, 3, n_fft)).astype(np.float32)
+    n = np.arange(n_fft)
+    window = (0.5 - 0.5 * np.cos(2 * np.pi * n / n_fft)).astype(np.float32)
+    fr = frames * window
+    tl = tail * window
+    pad = (n_fft - hop) // 2
+    # oracle (reference decoder.py:384-405 / 431-467)
+    cat = fr if first else np.concatenate([tl, fr], axis=1)
+    y, env = O.overlap_add(cat, window, hop)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        y = y / env
+    y = y[:, pad:] if first else y[:, n_fft - hop:]
+    y = y[:, :-pad] if last else y[:, :-(n_fft - hop)]
+    d_fr = torch.from_numpy(fr).cuda()
+    d_tl = torch.from_numpy(tl).cuda() if use_tail else None
+    d_w = torch.from_numpy(window).cuda()
+    out = torch.full((B, y.shape[1]), float("nan"), device="cuda")
+    _check(lib, lib.frt2_op_overlap_add(_p(d_fr), _p(d_tl), _p(d_w), None, _p(out), out.stride(0), B, T, n_fft, hop,
+                                        first, last, _stream()))
+    err = np.abs(out.cpu().numpy() - y).max()
+    assert err < 1e-5, err
