@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Benchmark of the codec-decode hot path (BASELINE.json metric: audio-seconds decoded per second).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one RedCodecB200.decode of the throughput workload (BASELINE.json configs[2]: batch 64 x 30 s
+utterances = tokens (64,16,375) -> 1920 audio-seconds, C0 architecture, random-init weights, synthetic tokens).
+N > 1 (torchrun): every rank decodes its own batch (utterances are independent: weak scaling, no collective in
+the data path); time = max over ranks.  One JSON line is printed by rank 0.
+
+--impl reference times the reference algorithm's CPU port (oracle/, numpy, all host threads) on a bounded sample of
+the same workload; the reference itself is pure PyTorch and /root/reference does not exist on the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "codec_decode_audio_seconds_per_second"
+UNIT = "audio-s/s"
+WORKLOAD = {"workload": "batch 64 x 30 s utterances, tokens (64,16,375) -> (64,720000) @24 kHz (BASELINE configs[2])",
+            "arch": "C0: rvq 16x2048x256 -> 512 -> 1024, E=1024, 12 layers, 16 heads, hop 240",
+            "batch": 64, "tokens_per_item": 375, "l2": "activations (>6 GB per step) exceed the 126 MB L2"}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port_throughput(sd, cfg, B, L, reps, warm):
+    """The oracle (numpy port of the reference algorithm) on the host cores: audio-s/s on a (B,16,L) sample."""
+    from fireredtts2_b200.weights import synthetic_tokens
+    from oracle import codec_oracle as O
+    tok = synthetic_tokens(cfg, B, L, 1234)
+    for _ in range(warm):
+        O.decode(sd, tok, cfg.num_heads, cfg.hop_length)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.decode(sd, tok, cfg.num_heads, cfg.hop_length)
+        ts.append(time.perf_counter() - t0)
+    audio_s = B * L / 12.5
+    return audio_s, ts
+
+
+def run_reference(args):
+    """Reference arm: the reference algorithm on CPU (oracle port), bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from fireredtts2_b200.config import C0
+    from fireredtts2_b200.weights import synthetic_state_dict
+    sd = synthetic_state_dict(C0, 0)
+    cores = os.cpu_count() or 1
+    B, L = 1, 375   # one 30 s utterance of the workload per step
+    audio_s, ts = cpu_port_throughput(sd, C0, B, L, args.steps, args.warmup)
+    total = sum(ts)
+    v = audio_s * len(ts) / total
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": WORKLOAD,
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{B} x 30 s utterance (tokens ({B},16,{L})) per step, numpy/OpenBLAS, all host threads"},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from fireredtts2_b200 import _native as N
+    from fireredtts2_b200.codec import RedCodecB200
+    from fireredtts2_b200.config import C0
+    from fireredtts2_b200.weights import synthetic_state_dict, synthetic_tokens
+    from oracle import codec_oracle as O   # cpu_baseline / parity check only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    cfg = C0
+    B, L = args.batch, args.tokens
+    sd = synthetic_state_dict(cfg, 0)
+    codec = RedCodecB200(cfg, sd, device=f"cuda:{local}", check_indices=False)
+    tok_host = torch.from_numpy(synthetic_tokens(cfg, B, L, 1234 + rank)).pin_memory()
+    tok_dev = tok_host.to(dev)
+    audio_s_step = B * L / 12.5
+    n_samples = cfg.samples_per_token * L
+    host_audio = torch.empty((B, n_samples), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 1)):
+        codec.decode(tok_dev)
+    barrier()
+
+    # ---- timed region 1: device-resident inputs/outputs ("value") ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    codec.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        audio = codec.decode(tok_dev)
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    prof = {N.PROF_NAMES[c]: codec.profile_get(c) for c in N.PROF_NAMES}
+    launches = codec.profile_get(N.PROF_ALL)["launches"]
+    codec.profile(False)
+    N.check(codec._lib.frt2_check_error(codec._h, codec._cuda_stream()))
+
+    # ---- timed region 2: end to end through the public API with HOST buffers ("e2e") ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        d_tok = tok_host.to(dev, non_blocking=True)
+        a = codec.decode(d_tok)
+        host_audio.copy_(a, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    barrier()
+    ms_e2e = 1e3 * (time.perf_counter() - t0)
+
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * audio_s_step * args.steps / (ms_dev / 1e3)
+    e2e = world * audio_s_step * args.steps / (ms_e2e / 1e3)
+    pk, pk_src = peaks()
+
+    # ---- roofline of the dominant kernel (tensor-bound GEMM), from CUDA events around every launch ----
+    g = prof["gemm_tc"]
+    achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
+    peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    roofline = {"kernel": "gemm_tc_kernel (tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM)", "bound": "tensor",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                "traffic": None, "peak_source": pk_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
+                "launches": g["launches"], "avg_launch_ms": g["ms"] / max(1, g["launches"]),
+                "share_of_step": g["ms"] / ms_dev}
+    kernels = {}
+    for name, r in prof.items():
+        if r["launches"] == 0:
+            continue
+        sec = r["ms"] * 1e-3
+        kernels[name] = {"ms_per_step": r["ms"] / args.steps, "launches_per_step": r["launches"] / args.steps,
+                         "tflops": r["flops"] / sec / 1e12 if r["flops"] else None,
+                         "gbs": r["bytes"] / sec / 1e9 if sec > 0 else None, "share": r["ms"] / ms_dev}
+
+    # ---- parity on a small sample + CPU baseline (oracle port on this box's host cores) ----
+    tok_s = synthetic_tokens(cfg, 1, 125, 1234)
+    codec.check_indices = True
+    a_gpu = codec.decode(torch.from_numpy(tok_s).to(dev)).cpu().numpy()
+    audio_s, ts = cpu_port_throughput(sd, cfg, 1, 125, 3, 1)
+    ref = O.decode(sd, tok_s, cfg.num_heads, cfg.hop_length)
+    parity = {"sample": "config 1: tokens (1,16,125), 10 s", "snr_db": O.snr_db(ref, a_gpu),
+              "max_abs": float(np.abs(ref - a_gpu).max()), "ref_peak": float(np.abs(ref).max()), "gate_snr_db": 40.0}
+    cores = os.cpu_count() or 1
+    cpu = {"value": audio_s / min(ts), "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "config 1: one 10 s utterance (tokens (1,16,125)), numpy/OpenBLAS oracle, best of 3 after 1 warm-up"}
+
+    # ---- first-chunk latency (BASELINE configs[1]): batch 1, one token, host token in -> host audio out ----
+    lat = first_chunk_latency(codec, cfg, dev, reps=args.latency_reps)
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "fp16 operands / fp32 accumulate+residual", "data": "synthetic",
+           "config": dict(WORKLOAD, batch=B, tokens_per_item=L, parallelism=f"utterance-sharded x{world} (no collective)"),
+           "realtime_factor_per_gpu": value / world,
+           "roofline": roofline, "cpu_baseline": cpu,
+           "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(tok_host.numel() * tok_host.element_size()),
+                   "d2h_bytes_per_step": int(host_audio.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+           "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels, "parity": parity, "latency": lat}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def first_chunk_latency(codec, cfg, dev, reps=200):
+    """p50/p99 of: host token -> H2D -> decode_one_token (empty state) -> D2H of the 1560 samples, batch 1.
+    The stream state comes from a pre-allocated pool (reset outside the timed call), as a server would keep it;
+    the variant that also allocates the state inside the call is reported separately."""
+    import torch
+    from fireredtts2_b200.weights import synthetic_tokens
+    tok = torch.from_numpy(synthetic_tokens(cfg, 1, 8, 7)).pin_memory()
+    out_host = torch.empty((1, cfg.samples_per_token), dtype=torch.float32).pin_memory()
+    codec.check_indices = True
+    codec.stream_max_tokens = 1200   # 96 s of audio per stream (LLM max_seq_len bound)
+
+    def one(i, cache, last=False):
+        t0 = time.perf_counter()
+        a, cache = codec.decode_one_token(tok[:, :, i:i + 1].to(dev, non_blocking=True), cache, last)
+        out_host[:, :a.shape[1]].copy_(a, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return 1e3 * (time.perf_counter() - t0), cache
+
+    pooled, steady, alloc = [], [], []
+    state = codec.new_stream(1)
+    for r in range(reps + 5):
+        codec.reset_stream(state)
+        torch.cuda.synchronize()
+        dt, cache = one(0, state)
+        if r >= 5:
+            pooled.append(dt)
+        if r < 25:   # steady-state per-token steps on the same stream
+            for i in range(1, 8):
+                dt, cache = one(i, cache)
+                steady.append(dt)
+    del state, cache
+    for r in range(20):
+        torch.cuda.synchronize()
+        dt, cache = one(0, {})
+        alloc.append(dt)
+        del cache
+    q = lambda v, p: sorted(v)[min(len(v) - 1, int(p * len(v)))]
+    return {"workload": "BASELINE configs[1]: batch 1, first token -> 1560 samples; host token in, host audio out "
+                        "(H2D + decode_one_token + D2H + sync), pooled stream state", "reps": reps,
+            "p50_first_chunk_ms": q(pooled, 0.5), "p99_first_chunk_ms": q(pooled, 0.99),
+            "p50_steady_token_ms": q(steady, 0.5), "p50_first_chunk_incl_state_alloc_ms": q(alloc, 0.5),
+            "target_ms": 10.0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--tokens", type=int, default=375)
+    ap.add_argument("--latency-reps", type=int, default=200)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,9 @@ ERR_BAD_ARG, ERR_BAD_DTYPE, ERR_INDEX_OOR, ERR_STATE_OVERFLOW, ERR_CUDA, ERR_MIS
 
 DBG_TAPS, DBG_GEMM_REF, DBG_ATTN_WARP = 1, 2, 4
 ACT_NONE, ACT_GELU, ACT_POLAR = 0, 1, 2
+PROF_GEMM, PROF_ATTN_TC, PROF_ATTN_WARP, PROF_LAYER_NORM, PROF_RVQ, PROF_OLA, PROF_ALL = 0, 1, 2, 3, 4, 5, -1
+PROF_NAMES = {PROF_GEMM: "gemm_tc", PROF_ATTN_TC: "attention_tc", PROF_ATTN_WARP: "attention_warp",
+              PROF_LAYER_NORM: "layer_norm", PROF_RVQ: "rvq_gather_sum", PROF_OLA: "overlap_add"}
 
 
 class Frt2Config(C.Structure):
@@ -48,6 +51,9 @@ SIGNATURES = {
     "frt2_set_debug": (_i, [_p, _i]),
     "frt2_get_tap": (_i, [_p, C.c_char_p, _p, _i64, C.POINTER(_i64), _p]),
     "frt2_check_error": (_i, [_p, _p]),
+    "frt2_profile": (_i, [_p, _i]),
+    "frt2_profile_get": (_i, [_p, _i, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double),
+                              C.POINTER(C.c_double)]),
     "frt2_op_gemm": (_i, [_i, _p, _p, _i, _i, _i, _i, _i, _f, _p, _i, _p, _p, _p, _p]),
     "frt2_op_layer_norm": (_i, [_p, _i, _i, _p, _p, _f, _i, _p, _p]),
     "frt2_op_attention": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

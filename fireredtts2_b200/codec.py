@@ -196,6 +196,19 @@ class RedCodecB200(torch.nn.Module):
             st.finished = bool(last_token)
         return audio, {_STATE_KEY: st}
 
+    def new_stream(self, batch: int = 1, max_tokens: Optional[int] = None) -> Dict[str, object]:
+        """Pre-allocate a stream state (a server keeps a pool of these so the first chunk pays no allocation);
+        pass the returned dict as ``cache_dict`` of the first ``decode_one_token`` call."""
+        with torch.cuda.device(self.device_index):
+            return {_STATE_KEY: _NativeStream(self, batch, max_tokens or self.stream_max_tokens)}
+
+    def reset_stream(self, cache_dict: Dict[str, object]) -> Dict[str, object]:
+        """Return a used state to its initial (empty) condition for the next utterance."""
+        st: _NativeStream = cache_dict[_STATE_KEY]
+        N.check(self._lib.frt2_stream_reset(st.ptr))
+        st.finished = False
+        return cache_dict
+
     def export_cache(self, cache_dict: Dict[str, object]) -> Dict[str, torch.Tensor]:
         """The state in the reference's own cache_dict layouts (model.py:346-375), for parity / hand-off."""
         st: _NativeStream = cache_dict[_STATE_KEY]
@@ -245,6 +258,15 @@ class RedCodecB200(torch.nn.Module):
                                               self._cuda_stream()))
             N.check(self._lib.frt2_check_error(self._h, self._cuda_stream()))
         return rows, s
+
+    def profile(self, enable: bool):
+        """Bracket every kernel of the following decode calls with CUDA events (bench.py roofline numbers)."""
+        N.check(self._lib.frt2_profile(self._h, int(enable)))
+
+    def profile_get(self, cls: int) -> Dict[str, float]:
+        ms, n, fl, by = C.c_double(0), C.c_int64(0), C.c_double(0), C.c_double(0)
+        N.check(self._lib.frt2_profile_get(self._h, cls, C.byref(ms), C.byref(n), C.byref(fl), C.byref(by)))
+        return {"ms": ms.value, "launches": n.value, "flops": fl.value, "bytes": by.value}
 
     def set_debug(self, flags: int):
         N.check(self._lib.frt2_set_debug(self._h, flags))

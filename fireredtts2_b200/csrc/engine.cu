@@ -191,6 +191,29 @@ struct Handle {
   float* window = nullptr;
   unsigned int* err_word = nullptr;
 
+  // optional per-kernel-class CUDA-event timing (bench.py roofline numbers) and launch counter
+  struct ProfRec { int cls; cudaEvent_t a, b; double flops, bytes; };
+  bool profile = false;
+  std::vector<ProfRec> prof;
+  size_t prof_n = 0;
+  long long launches = 0;
+  int prof_begin(int cls, double flops, double bytes, cudaStream_t st) {
+    ++launches;
+    if (!profile) return -1;
+    if (prof_n == prof.size()) {
+      ProfRec r{};
+      if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
+      prof.push_back(r);
+    }
+    ProfRec& r = prof[prof_n];
+    r.cls = cls; r.flops = flops; r.bytes = bytes;
+    cudaEventRecord(r.a, st);
+    return static_cast<int>(prof_n++);
+  }
+  void prof_end(int id, cudaStream_t st) {
+    if (id >= 0) cudaEventRecord(prof[id].b, st);
+  }
+
   // workspace arena (grow-only)
   uint8_t* ws = nullptr;
   size_t ws_bytes = 0;
@@ -202,6 +225,7 @@ struct Handle {
     for (void* p : owned) cudaFree(p);
     if (ws) cudaFree(ws);
     for (auto& kv : taps) cudaFree(kv.second.first);
+    for (auto& r : prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   }
 
   int dev_alloc(void** p, size_t bytes) {
@@ -248,10 +272,37 @@ struct Handle {
 
   int finalize();
   int ensure_ws(size_t bytes);
-  int run_gemm(const GemmDesc& g, cudaStream_t st) { return (debug & DBG_GEMM_REF) ? gemm_ref(g, st) : gemm_tc(g, st); }
+  int run_gemm(const GemmDesc& g, cudaStream_t st) {
+    const double flops = 2.0 * g.batches * g.rows_out * static_cast<double>(g.N) * g.ntaps * g.Kc;
+    const double bytes = 2.0 * (static_cast<double>(g.batches) * g.rows_a * g.Kc + static_cast<double>(g.N) * g.ntaps * g.Kc) +
+                         static_cast<double>(g.batches) * g.rows_out * g.N *
+                             ((g.out32 ? 4 : 0) + (g.out16 ? 2 : 0) + (g.resid ? 4 : 0));
+    const int id = prof_begin(FRT2_PROF_GEMM, flops, bytes, st);
+    const int rc = (debug & DBG_GEMM_REF) ? gemm_ref(g, st) : gemm_tc(g, st);
+    prof_end(id, st);
+    return rc;
+  }
   int run_attn(const AttnDesc& a, cudaStream_t st) {
-    if ((debug & DBG_ATTN_WARP) || a.hd != 64 || a.Tq < 32) return attention_warp(a, st);
-    return attention_tc(a, st);
+    // visible (query, key) pairs: block-causal sum_q ((q_pos0+q)|7)+1, else Tq*Tk
+    double pairs = static_cast<double>(a.Tq) * a.Tk;
+    if (a.block_causal) {
+      pairs = 0;
+      for (int q = 0; q < a.Tq; q += 8) pairs += 8.0 * std::min(a.Tk, ((a.q_pos0 + q) | 7) + 1);
+    }
+    const double flops = 4.0 * a.hd * pairs * a.B * a.H;
+    const double bytes = 2.0 * a.B * a.H * a.hd * (2.0 * a.Tq + 2.0 * a.Tk);
+    const bool warp = (debug & DBG_ATTN_WARP) || a.hd != 64 || a.Tq < 32;
+    const int id = prof_begin(warp ? FRT2_PROF_ATTN_WARP : FRT2_PROF_ATTN_TC, flops, bytes, st);
+    const int rc = warp ? attention_warp(a, st) : attention_tc(a, st);
+    prof_end(id, st);
+    return rc;
+  }
+  int run_ln(const float* x, int64_t rows, int rows_per_batch, const float* g, const float* b, float eps, int silu_,
+             __half* out, int64_t pitch, cudaStream_t st) {
+    const int id = prof_begin(FRT2_PROF_LAYER_NORM, 0.0, static_cast<double>(rows) * E * 6.0, st);
+    const int rc = layer_norm_rows_batched(x, E, rows, rows_per_batch, E, g, b, eps, silu_, out, E, pitch, st);
+    prof_end(id, st);
+    return rc;
   }
   int tap_f32(const char* name, const float* src, int64_t n, cudaStream_t st);
   int tap_f16(const char* name, const __half* src, int64_t ld, int64_t rows, int cols, cudaStream_t st);
@@ -622,8 +673,13 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   auto chunk_ptr = [&](const CB& c) { return c.p + static_cast<int64_t>(c.hist) * E; };
 
   // ---- K1: RVQ gather-and-sum (+ output projection) ----
-  FRT2_TRY(rvq_gather_sum(tokens, idx_bytes, sB, sQ, sL, B, nq_in, L, tables, K, rd, (debug & DBG_TAPS) ? emb32 : nullptr,
-                          emb16, nullptr, err_word, st));
+  {
+    // algorithmic bytes per token: nq*(idx + D*4) in, D*2 out
+    const int id = prof_begin(FRT2_PROF_RVQ, 0.0, static_cast<double>(R) * (nq_in * (idx_bytes + rd * 4.0) + rd * 2.0), st);
+    FRT2_TRY(rvq_gather_sum(tokens, idx_bytes, sB, sQ, sL, B, nq_in, L, tables, K, rd,
+                            (debug & DBG_TAPS) ? emb32 : nullptr, emb16, nullptr, err_word, st));
+    prof_end(id, st);
+  }
   FRT2_TRY(tap_f32("emb", emb32, R * rd, st));
   const __half* z = emb16;
   if (has_output_proj) {
@@ -654,9 +710,9 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     const ResW& w = res[r];
     const CB& c1 = cb[3 + 2 * r];
     const CB& c2 = cb[4 + 2 * r];
-    FRT2_TRY(layer_norm_rows_batched(x32, E, M, T, E, w.ln1_g, w.ln1_b, 1e-5f, 1, chunk_ptr(c1), E, c1.pitch, st));
+    FRT2_TRY(run_ln(x32, M, T, w.ln1_g, w.ln1_b, 1e-5f, 1, chunk_ptr(c1), c1.pitch, st));
     FRT2_TRY(conv_gemm(c1, T, 3, w.w1, E, w.b1, ACT_NONE, nullptr, y32, xp, nullptr, 0, 0));
-    FRT2_TRY(layer_norm_rows_batched(y32, E, M, T, E, w.ln2_g, w.ln2_b, 1e-5f, 1, chunk_ptr(c2), E, c2.pitch, st));
+    FRT2_TRY(run_ln(y32, M, T, w.ln2_g, w.ln2_b, 1e-5f, 1, chunk_ptr(c2), c2.pitch, st));
     FRT2_TRY(conv_gemm(c2, T, 3, w.w2, E, w.b2, ACT_NONE, x32, x32, xp, nullptr, 0, 0));
     return FRT2_OK;
   };
@@ -666,7 +722,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   // ---- 12 pre-LN transformer layers ----
   for (int i = 0; i < nl; ++i) {
     const LayerW& w = layers[i];
-    FRT2_TRY(layer_norm_rows(x32, E, static_cast<int>(M), E, w.ln1_g, w.ln1_b, 1e-5f, 0, n16, E, st));
+    FRT2_TRY(run_ln(x32, M, static_cast<int>(M), w.ln1_g, w.ln1_b, 1e-5f, 0, n16, 0, st));
     AttnDesc a{};
     a.B = B; a.H = H; a.hd = hd; a.Tq = T; a.out = o16; a.o_row_pitch = E; a.o_batch_pitch = xp;
     a.scale = 1.0f / std::sqrt(static_cast<float>(hd));
@@ -691,7 +747,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     }
     FRT2_TRY(run_attn(a, st));
     FRT2_TRY(flat_gemm(o16, M, E, w.w_o, E, w.b_o, ACT_NONE, x32, x32, nullptr, 0));
-    FRT2_TRY(layer_norm_rows(x32, E, static_cast<int>(M), E, w.ln2_g, w.ln2_b, 1e-5f, 0, n16, E, st));
+    FRT2_TRY(run_ln(x32, M, static_cast<int>(M), w.ln2_g, w.ln2_b, 1e-5f, 0, n16, 0, st));
     FRT2_TRY(flat_gemm(n16, M, E, w.w_fc1, 4 * E, w.b_fc1, ACT_GELU, nullptr, nullptr, g16, 4 * E));
     FRT2_TRY(flat_gemm(g16, M, 4 * E, w.w_fc2, E, w.b_fc2, ACT_NONE, x32, x32, nullptr, 0));
     if (i == 0) FRT2_TRY(tap_f32("layer0", x32, M * E, st));
@@ -699,7 +755,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   FRT2_TRY(tap_f32("layers", x32, M * E, st));
   FRT2_TRY(resblock(2));
   FRT2_TRY(resblock(3));
-  FRT2_TRY(layer_norm_rows(x32, E, static_cast<int>(M), E, fn_g, fn_b, 1e-6f, 0, n16, E, st));
+  FRT2_TRY(run_ln(x32, M, static_cast<int>(M), fn_g, fn_b, 1e-6f, 0, n16, 0, st));
   FRT2_TRY(tap_f16("final", n16, E, M, E, st));
   // ---- K5: head GEMM with polar epilogue -> windowed inverse DFT GEMM -> overlap-add ----
   if (spec_ld > 2 * n_bins) {
@@ -720,8 +776,13 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   } else {
     od.tail = nullptr; od.first = 1; od.last = 1;
   }
-  FRT2_TRY(istft_overlap_add(od, st));
+  {
+    const int id = prof_begin(FRT2_PROF_OLA, 0.0, static_cast<double>(M) * (n_fft + hop) * 4.0, st);
+    FRT2_TRY(istft_overlap_add(od, st));
+    prof_end(id, st);
+  }
   if (streaming) {
+    launches += 2;
     FRT2_TRY(istft_update_tail(frames32, od.frames_batch_pitch, s->tail, B, T, n_fft, st));
     ShiftTable tb{};
     tb.n = 11;
@@ -1019,6 +1080,39 @@ int frt2_get_tap(frt2_handle* hh, const char* name, float* out, int64_t capacity
   FRT2_CUDA_OK(cudaMemcpyAsync(out, it->second.first, it->second.second * 4, cudaMemcpyDeviceToDevice,
                                static_cast<cudaStream_t>(cuda_stream)));
   *n = it->second.second;
+  return FRT2_OK;
+}
+
+int frt2_profile(frt2_handle* hh, int enable) {
+  FRT2_REQUIRE(hh, FRT2_ERR_BAD_ARG, "null handle");
+  Handle& h = hh->h;
+  std::lock_guard<std::mutex> lk(h.mu);
+  h.profile = enable != 0;
+  h.prof_n = 0;
+  h.launches = 0;
+  return FRT2_OK;
+}
+
+int frt2_profile_get(frt2_handle* hh, int cls, double* ms, int64_t* launches, double* flops, double* bytes) {
+  FRT2_REQUIRE(hh, FRT2_ERR_BAD_ARG, "null handle");
+  Handle& h = hh->h;
+  std::lock_guard<std::mutex> lk(h.mu);
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  FRT2_CUDA_OK(cudaDeviceSynchronize());
+  double t = 0, f = 0, by = 0;
+  int64_t n = 0;
+  for (size_t i = 0; i < h.prof_n; ++i) {
+    const auto& r = h.prof[i];
+    if (cls != FRT2_PROF_ALL && r.cls != cls) continue;
+    float e = 0.f;
+    FRT2_CUDA_OK(cudaEventElapsedTime(&e, r.a, r.b));
+    t += e; f += r.flops; by += r.bytes; ++n;
+  }
+  if (cls == FRT2_PROF_ALL) n = h.launches;
+  if (ms) *ms = t;
+  if (launches) *launches = n;
+  if (flops) *flops = f;
+  if (bytes) *bytes = by;
   return FRT2_OK;
 }
 

@@ -50,6 +50,8 @@ struct GemmKParams {
   long long ld32;
   __half* out16;
   long long ld16;
+  int vec32;  // 16-byte vector access legal on out32 / resid rows
+  int vec16;  // ... on out16 rows
 };
 
 template <int BN>
@@ -67,7 +69,7 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, const uint32_t
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
   if (p.bias != nullptr) {
-    if (full_chunk) {
+    if (full_chunk && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -96,7 +98,7 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, const uint32_t
   }
   if (p.resid != nullptr) {
     const float* rp = p.resid + off32 + n0;
-    if (full_chunk) {
+    if (full_chunk && p.vec32) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 b = *reinterpret_cast<const float4*>(rp + 4 * j);
@@ -110,7 +112,7 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, const uint32_t
   }
   if (p.out32 != nullptr) {
     float* op = p.out32 + off32 + n0;
-    if (full_chunk) {
+    if (full_chunk && p.vec32) {
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(op + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -122,7 +124,7 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, const uint32_t
   }
   if (p.out16 != nullptr) {
     __half* op = p.out16 + off16 + n0;
-    if (full_chunk) {
+    if (full_chunk && p.vec16) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint4 q;
@@ -349,10 +351,6 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
                FRT2_ERR_BAD_ARG, "gemm_tc: operands must be 16-byte aligned");
   FRT2_REQUIRE(g.a_row_pitch % 8 == 0 && g.a_batch_pitch % 8 == 0, FRT2_ERR_BAD_ARG,
                "gemm_tc: A pitches must be multiples of 8 elements");
-  FRT2_REQUIRE((g.out32 == nullptr && g.resid == nullptr) || (g.ld32 % 4 == 0 && g.pitch32 % 4 == 0), FRT2_ERR_BAD_ARG,
-               "gemm_tc: ld32/pitch32 must be multiples of 4");
-  FRT2_REQUIRE(g.out16 == nullptr || (g.ld16 % 8 == 0 && g.pitch16 % 8 == 0), FRT2_ERR_BAD_ARG,
-               "gemm_tc: ld16/pitch16 must be multiples of 8");
   FRT2_REQUIRE(g.act != ACT_POLAR || (g.N % 2 == 0), FRT2_ERR_BAD_ARG, "gemm_tc: polar epilogue needs even N");
 
   const int BN = (g.N >= 512) ? 256 : 128;
@@ -392,6 +390,9 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   p.ld32 = g.ld32;
   p.out16 = g.out16;
   p.ld16 = g.ld16;
+  p.vec32 = (g.ld32 % 4 == 0 && g.pitch32 % 4 == 0 && (reinterpret_cast<uintptr_t>(g.out32) & 15) == 0 &&
+             (reinterpret_cast<uintptr_t>(g.resid) & 15) == 0 && (g.bias == nullptr || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0));
+  p.vec16 = (g.ld16 % 8 == 0 && g.pitch16 % 8 == 0 && (reinterpret_cast<uintptr_t>(g.out16) & 15) == 0);
 
   const int grid = std::min(p.num_tiles, g_num_sms);
   if (BN == 256) {
