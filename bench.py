@@ -227,6 +227,12 @@ def run_ours(args):
                          "tflops": r["flops"] / sec / 1e12 if r["flops"] else None,
                          "gbs": r["bytes"] / sec / 1e9 if sec > 0 else None, "share": r["ms"] / ms_dev}
 
+    if args.quick:
+        print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "ms_per_step": ms_dev / args.steps,
+                          "roofline": roofline, "kernels": kernels, "gpu_launches": int(launches), "quick": True}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ---- parity on a small sample + CPU baseline (oracle port on this box's host cores) ----
     tok_s = synthetic_tokens(cfg, 1, 125, 1234)
     codec.check_indices = True
@@ -309,6 +315,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--tokens", type=int, default=375)
     ap.add_argument("--latency-reps", type=int, default=200)
+    ap.add_argument("--quick", action="store_true", help="skip parity / cpu_baseline / latency legs (for ncu runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
