@@ -163,13 +163,27 @@ namespace {
 constexpr int AT_BQ = 128;      // query rows per CTA == TMEM lanes
 constexpr int AT_BK = 64;       // keys per tile
 constexpr int AT_HD = 64;
-constexpr int AT_STAGES = 3;
+constexpr int AT_STAGES = 2;
 constexpr int AT_THREADS = 192; // warps 0-3 softmax (thread == query row), warp 4 TMA, warp 5 MMA + TMEM alloc
 constexpr int AT_Q_BYTES = AT_BQ * AT_HD * 2;   // 16 KB
 constexpr int AT_KV_BYTES = AT_BK * AT_HD * 2;  // 8 KB
 constexpr int AT_P_BYTES = AT_BQ * AT_BK * 2;   // 16 KB
 constexpr int AT_TMEM_COLS = 128;               // S: cols [0,64), PV: cols [64,128)
 constexpr int AT_SMEM_BYTES = AT_Q_BYTES + AT_P_BYTES + 2 * AT_STAGES * AT_KV_BYTES + 1024 + 256;
+
+__device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2; ex2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// two exponentials per MUFU op: (x0, x1) fp32 -> packed halves (lo = 2^x0, hi = 2^x1)
+__device__ __forceinline__ uint32_t exp2_f16x2(float x0, float x1) {
+  uint32_t h, y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
+  return y;
+}
 
 struct AttnKParams {
   int Tq, Tk, q_pos0, block_causal, H;
@@ -179,7 +193,7 @@ struct AttnKParams {
   int q_col0, k_col0, v_col0;  // column of head 0 inside the respective tensor map
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+__global__ void __launch_bounds__(AT_THREADS, 3)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -266,7 +280,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint64_t dq = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sQ));
       const uint64_t dp = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sP));
       ptx::mbar_wait(q_full, 0);
-      auto issue_pv = [&](int j) {
+      auto issue_pv = [&](int j) {  // O (+)= P_j V_j, accumulated in TMEM across all key tiles
         const int st = j % AT_STAGES;
         ptx::mbar_wait(p_full, j & 1);
         ptx::mbar_wait(&v_full[st], (j / AT_STAGES) & 1);
@@ -276,7 +290,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int k = 0; k < AT_BK / 16; ++k) {
           // 16 keys = 16 rows of 128 B: MN-major operand advances 2048 B per K step; P advances 32 B
           const uint64_t dv = ptx::make_desc_mnmajor_sw128(vaddr + k * 2048, 1024, 1024);
-          ptx::mma_f16_ss(tmem_pv, dp + 2 * k, dv, idesc_pv, k != 0 ? 1u : 0u);
+          ptx::mma_f16_ss(tmem_pv, dp + 2 * k, dv, idesc_pv, (j | k) != 0 ? 1u : 0u);
         }
         ptx::mma_commit(pv_full);
         ptx::mma_commit(&v_empty[st]);
@@ -304,11 +318,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int qabs = p.q_pos0 + qi;        // absolute position
     int limit = p.Tk - 1;
     if (p.block_causal) limit = min(limit, qabs | 7);
-    float m = -CUDART_INF_F, l = 0.f;
-    float o[AT_HD];
-#pragma unroll
-    for (int c = 0; c < AT_HD; ++c) o[c] = 0.f;
-    uint8_t* prow = sP + r * 128;
+    // Lazy rescaling: m_ref is the exponent base in use.  It only moves when a tile's row maximum exceeds it by
+    // more than RESCALE_LOG2 (probabilities then stay <= 2^8, exact in the fp32 accumulator / safe in fp16), so
+    // the accumulator O can stay in TMEM and is touched by the softmax threads only on those rare tiles.
+    constexpr float RESCALE_LOG2 = 8.0f;
+    float m_ref = 0.f, l = 0.f;
+    const uint32_t prow_s = ptx::smem_u32(sP) + r * 128;
     const int sw = r & 7;
 
     for (int j = 0; j < ntiles; ++j) {
@@ -323,56 +338,72 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) ptx::mbar_arrive(s_empty);
 
       const int lim = limit - j * AT_BK;  // columns c <= lim are visible
-      float mx = -CUDART_INF_F;
+      if (lim < AT_BK - 1) {              // diagonal / last tile: mask (interior tiles skip this entirely)
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float v0 = __uint_as_float(sa[c]) * p.scale_log2;
-        float v1 = __uint_as_float(sb[c]) * p.scale_log2;
-        if (c > lim) v0 = -CUDART_INF_F;
-        if (c + 32 > lim) v1 = -CUDART_INF_F;
-        sa[c] = __float_as_uint(v0);
-        sb[c] = __float_as_uint(v1);
-        mx = fmaxf(mx, fmaxf(v0, v1));
-      }
-      const float m_new = fmaxf(m, mx);
-      // a row whose visible keys all lie in later tiles keeps m = -inf; use 0 as the exponent base then
-      const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-      const float alpha = exp2f(m - m_use);
-      float rs = 0.f;
-      uint32_t ph[32];  // 64 probabilities packed as half2
-#pragma unroll
-      for (int c = 0; c < 32; c += 2) {
-        const float p0 = exp2f(__uint_as_float(sa[c]) - m_use);
-        const float p1 = exp2f(__uint_as_float(sa[c + 1]) - m_use);
-        const float p2 = exp2f(__uint_as_float(sb[c]) - m_use);
-        const float p3 = exp2f(__uint_as_float(sb[c + 1]) - m_use);
-        rs += (p0 + p1) + (p2 + p3);
-        ph[c >> 1] = pack_half2(p0, p1);
-        ph[16 + (c >> 1)] = pack_half2(p2, p3);
-      }
-      l = l * alpha + rs;
-      m = m_new;
-
-      if (j > 0) {
-        // fold in P_{j-1} V_{j-1} (computed relative to the previous max), then rescale to the new max
-        ptx::mbar_wait(pv_full, (j - 1) & 1);
-        ptx::tc_fence_after();
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          uint32_t t[32];
-          ptx::tmem_ld32(tmem_pv + lane_off + half * 32, t);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) o[half * 32 + c] = (o[half * 32 + c] + __uint_as_float(t[c])) * alpha;
+        for (int c = 0; c < 32; ++c) {
+          if (c > lim) sa[c] = 0xff800000u;        // -inf
+          if (c + 32 > lim) sb[c] = 0xff800000u;
         }
-        ptx::tc_fence_before();
       }
-      // P tile -> shared memory, K-major SWIZZLE_128B: row r at r*128 B, 16-byte chunk c at (c ^ (r & 7))
+      float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};  // 4 independent chains
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(sa[c + u]), __uint_as_float(sb[c + u])));
+      }
+      const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;  // scale > 0
+
+      if (j == 0) {
+        m_ref = (m_tile == -CUDART_INF_F) ? 0.f : m_tile;
+      } else {
+        const bool need = m_tile > m_ref + RESCALE_LOG2;
+        if (__any_sync(0xffffffffu, need)) {
+          // O must be quiescent: every P V issued so far has completed
+          ptx::mbar_wait(pv_full, (j - 1) & 1);
+          ptx::tc_fence_after();
+          const float alpha = need ? fast_exp2(m_ref - m_tile) : 1.0f;
+          if (need) m_ref = m_tile;
+          l *= alpha;
+#pragma unroll 1
+          for (int q4 = 0; q4 < 4; ++q4) {  // 16 columns at a time keeps the rare path's register footprint small
+            uint32_t t[16];
+            ptx::tmem_ld16(tmem_pv + lane_off + q4 * 16, t);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) t[c] = __float_as_uint(__uint_as_float(t[c]) * alpha);
+            ptx::tmem_st16(tmem_pv + lane_off + q4 * 16, t);
+          }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+        }
+      }
+      // the single P buffer is free once P_{j-1} V_{j-1} has been consumed (issued a whole softmax period ago)
+      if (j > 0) ptx::mbar_wait(pv_full, (j - 1) & 1);
+      // p = 2^(s*scale - m_ref), converted to packed halves before the exponential (the result IS the fp16 P
+      // operand) and written straight to the K-major SWIZZLE_128B P tile: row r at r*128 B, chunk c at (c ^ (r&7))
+      const float neg_m = -m_ref;
+      __half2 acc[4];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        uint4 q;
-        q.x = ph[4 * c + 0]; q.y = ph[4 * c + 1]; q.z = ph[4 * c + 2]; q.w = ph[4 * c + 3];
-        *reinterpret_cast<uint4*>(prow + ((c ^ sw) << 4)) = q;
+        uint32_t w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int e = (c & 3) * 8 + 2 * u;
+          const uint32_t s0 = (c < 4) ? sa[e] : sb[e];
+          const uint32_t s1 = (c < 4) ? sa[e + 1] : sb[e + 1];
+          w[u] = exp2_f16x2(fmaf(__uint_as_float(s0), p.scale_log2, neg_m), fmaf(__uint_as_float(s1), p.scale_log2, neg_m));
+        }
+        const __half2 s01 = __hadd2(*reinterpret_cast<const __half2*>(&w[0]), *reinterpret_cast<const __half2*>(&w[1]));
+        const __half2 s23 = __hadd2(*reinterpret_cast<const __half2*>(&w[2]), *reinterpret_cast<const __half2*>(&w[3]));
+        const __half2 s4 = __hadd2(s01, s23);
+        acc[c & 3] = (c < 4) ? s4 : __hadd2(acc[c & 3], s4);
+        ptx::st_shared_v4(prow_s + ((c ^ sw) << 4), w[0], w[1], w[2], w[3]);
+      }
+      {
+        const float2 f0 = __half22float2(acc[0]), f1 = __half22float2(acc[1]);
+        const float2 f2 = __half22float2(acc[2]), f3 = __half22float2(acc[3]);
+        l += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
@@ -391,14 +422,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int c = 0; c < 32; c += 8) {
           uint4 q;
-          q.x = pack_half2((o[half * 32 + c + 0] + __uint_as_float(t[c + 0])) * inv,
-                           (o[half * 32 + c + 1] + __uint_as_float(t[c + 1])) * inv);
-          q.y = pack_half2((o[half * 32 + c + 2] + __uint_as_float(t[c + 2])) * inv,
-                           (o[half * 32 + c + 3] + __uint_as_float(t[c + 3])) * inv);
-          q.z = pack_half2((o[half * 32 + c + 4] + __uint_as_float(t[c + 4])) * inv,
-                           (o[half * 32 + c + 5] + __uint_as_float(t[c + 5])) * inv);
-          q.w = pack_half2((o[half * 32 + c + 6] + __uint_as_float(t[c + 6])) * inv,
-                           (o[half * 32 + c + 7] + __uint_as_float(t[c + 7])) * inv);
+          q.x = pack_half2(__uint_as_float(t[c + 0]) * inv, __uint_as_float(t[c + 1]) * inv);
+          q.y = pack_half2(__uint_as_float(t[c + 2]) * inv, __uint_as_float(t[c + 3]) * inv);
+          q.z = pack_half2(__uint_as_float(t[c + 4]) * inv, __uint_as_float(t[c + 5]) * inv);
+          q.w = pack_half2(__uint_as_float(t[c + 6]) * inv, __uint_as_float(t[c + 7]) * inv);
           *reinterpret_cast<uint4*>(op + half * 32 + c) = q;
         }
       }

@@ -8,12 +8,17 @@
 // which IS the causal left padding — reference decoder.py:88-91), the RVQ output projection, the iSTFT head
 // and the windowed inverse DFT.
 //
-// Structure (persistent, one CTA per SM, 256 threads):
-//   warp 0   TMA producer       : cp.async.bulk.tensor (SWIZZLE_128B) A box 64x128, W box 64xBN per k-block
-//   warp 1   MMA issuer         : one elected thread, tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16
-//   warp 2   TMEM allocator     : 2*BN columns = two fp32 accumulators (epilogue of tile i overlaps MMA of i+1)
-//   warps 4-7 epilogue          : tcgen05.ld 32x32b.x32 (thread == output row), bias/GELU/polar/residual,
-//                                 16-byte global stores
+// Structure (persistent, one CTA per SM, 384 threads):
+//   warp 0     TMA producer   : cp.async.bulk.tensor (SWIZZLE_128B) A box 64x128, W box 64xBN per k-block
+//   warp 1     MMA issuer     : one elected thread, tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16
+//   warp 2     TMEM allocator : 2*BN columns = two fp32 accumulators (epilogue of tile i overlaps MMA of i+1)
+//   warps 4-11 epilogue       : two warps per TMEM lane quarter, each owning half of the tile's columns.
+//                               tcgen05.ld 32x32b.x32 (thread == output row) -> bias / GELU / polar in registers
+//                               -> 128-byte swizzled rows in a per-warp shared-memory staging buffer -> one
+//                               cp.async.bulk.tensor store per 32x(128 B) box (full-line, coalesced writes; rows and
+//                               columns past the tensor edge are clipped by the TMA unit).  The fp32 residual is
+//                               fetched with coalesced 16-byte loads one chunk ahead, turned to row order through the
+//                               same staging buffer and added before the store.
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
 #include <algorithm>
 #include <mutex>
@@ -28,8 +33,12 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;          // 64 fp16 = 128 B = one SWIZZLE_128B row
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 256;
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int STAGING_BYTES = 32 * 128;  // per epilogue warp: 32 rows x 128 B
+
+enum StoreMode : int { STORE_DIRECT = 0, STORE_TMA16 = 1, STORE_TMA32 = 2 };
 
 struct GemmKParams {
   int rows_out;
@@ -50,8 +59,9 @@ struct GemmKParams {
   long long ld32;
   __half* out16;
   long long ld16;
-  int vec32;  // 16-byte vector access legal on out32 / resid rows
+  int vec32;  // 16-byte vector access legal on out32 / resid rows (direct mode)
   int vec16;  // ... on out16 rows
+  int store_mode;
 };
 
 template <int BN>
@@ -60,12 +70,29 @@ struct GemmCfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + EPI_WARPS * STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void store_chunk(const GemmKParams& p, const uint32_t (&r)[32], long long off32,
-                                            long long off16, int n0, bool full_chunk) {
-  float v[32];
+// exact-erf GELU evaluated with the Abramowitz-Stegun 7.1.26 rational approximation of erf (|err| <= 1.5e-7,
+// far below the fp16 rounding of the stored activation); ~3x fewer instructions than erff.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float e = __expf(-z * z);
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float erfv = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erfv);
+}
+
+// alpha, bias and activation on one 32-column chunk held by a thread (one output row)
+__device__ __forceinline__ void apply_chunk(const GemmKParams& p, const uint32_t (&r)[32], int n0, float (&v)[32]) {
+  const bool full_chunk = n0 + 32 <= p.N;
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
   if (p.bias != nullptr) {
@@ -73,7 +100,7 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, const uint32_t
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 b = __ldg(b4 + j);
+        const float4 b = __ldg(b4 + j);
         v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
       }
     } else {
@@ -84,24 +111,31 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, const uint32_t
   }
   if (p.act == ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
   } else if (p.act == ACT_POLAR) {
     // columns come in (log-magnitude, phase) pairs: reference decoder.py:505-518
 #pragma unroll
     for (int j = 0; j < 32; j += 2) {
-      float mag = fminf(expf(v[j]), 100.0f);
+      const float mag = fminf(expf(v[j]), 100.0f);
       float s, c;
       sincosf(v[j + 1], &s, &c);
       v[j] = mag * c;
       v[j + 1] = mag * s;
     }
   }
+}
+
+// direct (non-TMA) store of one chunk, used when the output pitch is not 16-byte aligned or both an fp32 and
+// an fp16 copy are requested
+__device__ __forceinline__ void store_chunk_direct(const GemmKParams& p, float (&v)[32], long long off32,
+                                                   long long off16, int n0) {
+  const bool full_chunk = n0 + 32 <= p.N;
   if (p.resid != nullptr) {
     const float* rp = p.resid + off32 + n0;
     if (full_chunk && p.vec32) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 b = *reinterpret_cast<const float4*>(rp + 4 * j);
+        const float4 b = *reinterpret_cast<const float4*>(rp + 4 * j);
         v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
       }
     } else {
@@ -142,17 +176,29 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, const uint32_t
   }
 }
 
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(ptx::smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmKParams p) {
+               const __grid_constant__ CUtensorMap tmC, const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* sStage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + EPI_WARPS * STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -164,6 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    if (p.store_mode != STORE_DIRECT) ptx::prefetch_tmap(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -172,7 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tfull_bar[s], 1);
-      ptx::mbar_init(&tempty_bar[s], 4);  // one arrive per epilogue warp
+      ptx::mbar_init(&tempty_bar[s], EPI_WARPS);  // one arrive per epilogue warp
     }
     ptx::fence_mbar_init();
   }
@@ -239,33 +286,136 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
-    const int wq = warp - 4;  // TMEM lane quarter == warp_id % 4
+    const int e = warp - 4;
+    const int wq = e & 3;        // TMEM lane quarter == warp_id % 4
+    const int hsel = e >> 2;     // which half of the tile's columns this warp owns
+    constexpr int CHUNKS_PER_WARP = BN / 64;  // 32-column chunks per warp
+    uint8_t* stg = sStage + e * STAGING_BYTES;
+    uint8_t* stg_row = stg + lane * 128;      // row-order access: thread == row
+    const int sw = lane & 7;
+    // coalesced residual access: lane covers row (i*4 + lane/8), 16-byte chunk (lane % 8)
+    const int crow = lane >> 3, cchunk = lane & 7;
+    const uint32_t tmem_lane = static_cast<uint32_t>(wq * 32) << 16;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int n_idx = tile % p.tiles_n;
       const int mb = tile / p.tiles_n;
       const int b = mb / p.tiles_m;
-      const int row = (mb % p.tiles_m) * BM + wq * 32 + lane;
+      const int row0 = (mb % p.tiles_m) * BM + wq * 32;   // first row of this warp's 32-row slab
+      const int row = row0 + lane;
       const bool valid_row = row < p.rows_out;
       const long long off32 = static_cast<long long>(b) * p.pitch32 + static_cast<long long>(row) * p.ld32;
       const long long off16 = static_cast<long long>(b) * p.pitch16 + static_cast<long long>(row) * p.ld16;
+      const int ncol0 = n_idx * BN + hsel * (BN / 2);     // first column owned by this warp
+      const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN + hsel * (BN / 2)) + tmem_lane;
+
+      // residual prefetch of the first chunk (coalesced; overlaps the wait for the accumulator)
+      float4 rpre[8];
+      const bool use_resid = (p.store_mode == STORE_TMA32) && (p.resid != nullptr);
+      auto prefetch_resid = [&](int n0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = row0 + i * 4 + crow;
+          rpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rr < p.rows_out && n0 + cchunk * 4 < p.N)
+            rpre[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<long long>(b) * p.pitch32 +
+                                                       static_cast<long long>(rr) * p.ld32 + n0 + cchunk * 4);
+        }
+      };
+      if (use_resid && ncol0 < p.N) prefetch_resid(ncol0);
+
       ptx::mbar_wait(&tfull_bar[as], aphase);
       ptx::tc_fence_after();
+
+      if (p.store_mode == STORE_TMA16) {
+        // ---- fp16 output: 64 columns (128 B per row) per TMA store
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = n_idx * BN + c * 32;
-        if (n0 >= p.N) break;
-        uint32_t r[32];
-        ptx::tmem_ld32(tmem_base + static_cast<uint32_t>(as * BN + c * 32) + (static_cast<uint32_t>(wq * 32) << 16), r);
-        ptx::tmem_ld_wait();
-        if (valid_row) store_chunk(p, r, off32, off16, n0, n0 + 32 <= p.N);
+        for (int g = 0; g < CHUNKS_PER_WARP / 2; ++g) {
+          const int n0 = ncol0 + g * 64;
+          if (n0 >= p.N) break;
+          uint32_t packed[32];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t r[32];
+            float v[32];
+            ptx::tmem_ld32(tmem_acc + g * 64 + hh * 32, r);
+            ptx::tmem_ld_wait();
+            apply_chunk(p, r, n0 + hh * 32, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) packed[hh * 16 + j] = pack_half2(v[2 * j], v[2 * j + 1]);
+          }
+          if (lane == 0) tma_store_wait_read();  // previous store has finished reading the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 q;
+            q.x = packed[4 * c + 0]; q.y = packed[4 * c + 1]; q.z = packed[4 * c + 2]; q.w = packed[4 * c + 3];
+            *reinterpret_cast<uint4*>(stg_row + ((c ^ sw) << 4)) = q;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_3d(&tmC, stg, n0, row0, b);
+        }
+      } else if (p.store_mode == STORE_TMA32) {
+        // ---- fp32 output (optionally + residual): 32 columns (128 B per row) per TMA store
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS_PER_WARP; ++c) {
+          const int n0 = ncol0 + c * 32;
+          if (n0 >= p.N) break;
+          uint32_t r[32];
+          float v[32];
+          ptx::tmem_ld32(tmem_acc + c * 32, r);
+          ptx::tmem_ld_wait();
+          apply_chunk(p, r, n0, v);
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+          if (use_resid) {
+            // coalesced-order registers -> staging -> row order
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + crow;
+              *reinterpret_cast<float4*>(stg + rr * 128 + ((cchunk ^ (rr & 7)) << 4)) = rpre[i];
+            }
+            __syncwarp();
+            if (c + 1 < CHUNKS_PER_WARP && n0 + 32 < p.N) prefetch_resid(n0 + 32);  // next chunk, in flight during math
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+              const float4 q = *reinterpret_cast<const float4*>(stg_row + ((cc ^ sw) << 4));
+              v[4 * cc + 0] += q.x; v[4 * cc + 1] += q.y; v[4 * cc + 2] += q.z; v[4 * cc + 3] += q.w;
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc)
+            *reinterpret_cast<float4*>(stg_row + ((cc ^ sw) << 4)) =
+                make_float4(v[4 * cc], v[4 * cc + 1], v[4 * cc + 2], v[4 * cc + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_3d(&tmC, stg, n0, row0, b);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS_PER_WARP; ++c) {
+          const int n0 = ncol0 + c * 32;
+          if (n0 >= p.N) break;
+          uint32_t r[32];
+          float v[32];
+          ptx::tmem_ld32(tmem_acc + c * 32, r);
+          ptx::tmem_ld_wait();
+          if (valid_row) {
+            apply_chunk(p, r, n0, v);
+            store_chunk_direct(p, v, off32, off16, n0);
+          }
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (lane == 0 && p.store_mode != STORE_DIRECT) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -306,15 +456,8 @@ void do_init() {
   }
 }
 
-}  // namespace
-
-int gemm_tc_init() {
-  std::call_once(g_once, do_init);
-  return g_init_status;
-}
-
-int tma_encode_fp16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box) {
+int tma_encode(CUtensorMap* map, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+               const uint64_t* strides_bytes, const uint32_t* box) {
   FRT2_TRY(gemm_tc_init());
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
@@ -326,9 +469,9 @@ int tma_encode_fp16(CUtensorMap* map, const void* base, int rank, const uint64_t
     estr[i] = 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
-                        gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_encode(map, dt, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdim, gstr, bdim, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)) + " (rank " +
               std::to_string(rank) + ", dims " + std::to_string(dims[0]) + "x" + std::to_string(dims[1]) +
@@ -336,6 +479,18 @@ int tma_encode_fp16(CUtensorMap* map, const void* base, int rank, const uint64_t
     return FRT2_ERR_CUDA;
   }
   return FRT2_OK;
+}
+
+}  // namespace
+
+int gemm_tc_init() {
+  std::call_once(g_once, do_init);
+  return g_init_status;
+}
+
+int tma_encode_fp16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box) {
+  return tma_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, base, rank, dims, strides_bytes, box);
 }
 
 int num_sms() {
@@ -352,11 +507,12 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   FRT2_REQUIRE(g.a_row_pitch % 8 == 0 && g.a_batch_pitch % 8 == 0, FRT2_ERR_BAD_ARG,
                "gemm_tc: A pitches must be multiples of 8 elements");
   FRT2_REQUIRE(g.act != ACT_POLAR || (g.N % 2 == 0), FRT2_ERR_BAD_ARG, "gemm_tc: polar epilogue needs even N");
+  FRT2_REQUIRE(g.out32 != nullptr || g.out16 != nullptr, FRT2_ERR_BAD_ARG, "gemm_tc: no output");
 
   const int BN = (g.N >= 512) ? 256 : 128;
   const uint64_t Ktot = static_cast<uint64_t>(g.ntaps) * g.Kc;
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   {
     uint64_t dims[3] = {static_cast<uint64_t>(g.Kc), static_cast<uint64_t>(g.rows_a), static_cast<uint64_t>(g.batches)};
     uint64_t strides[2] = {static_cast<uint64_t>(g.a_row_pitch) * 2,
@@ -391,14 +547,34 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   p.out16 = g.out16;
   p.ld16 = g.ld16;
   p.vec32 = (g.ld32 % 4 == 0 && g.pitch32 % 4 == 0 && (reinterpret_cast<uintptr_t>(g.out32) & 15) == 0 &&
-             (reinterpret_cast<uintptr_t>(g.resid) & 15) == 0 && (g.bias == nullptr || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0));
+             (reinterpret_cast<uintptr_t>(g.resid) & 15) == 0);
   p.vec16 = (g.ld16 % 8 == 0 && g.pitch16 % 8 == 0 && (reinterpret_cast<uintptr_t>(g.out16) & 15) == 0);
+
+  // output through TMA stores whenever the layout allows it (16-byte aligned base / pitches, single output)
+  p.store_mode = STORE_DIRECT;
+  tmC = tmA;
+  const uint64_t batch_rows = static_cast<uint64_t>(g.batches);
+  if (g.out16 != nullptr && g.out32 == nullptr && g.resid == nullptr && p.vec16) {
+    uint64_t dims[3] = {static_cast<uint64_t>(g.N), static_cast<uint64_t>(g.rows_out), batch_rows};
+    uint64_t strides[2] = {static_cast<uint64_t>(g.ld16) * 2,
+                           static_cast<uint64_t>(g.batches > 1 ? g.pitch16 : g.ld16 * g.rows_out) * 2};
+    uint32_t box[3] = {64, 32, 1};
+    FRT2_TRY(tma_encode(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, g.out16, 3, dims, strides, box));
+    p.store_mode = STORE_TMA16;
+  } else if (g.out32 != nullptr && g.out16 == nullptr && p.vec32 && (g.resid == nullptr || g.N % 4 == 0)) {
+    uint64_t dims[3] = {static_cast<uint64_t>(g.N), static_cast<uint64_t>(g.rows_out), batch_rows};
+    uint64_t strides[2] = {static_cast<uint64_t>(g.ld32) * 4,
+                           static_cast<uint64_t>(g.batches > 1 ? g.pitch32 : g.ld32 * g.rows_out) * 4};
+    uint32_t box[3] = {32, 32, 1};
+    FRT2_TRY(tma_encode(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, g.out32, 3, dims, strides, box));
+    p.store_mode = STORE_TMA32;
+  }
 
   const int grid = std::min(p.num_tiles, g_num_sms);
   if (BN == 256) {
-    gemm_tc_kernel<256><<<grid, GEMM_THREADS, GemmCfg<256>::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    gemm_tc_kernel<256><<<grid, GEMM_THREADS, GemmCfg<256>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   } else {
-    gemm_tc_kernel<128><<<grid, GEMM_THREADS, GemmCfg<128>::SMEM_BYTES, stream>>>(tmA, tmB, p);
+    gemm_tc_kernel<128><<<grid, GEMM_THREADS, GemmCfg<128>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   }
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;

@@ -1,0 +1,59 @@
+"""Micro-benchmarks of single kernels through the C ABI (for ncu captures and quick A/B timing).
+usage: python tools/op_bench.py attn|gemm [reps]"""
+import ctypes as C
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from fireredtts2_b200 import _native as N
+
+lib = N.load()
+P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+S = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def timeit(fn, reps):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def attn(reps, B=64, H=16, T=3000):
+    E = H * 64
+    qkv = torch.randn(B, T, 3 * E, device="cuda").half()
+    q, k, v = [qkv[..., i * E:(i + 1) * E].contiguous() for i in range(3)]
+    out = torch.empty(B, T, E, device="cuda", dtype=torch.half)
+    ms = timeit(lambda: N.check(lib.frt2_op_attention(0, P(q), P(k), P(v), P(out), B, H, 64, T, T, 0, 1, S())), reps)
+    pairs = sum(8 * min(T, (qq | 7) + 1) for qq in range(0, T, 8))
+    fl = 4.0 * 64 * pairs * B * H
+    print(f"attention_tc B={B} H={H} T={T}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+
+
+def gemm(reps, M=192000, K=1024, Nn=1024, act=0, resid=False, out32=False):
+    A = torch.randn(1, M, K, device="cuda").half()
+    W = (torch.randn(Nn, K, device="cuda") / 32).half()
+    bias = torch.randn(Nn, device="cuda")
+    o32 = torch.zeros(1, M, Nn, device="cuda") if (out32 or resid) else None
+    o16 = None if (out32 or resid) else torch.empty(1, M, Nn, device="cuda", dtype=torch.half)
+    ms = timeit(lambda: N.check(lib.frt2_op_gemm(0, P(A), P(W), 1, M, K, 1, Nn, 1.0, P(bias), act,
+                                                 P(o32) if resid else None, P(o32), P(o16), S())), reps)
+    print(f"gemm M={M} K={K} N={Nn} act={act} resid={resid} out32={out32}: {ms:.3f} ms  {2.0 * M * K * Nn / ms / 1e9:.1f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    what = sys.argv[1]
+    reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    if what == "attn":
+        attn(reps)
+    elif what == "gemm":
+        gemm(reps, K=1024, Nn=3072)
+        gemm(reps, K=1024, Nn=1024, resid=True)
+        gemm(reps, K=1024, Nn=4096, act=1)
+        gemm(reps, K=4096, Nn=1024, resid=True)
+        gemm(reps, K=1024, Nn=1024, out32=True)
