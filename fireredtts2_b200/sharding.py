@@ -1,0 +1,128 @@
+"""Multi-GPU partitioning of the codec decode path.
+
+Units (utterances, dialogue turns) are independent — a turn's decode depends only on its own tokens, the LLM
+carries the cross-turn context (reference fireredtts2.py:379-394) — so the path shards with no collective in
+the compute: one process per GPU, a full weight replica each, a static longest-first assignment of units to
+ranks.  The only exchange step is the gather of waveform chunks to one rank in unit order (config 4: the turns
+of a dialogue are concatenated on the time axis, reference fireredtts2.py:401), done with point-to-point
+``torch.distributed`` send/recv (NCCL over NVLink on GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+SAMPLES_PER_TOKEN = 1920
+
+
+def partition_units(lengths: Sequence[int], world: int) -> List[List[int]]:
+    """Longest-processing-time-first greedy assignment.  Returns, per rank, the unit indices it owns
+    (ascending).  Deterministic, so every rank computes the same plan without communicating."""
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    load = [0] * world
+    plan: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda k: (load[k], k))
+        plan[r].append(i)
+        load[r] += int(lengths[i])
+    for p in plan:
+        p.sort()
+    return plan
+
+
+def make_batches(unit_ids: Sequence[int], lengths: Sequence[int], max_batch: int, max_tokens: int) -> List[List[int]]:
+    """Group a rank's units into padded batches of similar length (longest first) bounded by `max_batch`
+    items and `max_tokens` padded tokens."""
+    ids = sorted(unit_ids, key=lambda i: (-int(lengths[i]), i))
+    batches: List[List[int]] = []
+    cur: List[int] = []
+    for i in ids:
+        if cur:
+            L = int(lengths[cur[0]])
+            if len(cur) + 1 > max_batch or (len(cur) + 1) * L > max_tokens:
+                batches.append(cur)
+                cur = []
+        cur.append(i)
+    if cur:
+        batches.append(cur)
+    return batches
+
+
+DecodeFn = Callable[[torch.Tensor, Optional[torch.Tensor]], torch.Tensor]
+
+
+def decode_units_local(decode_fn: DecodeFn, units: Sequence[torch.Tensor], unit_ids: Sequence[int],
+                       device: torch.device, max_batch: int = 64, max_tokens: int = 64 * 375,
+                       samples_per_token: int = SAMPLES_PER_TOKEN) -> dict:
+    """Decode the given units (each a (nq, L_i) integer tensor) in padded var-len batches.
+    Returns {unit_id: waveform (samples_per_token*L_i,) on `device`}."""
+    lengths = [int(u.shape[1]) for u in units]
+    out = {}
+    for batch in make_batches(unit_ids, lengths, max_batch, max_tokens):
+        L = max(lengths[i] for i in batch)
+        nq = units[batch[0]].shape[0]
+        tok = torch.zeros((len(batch), nq, L), dtype=units[batch[0]].dtype, device=device)
+        for k, i in enumerate(batch):
+            tok[k, :, :lengths[i]] = units[i].to(device)
+        lens = torch.tensor([lengths[i] for i in batch], dtype=torch.int32, device=device)
+        audio = decode_fn(tok, lens)
+        for k, i in enumerate(batch):
+            out[i] = audio[k, :samples_per_token * lengths[i]]
+    return out
+
+
+def decode_sharded(decode_fn: DecodeFn, units: Sequence[torch.Tensor], device: torch.device,
+                   group: Optional[dist.ProcessGroup] = None, dst: int = 0, max_batch: int = 64,
+                   max_tokens: int = 64 * 375, samples_per_token: int = SAMPLES_PER_TOKEN,
+                   gather: bool = True) -> Optional[List[torch.Tensor]]:
+    """Decode `units` (the same list on every rank) sharded over the ranks of `group`.
+
+    With ``gather`` the waveforms are collected on rank `dst` and returned there in unit order (other ranks
+    return None); without it every rank returns only its own units (None elsewhere in the list)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lengths = [int(u.shape[1]) for u in units]
+    plan = partition_units(lengths, world)
+    mine = decode_units_local(decode_fn, units, plan[rank], device, max_batch, max_tokens, samples_per_token)
+    if world == 1 or not gather:
+        return [mine.get(i) for i in range(len(units))]
+    # ---- the one exchange step: waveform chunks to `dst`, one flat message per rank ----
+    if rank != dst:
+        if plan[rank]:
+            flat = torch.cat([mine[i].reshape(-1) for i in plan[rank]]).contiguous()
+            dist.send(flat, dst=dst, group=group)
+        return None
+    result: List[Optional[torch.Tensor]] = [None] * len(units)
+    for i in plan[dst]:
+        result[i] = mine[i]
+    for r in range(world):
+        if r == dst or not plan[r]:
+            continue
+        n = sum(samples_per_token * lengths[i] for i in plan[r])
+        buf = torch.empty((n,), dtype=torch.float32, device=device)
+        dist.recv(buf, src=r, group=group)
+        off = 0
+        for i in plan[r]:
+            k = samples_per_token * lengths[i]
+            result[i] = buf[off:off + k]
+            off += k
+    return result  # type: ignore[return-value]
+
+
+def dialogue_turn_lengths(total_tokens: int = 2250, turns: int = 24, seed: int = 0, max_len: int = 375) -> List[int]:
+    """BASELINE.json configs[3]: a 3-minute 4-speaker dialogue = `turns` turns whose lengths are drawn
+    U[2 s, 15 s] and rescaled to sum to `total_tokens` (each <= 30 s, reference fireredtts2.py:383)."""
+    g = torch.Generator().manual_seed(seed)
+    raw = 25 + torch.rand(turns, generator=g) * (187.5 - 25)
+    lens = torch.clamp((raw * (total_tokens / raw.sum())).round().long(), 1, max_len)
+    diff = total_tokens - int(lens.sum())
+    i = 0
+    while diff != 0:   # distribute the rounding remainder
+        step = 1 if diff > 0 else -1
+        if 1 <= int(lens[i % turns]) + step <= max_len:
+            lens[i % turns] += step
+            diff -= step
+        i += 1
+    return [int(x) for x in lens]
