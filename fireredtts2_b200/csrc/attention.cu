@@ -160,16 +160,18 @@ int attention_warp(const AttnDesc& a, cudaStream_t stream) {
 // =====================================================================================================
 namespace {
 
-constexpr int AT_BQ = 128;      // query rows per CTA == TMEM lanes
-constexpr int AT_BK = 64;       // keys per tile
+constexpr int AT_BQ = 128;       // query rows per query tile == TMEM lanes
+constexpr int AT_QT = 2;         // query tiles per CTA (they share every K/V tile: half the L2->smem traffic)
+constexpr int AT_BK = 64;        // keys per tile
 constexpr int AT_HD = 64;
 constexpr int AT_STAGES = 2;
-constexpr int AT_THREADS = 192; // warps 0-3 softmax (thread == query row), warp 4 TMA, warp 5 MMA + TMEM alloc
-constexpr int AT_Q_BYTES = AT_BQ * AT_HD * 2;   // 16 KB
+constexpr int AT_SOFTMAX_WARPS = 4 * AT_QT;
+constexpr int AT_THREADS = (AT_SOFTMAX_WARPS + 2) * 32;  // + TMA warp + MMA/TMEM-alloc warp
+constexpr int AT_Q_BYTES = AT_BQ * AT_HD * 2;   // 16 KB per query tile
 constexpr int AT_KV_BYTES = AT_BK * AT_HD * 2;  // 8 KB
-constexpr int AT_P_BYTES = AT_BQ * AT_BK * 2;   // 16 KB
-constexpr int AT_TMEM_COLS = 128;               // S: cols [0,64), PV: cols [64,128)
-constexpr int AT_SMEM_BYTES = AT_Q_BYTES + AT_P_BYTES + 2 * AT_STAGES * AT_KV_BYTES + 1024 + 256;
+constexpr int AT_P_BYTES = AT_BQ * AT_BK * 2;   // 16 KB per query tile
+constexpr int AT_TMEM_COLS = 128 * AT_QT;       // per query tile: S cols [0,64), O cols [64,128)
+constexpr int AT_SMEM_BYTES = AT_QT * (AT_Q_BYTES + AT_P_BYTES) + 2 * AT_STAGES * AT_KV_BYTES + 1024 + 256;
 
 __device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2; ex2(-inf) = 0
   float y;
@@ -177,12 +179,20 @@ __device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2; ex2(-inf) = 
   return y;
 }
 
-// two exponentials per MUFU op: (x0, x1) fp32 -> packed halves (lo = 2^x0, hi = 2^x1)
+// (x0, x1) fp32 -> packed halves (lo = 2^x0, hi = 2^x1); the conversion to half happens BEFORE the exponential so
+// the result is directly the fp16 P operand
 __device__ __forceinline__ uint32_t exp2_f16x2(float x0, float x1) {
+#ifdef FRT2_EXP_F16X2
   uint32_t h, y;
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
   asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(h));
   return y;
+#else
+  uint32_t y;
+  const float e0 = fast_exp2(x0), e1 = fast_exp2(x1);
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(e1), "f"(e0));
+  return y;
+#endif
 }
 
 struct AttnKParams {
@@ -190,17 +200,16 @@ struct AttnKParams {
   float scale_log2;
   __half* out;
   long long o_row_pitch, o_batch_pitch;
-  int q_col0, k_col0, v_col0;  // column of head 0 inside the respective tensor map
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 3)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;
-  uint8_t* sP = sQ + AT_Q_BYTES;
-  uint8_t* sK = sP + AT_P_BYTES;
+  uint8_t* sQ = smem;                              // AT_QT tiles
+  uint8_t* sP = sQ + AT_QT * AT_Q_BYTES;           // AT_QT tiles
+  uint8_t* sK = sP + AT_QT * AT_P_BYTES;
   uint8_t* sV = sK + AT_STAGES * AT_KV_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_STAGES * AT_KV_BYTES);
   uint64_t* q_full = bars;
@@ -208,28 +217,38 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* k_empty = k_full + AT_STAGES;
   uint64_t* v_full = k_empty + AT_STAGES;
   uint64_t* v_empty = v_full + AT_STAGES;
-  uint64_t* s_full = v_empty + AT_STAGES;
-  uint64_t* s_empty = s_full + 1;
-  uint64_t* p_full = s_empty + 1;
-  uint64_t* pv_full = p_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + 1);
+  uint64_t* s_full = v_empty + AT_STAGES;   // [AT_QT]
+  uint64_t* s_empty = s_full + AT_QT;
+  uint64_t* p_full = s_empty + AT_QT;
+  uint64_t* pv_full = p_full + AT_QT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + AT_QT);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x;  // heaviest (latest) query tiles first
+  const int qpair = gridDim.x - 1 - blockIdx.x;  // heaviest (latest) query tiles first
   const int h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qt * AT_BQ;
+  const int q0 = qpair * (AT_BQ * AT_QT);
 
-  // number of 64-key tiles this query tile needs
-  int kmax = p.Tk - 1;
-  if (p.block_causal) kmax = min(kmax, (p.q_pos0 + min(q0 + AT_BQ, p.Tq) - 1) | 7);
-  const int ntiles = kmax / AT_BK + 1;
+  // number of 64-key tiles each query tile needs (0 = tile lies beyond the sequence)
+  int nt[AT_QT];
+#pragma unroll
+  for (int t = 0; t < AT_QT; ++t) {
+    const int qs = q0 + t * AT_BQ;
+    if (qs >= p.Tq) {
+      nt[t] = 0;
+    } else {
+      int kmax = p.Tk - 1;
+      if (p.block_causal) kmax = min(kmax, (p.q_pos0 + min(qs + AT_BQ, p.Tq) - 1) | 7);
+      nt[t] = kmax / AT_BK + 1;
+    }
+  }
+  const int ntiles = max(nt[0], nt[AT_QT - 1]);
 
-  if (warp == 4 && lane == 0) {
+  if (warp == AT_SOFTMAX_WARPS && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
   }
-  if (warp == 5 && lane == 0) {
+  if (warp == AT_SOFTMAX_WARPS + 1 && lane == 0) {
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < AT_STAGES; ++s) {
       ptx::mbar_init(&k_full[s], 1);
@@ -237,13 +256,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       ptx::mbar_init(&v_full[s], 1);
       ptx::mbar_init(&v_empty[s], 1);
     }
-    ptx::mbar_init(s_full, 1);
-    ptx::mbar_init(s_empty, 4);
-    ptx::mbar_init(p_full, 4);
-    ptx::mbar_init(pv_full, 1);
+    for (int t = 0; t < AT_QT; ++t) {
+      ptx::mbar_init(&s_full[t], 1);
+      ptx::mbar_init(&s_empty[t], 4);
+      ptx::mbar_init(&p_full[t], 4);
+      ptx::mbar_init(&pv_full[t], 1);
+    }
     ptx::fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == AT_SOFTMAX_WARPS + 1) {
     ptx::tmem_alloc(tmem_slot, AT_TMEM_COLS);
     ptx::tmem_relinquish();
   }
@@ -251,71 +272,87 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_pv = tmem_base + AT_BK;
 
-  if (warp == 4) {
+  if (warp == AT_SOFTMAX_WARPS) {
     // ------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
-      ptx::mbar_expect_tx(q_full, AT_Q_BYTES);
-      ptx::tma_load_3d(sQ, &tmQ, q_full, p.q_col0 + h * AT_HD, q0, b);
+      ptx::mbar_expect_tx(q_full, AT_QT * AT_Q_BYTES);
+#pragma unroll
+      for (int t = 0; t < AT_QT; ++t) ptx::tma_load_3d(sQ + t * AT_Q_BYTES, &tmQ, q_full, h * AT_HD, q0 + t * AT_BQ, b);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < ntiles; ++j) {
         ptx::mbar_wait(&k_empty[stage], phase ^ 1);
         ptx::mbar_expect_tx(&k_full[stage], AT_KV_BYTES);
-        ptx::tma_load_3d(sK + stage * AT_KV_BYTES, &tmK, &k_full[stage], p.k_col0 + h * AT_HD, j * AT_BK, b);
+        ptx::tma_load_3d(sK + stage * AT_KV_BYTES, &tmK, &k_full[stage], h * AT_HD, j * AT_BK, b);
         ptx::mbar_wait(&v_empty[stage], phase ^ 1);
         ptx::mbar_expect_tx(&v_full[stage], AT_KV_BYTES);
-        ptx::tma_load_3d(sV + stage * AT_KV_BYTES, &tmV, &v_full[stage], p.v_col0 + h * AT_HD, j * AT_BK, b);
+        ptx::tma_load_3d(sV + stage * AT_KV_BYTES, &tmV, &v_full[stage], h * AT_HD, j * AT_BK, b);
         if (++stage == AT_STAGES) { stage = 0; phase ^= 1; }
       }
     }
     __syncwarp();
-  } else if (warp == 5) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == AT_SOFTMAX_WARPS + 1) {
+    // ------------------------------------------------------------ MMA issuer (both query tiles)
     if (ptx::elect_one()) {
       constexpr uint32_t idesc_s = ptx::make_idesc_f16(AT_BQ, AT_BK, 0, 0);   // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_pv = ptx::make_idesc_f16(AT_BQ, AT_HD, 0, 1);  // P (K-major) x V (MN-major)
-      const uint64_t dq = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sQ));
-      const uint64_t dp = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sP));
       ptx::mbar_wait(q_full, 0);
-      auto issue_pv = [&](int j) {  // O (+)= P_j V_j, accumulated in TMEM across all key tiles
+      auto issue_pv = [&](int t, int j) {  // O_t (+)= P_t,j V_j, accumulated in TMEM across all key tiles
         const int st = j % AT_STAGES;
-        ptx::mbar_wait(p_full, j & 1);
+        ptx::mbar_wait(&p_full[t], j & 1);
         ptx::mbar_wait(&v_full[st], (j / AT_STAGES) & 1);
         ptx::tc_fence_after();
         const uint32_t vaddr = ptx::smem_u32(sV + st * AT_KV_BYTES);
+        const uint64_t dp = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sP + t * AT_P_BYTES));
 #pragma unroll
         for (int k = 0; k < AT_BK / 16; ++k) {
           // 16 keys = 16 rows of 128 B: MN-major operand advances 2048 B per K step; P advances 32 B
           const uint64_t dv = ptx::make_desc_mnmajor_sw128(vaddr + k * 2048, 1024, 1024);
-          ptx::mma_f16_ss(tmem_pv, dp + 2 * k, dv, idesc_pv, (j | k) != 0 ? 1u : 0u);
+          ptx::mma_f16_ss(tmem_base + t * 128 + AT_BK, dp + 2 * k, dv, idesc_pv, (j | k) != 0 ? 1u : 0u);
         }
-        ptx::mma_commit(pv_full);
-        ptx::mma_commit(&v_empty[st]);
+        ptx::mma_commit(&pv_full[t]);
       };
       for (int j = 0; j < ntiles; ++j) {
         const int st = j % AT_STAGES;
         ptx::mbar_wait(&k_full[st], (j / AT_STAGES) & 1);
-        if (j > 0) ptx::mbar_wait(s_empty, (j - 1) & 1);
-        ptx::tc_fence_after();
         const uint64_t dk = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sK + st * AT_KV_BYTES));
 #pragma unroll
-        for (int k = 0; k < AT_HD / 16; ++k) ptx::mma_f16_ss(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        ptx::mma_commit(s_full);
+        for (int t = 0; t < AT_QT; ++t) {
+          if (j < nt[t]) {
+            if (j > 0) ptx::mbar_wait(&s_empty[t], (j - 1) & 1);
+            ptx::tc_fence_after();
+            const uint64_t dq = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sQ + t * AT_Q_BYTES));
+#pragma unroll
+            for (int k = 0; k < AT_HD / 16; ++k)
+              ptx::mma_f16_ss(tmem_base + t * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+            ptx::mma_commit(&s_full[t]);
+          }
+        }
         ptx::mma_commit(&k_empty[st]);
-        if (j > 0) issue_pv(j - 1);
+        if (j > 0) {
+#pragma unroll
+          for (int t = 0; t < AT_QT; ++t)
+            if (j - 1 < nt[t]) issue_pv(t, j - 1);
+          ptx::mma_commit(&v_empty[(j - 1) % AT_STAGES]);
+        }
       }
-      issue_pv(ntiles - 1);
+#pragma unroll
+      for (int t = 0; t < AT_QT; ++t)
+        if (ntiles - 1 < nt[t]) issue_pv(t, ntiles - 1);
+      ptx::mma_commit(&v_empty[(ntiles - 1) % AT_STAGES]);
     }
     __syncwarp();
   } else {
     // ------------------------------------------------------------ softmax / output (thread == query row)
-    const int r = threadIdx.x;  // 0..127 == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    const int qi = q0 + r;                 // row inside this item's query block
-    const int qabs = p.q_pos0 + qi;        // absolute position
+    const int t = warp >> 2;                       // query tile of this warpgroup
+    const int r = threadIdx.x & (AT_BQ - 1);       // row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tmem_s = tmem_base + t * 128;
+    const uint32_t tmem_o = tmem_s + AT_BK;
+    const int my_tiles = nt[t];
+    const int qi = q0 + t * AT_BQ + r;             // row inside this item's query block
+    const int qabs = p.q_pos0 + qi;                // absolute position
     int limit = p.Tk - 1;
     if (p.block_causal) limit = min(limit, qabs | 7);
     // Lazy rescaling: m_ref is the exponent base in use.  It only moves when a tile's row maximum exceeds it by
@@ -323,11 +360,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // the accumulator O can stay in TMEM and is touched by the softmax threads only on those rare tiles.
     constexpr float RESCALE_LOG2 = 8.0f;
     float m_ref = 0.f, l = 0.f;
-    const uint32_t prow_s = ptx::smem_u32(sP) + r * 128;
+    const uint32_t prow_s = ptx::smem_u32(sP + t * AT_P_BYTES) + r * 128;
     const int sw = r & 7;
+    const uint32_t a_s_full = ptx::smem_u32(&s_full[t]), a_s_empty = ptx::smem_u32(&s_empty[t]);
+    const uint32_t a_p_full = ptx::smem_u32(&p_full[t]), a_pv_full = ptx::smem_u32(&pv_full[t]);
 
-    for (int j = 0; j < ntiles; ++j) {
-      ptx::mbar_wait(s_full, j & 1);
+    for (int j = 0; j < my_tiles; ++j) {
+      ptx::mbar_wait(a_s_full, j & 1);
       ptx::tc_fence_after();
       uint32_t sa[32], sb[32];
       ptx::tmem_ld32(tmem_s + lane_off, sa);
@@ -335,7 +374,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(s_empty);
+      if (lane == 0) ptx::mbar_arrive(a_s_empty);
 
       const int lim = limit - j * AT_BK;  // columns c <= lim are visible
       if (lim < AT_BK - 1) {              // diagonal / last tile: mask (interior tiles skip this entirely)
@@ -360,28 +399,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const bool need = m_tile > m_ref + RESCALE_LOG2;
         if (__any_sync(0xffffffffu, need)) {
           // O must be quiescent: every P V issued so far has completed
-          ptx::mbar_wait(pv_full, (j - 1) & 1);
+          ptx::mbar_wait(a_pv_full, (j - 1) & 1);
           ptx::tc_fence_after();
           const float alpha = need ? fast_exp2(m_ref - m_tile) : 1.0f;
           if (need) m_ref = m_tile;
           l *= alpha;
 #pragma unroll 1
           for (int q4 = 0; q4 < 4; ++q4) {  // 16 columns at a time keeps the rare path's register footprint small
-            uint32_t t[16];
-            ptx::tmem_ld16(tmem_pv + lane_off + q4 * 16, t);
+            uint32_t tt[16];
+            ptx::tmem_ld16(tmem_o + lane_off + q4 * 16, tt);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 16; ++c) t[c] = __float_as_uint(__uint_as_float(t[c]) * alpha);
-            ptx::tmem_st16(tmem_pv + lane_off + q4 * 16, t);
+            for (int c = 0; c < 16; ++c) tt[c] = __float_as_uint(__uint_as_float(tt[c]) * alpha);
+            ptx::tmem_st16(tmem_o + lane_off + q4 * 16, tt);
           }
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
         }
       }
       // the single P buffer is free once P_{j-1} V_{j-1} has been consumed (issued a whole softmax period ago)
-      if (j > 0) ptx::mbar_wait(pv_full, (j - 1) & 1);
-      // p = 2^(s*scale - m_ref), converted to packed halves before the exponential (the result IS the fp16 P
-      // operand) and written straight to the K-major SWIZZLE_128B P tile: row r at r*128 B, chunk c at (c ^ (r&7))
+      if (j > 0) ptx::mbar_wait(a_pv_full, (j - 1) & 1);
+      // p = 2^(s*scale - m_ref) as packed halves, written straight to the K-major SWIZZLE_128B P tile:
+      // row r at r*128 B, 16-byte chunk c at (c ^ (r & 7))
       const float neg_m = -m_ref;
       __half2 acc[4];
 #pragma unroll
@@ -407,33 +446,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       ptx::fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(p_full);
+      if (lane == 0) ptx::mbar_arrive(a_p_full);
     }
-    ptx::mbar_wait(pv_full, (ntiles - 1) & 1);
-    ptx::tc_fence_after();
-    const float inv = 1.0f / l;
-    __half* op = p.out + b * p.o_batch_pitch + static_cast<long long>(qi) * p.o_row_pitch + h * AT_HD;
+    if (my_tiles > 0) {
+      ptx::mbar_wait(a_pv_full, (my_tiles - 1) & 1);
+      ptx::tc_fence_after();
+      const float inv = 1.0f / l;
+      __half* op = p.out + b * p.o_batch_pitch + static_cast<long long>(qi) * p.o_row_pitch + h * AT_HD;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t t[32];
-      ptx::tmem_ld32(tmem_pv + lane_off + half * 32, t);
-      ptx::tmem_ld_wait();
-      if (qi < p.Tq) {
+      for (int half = 0; half < 2; ++half) {
+        uint32_t tt[32];
+        ptx::tmem_ld32(tmem_o + lane_off + half * 32, tt);
+        ptx::tmem_ld_wait();
+        if (qi < p.Tq) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 8) {
-          uint4 q;
-          q.x = pack_half2(__uint_as_float(t[c + 0]) * inv, __uint_as_float(t[c + 1]) * inv);
-          q.y = pack_half2(__uint_as_float(t[c + 2]) * inv, __uint_as_float(t[c + 3]) * inv);
-          q.z = pack_half2(__uint_as_float(t[c + 4]) * inv, __uint_as_float(t[c + 5]) * inv);
-          q.w = pack_half2(__uint_as_float(t[c + 6]) * inv, __uint_as_float(t[c + 7]) * inv);
-          *reinterpret_cast<uint4*>(op + half * 32 + c) = q;
+          for (int c = 0; c < 32; c += 8) {
+            uint4 q;
+            q.x = pack_half2(__uint_as_float(tt[c + 0]) * inv, __uint_as_float(tt[c + 1]) * inv);
+            q.y = pack_half2(__uint_as_float(tt[c + 2]) * inv, __uint_as_float(tt[c + 3]) * inv);
+            q.z = pack_half2(__uint_as_float(tt[c + 4]) * inv, __uint_as_float(tt[c + 5]) * inv);
+            q.w = pack_half2(__uint_as_float(tt[c + 6]) * inv, __uint_as_float(tt[c + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + half * 32 + c) = q;
+          }
         }
       }
+      ptx::tc_fence_before();
     }
-    ptx::tc_fence_before();
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == AT_SOFTMAX_WARPS + 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, AT_TMEM_COLS);
   }
@@ -492,8 +533,7 @@ int attention_tc(const AttnDesc& a, cudaStream_t stream) {
   p.out = a.out;
   p.o_row_pitch = a.o_row_pitch;
   p.o_batch_pitch = a.o_batch_pitch;
-  p.q_col0 = p.k_col0 = p.v_col0 = 0;
-  dim3 grid((a.Tq + AT_BQ - 1) / AT_BQ, a.H, a.B);
+  dim3 grid((a.Tq + AT_BQ * AT_QT - 1) / (AT_BQ * AT_QT), a.H, a.B);
   attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;

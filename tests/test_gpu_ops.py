@@ -146,6 +146,10 @@ ATTN_CASES = [
     (3, 2, 64, 8, 808, 800, 0),
     (1, 2, 64, 128, 128, 0, 1),
     (1, 1, 64, 64, 320, 256, 0),
+    (1, 2, 64, 200, 200, 0, 1),
+    (2, 1, 64, 264, 264, 0, 1),
+    (1, 1, 64, 136, 392, 256, 0),
+    (1, 3, 64, 520, 520, 0, 1),
 ]
 
 
