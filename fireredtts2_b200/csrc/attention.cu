@@ -39,6 +39,10 @@ __global__ void __launch_bounds__(128) attention_warp_kernel(AttnDesc a) {
   const int h = static_cast<int>((wid / nblk) % a.H);
   const int b = static_cast<int>(wid / (static_cast<long long>(nblk) * a.H));
   const float scale_log2 = a.scale * 1.4426950408889634f;
+  if (a.pos_ptr != nullptr) {  // streaming inside a captured graph: position comes from HBM
+    a.q_pos0 = *a.pos_ptr;
+    a.Tk = a.q_pos0 + a.Tq;
+  }
 
   const __half* qp = a.q + b * a.q_batch_pitch + static_cast<long long>(qb * 8) * a.q_row_pitch + h * HD;
   for (int e = lane; e < 8 * HD; e += 32) {

@@ -81,6 +81,8 @@ struct GemmDesc {
   int64_t ld32;
   __half* out16;          // fp16 output or null
   int64_t ld16;
+  const int* out_row_off; // optional device int: added to every output row index at run time (streaming KV append
+                          // inside a captured CUDA graph: the write position lives in HBM, not in a kernel argument)
 };
 
 int gemm_tc(const GemmDesc& g, cudaStream_t stream);    // tcgen05 / TMEM / TMA path (product)
@@ -100,6 +102,7 @@ struct AttnDesc {
   int q_pos0;        // absolute position of query row 0 (== Tk - Tq in streaming)
   int block_causal;  // 1: key j visible iff j <= ((q_pos0+i) | 7); 0: all Tk keys visible
   float scale;
+  const int* pos_ptr; // optional device int (attention_warp): q_pos0 = *pos_ptr, Tk = *pos_ptr + Tq at run time
 };
 int attention_warp(const AttnDesc& a, cudaStream_t stream);  // CUDA-core, one warp per 8-query block
 int attention_tc(const AttnDesc& a, cudaStream_t stream);    // tcgen05 flash attention (hd == 64)
@@ -124,6 +127,7 @@ struct OlaDesc {
   int64_t audio_pitch;
   int B, T, n_fft, hop;
   int first, last;       // streaming flags; offline == first && last
+  const int* ctrl;       // optional device {frames consumed so far, last flag}: overrides first/last at run time
 };
 int istft_overlap_add(const OlaDesc& d, cudaStream_t stream);
 int istft_update_tail(const float* frames, int64_t frames_batch_pitch, float* tail, int B, int T, int n_fft,

@@ -23,6 +23,7 @@ namespace {
 constexpr int DBG_TAPS = 1;       // record intermediates (frt2_get_tap)
 constexpr int DBG_GEMM_REF = 2;   // route every GEMM through the SIMT check kernel (tests only)
 constexpr int DBG_ATTN_WARP = 4;  // route attention through the warp kernel (tests only)
+constexpr int DBG_NO_GRAPH = 8;   // streaming: launch kernel by kernel instead of replaying the captured CUDA graph
 
 struct HostTensor {
   std::vector<int64_t> shape;
@@ -52,6 +53,27 @@ __global__ void half_to_float_kernel(const __half* __restrict__ src, long long l
   const int c = static_cast<int>(i - r * cols);
   dst[i] = __half2float(src[r * ld + c]);
 }
+
+// strided int32/int64 tokens -> contiguous int32 staging (B,nq,L) + the `last` flag of this call into the control
+// block; out-of-range values are flagged here (an int64 could alias after narrowing) and stored as -1
+template <typename IdxT>
+__global__ void stage_tokens_kernel(const IdxT* __restrict__ tokens, long long sB, long long sQ, long long sL, int B,
+                                    int nq, int L, int K, int* __restrict__ stage, int* ctrl, int last,
+                                    unsigned int* err_word) {
+  const int n = B * nq * L;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) ctrl[1] = last;
+  if (i >= n) return;
+  const int l = i % L, q = (i / L) % nq, b = i / (L * nq);
+  const long long raw = static_cast<long long>(tokens[b * sB + q * sQ + l * sL]);
+  int v = static_cast<int>(raw);
+  if (raw < 0 || raw >= K) {
+    atomicOr(err_word, DEV_ERR_INDEX_OOR);
+    v = -1;
+  }
+  stage[i] = v;
+}
+__global__ void advance_ctrl_kernel(int* ctrl, int frames) { ctrl[0] += frames; }
 
 struct ShiftEntry {
   __half* p;
@@ -308,7 +330,9 @@ struct Handle {
   int tap_f16(const char* name, const __half* src, int64_t ld, int64_t rows, int cols, cudaStream_t st);
 
   int pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B, int nq_in, int L,
-               const int32_t* lengths, float* audio, int64_t audio_pitch, Stream* s, int last, cudaStream_t st);
+               const int32_t* lengths, float* audio, int64_t audio_pitch, Stream* s, int last, cudaStream_t st,
+               bool graph_mode = false);
+  size_t ws_bytes_for(int B, int L) const;
 };
 
 struct Stream {
@@ -320,6 +344,13 @@ struct Stream {
   int conv_rpt[11] = {4, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8};  // rows per token
   std::vector<__half*> kv;  // per layer (B, Tmax, 2E)
   float* tail = nullptr;    // (B, 3, n_fft)
+  int* ctrl = nullptr;      // device {frames consumed, last flag, -, -}: read by the kernels of the captured step
+  int* tok_stage = nullptr; // (B, nq, chunk_cap) int32 contiguous
+  float* audio_stage = nullptr;  // (B, audio_stage_pitch)
+  int64_t audio_stage_pitch = 0;
+  cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
+  struct GraphRec { cudaGraphExec_t exec; const uint8_t* ws; long long kernels; };
+  std::map<std::pair<int, int>, GraphRec> graphs;  // (Lc, nq) -> captured step
 
   int64_t conv_pitch(int i) const { return static_cast<int64_t>(conv_hist[i] + conv_rpt[i] * chunk_cap) * h->E; }
   int64_t kv_pitch() const { return static_cast<int64_t>(max_tokens) * 8 * 2 * h->E; }
@@ -334,6 +365,15 @@ struct Stream {
     free_conv();
     for (auto p : kv) cudaFree(p);
     if (tail) cudaFree(tail);
+    if (ctrl) cudaFree(ctrl);
+    if (tok_stage) cudaFree(tok_stage);
+    if (audio_stage) cudaFree(audio_stage);
+    drop_graphs();
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+  }
+  void drop_graphs() {
+    for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
+    graphs.clear();
   }
   int ensure_chunk_cap(int Lc, cudaStream_t st);
   int reset();
@@ -603,8 +643,22 @@ int Handle::tap_f16(const char* name, const __half* src, int64_t ld, int64_t row
 // causal left padding comes from TMA out-of-bounds zero fill; attention is block-causal over the whole item.
 // Streaming: every conv input buffer is [history | chunk] owned by the stream, K/V are appended to the HBM
 // state and attention runs unmasked over state ++ chunk.
+size_t Handle::ws_bytes_for(int B, int L) const {
+  const size_t R = static_cast<size_t>(B) * L, M = 8 * R;
+  const size_t sizes[] = {R * rd * 4, R * rd * 2, R * E * 2, R * 4 * E * 2, R * 4 * E * 2, M * E * 2, M * E * 2,
+                          M * E * 4, M * E * 4, M * E * 2, M * 3 * E * 2, M * E * 2, M * 4 * E * 2,
+                          M * spec_ld * 2, M * n_fft * 4};
+  size_t off = 0;
+  for (size_t b : sizes) off = align_up(off + b, 1024);
+  return off;
+}
+
+// graph_mode (streaming only): tokens / audio are the stream's staging buffers and every position-dependent quantity
+// (K/V append row, attention length, first/last of the iSTFT) is read from the stream's control block in HBM, so the
+// recorded launch sequence is identical for every token and can be replayed as one CUDA graph.
 int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B, int nq_in, int L,
-                     const int32_t* lengths, float* audio, int64_t audio_pitch, Stream* s, int last, cudaStream_t st) {
+                     const int32_t* lengths, float* audio, int64_t audio_pitch, Stream* s, int last, cudaStream_t st,
+                     bool graph_mode) {
   const int64_t R = static_cast<int64_t>(B) * L;  // tokens
   const int T50 = 4 * L, T = 8 * L;
   const int64_t M = static_cast<int64_t>(B) * T;  // 100 Hz frames
@@ -739,11 +793,14 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
       g.A = n16; g.a_row_pitch = E; g.a_batch_pitch = xp; g.rows_a = T; g.batches = B; g.Kc = E; g.ntaps = 1;
       g.row_shift = 0; g.W = w.w_qkv + static_cast<int64_t>(E) * E; g.N = 2 * E; g.rows_out = T; g.alpha = 1.0f;
       g.bias = w.b_qkv + E; g.act = ACT_NONE; g.resid = nullptr; g.out32 = nullptr; g.ld32 = 0; g.pitch32 = 0;
-      g.out16 = s->kv[i] + static_cast<int64_t>(pos) * 2 * E; g.ld16 = 2 * E; g.pitch16 = s->kv_pitch();
+      g.ld16 = 2 * E; g.pitch16 = s->kv_pitch();
+      if (graph_mode) { g.out16 = s->kv[i]; g.out_row_off = s->ctrl; }
+      else            { g.out16 = s->kv[i] + static_cast<int64_t>(pos) * 2 * E; }
       FRT2_TRY(run_gemm(g, st));
       a.q = qkv16; a.q_row_pitch = E; a.q_batch_pitch = xp;
       a.k = s->kv[i]; a.v = s->kv[i] + E; a.kv_row_pitch = 2 * E; a.kv_batch_pitch = s->kv_pitch();
       a.Tk = pos + T; a.q_pos0 = pos; a.block_causal = 0;
+      if (graph_mode) a.pos_ptr = s->ctrl;
     }
     FRT2_TRY(run_attn(a, st));
     FRT2_TRY(flat_gemm(o16, M, E, w.w_o, E, w.b_o, ACT_NONE, x32, x32, nullptr, 0));
@@ -773,6 +830,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   od.n_fft = n_fft; od.hop = hop;
   if (streaming) {
     od.tail = s->tail; od.first = (s->n_tokens == 0); od.last = last;
+    if (graph_mode) od.ctrl = s->ctrl;
   } else {
     od.tail = nullptr; od.first = 1; od.last = 1;
   }
@@ -788,6 +846,8 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     tb.n = 11;
     for (int i = 0; i < 11; ++i) tb.e[i] = {s->conv[i], s->conv_hist[i], s->conv_rpt[i] * L, s->conv_pitch(i)};
     shift_history_kernel<<<dim3(8, 11), 256, 0, st>>>(tb, E, B);
+    advance_ctrl_kernel<<<1, 1, 0, st>>>(s->ctrl, T);
+    launches += 1;
     FRT2_CUDA_OK(cudaGetLastError());
   }
   tap_B = B;
@@ -806,6 +866,13 @@ int Stream::ensure_chunk_cap(int Lc, cudaStream_t st) {
     old_pitch[i] = conv_pitch(i);
   }
   chunk_cap = Lc;
+  drop_graphs();
+  if (tok_stage) cudaFree(tok_stage);
+  if (audio_stage) cudaFree(audio_stage);
+  audio_stage_pitch = static_cast<int64_t>(8) * h->hop * Lc + (h->n_fft - h->hop) / 2;
+  audio_stage_pitch = (audio_stage_pitch + 3) / 4 * 4;
+  FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&tok_stage), static_cast<size_t>(B) * h->nq * Lc * 4));
+  FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&audio_stage), static_cast<size_t>(B) * audio_stage_pitch * 4));
   for (int i = 0; i < 11; ++i) {
     const size_t bytes = static_cast<size_t>(B) * conv_pitch(i) * 2;
     FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&conv[i]), bytes));
@@ -824,6 +891,7 @@ int Stream::ensure_chunk_cap(int Lc, cudaStream_t st) {
 
 int Stream::reset() {
   n_tokens = 0;
+  FRT2_CUDA_OK(cudaMemset(ctrl, 0, 4 * sizeof(int)));
   for (int i = 0; i < 11; ++i)
     if (conv[i]) FRT2_CUDA_OK(cudaMemset(conv[i], 0, static_cast<size_t>(B) * conv_pitch(i) * 2));
   FRT2_CUDA_OK(cudaMemset(tail, 0, static_cast<size_t>(B) * 3 * h->n_fft * 4));
@@ -954,7 +1022,9 @@ int frt2_stream_create(frt2_handle* hh, int B, int max_tokens, frt2_stream** out
       return fail(FRT2_ERR_CUDA);
     }
   }
-  if (cudaMalloc(reinterpret_cast<void**>(&s.tail), static_cast<size_t>(B) * 3 * h.n_fft * 4) != cudaSuccess) {
+  if (cudaMalloc(reinterpret_cast<void**>(&s.tail), static_cast<size_t>(B) * 3 * h.n_fft * 4) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&s.ctrl), 4 * sizeof(int)) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&s.cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("frt2_stream_create: out of memory");
     return fail(FRT2_ERR_CUDA);
   }
@@ -992,7 +1062,57 @@ int frt2_decode_chunk(frt2_handle* hh, frt2_stream* ss, const void* tokens, int 
   FRT2_CUDA_OK(cudaSetDevice(h.device));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   FRT2_TRY(s.ensure_chunk_cap(Lc, st));
-  FRT2_TRY(h.pipeline(tokens, idx_bytes, sB, sQ, sL, s.B, nq, Lc, nullptr, audio, audio_pitch, &s, last, st));
+  // Short chunks (the per-token latency path) replay one captured CUDA graph per call; anything that needs host-side
+  // parameters per kernel (taps, per-kernel event timing, the tcgen05 attention for long chunks) runs kernel by kernel.
+  const bool graph_mode = !(h.debug & (DBG_NO_GRAPH | DBG_TAPS)) && !h.profile && 8 * Lc < 32;
+  if (!graph_mode) {
+    FRT2_TRY(h.pipeline(tokens, idx_bytes, sB, sQ, sL, s.B, nq, Lc, nullptr, audio, audio_pitch, &s, last, st, false));
+  } else {
+    const int ntok = s.B * nq * Lc;
+    if (idx_bytes == 4) {
+      stage_tokens_kernel<int><<<(ntok + 127) / 128, 128, 0, st>>>(static_cast<const int*>(tokens), sB, sQ, sL, s.B, nq,
+                                                                    Lc, h.K, s.tok_stage, s.ctrl, last, h.err_word);
+    } else {
+      stage_tokens_kernel<long long><<<(ntok + 127) / 128, 128, 0, st>>>(static_cast<const long long*>(tokens), sB, sQ,
+                                                                          sL, s.B, nq, Lc, h.K, s.tok_stage, s.ctrl,
+                                                                          last, h.err_word);
+    }
+    FRT2_CUDA_OK(cudaGetLastError());
+    FRT2_TRY(h.ensure_ws(h.ws_bytes_for(s.B, Lc)));  // before capture: no allocation may happen while recording
+    auto key = std::make_pair(Lc, nq);
+    auto it = s.graphs.find(key);
+    if (it != s.graphs.end() && it->second.ws != h.ws) {  // workspace moved since the capture
+      cudaGraphExecDestroy(it->second.exec);
+      s.graphs.erase(it);
+      it = s.graphs.end();
+    }
+    if (it == s.graphs.end()) {
+      const long long before = h.launches;
+      FRT2_CUDA_OK(cudaStreamBeginCapture(s.cap_stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = h.pipeline(s.tok_stage, 4, static_cast<int64_t>(nq) * Lc, Lc, 1, s.B, nq, Lc, nullptr, s.audio_stage,
+                                s.audio_stage_pitch, &s, last, s.cap_stream, true);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(s.cap_stream, &graph);
+      if (rc != FRT2_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+      }
+      FRT2_CUDA_OK(ce);
+      Stream::GraphRec rec{};
+      rec.ws = h.ws;
+      rec.kernels = h.launches - before;
+      h.launches = before;
+      const cudaError_t ie = cudaGraphInstantiate(&rec.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      FRT2_CUDA_OK(ie);
+      it = s.graphs.emplace(key, rec).first;
+    }
+    FRT2_CUDA_OK(cudaGraphLaunch(it->second.exec, st));
+    h.launches += it->second.kernels + 1;
+    FRT2_CUDA_OK(cudaMemcpy2DAsync(audio, static_cast<size_t>(audio_pitch) * 4, s.audio_stage,
+                                   static_cast<size_t>(s.audio_stage_pitch) * 4, static_cast<size_t>(n) * 4, s.B,
+                                   cudaMemcpyDeviceToDevice, st));
+  }
   s.n_tokens += Lc;
   if (n_samples) *n_samples = n;
   return FRT2_OK;
@@ -1050,6 +1170,9 @@ int frt2_import_state(frt2_handle* hh, frt2_stream* ss, int n_tokens, const floa
     transpose_tail_kernel<<<(B * 3 * h.n_fft + 255) / 256, 256, 0, st>>>(is_cache, s.tail, B, h.n_fft, 0);
   FRT2_CUDA_OK(cudaGetLastError());
   s.n_tokens = n_tokens;
+  const int ctrl_h[4] = {8 * n_tokens, 0, 0, 0};
+  FRT2_CUDA_OK(cudaMemcpyAsync(s.ctrl, ctrl_h, sizeof(ctrl_h), cudaMemcpyHostToDevice, st));
+  FRT2_CUDA_OK(cudaStreamSynchronize(st));
   return FRT2_OK;
 }
 

@@ -62,6 +62,7 @@ struct GemmKParams {
   int vec32;  // 16-byte vector access legal on out32 / resid rows (direct mode)
   int vec16;  // ... on out16 rows
   int store_mode;
+  const int* row_off_ptr;
 };
 
 template <int BN>
@@ -305,8 +306,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row0 = (mb % p.tiles_m) * BM + wq * 32;   // first row of this warp's 32-row slab
       const int row = row0 + lane;
       const bool valid_row = row < p.rows_out;
-      const long long off32 = static_cast<long long>(b) * p.pitch32 + static_cast<long long>(row) * p.ld32;
-      const long long off16 = static_cast<long long>(b) * p.pitch16 + static_cast<long long>(row) * p.ld16;
+      const int roff = (p.row_off_ptr != nullptr) ? __ldg(p.row_off_ptr) : 0;  // direct-store mode only
+      const long long off32 = static_cast<long long>(b) * p.pitch32 + static_cast<long long>(row + roff) * p.ld32;
+      const long long off16 = static_cast<long long>(b) * p.pitch16 + static_cast<long long>(row + roff) * p.ld16;
       const int ncol0 = n_idx * BN + hsel * (BN / 2);     // first column owned by this warp
       const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN + hsel * (BN / 2)) + tmem_lane;
 
@@ -552,9 +554,12 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
 
   // output through TMA stores whenever the layout allows it (16-byte aligned base / pitches, single output)
   p.store_mode = STORE_DIRECT;
+  p.row_off_ptr = g.out_row_off;
   tmC = tmA;
   const uint64_t batch_rows = static_cast<uint64_t>(g.batches);
-  if (g.out16 != nullptr && g.out32 == nullptr && g.resid == nullptr && p.vec16) {
+  if (g.out_row_off != nullptr) {
+    // run-time row offset: plain predicated stores (only used by the tiny streaming K/V append)
+  } else if (g.out16 != nullptr && g.out32 == nullptr && g.resid == nullptr && p.vec16) {
     uint64_t dims[3] = {static_cast<uint64_t>(g.N), static_cast<uint64_t>(g.rows_out), batch_rows};
     uint64_t strides[2] = {static_cast<uint64_t>(g.ld16) * 2,
                            static_cast<uint64_t>(g.batches > 1 ? g.pitch16 : g.ld16 * g.rows_out) * 2};

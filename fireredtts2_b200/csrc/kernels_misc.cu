@@ -193,6 +193,13 @@ int layer_norm_rows(const float* x, int64_t ldx, int rows, int C, const float* g
 __global__ void __launch_bounds__(256) overlap_add_kernel(OlaDesc d, int ntail, int start, int n_out_full) {
   const int b = blockIdx.y;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d.ctrl != nullptr) {  // streaming inside a captured graph: first / last come from HBM
+    const int first = (d.ctrl[0] == 0), last = d.ctrl[1];
+    const int pad = (d.n_fft - d.hop) / 2;
+    ntail = first ? 0 : (d.n_fft / d.hop - 1);
+    start = first ? pad : (d.n_fft - d.hop);
+    n_out_full = (ntail + d.T - 1) * d.hop + d.n_fft - start - (last ? pad : (d.n_fft - d.hop));
+  }
   if (n >= n_out_full) return;
   int TF = ntail + d.T;
   int n_out = n_out_full;
@@ -242,7 +249,8 @@ int istft_overlap_add(const OlaDesc& d, cudaStream_t stream) {
   const int TF = ntail + d.T;
   const int full = (TF - 1) * d.hop + d.n_fft;
   const int start = d.first ? pad : (d.n_fft - d.hop);
-  const int n_out = full - start - (d.last ? pad : (d.n_fft - d.hop));
+  int n_out = full - start - (d.last ? pad : (d.n_fft - d.hop));
+  if (d.ctrl != nullptr) n_out = d.T * d.hop + pad;  // upper bound over first/last combinations
   if (n_out <= 0) return FRT2_OK;
   dim3 grid((n_out + 255) / 256, d.B);
   overlap_add_kernel<<<grid, 256, 0, stream>>>(d, ntail, start, n_out);
@@ -297,8 +305,9 @@ __global__ void __launch_bounds__(128) gemm_ref_kernel(GemmDesc g) {
     v0 = mag * c;
     v1 = mag * s;
   }
-  const long long o32 = static_cast<long long>(b) * g.pitch32 + static_cast<long long>(m) * g.ld32 + n;
-  const long long o16 = static_cast<long long>(b) * g.pitch16 + static_cast<long long>(m) * g.ld16 + n;
+  const int roff = (g.out_row_off != nullptr) ? *g.out_row_off : 0;
+  const long long o32 = static_cast<long long>(b) * g.pitch32 + static_cast<long long>(m + roff) * g.ld32 + n;
+  const long long o16 = static_cast<long long>(b) * g.pitch16 + static_cast<long long>(m + roff) * g.ld16 + n;
   if (g.resid != nullptr) {
     v0 += g.resid[o32];
     if (has2) v1 += g.resid[o32 + 1];
