@@ -12,11 +12,13 @@ FRT2_OK = 0
 ERR_BAD_ARG, ERR_BAD_DTYPE, ERR_INDEX_OOR, ERR_STATE_OVERFLOW, ERR_CUDA, ERR_MISSING_TENSOR, ERR_NOT_FINALIZED = \
     -1, -2, -3, -4, -5, -6, -7
 
-DBG_TAPS, DBG_GEMM_REF, DBG_ATTN_WARP, DBG_NO_GRAPH = 1, 2, 4, 8
+DBG_TAPS, DBG_GEMM_REF, DBG_ATTN_WARP, DBG_NO_GRAPH, DBG_NO_SKINNY = 1, 2, 4, 8, 16
 ACT_NONE, ACT_GELU, ACT_POLAR = 0, 1, 2
-PROF_GEMM, PROF_ATTN_TC, PROF_ATTN_WARP, PROF_LAYER_NORM, PROF_RVQ, PROF_OLA, PROF_ALL = 0, 1, 2, 3, 4, 5, -1
+PROF_GEMM, PROF_ATTN_TC, PROF_ATTN_WARP, PROF_LAYER_NORM, PROF_RVQ, PROF_OLA, PROF_GEMM_SKINNY, PROF_ALL = \
+    0, 1, 2, 3, 4, 5, 6, -1
 PROF_NAMES = {PROF_GEMM: "gemm_tc", PROF_ATTN_TC: "attention_tc", PROF_ATTN_WARP: "attention_warp",
-              PROF_LAYER_NORM: "layer_norm", PROF_RVQ: "rvq_gather_sum", PROF_OLA: "overlap_add"}
+              PROF_LAYER_NORM: "layer_norm", PROF_RVQ: "rvq_gather_sum", PROF_OLA: "overlap_add",
+              PROF_GEMM_SKINNY: "gemm_skinny"}
 
 
 class Frt2Config(C.Structure):

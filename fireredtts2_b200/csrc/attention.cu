@@ -27,13 +27,20 @@ namespace frt2 {
 // =====================================================================================================
 namespace {
 
-template <int HD>
-__global__ void __launch_bounds__(128) attention_warp_kernel(AttnDesc a) {
+// NSPLIT == 1: four independent 8-query blocks per CTA (one warp each).  NSPLIT > 1 (streaming step, few queries and
+// a long KV state): the NSPLIT warps of a CTA share ONE query block, take interleaved 32-key chunks and merge their
+// partial (max, sum, accumulator) through shared memory — split-KV without a second kernel.
+template <int HD, int NSPLIT>
+__global__ void __launch_bounds__(NSPLIT == 1 ? 128 : NSPLIT * 32) attention_warp_kernel(AttnDesc a) {
   constexpr int DPL = HD / 32;  // output dims per lane
-  __shared__ float sq[4][8][HD];
+  constexpr int QW = (NSPLIT == 1) ? 4 : 1;   // query blocks per CTA
+  __shared__ float sq[QW][8][HD];
+  __shared__ float s_part[NSPLIT == 1 ? 1 : NSPLIT][8][HD + 2];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = a.Tq >> 3;
-  const long long wid = static_cast<long long>(blockIdx.x) * 4 + warp;
+  const int qslot = (NSPLIT == 1) ? warp : 0;
+  const int split = (NSPLIT == 1) ? 0 : warp;
+  const long long wid = (NSPLIT == 1) ? static_cast<long long>(blockIdx.x) * 4 + warp : static_cast<long long>(blockIdx.x);
   if (wid >= static_cast<long long>(a.B) * a.H * nblk) return;
   const int qb = static_cast<int>(wid % nblk);
   const int h = static_cast<int>((wid / nblk) % a.H);
@@ -45,11 +52,19 @@ __global__ void __launch_bounds__(128) attention_warp_kernel(AttnDesc a) {
   }
 
   const __half* qp = a.q + b * a.q_batch_pitch + static_cast<long long>(qb * 8) * a.q_row_pitch + h * HD;
-  for (int e = lane; e < 8 * HD; e += 32) {
-    const int r = e / HD, d = e - r * HD;
-    sq[warp][r][d] = __half2float(qp[r * a.q_row_pitch + d]) * scale_log2;
+  if (NSPLIT == 1) {
+    for (int e = lane; e < 8 * HD; e += 32) {
+      const int r = e / HD, d = e - r * HD;
+      sq[qslot][r][d] = __half2float(qp[r * a.q_row_pitch + d]) * scale_log2;
+    }
+    __syncwarp();
+  } else {
+    for (int e = threadIdx.x; e < 8 * HD; e += NSPLIT * 32) {
+      const int r = e / HD, d = e - r * HD;
+      sq[0][r][d] = __half2float(qp[r * a.q_row_pitch + d]) * scale_log2;
+    }
+    __syncthreads();
   }
-  __syncwarp();
 
   int kend = a.Tk - 1;
   if (a.block_causal) kend = min(kend, (a.q_pos0 + qb * 8) | 7);
@@ -64,7 +79,7 @@ __global__ void __launch_bounds__(128) attention_warp_kernel(AttnDesc a) {
 #pragma unroll
     for (int i = 0; i < DPL; ++i) acc[r][i] = 0.f;
   }
-  for (int j0 = 0; j0 <= kend; j0 += 32) {
+  for (int j0 = split * 32; j0 <= kend; j0 += NSPLIT * 32) {
     const int j = j0 + lane;
     const bool valid = j <= kend;
     float s[8];
@@ -85,8 +100,8 @@ __global__ void __launch_bounds__(128) attention_warp_kernel(AttnDesc a) {
         }
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
-          const float4 q0 = *reinterpret_cast<const float4*>(&sq[warp][r][c * 8]);
-          const float4 q1 = *reinterpret_cast<const float4*>(&sq[warp][r][c * 8 + 4]);
+          const float4 q0 = *reinterpret_cast<const float4*>(&sq[qslot][r][c * 8]);
+          const float4 q1 = *reinterpret_cast<const float4*>(&sq[qslot][r][c * 8 + 4]);
           s[r] += q0.x * kf[0] + q0.y * kf[1] + q0.z * kf[2] + q0.w * kf[3] + q1.x * kf[4] + q1.y * kf[5] +
                   q1.z * kf[6] + q1.w * kf[7];
         }
@@ -131,11 +146,42 @@ __global__ void __launch_bounds__(128) attention_warp_kernel(AttnDesc a) {
     }
   }
   __half* op = a.out + b * a.o_batch_pitch + static_cast<long long>(qb * 8) * a.o_row_pitch + h * HD + lane * DPL;
+  if (NSPLIT == 1) {
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const float inv = 1.0f / l[r];
+    for (int r = 0; r < 8; ++r) {
+      const float inv = 1.0f / l[r];
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) op[r * a.o_row_pitch + i] = __float2half_rn(acc[r][i] * inv);
+      for (int i = 0; i < DPL; ++i) op[r * a.o_row_pitch + i] = __float2half_rn(acc[r][i] * inv);
+    }
+  } else {
+    // merge the NSPLIT partial softmax states: out = sum_w acc_w 2^(m_w - M) / sum_w l_w 2^(m_w - M)
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) s_part[split][r][lane * DPL + i] = acc[r][i];
+      if (lane == 0) {
+        s_part[split][r][HD] = m[r];
+        s_part[split][r][HD + 1] = l[r];
+      }
+    }
+    __syncthreads();
+    if (warp < 8) {
+      const int r = warp;
+      float M = -CUDART_INF_F;
+      for (int w = 0; w < NSPLIT; ++w) M = fmaxf(M, s_part[w][r][HD]);
+      float L = 0.f, o[DPL];
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) o[i] = 0.f;
+      for (int w = 0; w < NSPLIT; ++w) {
+        const float sc = exp2f(s_part[w][r][HD] - M);   // 0 for warps that saw no key (m = -inf)
+        L += s_part[w][r][HD + 1] * sc;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) o[i] += s_part[w][r][lane * DPL + i] * sc;
+      }
+      const float inv = 1.0f / L;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) op[r * a.o_row_pitch + i] = __float2half_rn(o[i] * inv);
+    }
   }
 }
 
@@ -146,14 +192,21 @@ int attention_warp(const AttnDesc& a, cudaStream_t stream) {
   FRT2_REQUIRE(a.kv_row_pitch % 8 == 0, FRT2_ERR_BAD_ARG, "attention: K/V row pitch must be a multiple of 8");
   const long long warps = static_cast<long long>(a.B) * a.H * (a.Tq / 8);
   if (warps == 0) return FRT2_OK;
+  constexpr int NS = 16;
+  // few query blocks (the streaming step): 16 warps per block split the KV state; otherwise one warp per block
+  const bool split = warps <= 1024 && a.hd == 64;
   const unsigned grid = static_cast<unsigned>((warps + 3) / 4);
-  switch (a.hd) {
-    case 32: attention_warp_kernel<32><<<grid, 128, 0, stream>>>(a); break;
-    case 64: attention_warp_kernel<64><<<grid, 128, 0, stream>>>(a); break;
-    case 128: attention_warp_kernel<128><<<grid, 128, 0, stream>>>(a); break;
-    default:
-      set_error("attention: head_dim must be 32, 64 or 128");
-      return FRT2_ERR_BAD_ARG;
+  if (split) {
+    attention_warp_kernel<64, NS><<<static_cast<unsigned>(warps), NS * 32, 0, stream>>>(a);
+  } else {
+    switch (a.hd) {
+      case 32: attention_warp_kernel<32, 1><<<grid, 128, 0, stream>>>(a); break;
+      case 64: attention_warp_kernel<64, 1><<<grid, 128, 0, stream>>>(a); break;
+      case 128: attention_warp_kernel<128, 1><<<grid, 128, 0, stream>>>(a); break;
+      default:
+        set_error("attention: head_dim must be 32, 64 or 128");
+        return FRT2_ERR_BAD_ARG;
+    }
   }
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;

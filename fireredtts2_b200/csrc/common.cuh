@@ -88,6 +88,9 @@ struct GemmDesc {
 int gemm_tc(const GemmDesc& g, cudaStream_t stream);    // tcgen05 / TMEM / TMA path (product)
 int gemm_ref(const GemmDesc& g, cudaStream_t stream);   // plain SIMT fp32-accumulate check kernel (tests only)
 int gemm_tc_init();                                      // resolves cuTensorMapEncodeTiled, sets smem attrs
+int gemm_skinny(const GemmDesc& g, cudaStream_t stream); // <= 16 rows in total: weight-streaming CUDA-core kernel
+bool gemm_skinny_applicable(const GemmDesc& g);
+int gemm_skinny_init();
 
 // ---- attention ----
 struct AttnDesc {

@@ -23,6 +23,7 @@ namespace {
 constexpr int DBG_TAPS = 1;       // record intermediates (frt2_get_tap)
 constexpr int DBG_GEMM_REF = 2;   // route every GEMM through the SIMT check kernel (tests only)
 constexpr int DBG_ATTN_WARP = 4;  // route attention through the warp kernel (tests only)
+constexpr int DBG_NO_SKINNY = 16; // streaming: keep the tcgen05 GEMM even for <= 16 rows
 constexpr int DBG_NO_GRAPH = 8;   // streaming: launch kernel by kernel instead of replaying the captured CUDA graph
 
 struct HostTensor {
@@ -299,8 +300,9 @@ struct Handle {
     const double bytes = 2.0 * (static_cast<double>(g.batches) * g.rows_a * g.Kc + static_cast<double>(g.N) * g.ntaps * g.Kc) +
                          static_cast<double>(g.batches) * g.rows_out * g.N *
                              ((g.out32 ? 4 : 0) + (g.out16 ? 2 : 0) + (g.resid ? 4 : 0));
-    const int id = prof_begin(FRT2_PROF_GEMM, flops, bytes, st);
-    const int rc = (debug & DBG_GEMM_REF) ? gemm_ref(g, st) : gemm_tc(g, st);
+    const bool skinny = !(debug & (DBG_GEMM_REF | DBG_NO_SKINNY)) && gemm_skinny_applicable(g);
+    const int id = prof_begin(skinny ? FRT2_PROF_GEMM_SKINNY : FRT2_PROF_GEMM, flops, bytes, st);
+    const int rc = (debug & DBG_GEMM_REF) ? gemm_ref(g, st) : (skinny ? gemm_skinny(g, st) : gemm_tc(g, st));
     prof_end(id, st);
     return rc;
   }
@@ -398,6 +400,8 @@ static std::vector<float> weight_norm_host(const HostTensor& g, const HostTensor
 int Handle::finalize() {
   FRT2_CUDA_OK(cudaSetDevice(device));
   FRT2_TRY(gemm_tc_init());
+  FRT2_TRY(gemm_skinny_init());
+  FRT2_TRY(attention_tc_init());
   const HostTensor* t = nullptr;
   const std::string RVQ = "rvq.", UP = "upsample.", AD = "acoustic_decoder.", BB = "acoustic_decoder.backbone.";
 
@@ -1268,6 +1272,10 @@ int frt2_op_gemm(int impl, const void* A16, const void* W16, int batches, int ro
   g.pitch32 = static_cast<int64_t>(rows_per_batch) * N; g.pitch16 = g.pitch32; g.alpha = alpha; g.bias = bias; g.act = act;
   g.resid = resid; g.out32 = out32; g.ld32 = N; g.out16 = static_cast<__half*>(out16); g.ld16 = N;
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (impl == 2) {
+    FRT2_TRY(gemm_skinny_init());
+    return gemm_skinny(g, st);
+  }
   return impl == 0 ? gemm_tc(g, st) : gemm_ref(g, st);
 }
 

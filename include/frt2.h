@@ -114,13 +114,13 @@ int frt2_check_error(frt2_handle* h, void* cuda_stream);
  * launches, algorithmic FLOPs and algorithmic bytes (DESIGN.md states the per-unit figures).  Class
  * FRT2_PROF_ALL returns the total number of kernels launched since frt2_profile(h, *) in *launches. */
 enum { FRT2_PROF_GEMM = 0, FRT2_PROF_ATTN_TC = 1, FRT2_PROF_ATTN_WARP = 2, FRT2_PROF_LAYER_NORM = 3,
-       FRT2_PROF_RVQ = 4, FRT2_PROF_OLA = 5, FRT2_PROF_ALL = -1 };
+       FRT2_PROF_RVQ = 4, FRT2_PROF_OLA = 5, FRT2_PROF_GEMM_SKINNY = 6, FRT2_PROF_ALL = -1 };
 int frt2_profile(frt2_handle* h, int enable);
 int frt2_profile_get(frt2_handle* h, int cls, double* ms, int64_t* launches, double* flops, double* bytes);
 
 /* ---- single-operator entry points (unit parity tests and per-kernel roofline benches) ---- */
 /* C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias) (+ resid); A,W fp16 device, fp32 accumulate.
- * impl 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT check kernel.  ntaps > 1: causal conv over `batches` items of
+ * impl 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT check kernel, 2 = skinny weight-streaming kernel (<= 16 rows).  ntaps > 1: causal conv over `batches` items of
  * rows_per_batch rows, K = ntaps*Kc, zero left padding. */
 int frt2_op_gemm(int impl, const void* A16, const void* W16, int batches, int rows_per_batch, int Kc, int ntaps,
                  int N, float alpha, const float* bias, int act, const float* resid, float* out32, void* out16,

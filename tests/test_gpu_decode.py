@@ -18,7 +18,7 @@ SNR_GATE_DB = 40.0
 MAXABS_TOL = 0.05   # of the reference waveform peak
 
 MODES = {"simt_gemm+warp_attn": N.DBG_GEMM_REF | N.DBG_ATTN_WARP, "tc_gemm+warp_attn": N.DBG_ATTN_WARP, "product": 0,
-         "no_graph": N.DBG_NO_GRAPH}
+         "no_graph": N.DBG_NO_GRAPH, "no_skinny": N.DBG_NO_SKINNY}
 
 
 def _gate(name, ref, out):
@@ -128,7 +128,7 @@ def test_varlen_lengths_extension():
     assert np.all(a[1, (L - 4) * spt:] == 0)
 
 
-@pytest.mark.parametrize("mode", ["tc_gemm+warp_attn", "product", "no_graph"])
+@pytest.mark.parametrize("mode", ["tc_gemm+warp_attn", "product", "no_graph", "no_skinny"])
 @pytest.mark.parametrize("case", cases("stream"), ids=lambda c: c["name"])
 def test_streaming_vs_reference_golden(case, mode):
     cfg, sd, g = load_case(case)

@@ -200,3 +200,39 @@ def test_overlap_add(lib, B, T, first, last, use_tail):
                                         first, last, _stream()))
     err = np.abs(out.cpu().numpy() - y).max()
     assert err < 1e-5, err
+
+
+SKINNY_CASES = [
+    # batches, rows, Kc, taps, N, bias, act, resid, alpha
+    (1, 8, 1024, 1, 1024, True, 0, True, 1.0),
+    (1, 8, 1024, 1, 4096, True, 1, False, 1.0),
+    (1, 8, 4096, 1, 1024, True, 0, True, 1.0),
+    (1, 8, 1024, 7, 1024, True, 0, False, 1.0),
+    (2, 8, 128, 3, 128, True, 0, True, 1.0),
+    (1, 8, 1024, 1, 962, True, 2, False, 1.0),
+    (1, 8, 1024, 1, 960, False, 0, False, 1.0 / 960),
+    (1, 4, 512, 2, 1024, True, 1, False, 1.0),
+    (1, 1, 512, 1, 1024, True, 0, False, 1.0),
+    (3, 5, 64, 1, 70, True, 0, False, 1.0),
+]
+
+
+@pytest.mark.parametrize("case", SKINNY_CASES, ids=lambda c: "b%d_m%d_k%d_t%d_n%d_b%d_a%d_r%d" % c[:8])
+def test_gemm_skinny(lib, case):
+    batches, rows, Kc, taps, Nn, use_bias, act, use_resid, alpha = case
+    g = torch.Generator(device="cuda").manual_seed(7)
+    A = (torch.randn(batches, rows, Kc, device="cuda", generator=g)).half()
+    W = (torch.randn(Nn, taps * Kc, device="cuda", generator=g) / math.sqrt(taps * Kc)).half()
+    if act == 2:
+        W = W * 0.5
+    bias = torch.randn(Nn, device="cuda", generator=g) * 0.1 if use_bias else None
+    resid = torch.randn(batches, rows, Nn, device="cuda", generator=g) if use_resid else None
+    o32 = torch.full((batches, rows, Nn), float("nan"), device="cuda")
+    o16 = torch.full((batches, rows, Nn), float("nan"), device="cuda", dtype=torch.half)
+    _check(lib, lib.frt2_op_gemm(2, _p(A), _p(W), batches, rows, Kc, taps, Nn, alpha, _p(bias), act, _p(resid),
+                                 _p(o32), _p(o16), _stream()))
+    torch.cuda.synchronize()
+    ref = gemm_reference(A, W, taps, bias, act, resid, alpha)
+    scale = ref.abs().max().item() + 1e-6
+    assert (o32 - ref).abs().max().item() / scale < 2e-3
+    assert (o16.float() - ref).abs().max().item() / scale < 3e-3

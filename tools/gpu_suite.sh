@@ -11,7 +11,7 @@ run() {  # name, timeout, pytest args...
   grep -E "passed|failed|error" "$OUT/$name.log" | tail -1 | tee -a "$OUT/summary.txt"
 }
 : > "$OUT/summary.txt"
-run ops_gemm 600 tests/test_gpu_ops.py -k gemm
+run ops_gemm 600 tests/test_gpu_ops.py -k "gemm"
 run ops_ln 300 tests/test_gpu_ops.py -k layer_norm
 run ops_ola 300 tests/test_gpu_ops.py -k overlap_add
 run ops_attn_warp 600 tests/test_gpu_ops.py -k "attention and warp"

@@ -57,3 +57,31 @@ if __name__ == "__main__":
         gemm(reps, K=1024, Nn=4096, act=1)
         gemm(reps, K=4096, Nn=1024, resid=True)
         gemm(reps, K=1024, Nn=1024, out32=True)
+
+
+def skinny(reps):
+    for (K, Nn, taps) in [(1024, 1024, 1), (1024, 3072, 1), (1024, 4096, 1), (4096, 1024, 1), (1024, 1024, 3), (1024, 1024, 7)]:
+        A = torch.randn(1, 8, K, device="cuda").half()
+        W = (torch.randn(Nn, taps * K, device="cuda") / 32).half()
+        bias = torch.randn(Nn, device="cuda")
+        o16 = torch.empty(1, 8, Nn, device="cuda", dtype=torch.half)
+        for impl in (2, 0):
+            ms = timeit(lambda: N.check(lib.frt2_op_gemm(impl, P(A), P(W), 1, 8, K, taps, Nn, 1.0, P(bias), 0, None, None, P(o16), S())), reps)
+            print(f"impl={impl} M=8 K={K}x{taps} N={Nn}: {ms * 1e3:.2f} us/launch  {Nn * taps * K * 2 / ms / 1e6:.0f} GB/s")
+    x = torch.randn(8, 1024, device="cuda"); g = torch.ones(1024, device="cuda"); b = torch.zeros(1024, device="cuda")
+    o = torch.empty(8, 1024, device="cuda", dtype=torch.half)
+    ms = timeit(lambda: N.check(lib.frt2_op_layer_norm(P(x), 8, 1024, P(g), P(b), 1e-5, 0, P(o), S())), reps)
+    print(f"layer_norm 8 rows: {ms * 1e3:.2f} us/launch")
+    E = 1024
+    for Tk in (8, 128, 1000):
+        q = torch.randn(1, 8, E, device="cuda").half(); k = torch.randn(1, Tk, E, device="cuda").half(); v = torch.randn(1, Tk, E, device="cuda").half()
+        out = torch.empty(1, 8, E, device="cuda", dtype=torch.half)
+        ms = timeit(lambda: N.check(lib.frt2_op_attention(1, P(q), P(k), P(v), P(out), 1, 16, 64, 8, Tk, Tk - 8, 0, S())), reps)
+        print(f"attention_warp Tq=8 Tk={Tk}: {ms * 1e3:.2f} us/launch")
+    # empty-ish kernel launch cost through the same path
+    ms = timeit(lambda: torch.cuda._sleep(1), reps)
+    print(f"torch._sleep(1) launch: {ms * 1e3:.2f} us")
+
+
+if __name__ == "__main__" and sys.argv[1] == "skinny":
+    skinny(int(sys.argv[2]) if len(sys.argv) > 2 else 200)
