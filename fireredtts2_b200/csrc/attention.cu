@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(NSPLIT == 1 ? 128 : NSPLIT * 32) attention_war
     for (int r = 0; r < 8; ++r) {
       const float inv = 1.0f / l[r];
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) op[r * a.o_row_pitch + i] = __float2half_rn(acc[r][i] * inv);
+      for (int i = 0; i < DPL; ++i) op[r * a.o_row_pitch + i] = to_half_sat(acc[r][i] * inv);
     }
   } else {
     // merge the NSPLIT partial softmax states: out = sum_w acc_w 2^(m_w - M) / sum_w l_w 2^(m_w - M)
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(NSPLIT == 1 ? 128 : NSPLIT * 32) attention_war
       }
       const float inv = 1.0f / L;
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) op[r * a.o_row_pitch + i] = __float2half_rn(o[i] * inv);
+      for (int i = 0; i < DPL; ++i) op[r * a.o_row_pitch + i] = to_half_sat(o[i] * inv);
     }
   }
 }

@@ -48,9 +48,17 @@ __device__ __forceinline__ float gelu_erf(float x) {  // exact erf GELU (referen
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+// fp32 -> fp16 conversions saturate to +-65504 instead of overflowing to inf (one F2FP.SATFINITE instruction):
+// an out-of-range activation degrades gracefully instead of poisoning the utterance with NaNs.
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {  // lo = a, hi = b
+  uint32_t y;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(b), "f"(a));
+  return y;
+}
+__device__ __forceinline__ __half to_half_sat(float a) {
+  unsigned short y;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(y) : "f"(a));
+  return __ushort_as_half(y);
 }
 
 // ---- GEMM (tcgen05) ----

@@ -126,7 +126,7 @@ __global__ void import_cm_to_tm_kernel(const float* src, int C_total, int c_off,
     const int r = static_cast<int>((i / C) % rows);
     const int b = static_cast<int>(i / (static_cast<long long>(C) * rows));
     dst[b * batch_pitch + static_cast<long long>(r) * C + c] =
-        __float2half_rn(src[(static_cast<long long>(b) * C_total + c_off + c) * t_total + t_off + r]);
+        to_half_sat(src[(static_cast<long long>(b) * C_total + c_off + c) * t_total + t_off + r]);
   }
 }
 // kv state (B, Tmax, 2E) fp16 [k | v]  <->  reference (B, nl, H, T, 2*hd) fp32 slice of layer `layer`
@@ -157,7 +157,7 @@ __global__ void import_kv_kernel(const float* src, int nl, int layer, __half* kv
     const int ch = isv ? c - E : c;
     const int h = ch / hd, d = ch - h * hd;
     kv[b * batch_pitch + static_cast<long long>(t) * 2 * E + c] =
-        __float2half_rn(src[((((static_cast<long long>(b) * nl + layer) * H + h) * T + t) * 2 + isv) * hd + d]);
+        to_half_sat(src[((((static_cast<long long>(b) * nl + layer) * H + h) * T + t) * 2 + isv) * hd + d]);
   }
 }
 // is_cache (B, n_fft, 3) fp32 channel-major <-> tail (B, 3, n_fft) fp32
@@ -265,7 +265,7 @@ struct Handle {
     std::vector<__half> hbuf(v.size());
     const long long n = static_cast<long long>(v.size());
 #pragma omp parallel for schedule(static)
-    for (long long i = 0; i < n; ++i) hbuf[i] = __float2half_rn(v[i]);
+    for (long long i = 0; i < n; ++i) hbuf[i] = __float2half_rn(std::min(65504.0f, std::max(-65504.0f, v[i])));
     FRT2_TRY(dev_alloc(reinterpret_cast<void**>(out), hbuf.size() * 2));
     FRT2_CUDA_OK(cudaMemcpy(*out, hbuf.data(), hbuf.size() * 2, cudaMemcpyHostToDevice));
     return FRT2_OK;

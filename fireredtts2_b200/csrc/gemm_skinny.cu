@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(GemmDesc g, 
       const long long o16 = static_cast<long long>(b) * g.pitch16 + static_cast<long long>(r + roff) * g.ld16 + nn;
       if (g.resid != nullptr) v += g.resid[o32];
       if (g.out32 != nullptr) g.out32[o32] = v;
-      if (g.out16 != nullptr) g.out16[o16] = __float2half_rn(v);
+      if (g.out16 != nullptr) g.out16[o16] = to_half_sat(v);
     }
   }
 }

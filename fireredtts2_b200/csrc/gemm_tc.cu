@@ -21,6 +21,7 @@
 //                               same staging buffer and added before the store.
 // Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -75,19 +76,20 @@ struct GemmCfg {
       STAGES * STAGE_BYTES + EPI_WARPS * STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// exact-erf GELU evaluated with the Abramowitz-Stegun 7.1.26 rational approximation of erf (|err| <= 1.5e-7,
-// far below the fp16 rounding of the stored activation); ~3x fewer instructions than erff.
+// exact-erf GELU evaluated with the Abramowitz-Stegun 7.1.28 approximation erf(z) = 1 - (1 + a1 z + .. + a6 z^6)^-16
+// (|err| <= 3e-7, far below the fp16 rounding of the stored activation): 6 FMA + one MUFU.RCP + 4 squarings, i.e.
+// one special-function op per element instead of erff's branchy ~25 instructions.
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  const float e = __expf(-z * z);
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  const float erfv = copysignf(erf_abs, x);
+  float p = fmaf(z, 0.0000430638f, 0.0002765672f);
+  p = fmaf(p, z, 0.0001520143f);
+  p = fmaf(p, z, 0.0092705272f);
+  p = fmaf(p, z, 0.0422820123f);
+  p = fmaf(p, z, 0.0705230784f);
+  p = fmaf(p, z, 1.0f);
+  float r = __fdividef(1.0f, p);
+  r *= r; r *= r; r *= r; r *= r;       // p^-16
+  const float erfv = copysignf(1.0f - r, x);
   return 0.5f * x * (1.0f + erfv);
 }
 
@@ -172,7 +174,7 @@ __device__ __forceinline__ void store_chunk_direct(const GemmKParams& p, float (
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) op[j] = __float2half_rn(v[j]);
+        if (n0 + j < p.N) op[j] = to_half_sat(v[j]);
     }
   }
 }
@@ -186,6 +188,143 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// Epilogue of one 128 x BN accumulator tile held in this CTA's TMEM (shared by the 1-CTA and the 2-CTA kernels).
+// e = epilogue warp index 0..7, row_slab0 = first output row of this CTA's 128-row slab, tmem_acc = TMEM address of
+// the accumulator stage (tmem_stage).  Ends with tcgen05.fence::before_thread_sync + __syncwarp; the caller signals "TMEM free".
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtensorMap* tmC, uint8_t* sStage, int e,
+                                              int lane, uint32_t tmem_stage, int n_idx, int b, int row_slab0,
+                                              uint64_t* tfull, uint32_t aphase) {
+    const int wq = e & 3;        // TMEM lane quarter == warp_id % 4
+    const int hsel = e >> 2;     // which half of the tile's columns this warp owns
+    constexpr int CHUNKS_PER_WARP = BN / 64;  // 32-column chunks per warp
+    uint8_t* stg = sStage + e * STAGING_BYTES;
+    uint8_t* stg_row = stg + lane * 128;      // row-order access: thread == row
+    const int sw = lane & 7;
+    // coalesced residual access: lane covers row (i*4 + lane/8), 16-byte chunk (lane % 8)
+    const int crow = lane >> 3, cchunk = lane & 7;
+    const uint32_t tmem_lane = static_cast<uint32_t>(wq * 32) << 16;
+    {
+      const int row0 = row_slab0 + wq * 32;   // first row of this warp's 32-row slab
+      const int row = row0 + lane;
+      const bool valid_row = row < p.rows_out;
+      const int roff = (p.row_off_ptr != nullptr) ? __ldg(p.row_off_ptr) : 0;  // direct-store mode only
+      const long long off32 = static_cast<long long>(b) * p.pitch32 + static_cast<long long>(row + roff) * p.ld32;
+      const long long off16 = static_cast<long long>(b) * p.pitch16 + static_cast<long long>(row + roff) * p.ld16;
+      const int ncol0 = n_idx * BN + hsel * (BN / 2);     // first column owned by this warp
+      const uint32_t tmem_acc = tmem_stage + static_cast<uint32_t>(hsel * (BN / 2)) + tmem_lane;
+
+      // residual prefetch of the first chunk (coalesced; overlaps the wait for the accumulator)
+      float4 rpre[8];
+      const bool use_resid = (p.store_mode == STORE_TMA32) && (p.resid != nullptr);
+      auto prefetch_resid = [&](int n0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = row0 + i * 4 + crow;
+          rpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rr < p.rows_out && n0 + cchunk * 4 < p.N)
+            rpre[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<long long>(b) * p.pitch32 +
+                                                       static_cast<long long>(rr) * p.ld32 + n0 + cchunk * 4);
+        }
+      };
+      if (use_resid && ncol0 < p.N) prefetch_resid(ncol0);
+
+      ptx::mbar_wait(tfull, aphase);
+      ptx::tc_fence_after();
+
+      if (p.store_mode == STORE_TMA16) {
+        // ---- fp16 output: 64 columns (128 B per row) per TMA store
+#pragma unroll 1
+        for (int g = 0; g < CHUNKS_PER_WARP / 2; ++g) {
+          const int n0 = ncol0 + g * 64;
+          if (n0 >= p.N) break;
+          uint32_t packed[32];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t r[32];
+            float v[32];
+            ptx::tmem_ld32(tmem_acc + g * 64 + hh * 32, r);
+            ptx::tmem_ld_wait();
+            apply_chunk(p, r, n0 + hh * 32, v);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) packed[hh * 16 + j] = pack_half2(v[2 * j], v[2 * j + 1]);
+          }
+          if (lane == 0) tma_store_wait_read();  // previous store has finished reading the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 q;
+            q.x = packed[4 * c + 0]; q.y = packed[4 * c + 1]; q.z = packed[4 * c + 2]; q.w = packed[4 * c + 3];
+            *reinterpret_cast<uint4*>(stg_row + ((c ^ sw) << 4)) = q;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_3d(tmC, stg, n0, row0, b);
+        }
+      } else if (p.store_mode == STORE_TMA32) {
+        // ---- fp32 output (optionally + residual): 32 columns (128 B per row) per TMA store
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS_PER_WARP; ++c) {
+          const int n0 = ncol0 + c * 32;
+          if (n0 >= p.N) break;
+          uint32_t r[32];
+          float v[32];
+          ptx::tmem_ld32(tmem_acc + c * 32, r);
+          ptx::tmem_ld_wait();
+          apply_chunk(p, r, n0, v);
+          if (use_resid) {
+            // accumulator rows -> staging (row order) -> back in coalesced order, + prefetched residual, then plain
+            // coalesced 16-byte global stores (4 full 128-B lines per warp instruction): half the shared-memory
+            // traffic of staging both the residual and the result
+            __syncwarp();
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc)
+              *reinterpret_cast<float4*>(stg_row + ((cc ^ sw) << 4)) =
+                  make_float4(v[4 * cc], v[4 * cc + 1], v[4 * cc + 2], v[4 * cc + 3]);
+            __syncwarp();
+            const bool col_ok = n0 + cchunk * 4 < p.N;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + crow;
+              float4 q = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cchunk ^ (rr & 7)) << 4));
+              q.x += rpre[i].x; q.y += rpre[i].y; q.z += rpre[i].z; q.w += rpre[i].w;
+              if (row0 + rr < p.rows_out && col_ok)
+                *reinterpret_cast<float4*>(p.out32 + static_cast<long long>(b) * p.pitch32 +
+                                           static_cast<long long>(row0 + rr) * p.ld32 + n0 + cchunk * 4) = q;
+            }
+            if (c + 1 < CHUNKS_PER_WARP && n0 + 32 < p.N) prefetch_resid(n0 + 32);  // in flight during the next chunk
+            continue;
+          }
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc)
+            *reinterpret_cast<float4*>(stg_row + ((cc ^ sw) << 4)) =
+                make_float4(v[4 * cc], v[4 * cc + 1], v[4 * cc + 2], v[4 * cc + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_3d(tmC, stg, n0, row0, b);
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS_PER_WARP; ++c) {
+          const int n0 = ncol0 + c * 32;
+          if (n0 >= p.N) break;
+          uint32_t r[32];
+          float v[32];
+          ptx::tmem_ld32(tmem_acc + c * 32, r);
+          ptx::tmem_ld_wait();
+          if (valid_row) {
+            apply_chunk(p, r, n0, v);
+            store_chunk_direct(p, v, off32, off16, n0);
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+    }
 }
 
 template <int BN>
@@ -288,131 +427,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int e = warp - 4;
-    const int wq = e & 3;        // TMEM lane quarter == warp_id % 4
-    const int hsel = e >> 2;     // which half of the tile's columns this warp owns
-    constexpr int CHUNKS_PER_WARP = BN / 64;  // 32-column chunks per warp
-    uint8_t* stg = sStage + e * STAGING_BYTES;
-    uint8_t* stg_row = stg + lane * 128;      // row-order access: thread == row
-    const int sw = lane & 7;
-    // coalesced residual access: lane covers row (i*4 + lane/8), 16-byte chunk (lane % 8)
-    const int crow = lane >> 3, cchunk = lane & 7;
-    const uint32_t tmem_lane = static_cast<uint32_t>(wq * 32) << 16;
     int as = 0;
     uint32_t aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int n_idx = tile % p.tiles_n;
       const int mb = tile / p.tiles_n;
       const int b = mb / p.tiles_m;
-      const int row0 = (mb % p.tiles_m) * BM + wq * 32;   // first row of this warp's 32-row slab
-      const int row = row0 + lane;
-      const bool valid_row = row < p.rows_out;
-      const int roff = (p.row_off_ptr != nullptr) ? __ldg(p.row_off_ptr) : 0;  // direct-store mode only
-      const long long off32 = static_cast<long long>(b) * p.pitch32 + static_cast<long long>(row + roff) * p.ld32;
-      const long long off16 = static_cast<long long>(b) * p.pitch16 + static_cast<long long>(row + roff) * p.ld16;
-      const int ncol0 = n_idx * BN + hsel * (BN / 2);     // first column owned by this warp
-      const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(as * BN + hsel * (BN / 2)) + tmem_lane;
-
-      // residual prefetch of the first chunk (coalesced; overlaps the wait for the accumulator)
-      float4 rpre[8];
-      const bool use_resid = (p.store_mode == STORE_TMA32) && (p.resid != nullptr);
-      auto prefetch_resid = [&](int n0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = row0 + i * 4 + crow;
-          rpre[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rr < p.rows_out && n0 + cchunk * 4 < p.N)
-            rpre[i] = *reinterpret_cast<const float4*>(p.resid + static_cast<long long>(b) * p.pitch32 +
-                                                       static_cast<long long>(rr) * p.ld32 + n0 + cchunk * 4);
-        }
-      };
-      if (use_resid && ncol0 < p.N) prefetch_resid(ncol0);
-
-      ptx::mbar_wait(&tfull_bar[as], aphase);
-      ptx::tc_fence_after();
-
-      if (p.store_mode == STORE_TMA16) {
-        // ---- fp16 output: 64 columns (128 B per row) per TMA store
-#pragma unroll 1
-        for (int g = 0; g < CHUNKS_PER_WARP / 2; ++g) {
-          const int n0 = ncol0 + g * 64;
-          if (n0 >= p.N) break;
-          uint32_t packed[32];
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t r[32];
-            float v[32];
-            ptx::tmem_ld32(tmem_acc + g * 64 + hh * 32, r);
-            ptx::tmem_ld_wait();
-            apply_chunk(p, r, n0 + hh * 32, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) packed[hh * 16 + j] = pack_half2(v[2 * j], v[2 * j + 1]);
-          }
-          if (lane == 0) tma_store_wait_read();  // previous store has finished reading the staging buffer
-          __syncwarp();
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            uint4 q;
-            q.x = packed[4 * c + 0]; q.y = packed[4 * c + 1]; q.z = packed[4 * c + 2]; q.w = packed[4 * c + 3];
-            *reinterpret_cast<uint4*>(stg_row + ((c ^ sw) << 4)) = q;
-          }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) tma_store_3d(&tmC, stg, n0, row0, b);
-        }
-      } else if (p.store_mode == STORE_TMA32) {
-        // ---- fp32 output (optionally + residual): 32 columns (128 B per row) per TMA store
-#pragma unroll 1
-        for (int c = 0; c < CHUNKS_PER_WARP; ++c) {
-          const int n0 = ncol0 + c * 32;
-          if (n0 >= p.N) break;
-          uint32_t r[32];
-          float v[32];
-          ptx::tmem_ld32(tmem_acc + c * 32, r);
-          ptx::tmem_ld_wait();
-          apply_chunk(p, r, n0, v);
-          if (lane == 0) tma_store_wait_read();
-          __syncwarp();
-          if (use_resid) {
-            // coalesced-order registers -> staging -> row order
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = i * 4 + crow;
-              *reinterpret_cast<float4*>(stg + rr * 128 + ((cchunk ^ (rr & 7)) << 4)) = rpre[i];
-            }
-            __syncwarp();
-            if (c + 1 < CHUNKS_PER_WARP && n0 + 32 < p.N) prefetch_resid(n0 + 32);  // next chunk, in flight during math
-#pragma unroll
-            for (int cc = 0; cc < 8; ++cc) {
-              const float4 q = *reinterpret_cast<const float4*>(stg_row + ((cc ^ sw) << 4));
-              v[4 * cc + 0] += q.x; v[4 * cc + 1] += q.y; v[4 * cc + 2] += q.z; v[4 * cc + 3] += q.w;
-            }
-            __syncwarp();
-          }
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc)
-            *reinterpret_cast<float4*>(stg_row + ((cc ^ sw) << 4)) =
-                make_float4(v[4 * cc], v[4 * cc + 1], v[4 * cc + 2], v[4 * cc + 3]);
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) tma_store_3d(&tmC, stg, n0, row0, b);
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < CHUNKS_PER_WARP; ++c) {
-          const int n0 = ncol0 + c * 32;
-          if (n0 >= p.N) break;
-          uint32_t r[32];
-          float v[32];
-          ptx::tmem_ld32(tmem_acc + c * 32, r);
-          ptx::tmem_ld_wait();
-          if (valid_row) {
-            apply_chunk(p, r, n0, v);
-            store_chunk_direct(p, v, off32, off16, n0);
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
+      epilogue_tile<BN>(p, &tmC, sStage, e, lane, tmem_base + static_cast<uint32_t>(as * BN), n_idx, b,
+                        (mb % p.tiles_m) * BM, &tfull_bar[as], aphase);
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -424,6 +446,150 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+
+// =====================================================================================================
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on the two SMs of a TPC computes one 256 x 256 tile.  Each
+// CTA stages its own 128 rows of A and HALF of the W tile (128 of the 256 N-rows), so the shared-memory operand
+// traffic per SM drops from 12 KB to 8 KB per K=16 step and 6 pipeline stages fit; one thread of the leader CTA
+// issues tcgen05.mma.cta_group::2 for both SMs, each CTA's TMEM holds its own 128 x 256 fp32 accumulator (x2 stages)
+// and runs the unchanged epilogue on it.  Barriers: both CTAs' TMA loads report their bytes to the leader's "full"
+// barrier; MMA completion is multicast to the "empty"/"TMEM full" barriers of both CTAs; the peer's epilogue warps
+// arrive remotely on the leader's "TMEM empty" barrier.
+// =====================================================================================================
+struct Gemm2Cfg {
+  static constexpr int BN = 256;
+  static constexpr int STAGES = 6;
+  static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;           // this CTA's half of the W tile
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // 32 KB
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * STAGING_BYTES + 1024 + 256;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const GemmKParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int BN = Cfg::BN;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint8_t* sStage = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sStage + EPI_WARPS * STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();   // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    if (p.store_mode != STORE_DIRECT) ptx::prefetch_tmap(&tmC);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);            // leader's: its own arrive.expect_tx (bytes of BOTH CTAs)
+      ptx::mbar_init(&empty_bar[s], 1);           // multicast commit from the leader's MMA thread
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tfull_bar[s], 1);           // multicast commit
+      ptx::mbar_init(&tempty_bar[s], 2 * EPI_WARPS);  // leader's: epilogue warps of both CTAs
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2cta(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();   // barrier inits and TMEM allocation of both CTAs visible before any cross-CTA signal
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < p.num_tiles; tile += npairs) {
+        const int n_idx = tile % p.tiles_n;
+        const int mb = tile / p.tiles_n;
+        const int b = mb / p.tiles_m;
+        const int m0 = (mb % p.tiles_m) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = n_idx * BN + static_cast<int>(rank) * (BN / 2);
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const int tap = kb / p.kblocks_per_tap;
+          const int c0 = (kb - tap * p.kblocks_per_tap) * BK;
+          ptx::tma_load_3d_2cta(sA + stage * A_STAGE_BYTES, &tmA, full_leader, c0, m0 + tap + p.row_shift, b);
+          ptx::tma_load_2d_2cta(sB + stage * Cfg::B_STAGE_BYTES, &tmB, full_leader, kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(2 * BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = pair; tile < p.num_tiles; tile += npairs) {
+        ptx::mbar_wait(&tempty_bar[as], aphase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.num_kblocks; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sA + stage * A_STAGE_BYTES));
+          const uint64_t db = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sB + stage * Cfg::B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            ptx::mma_f16_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          ptx::mma_commit_2cta(&empty_bar[stage], 0x3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit_2cta(&tfull_bar[as], 0x3);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (each CTA on its own 128 rows)
+    const int e = warp - 4;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = pair; tile < p.num_tiles; tile += npairs) {
+      const int n_idx = tile % p.tiles_n;
+      const int mb = tile / p.tiles_n;
+      const int b = mb / p.tiles_m;
+      epilogue_tile<BN>(p, &tmC, sStage, e, lane, tmem_base + static_cast<uint32_t>(as * BN), n_idx, b,
+                        (mb % p.tiles_m) * (2 * BM) + static_cast<int>(rank) * BM, &tfull_bar[as], aphase);
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty_bar[as]), 0));
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (lane == 0 && p.store_mode != STORE_DIRECT) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();   // the peer's smem / TMEM must stay alive until the leader's last MMA has retired
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2cta(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -452,6 +618,8 @@ void do_init() {
   e = cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<128>::SMEM_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<256>::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Gemm2Cfg::SMEM_BYTES);
   if (e != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(gemm_tc_kernel): ") + cudaGetErrorString(e));
     g_init_status = FRT2_ERR_CUDA;
@@ -512,6 +680,11 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   FRT2_REQUIRE(g.out32 != nullptr || g.out16 != nullptr, FRT2_ERR_BAD_ARG, "gemm_tc: no output");
 
   const int BN = (g.N >= 512) ? 256 : 128;
+  // CTA pairs (256 x 256 tiles) for the large GEMMs; FRT2_GEMM_1CTA=1 forces the single-CTA kernel (A/B testing)
+  static const bool force_1cta = (getenv("FRT2_GEMM_1CTA") != nullptr);
+  const bool pair = !force_1cta && BN == 256 && g.rows_out >= 256 && g.out_row_off == nullptr;
+  const int BMT = pair ? 2 * BM : BM;           // rows per tile
+  const int BNB = pair ? BN / 2 : BN;           // W rows per TMA box
   const uint64_t Ktot = static_cast<uint64_t>(g.ntaps) * g.Kc;
 
   CUtensorMap tmA, tmB, tmC;
@@ -525,7 +698,7 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   {
     uint64_t dims[2] = {Ktot, static_cast<uint64_t>(g.N)};
     uint64_t strides[1] = {Ktot * 2};
-    uint32_t box[2] = {BK, static_cast<uint32_t>(BN)};
+    uint32_t box[2] = {BK, static_cast<uint32_t>(BNB)};
     FRT2_TRY(tma_encode_fp16(&tmB, g.W, 2, dims, strides, box));
   }
 
@@ -537,7 +710,7 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   p.kblocks_per_tap = g.Kc / BK;
   p.num_kblocks = g.ntaps * p.kblocks_per_tap;
   p.row_shift = g.row_shift;
-  p.tiles_m = (g.rows_out + BM - 1) / BM;
+  p.tiles_m = (g.rows_out + BMT - 1) / BMT;
   p.tiles_n = (g.N + BN - 1) / BN;
   p.num_tiles = g.batches * p.tiles_m * p.tiles_n;
   p.alpha = g.alpha;
@@ -575,11 +748,16 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
     p.store_mode = STORE_TMA32;
   }
 
-  const int grid = std::min(p.num_tiles, g_num_sms);
-  if (BN == 256) {
-    gemm_tc_kernel<256><<<grid, GEMM_THREADS, GemmCfg<256>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  if (pair) {
+    const int grid = 2 * std::min(p.num_tiles, g_num_sms / 2);
+    gemm_tc2_kernel<<<grid, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   } else {
-    gemm_tc_kernel<128><<<grid, GEMM_THREADS, GemmCfg<128>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+    const int grid = std::min(p.num_tiles, g_num_sms);
+    if (BN == 256) {
+      gemm_tc_kernel<256><<<grid, GEMM_THREADS, GemmCfg<256>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+    } else {
+      gemm_tc_kernel<128><<<grid, GEMM_THREADS, GemmCfg<128>::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+    }
   }
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;

@@ -317,8 +317,8 @@ __global__ void __launch_bounds__(128) gemm_ref_kernel(GemmDesc g) {
     if (has2) g.out32[o32 + 1] = v1;
   }
   if (g.out16 != nullptr) {
-    g.out16[o16] = __float2half_rn(v0);
-    if (has2) g.out16[o16 + 1] = __float2half_rn(v1);
+    g.out16[o16] = to_half_sat(v0);
+    if (has2) g.out16[o16 + 1] = to_half_sat(v1);
   }
 }
 

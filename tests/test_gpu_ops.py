@@ -236,3 +236,17 @@ def test_gemm_skinny(lib, case):
     scale = ref.abs().max().item() + 1e-6
     assert (o32 - ref).abs().max().item() / scale < 2e-3
     assert (o16.float() - ref).abs().max().item() / scale < 3e-3
+
+
+def test_fp16_outputs_saturate_instead_of_overflowing(lib):
+    """fp32 -> fp16 conversions saturate at +-65504 (F2FP.SATFINITE): no inf / NaN from an out-of-range activation."""
+    M, K, Nn = 256, 64, 512
+    A = torch.full((1, M, K), 300.0, device="cuda").half()
+    W = torch.full((Nn, K), 300.0, device="cuda").half()
+    W[1::2] = -300.0
+    for impl in (0, 1):
+        o16 = torch.zeros(1, M, Nn, device="cuda", dtype=torch.half)
+        _check(lib, lib.frt2_op_gemm(impl, _p(A), _p(W), 1, M, K, 1, Nn, 1.0, None, 0, None, None, _p(o16), _stream()))
+        torch.cuda.synchronize()
+        assert torch.isfinite(o16.float()).all()
+        assert (o16[0, :, 0::2] == 65504).all() and (o16[0, :, 1::2] == -65504).all()
