@@ -98,69 +98,90 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Two rows per warp: 2 x (C/128) independent 16-byte loads in flight per lane before the first reduction.
+template <int RPW>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x, long long ldx, long long rows,
                                                          int rows_per_batch, int C, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float eps, int apply_silu,
                                                          __half* __restrict__ out16, long long ld16,
                                                          long long out_batch_pitch) {
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
   const int C4 = C >> 2;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
-  float4 cache[LN_MAX_V4];
-  float s = 0.f;
+  float4 cache[RPW][LN_MAX_V4];
+  float s[RPW];
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
-    const int c = lane + 32 * i;
-    if (c < C4) {
-      cache[i] = xr[c];
-      s += (cache[i].x + cache[i].y) + (cache[i].z + cache[i].w);
+  for (int r = 0; r < RPW; ++r) {
+    s[r] = 0.f;
+    const long long row = min(row0 + r, rows - 1);
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C4) cache[r][i] = __ldcs(xr + c);
     }
   }
-  for (int c = lane + 32 * LN_MAX_V4; c < C4; c += 32) {
-    const float4 v = xr[c];
-    s += (v.x + v.y) + (v.z + v.w);
-  }
-  const float mean = warp_sum(s) / static_cast<float>(C);
-  float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
-    const int c = lane + 32 * i;
-    if (c < C4) {
-      const float a = cache[i].x - mean, b = cache[i].y - mean, cc = cache[i].z - mean, d = cache[i].w - mean;
-      q += (a * a + b * b) + (cc * cc + d * d);
+  for (int r = 0; r < RPW; ++r) {
+    const long long row = min(row0 + r, rows - 1);
+    const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C4) s[r] += (cache[r][i].x + cache[r][i].y) + (cache[r][i].z + cache[r][i].w);
+    }
+    for (int c = lane + 32 * LN_MAX_V4; c < C4; c += 32) {
+      const float4 v = xr[c];
+      s[r] += (v.x + v.y) + (v.z + v.w);
     }
   }
-  for (int c = lane + 32 * LN_MAX_V4; c < C4; c += 32) {
-    const float4 v = xr[c];
-    const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
-    q += (a * a + b * b) + (cc * cc + d * d);
-  }
-  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(C) + eps);
-  const long long bidx = row / rows_per_batch;
-  const long long t = row - bidx * rows_per_batch;
-  uint2* orow = reinterpret_cast<uint2*>(out16 + bidx * out_batch_pitch + t * ld16);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
-  auto emit = [&](int c, const float4& v) {
-    const float4 g = __ldg(g4 + c), bb = __ldg(b4 + c);
-    float y0 = (v.x - mean) * rstd * g.x + bb.x;
-    float y1 = (v.y - mean) * rstd * g.y + bb.y;
-    float y2 = (v.z - mean) * rstd * g.z + bb.z;
-    float y3 = (v.w - mean) * rstd * g.w + bb.w;
-    if (apply_silu) { y0 = silu(y0); y1 = silu(y1); y2 = silu(y2); y3 = silu(y3); }
-    uint2 h;
-    h.x = pack_half2(y0, y1);
-    h.y = pack_half2(y2, y3);
-    orow[c] = h;
-  };
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
-    const int c = lane + 32 * i;
-    if (c < C4) emit(c, cache[i]);
+  for (int r = 0; r < RPW; ++r) {
+    const long long row = row0 + r;
+    const float4* xr = reinterpret_cast<const float4*>(x + min(row, rows - 1) * ldx);
+    const float mean = warp_sum(s[r]) / static_cast<float>(C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C4) {
+        const float a = cache[r][i].x - mean, b = cache[r][i].y - mean, cc = cache[r][i].z - mean,
+                    d = cache[r][i].w - mean;
+        q += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    for (int c = lane + 32 * LN_MAX_V4; c < C4; c += 32) {
+      const float4 v = xr[c];
+      const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+      q += (a * a + b * b) + (cc * cc + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(C) + eps);
+    if (row >= rows) continue;   // (warp-uniform) duplicate of the last row
+    const long long bidx = row / rows_per_batch;
+    const long long t = row - bidx * rows_per_batch;
+    uint2* orow = reinterpret_cast<uint2*>(out16 + bidx * out_batch_pitch + t * ld16);
+    auto emit = [&](int c, const float4& v) {
+      const float4 g = __ldg(g4 + c), bb = __ldg(b4 + c);
+      float y0 = (v.x - mean) * rstd * g.x + bb.x;
+      float y1 = (v.y - mean) * rstd * g.y + bb.y;
+      float y2 = (v.z - mean) * rstd * g.z + bb.z;
+      float y3 = (v.w - mean) * rstd * g.w + bb.w;
+      if (apply_silu) { y0 = silu(y0); y1 = silu(y1); y2 = silu(y2); y3 = silu(y3); }
+      uint2 h;
+      h.x = pack_half2(y0, y1);
+      h.y = pack_half2(y2, y3);
+      orow[c] = h;
+    };
+#pragma unroll
+    for (int i = 0; i < LN_MAX_V4; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C4) emit(c, cache[r][i]);
+    }
+    for (int c = lane + 32 * LN_MAX_V4; c < C4; c += 32) emit(c, xr[c]);
   }
-  for (int c = lane + 32 * LN_MAX_V4; c < C4; c += 32) emit(c, xr[c]);
 }
 
 int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_per_batch, int C, const float* gamma,
@@ -170,9 +191,15 @@ int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_
                "layer_norm: C and pitches must be multiples of 4");
   if (rows == 0) return FRT2_OK;
   const int warps = 8;
-  const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
-  layer_norm_kernel<<<grid, warps * 32, 0, stream>>>(x, ldx, rows, rows_per_batch, C, gamma, beta, eps, apply_silu,
-                                                     out16, ld16, out_batch_pitch);
+  if (rows >= 4096) {
+    const unsigned grid = static_cast<unsigned>((rows + 2 * warps - 1) / (2 * warps));
+    layer_norm_kernel<2><<<grid, warps * 32, 0, stream>>>(x, ldx, rows, rows_per_batch, C, gamma, beta, eps, apply_silu,
+                                                          out16, ld16, out_batch_pitch);
+  } else {
+    const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
+    layer_norm_kernel<1><<<grid, warps * 32, 0, stream>>>(x, ldx, rows, rows_per_batch, C, gamma, beta, eps, apply_silu,
+                                                          out16, ld16, out_batch_pitch);
+  }
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;
 }

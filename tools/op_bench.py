@@ -85,3 +85,14 @@ def skinny(reps):
 
 if __name__ == "__main__" and sys.argv[1] == "skinny":
     skinny(int(sys.argv[2]) if len(sys.argv) > 2 else 200)
+
+
+def ln(reps, rows=192000, C=1024):
+    x = torch.randn(rows, C, device="cuda"); g = torch.ones(C, device="cuda"); b = torch.zeros(C, device="cuda")
+    o = torch.empty(rows, C, device="cuda", dtype=torch.half)
+    ms = timeit(lambda: N.check(lib.frt2_op_layer_norm(P(x), rows, C, P(g), P(b), 1e-5, 0, P(o), S())), reps)
+    print(f"layer_norm rows={rows} C={C}: {ms:.3f} ms  {rows * C * 6 / ms / 1e6:.0f} GB/s")
+
+
+if __name__ == "__main__" and sys.argv[1] == "ln":
+    ln(int(sys.argv[2]) if len(sys.argv) > 2 else 10)
