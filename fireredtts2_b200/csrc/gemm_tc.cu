@@ -87,7 +87,8 @@ __device__ __forceinline__ float gelu_fast(float x) {
   p = fmaf(p, z, 0.0422820123f);
   p = fmaf(p, z, 0.0705230784f);
   p = fmaf(p, z, 1.0f);
-  float r = __fdividef(1.0f, p);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
   r *= r; r *= r; r *= r; r *= r;       // p^-16
   const float erfv = copysignf(1.0f - r, x);
   return 0.5f * x * (1.0f + erfv);
@@ -96,21 +97,25 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // alpha, bias and activation on one 32-column chunk held by a thread (one output row)
 __device__ __forceinline__ void apply_chunk(const GemmKParams& p, const uint32_t (&r)[32], int n0, float (&v)[32]) {
   const bool full_chunk = n0 + 32 <= p.N;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
   if (p.bias != nullptr) {
     if (full_chunk && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 8; ++j) {   // one FFMA per element: acc * alpha + bias
         const float4 b = __ldg(b4 + j);
-        v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), p.alpha, b.x);
+        v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), p.alpha, b.y);
+        v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), p.alpha, b.z);
+        v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), p.alpha, b.w);
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) v[j] += __ldg(p.bias + n0 + j);
+        v[j] = fmaf(__uint_as_float(r[j]), p.alpha, (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f);
     }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
   }
   if (p.act == ACT_GELU) {
 #pragma unroll
