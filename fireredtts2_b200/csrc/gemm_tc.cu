@@ -76,22 +76,57 @@ struct GemmCfg {
       STAGES * STAGE_BYTES + EPI_WARPS * STAGING_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-// exact-erf GELU evaluated with the Abramowitz-Stegun 7.1.28 approximation erf(z) = 1 - (1 + a1 z + .. + a6 z^6)^-16
-// (|err| <= 3e-7, far below the fp16 rounding of the stored activation): 6 FMA + one MUFU.RCP + 4 squarings, i.e.
-// one special-function op per element instead of erff's branchy ~25 instructions.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float p = fmaf(z, 0.0000430638f, 0.0002765672f);
-  p = fmaf(p, z, 0.0001520143f);
-  p = fmaf(p, z, 0.0092705272f);
-  p = fmaf(p, z, 0.0422820123f);
-  p = fmaf(p, z, 0.0705230784f);
-  p = fmaf(p, z, 1.0f);
+// Packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2): two fp32 operations per issued instruction.  The epilogue of
+// the GELU GEMM is issue-bound (27 instructions per element measured), so halving the FMA-pipe instruction count of
+// the per-element math is what buys tensor-pipe time back.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b));
+  return d;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
   float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p));
-  r *= r; r *= r; r *= r; r *= r;       // p^-16
-  const float erfv = copysignf(1.0f - r, x);
-  return 0.5f * x * (1.0f + erfv);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+// exact-erf GELU on a pair of values, erf by Abramowitz-Stegun 7.1.28:
+//   erf(z) = 1 - (1 + a1 z + .. + a6 z^6)^-16,  |err| <= 3e-7  (far below the fp16 rounding of the stored activation)
+// 7 FFMA2 + 5 FMUL2 + 2 MUFU.RCP + sign handling per PAIR instead of erff's branchy ~25 instructions per value.
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  const f32x2 x = pk2(x0, x1);
+  const f32x2 z = pk2(fabsf(x0) * 0.70710678118654752440f, fabsf(x1) * 0.70710678118654752440f);
+  f32x2 p = fma2(z, pk2(0.0000430638f, 0.0000430638f), pk2(0.0002765672f, 0.0002765672f));
+  p = fma2(p, z, pk2(0.0001520143f, 0.0001520143f));
+  p = fma2(p, z, pk2(0.0092705272f, 0.0092705272f));
+  p = fma2(p, z, pk2(0.0422820123f, 0.0422820123f));
+  p = fma2(p, z, pk2(0.0705230784f, 0.0705230784f));
+  p = fma2(p, z, pk2(1.0f, 1.0f));
+  float p0, p1;
+  unpk2(p, p0, p1);
+  f32x2 r = pk2(rcp_approx(p0), rcp_approx(p1));
+  r = mul2(r, r); r = mul2(r, r); r = mul2(r, r); r = mul2(r, r);          // p^-16
+  float r0, r1;
+  unpk2(r, r0, r1);
+  // gelu = 0.5 x (1 + sign(x)(1 - r)) = 0.5 x + 0.5 |x| (1 - r)
+  const f32x2 one_m_r = pk2(1.0f - r0, 1.0f - r1);
+  const f32x2 hx = mul2(x, pk2(0.5f, 0.5f));
+  const f32x2 habs = pk2(fabsf(x0) * 0.5f, fabsf(x1) * 0.5f);
+  unpk2(fma2(habs, one_m_r, hx), x0, x1);
 }
 
 // alpha, bias and activation on one 32-column chunk held by a thread (one output row)
@@ -119,7 +154,7 @@ __device__ __forceinline__ void apply_chunk(const GemmKParams& p, const uint32_t
   }
   if (p.act == ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j]);
+    for (int j = 0; j < 32; j += 2) gelu_fast2(v[j], v[j + 1]);
   } else if (p.act == ACT_POLAR) {
     // columns come in (log-magnitude, phase) pairs: reference decoder.py:505-518
 #pragma unroll
