@@ -479,6 +479,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // p = 2^(s*scale - m_ref) as packed halves, written straight to the K-major SWIZZLE_128B P tile:
       // row r at r*128 B, 16-byte chunk c at (c ^ (r & 7))
       const float neg_m = -m_ref;
+      unsigned long long scale2, negm2;
+      asm("mov.b64 %0, {%1, %1};" : "=l"(scale2) : "f"(p.scale_log2));
+      asm("mov.b64 %0, {%1, %1};" : "=l"(negm2) : "f"(neg_m));
       __half2 acc[4];
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -488,7 +491,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int e = (c & 3) * 8 + 2 * u;
           const uint32_t s0 = (c < 4) ? sa[e] : sb[e];
           const uint32_t s1 = (c < 4) ? sa[e + 1] : sb[e + 1];
-          w[u] = exp2_f16x2(fmaf(__uint_as_float(s0), p.scale_log2, neg_m), fmaf(__uint_as_float(s1), p.scale_log2, neg_m));
+          // (s0, s1) * scale - m_ref as ONE packed fp32x2 FFMA2 (the loop is issue / MUFU co-bound)
+          unsigned long long xx;
+          asm("{\n\t.reg .b64 a;\n\tmov.b64 a, {%1, %2};\n\tfma.rn.f32x2 %0, a, %3, %4;\n\t}"
+              : "=l"(xx) : "r"(s0), "r"(s1), "l"(scale2), "l"(negm2));
+          float x0, x1;
+          asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
+          w[u] = exp2_f16x2(x0, x1);
         }
         const __half2 s01 = __hadd2(*reinterpret_cast<const __half2*>(&w[0]), *reinterpret_cast<const __half2*>(&w[1]));
         const __half2 s23 = __hadd2(*reinterpret_cast<const __half2*>(&w[2]), *reinterpret_cast<const __half2*>(&w[3]));
