@@ -8,7 +8,7 @@ utterances = tokens (64,16,375) -> 1920 audio-seconds, C0 architecture, random-i
 N > 1 (torchrun): every rank decodes its own batch (utterances are independent: weak scaling, no collective in
 the data path); time = max over ranks.  One JSON line is printed by rank 0.
 
---impl reference times the reference algorithm's CPU port (oracle/, numpy, all host threads) on a bounded sample of
+--impl reference times the reference algorithm's CPU port (oracle/codec_oracle_torch.py, ATen CPU ops, all host threads) on a bounded sample of
 the same workload; the reference itself is pure PyTorch and /root/reference does not exist on the GPU box.
 """
 from __future__ import annotations
@@ -93,16 +93,20 @@ class ClockSampler:
 
 
 def cpu_port_throughput(sd, cfg, B, L, reps, warm):
-    """The oracle (numpy port of the reference algorithm) on the host cores: audio-s/s on a (B,16,L) sample."""
+    """The reference algorithm on the host cores (oracle/codec_oracle_torch.py: the same ATen CPU kernels the reference
+    dispatches to, all host threads): audio-s/s on a (B,16,L) sample."""
+    import torch
     from fireredtts2_b200.weights import synthetic_tokens
-    from oracle import codec_oracle as O
+    from oracle import codec_oracle_torch as OT
+    torch.set_num_threads(os.cpu_count() or 1)
+    sdt = OT.to_torch(sd)
     tok = synthetic_tokens(cfg, B, L, 1234)
     for _ in range(warm):
-        O.decode(sd, tok, cfg.num_heads, cfg.hop_length)
+        OT.decode(sdt, tok, cfg.num_heads, cfg.hop_length)
     ts = []
     for _ in range(reps):
         t0 = time.perf_counter()
-        O.decode(sd, tok, cfg.num_heads, cfg.hop_length)
+        OT.decode(sdt, tok, cfg.num_heads, cfg.hop_length)
         ts.append(time.perf_counter() - t0)
     audio_s = B * L / 12.5
     return audio_s, ts
@@ -125,7 +129,7 @@ def run_reference(args):
            "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": WORKLOAD,
            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                            "sample": f"{B} x 30 s utterance (tokens ({B},16,{L})) per step, numpy/OpenBLAS, all host threads"},
+                            "sample": f"{B} x 30 s utterance (tokens ({B},16,{L})) per step, torch CPU ops (ATen/oneDNN/MKL), all host threads"},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
@@ -243,7 +247,7 @@ def run_ours(args):
               "max_abs": float(np.abs(ref - a_gpu).max()), "ref_peak": float(np.abs(ref).max()), "gate_snr_db": 40.0}
     cores = os.cpu_count() or 1
     cpu = {"value": audio_s / min(ts), "unit": UNIT, "cores": cores, "kind": "port",
-           "sample": "config 1: one 10 s utterance (tokens (1,16,125)), numpy/OpenBLAS oracle, best of 3 after 1 warm-up"}
+           "sample": "config 1: one 10 s utterance (tokens (1,16,125)), torch-CPU port of the reference, best of 3 after 1 warm-up"}
 
     # ---- first-chunk latency (BASELINE configs[1]): batch 1, one token, host token in -> host audio out ----
     lat = first_chunk_latency(codec, cfg, dev, reps=args.latency_reps)

@@ -92,3 +92,13 @@ def test_batch_row_equals_single():
     y = O.decode(sd, g["tokens"], cfg.num_heads)
     y0 = O.decode(sd, g["tokens"][1:2], cfg.num_heads)
     assert np.abs(y[1:2] - y0).max() < TOL_AUDIO
+
+
+@pytest.mark.parametrize("case", cases("offline") + cases("reference_init"), ids=lambda c: c["name"])
+def test_torch_cpu_port_matches_reference(case):
+    """The torch-CPU port used as the timed CPU baseline (bench.py) against the same golden vectors."""
+    from oracle import codec_oracle_torch as OT
+    cfg, sd, g = load_case(case)
+    y = OT.decode(OT.to_torch(sd), g["tokens"], cfg.num_heads, cfg.hop_length).numpy()
+    assert y.shape == g["audio"].shape
+    assert np.abs(y - g["audio"]).max() < TOL_AUDIO
