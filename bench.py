@@ -217,9 +217,20 @@ def run_ours(args):
     g = prof["gemm_tc"]
     achieved = g["flops"] / (g["ms"] * 1e-3) / 1e12 if g["ms"] > 0 else 0.0
     peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
-    roofline = {"kernel": "gemm_tc_kernel (tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM)", "bound": "tensor",
+    traffic = None   # DRAM bytes per launch of this kernel from the committed ncu capture of the same workload
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_dram_traffic.json")) as f:
+            tk = json.load(f)["kernels"]
+        traffic = [v["traffic_gb_per_launch"] * 1e9 for k, v in tk.items() if "gemm_tc" in k][0]
+    except Exception:
+        pass
+    roofline = {"kernel": "gemm_tc2_kernel (tcgen05.mma.cta_group::2 kind::f16, fp16 operands, fp32 accumulate in TMEM)",
+                "bound": "tensor",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "traffic": None, "peak_source": pk_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu, profiles/r01_dram_traffic.json)",
+                "algorithmic_bytes_per_launch": g["bytes"] / max(1, g["launches"]),
+                "algorithmic_flops_per_launch": g["flops"] / max(1, g["launches"]),
+                "peak_source": pk_src + ", bf16_tflops_sustained (kernel timed inside a long step)",
                 "launches": g["launches"], "avg_launch_ms": g["ms"] / max(1, g["launches"]),
                 "share_of_step": g["ms"] / ms_dev}
     kernels = {}
