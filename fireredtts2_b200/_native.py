@@ -42,6 +42,7 @@ SIGNATURES = {
     "frt2_finalize": (_i, [_p]),
     "frt2_destroy": (None, [_p]),
     "frt2_decode": (_i, [_p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _p, _i64, _p]),
+    "frt2_decode_pcm16": (_i, [_p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _p, _i64, _p]),
     "frt2_stream_create": (_i, [_p, _i, _i, C.POINTER(_p)]),
     "frt2_stream_reset": (_i, [_p]),
     "frt2_stream_destroy": (None, [_p]),

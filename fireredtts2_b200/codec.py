@@ -137,15 +137,17 @@ class RedCodecB200(torch.nn.Module):
 
     # ------------------------------------------------------------------ reference API
     @torch.inference_mode()
-    def decode(self, tokens: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """RedCodecInfer.decode (reference model.py:307-324).  ``lengths`` (B,) int32 token counts is an
-        extension for ragged batches: item b equals a standalone decode of its first lengths[b] tokens."""
+    def decode(self, tokens: torch.Tensor, lengths: Optional[torch.Tensor] = None, pcm16: bool = False) -> torch.Tensor:
+        """RedCodecInfer.decode (reference model.py:307-324).  Extensions: ``lengths`` (B,) int32 token counts for
+        ragged batches (item b equals a standalone decode of its first lengths[b] tokens); ``pcm16=True`` returns
+        the int16 PCM of the reference's wire format, ``(audio * 32767).astype(int16)``, straight from the kernel."""
         tokens = self._prep_tokens(tokens)
         B, nq, L = tokens.shape
+        out_dtype = torch.int16 if pcm16 else torch.float32
         if L == 0 or B == 0:
-            return torch.zeros((B, 0), dtype=torch.float32, device=tokens.device)
+            return torch.zeros((B, 0), dtype=out_dtype, device=tokens.device)
         with torch.cuda.device(self.device_index):
-            audio = torch.empty((B, self.cfg.samples_per_token * L), dtype=torch.float32, device=tokens.device)
+            audio = torch.empty((B, self.cfg.samples_per_token * L), dtype=out_dtype, device=tokens.device)
             lptr = None
             if lengths is not None:
                 lengths = lengths.to(device=tokens.device, dtype=torch.int32).contiguous()
@@ -153,9 +155,9 @@ class RedCodecB200(torch.nn.Module):
                     raise ValueError("lengths must have B entries")
                 lptr = C.c_void_p(lengths.data_ptr())
             sB, sQ, sL = tokens.stride()
-            N.check(self._lib.frt2_decode(self._h, C.c_void_p(tokens.data_ptr()), tokens.element_size(), sB, sQ, sL,
-                                          B, nq, L, lptr, C.c_void_p(audio.data_ptr()), audio.stride(0),
-                                          self._cuda_stream()))
+            fn = self._lib.frt2_decode_pcm16 if pcm16 else self._lib.frt2_decode
+            N.check(fn(self._h, C.c_void_p(tokens.data_ptr()), tokens.element_size(), sB, sQ, sL,
+                       B, nq, L, lptr, C.c_void_p(audio.data_ptr()), audio.stride(0), self._cuda_stream()))
             self._maybe_check()
         return audio
 

@@ -136,6 +136,7 @@ struct OlaDesc {
   int len_mul;
   float* audio;          // (B, *)
   int64_t audio_pitch;
+  int16_t* pcm16;        // optional: write int16 PCM = trunc(sample * 32767) (saturated) instead of fp32, same pitch
   int B, T, n_fft, hop;
   int first, last;       // streaming flags; offline == first && last
   const int* ctrl;       // optional device {frames consumed so far, last flag}: overrides first/last at run time

@@ -237,6 +237,8 @@ struct Handle {
     if (id >= 0) cudaEventRecord(prof[id].b, st);
   }
 
+  int16_t* pcm16_out = nullptr;  // set (under the mutex) by frt2_decode_pcm16 for the next pipeline run
+
   // workspace arena (grow-only)
   uint8_t* ws = nullptr;
   size_t ws_bytes = 0;
@@ -831,6 +833,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   OlaDesc od{};
   od.frames = frames32; od.frames_batch_pitch = static_cast<int64_t>(T) * n_fft; od.window = window;
   od.lengths = lengths; od.len_mul = 8; od.audio = audio; od.audio_pitch = audio_pitch; od.B = B; od.T = T;
+  od.pcm16 = pcm16_out;
   od.n_fft = n_fft; od.hop = hop;
   if (streaming) {
     od.tail = s->tail; od.first = (s->n_tokens == 0); od.last = last;
@@ -1006,6 +1009,21 @@ int frt2_decode(frt2_handle* hh, const void* tokens, int idx_bytes, int64_t sB, 
   FRT2_CUDA_OK(cudaSetDevice(h.device));
   return h.pipeline(tokens, idx_bytes, sB, sQ, sL, B, nq, L, lengths, audio, audio_pitch, nullptr, 1,
                     static_cast<cudaStream_t>(cuda_stream));
+}
+
+int frt2_decode_pcm16(frt2_handle* hh, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
+                      int nq, int L, const int32_t* lengths, int16_t* pcm, int64_t pcm_pitch, void* cuda_stream) {
+  FRT2_REQUIRE(hh, FRT2_ERR_BAD_ARG, "null handle");
+  Handle& h = hh->h;
+  FRT2_TRY(check_decode_args(h, tokens, idx_bytes, B, nq, L, reinterpret_cast<const float*>(pcm)));
+  FRT2_REQUIRE(pcm_pitch >= static_cast<int64_t>(8) * h.hop * L, FRT2_ERR_BAD_ARG, "pcm_pitch too small");
+  std::lock_guard<std::mutex> lk(h.mu);
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  h.pcm16_out = pcm;
+  const int rc = h.pipeline(tokens, idx_bytes, sB, sQ, sL, B, nq, L, lengths, nullptr, pcm_pitch, nullptr, 1,
+                            static_cast<cudaStream_t>(cuda_stream));
+  h.pcm16_out = nullptr;
+  return rc;
 }
 
 int frt2_stream_create(frt2_handle* hh, int B, int max_tokens, frt2_stream** out) {
@@ -1304,7 +1322,7 @@ int frt2_op_overlap_add(const float* frames, const float* tail, const float* win
   OlaDesc d{};
   d.frames = frames; d.frames_batch_pitch = static_cast<int64_t>(T) * n_fft; d.tail = tail; d.window = window;
   d.lengths = lengths; d.len_mul = 8; d.audio = audio; d.audio_pitch = audio_pitch; d.B = B; d.T = T; d.n_fft = n_fft;
-  d.hop = hop; d.first = first; d.last = last;
+  d.hop = hop; d.first = first; d.last = last; d.pcm16 = nullptr;
   return istft_overlap_add(d, static_cast<cudaStream_t>(cuda_stream));
 }
 

@@ -234,9 +234,10 @@ __global__ void __launch_bounds__(256) overlap_add_kernel(OlaDesc d, int ntail, 
     TF = min(TF, d.lengths[b] * d.len_mul);
     n_out = TF * d.hop;
   }
-  float* out = d.audio + static_cast<long long>(b) * d.audio_pitch + n;
+  const long long oidx = static_cast<long long>(b) * d.audio_pitch + n;
   if (n >= n_out) {
-    *out = 0.f;
+    if (d.pcm16 != nullptr) d.pcm16[oidx] = 0;
+    else d.audio[oidx] = 0.f;
     return;
   }
   const int m = n + start;
@@ -255,7 +256,14 @@ __global__ void __launch_bounds__(256) overlap_add_kernel(OlaDesc d, int ntail, 
     y += fr[off];
     env += w * w;
   }
-  *out = y / env;
+  const float smp = y / env;
+  if (d.pcm16 != nullptr) {
+    // the reference's wire format: (audio * 32767).astype(np.int16) (enhanced_fireredtts2.py:603,655) — truncation
+    // toward zero; out-of-range samples saturate here instead of wrapping
+    d.pcm16[oidx] = static_cast<int16_t>(__float2int_rz(fminf(fmaxf(smp * 32767.0f, -32768.0f), 32767.0f)));
+  } else {
+    d.audio[oidx] = smp;
+  }
 }
 
 // new tail = last 3 frames of [old tail | frames]; T >= 3 always (a token is 8 frames) so it is a plain copy

@@ -70,6 +70,12 @@ void frt2_destroy(frt2_handle* h);
 int frt2_decode(frt2_handle* h, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
                 int nq, int L, const int32_t* lengths, float* audio, int64_t audio_pitch, void* cuda_stream);
 
+/* Same decode, but the waveform is emitted directly as the int16 PCM of the reference's wire format,
+ * pcm = (int16) trunc(sample * 32767) ((audio * 32767).astype(np.int16), enhanced_fireredtts2.py:603,655), saturated
+ * instead of wrapped for out-of-range samples: half the device->host bytes of the fp32 waveform. */
+int frt2_decode_pcm16(frt2_handle* h, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
+                      int nq, int L, const int32_t* lengths, int16_t* pcm, int64_t pcm_pitch, void* cuda_stream);
+
 /* ---- streaming decode: RedCodecInfer.decode_one_token (model.py:326-376) ----
  * The stream object owns what the reference keeps in cache_dict (up_conv_cache, bb_conv_cache1/2, bb_kv_cache,
  * is_cache) in HBM, updated in place. */

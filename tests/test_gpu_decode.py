@@ -197,3 +197,30 @@ def test_graph_replay_equals_kernel_by_kernel():
     assert np.array_equal(outs[("product", 1)], outs[("product", 0)])
     ref = O.decode(sd, tok.cpu().numpy(), cfg.num_heads, cfg.hop_length)
     _gate("graph-stream-24-vs-offline", ref, outs[("product", 0)])
+
+
+def test_pcm16_output_is_the_reference_wire_format():
+    """decode(pcm16=True) == (decode() * 32767).astype(int16), the reference's wire conversion
+    (enhanced_fireredtts2.py:603,655), bit for bit."""
+    case = cases("offline")[0]
+    cfg, sd, g = load_case(case)
+    codec = build_codec(cfg, sd)
+    tok = torch.from_numpy(g["tokens"]).cuda()
+    f32 = to_np(codec.decode(tok))
+    pcm = codec.decode(tok, pcm16=True).cpu().numpy()
+    assert pcm.dtype == np.int16 and pcm.shape == f32.shape
+    assert np.array_equal(pcm, (f32 * 32767).astype(np.int16))
+
+
+def test_long_utterance_against_oracle():
+    """A 24 s utterance (T = 2400 frames): many query-tile pairs / key tiles in the block-causal attention and many
+    M tiles per item in the batched conv GEMMs; compared with the oracle on the same seeded inputs."""
+    from fireredtts2_b200.config import SMALL
+    from fireredtts2_b200.weights import synthetic_state_dict, synthetic_tokens
+    cfg = SMALL
+    sd = synthetic_state_dict(cfg, 5)
+    tok = synthetic_tokens(cfg, 2, 300, 9)
+    codec = build_codec(cfg, sd)
+    a = to_np(codec.decode(torch.from_numpy(tok).cuda()))
+    ref = O.decode(sd, tok, cfg.num_heads, cfg.hop_length)
+    _gate("small_B2_L300/audio", ref, a)

@@ -19,7 +19,7 @@ run ops_attn_tc 600 tests/test_gpu_ops.py -k "attention and tc"
 run decode_simt 900 tests/test_gpu_decode.py -k "offline_decode and simt"
 run decode_tcgemm 900 tests/test_gpu_decode.py -k "offline_decode and tc_gemm"
 run decode_product 900 tests/test_gpu_decode.py -k "offline_decode and product"
-run decode_misc 900 tests/test_gpu_decode.py -k "rvq or index or varlen"
+run decode_misc 900 tests/test_gpu_decode.py -k "rvq or index or varlen or pcm16"
 run decode_stream 900 tests/test_gpu_decode.py -k "stream or graph"
 run decode_c0 900 tests/test_gpu_decode.py -k "c0"
 timeout 600 python __graft_entry__.py --smoke > "$OUT/smoke.log" 2>&1; echo "smoke exit=$?" | tee -a "$OUT/summary.txt"
