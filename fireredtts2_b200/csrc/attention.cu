@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(NSPLIT == 1 ? 128 : NSPLIT * 32) attention_war
   constexpr int QW = (NSPLIT == 1) ? 4 : 1;   // query blocks per CTA
   __shared__ float sq[QW][8][HD];
   __shared__ float s_part[NSPLIT == 1 ? 1 : NSPLIT][8][HD + 2];
+  pdl_trigger();   // a following PDL-launched kernel (streaming skinny GEMM) may start its weight prefetch
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nblk = a.Tq >> 3;
   const int qslot = (NSPLIT == 1) ? warp : 0;

@@ -91,7 +91,28 @@ struct GemmDesc {
   int64_t ld16;
   const int* out_row_off; // optional device int: added to every output row index at run time (streaming KV append
                           // inside a captured CUDA graph: the write position lives in HBM, not in a kernel argument)
+  // optional second fp16 destination (gemm_skinny only): columns >= split_col go to out16_b at column (n - split_col)
+  // with their own pitches / run-time row offset — Q and K|V of the streaming step come out of ONE launch, Q into the
+  // chunk buffer and K|V appended to the HBM state
+  int split_col;
+  __half* out16_b;
+  int64_t ld16_b, pitch16_b;
+  const int* row_off_b;
+  // optional fused LayerNorm(+SiLU) prologue (gemm_skinny only, ntaps == 1): the A rows are LN(ln_x) computed on the
+  // fly from the fp32 residual stream (rows at ln_x + m*ln_ldx) instead of being read from A
+  const float* ln_x;
+  int64_t ln_ldx;
+  const float* ln_gamma;
+  const float* ln_beta;
+  float ln_eps;
+  int ln_silu;
 };
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor is still running; it must execute pdl_wait() before touching anything the predecessor
+// wrote.  pdl_trigger() lets the NEXT kernel of the stream begin its predecessor-independent prologue early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 int gemm_tc(const GemmDesc& g, cudaStream_t stream);    // tcgen05 / TMEM / TMA path (product)
 int gemm_ref(const GemmDesc& g, cudaStream_t stream);   // plain SIMT fp32-accumulate check kernel (tests only)

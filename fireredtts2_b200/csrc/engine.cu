@@ -3,6 +3,7 @@
 // (reference RedCodecInfer.decode_one_token + cache_dict, codec/model.py:326-376).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -710,13 +711,22 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     for (int i = 3; i < 11; ++i) cb[i] = {n16, 0, static_cast<int64_t>(T) * E};
   }
 
+  struct LnFuse { const float* x; const float* g; const float* b; float eps; };
+  // With <= 16 rows (the per-token streaming step) the GEMMs run on the skinny weight-streaming kernel, which can
+  // compute LayerNorm on the fly from the fp32 residual stream: the separate LN launch (and its round trip) goes.
+  static const bool no_lnfuse = (getenv("FRT2_NO_LNFUSE") != nullptr);   // A/B switch for measurements
+  const bool fuse_ln = (M <= 16) && !no_lnfuse && !(debug & (DBG_GEMM_REF | DBG_NO_SKINNY | DBG_TAPS));
   auto flat_gemm = [&](const __half* A, int64_t rows, int Kdim, const __half* W, int N, const float* bias, int act,
-                       const float* resid, float* out32, __half* out16, int64_t ld16, float alpha = 1.0f) {
+                       const float* resid, float* out32, __half* out16, int64_t ld16, float alpha = 1.0f,
+                       const LnFuse* ln = nullptr) {
     GemmDesc g{};
     g.A = A; g.a_row_pitch = Kdim; g.a_batch_pitch = 0; g.rows_a = static_cast<int>(rows); g.batches = 1;
     g.Kc = Kdim; g.ntaps = 1; g.row_shift = 0; g.W = W; g.N = N; g.rows_out = static_cast<int>(rows);
     g.pitch32 = 0; g.pitch16 = 0; g.alpha = alpha; g.bias = bias; g.act = act; g.resid = resid;
     g.out32 = out32; g.ld32 = N; g.out16 = out16; g.ld16 = ld16;
+    if (ln != nullptr) {
+      g.ln_x = ln->x; g.ln_ldx = Kdim; g.ln_gamma = ln->g; g.ln_beta = ln->b; g.ln_eps = ln->eps; g.ln_silu = 0;
+    }
     return run_gemm(g, st);
   };
   // causal conv over cb[i] with `taps` taps producing `rows` rows per item
@@ -782,27 +792,41 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   // ---- 12 pre-LN transformer layers ----
   for (int i = 0; i < nl; ++i) {
     const LayerW& w = layers[i];
-    FRT2_TRY(run_ln(x32, M, static_cast<int>(M), w.ln1_g, w.ln1_b, 1e-5f, 0, n16, 0, st));
+    const LnFuse ln1{x32, w.ln1_g, w.ln1_b, 1e-5f};
+    const LnFuse ln2{x32, w.ln2_g, w.ln2_b, 1e-5f};
+    if (!fuse_ln) FRT2_TRY(run_ln(x32, M, static_cast<int>(M), w.ln1_g, w.ln1_b, 1e-5f, 0, n16, 0, st));
     AttnDesc a{};
     a.B = B; a.H = H; a.hd = hd; a.Tq = T; a.out = o16; a.o_row_pitch = E; a.o_batch_pitch = xp;
     a.scale = 1.0f / std::sqrt(static_cast<float>(hd));
     if (!streaming) {
-      FRT2_TRY(flat_gemm(n16, M, E, w.w_qkv, 3 * E, w.b_qkv, ACT_NONE, nullptr, nullptr, qkv16, 3 * E));
+      FRT2_TRY(flat_gemm(n16, M, E, w.w_qkv, 3 * E, w.b_qkv, ACT_NONE, nullptr, nullptr, qkv16, 3 * E, 1.0f,
+                         fuse_ln ? &ln1 : nullptr));
       a.q = qkv16; a.q_row_pitch = 3 * E; a.q_batch_pitch = static_cast<int64_t>(T) * 3 * E;
       a.k = qkv16 + E; a.v = qkv16 + 2 * E; a.kv_row_pitch = 3 * E; a.kv_batch_pitch = a.q_batch_pitch;
       a.Tk = T; a.q_pos0 = 0; a.block_causal = 1;
     } else {
       // Q for the chunk; K|V appended in place to the HBM state of this layer (no re-copy: reference
       // whisper.py:100-104 + decoder.py:306 re-concatenate the whole cache every step)
-      FRT2_TRY(flat_gemm(n16, M, E, w.w_qkv, E, w.b_qkv, ACT_NONE, nullptr, nullptr, qkv16, E));
       GemmDesc g{};
       g.A = n16; g.a_row_pitch = E; g.a_batch_pitch = xp; g.rows_a = T; g.batches = B; g.Kc = E; g.ntaps = 1;
-      g.row_shift = 0; g.W = w.w_qkv + static_cast<int64_t>(E) * E; g.N = 2 * E; g.rows_out = T; g.alpha = 1.0f;
-      g.bias = w.b_qkv + E; g.act = ACT_NONE; g.resid = nullptr; g.out32 = nullptr; g.ld32 = 0; g.pitch32 = 0;
-      g.ld16 = 2 * E; g.pitch16 = s->kv_pitch();
-      if (graph_mode) { g.out16 = s->kv[i]; g.out_row_off = s->ctrl; }
-      else            { g.out16 = s->kv[i] + static_cast<int64_t>(pos) * 2 * E; }
-      FRT2_TRY(run_gemm(g, st));
+      g.row_shift = 0; g.rows_out = T; g.alpha = 1.0f; g.act = ACT_NONE; g.resid = nullptr; g.out32 = nullptr;
+      g.ld32 = 0; g.pitch32 = 0;
+      if (fuse_ln) {   // global row m = b*T + r is also the row of x32: LayerNorm computed inside the projection
+        g.ln_x = x32; g.ln_ldx = E; g.ln_gamma = w.ln1_g; g.ln_beta = w.ln1_b; g.ln_eps = 1e-5f; g.ln_silu = 0;
+      }
+      __half* kv_dst = graph_mode ? s->kv[i] : s->kv[i] + static_cast<int64_t>(pos) * 2 * E;
+      const int* kv_off = graph_mode ? s->ctrl : nullptr;
+      if (fuse_ln) {
+        // skinny path: ONE launch for q|k|v, columns >= E routed to the K|V state
+        g.W = w.w_qkv; g.N = 3 * E; g.bias = w.b_qkv; g.out16 = qkv16; g.ld16 = E; g.pitch16 = xp;
+        g.split_col = E; g.out16_b = kv_dst; g.ld16_b = 2 * E; g.pitch16_b = s->kv_pitch(); g.row_off_b = kv_off;
+        FRT2_TRY(run_gemm(g, st));
+      } else {
+        FRT2_TRY(flat_gemm(n16, M, E, w.w_qkv, E, w.b_qkv, ACT_NONE, nullptr, nullptr, qkv16, E));
+        g.W = w.w_qkv + static_cast<int64_t>(E) * E; g.N = 2 * E; g.bias = w.b_qkv + E;
+        g.out16 = kv_dst; g.ld16 = 2 * E; g.pitch16 = s->kv_pitch(); g.out_row_off = kv_off;
+        FRT2_TRY(run_gemm(g, st));
+      }
       a.q = qkv16; a.q_row_pitch = E; a.q_batch_pitch = xp;
       a.k = s->kv[i]; a.v = s->kv[i] + E; a.kv_row_pitch = 2 * E; a.kv_batch_pitch = s->kv_pitch();
       a.Tk = pos + T; a.q_pos0 = pos; a.block_causal = 0;
@@ -810,22 +834,25 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     }
     FRT2_TRY(run_attn(a, st));
     FRT2_TRY(flat_gemm(o16, M, E, w.w_o, E, w.b_o, ACT_NONE, x32, x32, nullptr, 0));
-    FRT2_TRY(run_ln(x32, M, static_cast<int>(M), w.ln2_g, w.ln2_b, 1e-5f, 0, n16, 0, st));
-    FRT2_TRY(flat_gemm(n16, M, E, w.w_fc1, 4 * E, w.b_fc1, ACT_GELU, nullptr, nullptr, g16, 4 * E));
+    if (!fuse_ln) FRT2_TRY(run_ln(x32, M, static_cast<int>(M), w.ln2_g, w.ln2_b, 1e-5f, 0, n16, 0, st));
+    FRT2_TRY(flat_gemm(n16, M, E, w.w_fc1, 4 * E, w.b_fc1, ACT_GELU, nullptr, nullptr, g16, 4 * E, 1.0f,
+                       fuse_ln ? &ln2 : nullptr));
     FRT2_TRY(flat_gemm(g16, M, 4 * E, w.w_fc2, E, w.b_fc2, ACT_NONE, x32, x32, nullptr, 0));
     if (i == 0) FRT2_TRY(tap_f32("layer0", x32, M * E, st));
   }
   FRT2_TRY(tap_f32("layers", x32, M * E, st));
   FRT2_TRY(resblock(2));
   FRT2_TRY(resblock(3));
-  FRT2_TRY(run_ln(x32, M, static_cast<int>(M), fn_g, fn_b, 1e-6f, 0, n16, 0, st));
+  const LnFuse lnf{x32, fn_g, fn_b, 1e-6f};
+  if (!fuse_ln) FRT2_TRY(run_ln(x32, M, static_cast<int>(M), fn_g, fn_b, 1e-6f, 0, n16, 0, st));
   FRT2_TRY(tap_f16("final", n16, E, M, E, st));
   // ---- K5: head GEMM with polar epilogue -> windowed inverse DFT GEMM -> overlap-add ----
   if (spec_ld > 2 * n_bins) {
     FRT2_CUDA_OK(cudaMemset2DAsync(spec16 + 2 * n_bins, static_cast<size_t>(spec_ld) * 2, 0,
                                    static_cast<size_t>(spec_ld - 2 * n_bins) * 2, M, st));
   }
-  FRT2_TRY(flat_gemm(n16, M, E, w_head, 2 * n_bins, b_head, ACT_POLAR, nullptr, nullptr, spec16, spec_ld));
+  FRT2_TRY(flat_gemm(n16, M, E, w_head, 2 * n_bins, b_head, ACT_POLAR, nullptr, nullptr, spec16, spec_ld, 1.0f,
+                     fuse_ln ? &lnf : nullptr));
   FRT2_TRY(tap_f16("spec", spec16, spec_ld, M, 2 * n_bins, st));
   FRT2_TRY(flat_gemm(spec16, M, spec_ld, w_idft, n_fft, nullptr, ACT_NONE, nullptr, frames32, nullptr, 0,
                      1.0f / static_cast<float>(n_fft)));

@@ -5,6 +5,8 @@
 // A 128-row tcgen05 tile would leave all but N/256 SMs idle; here each CTA owns 8 output columns so a 1024-column
 // layer spreads over 128 SMs, each warp streams one weight row with coalesced 16-byte loads, the (im2col'd, causal)
 // activation rows sit in shared memory, and accumulation is fp32.  Same contract / epilogues as gemm_tc.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace frt2 {
@@ -41,6 +43,29 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(GemmDesc g, 
   const bool col_ok = n < g.N;
   const uint4* wrow = reinterpret_cast<const uint4*>(g.W + static_cast<long long>(col_ok ? n : 0) * Ktot);
 
+  // ---- predecessor-independent prologue: the first weight vectors of this warp's row are already in flight while
+  //      the previous kernel of the step is still running (PDL), and while the activations are staged below
+  constexpr int PRE = 4;
+  uint4 wpre[PRE];
+  {
+    const int kc8_first = min(kchunk, Ktot) >> 3;
+#pragma unroll
+    for (int u = 0; u < PRE; ++u) {
+      const int k8 = lane + 32 * u;
+      wpre[u] = (col_ok && k8 < kc8_first) ? __ldg(wrow + k8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  // the epilogue's bias values (thread t -> column t % 8, and its polar partner) are also predecessor-independent
+  float bias_c = 0.f, bias_p = 0.f;
+  if (g.bias != nullptr && threadIdx.x < MR * SK_COLS) {
+    const int c = threadIdx.x % SK_COLS;
+    const int nn = blockIdx.x * SK_COLS + c;
+    if (nn < g.N) bias_c = __ldg(g.bias + nn);
+    if ((nn ^ 1) < g.N) bias_p = __ldg(g.bias + (nn ^ 1));
+  }
+  pdl_wait();      // everything below may read what the previous kernel wrote
+  pdl_trigger();   // the next kernel may start its own weight prefetch now
+
   float acc[MR];
 #pragma unroll
   for (int m = 0; m < MR; ++m) acc[m] = 0.f;
@@ -48,26 +73,81 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(GemmDesc g, 
   for (int kc0 = 0; kc0 < Ktot; kc0 += kchunk) {
     const int kc = min(kchunk, Ktot - kc0);
     const int kc8 = kc >> 3;
-    // ---- activation chunk -> smem (causal taps gathered here: row m, tap j reads input row r + j + row_shift)
-    for (int e = threadIdx.x; e < MR * kc8; e += blockDim.x) {
-      const int m = e / kc8, k8 = e - m * kc8;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (m < mtot) {
-        const int b = m / g.rows_out, r = m - b * g.rows_out;
-        const int kk = kc0 + k8 * 8;
-        const int tap = kk / g.Kc, c = kk - tap * g.Kc;
-        const int src = r + tap + g.row_shift;
-        if (src >= 0 && src < g.rows_a)
-          v = *reinterpret_cast<const uint4*>(g.A + static_cast<long long>(b) * g.a_batch_pitch +
-                                              static_cast<long long>(src) * g.a_row_pitch + c);
+    if (g.ln_gamma != nullptr) {
+      // ---- fused LayerNorm(+SiLU): one warp per row, fp32 statistics, result straight into the fp16 A tile
+      //      (reference nn.LayerNorm eps 1e-5 / 1e-6: whisper.py:134,140, decoder.py:246)
+      for (int m = warp; m < MR; m += SK_WARPS) {
+        __half* arow = sA + static_cast<size_t>(m) * kchunk;
+        if (m >= mtot) {
+          for (int c = lane * 8; c < kc; c += 256) *reinterpret_cast<uint4*>(arow + c) = make_uint4(0u, 0u, 0u, 0u);
+          continue;
+        }
+        const float4* xr = reinterpret_cast<const float4*>(g.ln_x + static_cast<long long>(m) * g.ln_ldx);
+        const int C4 = g.Kc >> 2;
+        float s = 0.f;
+        for (int c = lane; c < C4; c += 32) {
+          const float4 v = xr[c];
+          s += (v.x + v.y) + (v.z + v.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / static_cast<float>(g.Kc);
+        float q = 0.f;
+        for (int c = lane; c < C4; c += 32) {
+          const float4 v = xr[c];
+          const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, d = v.w - mean;
+          q += (a * a + b * b) + (cc * cc + d * d);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q / static_cast<float>(g.Kc) + g.ln_eps);
+        const float4* g4 = reinterpret_cast<const float4*>(g.ln_gamma);
+        const float4* b4 = reinterpret_cast<const float4*>(g.ln_beta);
+        for (int c = lane; c < C4; c += 32) {
+          const float4 v = xr[c], gg = __ldg(g4 + c), bb = __ldg(b4 + c);
+          float y0 = (v.x - mean) * rstd * gg.x + bb.x, y1 = (v.y - mean) * rstd * gg.y + bb.y;
+          float y2 = (v.z - mean) * rstd * gg.z + bb.z, y3 = (v.w - mean) * rstd * gg.w + bb.w;
+          if (g.ln_silu) { y0 = silu(y0); y1 = silu(y1); y2 = silu(y2); y3 = silu(y3); }
+          uint2 h;
+          h.x = pack_half2(y0, y1);
+          h.y = pack_half2(y2, y3);
+          *reinterpret_cast<uint2*>(arow + 4 * c) = h;
+        }
       }
-      *reinterpret_cast<uint4*>(sA + static_cast<size_t>(m) * kchunk + k8 * 8) = v;
+    } else {
+      // ---- activation chunk -> smem (causal taps gathered here: row m, tap j reads input row r + j + row_shift)
+      for (int e = threadIdx.x; e < MR * kc8; e += blockDim.x) {
+        const int m = e / kc8, k8 = e - m * kc8;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (m < mtot) {
+          const int b = m / g.rows_out, r = m - b * g.rows_out;
+          const int kk = kc0 + k8 * 8;
+          const int tap = kk / g.Kc, c = kk - tap * g.Kc;
+          const int src = r + tap + g.row_shift;
+          if (src >= 0 && src < g.rows_a)
+            v = *reinterpret_cast<const uint4*>(g.A + static_cast<long long>(b) * g.a_batch_pitch +
+                                                static_cast<long long>(src) * g.a_row_pitch + c);
+        }
+        *reinterpret_cast<uint4*>(sA + static_cast<size_t>(m) * kchunk + k8 * 8) = v;
+      }
     }
     __syncthreads();
     if (col_ok) {
       const uint4* wp = wrow + (kc0 >> 3);
+#pragma unroll
+      for (int u = 0; u < PRE; ++u) {      // the prefetched vectors (first chunk) or fresh loads (later chunks)
+        const int k8 = lane + 32 * u;
+        if (k8 < kc8) {
+          const uint4 w = (kc0 == 0) ? wpre[u] : __ldg(wp + k8);
+#pragma unroll
+          for (int m = 0; m < MR; ++m) {
+            const uint4 a = *reinterpret_cast<const uint4*>(sA + static_cast<size_t>(m) * kchunk + k8 * 8);
+            acc[m] = dot8(w, a, acc[m]);
+          }
+        }
+      }
 #pragma unroll 4
-      for (int k8 = lane; k8 < kc8; k8 += 32) {
+      for (int k8 = lane + 32 * PRE; k8 < kc8; k8 += 32) {
         const uint4 w = __ldg(wp + k8);
 #pragma unroll
         for (int m = 0; m < MR; ++m) {
@@ -92,18 +172,15 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(GemmDesc g, 
     const int m = t / SK_COLS, c = t - m * SK_COLS;
     const int nn = blockIdx.x * SK_COLS + c;
     if (m < mtot && nn < g.N) {
-      auto pre = [&](int cc) {
-        const int n2 = blockIdx.x * SK_COLS + cc;
-        float v = sOut[m * SK_COLS + cc] * g.alpha;
-        if (g.bias != nullptr && n2 < g.N) v += __ldg(g.bias + n2);
-        return v;
+      auto pre = [&](int cc) {   // cc == c (own column) or c ^ 1 (polar partner): biases were prefetched
+        return fmaf(sOut[m * SK_COLS + cc], g.alpha, cc == c ? bias_c : bias_p);
       };
       float v = pre(c);
       if (g.act == ACT_GELU) {
         v = gelu_erf(v);
       } else if (g.act == ACT_POLAR) {   // (log-magnitude, phase) pairs: reference decoder.py:505-518
-        const float lm = (c & 1) ? pre(c - 1) : v;
-        const float ph = (c & 1) ? v : pre(c + 1);
+        const float lm = (c & 1) ? pre(c ^ 1) : v;
+        const float ph = (c & 1) ? v : pre(c ^ 1);
         const float mag = fminf(expf(lm), 100.0f);
         float sn, cs;
         sincosf(ph, &sn, &cs);
@@ -113,9 +190,15 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(GemmDesc g, 
       const int roff = (g.out_row_off != nullptr) ? __ldg(g.out_row_off) : 0;
       const long long o32 = static_cast<long long>(b) * g.pitch32 + static_cast<long long>(r + roff) * g.ld32 + nn;
       const long long o16 = static_cast<long long>(b) * g.pitch16 + static_cast<long long>(r + roff) * g.ld16 + nn;
-      if (g.resid != nullptr) v += g.resid[o32];
-      if (g.out32 != nullptr) g.out32[o32] = v;
-      if (g.out16 != nullptr) g.out16[o16] = to_half_sat(v);
+      if (g.split_col > 0 && nn >= g.split_col) {
+        const int roff_b = (g.row_off_b != nullptr) ? __ldg(g.row_off_b) : 0;
+        g.out16_b[static_cast<long long>(b) * g.pitch16_b + static_cast<long long>(r + roff_b) * g.ld16_b +
+                  (nn - g.split_col)] = to_half_sat(v);
+      } else {
+        if (g.resid != nullptr) v += g.resid[o32];
+        if (g.out32 != nullptr) g.out32[o32] = v;
+        if (g.out16 != nullptr) g.out16[o16] = to_half_sat(v);
+      }
     }
   }
 }
@@ -144,12 +227,27 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t stream) {
   const int Ktot = g.ntaps * g.Kc;
   const int kchunk = Ktot < SK_KCHUNK ? Ktot : SK_KCHUNK;
   const int grid = (g.N + SK_COLS - 1) / SK_COLS;
+  FRT2_REQUIRE(g.ln_gamma == nullptr || (g.ntaps == 1 && g.Kc <= SK_KCHUNK && g.Kc % 4 == 0 && g.ln_x != nullptr),
+               FRT2_ERR_BAD_ARG, "gemm_skinny: fused LayerNorm needs ntaps == 1 and Kc <= 4096");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(SK_WARPS * 32);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap the weight prefetch with the
+  attr[0].val.programmaticStreamSerializationAllowed = 1;            // tail of the previous kernel of the step
+  // Measured on B200 (tools/stream_bench.py): inside the captured per-token graph the programmatic edges cost ~100 us
+  // per step (1217 vs 1103 us) — early-resident dependents compete with the running kernel for SM slots — so PDL is
+  // opt-in (FRT2_PDL=1) and the default is plain stream order.
+  static const bool use_pdl = (getenv("FRT2_PDL") != nullptr);
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
   if (mtot <= 8) {
-    const size_t smem = static_cast<size_t>(8) * kchunk * 2 + 8 * SK_COLS * 4;
-    gemm_skinny_kernel<8><<<grid, SK_WARPS * 32, smem, stream>>>(g, mtot);
+    cfg.dynamicSmemBytes = static_cast<size_t>(8) * kchunk * 2 + 8 * SK_COLS * 4;
+    FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<8>, g, mtot));
   } else {
-    const size_t smem = static_cast<size_t>(16) * kchunk * 2 + 16 * SK_COLS * 4;
-    gemm_skinny_kernel<16><<<grid, SK_WARPS * 32, smem, stream>>>(g, mtot);
+    cfg.dynamicSmemBytes = static_cast<size_t>(16) * kchunk * 2 + 16 * SK_COLS * 4;
+    FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<16>, g, mtot));
   }
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;

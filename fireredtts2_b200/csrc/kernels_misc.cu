@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(128) rvq_gather_sum_kernel(const IdxT* __restr
                                                              float* __restrict__ sum32, __half* __restrict__ sum16,
                                                              float* __restrict__ rows, unsigned int* err_word) {
   __shared__ int s_idx[RVQ_TOK][RVQ_MAX_NQ];
+  pdl_trigger();   // a following PDL-launched kernel (streaming skinny GEMM) may start its weight prefetch
   const long long R = static_cast<long long>(B) * L;
   const long long r0 = static_cast<long long>(blockIdx.x) * RVQ_TOK;
   for (int e = threadIdx.x; e < RVQ_TOK * nq; e += blockDim.x) {
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
                                                          const float* __restrict__ beta, float eps, int apply_silu,
                                                          __half* __restrict__ out16, long long ld16,
                                                          long long out_batch_pitch) {
+  pdl_trigger();
   const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
   if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
