@@ -15,6 +15,8 @@
 //                  Used for the short-query streaming step and as the on-device check for attention_tc.
 #include <math_constants.h>
 
+#include <cstdlib>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -253,6 +255,40 @@ __device__ __forceinline__ uint32_t exp2_f16x2(float x0, float x1) {
 #endif
 }
 
+// 2^x for a packed pair on the FMA pipe: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax
+// polynomial (rel. err 7.5e-5); 2^n by adding n to the exponent field (LEA).  x is clamped to >= -125 first.
+__device__ __forceinline__ uint32_t exp2_poly_f16x2(unsigned long long xx) {
+  float x0, x1;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
+  x0 = fmaxf(x0, -125.0f);
+  x1 = fmaxf(x1, -125.0f);
+  unsigned long long x, t, n, f, pl;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
+  const float MAGIC = 12582912.0f;   // 1.5 * 2^23: adding it rounds to the nearest integer in the low mantissa bits
+  unsigned long long magic2, nmagic2, c3, c2, c1, c0, neg1;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(magic2) : "f"(MAGIC));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(nmagic2) : "f"(-MAGIC));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c3) : "f"(0.055179595f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(0.242611851f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c1) : "f"(0.693259533f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(c0) : "f"(0.999927984f));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(neg1) : "f"(-1.0f));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(magic2));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(n) : "l"(t), "l"(nmagic2));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(f) : "l"(n), "l"(neg1), "l"(x));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pl) : "l"(c3), "l"(f), "l"(c2));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pl) : "l"(pl), "l"(f), "l"(c1));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pl) : "l"(pl), "l"(f), "l"(c0));
+  uint32_t t0, t1, p0, p1;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(pl));
+  const float r0 = __uint_as_float(p0 + (t0 << 23));   // exponent += n  (the MAGIC bits shift out)
+  const float r1 = __uint_as_float(p1 + (t1 << 23));
+  uint32_t y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(r1), "f"(r0));
+  return y;
+}
+
 struct AttnKParams {
   int Tq, Tk, q_pos0, block_causal, H;
   float scale_log2;
@@ -260,6 +296,11 @@ struct AttnKParams {
   long long o_row_pitch, o_batch_pitch;
 };
 
+// EMU = pairs (of the 4 per 8-key chunk) whose exponentials are evaluated on the FMA pipe instead of the MUFU
+// (the softmax is MUFU / issue co-bound at head_dim 64: 8192 exponentials per 128 x 64 tile at 16 per clock per SM
+// cost twice the tile's tensor time), Cody-Waite split + degree-3 minimax polynomial on packed fp32x2, rel. error
+// 7.5e-5 — below the fp16 rounding of P.
+template <int EMU>
 __global__ void __launch_bounds__(AT_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
@@ -435,6 +476,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) ptx::mbar_arrive(a_s_empty);
 
       const int lim = limit - j * AT_BK;  // columns c <= lim are visible
+      const bool diag = __any_sync(0xffffffffu, lim < AT_BK - 1);   // masked (-inf) scores: MUFU path only
       if (lim < AT_BK - 1) {              // diagonal / last tile: mask (interior tiles skip this entirely)
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
@@ -497,8 +539,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           asm("{\n\t.reg .b64 a;\n\tmov.b64 a, {%1, %2};\n\tfma.rn.f32x2 %0, a, %3, %4;\n\t}"
               : "=l"(xx) : "r"(s0), "r"(s1), "l"(scale2), "l"(negm2));
           float x0, x1;
-          asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
-          w[u] = exp2_f16x2(x0, x1);
+          if (u < EMU && !diag) {
+            w[u] = exp2_poly_f16x2(xx);
+          } else {
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
+            w[u] = exp2_f16x2(x0, x1);
+          }
         }
         const __half2 s01 = __hadd2(*reinterpret_cast<const __half2*>(&w[0]), *reinterpret_cast<const __half2*>(&w[1]));
         const __half2 s23 = __hadd2(*reinterpret_cast<const __half2*>(&w[2]), *reinterpret_cast<const __half2*>(&w[3]));
@@ -557,7 +603,11 @@ int attention_tc_init() {
     g_attn_status = gemm_tc_init();
     if (g_attn_status != FRT2_OK) return;
     cudaError_t e =
-        cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+        cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error(std::string("cudaFuncSetAttribute(attention_tc_kernel): ") + cudaGetErrorString(e));
       g_attn_status = FRT2_ERR_CUDA;
@@ -601,7 +651,13 @@ int attention_tc(const AttnDesc& a, cudaStream_t stream) {
   p.o_row_pitch = a.o_row_pitch;
   p.o_batch_pitch = a.o_batch_pitch;
   dim3 grid((a.Tq + AT_BQ * AT_QT - 1) / (AT_BQ * AT_QT), a.H, a.B);
-  attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  // Measured (B=64, H=16, T=3000, tools/op_bench.py attn): EMU 0 / 1 / 2 -> 2.00 / 2.07 / 2.34 ms.  The softmax loop is
+  // issue-bound before it is MUFU-bound, so moving exponentials to the FMA pipe costs more issue slots than the
+  // MUFU time it frees; the default keeps every exponential on the MUFU.  (FRT2_ATTN_EMU=1|2 for A/B runs.)
+  static const int emu = getenv("FRT2_ATTN_EMU") ? atoi(getenv("FRT2_ATTN_EMU")) : 0;
+  if (emu <= 0) attention_tc_kernel<0><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  else if (emu == 1) attention_tc_kernel<1><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  else attention_tc_kernel<2><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;
 }
