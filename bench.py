@@ -29,9 +29,11 @@ sys.path.insert(0, ROOT)
 
 METRIC = "codec_decode_audio_seconds_per_second"
 UNIT = "audio-s/s"
-WORKLOAD = {"workload": "batch 64 x 30 s utterances, tokens (64,16,375) -> (64,720000) @24 kHz (BASELINE configs[2])",
-            "arch": "C0: rvq 16x2048x256 -> 512 -> 1024, E=1024, 12 layers, 16 heads, hop 240",
-            "batch": 64, "tokens_per_item": 375, "l2": "activations (>6 GB per step) exceed the 126 MB L2"}
+WORKLOAD = {"workload": "BASELINE configs[2]: batch 64 x 30 s utterances codec decode, tokens (64,16,375) -> waveform "
+                        "(64,720000) @24 kHz; reference codec architecture C0 (16 codebooks x 2048 x 256, E=1024, "
+                        "12 layers, 16 heads, hop 240), random-init weights, synthetic tokens",
+            "batch": 64, "tokens_per_item": 375, "audio_seconds_per_step": 1920,
+            "l2": "inputs larger than L2: activations (>6 GB per step) exceed the 126 MB L2, no flush needed"}
 
 
 def peaks():
