@@ -192,13 +192,24 @@ def run_ours(args):
     N.check(codec._lib.frt2_check_error(codec._h, codec._cuda_stream()))
 
     # ---- timed region 2: end to end through the public API with HOST buffers ("e2e") ----
+    # Every step: pinned host tokens -> device, decode, waveform -> pinned host.  The device->host copy of step i runs
+    # on a second stream while step i+1 decodes (two pinned buffers); everything has landed on the host before the
+    # clock stops.
+    host_audio2 = [host_audio, torch.empty_like(host_audio).pin_memory()]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for i in range(args.steps):
         d_tok = tok_host.to(dev, non_blocking=True)
         a = codec.decode(d_tok)
-        host_audio.copy_(a, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        done = torch.cuda.Event()
+        done.record(main_stream)
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done)
+            host_audio2[i & 1].copy_(a, non_blocking=True)
+        a.record_stream(copy_stream)
+    copy_stream.synchronize()
     barrier()
     ms_e2e = 1e3 * (time.perf_counter() - t0)
 
