@@ -14,6 +14,8 @@ ERR_BAD_ARG, ERR_BAD_DTYPE, ERR_INDEX_OOR, ERR_STATE_OVERFLOW, ERR_CUDA, ERR_MIS
 
 DBG_TAPS, DBG_GEMM_REF, DBG_ATTN_WARP, DBG_NO_GRAPH, DBG_NO_SKINNY = 1, 2, 4, 8, 16
 ACT_NONE, ACT_GELU, ACT_POLAR = 0, 1, 2
+SLOT_ACTIVE, SLOT_LAST, SLOT_RESET = 1, 2, 4
+POOL_MAX_SLOTS = 256
 PROF_GEMM, PROF_ATTN_TC, PROF_ATTN_WARP, PROF_LAYER_NORM, PROF_RVQ, PROF_OLA, PROF_GEMM_SKINNY, PROF_ALL = \
     0, 1, 2, 3, 4, 5, 6, -1
 PROF_NAMES = {PROF_GEMM: "gemm_tc", PROF_ATTN_TC: "attention_tc", PROF_ATTN_WARP: "attention_warp",
@@ -48,6 +50,11 @@ SIGNATURES = {
     "frt2_stream_destroy": (None, [_p]),
     "frt2_stream_tokens": (_i, [_p]),
     "frt2_decode_chunk": (_i, [_p, _p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _i64, C.POINTER(_i), _p]),
+    "frt2_decode_chunk_pcm16": (_i, [_p, _p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _i64, C.POINTER(_i), _p]),
+    "frt2_pool_create": (_i, [_p, _i, _i, C.POINTER(_p)]),
+    "frt2_pool_step": (_i, [_p, _p, _p, _i, _i64, _i64, _i, C.POINTER(C.c_int32), _p, _i, _i64,
+                            C.POINTER(C.c_int32), _p]),
+    "frt2_pool_slot_tokens": (_i, [_p, _i]),
     "frt2_export_state": (_i, [_p, _p, _p, _p, _p, _p, _p, _p]),
     "frt2_import_state": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p]),
     "frt2_rvq_gather": (_i, [_p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _p, _p]),

@@ -162,9 +162,10 @@ class RedCodecB200(torch.nn.Module):
         return audio
 
     @torch.inference_mode()
-    def decode_one_token(self, token: torch.Tensor, cache_dict: Dict[str, object], last_token: bool
-                         ) -> Tuple[torch.Tensor, Dict[str, object]]:
-        """RedCodecInfer.decode_one_token (reference model.py:326-376).
+    def decode_one_token(self, token: torch.Tensor, cache_dict: Dict[str, object], last_token: bool,
+                         pcm16: bool = False) -> Tuple[torch.Tensor, Dict[str, object]]:
+        """RedCodecInfer.decode_one_token (reference model.py:326-376).  Extension: ``pcm16=True`` returns the chunk
+        as the int16 PCM the reference's streaming front puts on the wire (enhanced_fireredtts2.py:603,655).
 
         ``cache_dict`` is ``{}`` on the first call.  The returned dict carries the opaque in-HBM state under
         ``"frt2_state"`` (updated in place — re-using an *old* dict to fork a stream is not supported; use
@@ -186,13 +187,13 @@ class RedCodecB200(torch.nn.Module):
                 raise ValueError("stream already received its last token")
             first = st.n_tokens == 0
             n = self.cfg.samples_per_token * Lc - self.cfg.istft_pad * first + self.cfg.istft_pad * bool(last_token)
-            audio = torch.empty((B, n), dtype=torch.float32, device=token.device)
+            audio = torch.empty((B, n), dtype=torch.int16 if pcm16 else torch.float32, device=token.device)
             n_out = C.c_int(0)
             sB, sQ, sL = token.stride()
-            N.check(self._lib.frt2_decode_chunk(self._h, st.ptr, C.c_void_p(token.data_ptr()), token.element_size(),
-                                                sB, sQ, sL, nq, Lc, int(bool(last_token)),
-                                                C.c_void_p(audio.data_ptr()), audio.stride(0), C.byref(n_out),
-                                                self._cuda_stream()))
+            fn = self._lib.frt2_decode_chunk_pcm16 if pcm16 else self._lib.frt2_decode_chunk
+            N.check(fn(self._h, st.ptr, C.c_void_p(token.data_ptr()), token.element_size(),
+                       sB, sQ, sL, nq, Lc, int(bool(last_token)),
+                       C.c_void_p(audio.data_ptr()), audio.stride(0), C.byref(n_out), self._cuda_stream()))
             assert n_out.value == n
             self._maybe_check()
             st.finished = bool(last_token)
@@ -203,6 +204,10 @@ class RedCodecB200(torch.nn.Module):
         pass the returned dict as ``cache_dict`` of the first ``decode_one_token`` call."""
         with torch.cuda.device(self.device_index):
             return {_STATE_KEY: _NativeStream(self, batch, max_tokens or self.stream_max_tokens)}
+
+    def new_pool(self, slots: int, max_tokens: Optional[int] = None) -> "StreamPool":
+        """A pool of ``slots`` concurrent streams that decode one token each per step (continuous batching)."""
+        return StreamPool(self, slots, max_tokens or self.stream_max_tokens)
 
     def reset_stream(self, cache_dict: Dict[str, object]) -> Dict[str, object]:
         """Return a used state to its initial (empty) condition for the next utterance."""
@@ -281,3 +286,124 @@ class RedCodecB200(torch.nn.Module):
         if n.value != out.numel():
             raise ValueError(f"tap {name} has {n.value} elements, expected {out.numel()}")
         return out
+
+
+class StreamPool:
+    """Continuous batching of concurrent ``decode_one_token`` streams (C ABI ``frt2_pool_*``).
+
+    The reference decodes concurrent requests one after the other (one worker thread, enhanced_fireredtts2.py:199-203).
+    A pool keeps ``slots`` independent streaming states (reference cache_dict, model.py:346-375) in HBM and advances
+    all active ones by one token per ``step`` in a single batched launch sequence — each slot at its own position of
+    its own stream, joining and leaving at any step.  A slot's samples do not depend on what the other slots do.
+
+        pool = codec.new_pool(32)
+        a = pool.open()                                  # claim a free slot
+        out = pool.step({a: tok_a, b: tok_b}, last=[b])  # {slot: (nq,) or (nq,1) int tensor} -> {slot: audio (n,)}
+        pool.close(a)                                    # release (implicit after ``last``)
+    """
+
+    def __init__(self, codec: RedCodecB200, slots: int, max_tokens: int):
+        if not 1 <= slots <= N.POOL_MAX_SLOTS:
+            raise ValueError(f"slots must be in [1, {N.POOL_MAX_SLOTS}]")
+        self.codec = codec
+        self.slots = slots
+        self.max_tokens = max_tokens
+        self.ptr = C.c_void_p()
+        with torch.cuda.device(codec.device_index):
+            N.check(codec._lib.frt2_pool_create(codec._h, slots, max_tokens, C.byref(self.ptr)))
+            dev = torch.device("cuda", codec.device_index)
+            self._tok = torch.zeros((slots, codec.cfg.num_quantizers), dtype=torch.int32, device=dev)
+            self._tok_host = torch.zeros((slots, codec.cfg.num_quantizers), dtype=torch.int32).pin_memory()
+        self.width = codec.cfg.samples_per_token + codec.cfg.istft_pad
+        self._h2d_done = None     # event: the previous step's token upload has left the pinned buffer
+        self._free = list(range(slots - 1, -1, -1))
+        self._fresh = set()       # opened, no token yet: the first step carries RESET
+        self._open = set()
+
+    # -- slot management (host only) --
+    def open(self) -> int:
+        if not self._free:
+            raise RuntimeError("StreamPool: no free slot")
+        s = self._free.pop()
+        self._open.add(s)
+        self._fresh.add(s)
+        return s
+
+    def close(self, slot: int):
+        if slot in self._open:
+            self._open.discard(slot)
+            self._fresh.discard(slot)
+            self._free.append(slot)
+
+    @property
+    def n_open(self) -> int:
+        return len(self._open)
+
+    def slot_tokens(self, slot: int) -> int:
+        return int(self.codec._lib.frt2_pool_slot_tokens(self.ptr, slot))
+
+    # -- the step --
+    @torch.inference_mode()
+    def step_dense(self, tokens: torch.Tensor, flags, pcm16: bool = False) -> Tuple[torch.Tensor, list]:
+        """Lowest level: ``tokens`` (slots, nq) int32|int64 on the device, ``flags`` one FRT2_SLOT_* int per slot.
+        Returns ``(out (slots, 8*hop+pad) fp32|int16, n_samples per slot)``; slot b's chunk is ``out[b, :n[b]]``."""
+        c = self.codec
+        if tokens.dim() != 2 or tokens.shape[0] != self.slots:
+            raise ValueError(f"tokens must be (slots={self.slots}, nq), got {tuple(tokens.shape)}")
+        if tokens.dtype not in (torch.int32, torch.int64):
+            raise TypeError(f"tokens must be int32 or int64, got {tokens.dtype}")
+        if len(flags) != self.slots:
+            raise ValueError("flags must have one entry per slot")
+        with torch.cuda.device(c.device_index):
+            out = torch.empty((self.slots, self.width), dtype=torch.int16 if pcm16 else torch.float32,
+                              device=tokens.device)
+            f = (C.c_int32 * self.slots)(*[int(x) for x in flags])
+            n = (C.c_int32 * self.slots)()
+            N.check(c._lib.frt2_pool_step(c._h, self.ptr, C.c_void_p(tokens.data_ptr()), tokens.element_size(),
+                                          tokens.stride(0), tokens.stride(1), tokens.shape[1], f,
+                                          C.c_void_p(out.data_ptr()), int(pcm16), out.stride(0), n, c._cuda_stream()))
+            c._maybe_check()
+        return out, list(n)
+
+    @torch.inference_mode()
+    def step(self, tokens: Dict[int, torch.Tensor], last=(), pcm16: bool = False) -> Dict[int, torch.Tensor]:
+        """One token for each slot in ``tokens``; slots listed in ``last`` end their stream with it (and are released).
+        Returns ``{slot: chunk}`` with 1560 / 1920 / 2280-sample chunks exactly as decode_one_token would."""
+        last = set(last)
+        flags = [0] * self.slots
+        nq = None
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()
+        for s, t in tokens.items():
+            if s not in self._open:
+                raise ValueError(f"slot {s} is not open")
+            t = t.reshape(-1)
+            nq = t.numel() if nq is None else nq
+            if t.numel() != nq:
+                raise ValueError("all tokens of a step must use the same number of codebooks")
+            self._tok_host[s, :nq] = t.to("cpu", torch.int32) if t.device.type != "cpu" else t.to(torch.int32)
+            flags[s] = N.SLOT_ACTIVE | (N.SLOT_RESET if s in self._fresh else 0) | (N.SLOT_LAST if s in last else 0)
+        if nq is None:
+            return {}
+        self._tok.copy_(self._tok_host, non_blocking=True)
+        self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record(torch.cuda.current_stream(self.codec.device_index))
+        out, n = self.step_dense(self._tok[:, :nq], flags, pcm16)
+        res = {}
+        for s in tokens:
+            self._fresh.discard(s)
+            res[s] = out[s, :n[s]]
+            if s in last:
+                self.close(s)
+        return res
+
+    def destroy(self):
+        if self.ptr:
+            self.codec._lib.frt2_stream_destroy(self.ptr)
+            self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass

@@ -49,8 +49,11 @@ __global__ void __launch_bounds__(NSPLIT == 1 ? 128 : NSPLIT * 32) attention_war
   const int h = static_cast<int>((wid / nblk) % a.H);
   const int b = static_cast<int>(wid / (static_cast<long long>(nblk) * a.H));
   const float scale_log2 = a.scale * 1.4426950408889634f;
-  if (a.pos_ptr != nullptr) {  // streaming inside a captured graph: position comes from HBM
-    a.q_pos0 = *a.pos_ptr;
+  if (a.ctrl != nullptr) {  // streaming inside a captured graph: the item's position comes from its control block
+    const int* cb = a.ctrl + b * CTRL_INTS;
+    if (cb[CTRL_ACTIVE] == 0) return;   // idle pool slot (uniform per CTA: a CTA never spans two items' control blocks
+                                        // in the NSPLIT > 1 form; in the NSPLIT == 1 form the exit is per warp)
+    a.q_pos0 = cb[CTRL_POS];
     a.Tk = a.q_pos0 + a.Tq;
   }
 

@@ -61,6 +61,15 @@ __device__ __forceinline__ __half to_half_sat(float a) {
   return __ushort_as_half(y);
 }
 
+// ---- per-item streaming control block (HBM) ----
+// One block of CTRL_INTS ints per batch item / pool slot.  The kernels of a captured per-token step read every
+// position-dependent quantity from here, so the same CUDA graph serves every token of every stream; with one block
+// per item, the items of a batch may sit at different positions of different streams (continuous batching).
+constexpr int CTRL_INTS = 4;
+constexpr int CTRL_POS = 0;     // 100 Hz frames consumed so far (K/V append row, attention length, "first chunk")
+constexpr int CTRL_LAST = 1;    // this step is the item's last chunk (iSTFT keeps the trailing pad)
+constexpr int CTRL_ACTIVE = 2;  // 0: the slot is idle this step — no state update, no output
+
 // ---- GEMM (tcgen05) ----
 enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_POLAR = 2 };
 
@@ -89,15 +98,16 @@ struct GemmDesc {
   int64_t ld32;
   __half* out16;          // fp16 output or null
   int64_t ld16;
-  const int* out_row_off; // optional device int: added to every output row index at run time (streaming KV append
-                          // inside a captured CUDA graph: the write position lives in HBM, not in a kernel argument)
+  const int* out_row_off; // optional device ints: out_row_off[b * row_off_stride] is added to the output row index of
+  int row_off_stride;     // batch item b at run time (streaming KV append inside a captured CUDA graph: the write
+                          // position lives in HBM, not in a kernel argument; stride 0 = one offset for all items)
   // optional second fp16 destination (gemm_skinny only): columns >= split_col go to out16_b at column (n - split_col)
   // with their own pitches / run-time row offset — Q and K|V of the streaming step come out of ONE launch, Q into the
   // chunk buffer and K|V appended to the HBM state
   int split_col;
   __half* out16_b;
   int64_t ld16_b, pitch16_b;
-  const int* row_off_b;
+  const int* row_off_b;   // indexed with row_off_stride like out_row_off
   // optional fused LayerNorm(+SiLU) prologue (gemm_skinny only, ntaps == 1): the A rows are LN(ln_x) computed on the
   // fly from the fp32 residual stream (rows at ln_x + m*ln_ldx) instead of being read from A
   const float* ln_x;
@@ -134,7 +144,8 @@ struct AttnDesc {
   int q_pos0;        // absolute position of query row 0 (== Tk - Tq in streaming)
   int block_causal;  // 1: key j visible iff j <= ((q_pos0+i) | 7); 0: all Tk keys visible
   float scale;
-  const int* pos_ptr; // optional device int (attention_warp): q_pos0 = *pos_ptr, Tk = *pos_ptr + Tq at run time
+  const int* ctrl;   // optional per-item control blocks (attention_warp): item b has q_pos0 = ctrl[b*CTRL_INTS + CTRL_POS],
+                     // Tk = q_pos0 + Tq at run time; idle items (CTRL_ACTIVE == 0) are skipped
 };
 int attention_warp(const AttnDesc& a, cudaStream_t stream);  // CUDA-core, one warp per 8-query block
 int attention_tc(const AttnDesc& a, cudaStream_t stream);    // tcgen05 flash attention (hd == 64)
@@ -160,10 +171,11 @@ struct OlaDesc {
   int16_t* pcm16;        // optional: write int16 PCM = trunc(sample * 32767) (saturated) instead of fp32, same pitch
   int B, T, n_fft, hop;
   int first, last;       // streaming flags; offline == first && last
-  const int* ctrl;       // optional device {frames consumed so far, last flag}: overrides first/last at run time
+  const int* ctrl;       // optional per-item control blocks: first = (pos == 0), last and active come from HBM
 };
 int istft_overlap_add(const OlaDesc& d, cudaStream_t stream);
 int istft_update_tail(const float* frames, int64_t frames_batch_pitch, float* tail, int B, int T, int n_fft,
+                      const int* ctrl /* per-item control blocks or null: idle items keep their tail */,
                       cudaStream_t stream);
 int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_per_batch, int C, const float* gamma,
                             const float* beta, float eps, int apply_silu, __half* out16, int64_t ld16,

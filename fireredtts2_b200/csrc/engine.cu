@@ -56,17 +56,35 @@ __global__ void half_to_float_kernel(const __half* __restrict__ src, long long l
   dst[i] = __half2float(src[r * ld + c]);
 }
 
-// strided int32/int64 tokens -> contiguous int32 staging (B,nq,L) + the `last` flag of this call into the control
-// block; out-of-range values are flagged here (an int64 could alias after narrowing) and stored as -1
-template <typename IdxT>
+// strided int32/int64 tokens -> contiguous int32 staging (B,nq,L) + this call's flags into the per-item control
+// blocks; out-of-range values are flagged here (an int64 could alias after narrowing) and stored as -1.
+// slot_flags == nullptr (frt2_decode_chunk): every item is active and shares `last`.  Otherwise (frt2_pool_step) item b
+// takes FRT2_SLOT_* bits from slot_flags.f[b]: idle slots get token 0 and no range check, RESET rewinds the slot.
+struct SlotFlags { unsigned char f[FRT2_POOL_MAX_SLOTS]; };
+template <typename IdxT, bool POOL>
 __global__ void stage_tokens_kernel(const IdxT* __restrict__ tokens, long long sB, long long sQ, long long sL, int B,
                                     int nq, int L, int K, int* __restrict__ stage, int* ctrl, int last,
-                                    unsigned int* err_word) {
+                                    unsigned int* err_word, const SlotFlags flags) {
   const int n = B * nq * L;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i == 0) ctrl[1] = last;
+  if (i < B) {
+    int* cb = ctrl + i * CTRL_INTS;
+    if (POOL) {
+      const int f = flags.f[i];
+      if (f & FRT2_SLOT_RESET) cb[CTRL_POS] = 0;
+      cb[CTRL_LAST] = (f & FRT2_SLOT_LAST) ? 1 : 0;
+      cb[CTRL_ACTIVE] = (f & FRT2_SLOT_ACTIVE) ? 1 : 0;
+    } else {
+      cb[CTRL_LAST] = last;
+      cb[CTRL_ACTIVE] = 1;
+    }
+  }
   if (i >= n) return;
   const int l = i % L, q = (i / L) % nq, b = i / (L * nq);
+  if (POOL && !(flags.f[b] & FRT2_SLOT_ACTIVE)) {
+    stage[i] = 0;
+    return;
+  }
   const long long raw = static_cast<long long>(tokens[b * sB + q * sQ + l * sL]);
   int v = static_cast<int>(raw);
   if (raw < 0 || raw >= K) {
@@ -75,7 +93,19 @@ __global__ void stage_tokens_kernel(const IdxT* __restrict__ tokens, long long s
   }
   stage[i] = v;
 }
-__global__ void advance_ctrl_kernel(int* ctrl, int frames) { ctrl[0] += frames; }
+__global__ void advance_ctrl_kernel(int* ctrl, int frames, int B, int all_items) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B && (all_items || ctrl[b * CTRL_INTS + CTRL_ACTIVE] != 0)) ctrl[b * CTRL_INTS + CTRL_POS] += frames;
+}
+// staged fp32 chunk -> the caller's int16 PCM buffer, same rounding as the overlap-add kernel's direct PCM output
+__global__ void emit_pcm16_kernel(const float* __restrict__ stage, long long stage_pitch, int16_t* __restrict__ pcm,
+                                  long long pcm_pitch, int n, int B) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || b >= B) return;
+  const float smp = stage[b * stage_pitch + i];
+  pcm[b * pcm_pitch + i] = static_cast<int16_t>(__float2int_rz(fminf(fmaxf(smp * 32767.0f, -32768.0f), 32767.0f)));
+}
 
 struct ShiftEntry {
   __half* p;
@@ -87,8 +117,9 @@ struct ShiftTable {
   ShiftEntry e[16];
   int n;
 };
-// move the last `hist` rows of [hist | chunk] to the head of each streaming conv buffer (the new history)
-__global__ void shift_history_kernel(ShiftTable t, int E, int B) {
+// move the last `hist` rows of [hist | chunk] to the head of each streaming conv buffer (the new history);
+// items whose control block says idle keep their history
+__global__ void shift_history_kernel(ShiftTable t, int E, int B, const int* __restrict__ ctrl) {
   const int ei = blockIdx.y;
   const ShiftEntry en = t.e[ei];
   const int rows = en.rows;
@@ -98,9 +129,25 @@ __global__ void shift_history_kernel(ShiftTable t, int E, int B) {
     const int c = static_cast<int>(i % E);
     const int r = static_cast<int>((i / E) % en.hist);
     const int b = static_cast<int>(i / (static_cast<long long>(E) * en.hist));
+    if (ctrl != nullptr && ctrl[b * CTRL_INTS + CTRL_ACTIVE] == 0) continue;
     __half* base = en.p + b * en.batch_pitch;
     // rows >= hist so source (r + rows) never overlaps a not-yet-read destination row of another thread
     base[static_cast<long long>(r) * E + c] = base[static_cast<long long>(r + rows) * E + c];
+  }
+}
+
+// pool: a slot that starts a new stream this step gets its causal left padding back (zero conv history); the K/V
+// state and the iSTFT tail need no clearing — nothing before position 0 is ever read
+__global__ void reset_history_kernel(ShiftTable t, int E, int B, const SlotFlags flags) {
+  const int ei = blockIdx.y;
+  const ShiftEntry en = t.e[ei];
+  const long long total = static_cast<long long>(B) * en.hist * E;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / (static_cast<long long>(E) * en.hist));
+    if (!(flags.f[b] & FRT2_SLOT_RESET)) continue;
+    const long long rc = i - static_cast<long long>(b) * en.hist * E;
+    en.p[b * en.batch_pitch + rc] = __float2half_rn(0.f);
   }
 }
 
@@ -349,7 +396,10 @@ struct Stream {
   int conv_rpt[11] = {4, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8};  // rows per token
   std::vector<__half*> kv;  // per layer (B, Tmax, 2E)
   float* tail = nullptr;    // (B, 3, n_fft)
-  int* ctrl = nullptr;      // device {frames consumed, last flag, -, -}: read by the kernels of the captured step
+  int* ctrl = nullptr;      // device (B, CTRL_INTS) per-item control blocks: read by the kernels of the captured step
+  bool pooled = false;      // slot pool (frt2_pool_*): items are independent streams at their own positions
+  std::vector<int> slot_tokens;  // pool: host mirror of the tokens each slot has consumed
+  std::vector<char> slot_done;   // pool: the slot's stream received its LAST token
   int* tok_stage = nullptr; // (B, nq, chunk_cap) int32 contiguous
   float* audio_stage = nullptr;  // (B, audio_stage_pitch)
   int64_t audio_stage_pitch = 0;
@@ -358,7 +408,8 @@ struct Stream {
   std::map<std::pair<int, int>, GraphRec> graphs;  // (Lc, nq) -> captured step
 
   int64_t conv_pitch(int i) const { return static_cast<int64_t>(conv_hist[i] + conv_rpt[i] * chunk_cap) * h->E; }
-  int64_t kv_pitch() const { return static_cast<int64_t>(max_tokens) * 8 * 2 * h->E; }
+  // one token of slack: an idle pool slot still "appends" (and later overwrites) one chunk at its current position
+  int64_t kv_pitch() const { return static_cast<int64_t>(max_tokens + 1) * 8 * 2 * h->E; }
   void free_conv() {
     for (auto& p : conv) {
       if (p) cudaFree(p);
@@ -815,7 +866,8 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
         g.ln_x = x32; g.ln_ldx = E; g.ln_gamma = w.ln1_g; g.ln_beta = w.ln1_b; g.ln_eps = 1e-5f; g.ln_silu = 0;
       }
       __half* kv_dst = graph_mode ? s->kv[i] : s->kv[i] + static_cast<int64_t>(pos) * 2 * E;
-      const int* kv_off = graph_mode ? s->ctrl : nullptr;
+      const int* kv_off = graph_mode ? s->ctrl + CTRL_POS : nullptr;
+      g.row_off_stride = CTRL_INTS;
       if (fuse_ln) {
         // skinny path: ONE launch for q|k|v, columns >= E routed to the K|V state
         g.W = w.w_qkv; g.N = 3 * E; g.bias = w.b_qkv; g.out16 = qkv16; g.ld16 = E; g.pitch16 = xp;
@@ -830,7 +882,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
       a.q = qkv16; a.q_row_pitch = E; a.q_batch_pitch = xp;
       a.k = s->kv[i]; a.v = s->kv[i] + E; a.kv_row_pitch = 2 * E; a.kv_batch_pitch = s->kv_pitch();
       a.Tk = pos + T; a.q_pos0 = pos; a.block_causal = 0;
-      if (graph_mode) a.pos_ptr = s->ctrl;
+      if (graph_mode) a.ctrl = s->ctrl;
     }
     FRT2_TRY(run_attn(a, st));
     FRT2_TRY(flat_gemm(o16, M, E, w.w_o, E, w.b_o, ACT_NONE, x32, x32, nullptr, 0));
@@ -875,12 +927,13 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   }
   if (streaming) {
     launches += 2;
-    FRT2_TRY(istft_update_tail(frames32, od.frames_batch_pitch, s->tail, B, T, n_fft, st));
+    const int* cblk = graph_mode ? s->ctrl : nullptr;
+    FRT2_TRY(istft_update_tail(frames32, od.frames_batch_pitch, s->tail, B, T, n_fft, cblk, st));
     ShiftTable tb{};
     tb.n = 11;
     for (int i = 0; i < 11; ++i) tb.e[i] = {s->conv[i], s->conv_hist[i], s->conv_rpt[i] * L, s->conv_pitch(i)};
-    shift_history_kernel<<<dim3(8, 11), 256, 0, st>>>(tb, E, B);
-    advance_ctrl_kernel<<<1, 1, 0, st>>>(s->ctrl, T);
+    shift_history_kernel<<<dim3(8, 11), 256, 0, st>>>(tb, E, B, cblk);
+    advance_ctrl_kernel<<<(B + 127) / 128, 128, 0, st>>>(s->ctrl, T, B, graph_mode ? 0 : 1);
     launches += 1;
     FRT2_CUDA_OK(cudaGetLastError());
   }
@@ -925,7 +978,9 @@ int Stream::ensure_chunk_cap(int Lc, cudaStream_t st) {
 
 int Stream::reset() {
   n_tokens = 0;
-  FRT2_CUDA_OK(cudaMemset(ctrl, 0, 4 * sizeof(int)));
+  FRT2_CUDA_OK(cudaMemset(ctrl, 0, static_cast<size_t>(B) * CTRL_INTS * sizeof(int)));
+  std::fill(slot_tokens.begin(), slot_tokens.end(), 0);
+  std::fill(slot_done.begin(), slot_done.end(), 0);
   for (int i = 0; i < 11; ++i)
     if (conv[i]) FRT2_CUDA_OK(cudaMemset(conv[i], 0, static_cast<size_t>(B) * conv_pitch(i) * 2));
   FRT2_CUDA_OK(cudaMemset(tail, 0, static_cast<size_t>(B) * 3 * h->n_fft * 4));
@@ -1072,7 +1127,7 @@ int frt2_stream_create(frt2_handle* hh, int B, int max_tokens, frt2_stream** out
     }
   }
   if (cudaMalloc(reinterpret_cast<void**>(&s.tail), static_cast<size_t>(B) * 3 * h.n_fft * 4) != cudaSuccess ||
-      cudaMalloc(reinterpret_cast<void**>(&s.ctrl), 4 * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&s.ctrl), static_cast<size_t>(B) * CTRL_INTS * sizeof(int)) != cudaSuccess ||
       cudaStreamCreateWithFlags(&s.cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("frt2_stream_create: out of memory");
     return fail(FRT2_ERR_CUDA);
@@ -1094,14 +1149,70 @@ int frt2_stream_reset(frt2_stream* ss) {
 void frt2_stream_destroy(frt2_stream* ss) { delete ss; }
 int frt2_stream_tokens(const frt2_stream* ss) { return ss ? ss->s.n_tokens : 0; }
 
-int frt2_decode_chunk(frt2_handle* hh, frt2_stream* ss, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ,
-                      int64_t sL, int nq, int Lc, int last, float* audio, int64_t audio_pitch, int* n_samples,
-                      void* cuda_stream) {
+// Run the control-block-driven step for (Lc, nq): tokens come from the stream's staging buffer, audio goes to its
+// staging buffer, positions / flags are read from HBM.  Normally one CUDA-graph replay (captured on first use).
+static int run_ctrl_step(Handle& h, Stream& s, int nq, int Lc, cudaStream_t st, bool use_graph) {
+  FRT2_TRY(h.ensure_ws(h.ws_bytes_for(s.B, Lc)));  // before capture: no allocation may happen while recording
+  if (!use_graph)
+    return h.pipeline(s.tok_stage, 4, static_cast<int64_t>(nq) * Lc, Lc, 1, s.B, nq, Lc, nullptr, s.audio_stage,
+                      s.audio_stage_pitch, &s, 0, st, true);
+  auto key = std::make_pair(Lc, nq);
+  auto it = s.graphs.find(key);
+  if (it != s.graphs.end() && it->second.ws != h.ws) {  // workspace moved since the capture
+    cudaGraphExecDestroy(it->second.exec);
+    s.graphs.erase(it);
+    it = s.graphs.end();
+  }
+  if (it == s.graphs.end()) {
+    const long long before = h.launches;
+    FRT2_CUDA_OK(cudaStreamBeginCapture(s.cap_stream, cudaStreamCaptureModeThreadLocal));
+    const int rc = h.pipeline(s.tok_stage, 4, static_cast<int64_t>(nq) * Lc, Lc, 1, s.B, nq, Lc, nullptr, s.audio_stage,
+                              s.audio_stage_pitch, &s, 0, s.cap_stream, true);
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(s.cap_stream, &graph);
+    if (rc != FRT2_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    FRT2_CUDA_OK(ce);
+    Stream::GraphRec rec{};
+    rec.ws = h.ws;
+    rec.kernels = h.launches - before;
+    h.launches = before;
+    const cudaError_t ie = cudaGraphInstantiate(&rec.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    FRT2_CUDA_OK(ie);
+    it = s.graphs.emplace(key, rec).first;
+  }
+  FRT2_CUDA_OK(cudaGraphLaunch(it->second.exec, st));
+  h.launches += it->second.kernels;
+  return FRT2_OK;
+}
+
+// staged chunk -> caller's buffer (fp32 copy or int16 PCM conversion), n samples per item
+static int emit_chunk(Handle& h, Stream& s, float* audio, int16_t* pcm, int64_t pitch, int n, cudaStream_t st) {
+  if (pcm != nullptr) {
+    emit_pcm16_kernel<<<dim3((n + 255) / 256, s.B), 256, 0, st>>>(s.audio_stage, s.audio_stage_pitch, pcm, pitch, n, s.B);
+    FRT2_CUDA_OK(cudaGetLastError());
+  } else {
+    FRT2_CUDA_OK(cudaMemcpy2DAsync(audio, static_cast<size_t>(pitch) * 4, s.audio_stage,
+                                   static_cast<size_t>(s.audio_stage_pitch) * 4, static_cast<size_t>(n) * 4, s.B,
+                                   cudaMemcpyDeviceToDevice, st));
+  }
+  ++h.launches;
+  return FRT2_OK;
+}
+
+static int decode_chunk_impl(frt2_handle* hh, frt2_stream* ss, const void* tokens, int idx_bytes, int64_t sB,
+                             int64_t sQ, int64_t sL, int nq, int Lc, int last, float* audio, int16_t* pcm,
+                             int64_t audio_pitch, int* n_samples, void* cuda_stream) {
   FRT2_REQUIRE(hh && ss, FRT2_ERR_BAD_ARG, "null handle/stream");
   Handle& h = hh->h;
   Stream& s = ss->s;
   FRT2_REQUIRE(s.h == &h, FRT2_ERR_BAD_ARG, "stream belongs to another handle");
-  FRT2_TRY(check_decode_args(h, tokens, idx_bytes, s.B, nq, Lc, audio));
+  FRT2_REQUIRE(!s.pooled, FRT2_ERR_BAD_ARG, "this is a slot pool: use frt2_pool_step");
+  FRT2_TRY(check_decode_args(h, tokens, idx_bytes, s.B, nq, Lc,
+                             pcm ? reinterpret_cast<const float*>(pcm) : audio));
   FRT2_REQUIRE(s.n_tokens + Lc <= s.max_tokens, FRT2_ERR_STATE_OVERFLOW,
                "stream state overflow: more tokens than frt2_stream_create reserved");
   const int pad = (h.n_fft - h.hop) / 2;
@@ -1115,55 +1226,129 @@ int frt2_decode_chunk(frt2_handle* hh, frt2_stream* ss, const void* tokens, int 
   // parameters per kernel (taps, per-kernel event timing, the tcgen05 attention for long chunks) runs kernel by kernel.
   const bool graph_mode = !(h.debug & (DBG_NO_GRAPH | DBG_TAPS)) && !h.profile && 8 * Lc < 32;
   if (!graph_mode) {
-    FRT2_TRY(h.pipeline(tokens, idx_bytes, sB, sQ, sL, s.B, nq, Lc, nullptr, audio, audio_pitch, &s, last, st, false));
+    h.pcm16_out = pcm;
+    const int rc = h.pipeline(tokens, idx_bytes, sB, sQ, sL, s.B, nq, Lc, nullptr, audio, audio_pitch, &s, last, st,
+                              false);
+    h.pcm16_out = nullptr;
+    FRT2_TRY(rc);
   } else {
     const int ntok = s.B * nq * Lc;
+    const int nthr = std::max(ntok, s.B);
+    const SlotFlags none{};
     if (idx_bytes == 4) {
-      stage_tokens_kernel<int><<<(ntok + 127) / 128, 128, 0, st>>>(static_cast<const int*>(tokens), sB, sQ, sL, s.B, nq,
-                                                                    Lc, h.K, s.tok_stage, s.ctrl, last, h.err_word);
+      stage_tokens_kernel<int, false><<<(nthr + 127) / 128, 128, 0, st>>>(
+          static_cast<const int*>(tokens), sB, sQ, sL, s.B, nq, Lc, h.K, s.tok_stage, s.ctrl, last, h.err_word, none);
     } else {
-      stage_tokens_kernel<long long><<<(ntok + 127) / 128, 128, 0, st>>>(static_cast<const long long*>(tokens), sB, sQ,
-                                                                          sL, s.B, nq, Lc, h.K, s.tok_stage, s.ctrl,
-                                                                          last, h.err_word);
+      stage_tokens_kernel<long long, false><<<(nthr + 127) / 128, 128, 0, st>>>(
+          static_cast<const long long*>(tokens), sB, sQ, sL, s.B, nq, Lc, h.K, s.tok_stage, s.ctrl, last, h.err_word,
+          none);
     }
     FRT2_CUDA_OK(cudaGetLastError());
-    FRT2_TRY(h.ensure_ws(h.ws_bytes_for(s.B, Lc)));  // before capture: no allocation may happen while recording
-    auto key = std::make_pair(Lc, nq);
-    auto it = s.graphs.find(key);
-    if (it != s.graphs.end() && it->second.ws != h.ws) {  // workspace moved since the capture
-      cudaGraphExecDestroy(it->second.exec);
-      s.graphs.erase(it);
-      it = s.graphs.end();
-    }
-    if (it == s.graphs.end()) {
-      const long long before = h.launches;
-      FRT2_CUDA_OK(cudaStreamBeginCapture(s.cap_stream, cudaStreamCaptureModeThreadLocal));
-      const int rc = h.pipeline(s.tok_stage, 4, static_cast<int64_t>(nq) * Lc, Lc, 1, s.B, nq, Lc, nullptr, s.audio_stage,
-                                s.audio_stage_pitch, &s, last, s.cap_stream, true);
-      cudaGraph_t graph = nullptr;
-      const cudaError_t ce = cudaStreamEndCapture(s.cap_stream, &graph);
-      if (rc != FRT2_OK) {
-        if (graph) cudaGraphDestroy(graph);
-        return rc;
-      }
-      FRT2_CUDA_OK(ce);
-      Stream::GraphRec rec{};
-      rec.ws = h.ws;
-      rec.kernels = h.launches - before;
-      h.launches = before;
-      const cudaError_t ie = cudaGraphInstantiate(&rec.exec, graph, 0);
-      cudaGraphDestroy(graph);
-      FRT2_CUDA_OK(ie);
-      it = s.graphs.emplace(key, rec).first;
-    }
-    FRT2_CUDA_OK(cudaGraphLaunch(it->second.exec, st));
-    h.launches += it->second.kernels + 1;
-    FRT2_CUDA_OK(cudaMemcpy2DAsync(audio, static_cast<size_t>(audio_pitch) * 4, s.audio_stage,
-                                   static_cast<size_t>(s.audio_stage_pitch) * 4, static_cast<size_t>(n) * 4, s.B,
-                                   cudaMemcpyDeviceToDevice, st));
+    ++h.launches;
+    FRT2_TRY(run_ctrl_step(h, s, nq, Lc, st, true));
+    FRT2_TRY(emit_chunk(h, s, audio, pcm, audio_pitch, n, st));
   }
   s.n_tokens += Lc;
   if (n_samples) *n_samples = n;
+  return FRT2_OK;
+}
+
+int frt2_decode_chunk(frt2_handle* hh, frt2_stream* ss, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ,
+                      int64_t sL, int nq, int Lc, int last, float* audio, int64_t audio_pitch, int* n_samples,
+                      void* cuda_stream) {
+  return decode_chunk_impl(hh, ss, tokens, idx_bytes, sB, sQ, sL, nq, Lc, last, audio, nullptr, audio_pitch, n_samples,
+                           cuda_stream);
+}
+
+int frt2_decode_chunk_pcm16(frt2_handle* hh, frt2_stream* ss, const void* tokens, int idx_bytes, int64_t sB,
+                            int64_t sQ, int64_t sL, int nq, int Lc, int last, int16_t* pcm, int64_t pcm_pitch,
+                            int* n_samples, void* cuda_stream) {
+  return decode_chunk_impl(hh, ss, tokens, idx_bytes, sB, sQ, sL, nq, Lc, last, nullptr, pcm, pcm_pitch, n_samples,
+                           cuda_stream);
+}
+
+// ---- slot pool ----
+int frt2_pool_create(frt2_handle* hh, int slots, int max_tokens, frt2_stream** out) {
+  FRT2_REQUIRE(slots >= 1 && slots <= FRT2_POOL_MAX_SLOTS, FRT2_ERR_BAD_ARG,
+               "frt2_pool_create: slots must be in [1, FRT2_POOL_MAX_SLOTS]");
+  FRT2_TRY(frt2_stream_create(hh, slots, max_tokens, out));
+  Stream& s = (*out)->s;
+  s.pooled = true;
+  s.slot_tokens.assign(slots, 0);
+  s.slot_done.assign(slots, 0);
+  return FRT2_OK;
+}
+
+int frt2_pool_slot_tokens(const frt2_stream* ss, int slot) {
+  if (!ss || !ss->s.pooled || slot < 0 || slot >= ss->s.B) return 0;
+  return ss->s.slot_tokens[slot];
+}
+
+int frt2_pool_step(frt2_handle* hh, frt2_stream* ss, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ,
+                   int nq, const int32_t* slot_flags, void* out, int out_pcm16, int64_t out_pitch,
+                   int32_t* n_samples, void* cuda_stream) {
+  FRT2_REQUIRE(hh && ss && slot_flags, FRT2_ERR_BAD_ARG, "null handle/pool/flags");
+  Handle& h = hh->h;
+  Stream& s = ss->s;
+  FRT2_REQUIRE(s.h == &h, FRT2_ERR_BAD_ARG, "pool belongs to another handle");
+  FRT2_REQUIRE(s.pooled, FRT2_ERR_BAD_ARG, "not a slot pool (frt2_pool_create)");
+  FRT2_TRY(check_decode_args(h, tokens, idx_bytes, s.B, nq, 1, static_cast<const float*>(out)));
+  const int pad = (h.n_fft - h.hop) / 2;
+  const int width = 8 * h.hop + pad;
+  FRT2_REQUIRE(out_pitch >= width, FRT2_ERR_BAD_ARG, "out_pitch must be >= 8*hop + pad");
+  // validate the whole step before touching any state
+  SlotFlags flags{};
+  bool any_reset = false;
+  for (int b = 0; b < s.B; ++b) {
+    const int f = slot_flags[b];
+    FRT2_REQUIRE((f & ~(FRT2_SLOT_ACTIVE | FRT2_SLOT_LAST | FRT2_SLOT_RESET)) == 0, FRT2_ERR_BAD_ARG,
+                 "frt2_pool_step: unknown slot flag");
+    if (!(f & FRT2_SLOT_ACTIVE)) {
+      FRT2_REQUIRE(f == 0, FRT2_ERR_BAD_ARG, "frt2_pool_step: RESET / LAST need ACTIVE");
+      continue;
+    }
+    const int consumed = (f & FRT2_SLOT_RESET) ? 0 : s.slot_tokens[b];
+    FRT2_REQUIRE((f & FRT2_SLOT_RESET) || !s.slot_done[b], FRT2_ERR_BAD_ARG,
+                 "frt2_pool_step: the slot's stream has ended (LAST): set FRT2_SLOT_RESET to start a new one");
+    FRT2_REQUIRE(consumed + 1 <= s.max_tokens, FRT2_ERR_STATE_OVERFLOW,
+                 "pool slot overflow: more tokens than frt2_pool_create reserved");
+    flags.f[b] = static_cast<unsigned char>(f);
+    any_reset = any_reset || (f & FRT2_SLOT_RESET);
+  }
+  std::lock_guard<std::mutex> lk(h.mu);
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (any_reset) {
+    ShiftTable tb{};
+    tb.n = 11;
+    for (int i = 0; i < 11; ++i) tb.e[i] = {s.conv[i], s.conv_hist[i], 0, s.conv_pitch(i)};
+    reset_history_kernel<<<dim3(8, 11), 256, 0, st>>>(tb, h.E, s.B, flags);
+    ++h.launches;
+  }
+  const int nthr = s.B * nq;
+  if (idx_bytes == 4) {
+    stage_tokens_kernel<int, true><<<(nthr + 127) / 128, 128, 0, st>>>(
+        static_cast<const int*>(tokens), sB, sQ, 0, s.B, nq, 1, h.K, s.tok_stage, s.ctrl, 0, h.err_word, flags);
+  } else {
+    stage_tokens_kernel<long long, true><<<(nthr + 127) / 128, 128, 0, st>>>(
+        static_cast<const long long*>(tokens), sB, sQ, 0, s.B, nq, 1, h.K, s.tok_stage, s.ctrl, 0, h.err_word, flags);
+  }
+  FRT2_CUDA_OK(cudaGetLastError());
+  ++h.launches;
+  FRT2_TRY(run_ctrl_step(h, s, nq, 1, st, !(h.debug & DBG_NO_GRAPH) && !h.profile));
+  FRT2_TRY(emit_chunk(h, s, out_pcm16 ? nullptr : static_cast<float*>(out),
+                      out_pcm16 ? static_cast<int16_t*>(out) : nullptr, out_pitch, width, st));
+  for (int b = 0; b < s.B; ++b) {
+    const int f = flags.f[b];
+    int n = 0;
+    if (f & FRT2_SLOT_ACTIVE) {
+      if (f & FRT2_SLOT_RESET) s.slot_tokens[b] = 0;
+      n = 8 * h.hop - (s.slot_tokens[b] == 0 ? pad : 0) + ((f & FRT2_SLOT_LAST) ? pad : 0);
+      s.slot_tokens[b] += 1;
+      s.slot_done[b] = (f & FRT2_SLOT_LAST) ? 1 : 0;
+    }
+    if (n_samples) n_samples[b] = n;
+  }
   return FRT2_OK;
 }
 
@@ -1219,8 +1404,9 @@ int frt2_import_state(frt2_handle* hh, frt2_stream* ss, int n_tokens, const floa
     transpose_tail_kernel<<<(B * 3 * h.n_fft + 255) / 256, 256, 0, st>>>(is_cache, s.tail, B, h.n_fft, 0);
   FRT2_CUDA_OK(cudaGetLastError());
   s.n_tokens = n_tokens;
-  const int ctrl_h[4] = {8 * n_tokens, 0, 0, 0};
-  FRT2_CUDA_OK(cudaMemcpyAsync(s.ctrl, ctrl_h, sizeof(ctrl_h), cudaMemcpyHostToDevice, st));
+  std::vector<int> ctrl_h(static_cast<size_t>(B) * CTRL_INTS, 0);
+  for (int b = 0; b < B; ++b) ctrl_h[b * CTRL_INTS + CTRL_POS] = 8 * n_tokens;
+  FRT2_CUDA_OK(cudaMemcpyAsync(s.ctrl, ctrl_h.data(), ctrl_h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   FRT2_CUDA_OK(cudaStreamSynchronize(st));
   return FRT2_OK;
 }

@@ -187,11 +187,11 @@ __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(GemmDesc g, 
         v = (c & 1) ? mag * sn : mag * cs;
       }
       const int b = m / g.rows_out, r = m - b * g.rows_out;
-      const int roff = (g.out_row_off != nullptr) ? __ldg(g.out_row_off) : 0;
+      const int roff = (g.out_row_off != nullptr) ? __ldg(g.out_row_off + b * g.row_off_stride) : 0;
       const long long o32 = static_cast<long long>(b) * g.pitch32 + static_cast<long long>(r + roff) * g.ld32 + nn;
       const long long o16 = static_cast<long long>(b) * g.pitch16 + static_cast<long long>(r + roff) * g.ld16 + nn;
       if (g.split_col > 0 && nn >= g.split_col) {
-        const int roff_b = (g.row_off_b != nullptr) ? __ldg(g.row_off_b) : 0;
+        const int roff_b = (g.row_off_b != nullptr) ? __ldg(g.row_off_b + b * g.row_off_stride) : 0;
         g.out16_b[static_cast<long long>(b) * g.pitch16_b + static_cast<long long>(r + roff_b) * g.ld16_b +
                   (nn - g.split_col)] = to_half_sat(v);
       } else {

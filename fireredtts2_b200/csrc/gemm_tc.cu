@@ -64,6 +64,14 @@ struct GemmKParams {
   int vec16;  // ... on out16 rows
   int store_mode;
   const int* row_off_ptr;
+  int row_off_stride;
+  // packed-item tiles (short per-item row counts, e.g. the 8 frames per token of a batch of streams): one 128-row
+  // tile holds pack_items items x pack_rpb rows, loaded by ONE 3-D TMA box {64, pack_rpb, pack_items}; 0 = off
+  int pack_rpb;
+  int pack_items;
+  int batches;
+  int item_mul;        // first item of tile group g is g * item_mul (pack_items when packed, else 1)
+  int stage_tx_bytes;  // bytes one pipeline stage receives (A box + W box)
 };
 
 template <int BN>
@@ -248,11 +256,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
     const uint32_t tmem_lane = static_cast<uint32_t>(wq * 32) << 16;
     {
       const int row0 = row_slab0 + wq * 32;   // first row of this warp's 32-row slab
-      const int row = row0 + lane;
-      const bool valid_row = row < p.rows_out;
-      const int roff = (p.row_off_ptr != nullptr) ? __ldg(p.row_off_ptr) : 0;  // direct-store mode only
-      const long long off32 = static_cast<long long>(b) * p.pitch32 + static_cast<long long>(row + roff) * p.ld32;
-      const long long off16 = static_cast<long long>(b) * p.pitch16 + static_cast<long long>(row + roff) * p.ld16;
+      int row = row0 + lane;
+      int item = b;
+      bool valid_row = row < p.rows_out;
+      if (p.pack_rpb > 0) {   // packed-item tile (direct-store mode only): tile row -> (item, row of the item)
+        const int gi = row / p.pack_rpb;
+        item = b + gi;
+        row -= gi * p.pack_rpb;
+        valid_row = gi < p.pack_items && item < p.batches;
+      }
+      const int roff = (p.row_off_ptr != nullptr && valid_row) ? __ldg(p.row_off_ptr + item * p.row_off_stride) : 0;
+      const long long off32 = static_cast<long long>(item) * p.pitch32 + static_cast<long long>(row + roff) * p.ld32;
+      const long long off16 = static_cast<long long>(item) * p.pitch16 + static_cast<long long>(row + roff) * p.ld16;
       const int ncol0 = n_idx * BN + hsel * (BN / 2);     // first column owned by this warp
       const uint32_t tmem_acc = tmem_stage + static_cast<uint32_t>(hsel * (BN / 2)) + tmem_lane;
 
@@ -420,11 +435,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int n_idx = tile % p.tiles_n;
         const int mb = tile / p.tiles_n;
-        const int b = mb / p.tiles_m;
+        const int b = (mb / p.tiles_m) * p.item_mul;
         const int m0 = (mb % p.tiles_m) * BM;
         for (int kb = 0; kb < p.num_kblocks; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          ptx::mbar_expect_tx(&full_bar[stage], p.stage_tx_bytes);
           const int tap = kb / p.kblocks_per_tap;
           const int c0 = (kb - tap * p.kblocks_per_tap) * BK;
           ptx::tma_load_3d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], c0, m0 + tap + p.row_shift, b);
@@ -472,7 +487,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int n_idx = tile % p.tiles_n;
       const int mb = tile / p.tiles_n;
-      const int b = mb / p.tiles_m;
+      const int b = (mb / p.tiles_m) * p.item_mul;
       epilogue_tile<BN>(p, &tmC, sStage, e, lane, tmem_base + static_cast<uint32_t>(as * BN), n_idx, b,
                         (mb % p.tiles_m) * BM, &tfull_bar[as], aphase);
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[as]);
@@ -719,7 +734,15 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   FRT2_REQUIRE(g.act != ACT_POLAR || (g.N % 2 == 0), FRT2_ERR_BAD_ARG, "gemm_tc: polar epilogue needs even N");
   FRT2_REQUIRE(g.out32 != nullptr || g.out16 != nullptr, FRT2_ERR_BAD_ARG, "gemm_tc: no output");
 
-  const int BN = (g.N >= 512) ? 256 : 128;
+  // Packed-item tiles: a batch of items with few rows each (the 8 frames per token of a batch of streams / pool
+  // slots) would otherwise get one mostly empty 128-row tile per item, each re-streaming the whole weight panel.
+  static const bool no_pack = (getenv("FRT2_GEMM_NOPACK") != nullptr);   // A/B switch for measurements
+  const bool packed = !no_pack && g.batches > 1 && g.rows_out <= BM / 2;
+  const int pack_items = packed ? std::min(BM / g.rows_out, g.batches) : 0;
+  const int groups = packed ? (g.batches + pack_items - 1) / pack_items : g.batches;
+  // few row tiles (latency-bound steps): narrower N tiles put more SMs on the weight stream
+  const long long row_tiles = packed ? groups : static_cast<long long>(g.batches) * ((g.rows_out + BM - 1) / BM);
+  const int BN = (g.N >= 512 && row_tiles * ((g.N + 255) / 256) >= 64) ? 256 : 128;
   // CTA pairs (256 x 256 tiles) for the large GEMMs; FRT2_GEMM_1CTA=1 forces the single-CTA kernel (A/B testing)
   static const bool force_1cta = (getenv("FRT2_GEMM_1CTA") != nullptr);
   const bool pair = !force_1cta && BN == 256 && g.rows_out >= 256 && g.out_row_off == nullptr;
@@ -733,6 +756,10 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
     uint64_t strides[2] = {static_cast<uint64_t>(g.a_row_pitch) * 2,
                            static_cast<uint64_t>(g.batches > 1 ? g.a_batch_pitch : g.a_row_pitch * g.rows_a) * 2};
     uint32_t box[3] = {BK, BM, 1};
+    if (packed) {
+      box[1] = static_cast<uint32_t>(g.rows_out);
+      box[2] = static_cast<uint32_t>(pack_items);
+    }
     FRT2_TRY(tma_encode_fp16(&tmA, g.A, 3, dims, strides, box));
   }
   {
@@ -750,9 +777,14 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   p.kblocks_per_tap = g.Kc / BK;
   p.num_kblocks = g.ntaps * p.kblocks_per_tap;
   p.row_shift = g.row_shift;
-  p.tiles_m = (g.rows_out + BMT - 1) / BMT;
+  p.tiles_m = packed ? 1 : (g.rows_out + BMT - 1) / BMT;
   p.tiles_n = (g.N + BN - 1) / BN;
-  p.num_tiles = g.batches * p.tiles_m * p.tiles_n;
+  p.num_tiles = groups * p.tiles_m * p.tiles_n;
+  p.pack_rpb = packed ? g.rows_out : 0;
+  p.pack_items = pack_items;
+  p.batches = g.batches;
+  p.item_mul = packed ? pack_items : 1;
+  p.stage_tx_bytes = (packed ? pack_items * g.rows_out * BK * 2 : A_STAGE_BYTES) + BN * BK * 2;
   p.alpha = g.alpha;
   p.bias = g.bias;
   p.act = g.act;
@@ -768,10 +800,11 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   // output through TMA stores whenever the layout allows it (16-byte aligned base / pitches, single output)
   p.store_mode = STORE_DIRECT;
   p.row_off_ptr = g.out_row_off;
+  p.row_off_stride = g.row_off_stride;
   tmC = tmA;
   const uint64_t batch_rows = static_cast<uint64_t>(g.batches);
-  if (g.out_row_off != nullptr) {
-    // run-time row offset: plain predicated stores (only used by the tiny streaming K/V append)
+  if (g.out_row_off != nullptr || packed) {
+    // run-time row offset (streaming K/V append) or packed-item tile: plain predicated stores, one row per thread
   } else if (g.out16 != nullptr && g.out32 == nullptr && g.resid == nullptr && p.vec16) {
     uint64_t dims[3] = {static_cast<uint64_t>(g.N), static_cast<uint64_t>(g.rows_out), batch_rows};
     uint64_t strides[2] = {static_cast<uint64_t>(g.ld16) * 2,

@@ -222,12 +222,23 @@ int layer_norm_rows(const float* x, int64_t ldx, int rows, int C, const float* g
 __global__ void __launch_bounds__(256) overlap_add_kernel(OlaDesc d, int ntail, int start, int n_out_full) {
   const int b = blockIdx.y;
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d.ctrl != nullptr) {  // streaming inside a captured graph: first / last come from HBM
-    const int first = (d.ctrl[0] == 0), last = d.ctrl[1];
+  if (d.ctrl != nullptr) {  // streaming inside a captured graph: the item's first / last / active come from HBM
+    const int* cb = d.ctrl + b * CTRL_INTS;
+    const int first = (cb[CTRL_POS] == 0), last = cb[CTRL_LAST];
     const int pad = (d.n_fft - d.hop) / 2;
+    const int n_grid = n_out_full;   // upper bound the grid was sized for
     ntail = first ? 0 : (d.n_fft / d.hop - 1);
     start = first ? pad : (d.n_fft - d.hop);
     n_out_full = (ntail + d.T - 1) * d.hop + d.n_fft - start - (last ? pad : (d.n_fft - d.hop));
+    if (cb[CTRL_ACTIVE] == 0) n_out_full = 0;
+    if (n >= n_out_full) {   // past this item's sample count: defined zeros up to the common upper bound
+      if (n < n_grid) {
+        const long long o = static_cast<long long>(b) * d.audio_pitch + n;
+        if (d.pcm16 != nullptr) d.pcm16[o] = 0;
+        else d.audio[o] = 0.f;
+      }
+      return;
+    }
   }
   if (n >= n_out_full) return;
   int TF = ntail + d.T;
@@ -270,10 +281,11 @@ __global__ void __launch_bounds__(256) overlap_add_kernel(OlaDesc d, int ntail, 
 
 // new tail = last 3 frames of [old tail | frames]; T >= 3 always (a token is 8 frames) so it is a plain copy
 __global__ void update_tail_kernel(const float* __restrict__ frames, long long frames_batch_pitch, float* tail, int T,
-                                   int n_fft) {
+                                   int n_fft, const int* __restrict__ ctrl) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 3 * n_fft) return;
+  if (ctrl != nullptr && ctrl[b * CTRL_INTS + CTRL_ACTIVE] == 0) return;   // idle pool slot keeps its tail
   tail[static_cast<long long>(b) * 3 * n_fft + i] =
       frames[static_cast<long long>(b) * frames_batch_pitch + static_cast<long long>(T - 3) * n_fft + i];
 }
@@ -296,10 +308,10 @@ int istft_overlap_add(const OlaDesc& d, cudaStream_t stream) {
 }
 
 int istft_update_tail(const float* frames, int64_t frames_batch_pitch, float* tail, int B, int T, int n_fft,
-                      cudaStream_t stream) {
+                      const int* ctrl, cudaStream_t stream) {
   FRT2_REQUIRE(T >= 3, FRT2_ERR_BAD_ARG, "update_tail: chunk shorter than the iSTFT carry");
   dim3 grid((3 * n_fft + 255) / 256, B);
-  update_tail_kernel<<<grid, 256, 0, stream>>>(frames, frames_batch_pitch, tail, T, n_fft);
+  update_tail_kernel<<<grid, 256, 0, stream>>>(frames, frames_batch_pitch, tail, T, n_fft, ctrl);
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;
 }
@@ -342,7 +354,7 @@ __global__ void __launch_bounds__(128) gemm_ref_kernel(GemmDesc g) {
     v0 = mag * c;
     v1 = mag * s;
   }
-  const int roff = (g.out_row_off != nullptr) ? *g.out_row_off : 0;
+  const int roff = (g.out_row_off != nullptr) ? g.out_row_off[b * g.row_off_stride] : 0;
   const long long o32 = static_cast<long long>(b) * g.pitch32 + static_cast<long long>(m + roff) * g.ld32 + n;
   const long long o16 = static_cast<long long>(b) * g.pitch16 + static_cast<long long>(m + roff) * g.ld16 + n;
   if (g.resid != nullptr) {

@@ -90,6 +90,33 @@ int frt2_stream_tokens(const frt2_stream* s); /* tokens consumed so far */
 int frt2_decode_chunk(frt2_handle* h, frt2_stream* s, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ,
                       int64_t sL, int nq, int Lc, int last, float* audio, int64_t audio_pitch, int* n_samples,
                       void* cuda_stream);
+/* Same chunk, emitted as the int16 PCM of the reference's wire format (see frt2_decode_pcm16): what the streaming
+ * front sends per token (enhanced_fireredtts2.py:603,655). */
+int frt2_decode_chunk_pcm16(frt2_handle* h, frt2_stream* s, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ,
+                            int64_t sL, int nq, int Lc, int last, int16_t* pcm, int64_t pcm_pitch, int* n_samples,
+                            void* cuda_stream);
+
+/* ---- slot pool: many concurrent streams, one token each per step (continuous batching) ----
+ * The reference serves concurrent requests one after the other (one daemon worker, enhanced_fireredtts2.py:199-203;
+ * its asyncio BatchProcessor, performance_optimization.py:822, batches whole utterances after the fact).  A pool is
+ * `slots` independent decode_one_token states (model.py:326-376) in HBM that advance together: every step decodes ONE
+ * token for each active slot in a single batched launch sequence (one captured CUDA graph), each slot at its own
+ * position of its own stream.  Per slot and step the caller passes FRT2_SLOT_* flags (HOST int32 array, `slots`
+ * entries): ACTIVE = the slot has a token this step; RESET = the slot starts a new stream with this token (state
+ * rewound first); LAST = this is the stream's final token.  tokens: device (slots, nq) integers, element strides
+ * sB, sQ (idle slots are not read).  out: device (slots, out_pitch) fp32, or int16 PCM when out_pcm16 != 0; slot b
+ * receives n_samples[b] (HOST, written before return) = 8*hop - pad*[first token] + pad*[LAST] samples (0 when
+ * idle), zero-filled up to 8*hop + pad, so out_pitch >= 8*hop + pad.  A slot's samples are bit-identical whatever
+ * the other slots are doing.  After LAST a slot must be RESET before it is stepped again. */
+enum { FRT2_SLOT_ACTIVE = 1, FRT2_SLOT_LAST = 2, FRT2_SLOT_RESET = 4 };
+#define FRT2_POOL_MAX_SLOTS 256
+int frt2_pool_create(frt2_handle* h, int slots, int max_tokens, frt2_stream** out);
+int frt2_pool_step(frt2_handle* h, frt2_stream* pool, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ,
+                   int nq, const int32_t* slot_flags, void* out, int out_pcm16, int64_t out_pitch,
+                   int32_t* n_samples, void* cuda_stream);
+/* tokens consumed so far by one slot of a pool */
+int frt2_pool_slot_tokens(const frt2_stream* pool, int slot);
+
 /* Export / import the state in the reference's cache_dict layouts (fp32, contiguous, device):
  * up_conv_cache (B,E,3), bb_conv_cache1 (B,E,6), bb_conv_cache2 (B,8E,2), bb_kv_cache (B,layers,H,T,2*hd)
  * with T = 8*frt2_stream_tokens(s), is_cache (B,n_fft,3).  Any pointer may be NULL (skipped). */

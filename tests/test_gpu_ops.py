@@ -69,6 +69,13 @@ GEMM_CASES = [
     (1, 1000, 1024, 1, 962, True, 2, False, 1.0),
     (1, 640, 1024, 1, 960, False, 0, False, 1.0 / 960),
     (4, 8, 1024, 3, 1024, True, 0, True, 1.0),
+    # packed-item tiles: several short items share one 128-row tile (one 3-D TMA box {64, rows, items})
+    (20, 8, 256, 3, 256, True, 0, True, 1.0),
+    (64, 8, 1024, 7, 1024, True, 0, False, 1.0),
+    (130, 1, 512, 1, 512, False, 0, False, 1.0),
+    (5, 24, 128, 3, 192, True, 1, False, 1.0),
+    (3, 64, 128, 2, 962, True, 2, False, 1.0),
+    (33, 4, 1024, 2, 2048, True, 1, False, 1.0),
 ]
 
 
