@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfrt2_b200.so")
+LIB_PATH = os.environ.get("FRT2_LIB") or os.path.join(HERE, "libfrt2_b200.so")   # FRT2_LIB: A/B builds
 
 FRT2_OK = 0
 ERR_BAD_ARG, ERR_BAD_DTYPE, ERR_INDEX_OOR, ERR_STATE_OVERFLOW, ERR_CUDA, ERR_MISSING_TENSOR, ERR_NOT_FINALIZED = \

@@ -596,6 +596,297 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+
+// =====================================================================================================
+// attention_tcp: same tiling, but P never touches shared memory.  The softmax threads write the packed fp16
+// probabilities with tcgen05.st over the first 32 columns of the S accumulator they have just read (P aliases S), and
+// O += P V is issued in the TS form (A operand from tensor memory, V from shared memory).  Per (query tile, key tile)
+// this removes 16 KB of st.shared and 16 KB of MMA operand reads from the 128 B/clk shared-memory port — with both
+// operands in shared memory a 128 x 64 x 16 MMA reads 6 KB, i.e. 48 clk of port time for 32 clk of tensor time, and
+// the port (QK^T + PV + P stores + K/V fills: ~2300 clk per SM round) was a tighter bound than the MUFU (2048).
+// Aliasing orders the two MMAs of a tile: PV(j) must have consumed P(j) before QK^T(j+1) overwrites it.  Both are
+// issued by the same thread back to back (tcgen05.mma of one thread execute in issue order), so no barrier is needed
+// between them; the softmax of the other three query tiles resident on the SM covers the exposed MMA latency.
+// Barriers: s_full (S ready; also: every earlier PV of this tile has completed, so O is quiescent for the lazy
+// rescale), p_full (P stored), o_full (last PV of the tile done).  No P buffer, no s_empty / pv_full handshakes.
+// =====================================================================================================
+constexpr int AP_STAGES = 3;
+constexpr int AP_SMEM_BYTES = AT_QT * AT_Q_BYTES + 2 * AP_STAGES * AT_KV_BYTES + 1024 + 256;
+
+template <int EMU>
+__global__ void __launch_bounds__(AT_THREADS, 2)
+attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                              // AT_QT tiles
+  uint8_t* sK = sQ + AT_QT * AT_Q_BYTES;
+  uint8_t* sV = sK + AP_STAGES * AT_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AP_STAGES * AT_KV_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + AP_STAGES;
+  uint64_t* v_full = k_empty + AP_STAGES;
+  uint64_t* v_empty = v_full + AP_STAGES;
+  uint64_t* s_full = v_empty + AP_STAGES;   // [AT_QT]
+  uint64_t* p_full = s_full + AT_QT;
+  uint64_t* o_full = p_full + AT_QT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + AT_QT);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qpair = gridDim.x - 1 - blockIdx.x;  // heaviest (latest) query tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = qpair * (AT_BQ * AT_QT);
+
+  int nt[AT_QT];   // number of 64-key tiles each query tile needs (0 = tile lies beyond the sequence)
+#pragma unroll
+  for (int t = 0; t < AT_QT; ++t) {
+    const int qs = q0 + t * AT_BQ;
+    if (qs >= p.Tq) {
+      nt[t] = 0;
+    } else {
+      int kmax = p.Tk - 1;
+      if (p.block_causal) kmax = min(kmax, (p.q_pos0 + min(qs + AT_BQ, p.Tq) - 1) | 7);
+      nt[t] = kmax / AT_BK + 1;
+    }
+  }
+  const int ntiles = max(nt[0], nt[AT_QT - 1]);
+
+  if (warp == AT_SOFTMAX_WARPS && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+  }
+  if (warp == AT_SOFTMAX_WARPS + 1 && lane == 0) {
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < AP_STAGES; ++s) {
+      ptx::mbar_init(&k_full[s], 1);
+      ptx::mbar_init(&k_empty[s], 1);
+      ptx::mbar_init(&v_full[s], 1);
+      ptx::mbar_init(&v_empty[s], 1);
+    }
+    for (int t = 0; t < AT_QT; ++t) {
+      ptx::mbar_init(&s_full[t], 1);
+      ptx::mbar_init(&p_full[t], 4);
+      ptx::mbar_init(&o_full[t], 1);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == AT_SOFTMAX_WARPS + 1) {
+    ptx::tmem_alloc(tmem_slot, AT_TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == AT_SOFTMAX_WARPS) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      ptx::mbar_expect_tx(q_full, AT_QT * AT_Q_BYTES);
+#pragma unroll
+      for (int t = 0; t < AT_QT; ++t) ptx::tma_load_3d(sQ + t * AT_Q_BYTES, &tmQ, q_full, h * AT_HD, q0 + t * AT_BQ, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < ntiles; ++j) {
+        ptx::mbar_wait(&k_empty[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&k_full[stage], AT_KV_BYTES);
+        ptx::tma_load_3d(sK + stage * AT_KV_BYTES, &tmK, &k_full[stage], h * AT_HD, j * AT_BK, b);
+        ptx::mbar_wait(&v_empty[stage], phase ^ 1);
+        ptx::mbar_expect_tx(&v_full[stage], AT_KV_BYTES);
+        ptx::tma_load_3d(sV + stage * AT_KV_BYTES, &tmV, &v_full[stage], h * AT_HD, j * AT_BK, b);
+        if (++stage == AP_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == AT_SOFTMAX_WARPS + 1) {
+    // ------------------------------------------------------------ MMA issuer (both query tiles)
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc_s = ptx::make_idesc_f16(AT_BQ, AT_BK, 0, 0);   // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(AT_BQ, AT_HD, 0, 1);  // P (TMEM)    x V (MN-major)
+      ptx::mbar_wait(q_full, 0);
+      auto issue_pv = [&](int t, int j) {  // O_t (+)= P_t,j V_j, accumulated in TMEM across all key tiles
+        const int st = j % AP_STAGES;
+        ptx::mbar_wait(&p_full[t], j & 1);
+        ptx::mbar_wait(&v_full[st], (j / AP_STAGES) & 1);
+        ptx::tc_fence_after();
+        const uint32_t vaddr = ptx::smem_u32(sV + st * AT_KV_BYTES);
+#pragma unroll
+        for (int k = 0; k < AT_BK / 16; ++k) {
+          // 16 keys: V advances 16 rows of 128 B (MN-major operand), P advances 8 TMEM columns (2 halves per column)
+          const uint64_t dv = ptx::make_desc_mnmajor_sw128(vaddr + k * 2048, 1024, 1024);
+          ptx::mma_f16_ts(tmem_base + t * 128 + AT_BK, tmem_base + t * 128 + k * 8, dv, idesc_pv,
+                          (j | k) != 0 ? 1u : 0u);
+        }
+        if (j == nt[t] - 1) ptx::mma_commit(&o_full[t]);
+      };
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % AP_STAGES;
+        ptx::mbar_wait(&k_full[st], (j / AP_STAGES) & 1);
+        const uint64_t dk = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sK + st * AT_KV_BYTES));
+#pragma unroll
+        for (int t = 0; t < AT_QT; ++t) {
+          if (j > 0 && j - 1 < nt[t]) issue_pv(t, j - 1);   // consumes P_t,j-1 before S_t,j overwrites it (in order)
+          if (j < nt[t]) {
+            ptx::tc_fence_after();
+            const uint64_t dq = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sQ + t * AT_Q_BYTES));
+#pragma unroll
+            for (int k = 0; k < AT_HD / 16; ++k)
+              ptx::mma_f16_ss(tmem_base + t * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+            ptx::mma_commit(&s_full[t]);
+          }
+        }
+        ptx::mma_commit(&k_empty[st]);
+        if (j > 0) ptx::mma_commit(&v_empty[(j - 1) % AP_STAGES]);
+      }
+#pragma unroll
+      for (int t = 0; t < AT_QT; ++t)
+        if (ntiles - 1 < nt[t]) issue_pv(t, ntiles - 1);
+      ptx::mma_commit(&v_empty[(ntiles - 1) % AP_STAGES]);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------ softmax / output (thread == query row)
+    const int t = warp >> 2;                       // query tile of this warpgroup
+    const int r = threadIdx.x & (AT_BQ - 1);       // row inside the tile == TMEM lane
+    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t tmem_s = tmem_base + t * 128;
+    const uint32_t tmem_o = tmem_s + AT_BK;
+    const int my_tiles = nt[t];
+    const int qi = q0 + t * AT_BQ + r;             // row inside this item's query block
+    const int qabs = p.q_pos0 + qi;                // absolute position
+    int limit = p.Tk - 1;
+    if (p.block_causal) limit = min(limit, qabs | 7);
+    constexpr float RESCALE_LOG2 = 8.0f;           // lazy rescaling, see attention_tc_kernel
+    float m_ref = 0.f, l = 0.f;
+    const uint32_t a_s_full = ptx::smem_u32(&s_full[t]), a_p_full = ptx::smem_u32(&p_full[t]);
+
+    for (int j = 0; j < my_tiles; ++j) {
+      ptx::mbar_wait(a_s_full, j & 1);
+      ptx::tc_fence_after();
+      uint32_t sa[32], sb[32];
+      ptx::tmem_ld32(tmem_s + lane_off, sa);
+      ptx::tmem_ld32(tmem_s + lane_off + 32, sb);
+      ptx::tmem_ld_wait();
+
+      const int lim = limit - j * AT_BK;  // columns c <= lim are visible
+      const bool diag = __any_sync(0xffffffffu, lim < AT_BK - 1);   // masked (-inf) scores: MUFU path only
+      if (lim < AT_BK - 1) {              // diagonal / last tile: mask (interior tiles skip this entirely)
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          if (c > lim) sa[c] = 0xff800000u;        // -inf
+          if (c + 32 > lim) sb[c] = 0xff800000u;
+        }
+      }
+      float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};  // 4 independent chains
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(sa[c + u]), __uint_as_float(sb[c + u])));
+      }
+      const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;  // scale > 0
+
+      if (j == 0) {
+        m_ref = (m_tile == -CUDART_INF_F) ? 0.f : m_tile;
+      } else {
+        const bool need = m_tile > m_ref + RESCALE_LOG2;
+        if (__any_sync(0xffffffffu, need)) {
+          // O is quiescent: S_j was committed after P V_{j-1}, so every P V issued so far has completed
+          const float alpha = need ? fast_exp2(m_ref - m_tile) : 1.0f;
+          if (need) m_ref = m_tile;
+          l *= alpha;
+#pragma unroll 1
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t tt[16];
+            ptx::tmem_ld16(tmem_o + lane_off + q4 * 16, tt);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 16; ++c) tt[c] = __float_as_uint(__uint_as_float(tt[c]) * alpha);
+            ptx::tmem_st16(tmem_o + lane_off + q4 * 16, tt);
+          }
+        }
+      }
+      // p = 2^(s*scale - m_ref) as packed halves, stored over the first 32 columns of this row's S
+      const float neg_m = -m_ref;
+      unsigned long long scale2, negm2;
+      asm("mov.b64 %0, {%1, %1};" : "=l"(scale2) : "f"(p.scale_log2));
+      asm("mov.b64 %0, {%1, %1};" : "=l"(negm2) : "f"(neg_m));
+      __half2 acc[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {          // 16 keys (8 TMEM columns) per tcgen05.st
+        uint32_t w[8];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c = 2 * g + cc;          // 8-key chunk
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int e = (c & 3) * 8 + 2 * u;
+            const uint32_t s0 = (c < 4) ? sa[e] : sb[e];
+            const uint32_t s1 = (c < 4) ? sa[e + 1] : sb[e + 1];
+            unsigned long long xx;
+            asm("{\n\t.reg .b64 a;\n\tmov.b64 a, {%1, %2};\n\tfma.rn.f32x2 %0, a, %3, %4;\n\t}"
+                : "=l"(xx) : "r"(s0), "r"(s1), "l"(scale2), "l"(negm2));
+            if (u < EMU && !diag) {
+              w[cc * 4 + u] = exp2_poly_f16x2(xx);
+            } else {
+              float x0, x1;
+              asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
+              w[cc * 4 + u] = exp2_f16x2(x0, x1);
+            }
+          }
+          const __half2 s01 = __hadd2(*reinterpret_cast<const __half2*>(&w[cc * 4 + 0]),
+                                      *reinterpret_cast<const __half2*>(&w[cc * 4 + 1]));
+          const __half2 s23 = __hadd2(*reinterpret_cast<const __half2*>(&w[cc * 4 + 2]),
+                                      *reinterpret_cast<const __half2*>(&w[cc * 4 + 3]));
+          const __half2 s4 = __hadd2(s01, s23);
+          acc[c & 3] = (c < 4) ? s4 : __hadd2(acc[c & 3], s4);
+        }
+        ptx::tmem_st8(tmem_s + lane_off + g * 8, w);
+      }
+      {
+        const float2 f0 = __half22float2(acc[0]), f1 = __half22float2(acc[1]);
+        const float2 f2 = __half22float2(acc[2]), f3 = __half22float2(acc[3]);
+        l += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(a_p_full);
+    }
+    if (my_tiles > 0) {
+      ptx::mbar_wait(ptx::smem_u32(&o_full[t]), 0);
+      ptx::tc_fence_after();
+      const float inv = 1.0f / l;
+      __half* op = p.out + b * p.o_batch_pitch + static_cast<long long>(qi) * p.o_row_pitch + h * AT_HD;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t tt[32];
+        ptx::tmem_ld32(tmem_o + lane_off + half * 32, tt);
+        ptx::tmem_ld_wait();
+        if (qi < p.Tq) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            uint4 q;
+            q.x = pack_half2(__uint_as_float(tt[c + 0]) * inv, __uint_as_float(tt[c + 1]) * inv);
+            q.y = pack_half2(__uint_as_float(tt[c + 2]) * inv, __uint_as_float(tt[c + 3]) * inv);
+            q.z = pack_half2(__uint_as_float(tt[c + 4]) * inv, __uint_as_float(tt[c + 5]) * inv);
+            q.w = pack_half2(__uint_as_float(tt[c + 6]) * inv, __uint_as_float(tt[c + 7]) * inv);
+            *reinterpret_cast<uint4*>(op + half * 32 + c) = q;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == AT_SOFTMAX_WARPS + 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, AT_TMEM_COLS);
+  }
+}
+
 std::once_flag g_attn_once;
 int g_attn_status = FRT2_OK;
 
@@ -611,6 +902,10 @@ int attention_tc_init() {
       e = cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_tcp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_tcp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM_BYTES);
     if (e != cudaSuccess) {
       set_error(std::string("cudaFuncSetAttribute(attention_tc_kernel): ") + cudaGetErrorString(e));
       g_attn_status = FRT2_ERR_CUDA;
@@ -658,6 +953,13 @@ int attention_tc(const AttnDesc& a, cudaStream_t stream) {
   // issue-bound before it is MUFU-bound, so moving exponentials to the FMA pipe costs more issue slots than the
   // MUFU time it frees; the default keeps every exponential on the MUFU.  (FRT2_ATTN_EMU=1|2 for A/B runs.)
   static const int emu = getenv("FRT2_ATTN_EMU") ? atoi(getenv("FRT2_ATTN_EMU")) : 0;
+  static const bool p_in_smem = (getenv("FRT2_ATTN_PSMEM") != nullptr);   // A/B: the older kernel with P in shared memory
+  if (!p_in_smem) {
+    if (emu <= 0) attention_tcp_kernel<0><<<grid, AT_THREADS, AP_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    else attention_tcp_kernel<1><<<grid, AT_THREADS, AP_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+    FRT2_CUDA_OK(cudaGetLastError());
+    return FRT2_OK;
+  }
   if (emu <= 0) attention_tc_kernel<0><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   else if (emu == 1) attention_tc_kernel<1><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   else attention_tc_kernel<2><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
