@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import ctypes as C
 import json
-from typing import Dict, Optional, Tuple
+from typing import Dict, Iterable, Iterator, NamedTuple, Optional, Tuple
 
 import numpy as np
 import torch
@@ -25,6 +25,47 @@ from .weights import decode_keys, normalise_state_dict
 
 _STATE_KEY = "frt2_state"
 _REF_CACHE_KEYS = ("up_conv_cache", "bb_conv_cache1", "bb_conv_cache2", "bb_kv_cache", "is_cache")
+
+
+def resample(waveform: torch.Tensor, orig_freq: int, new_freq: int, lengths: Optional[torch.Tensor] = None
+             ) -> torch.Tensor:
+    """Drop-in for ``torchaudio.functional.resample(waveform, orig_freq, new_freq)`` with its defaults, as the reference
+    calls it on every generated turn (24 kHz -> 16 kHz for the context loop, fireredtts2.py:389-391) and on the prompt
+    (fireredtts2.py:65): ``(..., time)`` float32 CUDA tensor -> ``(..., ceil(new * time / orig))``.  Extension:
+    ``lengths`` (int32, one per row) resamples ragged rows as if each were ``lengths[i]`` long (rest of the row 0)."""
+    if orig_freq <= 0 or new_freq <= 0:
+        raise ValueError("Original frequency and desired frequecy should be positive")
+    if not waveform.is_floating_point():
+        raise TypeError(f"Expected floating point type for waveform tensor, but received {waveform.dtype}.")
+    if waveform.device.type != "cuda":
+        raise ValueError("fireredtts2_b200.codec.resample runs on CUDA tensors only (no CPU fallback)")
+    lib = N.load()
+    if int(orig_freq) == int(new_freq):
+        return waveform
+    shape = waveform.shape
+    x = waveform.to(torch.float32).reshape(-1, shape[-1])
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    B, n = x.shape
+    g = np.gcd(int(orig_freq), int(new_freq))
+    o, w = int(orig_freq) // g, int(new_freq) // g
+    n_out = -(-w * n // o)
+    dev = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    with torch.cuda.device(dev):
+        y = torch.empty((B, n_out), dtype=torch.float32, device=x.device)
+        lptr = None
+        if lengths is not None:
+            lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
+            if lengths.numel() != B:
+                raise ValueError("lengths must have one entry per row")
+            lptr = C.c_void_p(lengths.data_ptr())
+        got = C.c_int64(0)
+        if B and n:
+            N.check(lib.frt2_resample(dev, C.c_void_p(x.data_ptr()), x.stride(0), B, n, lptr, int(orig_freq),
+                                      int(new_freq), C.c_void_p(y.data_ptr()), y.stride(0) if n_out else 1,
+                                      C.byref(got), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+            assert got.value == n_out
+    return y.reshape(shape[:-1] + (n_out,))
 
 
 class _NativeStream:
@@ -163,7 +204,7 @@ class RedCodecB200(torch.nn.Module):
 
     @torch.inference_mode()
     def decode_one_token(self, token: torch.Tensor, cache_dict: Dict[str, object], last_token: bool,
-                         pcm16: bool = False) -> Tuple[torch.Tensor, Dict[str, object]]:
+                         pcm16: bool = False, _check: bool = True) -> Tuple[torch.Tensor, Dict[str, object]]:
         """RedCodecInfer.decode_one_token (reference model.py:326-376).  Extension: ``pcm16=True`` returns the chunk
         as the int16 PCM the reference's streaming front puts on the wire (enhanced_fireredtts2.py:603,655).
 
@@ -195,7 +236,8 @@ class RedCodecB200(torch.nn.Module):
                        sB, sQ, sL, nq, Lc, int(bool(last_token)),
                        C.c_void_p(audio.data_ptr()), audio.stride(0), C.byref(n_out), self._cuda_stream()))
             assert n_out.value == n
-            self._maybe_check()
+            if _check:
+                self._maybe_check()
             st.finished = bool(last_token)
         return audio, {_STATE_KEY: st}
 
@@ -204,6 +246,21 @@ class RedCodecB200(torch.nn.Module):
         pass the returned dict as ``cache_dict`` of the first ``decode_one_token`` call."""
         with torch.cuda.device(self.device_index):
             return {_STATE_KEY: _NativeStream(self, batch, max_tokens or self.stream_max_tokens)}
+
+    def decode_stream(self, frames: Iterable[torch.Tensor], pcm16: bool = True, batch: int = 1,
+                      ring: int = 16) -> Iterator["StreamChunk"]:
+        """The codec half of ``FireRedTTS2.generate_stream`` (reference fireredtts2.py:259-343; commented out there):
+        consume the frames the LLM emits one by one and yield the waveform chunk of frame *i-1* when frame *i* arrives
+        (one frame of delay, exactly as the reference's loop holds ``prev_sample`` back so that ``last_token`` is known),
+        then the final chunk.  See ``StreamDecoder``."""
+        dec = StreamDecoder(self, batch=batch, pcm16=pcm16, ring=ring)
+        for f in frames:
+            c = dec.push(f)
+            if c is not None:
+                yield c
+        c = dec.finish()
+        if c is not None:
+            yield c
 
     def new_pool(self, slots: int, max_tokens: Optional[int] = None) -> "StreamPool":
         """A pool of ``slots`` concurrent streams that decode one token each per step (continuous batching)."""
@@ -243,6 +300,8 @@ class RedCodecB200(torch.nn.Module):
         N.check(self._lib.frt2_import_state(self._h, st.ptr, T // 8, *[C.c_void_p(t.data_ptr()) for t in ts],
                                             self._cuda_stream()))
         torch.cuda.current_stream(self.device_index).synchronize()
+
+    resample = staticmethod(resample)   # torchaudio.functional.resample of the context loop, on the same device
 
     def encode(self, *args, **kwargs):
         """Out of scope for this path: delegated to the wrapped reference module."""
@@ -285,6 +344,88 @@ class RedCodecB200(torch.nn.Module):
                                        self._cuda_stream()))
         if n.value != out.numel():
             raise ValueError(f"tap {name} has {n.value} elements, expected {out.numel()}")
+        return out
+
+
+class StreamChunk(NamedTuple):
+    """One streamed chunk: ``samples`` (B, n) in pinned HOST memory (int16 PCM or fp32), valid once ``ready`` (a CUDA
+    event) has completed — call ``ready.synchronize()`` before reading the bytes; ``index`` = token index.  The buffer
+    belongs to a ring and is re-used ``ring`` chunks later: send or copy it before then."""
+    samples: torch.Tensor
+    ready: torch.cuda.Event
+    index: int
+
+
+class StreamDecoder:
+    """Live streaming front for one request.
+
+    The reference's ``generate_stream`` (fireredtts2.py:259-343) calls ``decode_one_token(prev_sample, cache, last)``
+    between two LLM frames on the default stream, so the LLM waits for the codec and the host for both.  Here each
+    codec step (one CUDA-graph replay, int16 PCM straight from the kernel) and its device->host copy run on a
+    dedicated CUDA stream that only waits for the event marking the frame's tokens: the LLM's next frame, enqueued on
+    the caller's stream, overlaps the codec step, and the host gets the wire-format bytes without synchronising the
+    caller's stream.  ``push(frame)`` returns the chunk of the PREVIOUS frame (None for the first frame);
+    ``finish()`` flushes the last frame with ``last_token=True``."""
+
+    def __init__(self, codec: RedCodecB200, batch: int = 1, pcm16: bool = True, max_tokens: Optional[int] = None,
+                 ring: int = 16):
+        self.codec = codec
+        self.batch = batch
+        self.pcm16 = pcm16
+        dev = torch.device("cuda", codec.device_index)
+        with torch.cuda.device(codec.device_index):
+            self._cache = codec.new_stream(batch, max_tokens)
+            self._side = torch.cuda.Stream(device=dev)
+            width = codec.cfg.samples_per_token + codec.cfg.istft_pad
+            dt = torch.int16 if pcm16 else torch.float32
+            self._ring = [torch.empty((batch, width), dtype=dt).pin_memory() for _ in range(max(2, ring))]
+        self._held: Optional[Tuple[torch.Tensor, torch.cuda.Event]] = None
+        self._n = 0
+        self._done = False
+
+    def _as_token(self, frame: torch.Tensor) -> torch.Tensor:
+        nq = frame.shape[-2] if frame.dim() == 3 else frame.shape[-1]
+        t = frame.reshape(self.batch, nq, 1) if frame.dim() != 3 else frame
+        if t.shape[0] != self.batch or t.shape[2] != 1:
+            raise ValueError(f"frame must be (nq,), (B,nq) or (B,nq,1) with B={self.batch}, got {tuple(frame.shape)}")
+        return self.codec._prep_tokens(t)
+
+    def _decode_held(self, last: bool) -> StreamChunk:
+        tok, ev = self._held
+        c = self.codec
+        with torch.cuda.device(c.device_index), torch.cuda.stream(self._side):
+            self._side.wait_event(ev)                       # the frame's tokens are complete
+            # no per-step host synchronisation: the device-side index check is read once, at the end of the stream
+            audio, self._cache = c.decode_one_token(tok, self._cache, last, pcm16=self.pcm16, _check=False)
+            tok.record_stream(self._side)
+            host = self._ring[self._n % len(self._ring)][:, :audio.shape[1]]
+            host.copy_(audio, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(self._side)
+            if last:
+                c._maybe_check()                            # IndexError for an out-of-range code anywhere in the stream
+        chunk = StreamChunk(host, ready, self._n)
+        self._n += 1
+        return chunk
+
+    def push(self, frame: torch.Tensor) -> Optional[StreamChunk]:
+        if self._done:
+            raise ValueError("stream already finished")
+        tok = self._as_token(frame)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.codec.device_index))
+        out = self._decode_held(False) if self._held is not None else None
+        self._held = (tok, ev)
+        return out
+
+    def finish(self) -> Optional[StreamChunk]:
+        if self._done:
+            return None
+        self._done = True
+        if self._held is None:
+            return None
+        out = self._decode_held(True)
+        self._held = None
         return out
 
 

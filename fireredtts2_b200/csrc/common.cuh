@@ -180,6 +180,8 @@ int istft_update_tail(const float* frames, int64_t frames_batch_pitch, float* ta
 int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_per_batch, int C, const float* gamma,
                             const float* beta, float eps, int apply_silu, __half* out16, int64_t ld16,
                             int64_t out_batch_pitch, cudaStream_t stream);
+int resample_rows(const float* x, int64_t x_pitch, int B, int64_t n_in, const int* lengths, const float* taps, int K,
+                  int width, int orig, int nnew, float* y, int64_t y_pitch, cudaStream_t stream);
 int tma_encode_fp16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box);
 int num_sms();

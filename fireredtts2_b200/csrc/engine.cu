@@ -8,6 +8,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -1420,6 +1421,81 @@ int frt2_rvq_gather(frt2_handle* hh, const void* tokens, int idx_bytes, int64_t 
   FRT2_CUDA_OK(cudaSetDevice(h.device));
   return rvq_gather_sum(tokens, idx_bytes, sB, sQ, sL, B, nq, L, h.codebooks, h.K, h.cd, sum, nullptr, rows, h.err_word,
                         static_cast<cudaStream_t>(cuda_stream));
+}
+
+// FIR bank of torchaudio's sinc_interp_hann resampler, computed in float32 in the same operation order as
+// torchaudio.functional._get_sinc_resample_kernel is run by resample() on a float32 waveform
+namespace {
+struct ResampleBank { float* taps = nullptr; int K = 0, width = 0, orig = 0, nnew = 0; };
+std::mutex g_resample_mu;
+std::map<std::tuple<int, int, int>, ResampleBank> g_resample_banks;   // (device, orig/gcd, new/gcd)
+
+int get_resample_bank(int device, int orig_freq, int new_freq, ResampleBank* out) {
+  int a = orig_freq, b = new_freq;
+  while (b) { const int t = a % b; a = b; b = t; }
+  const int orig = orig_freq / a, nnew = new_freq / a;
+  std::lock_guard<std::mutex> lk(g_resample_mu);
+  auto key = std::make_tuple(device, orig, nnew);
+  auto it = g_resample_banks.find(key);
+  if (it != g_resample_banks.end()) { *out = it->second; return FRT2_OK; }
+  const int lpw = 6;
+  const double rolloff = 0.99;
+  const float base = static_cast<float>(std::min(orig, nnew) * rolloff);
+  const int width = static_cast<int>(std::ceil(lpw * orig / (std::min(orig, nnew) * rolloff)));
+  const int K = 2 * width + orig;
+  FRT2_REQUIRE(K <= 4096 && static_cast<int64_t>(K) * nnew <= (1 << 24), FRT2_ERR_BAD_ARG,
+               "frt2_resample: rate pair needs too large a filter bank (reduce the rates by their gcd first)");
+  std::vector<float> taps(static_cast<size_t>(nnew) * K);
+  const float pi = static_cast<float>(M_PI);
+  const float scale = static_cast<float>(std::min(orig, nnew) * rolloff / orig);
+  for (int p = 0; p < nnew; ++p) {
+    for (int k = 0; k < K; ++k) {
+      const float idx = static_cast<float>(k - width) / static_cast<float>(orig);
+      float t = static_cast<float>(-p) / static_cast<float>(nnew) + idx;
+      t *= base;
+      t = std::min(std::max(t, static_cast<float>(-lpw)), static_cast<float>(lpw));
+      const float c = std::cos(t * pi / static_cast<float>(lpw) / 2.0f);
+      const float window = c * c;
+      t *= pi;
+      const float sinc = (t == 0.0f) ? 1.0f : std::sin(t) / t;
+      taps[static_cast<size_t>(p) * K + k] = sinc * (window * scale);
+    }
+  }
+  ResampleBank bank;
+  bank.K = K; bank.width = width; bank.orig = orig; bank.nnew = nnew;
+  FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&bank.taps), taps.size() * 4));
+  FRT2_CUDA_OK(cudaMemcpy(bank.taps, taps.data(), taps.size() * 4, cudaMemcpyHostToDevice));
+  g_resample_banks[key] = bank;
+  *out = bank;
+  return FRT2_OK;
+}
+}  // namespace
+
+int frt2_resample(int device, const float* in, int64_t in_pitch, int B, int64_t n_in, const int32_t* lengths,
+                  int orig_freq, int new_freq, float* out, int64_t out_pitch, int64_t* n_out, void* cuda_stream) {
+  FRT2_REQUIRE(in != nullptr && out != nullptr, FRT2_ERR_BAD_ARG, "frt2_resample: null pointer");
+  FRT2_REQUIRE(orig_freq > 0 && new_freq > 0, FRT2_ERR_BAD_ARG,
+               "Original frequency and desired frequecy should be positive");   // torchaudio's message
+  FRT2_REQUIRE(B >= 0 && n_in >= 0, FRT2_ERR_BAD_ARG, "frt2_resample: negative size");
+  int ndev = 0;
+  FRT2_CUDA_OK(cudaGetDeviceCount(&ndev));
+  FRT2_REQUIRE(device >= 0 && device < ndev, FRT2_ERR_BAD_ARG, "frt2_resample: no such CUDA device");
+  FRT2_CUDA_OK(cudaSetDevice(device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  if (orig_freq == new_freq) {   // torchaudio returns the waveform unchanged
+    FRT2_REQUIRE(out_pitch >= n_in, FRT2_ERR_BAD_ARG, "frt2_resample: out_pitch too small");
+    if (B > 0 && n_in > 0)
+      FRT2_CUDA_OK(cudaMemcpy2DAsync(out, out_pitch * 4, in, in_pitch * 4, n_in * 4, B, cudaMemcpyDeviceToDevice, st));
+    if (n_out) *n_out = n_in;
+    return FRT2_OK;
+  }
+  ResampleBank bank;
+  FRT2_TRY(get_resample_bank(device, orig_freq, new_freq, &bank));
+  const int64_t n = (n_in * bank.nnew + bank.orig - 1) / bank.orig;
+  FRT2_REQUIRE(out_pitch >= n && in_pitch >= n_in, FRT2_ERR_BAD_ARG, "frt2_resample: pitch too small");
+  if (n_out) *n_out = n;
+  return resample_rows(in, in_pitch, B, n_in, lengths, bank.taps, bank.K, bank.width, bank.orig, bank.nnew, out,
+                       out_pitch, st);
 }
 
 int frt2_set_debug(frt2_handle* hh, int flags) {

@@ -126,6 +126,17 @@ int frt2_import_state(frt2_handle* h, frt2_stream* s, int n_tokens, const float*
                       const float* bb_conv_cache1, const float* bb_conv_cache2, const float* bb_kv_cache,
                       const float* is_cache, void* cuda_stream);
 
+/* ---- waveform resampler of the context loop ----
+ * Replaces torchaudio.functional.resample(waveform, orig_freq, new_freq) with its defaults (sinc_interp_hann,
+ * lowpass_filter_width 6, rolloff 0.99) as the reference calls it on every generated turn (24 kHz -> 16 kHz,
+ * fireredtts2.py:389-391) and on the prompt (fireredtts2.py:65).  in: device fp32 (B, n_in) with row pitch in_pitch;
+ * out: device fp32 (B, ceil(new*n_in/orig)) with row pitch out_pitch; lengths: optional device int32 (B) of per-item
+ * sample counts <= n_in (ragged batch: item b is resampled as if it were lengths[b] long, the rest of its row is 0).
+ * *n_out (host, optional) receives ceil(new*n_in/orig).  Needs no handle (no weights): the FIR bank of a rate pair
+ * is built once per device and cached. */
+int frt2_resample(int device, const float* in, int64_t in_pitch, int B, int64_t n_in, const int32_t* lengths,
+                  int orig_freq, int new_freq, float* out, int64_t out_pitch, int64_t* n_out, void* cuda_stream);
+
 /* ---- parity hooks ----
  * Raw codebook rows and their index-ordered fp32 sum, bit-exact with VectorQuantize.decode_code /
  * ResidualVQ.decode_codes for Identity projections (rvq.py:56-60,145-164).  rows (B,L,nq,cd) / sum (B,L,cd),

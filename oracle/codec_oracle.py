@@ -417,6 +417,47 @@ def decode_chunk(sd, tokens, state: Optional[StreamState], last: bool, num_heads
     return y, new
 
 
+def resample_taps(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99):
+    """FIR bank of torchaudio.functional.resample (sinc_interp_hann), restated from torchaudio 2.11
+    functional._get_sinc_resample_kernel as the reference calls it (fireredtts2.py:65,389-391: defaults, the float32
+    waveform's dtype is used for the whole computation).  -> (taps (new, 2*width + orig) float32, width, orig, new)
+    with orig/new reduced by their gcd."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base = np.float32(min(orig, new) * rolloff)
+    width = int(math.ceil(lowpass_filter_width * orig / (min(orig, new) * rolloff)))
+    f32 = np.float32
+    idx = np.arange(-width, width + orig, dtype=f32)[None, :] / f32(orig)
+    t = np.arange(0, -new, -1, dtype=f32)[:, None] / f32(new) + idx
+    t = t * base
+    t = np.clip(t, f32(-lowpass_filter_width), f32(lowpass_filter_width))
+    window = np.cos(t * f32(math.pi) / f32(lowpass_filter_width) / f32(2)) ** 2
+    t = t * f32(math.pi)
+    scale = f32(min(orig, new) * rolloff / orig)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = np.where(t == 0, f32(1.0), np.sin(t) / t)
+    k = (k * (window * scale)).astype(f32)
+    return k, width, orig, new
+
+
+def resample(x: np.ndarray, orig_freq: int, new_freq: int) -> np.ndarray:
+    """torchaudio.functional.resample on (..., n) float32 (functional._apply_sinc_resample_kernel): zero-pad
+    (width, width + orig), strided correlation with the `new` phase filters, keep ceil(new * n / orig) samples."""
+    if orig_freq == new_freq:
+        return x
+    taps, width, orig, new = resample_taps(orig_freq, new_freq)
+    shape = x.shape
+    x2 = np.asarray(x, dtype=np.float32).reshape(-1, shape[-1])
+    n = x2.shape[1]
+    xp = np.pad(x2, ((0, 0), (width, width + orig)))
+    K = taps.shape[1]
+    frames = (xp.shape[1] - K) // orig + 1
+    win = np.lib.stride_tricks.sliding_window_view(xp, K, axis=1)[:, ::orig][:, :frames]   # (B, frames, K)
+    y = np.einsum("bfk,pk->bfp", win, taps, dtype=np.float32).reshape(x2.shape[0], -1)
+    target = int(math.ceil(new * n / orig))
+    return y[:, :target].reshape(shape[:-1] + (target,))
+
+
 def snr_db(ref: np.ndarray, out: np.ndarray) -> float:
     """SNR = 10 log10( sum ref^2 / sum (ref-out)^2 )  (SURVEY.md §8d parity gate)."""
     ref = np.asarray(ref, dtype=np.float64)

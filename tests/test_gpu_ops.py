@@ -257,3 +257,48 @@ def test_fp16_outputs_saturate_instead_of_overflowing(lib):
         torch.cuda.synchronize()
         assert torch.isfinite(o16.float()).all()
         assert (o16[0, :, 0::2] == 65504).all() and (o16[0, :, 1::2] == -65504).all()
+
+
+def _resample_golden():
+    import os
+    from .helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "resample.npz"))
+    names = sorted({k.split("::")[0] for k in g.files if "::" in k})
+    return [(n, g[n + "::x"], g[n + "::y"], int(g[n + "::rates"][0]), int(g[n + "::rates"][1])) for n in names]
+
+
+@pytest.mark.parametrize("case", _resample_golden(), ids=lambda c: c[0])
+def test_resample_matches_torchaudio_golden(case):
+    """K6 resampler through the C ABI against vectors produced by torchaudio.functional.resample (the call the
+    reference makes at fireredtts2.py:65,389-391).  fp32 FIR, K sequential FMAs: tolerance 1e-6 of full scale."""
+    from fireredtts2_b200.codec import resample
+    name, x, y, orig, new = case
+    out = resample(torch.from_numpy(x).cuda(), orig, new).cpu().numpy()
+    assert out.shape == y.shape
+    err = np.abs(out - y).max()
+    print(f"resample {name}: max-abs {err:.2e} at peak {np.abs(y).max():.2e}")
+    assert err <= 1e-6 * max(1.0, float(np.abs(y).max()))
+
+
+def test_resample_ragged_long_and_errors():
+    from fireredtts2_b200.codec import resample
+    from oracle import codec_oracle as O
+    rng = np.random.default_rng(8)
+    x = (rng.standard_normal((3, 50001)) * 0.2).astype(np.float32)       # many blocks per row
+    lens = np.asarray([50001, 12345, 1], dtype=np.int32)
+    out = resample(torch.from_numpy(x).cuda(), 24000, 16000, lengths=torch.from_numpy(lens)).cpu().numpy()
+    for b, n in enumerate(lens):
+        ref = O.resample(x[b:b + 1, :n], 24000, 16000)[0]
+        assert np.abs(out[b, :ref.shape[0]] - ref).max() <= 1e-6
+        assert np.all(out[b, ref.shape[0]:] == 0)
+    lead = resample(torch.from_numpy(x).cuda().reshape(3, 1, 50001), 24000, 16000)   # leading dims kept
+    assert lead.shape == (3, 1, 33334)
+    assert resample(torch.zeros(2, 0, device="cuda"), 24000, 16000).shape == (2, 0)
+    same = torch.from_numpy(x).cuda()
+    assert resample(same, 16000, 16000) is same
+    with pytest.raises(ValueError):
+        resample(same, 0, 16000)
+    with pytest.raises(TypeError):
+        resample(same.int(), 24000, 16000)
+    with pytest.raises(ValueError):
+        resample(torch.zeros(1, 8), 24000, 16000)                         # CPU tensor: no fallback path

@@ -162,3 +162,48 @@ def test_stream_chunk_pcm16():
             assert p.dtype == torch.int16 and p.shape == a.shape
             assert np.array_equal(p.cpu().numpy(), (to_np(a) * 32767).astype(np.int16))
             pos += lc
+
+
+def test_decode_stream_front_matches_offline_and_wire_format():
+    """codec.decode_stream (the codec half of the reference's generate_stream, fireredtts2.py:259-343): chunks come
+    back one frame late, in pinned host memory, as int16 PCM; concatenated they equal the offline decode's PCM up to
+    the fp16-operand tolerance, and the fp32 variant passes the SNR gate against the oracle."""
+    cfg = TINY
+    sd = synthetic_state_dict(cfg, 17)
+    codec = build_codec(cfg, sd, stream_max_tokens=16)
+    tok = synthetic_tokens(cfg, 1, 7, 5)
+    frames = [torch.from_numpy(tok[0, :, i]).cuda() for i in range(7)]
+
+    def llm():
+        for f in frames:
+            yield f
+
+    chunks = list(codec.decode_stream(llm(), pcm16=False))
+    assert [c.index for c in chunks] == list(range(7))
+    sizes = [c.samples.shape[1] for c in chunks]
+    spt, pad = cfg.samples_per_token, cfg.istft_pad
+    assert sizes == [spt - pad] + [spt] * 5 + [spt + pad]
+    for c in chunks:
+        c.ready.synchronize()
+        assert c.samples.is_pinned()
+    cat = np.concatenate([c.samples.numpy()[0] for c in chunks])
+    ref = O.decode(sd, tok, cfg.num_heads, cfg.hop_length)[0]
+    _, snr = report("decode_stream/fp32", ref, cat)
+    assert snr >= SNR_GATE_DB
+    pcm = list(codec.decode_stream(llm(), pcm16=True))
+    for c in pcm:
+        c.ready.synchronize()
+    pcm_cat = np.concatenate([c.samples.numpy()[0] for c in pcm])
+    assert pcm_cat.dtype == np.int16
+    assert np.array_equal(pcm_cat, (cat * 32767).astype(np.int16))
+    # the push/finish form used by a server loop
+    from fireredtts2_b200.codec import StreamDecoder
+    dec = StreamDecoder(codec, pcm16=False)
+    assert dec.push(frames[0]) is None
+    c0 = dec.push(frames[1])
+    c1 = dec.finish()
+    c0.ready.synchronize(); c1.ready.synchronize()
+    assert c0.samples.shape[1] == spt - pad and c1.samples.shape[1] == spt + pad
+    assert dec.finish() is None
+    with pytest.raises(ValueError):
+        dec.push(frames[2])

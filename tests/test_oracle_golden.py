@@ -102,3 +102,21 @@ def test_torch_cpu_port_matches_reference(case):
     y = OT.decode(OT.to_torch(sd), g["tokens"], cfg.num_heads, cfg.hop_length).numpy()
     assert y.shape == g["audio"].shape
     assert np.abs(y - g["audio"]).max() < TOL_AUDIO
+
+
+def _resample_cases():
+    import os
+    from .helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "resample.npz"))
+    names = sorted({k.split("::")[0] for k in g.files if "::" in k})
+    return [(n, g[n + "::x"], g[n + "::y"], int(g[n + "::rates"][0]), int(g[n + "::rates"][1])) for n in names]
+
+
+@pytest.mark.parametrize("case", _resample_cases(), ids=lambda c: c[0])
+def test_resample_oracle_matches_torchaudio_golden(case):
+    """oracle.resample restates torchaudio.functional.resample (third-party, torchaudio 2.11.0, not vendored in the
+    reference: fireredtts2.py:65,389-391); pinned to vectors produced by torchaudio (oracle/make_golden_resample.py)."""
+    name, x, y, orig, new = case
+    out = O.resample(x, orig, new)
+    assert out.shape == y.shape and out.dtype == np.float32
+    assert np.abs(out - y).max() <= 2e-7 * max(1.0, float(np.abs(y).max())) + 2e-7

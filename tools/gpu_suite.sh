@@ -14,6 +14,7 @@ run() {  # name, timeout, pytest args...
 run ops_gemm 600 tests/test_gpu_ops.py -k "gemm"
 run ops_ln 300 tests/test_gpu_ops.py -k layer_norm
 run ops_ola 300 tests/test_gpu_ops.py -k overlap_add
+run ops_resample 300 tests/test_gpu_ops.py -k resample
 run ops_attn_warp 600 tests/test_gpu_ops.py -k "attention and warp"
 run ops_attn_tc 600 tests/test_gpu_ops.py -k "attention and tc"
 run decode_simt 900 tests/test_gpu_decode.py -k "offline_decode and simt"

@@ -96,3 +96,15 @@ def ln(reps, rows=192000, C=1024):
 
 if __name__ == "__main__" and sys.argv[1] == "ln":
     ln(int(sys.argv[2]) if len(sys.argv) > 2 else 10)
+
+
+def resample_bench(reps, B=64, n=720000):
+    from fireredtts2_b200.codec import resample
+    x = torch.randn(B, n, device="cuda") * 0.1
+    ms = timeit(lambda: resample(x, 24000, 16000), reps)
+    by = B * n * 4 * (1 + 2 / 3)
+    print(f"resample 24k->16k B={B} n={n}: {ms:.3f} ms  {by / ms / 1e6:.0f} GB/s (algorithmic: 4 B in + 8/3 B out per input sample)")
+
+
+if __name__ == "__main__" and sys.argv[1] == "resample":
+    resample_bench(int(sys.argv[2]) if len(sys.argv) > 2 else 10)
