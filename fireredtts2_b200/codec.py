@@ -43,7 +43,7 @@ def resample(waveform: torch.Tensor, orig_freq: int, new_freq: int, lengths: Opt
     if int(orig_freq) == int(new_freq):
         return waveform
     shape = waveform.shape
-    x = waveform.to(torch.float32).reshape(-1, shape[-1])
+    x = waveform.to(torch.float32).reshape(int(np.prod(shape[:-1], dtype=np.int64)), shape[-1])
     if x.stride(1) != 1:
         x = x.contiguous()
     B, n = x.shape

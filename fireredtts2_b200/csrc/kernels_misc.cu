@@ -359,6 +359,52 @@ __global__ void __launch_bounds__(256) resample_kernel(const float* __restrict__
   }
 }
 
+// few output phases per frame (24 kHz -> 16 kHz: 2; 16 -> 24: 3): one thread produces ALL phases of a frame, so every
+// staged input sample is read from shared memory once per frame instead of once per output, and the taps come from a
+// [k][phase] shared-memory copy as one broadcast read per k.  Same sequential-k fp32 accumulation as the generic kernel.
+template <int NP>
+__global__ void __launch_bounds__(256) resample_np_kernel(const float* __restrict__ x, long long x_pitch, long long n_in,
+                                                          const int* __restrict__ lengths,
+                                                          const float* __restrict__ taps, int K, int width, int orig,
+                                                          int fr, float* __restrict__ y, long long y_pitch,
+                                                          long long n_out_max) {
+  extern __shared__ float s_in[];
+  const int span = (fr - 1) * orig + K;
+  float* s_taps = s_in + ((span + 3) & ~3);      // [K][NP]
+  const int b = blockIdx.y;
+  const long long n = (lengths != nullptr) ? min(static_cast<long long>(lengths[b]), n_in) : n_in;
+  const long long n_out = (n * NP + orig - 1) / orig;
+  const long long m0 = static_cast<long long>(blockIdx.x) * fr;
+  const long long in0 = m0 * orig - width;
+  const float* xb = x + b * x_pitch;
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    const long long g = in0 + i;
+    s_in[i] = (g >= 0 && g < n) ? __ldg(xb + g) : 0.f;
+  }
+  for (int i = threadIdx.x; i < K * NP; i += blockDim.x) {
+    const int k = i / NP, p = i - k * NP;
+    s_taps[i] = __ldg(taps + static_cast<long long>(p) * K + k);
+  }
+  __syncthreads();
+  float* yb = y + b * y_pitch;
+  for (int m = threadIdx.x; m < fr; m += blockDim.x) {
+    const long long j0 = (m0 + m) * NP;
+    if (j0 >= n_out_max) break;
+    float acc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[p] = 0.f;
+    const float* xi = s_in + m * orig;
+    for (int k = 0; k < K; ++k) {
+      const float xv = xi[k];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) acc[p] = fmaf(xv, s_taps[k * NP + p], acc[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+      if (j0 + p < n_out_max) yb[j0 + p] = (j0 + p < n_out) ? acc[p] : 0.f;
+  }
+}
+
 int resample_rows(const float* x, int64_t x_pitch, int B, int64_t n_in, const int* lengths, const float* taps, int K,
                   int width, int orig, int nnew, float* y, int64_t y_pitch, cudaStream_t stream) {
   if (B <= 0 || n_in <= 0) return FRT2_OK;
@@ -368,8 +414,20 @@ int resample_rows(const float* x, int64_t x_pitch, int B, int64_t n_in, const in
   const int span = (fr - 1) * orig + K;
   const int64_t frames = (n_out_max + nnew - 1) / nnew;
   dim3 grid(static_cast<unsigned>((frames + fr - 1) / fr), B);
-  resample_kernel<<<grid, 256, static_cast<size_t>(span) * 4, stream>>>(x, x_pitch, n_in, lengths, taps, K, width, orig,
-                                                                        nnew, fr, y, y_pitch, n_out_max);
+  const size_t smem_np = (static_cast<size_t>((span + 3) & ~3) + static_cast<size_t>(K) * nnew) * 4;
+  if (nnew == 2) {
+    resample_np_kernel<2><<<grid, 256, smem_np, stream>>>(x, x_pitch, n_in, lengths, taps, K, width, orig, fr, y,
+                                                          y_pitch, n_out_max);
+  } else if (nnew == 3) {
+    resample_np_kernel<3><<<grid, 256, smem_np, stream>>>(x, x_pitch, n_in, lengths, taps, K, width, orig, fr, y,
+                                                          y_pitch, n_out_max);
+  } else if (nnew == 1) {
+    resample_np_kernel<1><<<grid, 256, smem_np, stream>>>(x, x_pitch, n_in, lengths, taps, K, width, orig, fr, y,
+                                                          y_pitch, n_out_max);
+  } else {
+    resample_kernel<<<grid, 256, static_cast<size_t>(span) * 4, stream>>>(x, x_pitch, n_in, lengths, taps, K, width,
+                                                                          orig, nnew, fr, y, y_pitch, n_out_max);
+  }
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;
 }
