@@ -1071,7 +1071,7 @@ attention_t3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t a_p_full = ptx::smem_u32(&p_full[t]), a_pv_done = ptx::smem_u32(&pv_done[t]);
 
     for (int j = 0; j < my_tiles; ++j) {
-      ptx::mbar_wait(a_s_full, j & 1);
+      ptx::mbar_wait_likely_ready(a_s_full, j & 1);
       ptx::tc_fence_after();
       uint32_t sa[32], sb[32];
       ptx::tmem_ld32(tmem_s + lane_off, sa);
@@ -1151,7 +1151,7 @@ attention_t3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       // the P columns are free once P_{j-1} V_{j-1} has completed (issued a whole softmax period ago)
       if (j > 0) {
-        ptx::mbar_wait(a_pv_done, (j - 1) & 1);
+        ptx::mbar_wait_likely_ready(a_pv_done, (j - 1) & 1);
         ptx::tc_fence_after();
       }
       ptx::tmem_st32(tmem_p + lane_off, w);

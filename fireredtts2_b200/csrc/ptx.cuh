@@ -75,17 +75,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return mbar_try_wait(smem_u32(bar), parity);
 }
 // non-blocking probe (never suspends the thread): for an issuing thread that polls several barriers round-robin
-__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
       "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
       "selp.b32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar), "r"(parity)
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) { return mbar_test(smem_u32(bar), parity); }
+
 // Bounded spin: a protocol bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
@@ -104,6 +106,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) __trap();
   }
+}
+// wait that is expected to find the phase already complete: probe without suspending first
+__device__ __forceinline__ void mbar_wait_likely_ready(uint32_t bar, uint32_t parity) {
+  if (!mbar_test(bar, parity)) mbar_wait(bar, parity);
 }
 
 // ---------------------------------------------------------------- fences
