@@ -108,6 +108,15 @@ struct GemmDesc {
   __half* out16_b;
   int64_t ld16_b, pitch16_b;
   const int* row_off_b;   // indexed with row_off_stride like out_row_off
+  // LayerNorm folded across two tcgen05 GEMMs (offline path, gemm_tc only).  LN(x) W^T = rstd (x (gamma.W)^T - mean
+  // colsum) + (bias + beta W^T): the PRODUCER of the fp32 residual stream x (a GEMM with `resid`) also writes an fp16
+  // copy of x; row_stats_kernel reads that copy (2 B per element instead of LayerNorm's 4 in + 2 out) and leaves
+  // (mean, rstd) per row; the CONSUMER runs on the raw fp16 rows with gamma-folded weights and finishes the
+  // normalisation in its epilogue.
+  __half* x16_out;        // producer: fp16 copy of the output rows, flat (batches*rows_out, ld_x16)
+  int64_t ld_x16;
+  const float2* stats_in; // consumer: (mean, rstd) of its A rows
+  const float* colsum;    // consumer: (N) sum_k of the folded fp16 weights of column n
   // optional fused LayerNorm(+SiLU) prologue (gemm_skinny only, ntaps == 1): the A rows are LN(ln_x) computed on the
   // fly from the fp32 residual stream (rows at ln_x + m*ln_ldx) instead of being read from A
   const float* ln_x;
@@ -182,6 +191,8 @@ int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_
                             int64_t out_batch_pitch, cudaStream_t stream);
 int resample_rows(const float* x, int64_t x_pitch, int B, int64_t n_in, const int* lengths, const float* taps, int K,
                   int width, int orig, int nnew, float* y, int64_t y_pitch, cudaStream_t stream);
+// (mean, rstd) per row of an fp16 matrix (the statistics of a folded LayerNorm)
+int row_stats(const __half* x16, int64_t ld, int64_t rows, int C, float eps, float2* stats, cudaStream_t stream);
 int tma_encode_fp16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box);
 int num_sms();

@@ -27,6 +27,7 @@ constexpr int DBG_GEMM_REF = 2;   // route every GEMM through the SIMT check ker
 constexpr int DBG_ATTN_WARP = 4;  // route attention through the warp kernel (tests only)
 constexpr int DBG_NO_SKINNY = 16; // streaming: keep the tcgen05 GEMM even for <= 16 rows
 constexpr int DBG_NO_GRAPH = 8;   // streaming: launch kernel by kernel instead of replaying the captured CUDA graph
+constexpr int DBG_NO_LNFOLD = 32; // offline: separate LayerNorm kernels instead of LN folded across the GEMMs (A/B, tests)
 
 struct HostTensor {
   std::vector<int64_t> shape;
@@ -45,6 +46,10 @@ struct ResW {
 struct LayerW {
   float *ln1_g, *ln1_b, *b_qkv, *b_o, *ln2_g, *ln2_b, *b_fc1, *b_fc2;
   __half *w_qkv, *w_o, *w_fc1, *w_fc2;
+  // LayerNorm folded into the consuming GEMM: W' = W diag(gamma) (fp16), colsum[n] = sum_k W'[n,k] (of the ROUNDED
+  // fp16 values the tensor cores see), bias' = bias + W beta
+  __half *w_qkv_f, *w_fc1_f;
+  float *s_qkv, *c_qkv, *s_fc1, *c_fc1;
 };
 
 // small elementwise helpers -------------------------------------------------------------------------
@@ -259,6 +264,7 @@ struct Handle {
   std::vector<LayerW> layers;
   float *fn_g = nullptr, *fn_b = nullptr;
   __half* w_head = nullptr;    float* b_head = nullptr;
+  __half* w_head_f = nullptr;  float* s_head = nullptr;  float* c_head = nullptr;   // final_norm folded into the head
   __half* w_idft = nullptr;
   float* window = nullptr;
   unsigned int* err_word = nullptr;
@@ -322,6 +328,29 @@ struct Handle {
     return FRT2_OK;
   }
 
+  // fold LayerNorm(gamma, beta) into the Linear (W (N,K) row-major, bias (N) or null) that consumes it
+  int fold_ln(const float* W, const float* bias, const float* gamma, const float* beta, int64_t Nn, int64_t Kk,
+              __half** w_f, float** colsum, float** bias_f) {
+    std::vector<float> Wf(static_cast<size_t>(Nn) * Kk), cs(Nn), bf(Nn);
+#pragma omp parallel for schedule(static)
+    for (long long n = 0; n < Nn; ++n) {
+      double sacc = 0.0, bacc = bias ? bias[n] : 0.0;
+      for (int64_t k = 0; k < Kk; ++k) {
+        const float w = W[n * Kk + k];
+        const float wf = w * gamma[k];
+        Wf[n * Kk + k] = wf;
+        sacc += static_cast<double>(__half2float(__float2half_rn(std::min(65504.0f, std::max(-65504.0f, wf)))));
+        bacc += static_cast<double>(beta[k]) * w;
+      }
+      cs[n] = static_cast<float>(sacc);
+      bf[n] = static_cast<float>(bacc);
+    }
+    FRT2_TRY(upload_f16(Wf, w_f));
+    FRT2_TRY(upload_f32(cs, colsum));
+    FRT2_TRY(upload_f32(bf, bias_f));
+    return FRT2_OK;
+  }
+
   const HostTensor* find(const std::string& key) const {
     auto it = raw.find(key);
     return it == raw.end() ? nullptr : &it->second;
@@ -350,7 +379,7 @@ struct Handle {
     const double flops = 2.0 * g.batches * g.rows_out * static_cast<double>(g.N) * g.ntaps * g.Kc;
     const double bytes = 2.0 * (static_cast<double>(g.batches) * g.rows_a * g.Kc + static_cast<double>(g.N) * g.ntaps * g.Kc) +
                          static_cast<double>(g.batches) * g.rows_out * g.N *
-                             ((g.out32 ? 4 : 0) + (g.out16 ? 2 : 0) + (g.resid ? 4 : 0));
+                             ((g.out32 ? 4 : 0) + (g.out16 ? 2 : 0) + (g.resid ? 4 : 0) + (g.x16_out ? 2 : 0));
     const bool skinny = !(debug & (DBG_GEMM_REF | DBG_NO_SKINNY)) && gemm_skinny_applicable(g);
     const int id = prof_begin(skinny ? FRT2_PROF_GEMM_SKINNY : FRT2_PROF_GEMM, flops, bytes, st);
     const int rc = (debug & DBG_GEMM_REF) ? gemm_ref(g, st) : (skinny ? gemm_skinny(g, st) : gemm_tc(g, st));
@@ -614,6 +643,18 @@ int Handle::finalize() {
     FRT2_TRY(up_vec(p + "self_attn_layer_norm.bias", E, &lw.ln1_b));
     FRT2_TRY(up_vec(p + "final_layer_norm.weight", E, &lw.ln2_g));
     FRT2_TRY(up_vec(p + "final_layer_norm.bias", E, &lw.ln2_b));
+    {
+      const HostTensor *g1, *b1, *g2, *b2, *bf1;
+      FRT2_TRY(need(p + "self_attn_layer_norm.weight", &g1, {E}));
+      FRT2_TRY(need(p + "self_attn_layer_norm.bias", &b1, {E}));
+      FRT2_TRY(need(p + "final_layer_norm.weight", &g2, {E}));
+      FRT2_TRY(need(p + "final_layer_norm.bias", &b2, {E}));
+      FRT2_TRY(need(p + "fc1.bias", &bf1, {4 * E}));
+      FRT2_TRY(fold_ln(wqkv.data(), bqkv.data(), g1->data.data(), b1->data.data(), 3 * E, E, &lw.w_qkv_f, &lw.s_qkv,
+                       &lw.c_qkv));
+      FRT2_TRY(fold_ln(w1->data.data(), bf1->data.data(), g2->data.data(), b2->data.data(), 4 * E, E, &lw.w_fc1_f,
+                       &lw.s_fc1, &lw.c_fc1));
+    }
   }
   FRT2_TRY(up_vec(BB + "final_norm.weight", E, &fn_g));
   FRT2_TRY(up_vec(BB + "final_norm.bias", E, &fn_b));
@@ -633,6 +674,13 @@ int Handle::finalize() {
     }
     FRT2_TRY(upload_f16(W, &w_head));
     FRT2_TRY(upload_f32(bb, &b_head));
+    {
+      const HostTensor *fg, *fb;
+      FRT2_TRY(need(BB + "final_norm.weight", &fg, {E}));
+      FRT2_TRY(need(BB + "final_norm.bias", &fb, {E}));
+      FRT2_TRY(fold_ln(W.data(), bb.data(), fg->data.data(), fb->data.data(), 2 * n_bins, E, &w_head_f, &s_head,
+                       &c_head));
+    }
     FRT2_TRY(upload_f32(win->data, &window));
     // windowed inverse real DFT as a (n_fft x spec_ld) matrix over interleaved (Re, Im) columns:
     // fr[n] = (1/N) [Re S0 + (-1)^n Re S_{N/2} + 2 sum_f (Re S_f cos(2 pi f n/N) - Im S_f sin(2 pi f n/N))]
@@ -706,7 +754,7 @@ size_t Handle::ws_bytes_for(int B, int L) const {
   const size_t R = static_cast<size_t>(B) * L, M = 8 * R;
   const size_t sizes[] = {R * rd * 4, R * rd * 2, R * E * 2, R * 4 * E * 2, R * 4 * E * 2, M * E * 2, M * E * 2,
                           M * E * 4, M * E * 4, M * E * 2, M * 3 * E * 2, M * E * 2, M * 4 * E * 2,
-                          M * spec_ld * 2, M * n_fft * 4};
+                          M * spec_ld * 2, M * n_fft * 4, M * 8};
   size_t off = 0;
   for (size_t b : sizes) off = align_up(off + b, 1024);
   return off;
@@ -737,7 +785,9 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   const size_t o_x32 = carve(M * E * 4), o_y32 = carve(M * E * 4), o_n16 = carve(M * E * 2);
   const size_t o_qkv = carve(M * 3 * E * 2), o_o16 = carve(M * E * 2), o_g16 = carve(M * 4 * E * 2);
   const size_t o_spec = carve(M * spec_ld * 2), o_frames = carve(M * n_fft * 4);
+  const size_t o_stats = carve(M * 8);
   FRT2_TRY(ensure_ws(off));
+  float2* stats = reinterpret_cast<float2*>(ws + o_stats);
   float* emb32 = reinterpret_cast<float*>(ws + o_emb32);
   __half* emb16 = reinterpret_cast<__half*>(ws + o_emb16);
   __half* z16 = reinterpret_cast<__half*>(ws + o_z16);
@@ -768,9 +818,23 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   // compute LayerNorm on the fly from the fp32 residual stream: the separate LN launch (and its round trip) goes.
   static const bool no_lnfuse = (getenv("FRT2_NO_LNFUSE") != nullptr);   // A/B switch for measurements
   const bool fuse_ln = (M <= 16) && !no_lnfuse && !(debug & (DBG_GEMM_REF | DBG_NO_SKINNY | DBG_TAPS));
+  // Offline path: LayerNorm folded across the GEMMs (the producer of x32 also emits x16 + row partials into n16 /
+  // stats, the consumer runs on x16 with gamma-folded weights) — 25 of the 33 LayerNorm launches disappear; the
+  // LN + SiLU in front of the convolutions cannot be folded (non-linearity between LN and the contraction).
+  static const bool no_lnfold_env = (getenv("FRT2_NO_LNFOLD") != nullptr);   // A/B switch for measurements
+  const bool fold = !streaming && M > 16 && (B == 1 || T > 64) /* producers must not use packed-item tiles */ &&
+                    E % 8 == 0 && E <= 2048 && nl > 0 && !no_lnfold_env &&
+                    !(debug & (DBG_GEMM_REF | DBG_TAPS | DBG_NO_LNFOLD));
+  struct Fold { const __half* W; const float* colsum; const float* bias; float eps; };
+  auto run_stats = [&](float eps) -> int {   // (mean, rstd) of the rows of n16 (2 B per element in)
+    const int id = prof_begin(FRT2_PROF_LAYER_NORM, 0.0, static_cast<double>(M) * E * 2.0, st);
+    const int rc = row_stats(n16, E, M, E, eps, stats, st);
+    prof_end(id, st);
+    return rc;
+  };
   auto flat_gemm = [&](const __half* A, int64_t rows, int Kdim, const __half* W, int N, const float* bias, int act,
                        const float* resid, float* out32, __half* out16, int64_t ld16, float alpha = 1.0f,
-                       const LnFuse* ln = nullptr) {
+                       const LnFuse* ln = nullptr, const Fold* fc = nullptr, bool emit_stats = false) {
     GemmDesc g{};
     g.A = A; g.a_row_pitch = Kdim; g.a_batch_pitch = 0; g.rows_a = static_cast<int>(rows); g.batches = 1;
     g.Kc = Kdim; g.ntaps = 1; g.row_shift = 0; g.W = W; g.N = N; g.rows_out = static_cast<int>(rows);
@@ -779,17 +843,27 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     if (ln != nullptr) {
       g.ln_x = ln->x; g.ln_ldx = Kdim; g.ln_gamma = ln->g; g.ln_beta = ln->b; g.ln_eps = ln->eps; g.ln_silu = 0;
     }
+    if (fc != nullptr) {      // consumer of a folded LayerNorm: A is the raw fp16 residual stream
+      FRT2_TRY(run_stats(fc->eps));
+      g.W = fc->W; g.bias = fc->bias; g.colsum = fc->colsum; g.stats_in = stats;
+    }
+    if (emit_stats) {         // producer: fp16 copy of the new residual stream for the next folded LayerNorm
+      g.x16_out = n16; g.ld_x16 = E;
+    }
     return run_gemm(g, st);
   };
   // causal conv over cb[i] with `taps` taps producing `rows` rows per item
   auto conv_gemm = [&](const CB& in, int rows, int taps, const __half* W, int N, const float* bias, int act,
                        const float* resid, float* out32, int64_t pitch32, __half* out16, int64_t ld16,
-                       int64_t pitch16) {
+                       int64_t pitch16, bool emit_stats = false) {
     GemmDesc g{};
     g.A = in.p; g.a_row_pitch = E; g.a_batch_pitch = in.pitch; g.rows_a = in.hist + rows; g.batches = B;
     g.Kc = E; g.ntaps = taps; g.row_shift = in.hist - (taps - 1); g.W = W; g.N = N; g.rows_out = rows;
     g.pitch32 = pitch32; g.pitch16 = pitch16; g.alpha = 1.0f; g.bias = bias; g.act = act; g.resid = resid;
     g.out32 = out32; g.ld32 = E; g.out16 = out16; g.ld16 = ld16;
+    if (emit_stats) {
+      g.x16_out = n16; g.ld_x16 = E;
+    }
     return run_gemm(g, st);
   };
   auto chunk_ptr = [&](const CB& c) { return c.p + static_cast<int64_t>(c.hist) * E; };
@@ -828,31 +902,33 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   // ---- backbone: in_proj k7, 2 resnet blocks ----
   const int64_t xp = static_cast<int64_t>(T) * E;
   FRT2_TRY(conv_gemm(cb[2], T, 7, w_inproj, E, b_inproj, ACT_NONE, nullptr, x32, xp, nullptr, 0, 0));
-  auto resblock = [&](int r) -> int {
+  auto resblock = [&](int r, bool emit_stats = false) -> int {
     const ResW& w = res[r];
     const CB& c1 = cb[3 + 2 * r];
     const CB& c2 = cb[4 + 2 * r];
     FRT2_TRY(run_ln(x32, M, T, w.ln1_g, w.ln1_b, 1e-5f, 1, chunk_ptr(c1), c1.pitch, st));
     FRT2_TRY(conv_gemm(c1, T, 3, w.w1, E, w.b1, ACT_NONE, nullptr, y32, xp, nullptr, 0, 0));
     FRT2_TRY(run_ln(y32, M, T, w.ln2_g, w.ln2_b, 1e-5f, 1, chunk_ptr(c2), c2.pitch, st));
-    FRT2_TRY(conv_gemm(c2, T, 3, w.w2, E, w.b2, ACT_NONE, x32, x32, xp, nullptr, 0, 0));
+    FRT2_TRY(conv_gemm(c2, T, 3, w.w2, E, w.b2, ACT_NONE, x32, x32, xp, nullptr, 0, 0, emit_stats));
     return FRT2_OK;
   };
   FRT2_TRY(resblock(0));
-  FRT2_TRY(resblock(1));
+  FRT2_TRY(resblock(1, fold));           // feeds layer 0's self_attn_layer_norm
   FRT2_TRY(tap_f32("prior", x32, M * E, st));
   // ---- 12 pre-LN transformer layers ----
   for (int i = 0; i < nl; ++i) {
     const LayerW& w = layers[i];
     const LnFuse ln1{x32, w.ln1_g, w.ln1_b, 1e-5f};
     const LnFuse ln2{x32, w.ln2_g, w.ln2_b, 1e-5f};
-    if (!fuse_ln) FRT2_TRY(run_ln(x32, M, static_cast<int>(M), w.ln1_g, w.ln1_b, 1e-5f, 0, n16, 0, st));
+    const Fold f_qkv{w.w_qkv_f, w.s_qkv, w.c_qkv, 1e-5f};
+    const Fold f_fc1{w.w_fc1_f, w.s_fc1, w.c_fc1, 1e-5f};
+    if (!fuse_ln && !fold) FRT2_TRY(run_ln(x32, M, static_cast<int>(M), w.ln1_g, w.ln1_b, 1e-5f, 0, n16, 0, st));
     AttnDesc a{};
     a.B = B; a.H = H; a.hd = hd; a.Tq = T; a.out = o16; a.o_row_pitch = E; a.o_batch_pitch = xp;
     a.scale = 1.0f / std::sqrt(static_cast<float>(hd));
     if (!streaming) {
       FRT2_TRY(flat_gemm(n16, M, E, w.w_qkv, 3 * E, w.b_qkv, ACT_NONE, nullptr, nullptr, qkv16, 3 * E, 1.0f,
-                         fuse_ln ? &ln1 : nullptr));
+                         fuse_ln ? &ln1 : nullptr, fold ? &f_qkv : nullptr));
       a.q = qkv16; a.q_row_pitch = 3 * E; a.q_batch_pitch = static_cast<int64_t>(T) * 3 * E;
       a.k = qkv16 + E; a.v = qkv16 + 2 * E; a.kv_row_pitch = 3 * E; a.kv_batch_pitch = a.q_batch_pitch;
       a.Tk = T; a.q_pos0 = 0; a.block_causal = 1;
@@ -886,18 +962,21 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
       if (graph_mode) a.ctrl = s->ctrl;
     }
     FRT2_TRY(run_attn(a, st));
-    FRT2_TRY(flat_gemm(o16, M, E, w.w_o, E, w.b_o, ACT_NONE, x32, x32, nullptr, 0));
-    if (!fuse_ln) FRT2_TRY(run_ln(x32, M, static_cast<int>(M), w.ln2_g, w.ln2_b, 1e-5f, 0, n16, 0, st));
+    FRT2_TRY(flat_gemm(o16, M, E, w.w_o, E, w.b_o, ACT_NONE, x32, x32, nullptr, 0, 1.0f, nullptr, nullptr, fold));
+    if (!fuse_ln && !fold) FRT2_TRY(run_ln(x32, M, static_cast<int>(M), w.ln2_g, w.ln2_b, 1e-5f, 0, n16, 0, st));
     FRT2_TRY(flat_gemm(n16, M, E, w.w_fc1, 4 * E, w.b_fc1, ACT_GELU, nullptr, nullptr, g16, 4 * E, 1.0f,
-                       fuse_ln ? &ln2 : nullptr));
-    FRT2_TRY(flat_gemm(g16, M, 4 * E, w.w_fc2, E, w.b_fc2, ACT_NONE, x32, x32, nullptr, 0));
+                       fuse_ln ? &ln2 : nullptr, fold ? &f_fc1 : nullptr));
+    // fc2 feeds the next layer's self_attn_layer_norm (the last layer is followed by an LN + SiLU: not folded)
+    FRT2_TRY(flat_gemm(g16, M, 4 * E, w.w_fc2, E, w.b_fc2, ACT_NONE, x32, x32, nullptr, 0, 1.0f, nullptr, nullptr,
+                       fold && i + 1 < nl));
     if (i == 0) FRT2_TRY(tap_f32("layer0", x32, M * E, st));
   }
   FRT2_TRY(tap_f32("layers", x32, M * E, st));
   FRT2_TRY(resblock(2));
-  FRT2_TRY(resblock(3));
+  FRT2_TRY(resblock(3, fold));             // feeds final_norm
   const LnFuse lnf{x32, fn_g, fn_b, 1e-6f};
-  if (!fuse_ln) FRT2_TRY(run_ln(x32, M, static_cast<int>(M), fn_g, fn_b, 1e-6f, 0, n16, 0, st));
+  const Fold f_head{w_head_f, s_head, c_head, 1e-6f};
+  if (!fuse_ln && !fold) FRT2_TRY(run_ln(x32, M, static_cast<int>(M), fn_g, fn_b, 1e-6f, 0, n16, 0, st));
   FRT2_TRY(tap_f16("final", n16, E, M, E, st));
   // ---- K5: head GEMM with polar epilogue -> windowed inverse DFT GEMM -> overlap-add ----
   if (spec_ld > 2 * n_bins) {
@@ -905,7 +984,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
                                    static_cast<size_t>(spec_ld - 2 * n_bins) * 2, M, st));
   }
   FRT2_TRY(flat_gemm(n16, M, E, w_head, 2 * n_bins, b_head, ACT_POLAR, nullptr, nullptr, spec16, spec_ld, 1.0f,
-                     fuse_ln ? &lnf : nullptr));
+                     fuse_ln ? &lnf : nullptr, fold ? &f_head : nullptr));
   FRT2_TRY(tap_f16("spec", spec16, spec_ld, M, 2 * n_bins, st));
   FRT2_TRY(flat_gemm(spec16, M, spec_ld, w_idft, n_fft, nullptr, ACT_NONE, nullptr, frames32, nullptr, 0,
                      1.0f / static_cast<float>(n_fft)));

@@ -72,6 +72,12 @@ struct GemmKParams {
   int batches;
   int item_mul;        // first item of tile group g is g * item_mul (pack_items when packed, else 1)
   int stage_tx_bytes;  // bytes one pipeline stage receives (A box + W box)
+  // folded LayerNorm (see GemmDesc): producer side ...
+  __half* x16_out;
+  long long ld_x16;
+  // ... and consumer side
+  const float2* stats_in;   // (mean, rstd) per A row
+  const float* colsum;
 };
 
 template <int BN>
@@ -138,9 +144,35 @@ __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
 }
 
 // alpha, bias and activation on one 32-column chunk held by a thread (one output row)
-__device__ __forceinline__ void apply_chunk(const GemmKParams& p, const uint32_t (&r)[32], int n0, float (&v)[32]) {
+__device__ __forceinline__ void apply_chunk(const GemmKParams& p, const uint32_t (&r)[32], int n0, float (&v)[32],
+                                            float ln_mean = 0.f, float ln_rstd = 1.f) {
   const bool full_chunk = n0 + 32 <= p.N;
-  if (p.bias != nullptr) {
+  if (p.colsum != nullptr) {
+    // folded LayerNorm: v = rstd * (acc*alpha - mean*colsum[n]) + bias[n] = acc*k1 + (k2*colsum[n] + bias[n]) with the
+    // per-row k1 = alpha*rstd, k2 = -rstd*mean: two packed FFMA2 per PAIR of columns, i.e. the instruction count of
+    // the plain acc*alpha + bias epilogue
+    const float k1 = p.alpha * ln_rstd, k2 = -ln_rstd * ln_mean;
+    if (full_chunk) {
+      const f32x2 k1p = pk2(k1, k1), k2p = pk2(k2, k2);
+      const float4* c4 = reinterpret_cast<const float4*>(p.colsum + n0);
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 c = __ldg(c4 + j), b = __ldg(b4 + j);
+        const f32x2 t0 = fma2(k2p, pk2(c.x, c.y), pk2(b.x, b.y));
+        const f32x2 t1 = fma2(k2p, pk2(c.z, c.w), pk2(b.z, b.w));
+        unpk2(fma2(pk2(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1])), k1p, t0), v[4 * j + 0], v[4 * j + 1]);
+        unpk2(fma2(pk2(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])), k1p, t1), v[4 * j + 2], v[4 * j + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const bool ok = n0 + j < p.N;
+        v[j] = fmaf(__uint_as_float(r[j]), k1,
+                    fmaf(k2, ok ? __ldg(p.colsum + n0 + j) : 0.f, ok ? __ldg(p.bias + n0 + j) : 0.f));
+      }
+    }
+  } else if (p.bias != nullptr) {
     if (full_chunk && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
@@ -271,6 +303,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
       const int ncol0 = n_idx * BN + hsel * (BN / 2);     // first column owned by this warp
       const uint32_t tmem_acc = tmem_stage + static_cast<uint32_t>(hsel * (BN / 2)) + tmem_lane;
 
+      // folded LayerNorm, consumer side: this thread's row (mean, rstd), computed by row_stats_kernel from the fp16 copy
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (p.stats_in != nullptr && valid_row) {
+        const float2 t = __ldg(p.stats_in + static_cast<long long>(item) * p.rows_out + row);
+        ln_mean = t.x;
+        ln_rstd = t.y;
+      }
+
       // residual prefetch of the first chunk (coalesced; overlaps the wait for the accumulator)
       float4 rpre[8];
       const bool use_resid = (p.store_mode == STORE_TMA32) && (p.resid != nullptr);
@@ -302,7 +342,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
             float v[32];
             ptx::tmem_ld32(tmem_acc + g * 64 + hh * 32, r);
             ptx::tmem_ld_wait();
-            apply_chunk(p, r, n0 + hh * 32, v);
+            apply_chunk(p, r, n0 + hh * 32, v, ln_mean, ln_rstd);
 #pragma unroll
             for (int j = 0; j < 16; ++j) packed[hh * 16 + j] = pack_half2(v[2 * j], v[2 * j + 1]);
           }
@@ -328,7 +368,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
           float v[32];
           ptx::tmem_ld32(tmem_acc + c * 32, r);
           ptx::tmem_ld_wait();
-          apply_chunk(p, r, n0, v);
+          apply_chunk(p, r, n0, v, ln_mean, ln_rstd);
           if (use_resid) {
             // accumulator rows -> staging (row order) -> back in coalesced order, + prefetched residual, then plain
             // coalesced 16-byte global stores (4 full 128-B lines per warp instruction): half the shared-memory
@@ -345,9 +385,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
               const int rr = i * 4 + crow;
               float4 q = *reinterpret_cast<const float4*>(stg + rr * 128 + ((cchunk ^ (rr & 7)) << 4));
               q.x += rpre[i].x; q.y += rpre[i].y; q.z += rpre[i].z; q.w += rpre[i].w;
-              if (row0 + rr < p.rows_out && col_ok)
+              if (row0 + rr < p.rows_out && col_ok) {
                 *reinterpret_cast<float4*>(p.out32 + static_cast<long long>(b) * p.pitch32 +
                                            static_cast<long long>(row0 + rr) * p.ld32 + n0 + cchunk * 4) = q;
+                if (p.x16_out != nullptr) {   // folded LayerNorm, producer side: fp16 copy of the residual stream
+                  uint2 h;
+                  h.x = pack_half2(q.x, q.y);
+                  h.y = pack_half2(q.z, q.w);
+                  *reinterpret_cast<uint2*>(p.x16_out + (static_cast<long long>(b) * p.rows_out + row0 + rr) * p.ld_x16 +
+                                            n0 + cchunk * 4) = h;
+                }
+              }
             }
             if (c + 1 < CHUNKS_PER_WARP && n0 + 32 < p.N) prefetch_resid(n0 + 32);  // in flight during the next chunk
             continue;
@@ -372,7 +420,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
           ptx::tmem_ld32(tmem_acc + c * 32, r);
           ptx::tmem_ld_wait();
           if (valid_row) {
-            apply_chunk(p, r, n0, v);
+            apply_chunk(p, r, n0, v, ln_mean, ln_rstd);
             store_chunk_direct(p, v, off32, off16, n0);
           }
         }
@@ -801,6 +849,15 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   p.store_mode = STORE_DIRECT;
   p.row_off_ptr = g.out_row_off;
   p.row_off_stride = g.row_off_stride;
+  p.x16_out = g.x16_out;
+  p.ld_x16 = g.ld_x16;
+  p.stats_in = g.stats_in;
+  p.colsum = g.stats_in != nullptr ? g.colsum : nullptr;
+  if (g.stats_in != nullptr) {
+    FRT2_REQUIRE(g.colsum != nullptr && g.bias != nullptr && !packed &&
+                     (reinterpret_cast<uintptr_t>(g.colsum) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0,
+                 FRT2_ERR_BAD_ARG, "gemm_tc: folded LayerNorm consumer needs colsum and bias (16-byte aligned)");
+  }
   tmC = tmA;
   const uint64_t batch_rows = static_cast<uint64_t>(g.batches);
   if (g.out_row_off != nullptr || packed) {
@@ -821,6 +878,11 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
     p.store_mode = STORE_TMA32;
   }
 
+  if (g.x16_out != nullptr) {
+    FRT2_REQUIRE(p.store_mode == STORE_TMA32 && g.resid != nullptr && g.N % 4 == 0 && g.ld_x16 % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(g.x16_out) & 7) == 0,
+                 FRT2_ERR_BAD_ARG, "gemm_tc: the fp16 copy of the residual stream needs the fp32 residual epilogue");
+  }
   if (pair) {
     const int grid = 2 * std::min(p.num_tiles, g_num_sms / 2);
     gemm_tc2_kernel<<<grid, GEMM_THREADS, Gemm2Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);

@@ -208,6 +208,73 @@ int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_
   return FRT2_OK;
 }
 
+// =====================================================================================================
+// K4b — row statistics of the fp16 residual copy (folded LayerNorm): one warp per row, the row lives in registers
+// (C <= 2048: 8 x 16 B per lane), mean first, then the centred sum of squares.  2 B per element in, 8 B per row out.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) row_stats_kernel(const __half* __restrict__ x, long long ld, long long rows, int C,
+                                                        float eps, float2* __restrict__ stats) {
+  // two rows per warp, all loads of both rows in flight before the first use; ONE shuffle round per row pair:
+  // sums of (x - shift) and (x - shift)^2 with shift = the row's first element (no cancellation for rows with a
+  // large common offset), mean = shift + s1/C, var = s2/C - (s1/C)^2
+  const long long row0 = (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 2;
+  if (row0 >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int C8 = C >> 3;
+  uint4 cache[2][8];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + min(row0 + r, rows - 1) * ld);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C8) cache[r][i] = __ldcs(xr + c);
+    }
+  }
+  float s1[2], s2[2], shift[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const float first = __half2float(*reinterpret_cast<const __half*>(&cache[r][0]));   // lane 0 holds element 0
+    shift[r] = __shfl_sync(0xffffffffu, first, 0);
+    s1[r] = s2[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (lane + 32 * i < C8) {
+        const __half2* h = reinterpret_cast<const __half2*>(&cache[r][i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          const float a = f.x - shift[r], b = f.y - shift[r];
+          s1[r] += a + b;
+          s2[r] = fmaf(a, a, fmaf(b, b, s2[r]));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o);
+      s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
+    }
+  }
+  if (lane < 2 && row0 + lane < rows) {
+    const float inv_c = 1.0f / static_cast<float>(C);
+    const float m = (lane == 0 ? s1[0] : s1[1]) * inv_c;
+    const float var = fmaxf((lane == 0 ? s2[0] : s2[1]) * inv_c - m * m, 0.f);
+    stats[row0 + lane] = make_float2((lane == 0 ? shift[0] : shift[1]) + m, rsqrtf(var + eps));
+  }
+}
+
+int row_stats(const __half* x16, int64_t ld, int64_t rows, int C, float eps, float2* stats, cudaStream_t stream) {
+  FRT2_REQUIRE(C % 8 == 0 && C <= 2048 && ld % 8 == 0, FRT2_ERR_BAD_ARG, "row_stats: C must be a multiple of 8, <= 2048");
+  if (rows == 0) return FRT2_OK;
+  row_stats_kernel<<<static_cast<unsigned>((rows + 15) / 16), 256, 0, stream>>>(x16, ld, rows, C, eps, stats);
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
+
 int layer_norm_rows(const float* x, int64_t ldx, int rows, int C, const float* gamma, const float* beta, float eps,
                     int apply_silu, __half* out16, int64_t ld16, cudaStream_t stream) {
   return layer_norm_rows_batched(x, ldx, rows, rows > 0 ? rows : 1, C, gamma, beta, eps, apply_silu, out16, ld16, 0,

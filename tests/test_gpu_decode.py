@@ -55,6 +55,23 @@ def test_offline_decode_vs_reference_golden(case, mode):
     _gate(f"{case['name']}/{mode}/audio", g["audio"], audio)
 
 
+@pytest.mark.parametrize("case", cases("offline") + cases("reference_init"), ids=lambda c: c["name"])
+def test_folded_layernorm_vs_reference_golden(case):
+    """Product offline path (LayerNorm folded across the GEMMs: producer epilogue emits the fp16 residual copy + row
+    partials, consumer epilogue finishes the normalisation) and the same decode with separate LayerNorm kernels, both
+    against the reference's golden waveform."""
+    cfg, sd, g = load_case(case)
+    codec = build_codec(cfg, sd)
+    tok = torch.from_numpy(g["tokens"]).cuda()
+    folded = to_np(codec.decode(tok))
+    codec.set_debug(N.DBG_NO_LNFOLD)
+    plain = to_np(codec.decode(tok))
+    _gate(f"{case['name']}/ln-folded", g["audio"], folded)
+    _gate(f"{case['name']}/ln-kernels", g["audio"], plain)
+    _, snr = report(f"{case['name']}/folded-vs-kernels", plain, folded)
+    assert snr >= 50.0
+
+
 def test_c0_offline_vs_reference_golden():
     case = [c for c in cases("offline") if c["preset"] == "C0"][0]
     cfg, sd, g = load_case(case)
