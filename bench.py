@@ -279,6 +279,15 @@ def run_ours(args):
     ref = O.decode(sd, tok_s, cfg.num_heads, cfg.hop_length)
     parity = {"sample": "config 1: tokens (1,16,125), 10 s", "snr_db": O.snr_db(ref, a_gpu),
               "max_abs": float(np.abs(ref - a_gpu).max()), "ref_peak": float(np.abs(ref).max()), "gate_snr_db": 40.0}
+    # full-size property (the oracle cannot run 64 x 30 s): every item of the timed batch must equal, bit for bit, the
+    # standalone decode of the same tokens (items are independent; catches tile-scheduling / aliasing faults that only
+    # show when a launch runs many waves of tiles)
+    picks = sorted({0, B // 3, (2 * B) // 3, B - 1})
+    full = codec.decode(tok_dev)
+    worst = 0.0
+    for k in picks:
+        worst = max(worst, float((codec.decode(tok_dev[k:k + 1])[0] - full[k]).abs().max()))
+    parity["full_size_items_vs_standalone"] = {"items": picks, "max_abs": worst, "expect": 0.0}
     cores = os.cpu_count() or 1
     cpu = {"value": audio_s / min(ts), "unit": UNIT, "cores": cores, "kind": "port",
            "sample": "config 1: one 10 s utterance (tokens (1,16,125)), torch-CPU port of the reference, best of 3 after 1 warm-up"}

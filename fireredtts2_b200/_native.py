@@ -16,6 +16,7 @@ DBG_TAPS, DBG_GEMM_REF, DBG_ATTN_WARP, DBG_NO_GRAPH, DBG_NO_SKINNY, DBG_NO_LNFOL
 ACT_NONE, ACT_GELU, ACT_POLAR = 0, 1, 2
 SLOT_ACTIVE, SLOT_LAST, SLOT_RESET = 1, 2, 4
 POOL_MAX_SLOTS = 256
+PEER_HANDLE_BYTES = 64
 PROF_GEMM, PROF_ATTN_TC, PROF_ATTN_WARP, PROF_LAYER_NORM, PROF_RVQ, PROF_OLA, PROF_GEMM_SKINNY, PROF_ALL = \
     0, 1, 2, 3, 4, 5, 6, -1
 PROF_NAMES = {PROF_GEMM: "gemm_tc", PROF_ATTN_TC: "attention_tc", PROF_ATTN_WARP: "attention_warp",
@@ -45,6 +46,11 @@ SIGNATURES = {
     "frt2_destroy": (None, [_p]),
     "frt2_decode": (_i, [_p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _p, _i64, _p]),
     "frt2_decode_pcm16": (_i, [_p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _p, _i64, _p]),
+    "frt2_decode_scatter": (_i, [_p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _p, _i, _p, _p]),
+    "frt2_peer_alloc": (_i, [_i, _i64, C.POINTER(_p), C.c_char_p]),
+    "frt2_peer_open": (_i, [_i, C.c_char_p, C.POINTER(_p)]),
+    "frt2_peer_close": (_i, [_i, _p]),
+    "frt2_peer_free": (_i, [_i, _p]),
     "frt2_stream_create": (_i, [_p, _i, _i, C.POINTER(_p)]),
     "frt2_stream_reset": (_i, [_p]),
     "frt2_stream_destroy": (None, [_p]),

@@ -203,6 +203,34 @@ class RedCodecB200(torch.nn.Module):
         return audio
 
     @torch.inference_mode()
+    def decode_into(self, tokens: torch.Tensor, out_ptr: int, out_off: torch.Tensor,
+                    lengths: Optional[torch.Tensor] = None, pcm16: bool = False) -> None:
+        """Offline decode whose items are scattered: item b's ``1920 * L_b`` samples are written at element offset
+        ``out_off[b]`` of the buffer at device address ``out_ptr`` (fp32, or int16 PCM with ``pcm16``) and nothing
+        beyond them.  ``out_ptr`` may be a local tensor's ``data_ptr()`` — the turns of a dialogue land at their place
+        in the concatenated waveform (reference fireredtts2.py:399-401) — or a buffer of another GPU mapped with
+        ``sharding.PeerBuffer``, in which case the overlap-add kernel's stores go over NVLink (frt2_decode_scatter)."""
+        tokens = self._prep_tokens(tokens)
+        B, nq, L = tokens.shape
+        if L == 0 or B == 0:
+            return
+        with torch.cuda.device(self.device_index):
+            out_off = out_off.to(device=tokens.device, dtype=torch.int64).contiguous()
+            if out_off.numel() != B:
+                raise ValueError("out_off must have B entries")
+            lptr = None
+            if lengths is not None:
+                lengths = lengths.to(device=tokens.device, dtype=torch.int32).contiguous()
+                if lengths.numel() != B:
+                    raise ValueError("lengths must have B entries")
+                lptr = C.c_void_p(lengths.data_ptr())
+            sB, sQ, sL = tokens.stride()
+            N.check(self._lib.frt2_decode_scatter(
+                self._h, C.c_void_p(tokens.data_ptr()), tokens.element_size(), sB, sQ, sL, B, nq, L, lptr,
+                C.c_void_p(int(out_ptr)), 1 if pcm16 else 0, C.c_void_p(out_off.data_ptr()), self._cuda_stream()))
+            self._maybe_check()
+
+    @torch.inference_mode()
     def decode_one_token(self, token: torch.Tensor, cache_dict: Dict[str, object], last_token: bool,
                          pcm16: bool = False, _check: bool = True) -> Tuple[torch.Tensor, Dict[str, object]]:
         """RedCodecInfer.decode_one_token (reference model.py:326-376).  Extension: ``pcm16=True`` returns the chunk

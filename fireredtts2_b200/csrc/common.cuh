@@ -181,6 +181,8 @@ struct OlaDesc {
   int B, T, n_fft, hop;
   int first, last;       // streaming flags; offline == first && last
   const int* ctrl;       // optional per-item control blocks: first = (pos == 0), last and active come from HBM
+  const long long* out_off;  // optional (offline): item b's samples go to audio/pcm16 + out_off[b] instead of b*audio_pitch,
+                             // and nothing is written past the item's own sample count (scatter into a shared buffer)
 };
 int istft_overlap_add(const OlaDesc& d, cudaStream_t stream);
 int istft_update_tail(const float* frames, int64_t frames_batch_pitch, float* tail, int B, int T, int n_fft,

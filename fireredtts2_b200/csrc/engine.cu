@@ -293,6 +293,7 @@ struct Handle {
   }
 
   int16_t* pcm16_out = nullptr;  // set (under the mutex) by frt2_decode_pcm16 for the next pipeline run
+  const long long* scatter_off = nullptr;  // set (under the mutex) by frt2_decode_scatter: per-item output offsets
 
   // workspace arena (grow-only)
   uint8_t* ws = nullptr;
@@ -810,7 +811,10 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     cb[0] = {reinterpret_cast<__half*>(ws + o_x50), 0, static_cast<int64_t>(T50) * E};
     cb[1] = {reinterpret_cast<__half*>(ws + o_a16), 0, static_cast<int64_t>(T) * E};
     cb[2] = {reinterpret_cast<__half*>(ws + o_u16), 0, static_cast<int64_t>(T) * E};
-    for (int i = 3; i < 11; ++i) cb[i] = {n16, 0, static_cast<int64_t>(T) * E};
+    // the resnet-block convolutions read their LN+SiLU'd input from a16 (dead once upsample_conv has run), NOT from
+    // n16: with the folded LayerNorm the last conv of a block writes the fp16 copy of its output rows to n16 from its
+    // epilogue while later tiles of the same launch are still loading their A rows
+    for (int i = 3; i < 11; ++i) cb[i] = {reinterpret_cast<__half*>(ws + o_a16), 0, static_cast<int64_t>(T) * E};
   }
 
   struct LnFuse { const float* x; const float* g; const float* b; float eps; };
@@ -824,7 +828,8 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   static const bool no_lnfold_env = (getenv("FRT2_NO_LNFOLD") != nullptr);   // A/B switch for measurements
   const bool fold = !streaming && M > 16 && (B == 1 || T > 64) /* producers must not use packed-item tiles */ &&
                     E % 8 == 0 && E <= 2048 && nl > 0 && !no_lnfold_env &&
-                    !(debug & (DBG_GEMM_REF | DBG_TAPS | DBG_NO_LNFOLD));
+                    !(debug & (DBG_GEMM_REF | DBG_NO_LNFOLD)) &&
+                    (!(debug & DBG_TAPS) || getenv("FRT2_FOLD_WITH_TAPS") != nullptr /* debugging: "final" is then raw */);
   struct Fold { const __half* W; const float* colsum; const float* bias; float eps; };
   auto run_stats = [&](float eps) -> int {   // (mean, rstd) of the rows of n16 (2 B per element in)
     const int id = prof_begin(FRT2_PROF_LAYER_NORM, 0.0, static_cast<double>(M) * E * 2.0, st);
@@ -993,6 +998,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   od.frames = frames32; od.frames_batch_pitch = static_cast<int64_t>(T) * n_fft; od.window = window;
   od.lengths = lengths; od.len_mul = 8; od.audio = audio; od.audio_pitch = audio_pitch; od.B = B; od.T = T;
   od.pcm16 = pcm16_out;
+  od.out_off = streaming ? nullptr : scatter_off;
   od.n_fft = n_fft; od.hop = hop;
   if (streaming) {
     od.tail = s->tail; od.first = (s->n_tokens == 0); od.last = last;
@@ -1186,6 +1192,67 @@ int frt2_decode_pcm16(frt2_handle* hh, const void* tokens, int idx_bytes, int64_
                             static_cast<cudaStream_t>(cuda_stream));
   h.pcm16_out = nullptr;
   return rc;
+}
+
+int frt2_decode_scatter(frt2_handle* hh, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
+                        int nq, int L, const int32_t* lengths, void* out_base, int out_pcm16, const int64_t* out_off,
+                        void* cuda_stream) {
+  FRT2_REQUIRE(hh, FRT2_ERR_BAD_ARG, "null handle");
+  Handle& h = hh->h;
+  FRT2_TRY(check_decode_args(h, tokens, idx_bytes, B, nq, L, reinterpret_cast<const float*>(out_base)));
+  FRT2_REQUIRE(out_off != nullptr, FRT2_ERR_BAD_ARG, "frt2_decode_scatter: null out_off");
+  std::lock_guard<std::mutex> lk(h.mu);
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  h.scatter_off = reinterpret_cast<const long long*>(out_off);
+  h.pcm16_out = out_pcm16 ? static_cast<int16_t*>(out_base) : nullptr;
+  const int rc = h.pipeline(tokens, idx_bytes, sB, sQ, sL, B, nq, L, lengths, out_pcm16 ? nullptr : static_cast<float*>(out_base),
+                            0, nullptr, 1, static_cast<cudaStream_t>(cuda_stream));
+  h.scatter_off = nullptr;
+  h.pcm16_out = nullptr;
+  return rc;
+}
+
+// ---- peer memory: a waveform buffer on one GPU that the other ranks' overlap-add kernels write into ----
+int frt2_peer_alloc(int device, int64_t bytes, void** ptr, unsigned char* handle) {
+  FRT2_REQUIRE(ptr && handle && bytes > 0, FRT2_ERR_BAD_ARG, "frt2_peer_alloc: bad argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == FRT2_PEER_HANDLE_BYTES, "IPC handle size");
+  FRT2_CUDA_OK(cudaSetDevice(device));
+  void* p = nullptr;
+  FRT2_CUDA_OK(cudaMalloc(&p, static_cast<size_t>(bytes)));
+  cudaIpcMemHandle_t hd;
+  const cudaError_t e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    FRT2_CUDA_OK(e);
+  }
+  std::memcpy(handle, &hd, sizeof(hd));
+  *ptr = p;
+  return FRT2_OK;
+}
+
+int frt2_peer_open(int device, const unsigned char* handle, void** ptr) {
+  FRT2_REQUIRE(ptr && handle, FRT2_ERR_BAD_ARG, "frt2_peer_open: bad argument");
+  FRT2_CUDA_OK(cudaSetDevice(device));
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, handle, sizeof(hd));
+  void* p = nullptr;
+  FRT2_CUDA_OK(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+  *ptr = p;
+  return FRT2_OK;
+}
+
+int frt2_peer_close(int device, void* ptr) {
+  FRT2_REQUIRE(ptr, FRT2_ERR_BAD_ARG, "frt2_peer_close: null pointer");
+  FRT2_CUDA_OK(cudaSetDevice(device));
+  FRT2_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+  return FRT2_OK;
+}
+
+int frt2_peer_free(int device, void* ptr) {
+  if (ptr == nullptr) return FRT2_OK;
+  FRT2_CUDA_OK(cudaSetDevice(device));
+  FRT2_CUDA_OK(cudaFree(ptr));
+  return FRT2_OK;
 }
 
 int frt2_stream_create(frt2_handle* hh, int B, int max_tokens, frt2_stream** out) {

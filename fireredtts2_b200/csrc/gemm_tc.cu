@@ -882,6 +882,14 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
     FRT2_REQUIRE(p.store_mode == STORE_TMA32 && g.resid != nullptr && g.N % 4 == 0 && g.ld_x16 % 4 == 0 &&
                      (reinterpret_cast<uintptr_t>(g.x16_out) & 7) == 0,
                  FRT2_ERR_BAD_ARG, "gemm_tc: the fp16 copy of the residual stream needs the fp32 residual epilogue");
+    // the copy is written by the epilogue of early tiles while later tiles still load A: the two must not overlap
+    const char* a_lo = reinterpret_cast<const char*>(g.A);
+    const char* a_hi = a_lo + (static_cast<int64_t>(g.batches - 1) * g.a_batch_pitch +
+                               static_cast<int64_t>(g.rows_a) * g.a_row_pitch) * 2;
+    const char* x_lo = reinterpret_cast<const char*>(g.x16_out);
+    const char* x_hi = x_lo + static_cast<int64_t>(g.batches) * g.rows_out * g.ld_x16 * 2;
+    FRT2_REQUIRE(a_hi <= x_lo || x_hi <= a_lo, FRT2_ERR_BAD_ARG,
+                 "gemm_tc: the fp16 copy of the output rows must not alias the A operand");
   }
   if (pair) {
     const int grid = 2 * std::min(p.num_tiles, g_num_sms / 2);

@@ -316,8 +316,9 @@ __global__ void __launch_bounds__(256) overlap_add_kernel(OlaDesc d, int ntail, 
     TF = min(TF, d.lengths[b] * d.len_mul);
     n_out = TF * d.hop;
   }
-  const long long oidx = static_cast<long long>(b) * d.audio_pitch + n;
+  const long long oidx = (d.out_off != nullptr ? d.out_off[b] : static_cast<long long>(b) * d.audio_pitch) + n;
   if (n >= n_out) {
+    if (d.out_off != nullptr) return;   // scatter form: the neighbouring unit owns those samples
     if (d.pcm16 != nullptr) d.pcm16[oidx] = 0;
     else d.audio[oidx] = 0.f;
     return;

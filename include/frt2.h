@@ -76,6 +76,29 @@ int frt2_decode(frt2_handle* h, const void* tokens, int idx_bytes, int64_t sB, i
 int frt2_decode_pcm16(frt2_handle* h, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
                       int nq, int L, const int32_t* lengths, int16_t* pcm, int64_t pcm_pitch, void* cuda_stream);
 
+/* Offline decode that SCATTERS its items: item b's 8*hop*L_b samples (L_b = lengths[b], or L when lengths is NULL) go
+ * to out_base + out_off[b] (element offsets, device int64 (B)); nothing is written beyond an item's own samples.  This
+ * is how the turns of a dialogue land directly at their place in the concatenated waveform (the reference
+ * concatenates the decoded turns on the time axis afterwards, fireredtts2.py:399-401) — and, with out_base a buffer of
+ * ANOTHER GPU opened through frt2_peer_open, how a rank's overlap-add kernel delivers its waveforms to the gathering
+ * rank over NVLink without a separate collective.  out_pcm16 != 0: out_base is int16 PCM (see frt2_decode_pcm16). */
+int frt2_decode_scatter(frt2_handle* h, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
+                        int nq, int L, const int32_t* lengths, void* out_base, int out_pcm16, const int64_t* out_off,
+                        void* cuda_stream);
+
+/* ---- peer memory for the waveform gather ("NCCL over NVLink only to gather waveform chunks") ----
+ * The gathering rank allocates the destination buffer with frt2_peer_alloc and publishes the 64-byte handle (through
+ * torch.distributed, a file, ... — plain bytes); every other rank (one process per GPU, same box) maps it with
+ * frt2_peer_open and passes the mapped pointer as `audio` / `out_base` of its decode calls, so the last kernel of the
+ * path writes over NVLink / NVSwitch peer stores while the rest of the batch is still computing.  The writer
+ * synchronises its stream, then the ranks meet at a barrier; after that the owner may read the buffer.  All four
+ * calls are synchronous. */
+#define FRT2_PEER_HANDLE_BYTES 64
+int frt2_peer_alloc(int device, int64_t bytes, void** ptr, unsigned char* handle /* FRT2_PEER_HANDLE_BYTES out */);
+int frt2_peer_open(int device, const unsigned char* handle, void** ptr);
+int frt2_peer_close(int device, void* ptr);
+int frt2_peer_free(int device, void* ptr);
+
 /* ---- streaming decode: RedCodecInfer.decode_one_token (model.py:326-376) ----
  * The stream object owns what the reference keeps in cache_dict (up_conv_cache, bb_conv_cache1/2, bb_kv_cache,
  * is_cache) in HBM, updated in place. */

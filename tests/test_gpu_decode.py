@@ -145,6 +145,72 @@ def test_varlen_lengths_extension():
     assert np.all(a[1, (L - 4) * spt:] == 0)
 
 
+def test_c0_multi_wave_batch_items_are_independent():
+    """A batch large enough that every GEMM of the step runs several waves of tiles over the 148 SMs (12 x 159 tokens
+    at C0 = 15 264 frames): identical items must decode to bit-identical waveforms, equal to the standalone decode of
+    one item — with and without the folded LayerNorm.  (Regression: the folded-LayerNorm producer once wrote its fp16
+    copy into the buffer later tiles of the same launch were still reading as A.)"""
+    from fireredtts2_b200.config import C0
+    from fireredtts2_b200.weights import synthetic_state_dict, synthetic_tokens
+    import fireredtts2_b200._native as N
+    cfg = C0
+    codec = build_codec(cfg, synthetic_state_dict(cfg, 0), check_indices=False)
+    one = torch.from_numpy(synthetic_tokens(cfg, 1, 159, 77)).cuda()
+    tok = one.expand(12, -1, -1).contiguous()
+    outs = {}
+    for name, flags in (("fold", 0), ("nofold", N.DBG_NO_LNFOLD)):
+        codec.set_debug(flags)
+        single = codec.decode(one)
+        batch = codec.decode(tok)
+        diffs = [float((batch[k] - single[0]).abs().max()) for k in range(12)]
+        print(f"[parity] c0 12x159 {name}: max |item_k - standalone| = {max(diffs):.3e}")
+        assert max(diffs) == 0.0, (name, diffs)
+        outs[name] = to_np(single)
+    codec.set_debug(0)
+    _, snr = report("c0 12x159 fold vs separate LayerNorm kernels", outs["nofold"], outs["fold"])
+    assert snr > 50.0
+
+
+def test_scatter_decode_equals_padded_decode_bitwise():
+    """frt2_decode_scatter: each item's samples land at its own offset of one flat buffer (the concatenated dialogue,
+    reference fireredtts2.py:399-401), bit-identical to the padded-batch decode, and nothing else is touched."""
+    from fireredtts2_b200.sharding import PeerBuffer, unit_offsets
+    case = cases("offline")[0]
+    cfg, sd, g = load_case(case)
+    codec = build_codec(cfg, sd)
+    tok = torch.from_numpy(g["tokens"]).cuda()
+    B, _, L = tok.shape
+    spt = cfg.samples_per_token
+    lens = [L, L - 4][:B] + [L] * max(0, B - 2)
+    lens_t = torch.tensor(lens, dtype=torch.int32)
+    a = codec.decode(tok, lengths=lens_t)
+    order = list(reversed(range(B)))                       # units are laid out in reverse item order, with a gap
+    offs = unit_offsets([lens[i] for i in order], spt)
+    gap = 7
+    item_off = {i: offs[k] + gap * (k + 1) for k, i in enumerate(order)}
+    total = offs[-1] + gap * (B + 1)
+    for pcm16 in (False, True):
+        ref = codec.decode(tok, lengths=lens_t, pcm16=pcm16)
+        sentinel = 12345 if pcm16 else 777.0
+        buf = PeerBuffer(total, torch.int16 if pcm16 else torch.float32, torch.device("cuda", 0))
+        try:
+            flat = buf.tensor()
+            flat.fill_(sentinel)
+            codec.decode_into(tok, buf.ptr, torch.tensor([item_off[i] for i in range(B)]), lens_t, pcm16=pcm16)
+            torch.cuda.synchronize()
+            mask = torch.ones(total, dtype=torch.bool, device="cuda")
+            for i in range(B):
+                n = spt * lens[i]
+                assert torch.equal(flat[item_off[i]:item_off[i] + n], ref[i, :n]), (i, pcm16)
+                mask[item_off[i]:item_off[i] + n] = False
+            assert bool((flat[mask] == sentinel).all())    # gaps and the padding of short items stay untouched
+        finally:
+            buf.close()
+    assert torch.equal(a, codec.decode(tok, lengths=lens_t))
+    with pytest.raises(ValueError):
+        codec.decode_into(tok, 0, torch.zeros(B, dtype=torch.int64), lens_t)
+
+
 @pytest.mark.parametrize("mode", ["tc_gemm+warp_attn", "product", "no_graph", "no_skinny"])
 @pytest.mark.parametrize("case", cases("stream"), ids=lambda c: c["name"])
 def test_streaming_vs_reference_golden(case, mode):

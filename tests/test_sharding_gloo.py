@@ -114,3 +114,11 @@ def test_single_process_path_without_dist():
     units = _units(3, seed=1)
     res = decode_sharded(_oracle_decode_fn(sd), units, torch.device("cpu"))
     assert [r.shape[0] for r in res] == [TINY.samples_per_token * u.shape[1] for u in units]
+
+
+def test_unit_offsets_is_the_concatenation_layout():
+    from fireredtts2_b200.sharding import unit_offsets
+    lens = dialogue_turn_lengths()
+    offs = unit_offsets(lens)
+    assert offs[0] == 0 and offs[-1] == 1920 * 2250 and len(offs) == len(lens) + 1
+    assert all(offs[i + 1] - offs[i] == 1920 * lens[i] for i in range(len(lens)))

@@ -1,6 +1,7 @@
 """BASELINE.json configs[3]: a 3-minute 4-speaker dialogue (24 turns, 2250 tokens) with the turns sharded over the
-ranks and the waveform chunks gathered to rank 0 in turn order over NCCL.  Launch with torchrun (or plain python for
-1 GPU).  Prints one JSON line on rank 0."""
+ranks and the waveform chunks gathered to rank 0 in turn order over NCCL — or, with `--peer`, written by every rank's
+overlap-add kernel straight to the turn's place in the concatenated waveform on rank 0 (NVLink peer memory,
+sharding.decode_sharded_peer).  Launch with torchrun (or plain python for 1 GPU).  Prints one JSON line on rank 0."""
 import json
 import os
 import sys
@@ -12,7 +13,7 @@ import torch.distributed as dist
 
 from fireredtts2_b200.codec import RedCodecB200
 from fireredtts2_b200.config import C0
-from fireredtts2_b200.sharding import decode_sharded, dialogue_turn_lengths, partition_units
+from fireredtts2_b200.sharding import decode_sharded, decode_sharded_peer, dialogue_turn_lengths, partition_units
 from fireredtts2_b200.weights import synthetic_state_dict
 
 
@@ -30,8 +31,20 @@ def main():
     g = torch.Generator().manual_seed(11)
     units = [torch.randint(0, cfg.codebook_size, (cfg.num_quantizers, L), generator=g, dtype=torch.int32) for L in lens]
     fn = lambda tok, lengths: codec.decode(tok, lengths)
-    for _ in range(3):
+    peer = "--peer" in sys.argv
+    pbuf = None
+    if peer:
+        _, _, pbuf = decode_sharded_peer(codec, units, dev)
+
+    def run():
+        if peer:
+            flat, _, _ = decode_sharded_peer(codec, units, dev, buffer=pbuf)
+            return flat
         res = decode_sharded(fn, units, dev)
+        return torch.cat(res) if rank == 0 else None   # the concatenated dialogue (fireredtts2.py:401)
+
+    for _ in range(3):
+        run()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -41,9 +54,7 @@ def main():
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        res = decode_sharded(fn, units, dev)
-        if rank == 0:
-            full = torch.cat(res)           # (4 320 000,) the concatenated dialogue (fireredtts2.py:401)
+        full = run()                        # (4 320 000,) on rank 0
         torch.cuda.synchronize()
         ts.append(time.perf_counter() - t0)
     t = torch.tensor([min(ts)], device=dev, dtype=torch.float64)
@@ -55,11 +66,15 @@ def main():
         err = float((ref - full).abs().max())
         plan = partition_units(lens, world)
         print(json.dumps({"workload": "configs[3]: 180 s dialogue, 24 turns, 2250 tokens", "n_gpus": world,
+                          "gather": "peer-memory scatter over NVLink" if peer else "nccl send/recv",
                           "seconds": float(t[0]), "audio_s_per_s": 180.0 / float(t[0]),
                           "samples": int(full.numel()), "max_abs_vs_unsharded": err,
                           "rank_loads_tokens": [sum(lens[i] for i in p) for p in plan]}), flush=True)
     if world > 1:
         dist.barrier()
+    if pbuf is not None:
+        pbuf.close()
+    if world > 1:
         dist.destroy_process_group()
 
 
