@@ -63,6 +63,7 @@ SIGNATURES = {
     "frt2_pool_slot_tokens": (_i, [_p, _i]),
     "frt2_export_state": (_i, [_p, _p, _p, _p, _p, _p, _p, _p]),
     "frt2_import_state": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p]),
+    "frt2_rvq_encode": (_i, [_p, _p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p]),
     "frt2_resample": (_i, [_i, _p, _i64, _i, _i64, _p, _i, _i, _p, _i64, C.POINTER(_i64), _p]),
     "frt2_rvq_gather": (_i, [_p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _p, _p]),
     "frt2_set_debug": (_i, [_p, _i]),

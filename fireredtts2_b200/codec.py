@@ -121,6 +121,16 @@ class RedCodecB200(torch.nn.Module):
             a = np.ascontiguousarray(sd[key], dtype=np.float32)
             shape = (C.c_int64 * a.ndim)(*a.shape)
             N.check(self._lib.frt2_load_tensor(self._h, key.encode(), a.ctypes.data_as(C.c_void_p), a.ndim, shape, 0))
+        # encode-side tensors of the RVQ (optional: present in a full RedCodec checkpoint, absent from decode-only dicts)
+        self.has_rvq_encoder = False
+        for key, v in sd.items():
+            if key.startswith("rvq.") and (".in_project." in key or key.startswith("rvq.input_proj.")):
+                a = np.ascontiguousarray(v, dtype=np.float32)
+                shape = (C.c_int64 * a.ndim)(*a.shape)
+                N.check(self._lib.frt2_load_tensor(self._h, key.encode(), a.ctypes.data_as(C.c_void_p), a.ndim, shape, 0))
+                self.has_rvq_encoder = True
+        if not cfg.has_out_project:
+            self.has_rvq_encoder = True      # Identity in_project: the codebooks are all the encoder needs
         N.check(self._lib.frt2_finalize(self._h))
 
     # ------------------------------------------------------------------ constructors
@@ -337,6 +347,25 @@ class RedCodecB200(torch.nn.Module):
         if enc is None:
             raise NotImplementedError("encode() needs the reference RedCodecInfer (use RedCodecB200.from_reference)")
         return enc.encode(*args, **kwargs)
+
+    @torch.inference_mode()
+    def rvq_encode_codes(self, z: torch.Tensor, nq: Optional[int] = None) -> torch.Tensor:
+        """``ResidualVQ.encode_codes`` (reference rvq.py:128-143): z (B, input_dim, T) fp32, any strides (the
+        reference passes a transposed view, model.py:240) -> codes (nq, B, T) int64.  One CUDA kernel
+        (frt2_rvq_encode); needs the checkpoint's ``in_project`` / ``input_proj`` tensors in the state_dict."""
+        if z.dim() != 3:
+            raise ValueError(f"z must be (B, input_dim, T), got {tuple(z.shape)}")
+        dev = torch.device("cuda", self.device_index)
+        z = z.to(device=dev, dtype=torch.float32)
+        B, D, T = z.shape
+        nq = self.cfg.num_quantizers if nq is None else nq
+        with torch.cuda.device(self.device_index):
+            codes = torch.empty((nq, B, T), dtype=torch.int64, device=dev)
+            if B * T > 0:
+                sB, sD, sT = z.stride()
+                N.check(self._lib.frt2_rvq_encode(self._h, C.c_void_p(z.data_ptr()), sB, sD, sT, B, D, T, nq,
+                                                  C.c_void_p(codes.data_ptr()), self._cuda_stream()))
+        return codes
 
     # ------------------------------------------------------------------ parity hooks
     def rvq_gather(self, tokens: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:

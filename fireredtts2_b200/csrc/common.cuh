@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 
 #include "../../include/frt2.h"
@@ -165,6 +166,24 @@ int rvq_gather_sum(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, in
                    const float* tables /*(nq,K,D)*/, int K, int D, float* sum32 /*(B*L,D) or null*/,
                    __half* sum16 /*(B*L,D) or null*/, float* rows /*(B,L,nq,D) or null*/, unsigned int* err_word,
                    cudaStream_t stream);
+// RVQ encode (rvq_encode.cu): everything fp32, [k][column] weight layouts built at load
+struct RvqEncDesc {
+  const float* z;            // (B, input_dim, T) with element strides sB, sD, sT
+  int64_t sB, sD, sT;
+  int B, T, nq;
+  int input_dim, rd, cd, K;
+  const float* WinpT;        // (input_dim, rd) input_proj^T or null (Identity: input_dim == rd)
+  const float* binp;         // (rd)
+  const float* WinT;         // (nq, rd, cd) in_project^T or null (Identity: rd == cd)
+  const float* bin;          // (nq, cd)
+  const float* CT;           // (nq, cd, K) transposed codebooks
+  const float* c2;           // (nq, K) |c|^2
+  const float* C;            // (nq, K, cd) codebooks
+  const float* WoutT;        // (nq, cd, rd) out_project^T or null
+  const float* bout;         // (nq, rd)
+  long long* codes;          // (nq, B, T) int64
+};
+int rvq_encode(const RvqEncDesc& d, cudaStream_t stream);
 int layer_norm_rows(const float* x, int64_t ldx, int rows, int C, const float* gamma, const float* beta, float eps,
                     int apply_silu, __half* out16, int64_t ld16, cudaStream_t stream);
 // Overlap-add of windowed frames + window-square envelope normalisation + "same" trimming.

@@ -254,6 +254,12 @@ struct Handle {
   // packed weights
   float* codebooks = nullptr;  // (nq,K,cd) raw
   float* tables = nullptr;     // (nq,K,rd) folded with out_project (== codebooks when Identity)
+  // RVQ encode side (optional: built when the checkpoint's in_project / input_proj tensors were handed over)
+  bool enc_ready = false;
+  int enc_input_dim = 0;
+  float *enc_WinpT = nullptr, *enc_binp = nullptr, *enc_WinT = nullptr, *enc_bin = nullptr, *enc_CT = nullptr,
+        *enc_c2 = nullptr, *enc_WoutT = nullptr, *enc_bout = nullptr;
+  int build_rvq_encoder();
   __half* w_outproj = nullptr; float* b_outproj = nullptr;
   __half* w_up_in = nullptr;   float* b_up_in = nullptr;
   __half* w_up_conv = nullptr;
@@ -482,6 +488,77 @@ static std::vector<float> weight_norm_host(const HostTensor& g, const HostTensor
   return W;
 }
 
+// Encode-side tables of ResidualVQ (rvq.py:62-89,128-143), fp32, [k][column] layouts for coalesced reads.
+int Handle::build_rvq_encoder() {
+  const std::string RVQ = "rvq.";
+  if (has_out_project && find(RVQ + "quantizers.0.in_project.bias") == nullptr) return FRT2_OK;   // decode-only weights
+  const HostTensor* t = nullptr;
+  // input_proj: WNConv1d(input_dim, rvq_dim, 1) or Identity (rvq.py:110-114)
+  enc_input_dim = rd;
+  if (const HostTensor* v = find(RVQ + "input_proj.parametrizations.weight.original1")) {
+    FRT2_REQUIRE(v->shape.size() == 3 && v->shape[0] == rd && v->shape[2] == 1, FRT2_ERR_BAD_ARG,
+                 "rvq.input_proj weight must be (rvq_dim, input_dim, 1)");
+    enc_input_dim = static_cast<int>(v->shape[1]);
+    const HostTensor *g, *b;
+    FRT2_TRY(need(RVQ + "input_proj.parametrizations.weight.original0", &g, {rd, 1, 1}));
+    FRT2_TRY(need(RVQ + "input_proj.bias", &b, {rd}));
+    const std::vector<float> W = weight_norm_host(*g, *v);   // (rd, input_dim)
+    std::vector<float> WT(W.size());
+    for (int o = 0; o < rd; ++o)
+      for (int k = 0; k < enc_input_dim; ++k) WT[static_cast<size_t>(k) * rd + o] = W[static_cast<size_t>(o) * enc_input_dim + k];
+    FRT2_TRY(upload_f32(WT, &enc_WinpT));
+    FRT2_TRY(upload_f32(b->data, &enc_binp));
+  }
+  std::vector<float> CT(static_cast<size_t>(nq) * cd * K), c2(static_cast<size_t>(nq) * K);
+  std::vector<float> WinT, bin, WoutT, bout;
+  if (has_out_project) {
+    WinT.resize(static_cast<size_t>(nq) * rd * cd);
+    bin.resize(static_cast<size_t>(nq) * cd);
+    WoutT.resize(static_cast<size_t>(nq) * cd * rd);
+    bout.resize(static_cast<size_t>(nq) * rd);
+  }
+  for (int i = 0; i < nq; ++i) {
+    const std::string q = RVQ + "quantizers." + std::to_string(i);
+    FRT2_TRY(need(q + ".codebook", &t, {K, cd}));
+    for (int64_t k = 0; k < K; ++k) {
+      double ss = 0.0;
+      for (int c = 0; c < cd; ++c) {
+        const float v = t->data[k * cd + c];
+        CT[(static_cast<size_t>(i) * cd + c) * K + k] = v;
+        ss += static_cast<double>(v) * v;
+      }
+      c2[static_cast<size_t>(i) * K + k] = static_cast<float>(ss);
+    }
+    if (has_out_project) {
+      const HostTensor *g, *v, *b;
+      FRT2_TRY(need(q + ".in_project.parametrizations.weight.original0", &g, {cd, 1, 1}));
+      FRT2_TRY(need(q + ".in_project.parametrizations.weight.original1", &v, {cd, rd, 1}));
+      FRT2_TRY(need(q + ".in_project.bias", &b, {cd}));
+      const std::vector<float> Wi = weight_norm_host(*g, *v);   // (cd, rd)
+      for (int o = 0; o < cd; ++o)
+        for (int k = 0; k < rd; ++k) WinT[(static_cast<size_t>(i) * rd + k) * cd + o] = Wi[static_cast<size_t>(o) * rd + k];
+      std::memcpy(&bin[static_cast<size_t>(i) * cd], b->data.data(), static_cast<size_t>(cd) * 4);
+      FRT2_TRY(need(q + ".out_project.parametrizations.weight.original0", &g, {rd, 1, 1}));
+      FRT2_TRY(need(q + ".out_project.parametrizations.weight.original1", &v, {rd, cd, 1}));
+      FRT2_TRY(need(q + ".out_project.bias", &b, {rd}));
+      const std::vector<float> Wo = weight_norm_host(*g, *v);   // (rd, cd)
+      for (int o = 0; o < rd; ++o)
+        for (int k = 0; k < cd; ++k) WoutT[(static_cast<size_t>(i) * cd + k) * rd + o] = Wo[static_cast<size_t>(o) * cd + k];
+      std::memcpy(&bout[static_cast<size_t>(i) * rd], b->data.data(), static_cast<size_t>(rd) * 4);
+    }
+  }
+  FRT2_TRY(upload_f32(CT, &enc_CT));
+  FRT2_TRY(upload_f32(c2, &enc_c2));
+  if (has_out_project) {
+    FRT2_TRY(upload_f32(WinT, &enc_WinT));
+    FRT2_TRY(upload_f32(bin, &enc_bin));
+    FRT2_TRY(upload_f32(WoutT, &enc_WoutT));
+    FRT2_TRY(upload_f32(bout, &enc_bout));
+  }
+  enc_ready = true;
+  return FRT2_OK;
+}
+
 int Handle::finalize() {
   FRT2_CUDA_OK(cudaSetDevice(device));
   FRT2_TRY(gemm_tc_init());
@@ -523,6 +600,7 @@ int Handle::finalize() {
     if (has_out_project) FRT2_TRY(upload_f32(tab, &tables));
     else tables = codebooks;
   }
+  FRT2_TRY(build_rvq_encoder());
   if (has_output_proj) {
     const HostTensor *g, *v, *bo;
     FRT2_TRY(need(RVQ + "output_proj.parametrizations.weight.original0", &g, {E, 1, 1}));
@@ -1129,8 +1207,8 @@ int frt2_load_tensor(frt2_handle* hh, const char* key, const float* data, int nd
   Handle& h = hh->h;
   FRT2_REQUIRE(!h.finalized, FRT2_ERR_BAD_ARG, "frt2_load_tensor: handle already finalized");
   const std::string k(key);
-  // encode-only / training-only tensors are not part of the decode path
-  for (const char* skip : {"input_proj", "in_project", "inited", "cluster_size", "embed_avg"})
+  // training-only buffers are not part of the path (in_project / input_proj feed frt2_rvq_encode)
+  for (const char* skip : {"inited", "cluster_size", "embed_avg"})
     if (k.find(skip) != std::string::npos) return FRT2_OK;
   if (k.rfind("rvq.", 0) != 0 && k.rfind("upsample.", 0) != 0 && k.rfind("acoustic_decoder.", 0) != 0) return FRT2_OK;
   HostTensor t;
@@ -1567,6 +1645,26 @@ int frt2_rvq_gather(frt2_handle* hh, const void* tokens, int idx_bytes, int64_t 
   FRT2_CUDA_OK(cudaSetDevice(h.device));
   return rvq_gather_sum(tokens, idx_bytes, sB, sQ, sL, B, nq, L, h.codebooks, h.K, h.cd, sum, nullptr, rows, h.err_word,
                         static_cast<cudaStream_t>(cuda_stream));
+}
+
+int frt2_rvq_encode(frt2_handle* hh, const float* z, int64_t sB, int64_t sD, int64_t sT, int B, int input_dim, int T,
+                    int nq, int64_t* codes, void* cuda_stream) {
+  FRT2_REQUIRE(hh, FRT2_ERR_BAD_ARG, "null handle");
+  Handle& h = hh->h;
+  FRT2_REQUIRE(h.finalized, FRT2_ERR_NOT_FINALIZED, "handle not finalized");
+  FRT2_REQUIRE(h.enc_ready, FRT2_ERR_MISSING_TENSOR,
+               "frt2_rvq_encode: the encode-side tensors (rvq.quantizers.*.in_project, rvq.input_proj) were not loaded");
+  FRT2_REQUIRE(z != nullptr && codes != nullptr && B >= 0 && T >= 0, FRT2_ERR_BAD_ARG, "frt2_rvq_encode: bad argument");
+  FRT2_REQUIRE(input_dim == h.enc_input_dim, FRT2_ERR_BAD_ARG, "frt2_rvq_encode: z must have rvq.input_dim channels");
+  FRT2_REQUIRE(nq >= 1 && nq <= h.nq, FRT2_ERR_BAD_ARG, "nq must be in [1, num_quantizers]");
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  RvqEncDesc d{};
+  d.z = z; d.sB = sB; d.sD = sD; d.sT = sT; d.B = B; d.T = T; d.nq = nq;
+  d.input_dim = h.enc_input_dim; d.rd = h.rd; d.cd = h.cd; d.K = h.K;
+  d.WinpT = h.enc_WinpT; d.binp = h.enc_binp; d.WinT = h.enc_WinT; d.bin = h.enc_bin; d.CT = h.enc_CT; d.c2 = h.enc_c2;
+  d.C = h.codebooks; d.WoutT = h.enc_WoutT; d.bout = h.enc_bout;
+  d.codes = reinterpret_cast<long long*>(codes);
+  return rvq_encode(d, static_cast<cudaStream_t>(cuda_stream));
 }
 
 // FIR bank of torchaudio's sinc_interp_hann resampler, computed in float32 in the same operation order as

@@ -114,6 +114,22 @@ def synthetic_state_dict(cfg: CodecConfig, seed: int = 0) -> Dict[str, np.ndarra
     return sd
 
 
+def synthetic_encode_tensors(cfg: CodecConfig, seed: int = 0, input_dim: int = None) -> Dict[str, np.ndarray]:
+    """The encode-side tensors of ``ResidualVQ`` that ``synthetic_state_dict`` leaves out (they are not part of the
+    decode path): ``rvq.input_proj`` (present iff input_dim != rvq_dim, reference rvq.py:110-114) and every
+    ``rvq.quantizers.{i}.in_project`` (present iff rvq_dim != codebook_dim, rvq.py:28-34).  Own generator, so the
+    decode-side weights (and the golden vectors made from them) do not change."""
+    rng = np.random.default_rng(seed + 7919)
+    sd: Dict[str, np.ndarray] = {}
+    input_dim = cfg.embed_dim if input_dim is None else input_dim
+    if input_dim != cfg.rvq_dim:
+        _wn_conv1x1(rng, sd, PREFIX_RVQ + "input_proj", cfg.rvq_dim, input_dim)
+    if cfg.has_out_project:
+        for i in range(cfg.num_quantizers):
+            _wn_conv1x1(rng, sd, f"{PREFIX_RVQ}quantizers.{i}.in_project", cfg.codebook_dim, cfg.rvq_dim)
+    return sd
+
+
 def decode_keys(cfg: CodecConfig) -> List[str]:
     """Every state_dict key the decode path consumes, in the order they are handed to the C-ABI."""
     return list(synthetic_state_dict_keys(cfg))

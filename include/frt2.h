@@ -149,6 +149,18 @@ int frt2_import_state(frt2_handle* h, frt2_stream* s, int n_tokens, const float*
                       const float* bb_conv_cache1, const float* bb_conv_cache2, const float* bb_kv_cache,
                       const float* is_cache, void* cuda_stream);
 
+/* ---- RVQ encode (first stage): ResidualVQ.encode_codes (rvq.py:128-143) ----
+ * The producer of the token tensors this library decodes: input_proj, then per quantizer in_project -> nearest
+ * codebook row (VectorQuantize.encode_code, rvq.py:62-89: argmax of -(|z_e|^2 - 2 z_e.C^T + |C|^2), first maximum) ->
+ * residual -= out_project(z_e + (C[idx] - z_e)).  Needs the encode-side tensors of the checkpoint
+ * (rvq.quantizers.{i}.in_project.*, rvq.input_proj.*) to have been passed to frt2_load_tensor; FRT2_ERR_MISSING_TENSOR
+ * otherwise.  z: device fp32 (B, input_dim, T) with ELEMENT strides sB, sD, sT (the reference passes the channel-major
+ * (B, D, T) view, model.py:240; a time-major producer passes sD = 1).  codes: device int64 (nq, B, T) contiguous — the
+ * reference's return value (rvq.py:142).  One kernel, fp32 on the CUDA cores, distances evaluated in the reference's
+ * rounding order: an index differs from the reference's only where two codes tie within fp32 rounding. */
+int frt2_rvq_encode(frt2_handle* h, const float* z, int64_t sB, int64_t sD, int64_t sT, int B, int input_dim, int T,
+                    int nq, int64_t* codes, void* cuda_stream);
+
 /* ---- waveform resampler of the context loop ----
  * Replaces torchaudio.functional.resample(waveform, orig_freq, new_freq) with its defaults (sinc_interp_hann,
  * lowpass_filter_width 6, rolloff 0.99) as the reference calls it on every generated turn (24 kHz -> 16 kHz,

@@ -135,6 +135,61 @@ def rvq_decode_codes(sd, tokens, dt=np.float32):
     return emb, z
 
 
+def _wn_1x1(sd, prefix, dt=np.float32):
+    W = weight_norm(_f(sd, prefix + "parametrizations.weight.original0", dt),
+                    _f(sd, prefix + "parametrizations.weight.original1", dt))[:, :, 0]
+    return W.astype(dt), _f(sd, prefix + "bias", dt)
+
+
+def rvq_encode_codes(sd, z, nq: Optional[int] = None, dt=np.float32):
+    """ResidualVQ.encode_codes (reference rvq.py:128-143) over VectorQuantize.encode_code (rvq.py:62-89).
+
+    z (B, input_dim, T) channel-major as the reference receives it (model.py:240).  Returns
+    (codes (nq,B,T) int64, margin (nq,B,T)): margin = best - second best of -dist for every decision, i.e. how far the
+    chosen code is from a tie — a CUDA (or any other) implementation with a different summation order may legitimately
+    pick the runner-up only where margin is within fp32 rounding of the distance.
+      residual = input_proj(z)                                   rvq.py:129-130
+      z_e = in_project(residual)                                 rvq.py:65
+      dist = |z_e|^2 - (2 z_e) @ C^T + |C|^2 ; idx = argmax(-dist)   rvq.py:71-78 (first maximum)
+      z_q = z_e + (C[idx] - z_e) ; residual -= out_project(z_q)  rvq.py:82-86,138
+    """
+    z = np.asarray(z, dtype=dt)
+    B, D, T = z.shape
+    x = np.ascontiguousarray(z.transpose(0, 2, 1)).reshape(B * T, D)      # (B*T, D): "(b t) d", rvq.py:68
+    if f"{RVQ}input_proj.bias" in sd:
+        W, b = _wn_1x1(sd, RVQ + "input_proj.", dt)
+        x = x @ W.T + b
+    residual = x.astype(dt)
+    n_all = 0
+    while f"{RVQ}quantizers.{n_all}.codebook" in sd:
+        n_all += 1
+    nq = n_all if nq is None else nq
+    has_proj = f"{RVQ}quantizers.0.in_project.bias" in sd
+    codes = np.empty((nq, B, T), dtype=np.int64)
+    margin = np.empty((nq, B, T), dtype=dt)
+    for i in range(nq):
+        q = f"{RVQ}quantizers.{i}."
+        C = _f(sd, q + "codebook", dt)
+        z_e = residual
+        if has_proj:
+            Wi, bi = _wn_1x1(sd, q + "in_project.", dt)
+            z_e = (residual @ Wi.T + bi).astype(dt)
+        a = (z_e * z_e).sum(axis=1, keepdims=True, dtype=dt)
+        c2 = (C * C).sum(axis=1, keepdims=True, dtype=dt).T
+        dist = (a - ((dt(2) * z_e) @ C.T).astype(dt)).astype(dt) + c2
+        neg = -dist
+        idx = neg.argmax(axis=1)                                          # first maximum, like torch.max(1)[1] on CPU
+        part = np.partition(neg, -2, axis=1)
+        margin[i] = (part[:, -1] - part[:, -2]).reshape(B, T)
+        z_q = z_e + (C[idx] - z_e)
+        if has_proj:
+            Wo, bo = _wn_1x1(sd, q + "out_project.", dt)
+            z_q = (z_q @ Wo.T + bo).astype(dt)
+        residual = (residual - z_q).astype(dt)
+        codes[i] = idx.reshape(B, T)
+    return codes, margin
+
+
 # --------------------------------------------------------------------------------------------
 # UpConv 12.5 -> 50 Hz  (reference model.py:142-148)
 # --------------------------------------------------------------------------------------------
