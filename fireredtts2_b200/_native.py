@@ -12,7 +12,7 @@ FRT2_OK = 0
 ERR_BAD_ARG, ERR_BAD_DTYPE, ERR_INDEX_OOR, ERR_STATE_OVERFLOW, ERR_CUDA, ERR_MISSING_TENSOR, ERR_NOT_FINALIZED = \
     -1, -2, -3, -4, -5, -6, -7
 
-DBG_TAPS, DBG_GEMM_REF, DBG_ATTN_WARP, DBG_NO_GRAPH, DBG_NO_SKINNY, DBG_NO_LNFOLD = 1, 2, 4, 8, 16, 32
+DBG_TAPS, DBG_GEMM_REF, DBG_ATTN_WARP, DBG_NO_GRAPH, DBG_NO_SKINNY, DBG_NO_LNFOLD, DBG_NO_MEGA = 1, 2, 4, 8, 16, 32, 64
 ACT_NONE, ACT_GELU, ACT_POLAR = 0, 1, 2
 SLOT_ACTIVE, SLOT_LAST, SLOT_RESET = 1, 2, 4
 POOL_MAX_SLOTS = 256

@@ -214,6 +214,68 @@ int resample_rows(const float* x, int64_t x_pitch, int B, int64_t n_in, const in
                   int width, int orig, int nnew, float* y, int64_t y_pitch, cudaStream_t stream);
 // (mean, rstd) per row of an fp16 matrix (the statistics of a folded LayerNorm)
 int row_stats(const __half* x16, int64_t ld, int64_t rows, int C, float eps, float2* stats, cudaStream_t stream);
+// ---- persistent per-token step kernel (stream_mega.cu) ----
+// The ~90 launches of one streaming step (<= 16 rows) recorded as a list of ops and executed by ONE cooperative kernel
+// with a grid barrier between dependent ops.
+struct ShiftEntry {
+  __half* p;
+  int hist;
+  int rows;  // chunk rows written by this call
+  long long batch_pitch;
+};
+struct ShiftTable {
+  ShiftEntry e[16];
+  int n;
+};
+enum MegaKind : int { MK_RVQ = 0, MK_SKINNY = 1, MK_LN = 2, MK_ATTN = 3, MK_OLA = 4, MK_ROLL = 5 };
+struct MegaRvq {            // rvq_gather_sum over the staged int32 tokens (+ an optional 2-D zero fill of fp16 columns)
+  const int* tokens;
+  long long sB, sQ, sL;
+  int B, nq, L, K, D;
+  const float* tables;
+  __half* sum16;
+  unsigned int* err_word;
+  __half* zero_ptr;
+  long long zero_pitch;
+  int zero_cols, zero_rows;
+};
+struct MegaLn {             // layer_norm_rows_batched
+  const float* x;
+  long long ldx, rows;
+  int rows_per_batch, C;
+  const float *gamma, *beta;
+  float eps;
+  int silu;
+  __half* out16;
+  long long ld16, out_batch_pitch;
+};
+struct MegaRoll {           // update_tail + shift_history + advance_ctrl (the end-of-step state roll)
+  const float* frames;
+  long long frames_batch_pitch;
+  float* tail;
+  int T, n_fft, E, B;
+  ShiftTable tb;
+  int* ctrl;
+  int advance_frames;
+};
+struct MegaOp {
+  int kind, mtot, nblocks, pad;
+  union U {
+    GemmDesc g;
+    AttnDesc a;
+    MegaRvq r;
+    MegaLn l;
+    OlaDesc o;
+    MegaRoll ro;
+    U() {}
+  } u;
+  MegaOp() : kind(0), mtot(0), nblocks(0), pad(0) {}
+};
+int stream_mega_init();
+int stream_mega_grid();     // CTAs of the cooperative launch (one per SM)
+// ops: device array; bar: device counter (monotonic across launches), epoch0: its value when this launch starts
+int stream_mega_launch(const MegaOp* ops, int nops, unsigned int* bar, unsigned int epoch0, cudaStream_t stream,
+                       long long* trace = nullptr /* debug: 2*nops timestamps */);
 int tma_encode_fp16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box);
 int num_sms();

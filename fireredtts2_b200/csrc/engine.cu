@@ -27,6 +27,10 @@ constexpr int DBG_GEMM_REF = 2;   // route every GEMM through the SIMT check ker
 constexpr int DBG_ATTN_WARP = 4;  // route attention through the warp kernel (tests only)
 constexpr int DBG_NO_SKINNY = 16; // streaming: keep the tcgen05 GEMM even for <= 16 rows
 constexpr int DBG_NO_GRAPH = 8;   // streaming: launch kernel by kernel instead of replaying the captured CUDA graph
+constexpr int DBG_NO_MEGA = 64;   // streaming: CUDA-graph replay instead of the persistent step kernel (A/B, tests)
+#ifndef FRT2_MEGA_DEFAULT
+#define FRT2_MEGA_DEFAULT 0       // FRT2_MEGA=1 / =0 overrides at run time
+#endif
 constexpr int DBG_NO_LNFOLD = 32; // offline: separate LayerNorm kernels instead of LN folded across the GEMMs (A/B, tests)
 
 struct HostTensor {
@@ -113,16 +117,6 @@ __global__ void emit_pcm16_kernel(const float* __restrict__ stage, long long sta
   pcm[b * pcm_pitch + i] = static_cast<int16_t>(__float2int_rz(fminf(fmaxf(smp * 32767.0f, -32768.0f), 32767.0f)));
 }
 
-struct ShiftEntry {
-  __half* p;
-  int hist;
-  int rows;  // chunk rows written by this call
-  long long batch_pitch;
-};
-struct ShiftTable {
-  ShiftEntry e[16];
-  int n;
-};
 // move the last `hist` rows of [hist | chunk] to the head of each streaming conv buffer (the new history);
 // items whose control block says idle keep their history
 __global__ void shift_history_kernel(ShiftTable t, int E, int B, const int* __restrict__ ctrl) {
@@ -380,9 +374,24 @@ struct Handle {
     return FRT2_OK;
   }
 
+  // recording mode (persistent step kernel): the launch helpers append ops here instead of launching
+  std::vector<MegaOp>* rec = nullptr;
+  bool rec_fail = false;    // an op the step kernel cannot run (e.g. a tcgen05 GEMM): fall back to the CUDA graph
+
   int finalize();
   int ensure_ws(size_t bytes);
   int run_gemm(const GemmDesc& g, cudaStream_t st) {
+    if (rec != nullptr) {
+      const int mtot = g.batches * g.rows_out;
+      if (!gemm_skinny_applicable(g) || (g.ln_gamma != nullptr && (g.ntaps != 1 || g.Kc > 2048))) {
+        rec_fail = true;
+        return FRT2_OK;
+      }
+      MegaOp op;
+      op.kind = MK_SKINNY; op.mtot = mtot; op.nblocks = (g.N + 7) / 8; op.u.g = g;
+      rec->push_back(op);
+      return FRT2_OK;
+    }
     const double flops = 2.0 * g.batches * g.rows_out * static_cast<double>(g.N) * g.ntaps * g.Kc;
     const double bytes = 2.0 * (static_cast<double>(g.batches) * g.rows_a * g.Kc + static_cast<double>(g.N) * g.ntaps * g.Kc) +
                          static_cast<double>(g.batches) * g.rows_out * g.N *
@@ -394,6 +403,17 @@ struct Handle {
     return rc;
   }
   int run_attn(const AttnDesc& a, cudaStream_t st) {
+    if (rec != nullptr) {
+      const long long blocks = static_cast<long long>(a.B) * a.H * (a.Tq / 8);
+      if (a.hd != 64 || a.Tq % 8 != 0 || blocks > 1024 || a.ctrl == nullptr) {
+        rec_fail = true;
+        return FRT2_OK;
+      }
+      MegaOp op;
+      op.kind = MK_ATTN; op.nblocks = static_cast<int>(blocks); op.u.a = a;
+      rec->push_back(op);
+      return FRT2_OK;
+    }
     // visible (query, key) pairs: block-causal sum_q ((q_pos0+q)|7)+1, else Tq*Tk
     double pairs = static_cast<double>(a.Tq) * a.Tk;
     if (a.block_causal) {
@@ -410,6 +430,16 @@ struct Handle {
   }
   int run_ln(const float* x, int64_t rows, int rows_per_batch, const float* g, const float* b, float eps, int silu_,
              __half* out, int64_t pitch, cudaStream_t st) {
+    if (rec != nullptr) {
+      MegaOp op;
+      op.kind = MK_LN;
+      MegaLn& l = op.u.l;
+      l.x = x; l.ldx = E; l.rows = rows; l.rows_per_batch = rows_per_batch; l.C = E; l.gamma = g; l.beta = b; l.eps = eps;
+      l.silu = silu_; l.out16 = out; l.ld16 = E; l.out_batch_pitch = pitch;
+      if (E % 4 != 0 || pitch % 4 != 0 || rows >= 4096) rec_fail = true;
+      rec->push_back(op);
+      return FRT2_OK;
+    }
     const int id = prof_begin(FRT2_PROF_LAYER_NORM, 0.0, static_cast<double>(rows) * E * 6.0, st);
     const int rc = layer_norm_rows_batched(x, E, rows, rows_per_batch, E, g, b, eps, silu_, out, E, pitch, st);
     prof_end(id, st);
@@ -443,6 +473,11 @@ struct Stream {
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
   struct GraphRec { cudaGraphExec_t exec; const uint8_t* ws; long long kernels; };
   std::map<std::pair<int, int>, GraphRec> graphs;  // (Lc, nq) -> captured step
+  // persistent step kernel: (Lc, nq) -> recorded op list in HBM
+  struct MegaRec { MegaOp* ops; int nops; const uint8_t* ws; long long kernels; bool unsupported; };
+  std::map<std::pair<int, int>, MegaRec> megas;
+  unsigned int* mega_bar = nullptr;   // grid-barrier counter (monotonic; the host tracks its value)
+  unsigned int mega_epoch = 0;
 
   int64_t conv_pitch(int i) const { return static_cast<int64_t>(conv_hist[i] + conv_rpt[i] * chunk_cap) * h->E; }
   // one token of slack: an idle pool slot still "appends" (and later overwrites) one chunk at its current position
@@ -461,12 +496,16 @@ struct Stream {
     if (ctrl) cudaFree(ctrl);
     if (tok_stage) cudaFree(tok_stage);
     if (audio_stage) cudaFree(audio_stage);
+    if (mega_bar) cudaFree(mega_bar);
     drop_graphs();
     if (cap_stream) cudaStreamDestroy(cap_stream);
   }
   void drop_graphs() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
     graphs.clear();
+    for (auto& m : megas)
+      if (m.second.ops) cudaFree(m.second.ops);
+    megas.clear();
   }
   int ensure_chunk_cap(int Lc, cudaStream_t st);
   int reset();
@@ -564,6 +603,7 @@ int Handle::finalize() {
   FRT2_TRY(gemm_tc_init());
   FRT2_TRY(gemm_skinny_init());
   FRT2_TRY(attention_tc_init());
+  FRT2_TRY(stream_mega_init());
   const HostTensor* t = nullptr;
   const std::string RVQ = "rvq.", UP = "upsample.", AD = "acoustic_decoder.", BB = "acoustic_decoder.backbone.";
 
@@ -954,10 +994,21 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   // ---- K1: RVQ gather-and-sum (+ output projection) ----
   {
     // algorithmic bytes per token: nq*(idx + D*4) in, D*2 out
-    const int id = prof_begin(FRT2_PROF_RVQ, 0.0, static_cast<double>(R) * (nq_in * (idx_bytes + rd * 4.0) + rd * 2.0), st);
-    FRT2_TRY(rvq_gather_sum(tokens, idx_bytes, sB, sQ, sL, B, nq_in, L, tables, K, rd,
-                            (debug & DBG_TAPS) ? emb32 : nullptr, emb16, nullptr, err_word, st));
-    prof_end(id, st);
+    if (rec != nullptr) {
+      MegaOp op;
+      op.kind = MK_RVQ;
+      MegaRvq& r = op.u.r;
+      r.tokens = static_cast<const int*>(tokens); r.sB = sB; r.sQ = sQ; r.sL = sL; r.B = B; r.nq = nq_in; r.L = L; r.K = K;
+      r.D = rd; r.tables = tables; r.sum16 = emb16; r.err_word = err_word;
+      r.zero_ptr = nullptr; r.zero_pitch = 0; r.zero_cols = 0; r.zero_rows = 0;
+      if (idx_bytes != 4 || nq_in > 64 || rd % 4 != 0) rec_fail = true;
+      rec->push_back(op);
+    } else {
+      const int id = prof_begin(FRT2_PROF_RVQ, 0.0, static_cast<double>(R) * (nq_in * (idx_bytes + rd * 4.0) + rd * 2.0), st);
+      FRT2_TRY(rvq_gather_sum(tokens, idx_bytes, sB, sQ, sL, B, nq_in, L, tables, K, rd,
+                              (debug & DBG_TAPS) ? emb32 : nullptr, emb16, nullptr, err_word, st));
+      prof_end(id, st);
+    }
   }
   FRT2_TRY(tap_f32("emb", emb32, R * rd, st));
   const __half* z = emb16;
@@ -1063,8 +1114,14 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   FRT2_TRY(tap_f16("final", n16, E, M, E, st));
   // ---- K5: head GEMM with polar epilogue -> windowed inverse DFT GEMM -> overlap-add ----
   if (spec_ld > 2 * n_bins) {
-    FRT2_CUDA_OK(cudaMemset2DAsync(spec16 + 2 * n_bins, static_cast<size_t>(spec_ld) * 2, 0,
-                                   static_cast<size_t>(spec_ld - 2 * n_bins) * 2, M, st));
+    if (rec != nullptr) {   // the zero fill of the padding columns rides on the step's first op (nothing touches spec16 before)
+      MegaRvq& r = (*rec)[0].u.r;
+      r.zero_ptr = spec16 + 2 * n_bins; r.zero_pitch = spec_ld; r.zero_cols = spec_ld - 2 * n_bins;
+      r.zero_rows = static_cast<int>(M);
+    } else {
+      FRT2_CUDA_OK(cudaMemset2DAsync(spec16 + 2 * n_bins, static_cast<size_t>(spec_ld) * 2, 0,
+                                     static_cast<size_t>(spec_ld - 2 * n_bins) * 2, M, st));
+    }
   }
   FRT2_TRY(flat_gemm(n16, M, E, w_head, 2 * n_bins, b_head, ACT_POLAR, nullptr, nullptr, spec16, spec_ld, 1.0f,
                      fuse_ln ? &lnf : nullptr, fold ? &f_head : nullptr));
@@ -1083,6 +1140,22 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     if (graph_mode) od.ctrl = s->ctrl;
   } else {
     od.tail = nullptr; od.first = 1; od.last = 1;
+  }
+  if (rec != nullptr) {
+    // the whole tail of the step as two ops: overlap-add, then tail update + history shift + position advance
+    if (!streaming || od.ctrl == nullptr || n_fft != 4 * hop || E % 8 != 0 || n_fft % 4 != 0) rec_fail = true;
+    MegaOp op;
+    op.kind = MK_OLA; op.u.o = od;
+    rec->push_back(op);
+    MegaOp rl;
+    rl.kind = MK_ROLL;
+    MegaRoll& ro = rl.u.ro;
+    ro.frames = frames32; ro.frames_batch_pitch = od.frames_batch_pitch; ro.tail = s->tail; ro.T = T; ro.n_fft = n_fft;
+    ro.E = E; ro.B = B; ro.ctrl = s->ctrl; ro.advance_frames = T;
+    ro.tb.n = 11;
+    for (int i = 0; i < 11; ++i) ro.tb.e[i] = {s->conv[i], s->conv_hist[i], s->conv_rpt[i] * L, s->conv_pitch(i)};
+    rec->push_back(rl);
+    return FRT2_OK;
   }
   {
     const int id = prof_begin(FRT2_PROF_OLA, 0.0, static_cast<double>(M) * (n_fft + hop) * 4.0, st);
@@ -1382,6 +1455,64 @@ static int run_ctrl_step(Handle& h, Stream& s, int nq, int Lc, cudaStream_t st, 
     return h.pipeline(s.tok_stage, 4, static_cast<int64_t>(nq) * Lc, Lc, 1, s.B, nq, Lc, nullptr, s.audio_stage,
                       s.audio_stage_pitch, &s, 0, st, true);
   auto key = std::make_pair(Lc, nq);
+  // ---- persistent step kernel (<= 16 rows): the recorded op list run by ONE cooperative launch ----
+  static const bool mega_env = [] {
+    const char* e = getenv("FRT2_MEGA");
+    return e == nullptr ? FRT2_MEGA_DEFAULT != 0 : (e[0] != '0');
+  }();
+  if (mega_env && s.B * 8 * Lc <= 16 && !(h.debug & DBG_NO_MEGA)) {
+    auto mi = s.megas.find(key);
+    if (mi != s.megas.end() && mi->second.ws != h.ws) {   // workspace moved since the recording
+      if (mi->second.ops) cudaFree(mi->second.ops);
+      s.megas.erase(mi);
+      mi = s.megas.end();
+    }
+    if (mi == s.megas.end()) {
+      std::vector<MegaOp> ops;
+      const long long before = h.launches;
+      h.rec = &ops;
+      h.rec_fail = false;
+      const int rc = h.pipeline(s.tok_stage, 4, static_cast<int64_t>(nq) * Lc, Lc, 1, s.B, nq, Lc, nullptr, s.audio_stage,
+                                s.audio_stage_pitch, &s, 0, st, true);
+      h.rec = nullptr;
+      h.launches = before;
+      FRT2_TRY(rc);
+      Stream::MegaRec mr{nullptr, static_cast<int>(ops.size()), h.ws, static_cast<long long>(ops.size()),
+                         h.rec_fail || ops.empty() || ops[0].kind != MK_RVQ};
+      if (!mr.unsupported) {
+        FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&mr.ops), ops.size() * sizeof(MegaOp)));
+        FRT2_CUDA_OK(cudaMemcpy(mr.ops, ops.data(), ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
+        if (s.mega_bar == nullptr) {
+          FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&s.mega_bar), 4));
+          FRT2_CUDA_OK(cudaMemset(s.mega_bar, 0, 4));
+          s.mega_epoch = 0;
+        }
+      }
+      mi = s.megas.emplace(key, mr).first;
+    }
+    if (!mi->second.unsupported) {
+      static const bool trace_env = (getenv("FRT2_MEGA_TRACE") != nullptr);   // debug: per-op timeline of CTA 0 on stderr
+      long long* trace = nullptr;
+      static int trace_calls = 0;
+      if (trace_env && ++trace_calls == 12)
+        FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&trace), static_cast<size_t>(mi->second.nops) * 16));
+      FRT2_TRY(stream_mega_launch(mi->second.ops, mi->second.nops, s.mega_bar, s.mega_epoch, st, trace));
+      if (trace != nullptr) {
+        std::vector<long long> tr(static_cast<size_t>(mi->second.nops) * 2);
+        std::vector<MegaOp> hops(mi->second.nops);
+        FRT2_CUDA_OK(cudaStreamSynchronize(st));
+        FRT2_CUDA_OK(cudaMemcpy(tr.data(), trace, tr.size() * 8, cudaMemcpyDeviceToHost));
+        FRT2_CUDA_OK(cudaMemcpy(hops.data(), mi->second.ops, hops.size() * sizeof(MegaOp), cudaMemcpyDeviceToHost));
+        cudaFree(trace);
+        for (int i = 0; i < mi->second.nops; ++i)
+          fprintf(stderr, "megatrace op %3d kind %d nblocks %4d: body %6lld ns, barrier+wait %6lld ns\n", i, hops[i].kind,
+                  hops[i].nblocks, tr[2 * i + 1] - tr[2 * i], i + 1 < mi->second.nops ? tr[2 * i + 2] - tr[2 * i + 1] : 0LL);
+      }
+      s.mega_epoch += static_cast<unsigned int>(mi->second.nops - 1) * static_cast<unsigned int>(stream_mega_grid());
+      h.launches += 1;
+      return FRT2_OK;
+    }
+  }
   auto it = s.graphs.find(key);
   if (it != s.graphs.end() && it->second.ws != h.ws) {  // workspace moved since the capture
     cudaGraphExecDestroy(it->second.exec);
