@@ -30,10 +30,10 @@ namespace frt2 {
 // =====================================================================================================
 namespace {
 
-template <int HD, int NSPLIT>
+template <int HD, int NSPLIT, int KS = 1>
 __global__ void __launch_bounds__(NSPLIT == 1 ? 128 : NSPLIT * 32) attention_warp_kernel(AttnDesc a) {
   pdl_trigger();   // a following PDL-launched kernel (streaming skinny GEMM) may start its weight prefetch
-  attention_warp_body<HD, NSPLIT, false>(a, blockIdx.x);
+  attention_warp_body<HD, NSPLIT, false, KS>(a, blockIdx.x);
 }
 
 }  // namespace
@@ -47,7 +47,10 @@ int attention_warp(const AttnDesc& a, cudaStream_t stream) {
   // few query blocks (the streaming step): 16 warps per block split the KV state; otherwise one warp per block
   const bool split = warps <= 1024 && a.hd == 64;
   const unsigned grid = static_cast<unsigned>((warps + 3) / 4);
-  if (split) {
+  if (split && a.part != nullptr && a.part_count != nullptr && a.Tq == 8) {
+    // a long K/V state behind 8 queries: ATTN_KSPLIT CTAs per (item, head), merged by the last one to finish
+    attention_warp_kernel<64, NS, ATTN_KSPLIT><<<static_cast<unsigned>(warps * ATTN_KSPLIT), NS * 32, 0, stream>>>(a);
+  } else if (split) {
     attention_warp_kernel<64, NS><<<static_cast<unsigned>(warps), NS * 32, 0, stream>>>(a);
   } else {
     switch (a.hd) {

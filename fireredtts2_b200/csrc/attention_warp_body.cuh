@@ -12,8 +12,15 @@ namespace {
 // a long KV state): the NSPLIT warps of a CTA share ONE query block, take interleaved 32-key chunks and merge their
 // partial (max, sum, accumulator) through shared memory — split-KV without a second kernel.
 // COHERENT: the K rows may have been written earlier in the SAME kernel (persistent step kernel) — no ld.global.nc.
-template <int HD, int NSPLIT, bool COHERENT>
+// KS > 1 (with NSPLIT > 1): KS CTAs share one (item, head): CTA k of the group takes the 32-key chunks
+// (k*NSPLIT + warp) + i*KS*NSPLIT, so up to KS*NSPLIT chunks run in one round and the step's attention time stays flat
+// as the K/V state grows.  Only ceil(chunks / NSPLIT) CTAs (at most KS) have work; the others exit at once.  With more
+// than one working CTA each leaves its merged (max, sum, accumulator) in a.part, and the LAST one to arrive (atomic
+// counter per (item, head), reset by that CTA) merges them in CTA order — deterministic — and writes the rows.
+template <int HD, int NSPLIT, bool COHERENT, int KS = 1>
 __device__ __forceinline__ void attention_warp_body(AttnDesc a, long long vblock) {
+  const int kcta = (KS > 1) ? static_cast<int>(vblock % KS) : 0;
+  if (KS > 1) vblock /= KS;
   constexpr int DPL = HD / 32;  // output dims per lane
   constexpr int QW = (NSPLIT == 1) ? 4 : 1;   // query blocks per CTA
   __shared__ float sq[QW][8][HD];
@@ -64,12 +71,28 @@ __device__ __forceinline__ void attention_warp_body(AttnDesc a, long long vblock
 #pragma unroll
     for (int i = 0; i < DPL; ++i) acc[r][i] = 0.f;
   }
-  for (int j0 = split * 32; j0 <= kend; j0 += NSPLIT * 32) {
+  int nact = 1;   // CTAs of this (item, head) that have work
+  if (KS > 1) {
+    nact = min(KS, (kend / 32 + NSPLIT) / NSPLIT);
+    if (kcta >= nact) return;   // uniform per CTA
+  }
+  for (int j0 = (kcta * NSPLIT + split) * 32; j0 <= kend; j0 += KS * NSPLIT * 32) {
     const int j = j0 + lane;
     const bool valid = j <= kend;
     float s[8];
 #pragma unroll
     for (int r = 0; r < 8; ++r) s[r] = 0.f;
+    const int nk = min(32, kend - j0 + 1);
+    // the chunk's first 16 V rows are requested together with its K rows (they do not depend on the scores): the
+    // chunk costs one memory round trip instead of one for K plus one per batch of V rows
+    __half2 vpre[16];
+    if (DPL == 2) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int jj = min(u, nk - 1);
+        vpre[u] = *reinterpret_cast<const __half2*>(vp + static_cast<long long>(j0 + jj) * a.kv_row_pitch + lane * DPL);
+      }
+    }
     {
       const uint4* krow = reinterpret_cast<const uint4*>(kp + static_cast<long long>(valid ? j : kend) * a.kv_row_pitch);
 #pragma unroll
@@ -110,23 +133,35 @@ __device__ __forceinline__ void attention_warp_body(AttnDesc a, long long vblock
 #pragma unroll
       for (int i = 0; i < DPL; ++i) acc[r][i] *= alpha;
     }
-    const int nk = min(32, kend - j0 + 1);
     if (DPL == 2) {
-      // eight V rows in flight per round trip (a load-use chain per key would cost one L2 latency per key)
-      for (int jb = 0; jb < nk; jb += 8) {
-        __half2 vh[8];
+      __half2 vnext[16];
+      if (nk > 16) {   // second half of the chunk: requested now, consumed after the first half's FMAs
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int jj = min(jb + u, nk - 1);
-          vh[u] = *reinterpret_cast<const __half2*>(vp + static_cast<long long>(j0 + jj) * a.kv_row_pitch + lane * DPL);
+        for (int u = 0; u < 16; ++u) {
+          const int jj = min(16 + u, nk - 1);
+          vnext[u] = *reinterpret_cast<const __half2*>(vp + static_cast<long long>(j0 + jj) * a.kv_row_pitch + lane * DPL);
         }
+      }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (jb + u < nk) {
-            const float2 f = __half22float2(vh[u]);
+      for (int u = 0; u < 16; ++u) {
+        if (u < nk) {
+          const float2 f = __half22float2(vpre[u]);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            const float pj = __shfl_sync(0xffffffffu, p[r], u);
+            acc[r][0] = fmaf(pj, f.x, acc[r][0]);
+            acc[r][DPL - 1] = fmaf(pj, f.y, acc[r][DPL - 1]);
+          }
+        }
+      }
+      if (nk > 16) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          if (16 + u < nk) {
+            const float2 f = __half22float2(vnext[u]);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-              const float pj = __shfl_sync(0xffffffffu, p[r], jb + u);
+              const float pj = __shfl_sync(0xffffffffu, p[r], 16 + u);
               acc[r][0] = fmaf(pj, f.x, acc[r][0]);
               acc[r][DPL - 1] = fmaf(pj, f.y, acc[r][DPL - 1]);
             }
@@ -168,11 +203,11 @@ __device__ __forceinline__ void attention_warp_body(AttnDesc a, long long vblock
       }
     }
     __syncthreads();
+    __shared__ int s_last;
+    float M = -CUDART_INF_F, L = 0.f, o[DPL];
     if (warp < 8) {
       const int r = warp;
-      float M = -CUDART_INF_F;
       for (int w = 0; w < NSPLIT; ++w) M = fmaxf(M, s_part[w][r][HD]);
-      float L = 0.f, o[DPL];
 #pragma unroll
       for (int i = 0; i < DPL; ++i) o[i] = 0.f;
       for (int w = 0; w < NSPLIT; ++w) {
@@ -181,9 +216,52 @@ __device__ __forceinline__ void attention_warp_body(AttnDesc a, long long vblock
 #pragma unroll
         for (int i = 0; i < DPL; ++i) o[i] += s_part[w][r][lane * DPL + i] * sc;
       }
-      const float inv = 1.0f / L;
+      if (KS == 1 || nact == 1) {
+        const float inv = 1.0f / L;
 #pragma unroll
-      for (int i = 0; i < DPL; ++i) op[r * a.o_row_pitch + i] = to_half_sat(o[i] * inv);
+        for (int i = 0; i < DPL; ++i) op[r * a.o_row_pitch + i] = to_half_sat(o[i] * inv);
+      }
+    }
+    if (KS > 1 && nact > 1) {
+      // ---- cross-CTA merge: this CTA's state -> a.part[(item, head)][kcta][row][HD + 2]
+      const long long bh = static_cast<long long>(b) * a.H + h;
+      float* mine = a.part + ((bh * KS + kcta) * 8) * (HD + 2);
+      if (warp < 8) {
+        const int r = warp;
+#pragma unroll
+        for (int i = 0; i < DPL; ++i) mine[r * (HD + 2) + lane * DPL + i] = o[i];
+        if (lane == 0) {
+          mine[r * (HD + 2) + HD] = M;
+          mine[r * (HD + 2) + HD + 1] = L;
+        }
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) s_last = (atomicAdd(a.part_count + bh, 1) == nact - 1) ? 1 : 0;
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        if (warp < 8) {
+          const int r = warp;
+          const float* base = a.part + (bh * KS * 8 + r) * (HD + 2);
+          float M2 = -CUDART_INF_F;
+          for (int k = 0; k < nact; ++k) M2 = fmaxf(M2, __ldcg(base + static_cast<long long>(k) * 8 * (HD + 2) + HD));
+          float L2 = 0.f, o2[DPL];
+#pragma unroll
+          for (int i = 0; i < DPL; ++i) o2[i] = 0.f;
+          for (int k = 0; k < nact; ++k) {
+            const float* pk = base + static_cast<long long>(k) * 8 * (HD + 2);
+            const float sc = exp2f(__ldcg(pk + HD) - M2);
+            L2 += __ldcg(pk + HD + 1) * sc;
+#pragma unroll
+            for (int i = 0; i < DPL; ++i) o2[i] += __ldcg(pk + lane * DPL + i) * sc;
+          }
+          const float inv = 1.0f / L2;
+#pragma unroll
+          for (int i = 0; i < DPL; ++i) op[r * a.o_row_pitch + i] = to_half_sat(o2[i] * inv);
+        }
+        if (threadIdx.x == 0) a.part_count[bh] = 0;   // ready for the next step
+      }
     }
   }
 }

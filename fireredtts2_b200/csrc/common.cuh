@@ -156,7 +156,12 @@ struct AttnDesc {
   float scale;
   const int* ctrl;   // optional per-item control blocks (attention_warp): item b has q_pos0 = ctrl[b*CTRL_INTS + CTRL_POS],
                      // Tk = q_pos0 + Tq at run time; idle items (CTRL_ACTIVE == 0) are skipped
+  // optional (attention_warp, split form): workspace for splitting one (item, head) over ATTN_KSPLIT CTAs —
+  // part: (B*H, ATTN_KSPLIT, 8, hd + 2) floats, part_count: (B*H) ints, zero-initialised (each use leaves them zero)
+  float* part;
+  int* part_count;
 };
+constexpr int ATTN_KSPLIT = 8;
 int attention_warp(const AttnDesc& a, cudaStream_t stream);  // CUDA-core, one warp per 8-query block
 int attention_tc(const AttnDesc& a, cudaStream_t stream);    // tcgen05 flash attention (hd == 64)
 int attention_tc_init();

@@ -410,7 +410,8 @@ struct Handle {
         return FRT2_OK;
       }
       MegaOp op;
-      op.kind = MK_ATTN; op.nblocks = static_cast<int>(blocks); op.u.a = a;
+      op.kind = MK_ATTN; op.u.a = a;
+      op.nblocks = static_cast<int>(blocks) * ((a.part != nullptr && a.part_count != nullptr && a.Tq == 8) ? ATTN_KSPLIT : 1);
       rec->push_back(op);
       return FRT2_OK;
     }
@@ -463,6 +464,8 @@ struct Stream {
   int conv_rpt[11] = {4, 8, 8, 8, 8, 8, 8, 8, 8, 8, 8};  // rows per token
   std::vector<__half*> kv;  // per layer (B, Tmax, 2E)
   float* tail = nullptr;    // (B, 3, n_fft)
+  float* attn_part = nullptr;   // (B*H, ATTN_KSPLIT, 8, hd + 2): cross-CTA split of the step's attention (hd == 64 only)
+  int* attn_count = nullptr;    // (B*H) arrival counters, zero between launches
   int* ctrl = nullptr;      // device (B, CTRL_INTS) per-item control blocks: read by the kernels of the captured step
   bool pooled = false;      // slot pool (frt2_pool_*): items are independent streams at their own positions
   std::vector<int> slot_tokens;  // pool: host mirror of the tokens each slot has consumed
@@ -494,6 +497,8 @@ struct Stream {
     for (auto p : kv) cudaFree(p);
     if (tail) cudaFree(tail);
     if (ctrl) cudaFree(ctrl);
+    if (attn_part) cudaFree(attn_part);
+    if (attn_count) cudaFree(attn_count);
     if (tok_stage) cudaFree(tok_stage);
     if (audio_stage) cudaFree(audio_stage);
     if (mega_bar) cudaFree(mega_bar);
@@ -1094,6 +1099,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
       a.k = s->kv[i]; a.v = s->kv[i] + E; a.kv_row_pitch = 2 * E; a.kv_batch_pitch = s->kv_pitch();
       a.Tk = pos + T; a.q_pos0 = pos; a.block_causal = 0;
       if (graph_mode) a.ctrl = s->ctrl;
+      a.part = s->attn_part; a.part_count = s->attn_count;   // long K/V state: several CTAs per (item, head)
     }
     FRT2_TRY(run_attn(a, st));
     FRT2_TRY(flat_gemm(o16, M, E, w.w_o, E, w.b_o, ACT_NONE, x32, x32, nullptr, 0, 1.0f, nullptr, nullptr, fold));
@@ -1429,6 +1435,15 @@ int frt2_stream_create(frt2_handle* hh, int B, int max_tokens, frt2_stream** out
       cudaStreamCreateWithFlags(&s.cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("frt2_stream_create: out of memory");
     return fail(FRT2_ERR_CUDA);
+  }
+  if (h.E / h.H == 64 && static_cast<long long>(B) * h.H <= 1024) {
+    const size_t pf = static_cast<size_t>(B) * h.H * ATTN_KSPLIT * 8 * (64 + 2) * sizeof(float);
+    if (cudaMalloc(reinterpret_cast<void**>(&s.attn_part), pf) != cudaSuccess ||
+        cudaMalloc(reinterpret_cast<void**>(&s.attn_count), static_cast<size_t>(B) * h.H * sizeof(int)) != cudaSuccess ||
+        cudaMemset(s.attn_count, 0, static_cast<size_t>(B) * h.H * sizeof(int)) != cudaSuccess) {
+      set_error("frt2_stream_create: out of memory for the attention split workspace");
+      return fail(FRT2_ERR_CUDA);
+    }
   }
   st = s.ensure_chunk_cap(1, nullptr);
   if (st != FRT2_OK) return fail(st);

@@ -282,6 +282,34 @@ def test_graph_replay_equals_kernel_by_kernel():
     _gate("graph-stream-24-vs-offline", ref, outs[("product", 0)])
 
 
+def test_streaming_long_context_splits_attention_over_ctas():
+    """Past 512 frames of K/V state the step's attention runs on several CTAs per (item, head) whose partial softmax
+    states are merged by the last CTA to finish: 150 tokens (1200 frames -> 3 working CTAs) streamed one at a time must
+    still match the offline decode of the same tokens (the reference: streaming == offline, model.py:326-376), and
+    the graph replay must equal the eager launch sequence bit for bit (deterministic merge order)."""
+    case = [c for c in cases("stream") if c["name"] == "tiny_stream_1"][0]
+    cfg, sd, g = load_case(case)
+    assert cfg.head_dim == 64
+    n = 150
+    tok = torch.from_numpy(np.random.default_rng(3).integers(0, cfg.codebook_size, size=(2, cfg.num_quantizers, n))).cuda()
+    outs = {}
+    for mode in ("product", "no_graph"):
+        codec = build_codec(cfg, sd, stream_max_tokens=n + 2)
+        codec.set_debug(MODES[mode])
+        cache, chunks = {}, []
+        for i in range(n):
+            a, cache = codec.decode_one_token(tok[:, :, i:i + 1], cache, i == n - 1)
+            chunks.append(to_np(a))
+        outs[mode] = np.concatenate(chunks, axis=1)
+    assert np.array_equal(outs["product"], outs["no_graph"])
+    codec = build_codec(cfg, sd)
+    offline = to_np(codec.decode(tok))
+    _, snr = report("stream-150-tokens vs offline decode", offline, outs["product"])
+    assert snr > 50.0
+    ref = O.decode(sd, tok.cpu().numpy(), cfg.num_heads, cfg.hop_length)
+    _gate("stream-150-tokens vs oracle", ref, outs["product"])
+
+
 def test_pcm16_output_is_the_reference_wire_format():
     """decode(pcm16=True) == (decode() * 32767).astype(int16), the reference's wire conversion
     (enhanced_fireredtts2.py:603,655), bit for bit."""
