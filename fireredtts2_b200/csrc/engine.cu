@@ -405,13 +405,13 @@ struct Handle {
   int run_attn(const AttnDesc& a, cudaStream_t st) {
     if (rec != nullptr) {
       const long long blocks = static_cast<long long>(a.B) * a.H * (a.Tq / 8);
-      if (a.hd != 64 || a.Tq % 8 != 0 || blocks > 1024 || a.ctrl == nullptr) {
+      if (a.hd != 64 || a.Tq != 8 || blocks > 1024 || a.ctrl == nullptr || a.part == nullptr || a.part_count == nullptr) {
         rec_fail = true;
         return FRT2_OK;
       }
       MegaOp op;
       op.kind = MK_ATTN; op.u.a = a;
-      op.nblocks = static_cast<int>(blocks) * ((a.part != nullptr && a.part_count != nullptr && a.Tq == 8) ? ATTN_KSPLIT : 1);
+      op.nblocks = static_cast<int>(blocks) * ATTN_KSPLIT;
       rec->push_back(op);
       return FRT2_OK;
     }

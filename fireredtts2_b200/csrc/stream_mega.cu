@@ -195,8 +195,7 @@ stream_step_kernel(const MegaOp* __restrict__ ops, int nops, unsigned int* bar, 
       }
       case MK_ATTN:
         for (int vb = blockIdx.x; vb < op.nblocks; vb += gridDim.x) {
-          if (op.u.a.part != nullptr && op.u.a.Tq == 8) attention_warp_body<64, 16, true, ATTN_KSPLIT>(op.u.a, vb);
-          else attention_warp_body<64, 16, true>(op.u.a, vb);
+          attention_warp_body<64, 16, true, ATTN_KSPLIT>(op.u.a, vb);   // recorded only with the split workspace, Tq == 8
           __syncthreads();
         }
         break;
