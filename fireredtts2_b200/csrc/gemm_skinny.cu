@@ -16,10 +16,10 @@ namespace frt2 {
 
 namespace {
 
-template <int MR>
+template <int MR, int NT>
 __global__ void __launch_bounds__(SK_WARPS * 32) gemm_skinny_kernel(GemmDesc g, int mtot) {
   extern __shared__ __align__(16) uint8_t sk_smem_dyn[];
-  gemm_skinny_body<MR, true>(g, mtot, blockIdx.x, threadIdx.x, sk_smem_dyn, [] { __syncthreads(); });
+  gemm_skinny_body<MR, true, NT>(g, mtot, blockIdx.x, threadIdx.x, sk_smem_dyn, [] { __syncthreads(); });
 }
 
 // ---- round-1 FMA-loop kernel (one output column per warp, fp32 FMAs), kept for A/B measurements ----
@@ -215,10 +215,14 @@ int gemm_skinny_init() {
                                     8 * SK_KCHUNK * 2 + 8 * SK_COLS * 4));
   FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_skinny_fma_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     16 * SK_KCHUNK * 2 + 16 * SK_COLS * 4));
-  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_skinny_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(sk_smem_bytes(8, SK_KCHUNK, SK_KCHUNK))));
-  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_skinny_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(sk_smem_bytes(16, SK_KCHUNK, SK_KCHUNK))));
+  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_skinny_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sk_smem_bytes(8, SK_KCHUNK, SK_KCHUNK, 1))));
+  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_skinny_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sk_smem_bytes(16, SK_KCHUNK, SK_KCHUNK, 1))));
+  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_skinny_kernel<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sk_smem_bytes(8, SK_KCHUNK, SK_KCHUNK, 2))));
+  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_skinny_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sk_smem_bytes(16, SK_KCHUNK, SK_KCHUNK, 2))));
   return FRT2_OK;
 }
 
@@ -263,12 +267,23 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t stream) {
     FRT2_CUDA_OK(cudaGetLastError());
     return FRT2_OK;
   }
+  // wide layers (QKV, fc1): 16 columns per CTA — one wave of CTAs, activation rows staged / normalised half as often
+  static const bool no_nt2 = (getenv("FRT2_SKINNY_NT1") != nullptr);   // A/B switch for measurements
+  static const int nt2_min_n = [] {
+    const char* e = getenv("FRT2_SKINNY_NT2_MIN_N");
+    return e != nullptr ? atoi(e) : 2048;
+  }();
+  const int nt = (g.N >= nt2_min_n && !no_nt2) ? 2 : 1;
+  cfg.gridDim = dim3((g.N + SK_COLS * nt - 1) / (SK_COLS * nt));
+  const int ln_c = g.ln_gamma != nullptr ? g.Kc : 0;
   if (mtot <= 8) {
-    cfg.dynamicSmemBytes = sk_smem_bytes(8, kchunk, g.ln_gamma != nullptr ? g.Kc : 0);
-    FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<8>, g, mtot));
+    cfg.dynamicSmemBytes = sk_smem_bytes(8, kchunk, ln_c, nt);
+    if (nt == 2) FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<8, 2>, g, mtot));
+    else FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<8, 1>, g, mtot));
   } else {
-    cfg.dynamicSmemBytes = sk_smem_bytes(16, kchunk, g.ln_gamma != nullptr ? g.Kc : 0);
-    FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<16>, g, mtot));
+    cfg.dynamicSmemBytes = sk_smem_bytes(16, kchunk, ln_c, nt);
+    if (nt == 2) FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<16, 2>, g, mtot));
+    else FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<16, 1>, g, mtot));
   }
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;

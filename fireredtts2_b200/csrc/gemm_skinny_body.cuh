@@ -7,7 +7,7 @@ namespace frt2 {
 namespace {
 
 constexpr int SK_WARPS = 8;        // the 8 warps of a CTA split K
-constexpr int SK_COLS = 8;         // output columns per CTA == the n of mma.m16n8k16
+constexpr int SK_COLS = 8;         // output columns per n-tile == the n of mma.m16n8k16 (a CTA owns NT of them)
 constexpr int SK_MAXROWS = 16;     // == the m of mma.m16n8k16
 constexpr int SK_KCHUNK = 4096;    // activation chunk held in smem
 constexpr int SK_PAD = 32;         // halves of padding per activation row: rows g and g+1 of a quarter-warp's
@@ -16,8 +16,9 @@ constexpr int SK_NB = 16;          // k32 blocks (16-byte weight vectors per lan
 
 __host__ __device__ inline int sk_pitch(int kchunk) { return ((kchunk + 31) & ~31) + SK_PAD; }
 // ln_c = channels of a fused LayerNorm (its gamma / beta are staged in shared memory), 0 without one
-inline size_t sk_smem_bytes(int mr, int kchunk, int ln_c = 0) {
-  return static_cast<size_t>(mr) * sk_pitch(kchunk) * 2 + static_cast<size_t>(SK_WARPS + 1) * mr * SK_COLS * 4 +
+// nt = n-tiles (8 columns each) per CTA
+inline size_t sk_smem_bytes(int mr, int kchunk, int ln_c = 0, int nt = 1) {
+  return static_cast<size_t>(mr) * sk_pitch(kchunk) * 2 + static_cast<size_t>(SK_WARPS + 1) * mr * SK_COLS * nt * 4 +
          static_cast<size_t>(ln_c) * 8;
 }
 
@@ -48,39 +49,50 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 // `vblock` = which group of 8 output columns, `tid` = thread index inside the 256-thread group that runs the tile,
 // `sync` = barrier over exactly those 256 threads (__syncthreads in the stand-alone kernel, a named barrier when two
 // groups of the persistent step kernel work on different tiles), PDL = programmatic-dependent-launch hooks.
-template <int MR, bool PDL, typename Sync>
+// NT = 8-column n-tiles per CTA: 2 for the wide layers (N >= 2048: QKV, fc1) so that their CTAs fit ONE wave of the
+// 148 SMs and the activation rows are staged / normalised half as often; a column's arithmetic does not depend on NT.
+template <int MR, bool PDL, int NT = 1, typename Sync>
 __device__ __forceinline__ void gemm_skinny_body(const GemmDesc& g, int mtot, int vblock, int tid, uint8_t* sk_smem,
                                                  Sync sync) {
+  constexpr int COLS = SK_COLS * NT;
+  constexpr int NB = SK_NB / NT;     // weight vectors in flight per lane and n-tile
   __half* sA = reinterpret_cast<__half*>(sk_smem);                     // [MR][pitch]
   const int Ktot = g.ntaps * g.Kc;
   const int kchunk = min(Ktot, SK_KCHUNK);
   const int pitch = sk_pitch(kchunk);
-  float* sRed = reinterpret_cast<float*>(sk_smem + static_cast<size_t>(MR) * pitch * 2);   // [SK_WARPS][MR][SK_COLS]
-  float* sOut = sRed + SK_WARPS * MR * SK_COLS;                                             // [MR][SK_COLS]
-  float* sGam = sOut + MR * SK_COLS;                                                        // [Kc] (fused LayerNorm)
+  float* sRed = reinterpret_cast<float*>(sk_smem + static_cast<size_t>(MR) * pitch * 2);   // [SK_WARPS][MR][COLS]
+  float* sOut = sRed + SK_WARPS * MR * COLS;                                             // [MR][COLS]
+  float* sGam = sOut + MR * COLS;                                                        // [Kc] (fused LayerNorm)
   float* sBet = sGam + g.Kc;                                                                // [Kc]
   const int warp = tid >> 5, lane = tid & 31;
   const int gq = lane >> 2, tq = lane & 3;
-  const int n = vblock * SK_COLS + gq;
-  const bool col_ok = n < g.N;
-  const uint4* wrow = reinterpret_cast<const uint4*>(g.W + static_cast<long long>(col_ok ? n : 0) * Ktot);
+  bool col_ok[NT];
+  const uint4* wrow[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int n = vblock * COLS + t * SK_COLS + gq;
+    col_ok[t] = n < g.N;
+    wrow[t] = reinterpret_cast<const uint4*>(g.W + static_cast<long long>(col_ok[t] ? n : 0) * Ktot);
+  }
 
-  uint4 wv[SK_NB];
-  // weight vectors of this warp's blocks ib0 .. ib0+SK_NB-1 of the chunk starting at kc0 (kc halves long)
+  uint4 wv[NT][NB];
+  // weight vectors of this warp's blocks ib0 .. ib0+NB-1 of the chunk starting at kc0 (kc halves long)
   auto load_weights = [&](int kc0, int kc, int ib0) {
 #pragma unroll
-    for (int u = 0; u < SK_NB; ++u) {
+    for (int u = 0; u < NB; ++u) {
       const int k = (warp + SK_WARPS * (ib0 + u)) * 32 + tq * 8;
-      wv[u] = (col_ok && k < kc) ? __ldg(wrow + ((kc0 + k) >> 3)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int t = 0; t < NT; ++t)
+        wv[t][u] = (col_ok[t] && k < kc) ? __ldg(wrow[t] + ((kc0 + k) >> 3)) : make_uint4(0u, 0u, 0u, 0u);
     }
   };
   // ---- predecessor-independent prologue: the first weight vectors are in flight while the previous kernel of the
   //      step is still running (PDL) and while the activations are staged below
   load_weights(0, kchunk, 0);
   float bias_c = 0.f, bias_p = 0.f;
-  if (g.bias != nullptr && tid < MR * SK_COLS) {
-    const int c = tid % SK_COLS;
-    const int nn = vblock * SK_COLS + c;
+  if (g.bias != nullptr && tid < MR * COLS) {
+    const int c = tid % COLS;
+    const int nn = vblock * COLS + c;
     if (nn < g.N) bias_c = __ldg(g.bias + nn);
     if ((nn ^ 1) < g.N) bias_p = __ldg(g.bias + (nn ^ 1));
   }
@@ -97,9 +109,9 @@ __device__ __forceinline__ void gemm_skinny_body(const GemmDesc& g, int mtot, in
   // the epilogue's run-time row offsets and residual values are known now: fetch them under the main loop
   int ep_roff = 0, ep_roff_b = 0;
   float ep_resid = 0.f;
-  if (tid < MR * SK_COLS) {
-    const int m = tid / SK_COLS, c = tid - m * SK_COLS;
-    const int nn = vblock * SK_COLS + c;
+  if (tid < MR * COLS) {
+    const int m = tid / COLS, c = tid - m * COLS;
+    const int nn = vblock * COLS + c;
     if (m < mtot && nn < g.N) {
       const int b = m / g.rows_out, r = m - b * g.rows_out;
       if (g.out_row_off != nullptr) ep_roff = __ldg(g.out_row_off + b * g.row_off_stride);
@@ -111,7 +123,9 @@ __device__ __forceinline__ void gemm_skinny_body(const GemmDesc& g, int mtot, in
     }
   }
 
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[NT][4];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = acc[t][2] = acc[t][3] = 0.f;
 
   for (int kc0 = 0; kc0 < Ktot; kc0 += kchunk) {
     const int kc = min(kchunk, Ktot - kc0);
@@ -219,17 +233,20 @@ __device__ __forceinline__ void gemm_skinny_body(const GemmDesc& g, int mtot, in
       const int nblk = (kc + 31) >> 5;
       const int niter = nblk > warp ? (nblk - warp + SK_WARPS - 1) / SK_WARPS : 0;   // blocks of this warp
       const __half* abase = sA + static_cast<size_t>(gq) * pitch + tq * 8;
-      for (int ib0 = 0; ib0 < niter; ib0 += SK_NB) {
+      for (int ib0 = 0; ib0 < niter; ib0 += NB) {
         if (kc0 != 0 || ib0 != 0) load_weights(kc0, kc, ib0);
 #pragma unroll
-        for (int u = 0; u < SK_NB; ++u) {
+        for (int u = 0; u < NB; ++u) {
           if (ib0 + u < niter) {                                   // warp-uniform
             const int j = warp + SK_WARPS * (ib0 + u);
             const uint4 x = *reinterpret_cast<const uint4*>(abase + j * 32);
             uint4 y = make_uint4(0u, 0u, 0u, 0u);
             if (MR == 16) y = *reinterpret_cast<const uint4*>(abase + static_cast<size_t>(8) * pitch + j * 32);
-            mma16816(acc, x.x, y.x, x.y, y.y, wv[u].x, wv[u].y);
-            mma16816(acc, x.z, y.z, x.w, y.w, wv[u].z, wv[u].w);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+              mma16816(acc[t], x.x, y.x, x.y, y.y, wv[t][u].x, wv[t][u].y);
+              mma16816(acc[t], x.z, y.z, x.w, y.w, wv[t][u].z, wv[t][u].w);
+            }
           }
         }
       }
@@ -239,30 +256,33 @@ __device__ __forceinline__ void gemm_skinny_body(const GemmDesc& g, int mtot, in
   // ---- split-K reduction over the 8 warps (fixed order: deterministic).  acc: rows g (c0,c1) and g+8 (c2,c3),
   //      columns 2t, 2t+1
   {
-    float* r = sRed + static_cast<size_t>(warp) * MR * SK_COLS;
-    r[gq * SK_COLS + 2 * tq] = acc[0];
-    r[gq * SK_COLS + 2 * tq + 1] = acc[1];
-    if (MR == 16) {
-      r[(gq + 8) * SK_COLS + 2 * tq] = acc[2];
-      r[(gq + 8) * SK_COLS + 2 * tq + 1] = acc[3];
+    float* r = sRed + static_cast<size_t>(warp) * MR * COLS;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      r[gq * COLS + t * SK_COLS + 2 * tq] = acc[t][0];
+      r[gq * COLS + t * SK_COLS + 2 * tq + 1] = acc[t][1];
+      if (MR == 16) {
+        r[(gq + 8) * COLS + t * SK_COLS + 2 * tq] = acc[t][2];
+        r[(gq + 8) * COLS + t * SK_COLS + 2 * tq + 1] = acc[t][3];
+      }
     }
   }
   sync();
-  if (tid < MR * SK_COLS) {
+  if (tid < MR * COLS) {
     float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < SK_WARPS; ++w) v += sRed[w * MR * SK_COLS + tid];
+    for (int w = 0; w < SK_WARPS; ++w) v += sRed[w * MR * COLS + tid];
     sOut[tid] = v;
   }
   sync();
   // ---- epilogue: thread t -> (row m, column c); polar pairs read the neighbouring column from smem
   const int t = tid;
-  if (t < MR * SK_COLS) {
-    const int m = t / SK_COLS, c = t - m * SK_COLS;
-    const int nn = vblock * SK_COLS + c;
+  if (t < MR * COLS) {
+    const int m = t / COLS, c = t - m * COLS;
+    const int nn = vblock * COLS + c;
     if (m < mtot && nn < g.N) {
       auto pre = [&](int cc) {   // cc == c (own column) or c ^ 1 (polar partner): biases were prefetched
-        return fmaf(sOut[m * SK_COLS + cc], g.alpha, cc == c ? bias_c : bias_p);
+        return fmaf(sOut[m * COLS + cc], g.alpha, cc == c ? bias_c : bias_p);
       };
       float v = pre(c);
       if (g.act == ACT_GELU) {
