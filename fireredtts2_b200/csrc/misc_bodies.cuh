@@ -54,13 +54,18 @@ __device__ __forceinline__ void layer_norm_body(const float* x, long long ldx, l
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
   // gamma / beta of the register-cached columns: in flight together with the row, not one round trip per use
-  float4 gc[LN_MAX_V4], bc[LN_MAX_V4];
+  // (one row per warp only — the latency-bound streaming step; the two-row throughput kernel has no registers to spare
+  // and hides the latency with occupancy)
+  constexpr int NPRE = (RPW == 1) ? LN_MAX_V4 : 1;
+  float4 gc[NPRE], bc[NPRE];
+  if (RPW == 1) {
 #pragma unroll
-  for (int i = 0; i < LN_MAX_V4; ++i) {
-    const int c = lane + 32 * i;
-    if (c < C4) {
-      gc[i] = __ldg(g4 + c);
-      bc[i] = __ldg(b4 + c);
+    for (int i = 0; i < NPRE; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C4) {
+        gc[i] = __ldg(g4 + c);
+        bc[i] = __ldg(b4 + c);
+      }
     }
   }
 #pragma unroll
@@ -102,7 +107,10 @@ __device__ __forceinline__ void layer_norm_body(const float* x, long long ldx, l
 #pragma unroll
     for (int i = 0; i < LN_MAX_V4; ++i) {
       const int c = lane + 32 * i;
-      if (c < C4) emit(c, cache[r][i], gc[i], bc[i]);
+      if (c < C4) {
+        if (RPW == 1) emit(c, cache[r][i], gc[i % NPRE], bc[i % NPRE]);
+        else emit(c, cache[r][i], __ldg(g4 + c), __ldg(b4 + c));
+      }
     }
     for (int c = lane + 32 * LN_MAX_V4; c < C4; c += 32) emit(c, xr[c], __ldg(g4 + c), __ldg(b4 + c));
   }
