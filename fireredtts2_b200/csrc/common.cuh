@@ -262,7 +262,10 @@ struct MegaRoll {           // update_tail + shift_history + advance_ctrl (the e
   ShiftTable tb;
   int* ctrl;
   int advance_frames;
+  int all_items;            // 1: no control blocks in use (eager streaming) — every item is active
 };
+// the same roll as ONE stand-alone kernel (replaces update_tail + shift_history + advance_ctrl: two graph nodes fewer)
+int stream_state_roll(const MegaRoll& ro, cudaStream_t stream);
 struct MegaOp {
   int kind, mtot, nblocks, pad;
   union U {

@@ -1157,7 +1157,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     rl.kind = MK_ROLL;
     MegaRoll& ro = rl.u.ro;
     ro.frames = frames32; ro.frames_batch_pitch = od.frames_batch_pitch; ro.tail = s->tail; ro.T = T; ro.n_fft = n_fft;
-    ro.E = E; ro.B = B; ro.ctrl = s->ctrl; ro.advance_frames = T;
+    ro.E = E; ro.B = B; ro.ctrl = s->ctrl; ro.advance_frames = T; ro.all_items = 0;
     ro.tb.n = 11;
     for (int i = 0; i < 11; ++i) ro.tb.e[i] = {s->conv[i], s->conv_hist[i], s->conv_rpt[i] * L, s->conv_pitch(i)};
     rec->push_back(rl);
@@ -1169,16 +1169,24 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     prof_end(id, st);
   }
   if (streaming) {
-    launches += 2;
-    const int* cblk = graph_mode ? s->ctrl : nullptr;
-    FRT2_TRY(istft_update_tail(frames32, od.frames_batch_pitch, s->tail, B, T, n_fft, cblk, st));
-    ShiftTable tb{};
-    tb.n = 11;
-    for (int i = 0; i < 11; ++i) tb.e[i] = {s->conv[i], s->conv_hist[i], s->conv_rpt[i] * L, s->conv_pitch(i)};
-    shift_history_kernel<<<dim3(8, 11), 256, 0, st>>>(tb, E, B, cblk);
-    advance_ctrl_kernel<<<(B + 127) / 128, 128, 0, st>>>(s->ctrl, T, B, graph_mode ? 0 : 1);
-    launches += 1;
-    FRT2_CUDA_OK(cudaGetLastError());
+    // end-of-step state roll (new iSTFT tail, conv histories to the head, position advance) as one kernel
+    MegaRoll ro;
+    ro.frames = frames32; ro.frames_batch_pitch = od.frames_batch_pitch; ro.tail = s->tail; ro.T = T; ro.n_fft = n_fft;
+    ro.E = E; ro.B = B; ro.ctrl = s->ctrl; ro.advance_frames = T; ro.all_items = graph_mode ? 0 : 1;
+    ro.tb.n = 11;
+    for (int i = 0; i < 11; ++i) ro.tb.e[i] = {s->conv[i], s->conv_hist[i], s->conv_rpt[i] * L, s->conv_pitch(i)};
+    if (E % 8 == 0 && n_fft % 4 == 0) {
+      FRT2_TRY(stream_state_roll(ro, st));
+      launches += 1;
+    } else {
+      launches += 2;
+      const int* cblk = graph_mode ? s->ctrl : nullptr;
+      FRT2_TRY(istft_update_tail(frames32, od.frames_batch_pitch, s->tail, B, T, n_fft, cblk, st));
+      shift_history_kernel<<<dim3(8, 11), 256, 0, st>>>(ro.tb, E, B, cblk);
+      advance_ctrl_kernel<<<(B + 127) / 128, 128, 0, st>>>(s->ctrl, T, B, graph_mode ? 0 : 1);
+      launches += 1;
+      FRT2_CUDA_OK(cudaGetLastError());
+    }
   }
   tap_B = B;
   tap_L = L;

@@ -131,7 +131,7 @@ __device__ __forceinline__ void op_roll(const MegaRoll& ro) {
         const long long per = 3LL * ro.n_fft / 4;
         const int b = static_cast<int>(i / per);
         const long long k = i - b * per;
-        if (ro.ctrl[b * CTRL_INTS + CTRL_ACTIVE] == 0) continue;
+        if (!ro.all_items && ro.ctrl[b * CTRL_INTS + CTRL_ACTIVE] == 0) continue;
         val[u] = *reinterpret_cast<const uint4*>(ro.frames + b * ro.frames_batch_pitch +
                                                  static_cast<long long>(ro.T - 3) * ro.n_fft + 4 * k);
         dst[u] = reinterpret_cast<uint4*>(ro.tail + b * per * 4 + 4 * k);
@@ -143,7 +143,7 @@ __device__ __forceinline__ void op_roll(const MegaRoll& ro) {
         const int c = static_cast<int>(j % E8);
         const int r = static_cast<int>((j / E8) % en.hist);
         const int b = static_cast<int>(j / (static_cast<long long>(E8) * en.hist));
-        if (ro.ctrl[b * CTRL_INTS + CTRL_ACTIVE] == 0) continue;
+        if (!ro.all_items && ro.ctrl[b * CTRL_INTS + CTRL_ACTIVE] == 0) continue;
         __half* base = en.p + b * en.batch_pitch;
         val[u] = *reinterpret_cast<const uint4*>(base + static_cast<long long>(r + en.rows) * ro.E + c * 8);
         dst[u] = reinterpret_cast<uint4*>(base + static_cast<long long>(r) * ro.E + c * 8);
@@ -154,7 +154,8 @@ __device__ __forceinline__ void op_roll(const MegaRoll& ro) {
       if (dst[u] != nullptr) *dst[u] = val[u];
   }
   // position advance (engine.cu advance_ctrl_kernel, pool form: active items only).  Nothing in this op reads CTRL_POS.
-  if (gtid < ro.B && ro.ctrl[gtid * CTRL_INTS + CTRL_ACTIVE] != 0) ro.ctrl[gtid * CTRL_INTS + CTRL_POS] += ro.advance_frames;
+  if (gtid < ro.B && (ro.all_items || ro.ctrl[gtid * CTRL_INTS + CTRL_ACTIVE] != 0))
+    ro.ctrl[gtid * CTRL_INTS + CTRL_POS] += ro.advance_frames;
 }
 
 __global__ void __launch_bounds__(MG_THREADS, 1)
@@ -241,6 +242,8 @@ stream_step_kernel(const MegaOp* __restrict__ ops, int nops, unsigned int* bar, 
   }
 }
 
+__global__ void __launch_bounds__(256) state_roll_kernel(const MegaRoll ro) { op_roll(ro); }
+
 int g_mega_grid = 0;
 int g_mega_group_smem = 0;
 int g_mega_smem = 0;
@@ -265,6 +268,18 @@ int stream_mega_init() {
 }
 
 int stream_mega_grid() { return g_mega_grid; }
+
+int stream_state_roll(const MegaRoll& ro, cudaStream_t stream) {
+  FRT2_REQUIRE(ro.E % 8 == 0 && ro.n_fft % 4 == 0 && ro.T >= 3 && ro.tb.n <= 16, FRT2_ERR_BAD_ARG, "state roll: bad shape");
+  // enough threads that every 16-byte piece has its own (one round trip for the whole roll), at least one per item
+  long long pieces = 3LL * ro.n_fft / 4 * ro.B;
+  for (int i = 0; i < ro.tb.n; ++i) pieces += static_cast<long long>(ro.B) * ro.tb.e[i].hist * (ro.E / 8);
+  const long long threads = std::max<long long>(pieces, ro.B);
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((threads + 255) / 256, 4096));
+  state_roll_kernel<<<grid, 256, 0, stream>>>(ro);
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
 
 int stream_mega_launch(const MegaOp* ops, int nops, unsigned int* bar, unsigned int epoch0, cudaStream_t stream,
                        long long* trace) {

@@ -152,3 +152,29 @@ def test_oracle_rvq_encode_matches_reference_indices(name, preset):
     # and prefix nq reproduces the first rows
     c2, _ = O.rvq_encode_codes(sd, g["z"], nq=2)
     assert np.array_equal(c2, g["codes"][:2])
+
+
+def test_oracle_rvq_encode_properties():
+    """Size-independent properties of ResidualVQ.encode_codes on the oracle: (1) with Identity projections a codebook row is
+    its own nearest neighbour (distance 0), (2) every stage picks the codebook row closest to the current residual, (3) tokens are independent (any slice encodes the same)."""
+    from fireredtts2_b200.config import TINY_IDENT
+    from fireredtts2_b200.weights import synthetic_state_dict
+    cfg = TINY_IDENT
+    sd = synthetic_state_dict(cfg, 3)
+    rng = np.random.default_rng(0)
+    idx = rng.integers(0, cfg.codebook_size, size=(2, 40))
+    z = np.asarray(sd["rvq.quantizers.0.codebook"])[idx].transpose(0, 2, 1).copy()      # (B, cd, T), input_dim == rvq_dim
+    codes, _ = O.rvq_encode_codes(sd, z, nq=1)
+    assert np.array_equal(codes[0], idx)
+    z = rng.standard_normal((2, cfg.rvq_dim, 30)).astype(np.float32)
+    codes, _ = O.rvq_encode_codes(sd, z)
+    # every stage picks the row closest to the CURRENT residual (brute force in float64; Identity projections)
+    resid = z.transpose(0, 2, 1).astype(np.float64).reshape(-1, cfg.rvq_dim)
+    for i in range(cfg.num_quantizers):
+        C = np.asarray(sd[f"rvq.quantizers.{i}.codebook"], dtype=np.float64)
+        d = ((resid[:, None, :] - C[None, :, :]) ** 2).sum(-1)
+        chosen = codes[i].reshape(-1)
+        assert np.all(d[np.arange(len(chosen)), chosen] <= d.min(axis=1) + 1e-4)
+        resid = resid - C[chosen]
+    part, _ = O.rvq_encode_codes(sd, z[1:, :, 5:17])
+    assert np.array_equal(part, codes[:, 1:, 5:17])
