@@ -388,7 +388,10 @@ struct Handle {
         return FRT2_OK;
       }
       MegaOp op;
-      op.kind = MK_SKINNY; op.mtot = mtot; op.nblocks = (g.N + 7) / 8; op.u.g = g;
+      // n-tiles per CTA: one round of tiles over the grid (148 CTAs) where the register budget allows it
+      int nt = (g.N / 8 + stream_mega_grid() - 1) / std::max(1, stream_mega_grid());
+      nt = std::max(1, std::min(nt, mtot <= 8 ? 4 : 2));
+      op.kind = MK_SKINNY; op.mtot = mtot; op.pad = nt; op.nblocks = (g.N + 8 * nt - 1) / (8 * nt); op.u.g = g;
       rec->push_back(op);
       return FRT2_OK;
     }

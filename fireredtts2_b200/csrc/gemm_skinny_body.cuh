@@ -55,7 +55,7 @@ template <int MR, bool PDL, int NT = 1, typename Sync>
 __device__ __forceinline__ void gemm_skinny_body(const GemmDesc& g, int mtot, int vblock, int tid, uint8_t* sk_smem,
                                                  Sync sync) {
   constexpr int COLS = SK_COLS * NT;
-  constexpr int NB = SK_NB / NT;     // weight vectors in flight per lane and n-tile
+  constexpr int NB = NT == 1 ? SK_NB : (NT == 2 ? SK_NB / 2 : SK_NB / 4);   // weight vectors in flight per lane and n-tile
   __half* sA = reinterpret_cast<__half*>(sk_smem);                     // [MR][pitch]
   const int Ktot = g.ntaps * g.Kc;
   const int kchunk = min(Ktot, SK_KCHUNK);

@@ -3,8 +3,10 @@
 // One decode_one_token step (reference model.py:326-376) at <= 16 rows is ~90 dependent kernels of a few microseconds:
 // replayed as a CUDA graph it costs ~9 us per node (launch gap + CTA ramp + first-load latency) against a 66 us HBM floor
 // for the 429 MB of weights.  Here the SAME op list — recorded once per (chunk length, nq) by running the host pipeline
-// in recording mode — is interpreted by ONE cooperative kernel, one 512-thread CTA per SM, with a grid barrier (one
-// atomic + an acquire spin per CTA) between dependent ops instead of a kernel boundary.  The op bodies are the very
+// in recording mode — is interpreted by ONE cooperative kernel, one 256-thread CTA per SM (so that the op bodies keep the
+// 255-register budget they have as stand-alone kernels: a 512-thread CTA capped them at 128 and spilled the skinny GEMM's
+// weight vectors), with a grid barrier (one atomic + an acquire spin per CTA) between dependent ops instead of a kernel
+// boundary.  The op bodies are the very
 // device functions the stand-alone kernels run (gemm_skinny_body, attention_warp_body, layer_norm_body,
 // overlap_add_sample), so a step is bit-identical to the kernel-by-kernel path.
 //
@@ -22,8 +24,7 @@ namespace frt2 {
 
 namespace {
 
-constexpr int MG_THREADS = 512;
-constexpr int MG_GROUP = 256;                         // threads of one skinny-GEMM tile
+constexpr int MG_THREADS = 256;                       // == the skinny GEMM's tile group; 8 warps for attention / LayerNorm
 constexpr int MG_OP_WORDS = (sizeof(MegaOp) + 15) / 16;
 
 __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
@@ -45,10 +46,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int tar
     __threadfence();
   }
   __syncthreads();
-}
-
-__device__ __forceinline__ void group_sync(int grp) {
-  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(MG_GROUP) : "memory");
 }
 
 __device__ __forceinline__ void op_rvq(const MegaRvq& r, int* s_idx /* [4][64] */) {
@@ -181,22 +178,28 @@ stream_step_kernel(const MegaOp* __restrict__ ops, int nops, unsigned int* bar, 
     if (i + 1 < nops) fetch(i + 1);   // lands before the barrier's __syncthreads; op i+2 overwrites this slot only after it
     switch (op.kind) {
       case MK_SKINNY: {
-        const int grp = threadIdx.x / MG_GROUP, tid = threadIdx.x % MG_GROUP;
-        const int ngroups = (op.mtot <= 8) ? 2 : 1;   // MR = 16 needs the whole shared-memory budget for one tile
-        if (grp < ngroups) {
-          uint8_t* sm = mg_smem + grp * group_smem;
-          auto sync = [grp] { group_sync(grp); };
-          for (int vb = blockIdx.x + gridDim.x * grp; vb < op.nblocks; vb += gridDim.x * ngroups) {
-            if (op.mtot <= 8) gemm_skinny_body<8, false>(op.u.g, op.mtot, vb, tid, sm, sync);
-            else gemm_skinny_body<16, false>(op.u.g, op.mtot, vb, tid, sm, sync);
-            sync();   // the group's shared memory is reused by its next tile
+        // op.pad = n-tiles (8 columns each) per CTA, chosen at recording time so that a layer is ONE round of tiles
+        auto sync = [] { __syncthreads(); };
+        for (int vb = blockIdx.x; vb < op.nblocks; vb += gridDim.x) {
+          if (op.mtot <= 8) {
+            switch (op.pad) {
+              case 1: gemm_skinny_body<8, false, 1>(op.u.g, op.mtot, vb, threadIdx.x, mg_smem, sync); break;
+              case 2: gemm_skinny_body<8, false, 2>(op.u.g, op.mtot, vb, threadIdx.x, mg_smem, sync); break;
+              case 3: gemm_skinny_body<8, false, 3>(op.u.g, op.mtot, vb, threadIdx.x, mg_smem, sync); break;
+              default: gemm_skinny_body<8, false, 4>(op.u.g, op.mtot, vb, threadIdx.x, mg_smem, sync); break;
+            }
+          } else if (op.pad == 1) {
+            gemm_skinny_body<16, false, 1>(op.u.g, op.mtot, vb, threadIdx.x, mg_smem, sync);
+          } else {
+            gemm_skinny_body<16, false, 2>(op.u.g, op.mtot, vb, threadIdx.x, mg_smem, sync);
           }
+          __syncthreads();   // shared memory is reused by the CTA's next tile
         }
         break;
       }
       case MK_ATTN:
         for (int vb = blockIdx.x; vb < op.nblocks; vb += gridDim.x) {
-          attention_warp_body<64, 16, true, ATTN_KSPLIT>(op.u.a, vb);   // recorded only with the split workspace, Tq == 8
+          attention_warp_body<64, 8, true, ATTN_KSPLIT>(op.u.a, vb);   // recorded only with the split workspace, Tq == 8
           __syncthreads();
         }
         break;
@@ -256,9 +259,9 @@ int stream_mega_init() {
   FRT2_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   FRT2_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   FRT2_REQUIRE(coop != 0, FRT2_ERR_CUDA, "device does not support cooperative launches");
-  // a group's tile: the largest plain tile (K = 4096) or a fused-LayerNorm tile with up to 2048 channels
-  g_mega_group_smem = static_cast<int>((sk_smem_bytes(8, SK_KCHUNK, 2048) + 1023) & ~static_cast<size_t>(1023));
-  g_mega_smem = std::max(2 * g_mega_group_smem, static_cast<int>(sk_smem_bytes(16, SK_KCHUNK, 2048)));
+  // the largest tile: K = 4096 (plain) or a fused-LayerNorm tile with up to 2048 channels, up to 4 n-tiles
+  g_mega_group_smem = 0;
+  g_mega_smem = static_cast<int>(std::max(sk_smem_bytes(8, SK_KCHUNK, 2048, 4), sk_smem_bytes(16, SK_KCHUNK, 2048, 2)));
   FRT2_CUDA_OK(cudaFuncSetAttribute(stream_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_mega_smem));
   int per_sm = 0;
   FRT2_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_step_kernel, MG_THREADS, g_mega_smem));
