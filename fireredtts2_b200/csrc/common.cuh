@@ -47,7 +47,10 @@ enum : unsigned int { DEV_ERR_INDEX_OOR = 1u };
 __device__ __forceinline__ float gelu_erf(float x) {  // exact erf GELU (reference F.gelu / nn.GELU default)
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+// x * sigmoid(x) with the fast exponential and division (2 MUFU + 3 FP32 instead of ~20 instructions: the LN + SiLU
+// kernels were XU/issue-limited at 3.0 TB/s); the result is rounded to fp16 right after, 2 ulp of fp32 do not show.
+// x -> -inf: __expf overflows to +inf and the quotient is -0, as for the exact form.
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // fp32 -> fp16 conversions saturate to +-65504 instead of overflowing to inf (one F2FP.SATFINITE instruction):
 // an out-of-range activation degrades gracefully instead of poisoning the utterance with NaNs.
