@@ -1486,7 +1486,7 @@ static int run_ctrl_step(Handle& h, Stream& s, int nq, int Lc, cudaStream_t st, 
     const char* e = getenv("FRT2_MEGA");
     return e == nullptr ? FRT2_MEGA_DEFAULT != 0 : (e[0] != '0');
   }();
-  if (mega_env && s.B * 8 * Lc <= 16 && !(h.debug & DBG_NO_MEGA)) {
+  if (mega_env && stream_mega_grid() > 0 && s.B * 8 * Lc <= 16 && !(h.debug & DBG_NO_MEGA)) {
     auto mi = s.megas.find(key);
     if (mi != s.megas.end() && mi->second.ws != h.ws) {   // workspace moved since the recording
       if (mi->second.ops) cudaFree(mi->second.ops);

@@ -253,19 +253,25 @@ int g_mega_smem = 0;
 
 }  // namespace
 
+// Never fatal: the persistent step kernel is an opt-in path; if it cannot run here the grid stays 0 and the engine keeps
+// replaying the CUDA graph.
 int stream_mega_init() {
-  int dev = 0, sms = 0, coop = 0;
-  FRT2_CUDA_OK(cudaGetDevice(&dev));
-  FRT2_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  FRT2_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
-  FRT2_REQUIRE(coop != 0, FRT2_ERR_CUDA, "device does not support cooperative launches");
+  g_mega_grid = 0;
+  int dev = 0, sms = 0, coop = 0, per_sm = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || coop == 0) {
+    cudaGetLastError();
+    return FRT2_OK;
+  }
   // the largest tile: K = 4096 (plain) or a fused-LayerNorm tile with up to 2048 channels, up to 4 n-tiles
   g_mega_group_smem = 0;
   g_mega_smem = static_cast<int>(std::max(sk_smem_bytes(8, SK_KCHUNK, 2048, 4), sk_smem_bytes(16, SK_KCHUNK, 2048, 2)));
-  FRT2_CUDA_OK(cudaFuncSetAttribute(stream_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_mega_smem));
-  int per_sm = 0;
-  FRT2_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_step_kernel, MG_THREADS, g_mega_smem));
-  FRT2_REQUIRE(per_sm >= 1, FRT2_ERR_CUDA, "stream_step_kernel does not fit an SM");
+  if (cudaFuncSetAttribute(stream_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_mega_smem) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stream_step_kernel, MG_THREADS, g_mega_smem) != cudaSuccess ||
+      per_sm < 1) {
+    cudaGetLastError();
+    return FRT2_OK;
+  }
   g_mega_grid = sms;   // one CTA per SM
   return FRT2_OK;
 }

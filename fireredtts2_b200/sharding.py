@@ -174,6 +174,12 @@ class PeerBuffer:
         assert self.owner, "only the owning rank reads the gathered buffer"
         return torch.as_tensor(self, device=self.device)
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def close(self):
         if not self.ptr:
             return
