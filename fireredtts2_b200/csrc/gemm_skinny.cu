@@ -223,6 +223,10 @@ int gemm_skinny_init() {
                                     static_cast<int>(sk_smem_bytes(8, SK_KCHUNK, SK_KCHUNK, 2))));
   FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_skinny_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(sk_smem_bytes(16, SK_KCHUNK, SK_KCHUNK, 2))));
+  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_skinny_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sk_smem_bytes(8, SK_KCHUNK, SK_KCHUNK, 3))));
+  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_skinny_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(sk_smem_bytes(8, SK_KCHUNK, SK_KCHUNK, 4))));
   return FRT2_OK;
 }
 
@@ -273,13 +277,22 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t stream) {
     const char* e = getenv("FRT2_SKINNY_NT2_MIN_N");
     return e != nullptr ? atoi(e) : 2048;
   }();
-  const int nt = (g.N >= nt2_min_n && !no_nt2) ? 2 : 1;
+  static const int nt_max = [] {   // up to 3 / 4 n-tiles per CTA: one CTA per SM for N = 3072 / 4096 (A/B: =2 -> 562 vs 554 us)
+    const char* e = getenv("FRT2_SKINNY_NTMAX");
+    return e != nullptr ? atoi(e) : 4;
+  }();
+  int nt = (g.N >= nt2_min_n && !no_nt2) ? 2 : 1;
+  if (nt == 2 && nt_max > 2 && mtot <= 8) nt = std::max(2, std::min(nt_max, (g.N / 8 + 147) / 148));
   cfg.gridDim = dim3((g.N + SK_COLS * nt - 1) / (SK_COLS * nt));
   const int ln_c = g.ln_gamma != nullptr ? g.Kc : 0;
   if (mtot <= 8) {
     cfg.dynamicSmemBytes = sk_smem_bytes(8, kchunk, ln_c, nt);
-    if (nt == 2) FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<8, 2>, g, mtot));
-    else FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<8, 1>, g, mtot));
+    switch (nt) {
+      case 4: FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<8, 4>, g, mtot)); break;
+      case 3: FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<8, 3>, g, mtot)); break;
+      case 2: FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<8, 2>, g, mtot)); break;
+      default: FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<8, 1>, g, mtot)); break;
+    }
   } else {
     cfg.dynamicSmemBytes = sk_smem_bytes(16, kchunk, ln_c, nt);
     if (nt == 2) FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_skinny_kernel<16, 2>, g, mtot));
