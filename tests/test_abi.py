@@ -67,3 +67,27 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/frt2.h is the drop-in boundary for non-Python hosts: it must compile as C (no C++-isms, no CUDA types) and
+    a minimal C host that references every entry point must link against the library."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "frt2.h")).read()
+    names = sorted(set(re.findall(r"\b(frt2_[a-z0-9_]+)\s*\(", hdr)))
+    src = tmp_path / "host.c"
+    body = "\n".join(f"  p[{i}] = (fn){n};" for i, n in enumerate(names))
+    src.write_text('#include "frt2.h"\n#include <stdio.h>\ntypedef void (*fn)(void);\nint main(void) {\n  fn p[%d];\n%s\n'
+                   '  printf("%%s %%d\\n", frt2_version(), p[0] != 0);\n  return 0;\n}\n' % (len(names), body))
+    lib_dir = os.path.join(root, "fireredtts2_b200")
+    exe = tmp_path / "host"
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(root, "include"), str(src),
+                        "-o", str(exe), "-L", lib_dir, "-l:libfrt2_b200.so", "-Wl,-rpath," + lib_dir,
+                        "-Wl,--unresolved-symbols=ignore-in-shared-libs"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
