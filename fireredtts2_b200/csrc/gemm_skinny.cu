@@ -253,10 +253,11 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t stream) {
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // PDL: overlap the weight prefetch with the
   attr[0].val.programmaticStreamSerializationAllowed = 1;            // tail of the previous kernel of the step
-  // Measured on B200 (tools/stream_bench.py): inside the captured per-token graph the programmatic edges cost ~100 us
-  // per step (1217 vs 1103 us) — early-resident dependents compete with the running kernel for SM slots — so PDL is
-  // opt-in (FRT2_PDL=1) and the default is plain stream order.
-  static const bool use_pdl = (getenv("FRT2_PDL") != nullptr);
+  // Programmatic dependent launch: the next skinny kernel's prologue (all of its weight vectors, gamma/beta) is in flight
+  // while the current kernel drains.  With the round-1 kernels this cost ~100 us per step inside the captured graph
+  // (early-resident dependents competed for SM slots); with the current ones it saves ~20 (557 -> 538 us per token, full
+  // GPU suite green with it), so it is on by default; FRT2_NO_PDL=1 restores plain stream order (A/B).
+  static const bool use_pdl = (getenv("FRT2_NO_PDL") == nullptr);
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
   static const bool use_fma = (getenv("FRT2_SKINNY_FMA") != nullptr);   // A/B: the round-1 FMA-loop kernel
