@@ -1,5 +1,7 @@
+"""Debug: every unit of the config-4 dialogue decoded inside a padded var-len batch must equal its standalone decode, under
+the product path and the check paths (found the folded-LayerNorm aliasing fault)."""
 import os, sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from fireredtts2_b200.codec import RedCodecB200
 from fireredtts2_b200.config import C0
