@@ -12,7 +12,7 @@ FRT2_OK = 0
 ERR_BAD_ARG, ERR_BAD_DTYPE, ERR_INDEX_OOR, ERR_STATE_OVERFLOW, ERR_CUDA, ERR_MISSING_TENSOR, ERR_NOT_FINALIZED = \
     -1, -2, -3, -4, -5, -6, -7
 
-DBG_TAPS, DBG_GEMM_REF, DBG_ATTN_WARP, DBG_NO_GRAPH, DBG_NO_SKINNY, DBG_NO_LNFOLD, DBG_NO_MEGA = 1, 2, 4, 8, 16, 32, 64
+DBG_TAPS, DBG_GEMM_REF, DBG_ATTN_WARP, DBG_NO_GRAPH, DBG_NO_SKINNY, DBG_NO_LNFOLD = 1, 2, 4, 8, 16, 32
 ACT_NONE, ACT_GELU, ACT_POLAR = 0, 1, 2
 SLOT_ACTIVE, SLOT_LAST, SLOT_RESET = 1, 2, 4
 POOL_MAX_SLOTS = 256
@@ -55,6 +55,9 @@ SIGNATURES = {
     "frt2_stream_reset": (_i, [_p]),
     "frt2_stream_destroy": (None, [_p]),
     "frt2_stream_tokens": (_i, [_p]),
+    "frt2_stream_reserve": (_i, [_p, _i, _i, _i]),
+    "frt2_stream_check_error": (_i, [_p, _p, C.POINTER(C.c_int32), _p]),
+    "frt2_stream_fetch_errors": (_i, [_p, _p, _p, _p]),
     "frt2_decode_chunk": (_i, [_p, _p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _i64, C.POINTER(_i), _p]),
     "frt2_decode_chunk_pcm16": (_i, [_p, _p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _i64, C.POINTER(_i), _p]),
     "frt2_pool_create": (_i, [_p, _i, _i, C.POINTER(_p)]),

@@ -1,4 +1,6 @@
-"""Builds libfrt2_b200.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
+"""Builds libfrt2_b200.so in-tree with nvcc for sm_100a.  The library is a build product: it is git-ignored (a fresh
+checkout has to run this first — `python -m fireredtts2_b200.build`, or `__graft_entry__.build()`), but it is NOT
+gpurun-ignored, so an in-tree build travels to the GPU box with the snapshot (no JIT cache involved)."""
 from __future__ import annotations
 
 import os
@@ -8,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfrt2_b200.so")
-SOURCES = ["engine.cu", "gemm_tc.cu", "gemm_skinny.cu", "attention.cu", "kernels_misc.cu", "rvq_encode.cu", "stream_mega.cu"]
+SOURCES = ["engine.cu", "gemm_tc.cu", "gemm_skinny.cu", "attention.cu", "kernels_misc.cu", "rvq_encode.cu", "stream_state.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-fopenmp,-O2", "--expt-relaxed-constexpr"]

@@ -274,16 +274,23 @@ class RedCodecB200(torch.nn.Module):
                        sB, sQ, sL, nq, Lc, int(bool(last_token)),
                        C.c_void_p(audio.data_ptr()), audio.stride(0), C.byref(n_out), self._cuda_stream()))
             assert n_out.value == n
-            if _check:
-                self._maybe_check()
             st.finished = bool(last_token)
+            if _check and self.check_indices:   # IndexError inside the offending call, like the reference (rvq.py:58)
+                N.check(self._lib.frt2_stream_check_error(self._h, st.ptr, None, self._cuda_stream()))
         return audio, {_STATE_KEY: st}
 
     def new_stream(self, batch: int = 1, max_tokens: Optional[int] = None) -> Dict[str, object]:
-        """Pre-allocate a stream state (a server keeps a pool of these so the first chunk pays no allocation);
-        pass the returned dict as ``cache_dict`` of the first ``decode_one_token`` call."""
+        """A stream state up front; pass the returned dict as ``cache_dict`` of the first ``decode_one_token`` call.
+        Not needed for latency: the native handle recycles the states of finished utterances, so the reference's own
+        call pattern ``decode_one_token(tok, {}, last)`` pays no allocation either (see ``reserve_streams``)."""
         with torch.cuda.device(self.device_index):
             return {_STATE_KEY: _NativeStream(self, batch, max_tokens or self.stream_max_tokens)}
+
+    def reserve_streams(self, count: int = 1, batch: int = 1, max_tokens: Optional[int] = None) -> None:
+        """Keep ``count`` spare stream states (device buffers + the captured per-token step) in the handle, so that the
+        first ``decode_one_token(tok, {}, ...)`` calls of a freshly loaded model are as fast as every later one."""
+        with torch.cuda.device(self.device_index):
+            N.check(self._lib.frt2_stream_reserve(self._h, batch, max_tokens or self.stream_max_tokens, count))
 
     def decode_stream(self, frames: Iterable[torch.Tensor], pcm16: bool = True, batch: int = 1,
                       ring: int = 16) -> Iterator["StreamChunk"]:
@@ -305,7 +312,8 @@ class RedCodecB200(torch.nn.Module):
         return StreamPool(self, slots, max_tokens or self.stream_max_tokens)
 
     def reset_stream(self, cache_dict: Dict[str, object]) -> Dict[str, object]:
-        """Return a used state to its initial (empty) condition for the next utterance."""
+        """Return a used state to its initial (empty) condition for the next utterance.  Stream-ordered: the state is
+        cleared by a kernel on the CUDA stream of the next ``decode_one_token`` call, nothing synchronises."""
         st: _NativeStream = cache_dict[_STATE_KEY]
         N.check(self._lib.frt2_stream_reset(st.ptr))
         st.finished = False
@@ -436,9 +444,31 @@ class StreamDecoder:
             width = codec.cfg.samples_per_token + codec.cfg.istft_pad
             dt = torch.int16 if pcm16 else torch.float32
             self._ring = [torch.empty((batch, width), dtype=dt).pin_memory() for _ in range(max(2, ring))]
+            # the stream's device-side error words (word 0: any item sent an out-of-range code) ride along with every
+            # chunk into pinned memory and are tested one step late, once the chunk's event has completed
+            self._err_ring = [torch.zeros(1 + batch, dtype=torch.int32).pin_memory() for _ in range(max(2, ring))]
         self._held: Optional[Tuple[torch.Tensor, torch.cuda.Event]] = None
+        self._unchecked = []      # (ready event, error words, chunk index) of chunks whose words were not tested yet
         self._n = 0
         self._done = False
+
+    def _check_completed(self, wait: bool = False) -> None:
+        """IndexError for an out-of-range code, raised to THIS request (the words belong to this stream) at the first
+        push / finish after the offending chunk has left the device."""
+        keep = []
+        for ev, words, idx in self._unchecked:
+            if wait:
+                ev.synchronize()
+            if not ev.query():
+                keep.append((ev, words, idx))
+            elif int(words[0]) != 0:
+                self._unchecked = []
+                c = self.codec
+                st = self._cache[_STATE_KEY]
+                with torch.cuda.device(c.device_index):   # clears the stream's words
+                    c._lib.frt2_stream_check_error(c._h, st.ptr, None, C.c_void_p(self._side.cuda_stream))
+                raise IndexError(f"index out of range in self (code frame {idx} of this stream)")
+        self._unchecked = keep
 
     def _as_token(self, frame: torch.Tensor) -> torch.Tensor:
         nq = frame.shape[-2] if frame.dim() == 3 else frame.shape[-1]
@@ -452,22 +482,28 @@ class StreamDecoder:
         c = self.codec
         with torch.cuda.device(c.device_index), torch.cuda.stream(self._side):
             self._side.wait_event(ev)                       # the frame's tokens are complete
-            # no per-step host synchronisation: the device-side index check is read once, at the end of the stream
+            # no per-step host synchronisation: the stream's error words follow each chunk to the host (below)
             audio, self._cache = c.decode_one_token(tok, self._cache, last, pcm16=self.pcm16, _check=False)
             tok.record_stream(self._side)
             host = self._ring[self._n % len(self._ring)][:, :audio.shape[1]]
             host.copy_(audio, non_blocking=True)
+            words = self._err_ring[self._n % len(self._err_ring)]
+            N.check(c._lib.frt2_stream_fetch_errors(c._h, self._cache[_STATE_KEY].ptr, C.c_void_p(words.data_ptr()),
+                                                    C.c_void_p(self._side.cuda_stream)))
             ready = torch.cuda.Event()
             ready.record(self._side)
-            if last:
-                c._maybe_check()                            # IndexError for an out-of-range code anywhere in the stream
+        self._unchecked.append((ready, words, self._n))
         chunk = StreamChunk(host, ready, self._n)
         self._n += 1
+        if last and c.check_indices:
+            self._check_completed(wait=True)                # nothing of this stream is left unchecked
         return chunk
 
     def push(self, frame: torch.Tensor) -> Optional[StreamChunk]:
         if self._done:
             raise ValueError("stream already finished")
+        if self.codec.check_indices:
+            self._check_completed()
         tok = self._as_token(frame)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.codec.device_index))
@@ -484,6 +520,17 @@ class StreamDecoder:
         out = self._decode_held(True)
         self._held = None
         return out
+
+
+class StreamPoolIndexError(IndexError):
+    """Some slots of a ``StreamPool.step`` sent an out-of-range code (the reference raises IndexError inside the
+    offending request's ``decode_one_token``, rvq.py:58).  ``slots`` = the offending slots (their streams have been
+    closed); ``results`` = the chunks of every other slot of the step, which are unaffected and must still be delivered."""
+
+    def __init__(self, slots, results):
+        super().__init__(f"index out of range in self (pool slots {sorted(slots)})")
+        self.slots = sorted(slots)
+        self.results = results
 
 
 class StreamPool:
@@ -542,9 +589,12 @@ class StreamPool:
 
     # -- the step --
     @torch.inference_mode()
-    def step_dense(self, tokens: torch.Tensor, flags, pcm16: bool = False) -> Tuple[torch.Tensor, list]:
+    def step_dense(self, tokens: torch.Tensor, flags, pcm16: bool = False, bad_slots: Optional[list] = None
+                   ) -> Tuple[torch.Tensor, list]:
         """Lowest level: ``tokens`` (slots, nq) int32|int64 on the device, ``flags`` one FRT2_SLOT_* int per slot.
-        Returns ``(out (slots, 8*hop+pad) fp32|int16, n_samples per slot)``; slot b's chunk is ``out[b, :n[b]]``."""
+        Returns ``(out (slots, 8*hop+pad) fp32|int16, n_samples per slot)``; slot b's chunk is ``out[b, :n[b]]``.
+        Out-of-range codes are reported per slot from the pool's own error words: with ``bad_slots`` (a list) the
+        offending slots are appended to it, otherwise IndexError is raised after the step has completed."""
         c = self.codec
         if tokens.dim() != 2 or tokens.shape[0] != self.slots:
             raise ValueError(f"tokens must be (slots={self.slots}, nq), got {tuple(tokens.shape)}")
@@ -560,7 +610,16 @@ class StreamPool:
             N.check(c._lib.frt2_pool_step(c._h, self.ptr, C.c_void_p(tokens.data_ptr()), tokens.element_size(),
                                           tokens.stride(0), tokens.stride(1), tokens.shape[1], f,
                                           C.c_void_p(out.data_ptr()), int(pcm16), out.stride(0), n, c._cuda_stream()))
-            c._maybe_check()
+            if c.check_indices:
+                item = (C.c_int32 * self.slots)()
+                rc = c._lib.frt2_stream_check_error(c._h, self.ptr, item, c._cuda_stream())
+                if rc == N.ERR_INDEX_OOR:
+                    bad = [b for b in range(self.slots) if item[b]]
+                    if bad_slots is None:
+                        raise IndexError(f"index out of range in self (pool slots {bad})")
+                    bad_slots.extend(bad)
+                else:
+                    N.check(rc)
         return out, list(n)
 
     @torch.inference_mode()
@@ -586,13 +645,18 @@ class StreamPool:
         self._tok.copy_(self._tok_host, non_blocking=True)
         self._h2d_done = torch.cuda.Event()
         self._h2d_done.record(torch.cuda.current_stream(self.codec.device_index))
-        out, n = self.step_dense(self._tok[:, :nq], flags, pcm16)
+        bad: list = []
+        # a native-side refusal (bad flag, slot overflow) raises here before any state — native or host — has changed
+        out, n = self.step_dense(self._tok[:, :nq], flags, pcm16, bad_slots=bad)
         res = {}
-        for s in tokens:
+        for s in tokens:          # the native side has advanced every active slot: mirror that first
             self._fresh.discard(s)
-            res[s] = out[s, :n[s]]
-            if s in last:
+            if s in last or s in bad:
                 self.close(s)
+            if s not in bad:
+                res[s] = out[s, :n[s]]
+        if bad:                   # one bad token must not cost the other slots their chunk
+            raise StreamPoolIndexError([s for s in bad if s in tokens], res)
         return res
 
     def destroy(self):

@@ -5,12 +5,10 @@
 //   chunked : queries are the new frames at absolute positions q_pos0.., keys = KV state ++ chunk, no mask
 //             inside the chunk (reference forward_chunk passes attn_mask=None).
 //
-// attention_tc   : tcgen05 flash attention, hd = 64.  One CTA per (128-query tile, head, item), 64-key tiles.
-//                  S = Q K^T and P V on the tensor cores with fp32 accumulators in TMEM; softmax in fp32 with
-//                  one thread per query row (tcgen05.ld gives a thread its whole row: no shuffles);
-//                  P goes back through shared memory in the SWIZZLE_128B K-major layout; V is consumed
-//                  straight from its natural (key, d) layout as an MN-major operand.  Two CTAs per SM so one
-//                  CTA's exponentials overlap the other's MMAs.
+// attention_tc   : tcgen05 flash attention, hd = 64 (attention_t3_kernel below).  64-key tiles, S = Q K^T and P V on
+//                  the tensor cores with fp32 accumulators in TMEM; softmax in fp32 with one thread per query row
+//                  (tcgen05.ld gives a thread its whole row: no shuffles); P stays in tensor memory (TS-form P V);
+//                  V is consumed straight from its natural (key, d) layout as an MN-major operand.
 // attention_warp : CUDA-core kernel, one warp per 8-query block (all 8 rows of a block see the same keys).
 //                  Used for the short-query streaming step and as the on-device check for attention_tc.
 #include <math_constants.h>
@@ -72,17 +70,10 @@ int attention_warp(const AttnDesc& a, cudaStream_t stream) {
 namespace {
 
 constexpr int AT_BQ = 128;       // query rows per query tile == TMEM lanes
-constexpr int AT_QT = 2;         // query tiles per CTA (they share every K/V tile: half the L2->smem traffic)
 constexpr int AT_BK = 64;        // keys per tile
 constexpr int AT_HD = 64;
-constexpr int AT_STAGES = 2;
-constexpr int AT_SOFTMAX_WARPS = 4 * AT_QT;
-constexpr int AT_THREADS = (AT_SOFTMAX_WARPS + 2) * 32;  // + TMA warp + MMA/TMEM-alloc warp
 constexpr int AT_Q_BYTES = AT_BQ * AT_HD * 2;   // 16 KB per query tile
 constexpr int AT_KV_BYTES = AT_BK * AT_HD * 2;  // 8 KB
-constexpr int AT_P_BYTES = AT_BQ * AT_BK * 2;   // 16 KB per query tile
-constexpr int AT_TMEM_COLS = 128 * AT_QT;       // per query tile: S cols [0,64), O cols [64,128)
-constexpr int AT_SMEM_BYTES = AT_QT * (AT_Q_BYTES + AT_P_BYTES) + 2 * AT_STAGES * AT_KV_BYTES + 1024 + 256;
 
 __device__ __forceinline__ float fast_exp2(float x) {  // MUFU.EX2; ex2(-inf) = 0
   float y;
@@ -106,40 +97,6 @@ __device__ __forceinline__ uint32_t exp2_f16x2(float x0, float x1) {
 #endif
 }
 
-// 2^x for a packed pair on the FMA pipe: x = n + f, n = round(x), f in [-0.5, 0.5]; 2^f by a degree-3 minimax
-// polynomial (rel. err 7.5e-5); 2^n by adding n to the exponent field (LEA).  x is clamped to >= -125 first.
-__device__ __forceinline__ uint32_t exp2_poly_f16x2(unsigned long long xx) {
-  float x0, x1;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
-  x0 = fmaxf(x0, -125.0f);
-  x1 = fmaxf(x1, -125.0f);
-  unsigned long long x, t, n, f, pl;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(x0), "f"(x1));
-  const float MAGIC = 12582912.0f;   // 1.5 * 2^23: adding it rounds to the nearest integer in the low mantissa bits
-  unsigned long long magic2, nmagic2, c3, c2, c1, c0, neg1;
-  asm("mov.b64 %0, {%1, %1};" : "=l"(magic2) : "f"(MAGIC));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(nmagic2) : "f"(-MAGIC));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(c3) : "f"(0.055179595f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(0.242611851f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(c1) : "f"(0.693259533f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(c0) : "f"(0.999927984f));
-  asm("mov.b64 %0, {%1, %1};" : "=l"(neg1) : "f"(-1.0f));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(x), "l"(magic2));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(n) : "l"(t), "l"(nmagic2));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(f) : "l"(n), "l"(neg1), "l"(x));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pl) : "l"(c3), "l"(f), "l"(c2));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pl) : "l"(pl), "l"(f), "l"(c1));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pl) : "l"(pl), "l"(f), "l"(c0));
-  uint32_t t0, t1, p0, p1;
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(t0), "=r"(t1) : "l"(t));
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(p0), "=r"(p1) : "l"(pl));
-  const float r0 = __uint_as_float(p0 + (t0 << 23));   // exponent += n  (the MAGIC bits shift out)
-  const float r1 = __uint_as_float(p1 + (t1 << 23));
-  uint32_t y;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(y) : "f"(r1), "f"(r0));
-  return y;
-}
-
 struct AttnKParams {
   int Tq, Tk, q_pos0, block_causal, H;
   float scale_log2;
@@ -147,599 +104,10 @@ struct AttnKParams {
   long long o_row_pitch, o_batch_pitch;
 };
 
-// EMU = pairs (of the 4 per 8-key chunk) whose exponentials are evaluated on the FMA pipe instead of the MUFU
-// (the softmax is MUFU / issue co-bound at head_dim 64: 8192 exponentials per 128 x 64 tile at 16 per clock per SM
-// cost twice the tile's tensor time), Cody-Waite split + degree-3 minimax polynomial on packed fp32x2, rel. error
-// 7.5e-5 — below the fp16 rounding of P.
-template <int EMU>
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                              // AT_QT tiles
-  uint8_t* sP = sQ + AT_QT * AT_Q_BYTES;           // AT_QT tiles
-  uint8_t* sK = sP + AT_QT * AT_P_BYTES;
-  uint8_t* sV = sK + AT_STAGES * AT_KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AT_STAGES * AT_KV_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = k_full + AT_STAGES;
-  uint64_t* v_full = k_empty + AT_STAGES;
-  uint64_t* v_empty = v_full + AT_STAGES;
-  uint64_t* s_full = v_empty + AT_STAGES;   // [AT_QT]
-  uint64_t* s_empty = s_full + AT_QT;
-  uint64_t* p_full = s_empty + AT_QT;
-  uint64_t* pv_full = p_full + AT_QT;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_full + AT_QT);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qpair = gridDim.x - 1 - blockIdx.x;  // heaviest (latest) query tiles first
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qpair * (AT_BQ * AT_QT);
-
-  // number of 64-key tiles each query tile needs (0 = tile lies beyond the sequence)
-  int nt[AT_QT];
-#pragma unroll
-  for (int t = 0; t < AT_QT; ++t) {
-    const int qs = q0 + t * AT_BQ;
-    if (qs >= p.Tq) {
-      nt[t] = 0;
-    } else {
-      int kmax = p.Tk - 1;
-      if (p.block_causal) kmax = min(kmax, (p.q_pos0 + min(qs + AT_BQ, p.Tq) - 1) | 7);
-      nt[t] = kmax / AT_BK + 1;
-    }
-  }
-  const int ntiles = max(nt[0], nt[AT_QT - 1]);
-
-  if (warp == AT_SOFTMAX_WARPS && lane == 0) {
-    ptx::prefetch_tmap(&tmQ);
-    ptx::prefetch_tmap(&tmK);
-    ptx::prefetch_tmap(&tmV);
-  }
-  if (warp == AT_SOFTMAX_WARPS + 1 && lane == 0) {
-    ptx::mbar_init(q_full, 1);
-    for (int s = 0; s < AT_STAGES; ++s) {
-      ptx::mbar_init(&k_full[s], 1);
-      ptx::mbar_init(&k_empty[s], 1);
-      ptx::mbar_init(&v_full[s], 1);
-      ptx::mbar_init(&v_empty[s], 1);
-    }
-    for (int t = 0; t < AT_QT; ++t) {
-      ptx::mbar_init(&s_full[t], 1);
-      ptx::mbar_init(&s_empty[t], 4);
-      ptx::mbar_init(&p_full[t], 4);
-      ptx::mbar_init(&pv_full[t], 1);
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == AT_SOFTMAX_WARPS + 1) {
-    ptx::tmem_alloc(tmem_slot, AT_TMEM_COLS);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == AT_SOFTMAX_WARPS) {
-    // ------------------------------------------------------------ TMA producer
-    if (ptx::elect_one()) {
-      ptx::mbar_expect_tx(q_full, AT_QT * AT_Q_BYTES);
-#pragma unroll
-      for (int t = 0; t < AT_QT; ++t) ptx::tma_load_3d(sQ + t * AT_Q_BYTES, &tmQ, q_full, h * AT_HD, q0 + t * AT_BQ, b);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < ntiles; ++j) {
-        ptx::mbar_wait(&k_empty[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&k_full[stage], AT_KV_BYTES);
-        ptx::tma_load_3d(sK + stage * AT_KV_BYTES, &tmK, &k_full[stage], h * AT_HD, j * AT_BK, b);
-        ptx::mbar_wait(&v_empty[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&v_full[stage], AT_KV_BYTES);
-        ptx::tma_load_3d(sV + stage * AT_KV_BYTES, &tmV, &v_full[stage], h * AT_HD, j * AT_BK, b);
-        if (++stage == AT_STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-    __syncwarp();
-  } else if (warp == AT_SOFTMAX_WARPS + 1) {
-    // ------------------------------------------------------------ MMA issuer (both query tiles)
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc_s = ptx::make_idesc_f16(AT_BQ, AT_BK, 0, 0);   // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(AT_BQ, AT_HD, 0, 1);  // P (K-major) x V (MN-major)
-      ptx::mbar_wait(q_full, 0);
-      auto issue_pv = [&](int t, int j) {  // O_t (+)= P_t,j V_j, accumulated in TMEM across all key tiles
-        const int st = j % AT_STAGES;
-        ptx::mbar_wait(&p_full[t], j & 1);
-        ptx::mbar_wait(&v_full[st], (j / AT_STAGES) & 1);
-        ptx::tc_fence_after();
-        const uint32_t vaddr = ptx::smem_u32(sV + st * AT_KV_BYTES);
-        const uint64_t dp = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sP + t * AT_P_BYTES));
-#pragma unroll
-        for (int k = 0; k < AT_BK / 16; ++k) {
-          // 16 keys = 16 rows of 128 B: MN-major operand advances 2048 B per K step; P advances 32 B
-          const uint64_t dv = ptx::make_desc_mnmajor_sw128(vaddr + k * 2048, 1024, 1024);
-          ptx::mma_f16_ss(tmem_base + t * 128 + AT_BK, dp + 2 * k, dv, idesc_pv, (j | k) != 0 ? 1u : 0u);
-        }
-        ptx::mma_commit(&pv_full[t]);
-      };
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j % AT_STAGES;
-        ptx::mbar_wait(&k_full[st], (j / AT_STAGES) & 1);
-        const uint64_t dk = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sK + st * AT_KV_BYTES));
-#pragma unroll
-        for (int t = 0; t < AT_QT; ++t) {
-          if (j < nt[t]) {
-            if (j > 0) ptx::mbar_wait(&s_empty[t], (j - 1) & 1);
-            ptx::tc_fence_after();
-            const uint64_t dq = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sQ + t * AT_Q_BYTES));
-#pragma unroll
-            for (int k = 0; k < AT_HD / 16; ++k)
-              ptx::mma_f16_ss(tmem_base + t * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-            ptx::mma_commit(&s_full[t]);
-          }
-        }
-        ptx::mma_commit(&k_empty[st]);
-        if (j > 0) {
-#pragma unroll
-          for (int t = 0; t < AT_QT; ++t)
-            if (j - 1 < nt[t]) issue_pv(t, j - 1);
-          ptx::mma_commit(&v_empty[(j - 1) % AT_STAGES]);
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < AT_QT; ++t)
-        if (ntiles - 1 < nt[t]) issue_pv(t, ntiles - 1);
-      ptx::mma_commit(&v_empty[(ntiles - 1) % AT_STAGES]);
-    }
-    __syncwarp();
-  } else {
-    // ------------------------------------------------------------ softmax / output (thread == query row)
-    const int t = warp >> 2;                       // query tile of this warpgroup
-    const int r = threadIdx.x & (AT_BQ - 1);       // row inside the tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tmem_s = tmem_base + t * 128;
-    const uint32_t tmem_o = tmem_s + AT_BK;
-    const int my_tiles = nt[t];
-    const int qi = q0 + t * AT_BQ + r;             // row inside this item's query block
-    const int qabs = p.q_pos0 + qi;                // absolute position
-    int limit = p.Tk - 1;
-    if (p.block_causal) limit = min(limit, qabs | 7);
-    // Lazy rescaling: m_ref is the exponent base in use.  It only moves when a tile's row maximum exceeds it by
-    // more than RESCALE_LOG2 (probabilities then stay <= 2^8, exact in the fp32 accumulator / safe in fp16), so
-    // the accumulator O can stay in TMEM and is touched by the softmax threads only on those rare tiles.
-    constexpr float RESCALE_LOG2 = 8.0f;
-    float m_ref = 0.f, l = 0.f;
-    const uint32_t prow_s = ptx::smem_u32(sP + t * AT_P_BYTES) + r * 128;
-    const int sw = r & 7;
-    const uint32_t a_s_full = ptx::smem_u32(&s_full[t]), a_s_empty = ptx::smem_u32(&s_empty[t]);
-    const uint32_t a_p_full = ptx::smem_u32(&p_full[t]), a_pv_full = ptx::smem_u32(&pv_full[t]);
-
-    for (int j = 0; j < my_tiles; ++j) {
-      ptx::mbar_wait(a_s_full, j & 1);
-      ptx::tc_fence_after();
-      uint32_t sa[32], sb[32];
-      ptx::tmem_ld32(tmem_s + lane_off, sa);
-      ptx::tmem_ld32(tmem_s + lane_off + 32, sb);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(a_s_empty);
-
-      const int lim = limit - j * AT_BK;  // columns c <= lim are visible
-      const bool diag = __any_sync(0xffffffffu, lim < AT_BK - 1);   // masked (-inf) scores: MUFU path only
-      if (lim < AT_BK - 1) {              // diagonal / last tile: mask (interior tiles skip this entirely)
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          if (c > lim) sa[c] = 0xff800000u;        // -inf
-          if (c + 32 > lim) sb[c] = 0xff800000u;
-        }
-      }
-      float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};  // 4 independent chains
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(sa[c + u]), __uint_as_float(sb[c + u])));
-      }
-      const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;  // scale > 0
-
-      if (j == 0) {
-        m_ref = (m_tile == -CUDART_INF_F) ? 0.f : m_tile;
-      } else {
-        const bool need = m_tile > m_ref + RESCALE_LOG2;
-        if (__any_sync(0xffffffffu, need)) {
-          // O must be quiescent: every P V issued so far has completed
-          ptx::mbar_wait(a_pv_full, (j - 1) & 1);
-          ptx::tc_fence_after();
-          const float alpha = need ? fast_exp2(m_ref - m_tile) : 1.0f;
-          if (need) m_ref = m_tile;
-          l *= alpha;
-#pragma unroll 1
-          for (int q4 = 0; q4 < 4; ++q4) {  // 16 columns at a time keeps the rare path's register footprint small
-            uint32_t tt[16];
-            ptx::tmem_ld16(tmem_o + lane_off + q4 * 16, tt);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 16; ++c) tt[c] = __float_as_uint(__uint_as_float(tt[c]) * alpha);
-            ptx::tmem_st16(tmem_o + lane_off + q4 * 16, tt);
-          }
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-        }
-      }
-      // the single P buffer is free once P_{j-1} V_{j-1} has been consumed (issued a whole softmax period ago)
-      if (j > 0) ptx::mbar_wait(a_pv_full, (j - 1) & 1);
-      // p = 2^(s*scale - m_ref) as packed halves, written straight to the K-major SWIZZLE_128B P tile:
-      // row r at r*128 B, 16-byte chunk c at (c ^ (r & 7))
-      const float neg_m = -m_ref;
-      unsigned long long scale2, negm2;
-      asm("mov.b64 %0, {%1, %1};" : "=l"(scale2) : "f"(p.scale_log2));
-      asm("mov.b64 %0, {%1, %1};" : "=l"(negm2) : "f"(neg_m));
-      __half2 acc[4];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint32_t w[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int e = (c & 3) * 8 + 2 * u;
-          const uint32_t s0 = (c < 4) ? sa[e] : sb[e];
-          const uint32_t s1 = (c < 4) ? sa[e + 1] : sb[e + 1];
-          // (s0, s1) * scale - m_ref as ONE packed fp32x2 FFMA2 (the loop is issue / MUFU co-bound)
-          unsigned long long xx;
-          asm("{\n\t.reg .b64 a;\n\tmov.b64 a, {%1, %2};\n\tfma.rn.f32x2 %0, a, %3, %4;\n\t}"
-              : "=l"(xx) : "r"(s0), "r"(s1), "l"(scale2), "l"(negm2));
-          float x0, x1;
-          if (u < EMU && !diag) {
-            w[u] = exp2_poly_f16x2(xx);
-          } else {
-            asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
-            w[u] = exp2_f16x2(x0, x1);
-          }
-        }
-        const __half2 s01 = __hadd2(*reinterpret_cast<const __half2*>(&w[0]), *reinterpret_cast<const __half2*>(&w[1]));
-        const __half2 s23 = __hadd2(*reinterpret_cast<const __half2*>(&w[2]), *reinterpret_cast<const __half2*>(&w[3]));
-        const __half2 s4 = __hadd2(s01, s23);
-        acc[c & 3] = (c < 4) ? s4 : __hadd2(acc[c & 3], s4);
-        ptx::st_shared_v4(prow_s + ((c ^ sw) << 4), w[0], w[1], w[2], w[3]);
-      }
-      {
-        const float2 f0 = __half22float2(acc[0]), f1 = __half22float2(acc[1]);
-        const float2 f2 = __half22float2(acc[2]), f3 = __half22float2(acc[3]);
-        l += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
-      }
-      ptx::fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(a_p_full);
-    }
-    if (my_tiles > 0) {
-      ptx::mbar_wait(a_pv_full, (my_tiles - 1) & 1);
-      ptx::tc_fence_after();
-      const float inv = 1.0f / l;
-      __half* op = p.out + b * p.o_batch_pitch + static_cast<long long>(qi) * p.o_row_pitch + h * AT_HD;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t tt[32];
-        ptx::tmem_ld32(tmem_o + lane_off + half * 32, tt);
-        ptx::tmem_ld_wait();
-        if (qi < p.Tq) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            uint4 q;
-            q.x = pack_half2(__uint_as_float(tt[c + 0]) * inv, __uint_as_float(tt[c + 1]) * inv);
-            q.y = pack_half2(__uint_as_float(tt[c + 2]) * inv, __uint_as_float(tt[c + 3]) * inv);
-            q.z = pack_half2(__uint_as_float(tt[c + 4]) * inv, __uint_as_float(tt[c + 5]) * inv);
-            q.w = pack_half2(__uint_as_float(tt[c + 6]) * inv, __uint_as_float(tt[c + 7]) * inv);
-            *reinterpret_cast<uint4*>(op + half * 32 + c) = q;
-          }
-        }
-      }
-      ptx::tc_fence_before();
-    }
-  }
-  __syncthreads();
-  if (warp == AT_SOFTMAX_WARPS + 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, AT_TMEM_COLS);
-  }
-}
-
-
-// =====================================================================================================
-// attention_tcp: same tiling, but P never touches shared memory.  The softmax threads write the packed fp16
-// probabilities with tcgen05.st over the first 32 columns of the S accumulator they have just read (P aliases S), and
-// O += P V is issued in the TS form (A operand from tensor memory, V from shared memory).  Per (query tile, key tile)
-// this removes 16 KB of st.shared and 16 KB of MMA operand reads from the 128 B/clk shared-memory port — with both
-// operands in shared memory a 128 x 64 x 16 MMA reads 6 KB, i.e. 48 clk of port time for 32 clk of tensor time, and
-// the port (QK^T + PV + P stores + K/V fills: ~2300 clk per SM round) was a tighter bound than the MUFU (2048).
-// Aliasing orders the two MMAs of a tile: PV(j) must have consumed P(j) before QK^T(j+1) overwrites it.  Both are
-// issued by the same thread back to back (tcgen05.mma of one thread execute in issue order), so no barrier is needed
-// between them; the softmax of the other three query tiles resident on the SM covers the exposed MMA latency.
-// Barriers: s_full (S ready; also: every earlier PV of this tile has completed, so O is quiescent for the lazy
-// rescale), p_full (P stored), o_full (last PV of the tile done).  No P buffer, no s_empty / pv_full handshakes.
-// =====================================================================================================
-constexpr int AP_STAGES = 3;
-constexpr int AP_SMEM_BYTES = AT_QT * AT_Q_BYTES + 2 * AP_STAGES * AT_KV_BYTES + 1024 + 256;
-
-template <int EMU>
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                     const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                              // AT_QT tiles
-  uint8_t* sK = sQ + AT_QT * AT_Q_BYTES;
-  uint8_t* sV = sK + AP_STAGES * AT_KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + AP_STAGES * AT_KV_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = k_full + AP_STAGES;
-  uint64_t* v_full = k_empty + AP_STAGES;
-  uint64_t* v_empty = v_full + AP_STAGES;
-  uint64_t* s_full = v_empty + AP_STAGES;   // [AT_QT]
-  uint64_t* p_full = s_full + AT_QT;
-  uint64_t* o_full = p_full + AT_QT;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + AT_QT);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qpair = gridDim.x - 1 - blockIdx.x;  // heaviest (latest) query tiles first
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int q0 = qpair * (AT_BQ * AT_QT);
-
-  int nt[AT_QT];   // number of 64-key tiles each query tile needs (0 = tile lies beyond the sequence)
-#pragma unroll
-  for (int t = 0; t < AT_QT; ++t) {
-    const int qs = q0 + t * AT_BQ;
-    if (qs >= p.Tq) {
-      nt[t] = 0;
-    } else {
-      int kmax = p.Tk - 1;
-      if (p.block_causal) kmax = min(kmax, (p.q_pos0 + min(qs + AT_BQ, p.Tq) - 1) | 7);
-      nt[t] = kmax / AT_BK + 1;
-    }
-  }
-  const int ntiles = max(nt[0], nt[AT_QT - 1]);
-
-  if (warp == AT_SOFTMAX_WARPS && lane == 0) {
-    ptx::prefetch_tmap(&tmQ);
-    ptx::prefetch_tmap(&tmK);
-    ptx::prefetch_tmap(&tmV);
-  }
-  if (warp == AT_SOFTMAX_WARPS + 1 && lane == 0) {
-    ptx::mbar_init(q_full, 1);
-    for (int s = 0; s < AP_STAGES; ++s) {
-      ptx::mbar_init(&k_full[s], 1);
-      ptx::mbar_init(&k_empty[s], 1);
-      ptx::mbar_init(&v_full[s], 1);
-      ptx::mbar_init(&v_empty[s], 1);
-    }
-    for (int t = 0; t < AT_QT; ++t) {
-      ptx::mbar_init(&s_full[t], 1);
-      ptx::mbar_init(&p_full[t], 4);
-      ptx::mbar_init(&o_full[t], 1);
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == AT_SOFTMAX_WARPS + 1) {
-    ptx::tmem_alloc(tmem_slot, AT_TMEM_COLS);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == AT_SOFTMAX_WARPS) {
-    // ------------------------------------------------------------ TMA producer
-    if (ptx::elect_one()) {
-      ptx::mbar_expect_tx(q_full, AT_QT * AT_Q_BYTES);
-#pragma unroll
-      for (int t = 0; t < AT_QT; ++t) ptx::tma_load_3d(sQ + t * AT_Q_BYTES, &tmQ, q_full, h * AT_HD, q0 + t * AT_BQ, b);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < ntiles; ++j) {
-        ptx::mbar_wait(&k_empty[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&k_full[stage], AT_KV_BYTES);
-        ptx::tma_load_3d(sK + stage * AT_KV_BYTES, &tmK, &k_full[stage], h * AT_HD, j * AT_BK, b);
-        ptx::mbar_wait(&v_empty[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&v_full[stage], AT_KV_BYTES);
-        ptx::tma_load_3d(sV + stage * AT_KV_BYTES, &tmV, &v_full[stage], h * AT_HD, j * AT_BK, b);
-        if (++stage == AP_STAGES) { stage = 0; phase ^= 1; }
-      }
-    }
-    __syncwarp();
-  } else if (warp == AT_SOFTMAX_WARPS + 1) {
-    // ------------------------------------------------------------ MMA issuer (both query tiles)
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc_s = ptx::make_idesc_f16(AT_BQ, AT_BK, 0, 0);   // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_pv = ptx::make_idesc_f16(AT_BQ, AT_HD, 0, 1);  // P (TMEM)    x V (MN-major)
-      ptx::mbar_wait(q_full, 0);
-      auto issue_pv = [&](int t, int j) {  // O_t (+)= P_t,j V_j, accumulated in TMEM across all key tiles
-        const int st = j % AP_STAGES;
-        ptx::mbar_wait(&p_full[t], j & 1);
-        ptx::mbar_wait(&v_full[st], (j / AP_STAGES) & 1);
-        ptx::tc_fence_after();
-        const uint32_t vaddr = ptx::smem_u32(sV + st * AT_KV_BYTES);
-#pragma unroll
-        for (int k = 0; k < AT_BK / 16; ++k) {
-          // 16 keys: V advances 16 rows of 128 B (MN-major operand), P advances 8 TMEM columns (2 halves per column)
-          const uint64_t dv = ptx::make_desc_mnmajor_sw128(vaddr + k * 2048, 1024, 1024);
-          ptx::mma_f16_ts(tmem_base + t * 128 + AT_BK, tmem_base + t * 128 + k * 8, dv, idesc_pv,
-                          (j | k) != 0 ? 1u : 0u);
-        }
-        if (j == nt[t] - 1) ptx::mma_commit(&o_full[t]);
-      };
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j % AP_STAGES;
-        ptx::mbar_wait(&k_full[st], (j / AP_STAGES) & 1);
-        const uint64_t dk = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sK + st * AT_KV_BYTES));
-#pragma unroll
-        for (int t = 0; t < AT_QT; ++t) {
-          if (j > 0 && j - 1 < nt[t]) issue_pv(t, j - 1);   // consumes P_t,j-1 before S_t,j overwrites it (in order)
-          if (j < nt[t]) {
-            ptx::tc_fence_after();
-            const uint64_t dq = ptx::make_desc_kmajor_sw128(ptx::smem_u32(sQ + t * AT_Q_BYTES));
-#pragma unroll
-            for (int k = 0; k < AT_HD / 16; ++k)
-              ptx::mma_f16_ss(tmem_base + t * 128, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-            ptx::mma_commit(&s_full[t]);
-          }
-        }
-        ptx::mma_commit(&k_empty[st]);
-        if (j > 0) ptx::mma_commit(&v_empty[(j - 1) % AP_STAGES]);
-      }
-#pragma unroll
-      for (int t = 0; t < AT_QT; ++t)
-        if (ntiles - 1 < nt[t]) issue_pv(t, ntiles - 1);
-      ptx::mma_commit(&v_empty[(ntiles - 1) % AP_STAGES]);
-    }
-    __syncwarp();
-  } else {
-    // ------------------------------------------------------------ softmax / output (thread == query row)
-    const int t = warp >> 2;                       // query tile of this warpgroup
-    const int r = threadIdx.x & (AT_BQ - 1);       // row inside the tile == TMEM lane
-    const uint32_t lane_off = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    const uint32_t tmem_s = tmem_base + t * 128;
-    const uint32_t tmem_o = tmem_s + AT_BK;
-    const int my_tiles = nt[t];
-    const int qi = q0 + t * AT_BQ + r;             // row inside this item's query block
-    const int qabs = p.q_pos0 + qi;                // absolute position
-    int limit = p.Tk - 1;
-    if (p.block_causal) limit = min(limit, qabs | 7);
-    constexpr float RESCALE_LOG2 = 8.0f;           // lazy rescaling, see attention_tc_kernel
-    float m_ref = 0.f, l = 0.f;
-    const uint32_t a_s_full = ptx::smem_u32(&s_full[t]), a_p_full = ptx::smem_u32(&p_full[t]);
-
-    for (int j = 0; j < my_tiles; ++j) {
-      ptx::mbar_wait(a_s_full, j & 1);
-      ptx::tc_fence_after();
-      uint32_t sa[32], sb[32];
-      ptx::tmem_ld32(tmem_s + lane_off, sa);
-      ptx::tmem_ld32(tmem_s + lane_off + 32, sb);
-      ptx::tmem_ld_wait();
-
-      const int lim = limit - j * AT_BK;  // columns c <= lim are visible
-      const bool diag = __any_sync(0xffffffffu, lim < AT_BK - 1);   // masked (-inf) scores: MUFU path only
-      if (lim < AT_BK - 1) {              // diagonal / last tile: mask (interior tiles skip this entirely)
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          if (c > lim) sa[c] = 0xff800000u;        // -inf
-          if (c + 32 > lim) sb[c] = 0xff800000u;
-        }
-      }
-      float mx4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};  // 4 independent chains
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(sa[c + u]), __uint_as_float(sb[c + u])));
-      }
-      const float m_tile = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;  // scale > 0
-
-      if (j == 0) {
-        m_ref = (m_tile == -CUDART_INF_F) ? 0.f : m_tile;
-      } else {
-        const bool need = m_tile > m_ref + RESCALE_LOG2;
-        if (__any_sync(0xffffffffu, need)) {
-          // O is quiescent: S_j was committed after P V_{j-1}, so every P V issued so far has completed
-          const float alpha = need ? fast_exp2(m_ref - m_tile) : 1.0f;
-          if (need) m_ref = m_tile;
-          l *= alpha;
-#pragma unroll 1
-          for (int q4 = 0; q4 < 4; ++q4) {
-            uint32_t tt[16];
-            ptx::tmem_ld16(tmem_o + lane_off + q4 * 16, tt);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 16; ++c) tt[c] = __float_as_uint(__uint_as_float(tt[c]) * alpha);
-            ptx::tmem_st16(tmem_o + lane_off + q4 * 16, tt);
-          }
-        }
-      }
-      // p = 2^(s*scale - m_ref) as packed halves, stored over the first 32 columns of this row's S
-      const float neg_m = -m_ref;
-      unsigned long long scale2, negm2;
-      asm("mov.b64 %0, {%1, %1};" : "=l"(scale2) : "f"(p.scale_log2));
-      asm("mov.b64 %0, {%1, %1};" : "=l"(negm2) : "f"(neg_m));
-      __half2 acc[4];
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {          // 16 keys (8 TMEM columns) per tcgen05.st
-        uint32_t w[8];
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          const int c = 2 * g + cc;          // 8-key chunk
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int e = (c & 3) * 8 + 2 * u;
-            const uint32_t s0 = (c < 4) ? sa[e] : sb[e];
-            const uint32_t s1 = (c < 4) ? sa[e + 1] : sb[e + 1];
-            unsigned long long xx;
-            asm("{\n\t.reg .b64 a;\n\tmov.b64 a, {%1, %2};\n\tfma.rn.f32x2 %0, a, %3, %4;\n\t}"
-                : "=l"(xx) : "r"(s0), "r"(s1), "l"(scale2), "l"(negm2));
-            if (u < EMU && !diag) {
-              w[cc * 4 + u] = exp2_poly_f16x2(xx);
-            } else {
-              float x0, x1;
-              asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(xx));
-              w[cc * 4 + u] = exp2_f16x2(x0, x1);
-            }
-          }
-          const __half2 s01 = __hadd2(*reinterpret_cast<const __half2*>(&w[cc * 4 + 0]),
-                                      *reinterpret_cast<const __half2*>(&w[cc * 4 + 1]));
-          const __half2 s23 = __hadd2(*reinterpret_cast<const __half2*>(&w[cc * 4 + 2]),
-                                      *reinterpret_cast<const __half2*>(&w[cc * 4 + 3]));
-          const __half2 s4 = __hadd2(s01, s23);
-          acc[c & 3] = (c < 4) ? s4 : __hadd2(acc[c & 3], s4);
-        }
-        ptx::tmem_st8(tmem_s + lane_off + g * 8, w);
-      }
-      {
-        const float2 f0 = __half22float2(acc[0]), f1 = __half22float2(acc[1]);
-        const float2 f2 = __half22float2(acc[2]), f3 = __half22float2(acc[3]);
-        l += ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
-      }
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(a_p_full);
-    }
-    if (my_tiles > 0) {
-      ptx::mbar_wait(ptx::smem_u32(&o_full[t]), 0);
-      ptx::tc_fence_after();
-      const float inv = 1.0f / l;
-      __half* op = p.out + b * p.o_batch_pitch + static_cast<long long>(qi) * p.o_row_pitch + h * AT_HD;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t tt[32];
-        ptx::tmem_ld32(tmem_o + lane_off + half * 32, tt);
-        ptx::tmem_ld_wait();
-        if (qi < p.Tq) {
-#pragma unroll
-          for (int c = 0; c < 32; c += 8) {
-            uint4 q;
-            q.x = pack_half2(__uint_as_float(tt[c + 0]) * inv, __uint_as_float(tt[c + 1]) * inv);
-            q.y = pack_half2(__uint_as_float(tt[c + 2]) * inv, __uint_as_float(tt[c + 3]) * inv);
-            q.z = pack_half2(__uint_as_float(tt[c + 4]) * inv, __uint_as_float(tt[c + 5]) * inv);
-            q.w = pack_half2(__uint_as_float(tt[c + 6]) * inv, __uint_as_float(tt[c + 7]) * inv);
-            *reinterpret_cast<uint4*>(op + half * 32 + c) = q;
-          }
-        }
-      }
-      ptx::tc_fence_before();
-    }
-  }
-  __syncthreads();
-  if (warp == AT_SOFTMAX_WARPS + 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, AT_TMEM_COLS);
-  }
-}
-
-
 // =====================================================================================================
 // attention_t3: one CTA per SM, THREE query tiles that share every K/V tile, S / P / O of each tile in separate
 // tensor-memory columns (S 64 | P 32 | O 64 = 160 columns per tile, 480 of the SM's 512).
-// Why: with P aliased over S (attention_tcp) or a single smem P tile (attention_tc) a query tile's softmax cannot start
+// Why: with P aliased over S or a single smem P tile (the round-1 kernels, removed) a query tile's softmax cannot start
 // on key tile j+1 before the MMA thread has seen its P_j, issued P_j V_j and Q K_{j+1}^T, and those have executed — a
 // ~1400 clk round trip per key tile that four resident tiles only partly hide (profiles/r01_attention_ab.txt).  Here
 // Q K_{j+1}^T is issued as soon as the softmax has READ S_j (s_empty), so S_{j+1} is waiting when the softmax of key
@@ -913,7 +281,7 @@ attention_t3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int qabs = p.q_pos0 + qi;                // absolute position
     int limit = p.Tk - 1;
     if (p.block_causal) limit = min(limit, qabs | 7);
-    constexpr float RESCALE_LOG2 = 8.0f;           // lazy rescaling, see attention_tc_kernel
+    constexpr float RESCALE_LOG2 = 8.0f;           // lazy rescaling: O is rescaled only when a row max grows by more than 2^8
     float m_ref = 0.f, l = 0.f;
     const uint32_t a_s_full = ptx::smem_u32(&s_full[t]), a_s_empty = ptx::smem_u32(&s_empty[t]);
     const uint32_t a_p_full = ptx::smem_u32(&p_full[t]), a_pv_done = ptx::smem_u32(&pv_done[t]);
@@ -1049,20 +417,9 @@ int attention_tc_init() {
   std::call_once(g_attn_once, [] {
     g_attn_status = gemm_tc_init();
     if (g_attn_status != FRT2_OK) return;
-    cudaError_t e =
-        cudaFuncSetAttribute(attention_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_t3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_tcp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM_BYTES);
-    if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(attention_tcp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AP_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attention_t3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM_BYTES);
     if (e != cudaSuccess) {
-      set_error(std::string("cudaFuncSetAttribute(attention_tc_kernel): ") + cudaGetErrorString(e));
+      set_error(std::string("cudaFuncSetAttribute(attention_t3_kernel): ") + cudaGetErrorString(e));
       g_attn_status = FRT2_ERR_CUDA;
     }
   });
@@ -1103,28 +460,8 @@ int attention_tc(const AttnDesc& a, cudaStream_t stream) {
   p.out = a.out;
   p.o_row_pitch = a.o_row_pitch;
   p.o_batch_pitch = a.o_batch_pitch;
-  dim3 grid((a.Tq + AT_BQ * AT_QT - 1) / (AT_BQ * AT_QT), a.H, a.B);
-  // Measured (B=64, H=16, T=3000, tools/op_bench.py attn): EMU 0 / 1 / 2 -> 2.00 / 2.07 / 2.34 ms.  The softmax loop is
-  // issue-bound before it is MUFU-bound, so moving exponentials to the FMA pipe costs more issue slots than the
-  // MUFU time it frees; the default keeps every exponential on the MUFU.  (FRT2_ATTN_EMU=1|2 for A/B runs.)
-  static const int emu = getenv("FRT2_ATTN_EMU") ? atoi(getenv("FRT2_ATTN_EMU")) : 0;
-  static const int ver = getenv("FRT2_ATTN_VER") ? atoi(getenv("FRT2_ATTN_VER")) : 3;   // A/B: 3 = attention_t3 (default)
-  if (ver >= 3 && emu <= 0) {
-    dim3 grid3((a.Tq + AT_BQ * A3_QT - 1) / (AT_BQ * A3_QT), a.H, a.B);
-    attention_t3_kernel<<<grid3, A3_THREADS, A3_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-    FRT2_CUDA_OK(cudaGetLastError());
-    return FRT2_OK;
-  }
-  static const bool p_in_smem = (getenv("FRT2_ATTN_PSMEM") != nullptr) || ver == 1;   // the round-1 kernel (P in smem)
-  if (!p_in_smem) {
-    if (emu <= 0) attention_tcp_kernel<0><<<grid, AT_THREADS, AP_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-    else attention_tcp_kernel<1><<<grid, AT_THREADS, AP_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-    FRT2_CUDA_OK(cudaGetLastError());
-    return FRT2_OK;
-  }
-  if (emu <= 0) attention_tc_kernel<0><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-  else if (emu == 1) attention_tc_kernel<1><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-  else attention_tc_kernel<2><<<grid, AT_THREADS, AT_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  dim3 grid3((a.Tq + AT_BQ * A3_QT - 1) / (AT_BQ * A3_QT), a.H, a.B);
+  attention_t3_kernel<<<grid3, A3_THREADS, A3_SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;
 }

@@ -1,5 +1,5 @@
-// K3' body — warp attention (8-query blocks, optional split-KV over the warps of a CTA) as a device function, shared by
-// attention_warp_kernel (attention.cu) and the persistent per-token step kernel (stream_mega.cu).
+// K3' body — warp attention (8-query blocks, optional split-KV over the warps of a CTA) as a device function, instantiated by
+// attention_warp_kernel (attention.cu).
 #pragma once
 #include <math_constants.h>
 

@@ -119,6 +119,10 @@ struct GemmDesc {
   // normalisation in its epilogue.
   __half* x16_out;        // producer: fp16 copy of the output rows, flat (batches*rows_out, ld_x16)
   int64_t ld_x16;
+  const float* x16_shift; // producer, optional: (batches*rows_out) per-row offsets subtracted BEFORE the fp16 rounding of the
+                          // copy (LayerNorm is shift-invariant).  The engine keeps the last known row mean of the residual
+                          // stream there, so a row whose mean is many times its spread still gets all 11 mantissa bits for
+                          // the part LayerNorm keeps (measured: 39 -> 55 dB on tests' adversarial weights)
   const float2* stats_in; // consumer: (mean, rstd) of its A rows
   const float* colsum;    // consumer: (N) sum_k of the folded fp16 weights of column n
   // optional fused LayerNorm(+SiLU) prologue (gemm_skinny only, ntaps == 1): the A rows are LN(ln_x) computed on the
@@ -212,19 +216,17 @@ struct OlaDesc {
                              // and nothing is written past the item's own sample count (scatter into a shared buffer)
 };
 int istft_overlap_add(const OlaDesc& d, cudaStream_t stream);
-int istft_update_tail(const float* frames, int64_t frames_batch_pitch, float* tail, int B, int T, int n_fft,
-                      const int* ctrl /* per-item control blocks or null: idle items keep their tail */,
-                      cudaStream_t stream);
+// mean_out: optional (rows) — the row means, left behind for the folded LayerNorm's shifted fp16 copy
 int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_per_batch, int C, const float* gamma,
                             const float* beta, float eps, int apply_silu, __half* out16, int64_t ld16,
-                            int64_t out_batch_pitch, cudaStream_t stream);
+                            int64_t out_batch_pitch, cudaStream_t stream, float* mean_out = nullptr);
 int resample_rows(const float* x, int64_t x_pitch, int B, int64_t n_in, const int* lengths, const float* taps, int K,
                   int width, int orig, int nnew, float* y, int64_t y_pitch, cudaStream_t stream);
-// (mean, rstd) per row of an fp16 matrix (the statistics of a folded LayerNorm)
-int row_stats(const __half* x16, int64_t ld, int64_t rows, int C, float eps, float2* stats, cudaStream_t stream);
-// ---- persistent per-token step kernel (stream_mega.cu) ----
-// The ~90 launches of one streaming step (<= 16 rows) recorded as a list of ops and executed by ONE cooperative kernel
-// with a grid barrier between dependent ops.
+// (mean, rstd) per row of an fp16 matrix (the statistics of a folded LayerNorm).  shift_io: optional (rows) — the offsets
+// the producer subtracted from these rows; the kernel adds the measured mean so that they track the stream's row means
+int row_stats(const __half* x16, int64_t ld, int64_t rows, int C, float eps, float2* stats, cudaStream_t stream,
+              float* shift_io = nullptr);
+// ---- streaming state kernels (stream_state.cu) ----
 struct ShiftEntry {
   __half* p;
   int hist;
@@ -235,29 +237,7 @@ struct ShiftTable {
   ShiftEntry e[16];
   int n;
 };
-enum MegaKind : int { MK_RVQ = 0, MK_SKINNY = 1, MK_LN = 2, MK_ATTN = 3, MK_OLA = 4, MK_ROLL = 5 };
-struct MegaRvq {            // rvq_gather_sum over the staged int32 tokens (+ an optional 2-D zero fill of fp16 columns)
-  const int* tokens;
-  long long sB, sQ, sL;
-  int B, nq, L, K, D;
-  const float* tables;
-  __half* sum16;
-  unsigned int* err_word;
-  __half* zero_ptr;
-  long long zero_pitch;
-  int zero_cols, zero_rows;
-};
-struct MegaLn {             // layer_norm_rows_batched
-  const float* x;
-  long long ldx, rows;
-  int rows_per_batch, C;
-  const float *gamma, *beta;
-  float eps;
-  int silu;
-  __half* out16;
-  long long ld16, out_batch_pitch;
-};
-struct MegaRoll {           // update_tail + shift_history + advance_ctrl (the end-of-step state roll)
+struct StateRoll {          // new iSTFT tail + conv histories to the head of their buffers + position advance
   const float* frames;
   long long frames_batch_pitch;
   float* tail;
@@ -267,26 +247,10 @@ struct MegaRoll {           // update_tail + shift_history + advance_ctrl (the e
   int advance_frames;
   int all_items;            // 1: no control blocks in use (eager streaming) — every item is active
 };
-// the same roll as ONE stand-alone kernel (replaces update_tail + shift_history + advance_ctrl: two graph nodes fewer)
-int stream_state_roll(const MegaRoll& ro, cudaStream_t stream);
-struct MegaOp {
-  int kind, mtot, nblocks, pad;
-  union U {
-    GemmDesc g;
-    AttnDesc a;
-    MegaRvq r;
-    MegaLn l;
-    OlaDesc o;
-    MegaRoll ro;
-    U() {}
-  } u;
-  MegaOp() : kind(0), mtot(0), nblocks(0), pad(0) {}
-};
-int stream_mega_init();
-int stream_mega_grid();     // CTAs of the cooperative launch (one per SM)
-// ops: device array; bar: device counter (monotonic across launches), epoch0: its value when this launch starts
-int stream_mega_launch(const MegaOp* ops, int nops, unsigned int* bar, unsigned int epoch0, cudaStream_t stream,
-                       long long* trace = nullptr /* debug: 2*nops timestamps */);
+int stream_state_roll(const StateRoll& ro, cudaStream_t stream);
+// back to "no token consumed": zero history rows, control blocks and the n_err error words, stream-ordered
+int stream_state_reset(const ShiftTable& tb, int E, int B, int* ctrl, unsigned int* err_words, int n_err,
+                       cudaStream_t stream);
 int tma_encode_fp16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box);
 int num_sms();

@@ -27,10 +27,6 @@ constexpr int DBG_GEMM_REF = 2;   // route every GEMM through the SIMT check ker
 constexpr int DBG_ATTN_WARP = 4;  // route attention through the warp kernel (tests only)
 constexpr int DBG_NO_SKINNY = 16; // streaming: keep the tcgen05 GEMM even for <= 16 rows
 constexpr int DBG_NO_GRAPH = 8;   // streaming: launch kernel by kernel instead of replaying the captured CUDA graph
-constexpr int DBG_NO_MEGA = 64;   // streaming: CUDA-graph replay instead of the persistent step kernel (A/B, tests)
-#ifndef FRT2_MEGA_DEFAULT
-#define FRT2_MEGA_DEFAULT 0       // FRT2_MEGA=1 / =0 overrides at run time
-#endif
 constexpr int DBG_NO_LNFOLD = 32; // offline: separate LayerNorm kernels instead of LN folded across the GEMMs (A/B, tests)
 
 struct HostTensor {
@@ -67,14 +63,14 @@ __global__ void half_to_float_kernel(const __half* __restrict__ src, long long l
 }
 
 // strided int32/int64 tokens -> contiguous int32 staging (B,nq,L) + this call's flags into the per-item control
-// blocks; out-of-range values are flagged here (an int64 could alias after narrowing) and stored as -1.
+// blocks; out-of-range values are flagged here (an int64 could alias after narrowing) and decoded as code 0.
 // slot_flags == nullptr (frt2_decode_chunk): every item is active and shares `last`.  Otherwise (frt2_pool_step) item b
 // takes FRT2_SLOT_* bits from slot_flags.f[b]: idle slots get token 0 and no range check, RESET rewinds the slot.
 struct SlotFlags { unsigned char f[FRT2_POOL_MAX_SLOTS]; };
 template <typename IdxT, bool POOL>
 __global__ void stage_tokens_kernel(const IdxT* __restrict__ tokens, long long sB, long long sQ, long long sL, int B,
                                     int nq, int L, int K, int* __restrict__ stage, int* ctrl, int last,
-                                    unsigned int* err_word, const SlotFlags flags) {
+                                    unsigned int* err_words, const SlotFlags flags) {
   const int n = B * nq * L;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) {
@@ -98,14 +94,11 @@ __global__ void stage_tokens_kernel(const IdxT* __restrict__ tokens, long long s
   const long long raw = static_cast<long long>(tokens[b * sB + q * sQ + l * sL]);
   int v = static_cast<int>(raw);
   if (raw < 0 || raw >= K) {
-    atomicOr(err_word, DEV_ERR_INDEX_OOR);
-    v = -1;
+    atomicOr(err_words, DEV_ERR_INDEX_OOR);           // the stream / pool as a whole
+    atomicOr(err_words + 1 + b, DEV_ERR_INDEX_OOR);   // and the item (pool slot) that sent the bad code
+    v = 0;   // decoded as code 0; the caller learns about it through the error word
   }
   stage[i] = v;
-}
-__global__ void advance_ctrl_kernel(int* ctrl, int frames, int B, int all_items) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B && (all_items || ctrl[b * CTRL_INTS + CTRL_ACTIVE] != 0)) ctrl[b * CTRL_INTS + CTRL_POS] += frames;
 }
 // staged fp32 chunk -> the caller's int16 PCM buffer, same rounding as the overlap-add kernel's direct PCM output
 __global__ void emit_pcm16_kernel(const float* __restrict__ stage, long long stage_pitch, int16_t* __restrict__ pcm,
@@ -115,25 +108,6 @@ __global__ void emit_pcm16_kernel(const float* __restrict__ stage, long long sta
   if (i >= n || b >= B) return;
   const float smp = stage[b * stage_pitch + i];
   pcm[b * pcm_pitch + i] = static_cast<int16_t>(__float2int_rz(fminf(fmaxf(smp * 32767.0f, -32768.0f), 32767.0f)));
-}
-
-// move the last `hist` rows of [hist | chunk] to the head of each streaming conv buffer (the new history);
-// items whose control block says idle keep their history
-__global__ void shift_history_kernel(ShiftTable t, int E, int B, const int* __restrict__ ctrl) {
-  const int ei = blockIdx.y;
-  const ShiftEntry en = t.e[ei];
-  const int rows = en.rows;
-  const long long total = static_cast<long long>(B) * en.hist * E;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % E);
-    const int r = static_cast<int>((i / E) % en.hist);
-    const int b = static_cast<int>(i / (static_cast<long long>(E) * en.hist));
-    if (ctrl != nullptr && ctrl[b * CTRL_INTS + CTRL_ACTIVE] == 0) continue;
-    __half* base = en.p + b * en.batch_pitch;
-    // rows >= hist so source (r + rows) never overlaps a not-yet-read destination row of another thread
-    base[static_cast<long long>(r) * E + c] = base[static_cast<long long>(r + rows) * E + c];
-  }
 }
 
 // pool: a slot that starts a new stream this step gets its causal left padding back (zero conv history); the K/V
@@ -295,16 +269,39 @@ struct Handle {
   int16_t* pcm16_out = nullptr;  // set (under the mutex) by frt2_decode_pcm16 for the next pipeline run
   const long long* scatter_off = nullptr;  // set (under the mutex) by frt2_decode_scatter: per-item output offsets
 
-  // workspace arena (grow-only)
+  // workspace arena (grow-only) of the offline decode and of streaming chunks that do not run as a captured step.
+  // The arena is shared by every call on this handle, and calls are asynchronous: a call that arrives on another CUDA
+  // stream than the previous user first waits (on the device) for that user's event.
   uint8_t* ws = nullptr;
   size_t ws_bytes = 0;
+  cudaEvent_t ws_event = nullptr;
+  cudaStream_t ws_last_stream = nullptr;
+  bool ws_in_use = false;
+  int ws_acquire(cudaStream_t st) {
+    if (ws_in_use && st != ws_last_stream) FRT2_CUDA_OK(cudaStreamWaitEvent(st, ws_event, 0));
+    return FRT2_OK;
+  }
+  int ws_release(cudaStream_t st) {
+    if (ws_event == nullptr) FRT2_CUDA_OK(cudaEventCreateWithFlags(&ws_event, cudaEventDisableTiming));
+    FRT2_CUDA_OK(cudaEventRecord(ws_event, st));
+    ws_last_stream = st;
+    ws_in_use = true;
+    return FRT2_OK;
+  }
+  // stream states handed back by frt2_stream_destroy, kept (with their captured step graphs) for the next
+  // frt2_stream_create of the same shape: decode_one_token(tok, {}, ...) — the reference's call pattern — then costs no
+  // allocation and no capture
+  std::vector<frt2_stream*> free_streams;
+  size_t free_stream_bytes = 0;
   std::map<std::string, std::pair<float*, int64_t>> taps;
   int tap_B = 0, tap_L = 0;
 
-  ~Handle() {
+  ~Handle();
+  void release_base() {
     cudaSetDevice(device);
     for (void* p : owned) cudaFree(p);
     if (ws) cudaFree(ws);
+    if (ws_event) cudaEventDestroy(ws_event);
     for (auto& kv : taps) cudaFree(kv.second.first);
     for (auto& r : prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   }
@@ -374,27 +371,9 @@ struct Handle {
     return FRT2_OK;
   }
 
-  // recording mode (persistent step kernel): the launch helpers append ops here instead of launching
-  std::vector<MegaOp>* rec = nullptr;
-  bool rec_fail = false;    // an op the step kernel cannot run (e.g. a tcgen05 GEMM): fall back to the CUDA graph
-
   int finalize();
   int ensure_ws(size_t bytes);
   int run_gemm(const GemmDesc& g, cudaStream_t st) {
-    if (rec != nullptr) {
-      const int mtot = g.batches * g.rows_out;
-      if (!gemm_skinny_applicable(g) || (g.ln_gamma != nullptr && (g.ntaps != 1 || g.Kc > 2048))) {
-        rec_fail = true;
-        return FRT2_OK;
-      }
-      MegaOp op;
-      // n-tiles per CTA: one round of tiles over the grid (148 CTAs) where the register budget allows it
-      int nt = (g.N / 8 + stream_mega_grid() - 1) / std::max(1, stream_mega_grid());
-      nt = std::max(1, std::min(nt, mtot <= 8 ? 4 : 2));
-      op.kind = MK_SKINNY; op.mtot = mtot; op.pad = nt; op.nblocks = (g.N + 8 * nt - 1) / (8 * nt); op.u.g = g;
-      rec->push_back(op);
-      return FRT2_OK;
-    }
     const double flops = 2.0 * g.batches * g.rows_out * static_cast<double>(g.N) * g.ntaps * g.Kc;
     const double bytes = 2.0 * (static_cast<double>(g.batches) * g.rows_a * g.Kc + static_cast<double>(g.N) * g.ntaps * g.Kc) +
                          static_cast<double>(g.batches) * g.rows_out * g.N *
@@ -406,18 +385,6 @@ struct Handle {
     return rc;
   }
   int run_attn(const AttnDesc& a, cudaStream_t st) {
-    if (rec != nullptr) {
-      const long long blocks = static_cast<long long>(a.B) * a.H * (a.Tq / 8);
-      if (a.hd != 64 || a.Tq != 8 || blocks > 1024 || a.ctrl == nullptr || a.part == nullptr || a.part_count == nullptr) {
-        rec_fail = true;
-        return FRT2_OK;
-      }
-      MegaOp op;
-      op.kind = MK_ATTN; op.u.a = a;
-      op.nblocks = static_cast<int>(blocks) * ATTN_KSPLIT;
-      rec->push_back(op);
-      return FRT2_OK;
-    }
     // visible (query, key) pairs: block-causal sum_q ((q_pos0+q)|7)+1, else Tq*Tk
     double pairs = static_cast<double>(a.Tq) * a.Tk;
     if (a.block_causal) {
@@ -433,19 +400,9 @@ struct Handle {
     return rc;
   }
   int run_ln(const float* x, int64_t rows, int rows_per_batch, const float* g, const float* b, float eps, int silu_,
-             __half* out, int64_t pitch, cudaStream_t st) {
-    if (rec != nullptr) {
-      MegaOp op;
-      op.kind = MK_LN;
-      MegaLn& l = op.u.l;
-      l.x = x; l.ldx = E; l.rows = rows; l.rows_per_batch = rows_per_batch; l.C = E; l.gamma = g; l.beta = b; l.eps = eps;
-      l.silu = silu_; l.out16 = out; l.ld16 = E; l.out_batch_pitch = pitch;
-      if (E % 4 != 0 || pitch % 4 != 0 || rows >= 4096) rec_fail = true;
-      rec->push_back(op);
-      return FRT2_OK;
-    }
+             __half* out, int64_t pitch, cudaStream_t st, float* mean_out = nullptr) {
     const int id = prof_begin(FRT2_PROF_LAYER_NORM, 0.0, static_cast<double>(rows) * E * 6.0, st);
-    const int rc = layer_norm_rows_batched(x, E, rows, rows_per_batch, E, g, b, eps, silu_, out, E, pitch, st);
+    const int rc = layer_norm_rows_batched(x, E, rows, rows_per_batch, E, g, b, eps, silu_, out, E, pitch, st, mean_out);
     prof_end(id, st);
     return rc;
   }
@@ -470,24 +427,43 @@ struct Stream {
   float* attn_part = nullptr;   // (B*H, ATTN_KSPLIT, 8, hd + 2): cross-CTA split of the step's attention (hd == 64 only)
   int* attn_count = nullptr;    // (B*H) arrival counters, zero between launches
   int* ctrl = nullptr;      // device (B, CTRL_INTS) per-item control blocks: read by the kernels of the captured step
+  // device error words of THIS stream / pool (1 + B): word 0 = some item sent an out-of-range code, word 1 + b = item b
+  // did.  A handle-global word would let one request consume another request's error.
+  unsigned int* err_words = nullptr;
   bool pooled = false;      // slot pool (frt2_pool_*): items are independent streams at their own positions
   std::vector<int> slot_tokens;  // pool: host mirror of the tokens each slot has consumed
   std::vector<char> slot_done;   // pool: the slot's stream received its LAST token
   int* tok_stage = nullptr; // (B, nq, chunk_cap) int32 contiguous
   float* audio_stage = nullptr;  // (B, audio_stage_pitch)
   int64_t audio_stage_pitch = 0;
+  // step workspace of the captured per-token step (chunks of <= 3 tokens): private to the stream, so streams that
+  // decode concurrently on different CUDA streams never share activations, and the captured graph never goes stale
+  uint8_t* ws = nullptr;
+  size_t ws_bytes = 0;
   cudaStream_t cap_stream = nullptr;  // capture happens here (the caller's stream may be the legacy default stream)
-  struct GraphRec { cudaGraphExec_t exec; const uint8_t* ws; long long kernels; };
+  struct GraphRec { cudaGraphExec_t exec; long long kernels; };
   std::map<std::pair<int, int>, GraphRec> graphs;  // (Lc, nq) -> captured step
-  // persistent step kernel: (Lc, nq) -> recorded op list in HBM
-  struct MegaRec { MegaOp* ops; int nops; const uint8_t* ws; long long kernels; bool unsupported; };
-  std::map<std::pair<int, int>, MegaRec> megas;
-  unsigned int* mega_bar = nullptr;   // grid-barrier counter (monotonic; the host tracks its value)
-  unsigned int mega_epoch = 0;
+  // stream-ordered bookkeeping: the state is reset by a kernel on the stream of the NEXT decode call, and a call that
+  // arrives on another CUDA stream than the previous one waits (on the device) for the previous call's event
+  bool pending_reset = true;
+  cudaEvent_t last_use = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool used = false;
 
   int64_t conv_pitch(int i) const { return static_cast<int64_t>(conv_hist[i] + conv_rpt[i] * chunk_cap) * h->E; }
   // one token of slack: an idle pool slot still "appends" (and later overwrites) one chunk at its current position
   int64_t kv_pitch() const { return static_cast<int64_t>(max_tokens + 1) * 8 * 2 * h->E; }
+  size_t footprint() const {   // device bytes this state holds (bounds the handle's pool of spare states)
+    size_t n = static_cast<size_t>(h->nl) * B * kv_pitch() * 2 + ws_bytes;
+    for (int i = 0; i < 11; ++i) n += static_cast<size_t>(B) * conv_pitch(i) * 2;
+    return n;
+  }
+  ShiftTable shift_table(int rows_mul) const {
+    ShiftTable tb{};
+    tb.n = 11;
+    for (int i = 0; i < 11; ++i) tb.e[i] = {conv[i], conv_hist[i], conv_rpt[i] * rows_mul, conv_pitch(i)};
+    return tb;
+  }
   void free_conv() {
     for (auto& p : conv) {
       if (p) cudaFree(p);
@@ -500,23 +476,26 @@ struct Stream {
     for (auto p : kv) cudaFree(p);
     if (tail) cudaFree(tail);
     if (ctrl) cudaFree(ctrl);
+    if (err_words) cudaFree(err_words);
     if (attn_part) cudaFree(attn_part);
     if (attn_count) cudaFree(attn_count);
     if (tok_stage) cudaFree(tok_stage);
     if (audio_stage) cudaFree(audio_stage);
-    if (mega_bar) cudaFree(mega_bar);
+    if (ws) cudaFree(ws);
     drop_graphs();
     if (cap_stream) cudaStreamDestroy(cap_stream);
+    if (last_use) cudaEventDestroy(last_use);
   }
   void drop_graphs() {
     for (auto& g : graphs) cudaGraphExecDestroy(g.second.exec);
     graphs.clear();
-    for (auto& m : megas)
-      if (m.second.ops) cudaFree(m.second.ops);
-    megas.clear();
   }
   int ensure_chunk_cap(int Lc, cudaStream_t st);
-  int reset();
+  int ensure_ws(size_t bytes);
+  // order this call after the stream's previous user and apply a pending reset, both on `st`
+  int begin_use(cudaStream_t st);
+  int end_use(cudaStream_t st);
+  void mark_reset();
 };
 
 // ------------------------------------------------------------------ weight repack (host, once)
@@ -611,7 +590,6 @@ int Handle::finalize() {
   FRT2_TRY(gemm_tc_init());
   FRT2_TRY(gemm_skinny_init());
   FRT2_TRY(attention_tc_init());
-  FRT2_TRY(stream_mega_init());
   const HostTensor* t = nullptr;
   const std::string RVQ = "rvq.", UP = "upsample.", AD = "acoustic_decoder.", BB = "acoustic_decoder.backbone.";
 
@@ -881,7 +859,7 @@ size_t Handle::ws_bytes_for(int B, int L) const {
   const size_t R = static_cast<size_t>(B) * L, M = 8 * R;
   const size_t sizes[] = {R * rd * 4, R * rd * 2, R * E * 2, R * 4 * E * 2, R * 4 * E * 2, M * E * 2, M * E * 2,
                           M * E * 4, M * E * 4, M * E * 2, M * 3 * E * 2, M * E * 2, M * 4 * E * 2,
-                          M * spec_ld * 2, M * n_fft * 4, M * 8};
+                          M * spec_ld * 2, M * n_fft * 4, M * 8, M * 4};
   size_t off = 0;
   for (size_t b : sizes) off = align_up(off + b, 1024);
   return off;
@@ -912,9 +890,21 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   const size_t o_x32 = carve(M * E * 4), o_y32 = carve(M * E * 4), o_n16 = carve(M * E * 2);
   const size_t o_qkv = carve(M * 3 * E * 2), o_o16 = carve(M * E * 2), o_g16 = carve(M * 4 * E * 2);
   const size_t o_spec = carve(M * spec_ld * 2), o_frames = carve(M * n_fft * 4);
-  const size_t o_stats = carve(M * 8);
-  FRT2_TRY(ensure_ws(off));
+  const size_t o_stats = carve(M * 8), o_shift = carve(M * 4);
+  // The captured per-token step works in the stream's private workspace; everything else in the handle's arena, which
+  // the call first acquires against users on other CUDA streams.
+  uint8_t* ws = nullptr;
+  if (graph_mode) {
+    FRT2_TRY(s->ensure_ws(off));
+    ws = s->ws;
+  } else {
+    FRT2_TRY(ensure_ws(off));
+    FRT2_TRY(ws_acquire(st));
+    ws = this->ws;
+  }
+  unsigned int* errw = streaming ? s->err_words : err_word;
   float2* stats = reinterpret_cast<float2*>(ws + o_stats);
+  float* rowshift = reinterpret_cast<float*>(ws + o_shift);
   float* emb32 = reinterpret_cast<float*>(ws + o_emb32);
   __half* emb16 = reinterpret_cast<__half*>(ws + o_emb16);
   __half* z16 = reinterpret_cast<__half*>(ws + o_z16);
@@ -956,10 +946,16 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
                     E % 8 == 0 && E <= 2048 && nl > 0 && !no_lnfold_env &&
                     !(debug & (DBG_GEMM_REF | DBG_NO_LNFOLD)) &&
                     (!(debug & DBG_TAPS) || getenv("FRT2_FOLD_WITH_TAPS") != nullptr /* debugging: "final" is then raw */);
+  // The fp16 copy is rounded AFTER subtracting the last known mean of its row (LayerNorm is shift-invariant): a
+  // checkpoint whose residual rows carry a mean of many times their spread keeps all 11 mantissa bits for the part the
+  // normalisation keeps.  rowshift is written by the LN + SiLU kernel that reads x32 in front of every producer chain
+  // and advanced by row_stats (true mean = shift + mean of the copy).  FRT2_NO_LNSHIFT=1: plain fp16(x) copy (A/B).
+  static const bool no_lnshift_env = (getenv("FRT2_NO_LNSHIFT") != nullptr);
+  float* shift = (fold && !no_lnshift_env) ? rowshift : nullptr;
   struct Fold { const __half* W; const float* colsum; const float* bias; float eps; };
   auto run_stats = [&](float eps) -> int {   // (mean, rstd) of the rows of n16 (2 B per element in)
     const int id = prof_begin(FRT2_PROF_LAYER_NORM, 0.0, static_cast<double>(M) * E * 2.0, st);
-    const int rc = row_stats(n16, E, M, E, eps, stats, st);
+    const int rc = row_stats(n16, E, M, E, eps, stats, st, shift);
     prof_end(id, st);
     return rc;
   };
@@ -979,7 +975,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
       g.W = fc->W; g.bias = fc->bias; g.colsum = fc->colsum; g.stats_in = stats;
     }
     if (emit_stats) {         // producer: fp16 copy of the new residual stream for the next folded LayerNorm
-      g.x16_out = n16; g.ld_x16 = E;
+      g.x16_out = n16; g.ld_x16 = E; g.x16_shift = shift;
     }
     return run_gemm(g, st);
   };
@@ -993,7 +989,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     g.pitch32 = pitch32; g.pitch16 = pitch16; g.alpha = 1.0f; g.bias = bias; g.act = act; g.resid = resid;
     g.out32 = out32; g.ld32 = E; g.out16 = out16; g.ld16 = ld16;
     if (emit_stats) {
-      g.x16_out = n16; g.ld_x16 = E;
+      g.x16_out = n16; g.ld_x16 = E; g.x16_shift = shift;
     }
     return run_gemm(g, st);
   };
@@ -1002,19 +998,10 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   // ---- K1: RVQ gather-and-sum (+ output projection) ----
   {
     // algorithmic bytes per token: nq*(idx + D*4) in, D*2 out
-    if (rec != nullptr) {
-      MegaOp op;
-      op.kind = MK_RVQ;
-      MegaRvq& r = op.u.r;
-      r.tokens = static_cast<const int*>(tokens); r.sB = sB; r.sQ = sQ; r.sL = sL; r.B = B; r.nq = nq_in; r.L = L; r.K = K;
-      r.D = rd; r.tables = tables; r.sum16 = emb16; r.err_word = err_word;
-      r.zero_ptr = nullptr; r.zero_pitch = 0; r.zero_cols = 0; r.zero_rows = 0;
-      if (idx_bytes != 4 || nq_in > 64 || rd % 4 != 0) rec_fail = true;
-      rec->push_back(op);
-    } else {
+    {
       const int id = prof_begin(FRT2_PROF_RVQ, 0.0, static_cast<double>(R) * (nq_in * (idx_bytes + rd * 4.0) + rd * 2.0), st);
       FRT2_TRY(rvq_gather_sum(tokens, idx_bytes, sB, sQ, sL, B, nq_in, L, tables, K, rd,
-                              (debug & DBG_TAPS) ? emb32 : nullptr, emb16, nullptr, err_word, st));
+                              (debug & DBG_TAPS) ? emb32 : nullptr, emb16, nullptr, errw, st));
       prof_end(id, st);
     }
   }
@@ -1048,7 +1035,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     const ResW& w = res[r];
     const CB& c1 = cb[3 + 2 * r];
     const CB& c2 = cb[4 + 2 * r];
-    FRT2_TRY(run_ln(x32, M, T, w.ln1_g, w.ln1_b, 1e-5f, 1, chunk_ptr(c1), c1.pitch, st));
+    FRT2_TRY(run_ln(x32, M, T, w.ln1_g, w.ln1_b, 1e-5f, 1, chunk_ptr(c1), c1.pitch, st, emit_stats ? shift : nullptr));
     FRT2_TRY(conv_gemm(c1, T, 3, w.w1, E, w.b1, ACT_NONE, nullptr, y32, xp, nullptr, 0, 0));
     FRT2_TRY(run_ln(y32, M, T, w.ln2_g, w.ln2_b, 1e-5f, 1, chunk_ptr(c2), c2.pitch, st));
     FRT2_TRY(conv_gemm(c2, T, 3, w.w2, E, w.b2, ACT_NONE, x32, x32, xp, nullptr, 0, 0, emit_stats));
@@ -1123,11 +1110,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   FRT2_TRY(tap_f16("final", n16, E, M, E, st));
   // ---- K5: head GEMM with polar epilogue -> windowed inverse DFT GEMM -> overlap-add ----
   if (spec_ld > 2 * n_bins) {
-    if (rec != nullptr) {   // the zero fill of the padding columns rides on the step's first op (nothing touches spec16 before)
-      MegaRvq& r = (*rec)[0].u.r;
-      r.zero_ptr = spec16 + 2 * n_bins; r.zero_pitch = spec_ld; r.zero_cols = spec_ld - 2 * n_bins;
-      r.zero_rows = static_cast<int>(M);
-    } else {
+    {
       FRT2_CUDA_OK(cudaMemset2DAsync(spec16 + 2 * n_bins, static_cast<size_t>(spec_ld) * 2, 0,
                                      static_cast<size_t>(spec_ld - 2 * n_bins) * 2, M, st));
     }
@@ -1150,22 +1133,6 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   } else {
     od.tail = nullptr; od.first = 1; od.last = 1;
   }
-  if (rec != nullptr) {
-    // the whole tail of the step as two ops: overlap-add, then tail update + history shift + position advance
-    if (!streaming || od.ctrl == nullptr || n_fft != 4 * hop || E % 8 != 0 || n_fft % 4 != 0) rec_fail = true;
-    MegaOp op;
-    op.kind = MK_OLA; op.u.o = od;
-    rec->push_back(op);
-    MegaOp rl;
-    rl.kind = MK_ROLL;
-    MegaRoll& ro = rl.u.ro;
-    ro.frames = frames32; ro.frames_batch_pitch = od.frames_batch_pitch; ro.tail = s->tail; ro.T = T; ro.n_fft = n_fft;
-    ro.E = E; ro.B = B; ro.ctrl = s->ctrl; ro.advance_frames = T; ro.all_items = 0;
-    ro.tb.n = 11;
-    for (int i = 0; i < 11; ++i) ro.tb.e[i] = {s->conv[i], s->conv_hist[i], s->conv_rpt[i] * L, s->conv_pitch(i)};
-    rec->push_back(rl);
-    return FRT2_OK;
-  }
   {
     const int id = prof_begin(FRT2_PROF_OLA, 0.0, static_cast<double>(M) * (n_fft + hop) * 4.0, st);
     FRT2_TRY(istft_overlap_add(od, st));
@@ -1173,24 +1140,14 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   }
   if (streaming) {
     // end-of-step state roll (new iSTFT tail, conv histories to the head, position advance) as one kernel
-    MegaRoll ro;
+    StateRoll ro;
     ro.frames = frames32; ro.frames_batch_pitch = od.frames_batch_pitch; ro.tail = s->tail; ro.T = T; ro.n_fft = n_fft;
     ro.E = E; ro.B = B; ro.ctrl = s->ctrl; ro.advance_frames = T; ro.all_items = graph_mode ? 0 : 1;
-    ro.tb.n = 11;
-    for (int i = 0; i < 11; ++i) ro.tb.e[i] = {s->conv[i], s->conv_hist[i], s->conv_rpt[i] * L, s->conv_pitch(i)};
-    if (E % 8 == 0 && n_fft % 4 == 0) {
-      FRT2_TRY(stream_state_roll(ro, st));
-      launches += 1;
-    } else {
-      launches += 2;
-      const int* cblk = graph_mode ? s->ctrl : nullptr;
-      FRT2_TRY(istft_update_tail(frames32, od.frames_batch_pitch, s->tail, B, T, n_fft, cblk, st));
-      shift_history_kernel<<<dim3(8, 11), 256, 0, st>>>(ro.tb, E, B, cblk);
-      advance_ctrl_kernel<<<(B + 127) / 128, 128, 0, st>>>(s->ctrl, T, B, graph_mode ? 0 : 1);
-      launches += 1;
-      FRT2_CUDA_OK(cudaGetLastError());
-    }
+    ro.tb = s->shift_table(L);
+    FRT2_TRY(stream_state_roll(ro, st));
+    launches += 1;
   }
+  if (!graph_mode) FRT2_TRY(ws_release(st));
   tap_B = B;
   tap_L = L;
   return FRT2_OK;
@@ -1208,8 +1165,11 @@ int Stream::ensure_chunk_cap(int Lc, cudaStream_t st) {
   }
   chunk_cap = Lc;
   drop_graphs();
+  if (old_cap > 0) FRT2_CUDA_OK(cudaStreamSynchronize(st));   // the old staging buffers may still be in use
   if (tok_stage) cudaFree(tok_stage);
   if (audio_stage) cudaFree(audio_stage);
+  tok_stage = nullptr;
+  audio_stage = nullptr;
   audio_stage_pitch = static_cast<int64_t>(8) * h->hop * Lc + (h->n_fft - h->hop) / 2;
   audio_stage_pitch = (audio_stage_pitch + 3) / 4 * 4;
   FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&tok_stage), static_cast<size_t>(B) * h->nq * Lc * 4));
@@ -1230,14 +1190,41 @@ int Stream::ensure_chunk_cap(int Lc, cudaStream_t st) {
   return FRT2_OK;
 }
 
-int Stream::reset() {
+int Stream::ensure_ws(size_t bytes) {
+  if (bytes <= ws_bytes) return FRT2_OK;
+  if (ws) {
+    FRT2_CUDA_OK(cudaDeviceSynchronize());
+    FRT2_CUDA_OK(cudaFree(ws));
+    ws = nullptr;
+    ws_bytes = 0;
+    drop_graphs();   // captured steps point into the old workspace
+  }
+  FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ws), bytes));
+  ws_bytes = bytes;
+  return FRT2_OK;
+}
+
+void Stream::mark_reset() {
   n_tokens = 0;
-  FRT2_CUDA_OK(cudaMemset(ctrl, 0, static_cast<size_t>(B) * CTRL_INTS * sizeof(int)));
   std::fill(slot_tokens.begin(), slot_tokens.end(), 0);
   std::fill(slot_done.begin(), slot_done.end(), 0);
-  for (int i = 0; i < 11; ++i)
-    if (conv[i]) FRT2_CUDA_OK(cudaMemset(conv[i], 0, static_cast<size_t>(B) * conv_pitch(i) * 2));
-  FRT2_CUDA_OK(cudaMemset(tail, 0, static_cast<size_t>(B) * 3 * h->n_fft * 4));
+  pending_reset = true;
+}
+
+int Stream::begin_use(cudaStream_t st) {
+  if (used && st != last_stream) FRT2_CUDA_OK(cudaStreamWaitEvent(st, last_use, 0));
+  if (pending_reset) {
+    FRT2_TRY(stream_state_reset(shift_table(0), h->E, B, ctrl, err_words, 1 + B, st));
+    pending_reset = false;
+  }
+  return FRT2_OK;
+}
+
+int Stream::end_use(cudaStream_t st) {
+  if (last_use == nullptr) FRT2_CUDA_OK(cudaEventCreateWithFlags(&last_use, cudaEventDisableTiming));
+  FRT2_CUDA_OK(cudaEventRecord(last_use, st));
+  last_stream = st;
+  used = true;
   return FRT2_OK;
 }
 
@@ -1250,6 +1237,12 @@ using namespace frt2;
 
 struct frt2_handle { Handle h; };
 struct frt2_stream { Stream s; };
+
+frt2::Handle::~Handle() {
+  cudaSetDevice(device);
+  for (frt2_stream* fs : free_streams) delete fs;
+  release_base();
+}
 
 extern "C" {
 
@@ -1423,12 +1416,11 @@ int frt2_peer_free(int device, void* ptr) {
   return FRT2_OK;
 }
 
-int frt2_stream_create(frt2_handle* hh, int B, int max_tokens, frt2_stream** out) {
-  FRT2_REQUIRE(hh && out, FRT2_ERR_BAD_ARG, "null argument");
-  Handle& h = hh->h;
-  FRT2_REQUIRE(h.finalized, FRT2_ERR_NOT_FINALIZED, "handle not finalized");
-  FRT2_REQUIRE(B >= 1 && max_tokens >= 1, FRT2_ERR_BAD_ARG, "B and max_tokens must be >= 1");
-  FRT2_CUDA_OK(cudaSetDevice(h.device));
+// Spare stream states kept by the handle (see Handle::free_streams): at most this many / this many bytes.
+static constexpr size_t STREAM_POOL_MAX = 16;
+static constexpr size_t STREAM_POOL_MAX_BYTES = static_cast<size_t>(8) << 30;
+
+static int stream_create_fresh(Handle& h, int B, int max_tokens, frt2_stream** out) {
   auto* w = new frt2_stream();
   Stream& s = w->s;
   s.h = &h; s.B = B; s.max_tokens = max_tokens;
@@ -1443,6 +1435,7 @@ int frt2_stream_create(frt2_handle* hh, int B, int max_tokens, frt2_stream** out
   }
   if (cudaMalloc(reinterpret_cast<void**>(&s.tail), static_cast<size_t>(B) * 3 * h.n_fft * 4) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&s.ctrl), static_cast<size_t>(B) * CTRL_INTS * sizeof(int)) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&s.err_words), static_cast<size_t>(1 + B) * sizeof(unsigned int)) != cudaSuccess ||
       cudaStreamCreateWithFlags(&s.cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
     set_error("frt2_stream_create: out of memory");
     return fail(FRT2_ERR_CUDA);
@@ -1458,116 +1451,167 @@ int frt2_stream_create(frt2_handle* hh, int B, int max_tokens, frt2_stream** out
   }
   st = s.ensure_chunk_cap(1, nullptr);
   if (st != FRT2_OK) return fail(st);
-  st = s.reset();
+  st = s.ensure_ws(h.ws_bytes_for(B, 1));
   if (st != FRT2_OK) return fail(st);
+  s.mark_reset();   // the reset kernel runs on the stream of the first decode call
+  // everything above ran on the null stream (allocation-time memsets): make it visible to any stream
+  if (cudaDeviceSynchronize() != cudaSuccess) {
+    set_error("frt2_stream_create: device synchronisation failed");
+    return fail(FRT2_ERR_CUDA);
+  }
   *out = w;
+  return FRT2_OK;
+}
+
+int frt2_stream_create(frt2_handle* hh, int B, int max_tokens, frt2_stream** out) {
+  FRT2_REQUIRE(hh && out, FRT2_ERR_BAD_ARG, "null argument");
+  Handle& h = hh->h;
+  FRT2_REQUIRE(h.finalized, FRT2_ERR_NOT_FINALIZED, "handle not finalized");
+  FRT2_REQUIRE(B >= 1 && max_tokens >= 1, FRT2_ERR_BAD_ARG, "B and max_tokens must be >= 1");
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  {
+    // a spare state of this shape (returned by frt2_stream_destroy, or made by frt2_stream_reserve): no allocation, no
+    // graph capture — its reset is a kernel on the stream of the first decode call
+    std::lock_guard<std::mutex> lk(h.mu);
+    for (size_t i = 0; i < h.free_streams.size(); ++i) {
+      Stream& c = h.free_streams[i]->s;
+      if (c.B == B && c.max_tokens == max_tokens && !c.pooled) {
+        *out = h.free_streams[i];
+        h.free_stream_bytes -= c.footprint();
+        h.free_streams.erase(h.free_streams.begin() + i);
+        c.mark_reset();
+        return FRT2_OK;
+      }
+    }
+  }
+  return stream_create_fresh(h, B, max_tokens, out);
+}
+
+static int capture_step(Handle& h, Stream& s, int nq, int Lc);
+
+int frt2_stream_reserve(frt2_handle* hh, int B, int max_tokens, int count) {
+  FRT2_REQUIRE(hh, FRT2_ERR_BAD_ARG, "null handle");
+  Handle& h = hh->h;
+  FRT2_REQUIRE(h.finalized, FRT2_ERR_NOT_FINALIZED, "handle not finalized");
+  FRT2_REQUIRE(B >= 1 && max_tokens >= 1 && count >= 0, FRT2_ERR_BAD_ARG, "frt2_stream_reserve: bad argument");
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  for (int i = 0; i < count; ++i) {
+    {
+      std::lock_guard<std::mutex> lk(h.mu);
+      int have = 0;
+      for (frt2_stream* fs : h.free_streams) have += (fs->s.B == B && fs->s.max_tokens == max_tokens && !fs->s.pooled);
+      if (have >= count || h.free_streams.size() >= STREAM_POOL_MAX) return FRT2_OK;
+    }
+    frt2_stream* fs = nullptr;
+    FRT2_TRY(stream_create_fresh(h, B, max_tokens, &fs));
+    std::lock_guard<std::mutex> lk(h.mu);
+    if (B * 8 < 32) {   // the per-token step of this shape, captured now instead of inside the first request
+      const int rc = capture_step(h, fs->s, h.nq, 1);
+      if (rc != FRT2_OK) {
+        delete fs;
+        return rc;
+      }
+    }
+    h.free_stream_bytes += fs->s.footprint();
+    h.free_streams.push_back(fs);
+  }
   return FRT2_OK;
 }
 
 int frt2_stream_reset(frt2_stream* ss) {
   FRT2_REQUIRE(ss, FRT2_ERR_BAD_ARG, "null stream");
-  FRT2_CUDA_OK(cudaSetDevice(ss->s.h->device));
-  FRT2_CUDA_OK(cudaDeviceSynchronize());
-  return ss->s.reset();
+  std::lock_guard<std::mutex> lk(ss->s.h->mu);
+  ss->s.mark_reset();   // stream-ordered: the reset kernel runs on the stream of the next decode call
+  return FRT2_OK;
 }
-void frt2_stream_destroy(frt2_stream* ss) { delete ss; }
+
+void frt2_stream_destroy(frt2_stream* ss) {
+  if (ss == nullptr) return;
+  Handle& h = *ss->s.h;
+  {
+    std::lock_guard<std::mutex> lk(h.mu);
+    const size_t fp = ss->s.footprint();
+    if (!ss->s.pooled && h.free_streams.size() < STREAM_POOL_MAX && h.free_stream_bytes + fp <= STREAM_POOL_MAX_BYTES) {
+      ss->s.mark_reset();
+      h.free_stream_bytes += fp;
+      h.free_streams.push_back(ss);
+      return;
+    }
+  }
+  cudaSetDevice(h.device);
+  cudaDeviceSynchronize();   // kernels of the last request may still be using the state
+  delete ss;
+}
 int frt2_stream_tokens(const frt2_stream* ss) { return ss ? ss->s.n_tokens : 0; }
+
+int frt2_stream_check_error(frt2_handle* hh, frt2_stream* ss, int32_t* item_flags, void* cuda_stream) {
+  FRT2_REQUIRE(hh && ss, FRT2_ERR_BAD_ARG, "null handle/stream");
+  Handle& h = hh->h;
+  Stream& s = ss->s;
+  FRT2_REQUIRE(s.h == &h, FRT2_ERR_BAD_ARG, "stream belongs to another handle");
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  std::vector<unsigned int> w(1 + s.B, 0u);
+  FRT2_CUDA_OK(cudaMemcpyAsync(w.data(), s.err_words, w.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  FRT2_CUDA_OK(cudaStreamSynchronize(st));
+  if (item_flags != nullptr)
+    for (int b = 0; b < s.B; ++b) item_flags[b] = static_cast<int32_t>(w[1 + b]);
+  if (w[0] != 0) {
+    FRT2_CUDA_OK(cudaMemsetAsync(s.err_words, 0, w.size() * sizeof(unsigned int), st));
+    if (w[0] & DEV_ERR_INDEX_OOR) {
+      set_error("index out of range in self");
+      return FRT2_ERR_INDEX_OUT_OF_RANGE;
+    }
+  }
+  return FRT2_OK;
+}
+
+int frt2_stream_fetch_errors(frt2_handle* hh, frt2_stream* ss, uint32_t* host_words, void* cuda_stream) {
+  FRT2_REQUIRE(hh && ss && host_words, FRT2_ERR_BAD_ARG, "null handle/stream/buffer");
+  FRT2_REQUIRE(ss->s.h == &hh->h, FRT2_ERR_BAD_ARG, "stream belongs to another handle");
+  FRT2_CUDA_OK(cudaSetDevice(hh->h.device));
+  FRT2_CUDA_OK(cudaMemcpyAsync(host_words, ss->s.err_words, static_cast<size_t>(1 + ss->s.B) * sizeof(unsigned int),
+                               cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(cuda_stream)));
+  return FRT2_OK;
+}
+
+// Capture the control-block-driven step for (Lc, nq) on the stream's private workspace (h.mu held by the caller).
+static int capture_step(Handle& h, Stream& s, int nq, int Lc) {
+  auto key = std::make_pair(Lc, nq);
+  if (s.graphs.count(key)) return FRT2_OK;
+  FRT2_TRY(s.ensure_chunk_cap(Lc, nullptr));
+  FRT2_TRY(s.ensure_ws(h.ws_bytes_for(s.B, Lc)));  // before capture: no allocation may happen while recording
+  const long long before = h.launches;
+  FRT2_CUDA_OK(cudaStreamBeginCapture(s.cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = h.pipeline(s.tok_stage, 4, static_cast<int64_t>(nq) * Lc, Lc, 1, s.B, nq, Lc, nullptr, s.audio_stage,
+                            s.audio_stage_pitch, &s, 0, s.cap_stream, true);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(s.cap_stream, &graph);
+  if (rc != FRT2_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  FRT2_CUDA_OK(ce);
+  Stream::GraphRec rec{};
+  rec.kernels = h.launches - before;
+  h.launches = before;
+  const cudaError_t ie = cudaGraphInstantiate(&rec.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  FRT2_CUDA_OK(ie);
+  s.graphs.emplace(key, rec);
+  return FRT2_OK;
+}
 
 // Run the control-block-driven step for (Lc, nq): tokens come from the stream's staging buffer, audio goes to its
 // staging buffer, positions / flags are read from HBM.  Normally one CUDA-graph replay (captured on first use).
 static int run_ctrl_step(Handle& h, Stream& s, int nq, int Lc, cudaStream_t st, bool use_graph) {
-  FRT2_TRY(h.ensure_ws(h.ws_bytes_for(s.B, Lc)));  // before capture: no allocation may happen while recording
   if (!use_graph)
     return h.pipeline(s.tok_stage, 4, static_cast<int64_t>(nq) * Lc, Lc, 1, s.B, nq, Lc, nullptr, s.audio_stage,
                       s.audio_stage_pitch, &s, 0, st, true);
-  auto key = std::make_pair(Lc, nq);
-  // ---- persistent step kernel (<= 16 rows): the recorded op list run by ONE cooperative launch ----
-  static const bool mega_env = [] {
-    const char* e = getenv("FRT2_MEGA");
-    return e == nullptr ? FRT2_MEGA_DEFAULT != 0 : (e[0] != '0');
-  }();
-  if (mega_env && stream_mega_grid() > 0 && s.B * 8 * Lc <= 16 && !(h.debug & DBG_NO_MEGA)) {
-    auto mi = s.megas.find(key);
-    if (mi != s.megas.end() && mi->second.ws != h.ws) {   // workspace moved since the recording
-      if (mi->second.ops) cudaFree(mi->second.ops);
-      s.megas.erase(mi);
-      mi = s.megas.end();
-    }
-    if (mi == s.megas.end()) {
-      std::vector<MegaOp> ops;
-      const long long before = h.launches;
-      h.rec = &ops;
-      h.rec_fail = false;
-      const int rc = h.pipeline(s.tok_stage, 4, static_cast<int64_t>(nq) * Lc, Lc, 1, s.B, nq, Lc, nullptr, s.audio_stage,
-                                s.audio_stage_pitch, &s, 0, st, true);
-      h.rec = nullptr;
-      h.launches = before;
-      FRT2_TRY(rc);
-      Stream::MegaRec mr{nullptr, static_cast<int>(ops.size()), h.ws, static_cast<long long>(ops.size()),
-                         h.rec_fail || ops.empty() || ops[0].kind != MK_RVQ};
-      if (!mr.unsupported) {
-        FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&mr.ops), ops.size() * sizeof(MegaOp)));
-        FRT2_CUDA_OK(cudaMemcpy(mr.ops, ops.data(), ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
-        if (s.mega_bar == nullptr) {
-          FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&s.mega_bar), 4));
-          FRT2_CUDA_OK(cudaMemset(s.mega_bar, 0, 4));
-          s.mega_epoch = 0;
-        }
-      }
-      mi = s.megas.emplace(key, mr).first;
-    }
-    if (!mi->second.unsupported) {
-      static const bool trace_env = (getenv("FRT2_MEGA_TRACE") != nullptr);   // debug: per-op timeline of CTA 0 on stderr
-      long long* trace = nullptr;
-      static int trace_calls = 0;
-      if (trace_env && ++trace_calls == 12)
-        FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&trace), static_cast<size_t>(mi->second.nops) * 16));
-      FRT2_TRY(stream_mega_launch(mi->second.ops, mi->second.nops, s.mega_bar, s.mega_epoch, st, trace));
-      if (trace != nullptr) {
-        std::vector<long long> tr(static_cast<size_t>(mi->second.nops) * 2);
-        std::vector<MegaOp> hops(mi->second.nops);
-        FRT2_CUDA_OK(cudaStreamSynchronize(st));
-        FRT2_CUDA_OK(cudaMemcpy(tr.data(), trace, tr.size() * 8, cudaMemcpyDeviceToHost));
-        FRT2_CUDA_OK(cudaMemcpy(hops.data(), mi->second.ops, hops.size() * sizeof(MegaOp), cudaMemcpyDeviceToHost));
-        cudaFree(trace);
-        for (int i = 0; i < mi->second.nops; ++i)
-          fprintf(stderr, "megatrace op %3d kind %d nblocks %4d: body %6lld ns, barrier+wait %6lld ns\n", i, hops[i].kind,
-                  hops[i].nblocks, tr[2 * i + 1] - tr[2 * i], i + 1 < mi->second.nops ? tr[2 * i + 2] - tr[2 * i + 1] : 0LL);
-      }
-      s.mega_epoch += static_cast<unsigned int>(mi->second.nops - 1) * static_cast<unsigned int>(stream_mega_grid());
-      h.launches += 1;
-      return FRT2_OK;
-    }
-  }
-  auto it = s.graphs.find(key);
-  if (it != s.graphs.end() && it->second.ws != h.ws) {  // workspace moved since the capture
-    cudaGraphExecDestroy(it->second.exec);
-    s.graphs.erase(it);
-    it = s.graphs.end();
-  }
-  if (it == s.graphs.end()) {
-    const long long before = h.launches;
-    FRT2_CUDA_OK(cudaStreamBeginCapture(s.cap_stream, cudaStreamCaptureModeThreadLocal));
-    const int rc = h.pipeline(s.tok_stage, 4, static_cast<int64_t>(nq) * Lc, Lc, 1, s.B, nq, Lc, nullptr, s.audio_stage,
-                              s.audio_stage_pitch, &s, 0, s.cap_stream, true);
-    cudaGraph_t graph = nullptr;
-    const cudaError_t ce = cudaStreamEndCapture(s.cap_stream, &graph);
-    if (rc != FRT2_OK) {
-      if (graph) cudaGraphDestroy(graph);
-      return rc;
-    }
-    FRT2_CUDA_OK(ce);
-    Stream::GraphRec rec{};
-    rec.ws = h.ws;
-    rec.kernels = h.launches - before;
-    h.launches = before;
-    const cudaError_t ie = cudaGraphInstantiate(&rec.exec, graph, 0);
-    cudaGraphDestroy(graph);
-    FRT2_CUDA_OK(ie);
-    it = s.graphs.emplace(key, rec).first;
-  }
-  FRT2_CUDA_OK(cudaGraphLaunch(it->second.exec, st));
-  h.launches += it->second.kernels;
+  FRT2_TRY(capture_step(h, s, nq, Lc));
+  const Stream::GraphRec& g = s.graphs.at(std::make_pair(Lc, nq));
+  FRT2_CUDA_OK(cudaGraphLaunch(g.exec, st));
+  h.launches += g.kernels;
   return FRT2_OK;
 }
 
@@ -1595,15 +1639,16 @@ static int decode_chunk_impl(frt2_handle* hh, frt2_stream* ss, const void* token
   FRT2_REQUIRE(!s.pooled, FRT2_ERR_BAD_ARG, "this is a slot pool: use frt2_pool_step");
   FRT2_TRY(check_decode_args(h, tokens, idx_bytes, s.B, nq, Lc,
                              pcm ? reinterpret_cast<const float*>(pcm) : audio));
+  std::lock_guard<std::mutex> lk(h.mu);
   FRT2_REQUIRE(s.n_tokens + Lc <= s.max_tokens, FRT2_ERR_STATE_OVERFLOW,
                "stream state overflow: more tokens than frt2_stream_create reserved");
   const int pad = (h.n_fft - h.hop) / 2;
   const int n = 8 * h.hop * Lc - (s.n_tokens == 0 ? pad : 0) + (last ? pad : 0);
   FRT2_REQUIRE(audio_pitch >= n, FRT2_ERR_BAD_ARG, "audio_pitch too small");
-  std::lock_guard<std::mutex> lk(h.mu);
   FRT2_CUDA_OK(cudaSetDevice(h.device));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   FRT2_TRY(s.ensure_chunk_cap(Lc, st));
+  FRT2_TRY(s.begin_use(st));   // ordered after the state's previous user; pending reset applied on this stream
   // Short chunks (the per-token latency path) replay one captured CUDA graph per call; anything that needs host-side
   // parameters per kernel (taps, per-kernel event timing, the tcgen05 attention for long chunks) runs kernel by kernel.
   const bool graph_mode = !(h.debug & (DBG_NO_GRAPH | DBG_TAPS)) && !h.profile && 8 * Lc < 32;
@@ -1619,10 +1664,10 @@ static int decode_chunk_impl(frt2_handle* hh, frt2_stream* ss, const void* token
     const SlotFlags none{};
     if (idx_bytes == 4) {
       stage_tokens_kernel<int, false><<<(nthr + 127) / 128, 128, 0, st>>>(
-          static_cast<const int*>(tokens), sB, sQ, sL, s.B, nq, Lc, h.K, s.tok_stage, s.ctrl, last, h.err_word, none);
+          static_cast<const int*>(tokens), sB, sQ, sL, s.B, nq, Lc, h.K, s.tok_stage, s.ctrl, last, s.err_words, none);
     } else {
       stage_tokens_kernel<long long, false><<<(nthr + 127) / 128, 128, 0, st>>>(
-          static_cast<const long long*>(tokens), sB, sQ, sL, s.B, nq, Lc, h.K, s.tok_stage, s.ctrl, last, h.err_word,
+          static_cast<const long long*>(tokens), sB, sQ, sL, s.B, nq, Lc, h.K, s.tok_stage, s.ctrl, last, s.err_words,
           none);
     }
     FRT2_CUDA_OK(cudaGetLastError());
@@ -1630,6 +1675,7 @@ static int decode_chunk_impl(frt2_handle* hh, frt2_stream* ss, const void* token
     FRT2_TRY(run_ctrl_step(h, s, nq, Lc, st, true));
     FRT2_TRY(emit_chunk(h, s, audio, pcm, audio_pitch, n, st));
   }
+  FRT2_TRY(s.end_use(st));
   s.n_tokens += Lc;
   if (n_samples) *n_samples = n;
   return FRT2_OK;
@@ -1678,6 +1724,7 @@ int frt2_pool_step(frt2_handle* hh, frt2_stream* ss, const void* tokens, int idx
   const int pad = (h.n_fft - h.hop) / 2;
   const int width = 8 * h.hop + pad;
   FRT2_REQUIRE(out_pitch >= width, FRT2_ERR_BAD_ARG, "out_pitch must be >= 8*hop + pad");
+  std::lock_guard<std::mutex> lk(h.mu);
   // validate the whole step before touching any state
   SlotFlags flags{};
   bool any_reset = false;
@@ -1697,29 +1744,27 @@ int frt2_pool_step(frt2_handle* hh, frt2_stream* ss, const void* tokens, int idx
     flags.f[b] = static_cast<unsigned char>(f);
     any_reset = any_reset || (f & FRT2_SLOT_RESET);
   }
-  std::lock_guard<std::mutex> lk(h.mu);
   FRT2_CUDA_OK(cudaSetDevice(h.device));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  FRT2_TRY(s.begin_use(st));
   if (any_reset) {
-    ShiftTable tb{};
-    tb.n = 11;
-    for (int i = 0; i < 11; ++i) tb.e[i] = {s.conv[i], s.conv_hist[i], 0, s.conv_pitch(i)};
-    reset_history_kernel<<<dim3(8, 11), 256, 0, st>>>(tb, h.E, s.B, flags);
+    reset_history_kernel<<<dim3(8, 11), 256, 0, st>>>(s.shift_table(0), h.E, s.B, flags);
     ++h.launches;
   }
   const int nthr = s.B * nq;
   if (idx_bytes == 4) {
     stage_tokens_kernel<int, true><<<(nthr + 127) / 128, 128, 0, st>>>(
-        static_cast<const int*>(tokens), sB, sQ, 0, s.B, nq, 1, h.K, s.tok_stage, s.ctrl, 0, h.err_word, flags);
+        static_cast<const int*>(tokens), sB, sQ, 0, s.B, nq, 1, h.K, s.tok_stage, s.ctrl, 0, s.err_words, flags);
   } else {
     stage_tokens_kernel<long long, true><<<(nthr + 127) / 128, 128, 0, st>>>(
-        static_cast<const long long*>(tokens), sB, sQ, 0, s.B, nq, 1, h.K, s.tok_stage, s.ctrl, 0, h.err_word, flags);
+        static_cast<const long long*>(tokens), sB, sQ, 0, s.B, nq, 1, h.K, s.tok_stage, s.ctrl, 0, s.err_words, flags);
   }
   FRT2_CUDA_OK(cudaGetLastError());
   ++h.launches;
   FRT2_TRY(run_ctrl_step(h, s, nq, 1, st, !(h.debug & DBG_NO_GRAPH) && !h.profile));
   FRT2_TRY(emit_chunk(h, s, out_pcm16 ? nullptr : static_cast<float*>(out),
                       out_pcm16 ? static_cast<int16_t*>(out) : nullptr, out_pitch, width, st));
+  FRT2_TRY(s.end_use(st));
   for (int b = 0; b < s.B; ++b) {
     const int f = flags.f[b];
     int n = 0;
@@ -1738,9 +1783,11 @@ int frt2_export_state(frt2_handle* hh, const frt2_stream* ss, float* up_conv_cac
                       float* bb_conv_cache2, float* bb_kv_cache, float* is_cache, void* cuda_stream) {
   FRT2_REQUIRE(hh && ss, FRT2_ERR_BAD_ARG, "null handle/stream");
   Handle& h = hh->h;
-  const Stream& s = ss->s;
+  Stream& s = const_cast<Stream&>(ss->s);
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  std::lock_guard<std::mutex> lk(h.mu);
   FRT2_CUDA_OK(cudaSetDevice(h.device));
+  FRT2_TRY(s.begin_use(st));
   const int E = h.E, B = s.B;
   if (up_conv_cache) {  // (B,E,3) = [last x50 frame | last two post-GELU frames]  (decoder.py:624-655)
     export_tm_to_cm_kernel<<<grid_for(1LL * B * E), 256, 0, st>>>(s.conv[0], s.conv_pitch(0), 1, E, up_conv_cache, E, 0, 3, 0, B);
@@ -1757,6 +1804,7 @@ int frt2_export_state(frt2_handle* hh, const frt2_stream* ss, float* up_conv_cac
   if (is_cache)
     transpose_tail_kernel<<<(B * 3 * h.n_fft + 255) / 256, 256, 0, st>>>(s.tail, is_cache, B, h.n_fft, 1);
   FRT2_CUDA_OK(cudaGetLastError());
+  FRT2_TRY(s.end_use(st));
   return FRT2_OK;
 }
 
@@ -1768,7 +1816,9 @@ int frt2_import_state(frt2_handle* hh, frt2_stream* ss, int n_tokens, const floa
   Stream& s = ss->s;
   FRT2_REQUIRE(n_tokens >= 0 && n_tokens <= s.max_tokens, FRT2_ERR_STATE_OVERFLOW, "n_tokens exceeds the stream capacity");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  std::lock_guard<std::mutex> lk(h.mu);
   FRT2_CUDA_OK(cudaSetDevice(h.device));
+  FRT2_TRY(s.begin_use(st));
   const int E = h.E, B = s.B;
   if (up_conv_cache) {
     import_cm_to_tm_kernel<<<grid_for(1LL * B * E), 256, 0, st>>>(up_conv_cache, E, 0, 3, 0, s.conv[0], s.conv_pitch(0), 1, E, B);
@@ -1790,6 +1840,7 @@ int frt2_import_state(frt2_handle* hh, frt2_stream* ss, int n_tokens, const floa
   for (int b = 0; b < B; ++b) ctrl_h[b * CTRL_INTS + CTRL_POS] = 8 * n_tokens;
   FRT2_CUDA_OK(cudaMemcpyAsync(s.ctrl, ctrl_h.data(), ctrl_h.size() * sizeof(int), cudaMemcpyHostToDevice, st));
   FRT2_CUDA_OK(cudaStreamSynchronize(st));
+  FRT2_TRY(s.end_use(st));
   return FRT2_OK;
 }
 

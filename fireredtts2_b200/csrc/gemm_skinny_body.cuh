@@ -1,5 +1,5 @@
-// K2s body — the <= 16-row weight-streaming GEMM of the token step as a device function, shared by the stand-alone
-// kernel (gemm_skinny.cu) and the persistent per-token step kernel (stream_mega.cu).  See gemm_skinny.cu for the design.
+// K2s body — the <= 16-row weight-streaming GEMM of the token step as a device function, instantiated by
+// gemm_skinny_kernel (gemm_skinny.cu).  See gemm_skinny.cu for the design.
 #pragma once
 #include "common.cuh"
 

@@ -75,6 +75,7 @@ struct GemmKParams {
   // folded LayerNorm (see GemmDesc): producer side ...
   __half* x16_out;
   long long ld_x16;
+  const float* x16_shift;   // per-row offset subtracted before the fp16 rounding of the copy, or null
   // ... and consumer side
   const float2* stats_in;   // (mean, rstd) per A row
   const float* colsum;
@@ -325,6 +326,14 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
         }
       };
       if (use_resid && ncol0 < p.N) prefetch_resid(ncol0);
+      // folded LayerNorm, producer side: offsets of the 8 rows this lane covers in the coalesced order
+      float xsh[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = row0 + i * 4 + crow;
+        xsh[i] = (p.x16_shift != nullptr && rr < p.rows_out)
+                     ? __ldg(p.x16_shift + static_cast<long long>(b) * p.rows_out + rr) : 0.f;
+      }
 
       ptx::mbar_wait(tfull, aphase);
       ptx::tc_fence_after();
@@ -390,8 +399,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKParams& p, const CUtens
                                            static_cast<long long>(row0 + rr) * p.ld32 + n0 + cchunk * 4) = q;
                 if (p.x16_out != nullptr) {   // folded LayerNorm, producer side: fp16 copy of the residual stream
                   uint2 h;
-                  h.x = pack_half2(q.x, q.y);
-                  h.y = pack_half2(q.z, q.w);
+                  h.x = pack_half2(q.x - xsh[i], q.y - xsh[i]);
+                  h.y = pack_half2(q.z - xsh[i], q.w - xsh[i]);
                   *reinterpret_cast<uint2*>(p.x16_out + (static_cast<long long>(b) * p.rows_out + row0 + rr) * p.ld_x16 +
                                             n0 + cchunk * 4) = h;
                 }
@@ -851,6 +860,7 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   p.row_off_stride = g.row_off_stride;
   p.x16_out = g.x16_out;
   p.ld_x16 = g.ld_x16;
+  p.x16_shift = g.x16_out != nullptr ? g.x16_shift : nullptr;
   p.stats_in = g.stats_in;
   p.colsum = g.stats_in != nullptr ? g.colsum : nullptr;
   if (g.stats_in != nullptr) {

@@ -99,15 +99,15 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
                                                          int rows_per_batch, int C, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, float eps, int apply_silu,
                                                          __half* __restrict__ out16, long long ld16,
-                                                         long long out_batch_pitch) {
+                                                         long long out_batch_pitch, float* __restrict__ mean_out) {
   pdl_trigger();
   layer_norm_body<RPW>(x, ldx, rows, rows_per_batch, C, gamma, beta, eps, apply_silu, out16, ld16, out_batch_pitch,
-                       (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW);
+                       (static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW, mean_out);
 }
 
 int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_per_batch, int C, const float* gamma,
                             const float* beta, float eps, int apply_silu, __half* out16, int64_t ld16,
-                            int64_t out_batch_pitch, cudaStream_t stream) {
+                            int64_t out_batch_pitch, cudaStream_t stream, float* mean_out) {
   FRT2_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ld16 % 4 == 0 && out_batch_pitch % 4 == 0, FRT2_ERR_BAD_ARG,
                "layer_norm: C and pitches must be multiples of 4");
   if (rows == 0) return FRT2_OK;
@@ -115,11 +115,11 @@ int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_
   if (rows >= 4096) {
     const unsigned grid = static_cast<unsigned>((rows + 2 * warps - 1) / (2 * warps));
     layer_norm_kernel<2><<<grid, warps * 32, 0, stream>>>(x, ldx, rows, rows_per_batch, C, gamma, beta, eps, apply_silu,
-                                                          out16, ld16, out_batch_pitch);
+                                                          out16, ld16, out_batch_pitch, mean_out);
   } else {
     const unsigned grid = static_cast<unsigned>((rows + warps - 1) / warps);
     layer_norm_kernel<1><<<grid, warps * 32, 0, stream>>>(x, ldx, rows, rows_per_batch, C, gamma, beta, eps, apply_silu,
-                                                          out16, ld16, out_batch_pitch);
+                                                          out16, ld16, out_batch_pitch, mean_out);
   }
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;
@@ -130,7 +130,8 @@ int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_
 // (C <= 2048: 8 x 16 B per lane), mean first, then the centred sum of squares.  2 B per element in, 8 B per row out.
 // =====================================================================================================
 __global__ void __launch_bounds__(256) row_stats_kernel(const __half* __restrict__ x, long long ld, long long rows, int C,
-                                                        float eps, float2* __restrict__ stats) {
+                                                        float eps, float2* __restrict__ stats,
+                                                        float* __restrict__ shift_io) {
   // two rows per warp, all loads of both rows in flight before the first use; ONE shuffle round per row pair:
   // sums of (x - shift) and (x - shift)^2 with shift = the row's first element (no cancellation for rows with a
   // large common offset), mean = shift + s1/C, var = s2/C - (s1/C)^2
@@ -180,14 +181,18 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const __half* __restrict
     const float inv_c = 1.0f / static_cast<float>(C);
     const float m = (lane == 0 ? s1[0] : s1[1]) * inv_c;
     const float var = fmaxf((lane == 0 ? s2[0] : s2[1]) * inv_c - m * m, 0.f);
-    stats[row0 + lane] = make_float2((lane == 0 ? shift[0] : shift[1]) + m, rsqrtf(var + eps));
+    const float mean = (lane == 0 ? shift[0] : shift[1]) + m;
+    stats[row0 + lane] = make_float2(mean, rsqrtf(var + eps));
+    // the rows are the residual stream minus shift_io[row] (GemmDesc::x16_shift): keep the offsets on the row means
+    if (shift_io != nullptr) shift_io[row0 + lane] += mean;
   }
 }
 
-int row_stats(const __half* x16, int64_t ld, int64_t rows, int C, float eps, float2* stats, cudaStream_t stream) {
+int row_stats(const __half* x16, int64_t ld, int64_t rows, int C, float eps, float2* stats, cudaStream_t stream,
+              float* shift_io) {
   FRT2_REQUIRE(C % 8 == 0 && C <= 2048 && ld % 8 == 0, FRT2_ERR_BAD_ARG, "row_stats: C must be a multiple of 8, <= 2048");
   if (rows == 0) return FRT2_OK;
-  row_stats_kernel<<<static_cast<unsigned>((rows + 15) / 16), 256, 0, stream>>>(x16, ld, rows, C, eps, stats);
+  row_stats_kernel<<<static_cast<unsigned>((rows + 15) / 16), 256, 0, stream>>>(x16, ld, rows, C, eps, stats, shift_io);
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;
 }
@@ -271,17 +276,6 @@ __global__ void __launch_bounds__(256) overlap_add_vec4_kernel(OlaDesc d, int nt
   }
 }
 
-// new tail = last 3 frames of [old tail | frames]; T >= 3 always (a token is 8 frames) so it is a plain copy
-__global__ void update_tail_kernel(const float* __restrict__ frames, long long frames_batch_pitch, float* tail, int T,
-                                   int n_fft, const int* __restrict__ ctrl) {
-  const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 3 * n_fft) return;
-  if (ctrl != nullptr && ctrl[b * CTRL_INTS + CTRL_ACTIVE] == 0) return;   // idle pool slot keeps its tail
-  tail[static_cast<long long>(b) * 3 * n_fft + i] =
-      frames[static_cast<long long>(b) * frames_batch_pitch + static_cast<long long>(T - 3) * n_fft + i];
-}
-
 int istft_overlap_add(const OlaDesc& d, cudaStream_t stream) {
   FRT2_REQUIRE(d.n_fft % d.hop == 0 && d.T >= 1 && d.B >= 1, FRT2_ERR_BAD_ARG, "overlap_add: bad shape");
   const int pad = (d.n_fft - d.hop) / 2;
@@ -307,15 +301,6 @@ int istft_overlap_add(const OlaDesc& d, cudaStream_t stream) {
   }
   dim3 grid((n_out + 255) / 256, d.B);
   overlap_add_kernel<<<grid, 256, 0, stream>>>(d, ntail, start, n_out);
-  FRT2_CUDA_OK(cudaGetLastError());
-  return FRT2_OK;
-}
-
-int istft_update_tail(const float* frames, int64_t frames_batch_pitch, float* tail, int B, int T, int n_fft,
-                      const int* ctrl, cudaStream_t stream) {
-  FRT2_REQUIRE(T >= 3, FRT2_ERR_BAD_ARG, "update_tail: chunk shorter than the iSTFT carry");
-  dim3 grid((3 * n_fft + 255) / 256, B);
-  update_tail_kernel<<<grid, 256, 0, stream>>>(frames, frames_batch_pitch, tail, T, n_fft, ctrl);
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;
 }

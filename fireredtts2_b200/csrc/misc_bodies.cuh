@@ -1,5 +1,4 @@
-// Device-function bodies of the small bandwidth-bound kernels (LayerNorm rows, overlap-add sample), shared by the
-// stand-alone kernels (kernels_misc.cu) and the persistent per-token step kernel (stream_mega.cu).
+// Device-function bodies of the small bandwidth-bound kernels (LayerNorm rows, overlap-add sample) of kernels_misc.cu.
 #pragma once
 #include "common.cuh"
 
@@ -20,7 +19,7 @@ template <int RPW>
 __device__ __forceinline__ void layer_norm_body(const float* x, long long ldx, long long rows, int rows_per_batch, int C,
                                                 const float* gamma, const float* beta, float eps, int apply_silu,
                                                 __half* out16, long long ld16, long long out_batch_pitch,
-                                                long long row0) {
+                                                long long row0, float* mean_out = nullptr) {
   if (row0 >= rows) return;
   const int lane = threadIdx.x & 31;
   const int C4 = C >> 2;
@@ -90,6 +89,7 @@ __device__ __forceinline__ void layer_norm_body(const float* x, long long ldx, l
     }
     const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(C) + eps);
     if (row >= rows) continue;   // (warp-uniform) duplicate of the last row
+    if (mean_out != nullptr && lane == 0) mean_out[row] = mean;
     const long long bidx = row / rows_per_batch;
     const long long t = row - bidx * rows_per_batch;
     uint2* orow = reinterpret_cast<uint2*>(out16 + bidx * out_batch_pitch + t * ld16);

@@ -114,6 +114,44 @@ def synthetic_state_dict(cfg: CodecConfig, seed: int = 0) -> Dict[str, np.ndarra
     return sd
 
 
+def adversarial_state_dict(cfg: CodecConfig, seed: int = 0, mean_offset: float = 12.0, outlier_scale: float = 100.0,
+                           fc1_scale: float = 400.0, fc2_scale: float = 1.0 / 40.0) -> Dict[str, np.ndarray]:
+    """Weights of the same architecture that stress the fp16-operand / folded-LayerNorm path the way a trained
+    checkpoint can (a random init with sigma = 0.02 is the kindest possible input):
+
+    * every LayerNorm gamma log-uniform in [0.1, 5], beta ~ N(0, 0.5);
+    * a constant added to the bias of the convolution that opens the fp32 residual stream (``backbone.in_proj``), so
+      that every row of the stream carries a mean many times its spread;
+    * four outlier channels of that convolution scaled by ``outlier_scale`` ("massive activations");
+    * fc1 scaled up / fc2 scaled down so that the GELU activations reach 1e3 - 1e4 and the residual norm grows with
+      depth.
+
+    Same numpy generator discipline as ``synthetic_state_dict``: regenerated bit for bit on the GPU box and loaded into
+    the real reference in the build container (oracle/make_golden.py) for the golden waveforms."""
+    sd = synthetic_state_dict(cfg, seed)
+    rng = np.random.default_rng(seed + 104729)
+    E = cfg.embed_dim
+    for k in sorted(sd):
+        is_ln = (k.endswith(("block1.1.weight", "block2.1.weight", "layer_norm.weight", "final_norm.weight")))
+        if is_ln:
+            sd[k] = np.exp(rng.uniform(math.log(0.1), math.log(5.0), size=sd[k].shape)).astype(np.float32)
+            sd[k[:-6] + "bias"] = (0.5 * rng.standard_normal(sd[k].shape)).astype(np.float32)
+    bb = PREFIX_AD + "backbone."
+    ch = rng.choice(E, size=4, replace=False)
+    w = sd[bb + "in_proj.weight"].copy()
+    b = sd[bb + "in_proj.bias"].copy()
+    w[ch] *= outlier_scale
+    b[ch] *= outlier_scale
+    b += np.float32(mean_offset)
+    sd[bb + "in_proj.weight"], sd[bb + "in_proj.bias"] = w, b.astype(np.float32)
+    for i in range(cfg.num_layers):
+        t = f"{bb}transformers.{i}."
+        sd[t + "fc1.weight"] = (sd[t + "fc1.weight"] * np.float32(fc1_scale)).astype(np.float32)
+        sd[t + "fc1.bias"] = (sd[t + "fc1.bias"] * np.float32(fc1_scale)).astype(np.float32)
+        sd[t + "fc2.weight"] = (sd[t + "fc2.weight"] * np.float32(fc2_scale)).astype(np.float32)
+    return sd
+
+
 def synthetic_encode_tensors(cfg: CodecConfig, seed: int = 0, input_dim: int = None) -> Dict[str, np.ndarray]:
     """The encode-side tensors of ``ResidualVQ`` that ``synthetic_state_dict`` leaves out (they are not part of the
     decode path): ``rvq.input_proj`` (present iff input_dim != rvq_dim, reference rvq.py:110-114) and every

@@ -103,9 +103,26 @@ int frt2_peer_free(int device, void* ptr);
  * The stream object owns what the reference keeps in cache_dict (up_conv_cache, bb_conv_cache1/2, bb_kv_cache,
  * is_cache) in HBM, updated in place. */
 int frt2_stream_create(frt2_handle* h, int B, int max_tokens, frt2_stream** out);
+/* Back to "no token consumed".  Stream-ordered: nothing runs here; the state is cleared by a kernel on the CUDA stream
+ * of the next decode call, after everything the state's previous user enqueued (no device synchronisation). */
 int frt2_stream_reset(frt2_stream* s);
+/* The reference's call pattern is decode_one_token(token, {}, last) with a fresh cache_dict per utterance
+ * (model.py:346): create / destroy per utterance.  frt2_stream_destroy therefore hands the state (device buffers and the
+ * captured per-token step) back to a small per-handle pool and frt2_stream_create of the same (B, max_tokens) takes it
+ * from there — no allocation, no capture, no synchronisation in the request path.  frt2_stream_reserve fills that pool
+ * ahead of the first request (`count` spare states, per-token step captured). */
 void frt2_stream_destroy(frt2_stream* s);
+int frt2_stream_reserve(frt2_handle* h, int B, int max_tokens, int count);
 int frt2_stream_tokens(const frt2_stream* s); /* tokens consumed so far */
+/* Out-of-range codes are detected on the device, per stream and per batch item / pool slot (the reference raises
+ * IndexError inside the offending decode_one_token, rvq.py:58).  frt2_stream_check_error synchronises cuda_stream, reads
+ * and clears THIS stream's (or pool's) error words and returns FRT2_ERR_INDEX_OUT_OF_RANGE if any item sent a bad code
+ * since the last check; item_flags (host, B entries, optional) receives a non-zero value for each offending item.  A bad
+ * code is decoded as code 0.  frt2_stream_fetch_errors enqueues an asynchronous copy of the 1 + B words (word 0: any
+ * item; word 1 + b: item b) to host_words (pinned host memory) on cuda_stream and neither synchronises nor clears: a
+ * streaming front copies them alongside each chunk and tests word 0 once the chunk's event has completed. */
+int frt2_stream_check_error(frt2_handle* h, frt2_stream* s, int32_t* item_flags, void* cuda_stream);
+int frt2_stream_fetch_errors(frt2_handle* h, frt2_stream* s, uint32_t* host_words, void* cuda_stream);
 /* One chunk of Lc >= 1 tokens per item.  n_samples (host, written before return) =
  * 8*hop*Lc - pad*[first chunk] + pad*[last], pad = (n_fft-hop)/2, exactly as ISTFT.forward_chunk slices
  * (decoder.py:459-467).  Attention inside the chunk is unmasked like the reference's forward_chunk
@@ -184,7 +201,8 @@ int frt2_rvq_gather(frt2_handle* h, const void* tokens, int idx_bytes, int64_t s
  * the decode.  Returns the number of floats written through *n. */
 int frt2_set_debug(frt2_handle* h, int flags);
 int frt2_get_tap(frt2_handle* h, const char* name, float* out, int64_t capacity, int64_t* n, void* cuda_stream);
-/* Synchronise the stream and translate the device-side error word (out-of-range code index) into a status. */
+/* Synchronise the stream and translate the handle's device-side error word (out-of-range code index of an OFFLINE decode /
+ * frt2_rvq_gather since the last check) into a status.  Streams and pools have their own words: frt2_stream_check_error. */
 int frt2_check_error(frt2_handle* h, void* cuda_stream);
 
 /* ---- measurement ----

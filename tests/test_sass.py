@@ -45,6 +45,14 @@ def test_every_kernel_is_compiled_for_sm_100a_only(sass):
     assert all("EF_CUDA_SM100" in b[:600] for b in sass.values())
 
 
+def test_no_shelved_kernels_ship(sass):
+    """Kernels that are off the product path do not ship: one tcgen05 attention kernel, one skinny GEMM family, no
+    persistent step interpreter."""
+    names = " ".join(sass)
+    for gone in ("attention_tc_kernel", "attention_tcp_kernel", "gemm_skinny_fma_kernel", "stream_step_kernel"):
+        assert gone not in names, gone
+
+
 def test_gemm_kernels_run_on_tcgen05_with_tma(sass):
     for name in ("gemm_tc2_kernel", "gemm_tc_kernelILi256", "gemm_tc_kernelILi128"):
         b = _fn(sass, name)
@@ -65,6 +73,6 @@ def test_attention_keeps_p_in_tensor_memory(sass):
 def test_token_step_kernels(sass):
     b = _fn(sass, "gemm_skinny_kernelILi8ELi1")
     assert _count(b, "HMMA") >= 2 and _count(b, "LDGSTS") >= 1                     # mma.sync + cp.async staging
-    assert _count(_fn(sass, "stream_step_kernel"), "HMMA") >= 2
+    assert _count(_fn(sass, "state_roll_kernel"), "STG.E.128") >= 1 and _count(_fn(sass, "state_reset_kernel"), "STG.E.128") >= 1
     assert _count(_fn(sass, "overlap_add_vec4_kernel"), "STG.E.128") >= 1
     assert _count(_fn(sass, "rvq_encode_kernel"), "FFMA") >= 100
