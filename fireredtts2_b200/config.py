@@ -129,4 +129,7 @@ SMALL = CodecConfig(rvq_dim=128, output_dim=256, num_quantizers=8, codebook_size
 MICRO = CodecConfig(rvq_dim=64, output_dim=64, num_quantizers=2, codebook_size=16, codebook_dim=16,
                     embed_dim=64, num_layers=1, num_heads=1)
 
-PRESETS = {"MICRO": MICRO, "C0": C0, "C1": C1, "TINY": TINY, "TINY_IDENT": TINY_IDENT, "SMALL": SMALL}
+# C0 widths with 4 layers: the adversarial-weights parity fixtures (tests/golden/adv4_*)
+ADV4 = dataclasses.replace(C0, num_layers=4)
+
+PRESETS = {"ADV4": ADV4, "MICRO": MICRO, "C0": C0, "C1": C1, "TINY": TINY, "TINY_IDENT": TINY_IDENT, "SMALL": SMALL}

@@ -24,39 +24,16 @@ import torch.nn as nn
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.environ.get("FRT2_REFERENCE", "/root/reference"))
-
-from fireredtts2.codec.decoder import AcousticDecoder  # noqa: E402  (reference)
-from fireredtts2.codec.model import RedCodecInfer, UpConv  # noqa: E402  (reference)
-from fireredtts2.codec.rvq import ResidualVQ  # noqa: E402  (reference)
+os.environ.setdefault("FRT2_REFERENCE", "/root/reference")   # golden vectors come from the read-only checkout itself
 
 from fireredtts2_b200.config import PRESETS, CodecConfig  # noqa: E402
-from fireredtts2_b200.weights import synthetic_state_dict, synthetic_tokens  # noqa: E402
+from fireredtts2_b200.weights import adversarial_state_dict, synthetic_state_dict, synthetic_tokens  # noqa: E402
+from oracle.reference_runner import _import as _import_reference, build_reference  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-
-
-class RefDecodeOnly(RedCodecInfer):
-    """RedCodecInfer with only the three decode-side sub-modules (SURVEY.md §8c recipe)."""
-
-    def __init__(self, cfg: CodecConfig):
-        nn.Module.__init__(self)
-        d = cfg.to_reference_dict()
-        self.rvq = ResidualVQ(**d["rvq"])
-        self.upsample = UpConv(**d["upsample"])
-        self.acoustic_decoder = AcousticDecoder(**d["acoustic_decoder"])
-
-
-def build_reference(cfg: CodecConfig, sd_np):
-    torch.manual_seed(0)
-    m = RefDecodeOnly(cfg).eval()
-    sd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd_np.items()}
-    missing, unexpected = m.load_state_dict(sd, strict=False)
-    assert not unexpected, unexpected
-    enc_only = ("input_proj", "in_project", "inited", "cluster_size", "embed_avg")
-    bad = [k for k in missing if not any(e in k for e in enc_only)]
-    assert not bad, bad
-    return m
+RefDecodeOnly, _REF_ROOT = _import_reference()
+assert _REF_ROOT == "/root/reference", _REF_ROOT
+WEIGHTS = {"synthetic": synthetic_state_dict, "adversarial": adversarial_state_dict}
 
 
 def record_intermediates(m, tokens):
@@ -88,9 +65,9 @@ def record_intermediates(m, tokens):
     return taps
 
 
-def case_offline(name, preset, B, L, wseed, tseed, idx_dtype, keep):
+def case_offline(name, preset, B, L, wseed, tseed, idx_dtype, keep, weights="synthetic"):
     cfg = PRESETS[preset]
-    sd = synthetic_state_dict(cfg, wseed)
+    sd = WEIGHTS[weights](cfg, wseed)
     m = build_reference(cfg, sd)
     tok = synthetic_tokens(cfg, B, L, tseed, np.int64)
     t = torch.from_numpy(tok)
@@ -101,13 +78,14 @@ def case_offline(name, preset, B, L, wseed, tseed, idx_dtype, keep):
     out = {k: taps[k] for k in keep}
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), tokens=tok, **out)
     return dict(name=name, kind="offline", preset=preset, B=B, L=L, wseed=wseed, tseed=tseed,
-                idx=idx_dtype, keys=sorted(out))
+                idx=idx_dtype, keys=sorted(out), weights=weights)
 
 
-def case_stream(name, preset, B, L, wseed, tseed, chunks):
-    """decode_one_token over `chunks` (list of chunk lengths summing to L)."""
+def case_stream(name, preset, B, L, wseed, tseed, chunks, weights="synthetic", keep_kv=True, keep_offline=True):
+    """decode_one_token over `chunks` (list of chunk lengths summing to L).  keep_kv=False drops bb_kv_cache from the
+    fixture (12.6 MB after 16 tokens at C0); the four small caches are always kept."""
     cfg = PRESETS[preset]
-    sd = synthetic_state_dict(cfg, wseed)
+    sd = WEIGHTS[weights](cfg, wseed)
     m = build_reference(cfg, sd)
     tok = synthetic_tokens(cfg, B, L, tseed, np.int64)
     t = torch.from_numpy(tok)
@@ -121,12 +99,31 @@ def case_stream(name, preset, B, L, wseed, tseed, chunks):
             pos += lc
         offline = m.decode(t).numpy()
     save = {f"audio_{i}": o for i, o in enumerate(outs)}
-    save.update({"cache_" + k: v.numpy().copy() for k, v in cache.items()})
-    save["offline"] = offline
+    save.update({"cache_" + k: v.numpy().copy() for k, v in cache.items() if keep_kv or k != "bb_kv_cache"})
+    if keep_offline:
+        save["offline"] = offline
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), tokens=tok, chunks=np.asarray(chunks), **save)
     cat = np.concatenate(outs, axis=1)
-    return dict(name=name, kind="stream", preset=preset, B=B, L=L, wseed=wseed, tseed=tseed,
+    return dict(name=name, kind="stream", preset=preset, B=B, L=L, wseed=wseed, tseed=tseed, weights=weights,
                 chunks=list(chunks), stream_vs_offline_maxabs=float(np.abs(cat - offline).max()))
+
+
+def case_rvq_emb(name, preset, B, L, wseed, tseed):
+    """ResidualVQ.decode_codes on an Identity-out_project config (C1): the index-ordered fp32 sum `emb` is what reaches
+    rvq.output_proj (captured with a forward pre-hook) and must be reproduced bit for bit (rvq.py:145-164)."""
+    cfg = PRESETS[preset]
+    assert not cfg.has_out_project
+    sd = synthetic_state_dict(cfg, wseed)
+    m = build_reference(cfg, sd)
+    tok = synthetic_tokens(cfg, B, L, tseed, np.int64)
+    got = {}
+    h = m.rvq.output_proj.register_forward_pre_hook(lambda _m, inp: got.__setitem__("emb", inp[0].detach().numpy().copy()))
+    with torch.inference_mode():
+        z = m.rvq.decode_codes(torch.from_numpy(tok).permute(1, 0, 2))
+    h.remove()
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), tokens=tok, emb=got["emb"].transpose(0, 2, 1).copy(),
+                        z=z.numpy().transpose(0, 2, 1).copy())
+    return dict(name=name, kind="rvq_emb", preset=preset, B=B, L=L, wseed=wseed, tseed=tseed)
 
 
 def case_reference_init(name, preset, L):
@@ -162,6 +159,22 @@ def main():
     man.append(case_reference_init("micro_refinit", "MICRO", 5))
     # C0 (the benchmark architecture), config-1 shape shortened to 25 tokens (2 s) to keep the fixture small
     man.append(case_offline("c0_offline_L25", "C0", 1, 25, 0, 1234, "int64", ["audio"]))
+    # ---- the BASELINE.json configs themselves ----
+    # configs[0]: one 10 s monologue, C0
+    man.append(case_offline("c0_offline_L125", "C0", 1, 125, 0, 1234, "int64", ["audio"]))
+    # configs[2] item shape: one 30 s utterance, C0 (the benchmark decodes 64 of these per step)
+    man.append(case_offline("c0_offline_L375", "C0", 1, 375, 0, 4242, "int64", ["audio"]))
+    # configs[1]: streaming, batch 1, one token per call, C0 — 16 tokens, and 72 tokens (> 512 frames of K/V state: the
+    # step's attention is then split over several CTAs per head)
+    man.append(case_stream("c0_stream_16", "C0", 1, 16, 0, 777, [1] * 16, keep_kv=False, keep_offline=False))
+    man.append(case_stream("c0_stream_72", "C0", 1, 72, 0, 778, [1] * 72, keep_kv=False, keep_offline=False))
+    # C1 = C0 with Identity out_project: the bit-exact index-ordered sum at C0 dimensions
+    man.append(case_rvq_emb("c1_rvq_emb", "C1", 2, 20, 0, 31))
+    # adversarial weights (weights.adversarial_state_dict): LayerNorm gamma in [0.1, 5], row mean ~ 50 x row spread,
+    # outlier channels x 100, GELU activations in the thousands — 4 layers at the C0 widths
+    man.append(case_offline("adv4_offline", "ADV4", 2, 40, 0, 99, "int64", ["audio"], weights="adversarial"))
+    man.append(case_stream("adv4_stream_12", "ADV4", 1, 12, 0, 98, [1] * 12, weights="adversarial", keep_kv=False,
+                           keep_offline=False))
     with open(os.path.join(GOLDEN, "MANIFEST.json"), "w") as f:
         json.dump({"generator": "oracle/make_golden.py", "torch": torch.__version__, "cases": man}, f, indent=1)
     for c in man:

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 from fireredtts2_b200.config import PRESETS
-from fireredtts2_b200.weights import synthetic_state_dict
+from fireredtts2_b200.weights import adversarial_state_dict, synthetic_state_dict
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -25,6 +25,8 @@ def load_case(case):
     cfg = PRESETS[case["preset"]]
     if case["kind"] == "reference_init":
         sd = {k[4:]: g[k] for k in g.files if k.startswith("sd::")}
+    elif case.get("weights") == "adversarial":
+        sd = adversarial_state_dict(cfg, case["wseed"])
     else:
         sd = synthetic_state_dict(cfg, case["wseed"])
     return cfg, sd, g

@@ -29,8 +29,8 @@ def _gate(name, ref, out):
 
 
 @pytest.mark.parametrize("mode", ["simt_gemm+warp_attn", "tc_gemm+warp_attn", "product"])
-@pytest.mark.parametrize("case", [c for c in cases("offline") + cases("reference_init") if c["preset"] != "C0"],
-                         ids=lambda c: c["name"])
+@pytest.mark.parametrize("case", [c for c in cases("offline") + cases("reference_init")
+                                  if c["preset"] not in ("C0", "ADV4")], ids=lambda c: c["name"])
 def test_offline_decode_vs_reference_golden(case, mode):
     cfg, sd, g = load_case(case)
     codec = build_codec(cfg, sd)
@@ -69,7 +69,84 @@ def test_folded_layernorm_vs_reference_golden(case):
     _gate(f"{case['name']}/ln-folded", g["audio"], folded)
     _gate(f"{case['name']}/ln-kernels", g["audio"], plain)
     _, snr = report(f"{case['name']}/folded-vs-kernels", plain, folded)
-    assert snr >= 50.0
+    assert snr >= (45.0 if case.get("weights") == "adversarial" else 50.0)
+
+
+def test_adversarial_weights_keep_the_gate():
+    """Weights that stress fp16 operands and the folded LayerNorm the way a trained checkpoint can (LayerNorm gamma in
+    [0.1, 5], residual rows at ~100 +- 2, four outlier channels x 100, GELU activations in the thousands; 4 layers at the
+    C0 widths; weights.adversarial_state_dict) against the real reference's waveform on the same weights.  Reported: the
+    product path (fp16 copy rounded after subtracting the row mean), the same path with the plain fp16(x) copy it
+    replaces (FRT2_NO_LNSHIFT=1 is read once per process, so that variant is only reported by tools/adv_report.py), and
+    separate LayerNorm kernels."""
+    case = [c for c in cases("offline") if c["name"] == "adv4_offline"][0]
+    cfg, sd, g = load_case(case)
+    codec = build_codec(cfg, sd)
+    tok = torch.from_numpy(g["tokens"]).cuda()
+    folded = to_np(codec.decode(tok))
+    _, snr_f = report("adv4/product (folded LayerNorm, mean-shifted copy)", g["audio"], folded)
+    codec.set_debug(N.DBG_NO_LNFOLD)
+    plain = to_np(codec.decode(tok))
+    _, snr_p = report("adv4/separate LayerNorm kernels", g["audio"], plain)
+    assert snr_f >= SNR_GATE_DB and snr_p >= SNR_GATE_DB
+    assert snr_f >= snr_p - 3.0, "the folded form must not cost more than 3 dB against separate LayerNorm kernels"
+    # batch rows are independent here too
+    codec.set_debug(0)
+    one = to_np(codec.decode(tok[1:2]))
+    assert np.array_equal(one[0], folded[1])
+
+
+@pytest.mark.parametrize("case", cases("rvq_emb"), ids=lambda c: c["name"])
+def test_c1_rvq_sum_bit_exact_vs_reference(case):
+    """C1 = C0 with Identity out_project: gathered rows and the index-ordered fp32 sum at the C0 dimensions
+    (16 codebooks x 2048 x 256), bit for bit against the REAL reference's tensor (captured in front of rvq.output_proj)."""
+    cfg, sd, g = load_case(case)
+    codec = build_codec(cfg, sd)
+    for dtype in (torch.int64, torch.int32):
+        tok = torch.from_numpy(g["tokens"]).cuda().to(dtype)
+        rows, s = codec.rvq_gather(tok)
+        assert np.array_equal(to_np(s), g["emb"])
+        assert np.array_equal(to_np(rows), O.rvq_gather(sd, g["tokens"]))
+    codec.set_debug(N.DBG_TAPS)
+    codec.decode(torch.from_numpy(g["tokens"]).cuda())
+    B, L = case["B"], case["L"]
+    assert np.array_equal(to_np(codec.get_tap("emb", (B, L, cfg.rvq_dim))), g["emb"])     # the decode path's own sum
+    _, snr = report("c1/z", g["z"], to_np(codec.get_tap("z", (B, L, cfg.embed_dim))))
+    assert snr > 45.0
+
+
+def test_c0_varlen_distinct_items_multi_wave():
+    """14 DISTINCT C0 items of different lengths in one padded batch (every GEMM of the step runs several waves of
+    tiles): every item must equal the standalone decode of its own first L_b tokens bit for bit — rows never see their
+    neighbours — and two of them are checked against the oracle."""
+    from fireredtts2_b200.config import C0
+    from fireredtts2_b200.weights import synthetic_state_dict, synthetic_tokens
+    cfg = C0
+    sd = synthetic_state_dict(cfg, 0)
+    codec = build_codec(cfg, sd)
+    rng = np.random.default_rng(5)
+    Bn, L = 14, 170
+    lens = [int(x) for x in rng.integers(60, L + 1, size=Bn)]
+    lens[3] = L
+    tok_np = synthetic_tokens(cfg, Bn, L, 4321)
+    tok = torch.from_numpy(tok_np).cuda()
+    spt = cfg.samples_per_token
+    for flags in (0, N.DBG_NO_LNFOLD):
+        codec.set_debug(flags)
+        batch = codec.decode(tok, lengths=torch.tensor(lens, dtype=torch.int32))
+        worst = 0.0
+        for b in range(Bn):
+            single = codec.decode(tok[b:b + 1, :, :lens[b]])
+            worst = max(worst, float((batch[b, :lens[b] * spt] - single[0]).abs().max()))
+            if lens[b] < L:
+                assert float(batch[b, lens[b] * spt:].abs().max()) == 0.0
+        print(f"[parity] c0 14 distinct var-len items, debug {flags}: max |item - standalone| = {worst:.3e}")
+        assert worst == 0.0
+    codec.set_debug(0)
+    batch = to_np(codec.decode(tok, lengths=torch.tensor(lens, dtype=torch.int32)))
+    for b in (0, 9):
+        ref = O.decode(sd, tok_np[b:b + 1, :, :lens[b]], cfg.num_heads, cfg.hop_length)
+        _gate(f"c0-varlen/item{b}", ref, batch[b:b + 1, :lens[b] * spt])
 
 
 def test_c0_offline_vs_reference_golden():
@@ -215,7 +292,7 @@ def test_scatter_decode_equals_padded_decode_bitwise():
 @pytest.mark.parametrize("case", cases("stream"), ids=lambda c: c["name"])
 def test_streaming_vs_reference_golden(case, mode):
     cfg, sd, g = load_case(case)
-    codec = build_codec(cfg, sd, stream_max_tokens=32)
+    codec = build_codec(cfg, sd, stream_max_tokens=max(32, case["L"] + 1))
     codec.set_debug(MODES[mode])
     tok = torch.from_numpy(g["tokens"]).cuda()
     chunks = list(g["chunks"])
@@ -231,6 +308,9 @@ def test_streaming_vs_reference_golden(case, mode):
     _gate(f"{case['name']}/{mode}/stream-audio", refcat, cat)
     exported = codec.export_cache(cache)
     for k, v in exported.items():
+        if "cache_" + k not in g.files:      # the K/V cache of the C0-width fixtures is not stored (12.6 MB per 16 tokens)
+            assert k == "bb_kv_cache"
+            continue
         ref = g["cache_" + k]
         assert tuple(v.shape) == ref.shape, k
         _, snr = report(f"{case['name']}/{mode}/cache/{k}", ref, to_np(v))

@@ -8,6 +8,15 @@ from tests.helpers import cases, load_case
 
 TOL_AUDIO = 2e-6      # fp32 vs fp32, different summation orders (observed <= 2.2e-7)
 TOL_FEAT = 2e-5       # intermediates have magnitudes of a few units (observed <= 4.3e-6)
+# adversarial weights (weights.adversarial_state_dict): activations in the thousands and a residual stream whose rows sit
+# at ~100 +- 2 put the fp32 noise floor of ANY summation order at ~1e-4 of a 0.4 peak — the reference's own streaming vs
+# offline decode differ by 1.0e-4 on these weights (MANIFEST stream_vs_offline_maxabs)
+TOL_AUDIO_ADV = 1e-3
+SNR_ADV_DB = 60.0
+
+
+def _tol(case):
+    return TOL_AUDIO_ADV if case.get("weights") == "adversarial" else TOL_AUDIO
 
 
 @pytest.mark.parametrize("case", cases("offline") + cases("reference_init"), ids=lambda c: c["name"])
@@ -16,8 +25,8 @@ def test_offline_decode_matches_reference(case):
     taps = {}
     y = O.decode(sd, g["tokens"], cfg.num_heads, cfg.hop_length, taps=taps)
     assert y.shape == g["audio"].shape == (case["B"], case["L"] * cfg.samples_per_token)
-    assert np.abs(y - g["audio"]).max() < TOL_AUDIO
-    assert O.snr_db(g["audio"], y) > 100.0
+    assert np.abs(y - g["audio"]).max() < _tol(case)
+    assert O.snr_db(g["audio"], y) > (SNR_ADV_DB if case.get("weights") == "adversarial" else 100.0)
     for k in ("z", "x50", "prior", "layer0", "final"):
         if k in g.files:
             assert np.abs(taps[k] - g[k]).max() < TOL_FEAT, k
@@ -37,19 +46,33 @@ def test_streaming_decode_matches_reference(case):
         first, last = i == 0, i == len(chunks) - 1
         n = cfg.samples_per_token * lc - cfg.istft_pad * first + cfg.istft_pad * last
         assert y.shape == ref.shape == (case["B"], n)
-        assert np.abs(y - ref).max() < TOL_AUDIO
+        assert np.abs(y - ref).max() < _tol(case)
         outs.append(y)
         pos += lc
+    adv = case.get("weights") == "adversarial"
     for k, v in st.to_reference_layout(cfg.num_heads).items():
+        if "cache_" + k not in g.files:     # the large K/V cache is not stored for the C0-width fixtures
+            assert k == "bb_kv_cache"
+            continue
         ref = g["cache_" + k]
         assert v.shape == ref.shape, k
-        assert np.abs(v - ref).max() < TOL_FEAT, k
+        assert np.abs(v - ref).max() < (TOL_FEAT if not adv else 1e-3 * max(1.0, float(np.abs(ref).max()))), k
     # one token per call == offline (block of 8 frames == one token); multi-token chunks are unmasked
     # inside the chunk (whisper.py:107-113) and legitimately differ from offline.
     cat = np.concatenate(outs, axis=1)
-    if all(c == 1 for c in chunks):
+    assert cat.shape == (case["B"], case["L"] * cfg.samples_per_token)
+    if "offline" in g.files and all(c == 1 for c in chunks):
         assert np.abs(cat - g["offline"]).max() < TOL_AUDIO
-    assert cat.shape == g["offline"].shape
+
+
+@pytest.mark.parametrize("case", cases("rvq_emb"), ids=lambda c: c["name"])
+def test_rvq_sum_matches_reference_bit_for_bit(case):
+    """C1 (C0 with Identity out_project): the index-ordered fp32 sum that reaches rvq.output_proj in the real
+    reference (captured with a forward pre-hook by oracle/make_golden.py) equals the oracle's, bit for bit."""
+    cfg, sd, g = load_case(case)
+    emb, z = O.rvq_decode_codes(sd, g["tokens"])
+    assert emb.shape == g["emb"].shape and np.array_equal(emb, g["emb"])
+    assert np.abs(z - g["z"]).max() < TOL_FEAT
 
 
 def test_identity_projection_sum_is_index_ordered():
@@ -101,7 +124,7 @@ def test_torch_cpu_port_matches_reference(case):
     cfg, sd, g = load_case(case)
     y = OT.decode(OT.to_torch(sd), g["tokens"], cfg.num_heads, cfg.hop_length).numpy()
     assert y.shape == g["audio"].shape
-    assert np.abs(y - g["audio"]).max() < TOL_AUDIO
+    assert np.abs(y - g["audio"]).max() < _tol(case)
 
 
 def _resample_cases():
