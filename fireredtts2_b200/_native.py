@@ -78,6 +78,7 @@ SIGNATURES = {
     "frt2_op_gemm": (_i, [_i, _p, _p, _i, _i, _i, _i, _i, _f, _p, _i, _p, _p, _p, _p]),
     "frt2_op_layer_norm": (_i, [_p, _i, _i, _p, _p, _f, _i, _p, _p]),
     "frt2_op_attention": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "frt2_op_attention_trace": (_i, [_p]),
     "frt2_op_overlap_add": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
     "frt2_last_error": (C.c_char_p, []),
     "frt2_version": (C.c_char_p, []),

@@ -167,11 +167,15 @@ struct AttnDesc {
   // part: (B*H, ATTN_KSPLIT, 8, hd + 2) floats, part_count: (B*H) ints, zero-initialised (each use leaves them zero)
   float* part;
   int* part_count;
+  // optional (attention_tc): two zero-initialised device words for the persistent kernel's item scheduler (each launch
+  // leaves them zero); launches sharing a pair must be stream-ordered.  nullptr: a library-owned ring is used.
+  unsigned int* sched;
 };
 constexpr int ATTN_KSPLIT = 8;
 int attention_warp(const AttnDesc& a, cudaStream_t stream);  // CUDA-core, one warp per 8-query block
-int attention_tc(const AttnDesc& a, cudaStream_t stream);    // tcgen05 flash attention (hd == 64)
+int attention_tc(const AttnDesc& a, cudaStream_t stream);    // tcgen05 flash attention (hd == 64 or 128)
 int attention_tc_init();
+void attention_tc_set_trace(void* dev_buf);
 
 // ---- misc kernels ----
 int rvq_gather_sum(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B, int nq, int L,

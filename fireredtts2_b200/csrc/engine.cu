@@ -393,7 +393,7 @@ struct Handle {
     }
     const double flops = 4.0 * a.hd * pairs * a.B * a.H;
     const double bytes = 2.0 * a.B * a.H * a.hd * (2.0 * a.Tq + 2.0 * a.Tk);
-    const bool warp = (debug & DBG_ATTN_WARP) || a.hd != 64 || a.Tq < 32;
+    const bool warp = (debug & DBG_ATTN_WARP) || (a.hd != 64 && a.hd != 128) || a.Tq < 32;
     const int id = prof_begin(warp ? FRT2_PROF_ATTN_WARP : FRT2_PROF_ATTN_TC, flops, bytes, st);
     const int rc = warp ? attention_warp(a, st) : attention_tc(a, st);
     prof_end(id, st);
@@ -805,8 +805,10 @@ int Handle::finalize() {
     }
     FRT2_TRY(upload_f16(Bm, &w_idft));
   }
-  FRT2_TRY(dev_alloc(reinterpret_cast<void**>(&err_word), 4));
-  FRT2_CUDA_OK(cudaMemset(err_word, 0, 4));
+  // err_word[0]: device error word; err_word[2..3]: item scheduler of the persistent attention kernel (offline arena
+  // users are stream-ordered by ws_acquire, so one pair per handle is enough)
+  FRT2_TRY(dev_alloc(reinterpret_cast<void**>(&err_word), 16));
+  FRT2_CUDA_OK(cudaMemset(err_word, 0, 16));
   raw.clear();
   finalized = true;
   return FRT2_OK;
@@ -1061,6 +1063,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
       a.q = qkv16; a.q_row_pitch = 3 * E; a.q_batch_pitch = static_cast<int64_t>(T) * 3 * E;
       a.k = qkv16 + E; a.v = qkv16 + 2 * E; a.kv_row_pitch = 3 * E; a.kv_batch_pitch = a.q_batch_pitch;
       a.Tk = T; a.q_pos0 = 0; a.block_causal = 1;
+      a.sched = err_word + 2;
     } else {
       // Q for the chunk; K|V appended in place to the HBM state of this layer (no re-copy: reference
       // whisper.py:100-104 + decoder.py:306 re-concatenate the whole cache every step)
@@ -2055,6 +2058,11 @@ int frt2_op_attention(int impl, const void* q16, const void* k16, const void* v1
   a.scale = 1.0f / std::sqrt(static_cast<float>(hd));
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   return impl == 0 ? attention_tc(a, st) : attention_warp(a, st);
+}
+
+int frt2_op_attention_trace(void* dev_buf) {
+  attention_tc_set_trace(dev_buf);
+  return FRT2_OK;
 }
 
 int frt2_op_overlap_add(const float* frames, const float* tail, const float* window, const int32_t* lengths,

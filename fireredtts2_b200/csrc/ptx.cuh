@@ -107,6 +107,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > (1u << 26)) __trap();
   }
 }
+// pure spin (never suspended by the hardware): lowest wake-up latency, costs issue slots while it waits
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t spins = 0;
+  while (!mbar_test(a, parity)) {
+    if (++spins > (1u << 28)) __trap();
+  }
+}
 // wait that is expected to find the phase already complete: probe without suspending first
 __device__ __forceinline__ void mbar_wait_likely_ready(uint32_t bar, uint32_t parity) {
   if (!mbar_test(bar, parity)) mbar_wait(bar, parity);
@@ -238,6 +246,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ int4 ld_shared_v4(uint32_t addr) {
+  int4 v;
+  asm volatile("ld.volatile.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }

@@ -227,6 +227,9 @@ int frt2_op_layer_norm(const float* x, int rows, int C, const float* gamma, cons
 /* q,k,v,out: fp16 (B,T,H*hd) contiguous.  impl 0 = tcgen05 flash kernel, 1 = warp kernel. */
 int frt2_op_attention(int impl, const void* q16, const void* k16, const void* v16, void* out16, int B, int H,
                       int hd, int Tq, int Tk, int q_pos0, int block_causal, void* cuda_stream);
+/* debug: while dev_buf (16*128*8 uint32, device) is set, CTA 0 of the persistent tcgen05 attention kernel writes
+ * clock64 stamps of its softmax / MMA-issue phases there (tools/attn_trace.py); NULL switches it off. */
+int frt2_op_attention_trace(void* dev_buf);
 int frt2_op_overlap_add(const float* frames, const float* tail, const float* window, const int32_t* lengths,
                         float* audio, int64_t audio_pitch, int B, int T, int n_fft, int hop, int first, int last,
                         void* cuda_stream);

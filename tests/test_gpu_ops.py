@@ -157,6 +157,16 @@ ATTN_CASES = [
     (2, 1, 64, 264, 264, 0, 1),
     (1, 1, 64, 136, 392, 256, 0),
     (1, 3, 64, 520, 520, 0, 1),
+    # more work items than SMs: every CTA of the persistent kernel walks through several (group, head, item) items
+    (4, 16, 64, 1504, 1504, 0, 1),
+    (40, 8, 64, 264, 264, 0, 1),
+    # head dim 128 (two query tiles per CTA)
+    (1, 2, 128, 72, 72, 0, 1),
+    (2, 8, 128, 1000, 1000, 0, 1),
+    (3, 8, 128, 1504, 1504, 0, 1),
+    (2, 2, 128, 32, 232, 200, 0),
+    (1, 1, 128, 136, 392, 256, 0),
+    (24, 8, 128, 200, 200, 0, 1),
 ]
 
 
@@ -177,6 +187,31 @@ def test_attention(lib, impl, case):
     print(f"attention impl={impl} {case}: max-abs err {err:.3e}")
     assert torch.isfinite(out.float()).all()
     assert err < (2e-3 if impl == 1 else 4e-3), err
+
+
+@pytest.mark.parametrize("hd", [64, 128])
+def test_attention_tc_sharp_rows_and_repeated_launches(lib, hd):
+    """Logits with a large spread: row maxima keep growing by more than the lazy-rescale threshold (2^8) along the
+    keys, so the speculative exponentials are redone after rescaling O.  Launched three times back to back: the item
+    scheduler's device counters re-arm themselves at the end of every launch."""
+    B, H, Tq = 3, 8, 1100
+    E = H * hd
+    g = torch.Generator(device="cuda").manual_seed(11)
+    ramp = torch.linspace(0.5, 5.0, Tq, device="cuda")[None, :, None]
+    q = (torch.randn(B, Tq, E, device="cuda", generator=g) * 2.0).half()
+    k = (torch.randn(B, Tq, E, device="cuda", generator=g) * ramp).half()   # later keys score higher and higher
+    v = torch.randn(B, Tq, E, device="cuda", generator=g).half()
+    ref = attention_reference(q, k, v, H, 0, 1)
+    outs = []
+    for _ in range(3):
+        out = torch.full((B, Tq, E), float("nan"), device="cuda", dtype=torch.half)
+        _check(lib, lib.frt2_op_attention(0, _p(q), _p(k), _p(v), _p(out), B, H, hd, Tq, Tq, 0, 1, _stream()))
+        outs.append(out)
+    torch.cuda.synchronize()
+    err = (outs[0].float() - ref).abs().max().item()
+    print(f"attention tc sharp hd={hd}: max-abs err {err:.3e}")
+    assert torch.isfinite(outs[0].float()).all() and err < 8e-3, err
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
 @pytest.mark.parametrize("B,T,first,last,use_tail", [(2, 24, 1, 1, 0), (1, 8, 1, 0, 1), (2, 8, 0, 0, 1),

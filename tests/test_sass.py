@@ -64,10 +64,15 @@ def test_gemm_kernels_run_on_tcgen05_with_tma(sass):
 
 
 def test_attention_keeps_p_in_tensor_memory(sass):
-    b = _fn(sass, "attention_t3_kernel")
-    assert _count(b, "UTCHMMA") >= 8 and _count(b, "UTMALDG") >= 3
-    assert _count(b, "STTM") >= 1 and _count(b, "LDTM") >= 2                       # P written to / S, O read from TMEM
-    assert _count(b, "MUFU.EX2") >= 64 and _count(b, "HMMA") == 0
+    # product kernels: persistent, head dim 64 (3 query tiles, a quarter of the exponentials on the FMA pipe) and 128
+    for name, min_ex2 in (("attention_t4_kernelILi64ELi3ELb1ELb0ELi2", 48), ("attention_t4_kernelILi128ELi2ELb1ELb0ELi2", 48),
+                          ("attention_t3_kernel", 64)):   # t3: the one predecessor kept for A/B (FRT2_ATTN_VER=3)
+        b = _fn(sass, name)
+        assert _count(b, "UTCHMMA") >= 8 and _count(b, "UTMALDG") >= 3, name
+        assert _count(b, "STTM") >= 1 and _count(b, "LDTM") >= 2, name             # P written to / S, O read from TMEM
+        assert _count(b, "MUFU.EX2") >= min_ex2 and _count(b, "HMMA") == 0, name
+    b = _fn(sass, "attention_t4_kernelILi64ELi3ELb1ELb0ELi2")
+    assert _count(b, "FFMA2") >= 32 + 8 * 4                                        # scale/subtract + the polynomial 2^x pairs
 
 
 def test_token_step_kernels(sass):
