@@ -587,6 +587,10 @@ def run_ours(args):
 
     # ---- first-chunk latency (BASELINE configs[1]): batch 1, one token, host token in -> host audio out ----
     lat = first_chunk_latency(codec, cfg, dev, reps=args.latency_reps)
+    try:
+        lat["generate_stream_overlap"] = llm_overlap(codec, cfg, dev)
+    except Exception as e:      # noqa: BLE001 — an extra record must never cost the bench line
+        lat["generate_stream_overlap"] = {"unavailable": repr(e)}
 
     cfg_out = dict(WORKLOAD, batch=B, tokens_per_item=L,
                    parallelism=(f"utterance-sharded x{world}; gather of the waveforms to rank 0 inside the timed regions: "
@@ -729,6 +733,118 @@ def first_chunk_latency(codec, cfg, dev, reps=200):
                          "frac": wbytes / (step_us * 1e-6) / 1e9 / hbm,
                          "note": "every fp16 weight of the decode path streamed once per 80 ms token (weights exceed the "
                                  "126 MB L2); the step is a chain of ~90 dependent <= 16-row kernels, i.e. latency-bound"}}
+
+
+def llm_overlap(codec, cfg, dev, frames=96, producer_ms=(4.0, 12.0)):
+    """SURVEY 8f.1 — the codec half of the reference's ``generate_stream`` (fireredtts2.py:259-343) next to a SIMULATED
+    frame producer.  The LLM is out of scope, so the producer is a stand-in with the same shape of work: per frame a
+    chain of dependent batch-1 matrix-vector products that streams `weight_mb` of fp16 weights from HBM on the caller's
+    stream (the dual transformer emits one 16-code frame per 80 ms of audio) and then publishes that frame's codes.
+
+      serial     the reference's loop: frame i, then ``decode_one_token(frame i-1)`` on the SAME stream, then the chunk is
+                 read to the host (``yield audio_chunk``) before frame i+1 is started
+      overlapped ``StreamDecoder.push``: the codec step + its device->host copy run on a side stream that only waits
+                 for the frame's codes; the producer's next frame is enqueued at once; nothing synchronises per frame
+
+    Reports wall time per frame of both, of the producer alone, and the device-side delay from "codes of frame i
+    complete" to "chunk i in pinned host memory" while the producer of frame i+1 is running."""
+    import torch
+    from fireredtts2_b200.codec import StreamDecoder
+    from fireredtts2_b200.weights import synthetic_tokens
+    tok = torch.from_numpy(synthetic_tokens(cfg, 1, frames, 21)).to(dev)          # (1, nq, frames)
+    codes = tok[0].t().contiguous()                                               # (frames, nq)
+    D, layers = 4096, 12
+    Wp = [torch.randn(D, D, device=dev, dtype=torch.float16) * 0.01 for _ in range(layers)]
+    x0 = torch.randn(1, D, device=dev, dtype=torch.float16)
+    slot = torch.zeros(cfg.num_quantizers, dtype=codes.dtype, device=dev)
+
+    def chain(reps):
+        x = x0
+        for _ in range(reps):
+            for w in Wp:
+                x = torch.tanh(x @ w)
+        return x
+
+    # calibrate: repetitions of the 12-matvec chain per frame for the requested producer time
+    torch.cuda.synchronize()
+    for _ in range(3):
+        chain(4)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    chain(20)
+    torch.cuda.synchronize()
+    per_rep_ms = 1e3 * (time.perf_counter() - t0) / 20
+    out = {"workload": "BASELINE configs[1] in a generate_stream loop: simulated frame producer (dependent batch-1 "
+                       f"matvec chain over {layers} x {D}x{D} fp16 weights per repetition, {per_rep_ms:.3f} ms each) + "
+                       "the codec step per frame, batch 1, int16 PCM chunks to pinned host memory", "frames": frames,
+           "cases": []}
+    host = torch.empty((1, cfg.samples_per_token + cfg.istft_pad), dtype=torch.int16).pin_memory()
+    for want_ms in producer_ms:
+        reps = max(1, int(round(want_ms / per_rep_ms)))
+
+        def produce(i):
+            x = chain(reps)
+            # the frame's codes become available when the producer's last kernel has run
+            return codes[i] + (x[0, :1] * 0).to(codes.dtype)
+
+        def run_producer_only():
+            for i in range(frames):
+                produce(i)
+            torch.cuda.synchronize()
+
+        def run_serial():
+            cache, prev = {}, None
+            for i in range(frames):
+                s = produce(i)
+                if prev is not None:
+                    a, cache = codec.decode_one_token(prev.view(1, -1, 1), cache, False, pcm16=True)
+                    host[:, :a.shape[1]].copy_(a, non_blocking=True)
+                    torch.cuda.current_stream().synchronize()      # the consumer gets the chunk before the next frame
+                prev = s
+            a, cache = codec.decode_one_token(prev.view(1, -1, 1), cache, True, pcm16=True)
+            host[:, :a.shape[1]].copy_(a, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        def run_overlapped(measure=False):
+            dec = StreamDecoder(codec, pcm16=True, ring=frames + 2, timing=measure)
+            marks, readies = [], []
+            for i in range(frames):
+                s = produce(i)
+                if measure:
+                    ev = torch.cuda.Event(enable_timing=True)
+                    ev.record()
+                    marks.append(ev)
+                c = dec.push(s)
+                if c is not None:
+                    readies.append(c.ready)
+            c = dec.finish()
+            readies.append(c.ready)
+            c.ready.synchronize()
+            torch.cuda.synchronize()
+            if measure:   # device clock: codes of frame i complete -> chunk i in pinned host memory
+                return sorted(m.elapsed_time(r) for m, r in zip(marks, readies))
+            return None
+
+        res = {}
+        for name, fn in (("producer_only", run_producer_only), ("serial", run_serial), ("overlapped", run_overlapped)):
+            fn()
+            ts = []
+            for _ in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                fn()
+                ts.append(1e3 * (time.perf_counter() - t0) / frames)
+            res[name] = min(ts)
+        rec = {"producer_ms_per_frame": res["producer_only"], "serial_ms_per_frame": res["serial"],
+               "overlapped_ms_per_frame": res["overlapped"],
+               "codec_cost_serial_ms": res["serial"] - res["producer_only"],
+               "codec_cost_overlapped_ms": res["overlapped"] - res["producer_only"],
+               "audio_ms_per_frame": 80.0}
+        d = run_overlapped(measure=True)
+        rec["codes_ready_to_chunk_on_host_ms_p50"] = d[len(d) // 2]
+        rec["codes_ready_to_chunk_on_host_ms_p99"] = d[min(len(d) - 1, int(0.99 * len(d)))]
+        out["cases"].append(rec)
+    return out
 
 
 def main():

@@ -30,6 +30,12 @@ class Frt2Config(C.Structure):
         "num_layers", "num_heads", "hop_length", "upconv_stride")]
 
 
+class Frt2EncConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "ssl_in_dim", "ssl_embed_dim", "ssl_out_dim", "ssl_num_layers", "ssl_num_heads", "ssl_ffn_dim", "aco_dim",
+        "avg_pooler")]
+
+
 class Frt2Error(RuntimeError):
     def __init__(self, status: int, msg: str):
         super().__init__(f"libfrt2_b200 status {status}: {msg}")
@@ -67,6 +73,11 @@ SIGNATURES = {
     "frt2_export_state": (_i, [_p, _p, _p, _p, _p, _p, _p, _p]),
     "frt2_import_state": (_i, [_p, _p, _i, _p, _p, _p, _p, _p, _p]),
     "frt2_rvq_encode": (_i, [_p, _p, _i64, _i64, _i64, _i, _i, _i, _i, _p, _p]),
+    "frt2_enc_create": (_i, [C.POINTER(Frt2EncConfig), _i, C.POINTER(_p)]),
+    "frt2_enc_load_tensor": (_i, [_p, C.c_char_p, _p, _i, C.POINTER(_i64), _i]),
+    "frt2_enc_finalize": (_i, [_p]),
+    "frt2_enc_destroy": (None, [_p]),
+    "frt2_enc_features": (_i, [_p, _p, _p, _i, _i, _p, C.POINTER(_i64), _p]),
     "frt2_resample": (_i, [_i, _p, _i64, _i, _i64, _p, _i, _i, _p, _i64, C.POINTER(_i64), _p]),
     "frt2_rvq_gather": (_i, [_p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _p, _p]),
     "frt2_set_debug": (_i, [_p, _i]),

@@ -433,10 +433,11 @@ class StreamDecoder:
     ``finish()`` flushes the last frame with ``last_token=True``."""
 
     def __init__(self, codec: RedCodecB200, batch: int = 1, pcm16: bool = True, max_tokens: Optional[int] = None,
-                 ring: int = 16):
+                 ring: int = 16, timing: bool = False):
         self.codec = codec
         self.batch = batch
         self.pcm16 = pcm16
+        self.timing = timing      # chunk events carry timestamps (measurements only)
         dev = torch.device("cuda", codec.device_index)
         with torch.cuda.device(codec.device_index):
             self._cache = codec.new_stream(batch, max_tokens)
@@ -490,7 +491,7 @@ class StreamDecoder:
             words = self._err_ring[self._n % len(self._err_ring)]
             N.check(c._lib.frt2_stream_fetch_errors(c._h, self._cache[_STATE_KEY].ptr, C.c_void_p(words.data_ptr()),
                                                     C.c_void_p(self._side.cuda_stream)))
-            ready = torch.cuda.Event()
+            ready = torch.cuda.Event(enable_timing=self.timing)
             ready.record(self._side)
         self._unchecked.append((ready, words, self._n))
         chunk = StreamChunk(host, ready, self._n)

@@ -178,6 +178,36 @@ int frt2_import_state(frt2_handle* h, frt2_stream* s, int n_tokens, const float*
 int frt2_rvq_encode(frt2_handle* h, const float* z, int64_t sB, int64_t sD, int64_t sT, int B, int input_dim, int T,
                     int nq, int64_t* codes, void* cuda_stream);
 
+/* ---- codec ENCODE side behind the feature encoders ----
+ * Everything RedCodecInfer._encode_one_batch (model.py:218-236) runs between the two Whisper encoders and
+ * ResidualVQ.encode_codes: SslAdaptor (model.py:19-77: Linear, N x WhisperEncoderLayer with full attention, LayerNorm,
+ * Linear), torch.cat([sem, aco], dim=2) (model.py:230) and ResidualDownConv (model.py:80-121).  The config mirrors
+ * config_codec.json["codec"]["ssl_adaptor"|"acoustic_encoder"|"downsample"]; downsample.embed_dim must equal
+ * ssl_out_dim + aco_dim and is what rvq.input_dim sees. */
+typedef struct frt2_enc_config {
+  int32_t ssl_in_dim;     /* ssl_adaptor.in_dim = the SSL encoder's width (1280, whisper.py:363) */
+  int32_t ssl_embed_dim;  /* ssl_adaptor.embed_dim */
+  int32_t ssl_out_dim;    /* ssl_adaptor.out_dim */
+  int32_t ssl_num_layers; /* ssl_adaptor.num_layers */
+  int32_t ssl_num_heads;  /* ssl_adaptor.num_heads (head_dim 32, 64 or 128; 64 / 128 run on tcgen05) */
+  int32_t ssl_ffn_dim;    /* ssl_adaptor.ffn_dim, 0 = 4 * embed_dim (whisper.py:137) */
+  int32_t aco_dim;        /* acoustic_encoder.embed_dim */
+  int32_t avg_pooler;     /* downsample.avg_pooler (model.py:84) */
+} frt2_enc_config;
+typedef struct frt2_encoder frt2_encoder;
+int frt2_enc_create(const frt2_enc_config* cfg, int device, frt2_encoder** out);
+/* Reference state_dict keys "ssl_adaptor.*" and "downsample.*" (fp32, reference layouts); other keys are ignored. */
+int frt2_enc_load_tensor(frt2_encoder* e, const char* key, const float* data, int ndim, const int64_t* shape,
+                         int on_device);
+int frt2_enc_finalize(frt2_encoder* e);
+void frt2_enc_destroy(frt2_encoder* e);
+/* ssl (B,T,ssl_in_dim), aco (B,T,aco_dim): device fp32, contiguous, the outputs of the two feature encoders at 50 Hz
+ * (every item T frames long: the reference encodes fixed 6 s chunks, model.py:262-275); T a multiple of avg_pooler.
+ * vq_in: device fp32 (B, T/avg_pooler, ssl_out_dim + aco_dim) = the input of ResidualVQ.encode_codes in time-major
+ * layout (hand it to frt2_rvq_encode with sD = 1, sT = dim).  *launches (host, optional) = kernels launched. */
+int frt2_enc_features(frt2_encoder* e, const float* ssl, const float* aco, int B, int T, float* vq_in,
+                      int64_t* launches, void* cuda_stream);
+
 /* ---- waveform resampler of the context loop ----
  * Replaces torchaudio.functional.resample(waveform, orig_freq, new_freq) with its defaults (sinc_interp_hann,
  * lowpass_filter_width 6, rolloff 0.99) as the reference calls it on every generated turn (24 kHz -> 16 kHz,

@@ -189,6 +189,29 @@ def test_attention(lib, impl, case):
     assert err < (2e-3 if impl == 1 else 4e-3), err
 
 
+@pytest.mark.parametrize("case", [(3, 4, 64, 300, 300), (2, 12, 64, 300, 300), (2, 2, 128, 300, 300), (1, 2, 64, 52, 52),
+                                  (5, 20, 64, 1500, 1500)],
+                         ids=lambda c: "B%d_H%d_hd%d_q%d_k%d" % c)
+def test_attention_tc_full_mask_odd_lengths(lib, case):
+    """The encode side's attention (whisper.py:49-79 under make_nonpad_mask of full-length items): no mask, sequence
+    lengths that are not multiples of 8 (T = 300 frames per 6 s chunk, 1500 per 30 s) — tcgen05 kernel only (the warp
+    kernel works on 8-query blocks)."""
+    B, H, hd, Tq, Tk = case
+    E = H * hd
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randn(B, Tq, E, device="cuda", generator=g).half()
+    k = torch.randn(B, Tk, E, device="cuda", generator=g).half()
+    v = torch.randn(B, Tk, E, device="cuda", generator=g).half()
+    out = torch.full((B, Tq, E), float("nan"), device="cuda", dtype=torch.half)
+    _check(lib, lib.frt2_op_attention(0, _p(q), _p(k), _p(v), _p(out), B, H, hd, Tq, Tk, 0, 0, _stream()))
+    torch.cuda.synchronize()
+    ref = attention_reference(q, k, v, H, 0, 0)
+    err = (out.float() - ref).abs().max().item()
+    print(f"attention tc full mask {case}: max-abs err {err:.3e}")
+    assert torch.isfinite(out.float()).all()
+    assert err < 4e-3, err
+
+
 @pytest.mark.parametrize("hd", [64, 128])
 def test_attention_tc_sharp_rows_and_repeated_launches(lib, hd):
     """Logits with a large spread: row maxima keep growing by more than the lazy-rescale threshold (2^8) along the

@@ -201,3 +201,53 @@ def test_oracle_rvq_encode_properties():
         resid = resid - C[chosen]
     part, _ = O.rvq_encode_codes(sd, z[1:, :, 5:17])
     assert np.array_equal(part, codes[:, 1:, 5:17])
+
+
+# ---- codec encode side behind the feature encoders (SslAdaptor + cat + ResidualDownConv, model.py:19-121,225-232) ----
+ENC_CASES = [("enc_etiny", "ETINY", "TINY"), ("enc_esmall", "ESMALL", "SMALL"), ("enc_ec0", "EC0", "C0")]
+
+
+def load_encoder_case(name, enc_preset, preset):
+    """-> (encoder cfg, codec cfg, encoder state_dict, codec state_dict incl. RVQ encode tensors, ssl, aco, golden)"""
+    import os
+    from tests.helpers import GOLDEN
+    from fireredtts2_b200.config import PRESETS
+    from fireredtts2_b200.encoder import ENC_PRESETS, synthetic_encoder_state_dict, synthetic_features
+    from fireredtts2_b200.weights import synthetic_encode_tensors, synthetic_state_dict
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    B, T, wseed, dseed = [int(v) for v in g["meta"]]
+    ecfg, cfg = ENC_PRESETS[enc_preset], PRESETS[preset]
+    esd = synthetic_encoder_state_dict(ecfg, wseed)
+    sd = dict(synthetic_state_dict(cfg, wseed))
+    sd.update(synthetic_encode_tensors(cfg, wseed, ecfg.down_dim))
+    ssl, aco = synthetic_features(ecfg, B, T, dseed)
+    return ecfg, cfg, esd, sd, ssl, aco, g
+
+
+@pytest.mark.parametrize("name,enc_preset,preset", ENC_CASES)
+def test_encoder_oracle_matches_reference_golden(name, enc_preset, preset):
+    """oracle.encoder_oracle against SslAdaptor / ResidualDownConv / ResidualVQ.encode_codes of the real reference."""
+    from oracle import encoder_oracle as EO
+    ecfg, cfg, esd, sd, ssl, aco, g = load_encoder_case(name, enc_preset, preset)
+    sem = EO.ssl_adaptor(esd, ssl, ecfg.ssl_num_heads)
+    assert sem.shape == g["sem"].shape
+    assert np.abs(sem - g["sem"]).max() < 2e-5 and O.snr_db(g["sem"], sem) > 100.0
+    vq = EO.encode_features(esd, ssl, aco, ecfg.ssl_num_heads, ecfg.avg_pooler)
+    assert vq.shape == g["vq_in"].shape
+    assert np.abs(vq - g["vq_in"]).max() < 2e-5 and O.snr_db(g["vq_in"], vq) > 100.0
+    # the indices the reference derives from ITS features, reproduced by the oracle from the same features
+    codes, _ = O.rvq_encode_codes(sd, np.ascontiguousarray(g["vq_in"].transpose(0, 2, 1)))
+    assert np.array_equal(codes.transpose(1, 0, 2), g["codes"])
+
+
+def test_encoder_config_roundtrip():
+    from fireredtts2_b200.encoder import EC0, EncoderConfig, encoder_keys, synthetic_encoder_state_dict
+    d = EC0.to_reference_dict()
+    d["acoustic_encoder"] = {"embed_dim": EC0.aco_dim}
+    assert EncoderConfig.from_reference_dict({"codec": d}) == EC0
+    with pytest.raises(ValueError):
+        bad = dict(d, downsample=dict(d["downsample"], embed_dim=EC0.down_dim + 8))
+        EncoderConfig.from_reference_dict(bad)
+    sd = synthetic_encoder_state_dict(EC0, 0)
+    assert sorted(sd) == sorted(encoder_keys(EC0))
+    assert sd["downsample.gate_proj.weight"].shape == (4 * EC0.down_dim, EC0.down_dim, 4)
