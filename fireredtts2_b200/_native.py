@@ -33,7 +33,8 @@ class Frt2Config(C.Structure):
 class Frt2EncConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "ssl_in_dim", "ssl_embed_dim", "ssl_out_dim", "ssl_num_layers", "ssl_num_heads", "ssl_ffn_dim", "aco_dim",
-        "avg_pooler")]
+        "avg_pooler", "ssl_enc_layers", "ssl_enc_heads", "ssl_enc_ffn_dim", "aco_layers", "aco_heads", "aco_ffn_dim",
+        "num_mels", "max_positions")]
 
 
 class Frt2Error(RuntimeError):
@@ -78,6 +79,7 @@ SIGNATURES = {
     "frt2_enc_finalize": (_i, [_p]),
     "frt2_enc_destroy": (None, [_p]),
     "frt2_enc_features": (_i, [_p, _p, _p, _i, _i, _p, C.POINTER(_i64), _p]),
+    "frt2_enc_audio_features": (_i, [_p, _p, _i64, _i, _i64, _p, _p, _p, _p, C.POINTER(_i64), _p]),
     "frt2_resample": (_i, [_i, _p, _i64, _i, _i64, _p, _i, _i, _p, _i64, C.POINTER(_i64), _p]),
     "frt2_rvq_gather": (_i, [_p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _p, _p]),
     "frt2_set_debug": (_i, [_p, _i]),

@@ -441,7 +441,7 @@ class StreamDecoder:
         dev = torch.device("cuda", codec.device_index)
         with torch.cuda.device(codec.device_index):
             self._cache = codec.new_stream(batch, max_tokens)
-            self._side = torch.cuda.Stream(device=dev)
+            self._side = torch.cuda.Stream(device=dev, priority=-1)   # the step is tiny and latency-critical
             width = codec.cfg.samples_per_token + codec.cfg.istft_pad
             dt = torch.int16 if pcm16 else torch.float32
             self._ring = [torch.empty((batch, width), dtype=dt).pin_memory() for _ in range(max(2, ring))]

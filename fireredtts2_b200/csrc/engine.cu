@@ -1238,6 +1238,18 @@ int Stream::end_use(cudaStream_t st) {
 // =====================================================================================================
 using namespace frt2;
 
+// The per-token step is captured on a stream of the HIGHEST priority: its kernel nodes inherit that priority, so a
+// replay that shares the GPU with a bulk producer (the LLM's next frame on the caller's stream, an offline decode of
+// another request) gets its ~90 small CTA waves scheduled ahead of the producer's pending ones instead of queueing
+// behind every one of its kernels.  FRT2_STEP_PRIO=0 restores default-priority nodes (A/B).
+static cudaError_t create_step_stream(cudaStream_t* out) {
+  static const bool prio = !(getenv("FRT2_STEP_PRIO") != nullptr && atoi(getenv("FRT2_STEP_PRIO")) == 0);
+  int least = 0, greatest = 0;
+  if (prio && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess)
+    return cudaStreamCreateWithPriority(out, cudaStreamNonBlocking, greatest);
+  return cudaStreamCreateWithFlags(out, cudaStreamNonBlocking);
+}
+
 struct frt2_handle { Handle h; };
 struct frt2_stream { Stream s; };
 
@@ -1439,7 +1451,7 @@ static int stream_create_fresh(Handle& h, int B, int max_tokens, frt2_stream** o
   if (cudaMalloc(reinterpret_cast<void**>(&s.tail), static_cast<size_t>(B) * 3 * h.n_fft * 4) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&s.ctrl), static_cast<size_t>(B) * CTRL_INTS * sizeof(int)) != cudaSuccess ||
       cudaMalloc(reinterpret_cast<void**>(&s.err_words), static_cast<size_t>(1 + B) * sizeof(unsigned int)) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&s.cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      create_step_stream(&s.cap_stream) != cudaSuccess) {
     set_error("frt2_stream_create: out of memory");
     return fail(FRT2_ERR_CUDA);
   }

@@ -193,10 +193,20 @@ typedef struct frt2_enc_config {
   int32_t ssl_ffn_dim;    /* ssl_adaptor.ffn_dim, 0 = 4 * embed_dim (whisper.py:137) */
   int32_t aco_dim;        /* acoustic_encoder.embed_dim */
   int32_t avg_pooler;     /* downsample.avg_pooler (model.py:84) */
+  /* the two feature encoders (optional: all of the following 0 = only frt2_enc_features is available) */
+  int32_t ssl_enc_layers;  /* PretrainedWhisperEncoder: 32 layers, 20 heads, ffn 5120 at width ssl_in_dim (whisper.py:359-369) */
+  int32_t ssl_enc_heads;
+  int32_t ssl_enc_ffn_dim; /* 0 = 4 * width */
+  int32_t aco_layers;      /* acoustic_encoder.num_layers / num_heads / ffn_dim (whisper.py:398-401) */
+  int32_t aco_heads;       /* any head_dim <= 128 that is a multiple of 8 (zero-padded to 64 / 128 at load) */
+  int32_t aco_ffn_dim;
+  int32_t num_mels;        /* 128 (whisper.py:372,391); n_fft 400, hop 160, 16 kHz, 0..8000 Hz are fixed (whisper.py:373-377) */
+  int32_t max_positions;   /* 1500 (whisper.py:366,403) */
 } frt2_enc_config;
 typedef struct frt2_encoder frt2_encoder;
 int frt2_enc_create(const frt2_enc_config* cfg, int device, frt2_encoder** out);
-/* Reference state_dict keys "ssl_adaptor.*" and "downsample.*" (fp32, reference layouts); other keys are ignored. */
+/* Reference state_dict keys "ssl_adaptor.*", "downsample.*" and — when the feature encoders are configured — "ssl.*",
+ * "acoustic_encoder.*" (fp32, reference layouts); other keys are ignored. */
 int frt2_enc_load_tensor(frt2_encoder* e, const char* key, const float* data, int ndim, const int64_t* shape,
                          int on_device);
 int frt2_enc_finalize(frt2_encoder* e);
@@ -207,6 +217,15 @@ void frt2_enc_destroy(frt2_encoder* e);
  * layout (hand it to frt2_rvq_encode with sD = 1, sT = dim).  *launches (host, optional) = kernels launched. */
 int frt2_enc_features(frt2_encoder* e, const float* ssl, const float* aco, int B, int T, float* vq_in,
                       int64_t* launches, void* cuda_stream);
+
+/* The whole of RedCodecInfer._encode_one_batch (model.py:218-236) up to the RVQ input, from the waveform: log-mel
+ * front end (WhisperMelExtractor, whisper.py:261-302), the SSL and the acoustic WhisperEncoder (whisper.py:195-258),
+ * then everything frt2_enc_features does.  audio16k: device fp32 (B, n) with row pitch audio_pitch, n a multiple of 1280
+ * (the reference pads every chunk to 6 s = 96000 samples, model.py:262-275).  vq_in: (B, n/1280, dim).  Optional
+ * parity taps (device fp32, may be NULL): mel_out (B, n/160, num_mels), ssl_out (B, n/320, ssl_in_dim), aco_out
+ * (B, n/320, aco_dim) = the outputs of the feature extractor and of the two encoders. */
+int frt2_enc_audio_features(frt2_encoder* e, const float* audio16k, int64_t audio_pitch, int B, int64_t n, float* vq_in,
+                            float* mel_out, float* ssl_out, float* aco_out, int64_t* launches, void* cuda_stream);
 
 /* ---- waveform resampler of the context loop ----
  * Replaces torchaudio.functional.resample(waveform, orig_freq, new_freq) with its defaults (sinc_interp_hann,

@@ -251,3 +251,53 @@ def test_encoder_config_roundtrip():
     sd = synthetic_encoder_state_dict(EC0, 0)
     assert sorted(sd) == sorted(encoder_keys(EC0))
     assert sd["downsample.gate_proj.weight"].shape == (4 * EC0.down_dim, EC0.down_dim, 4)
+
+
+# ---- the whole encode path from the waveform (log-mel, both Whisper encoders, ssl_adaptor, downsample; model.py:218-236) ----
+ENC_AUDIO_CASES = [("encaudio_etinyf", "ETINYF", "TINY"), ("encaudio_epadf", "EPADF", "SMALL")]
+
+
+def load_encoder_audio_case(name, enc_preset, preset):
+    """-> (encoder cfg, codec cfg, encoder state_dict incl. the feature encoders, codec state_dict, audio, golden)"""
+    import os
+    from tests.helpers import GOLDEN
+    from fireredtts2_b200.config import PRESETS
+    from fireredtts2_b200.encoder import (ENC_PRESETS, synthetic_audio, synthetic_encoder_state_dict,
+                                          synthetic_front_state_dict)
+    from fireredtts2_b200.weights import synthetic_encode_tensors, synthetic_state_dict
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    B, n, wseed, dseed = [int(v) for v in g["meta"]]
+    ecfg, cfg = ENC_PRESETS[enc_preset], PRESETS[preset]
+    esd = dict(synthetic_encoder_state_dict(ecfg, wseed))
+    esd.update(synthetic_front_state_dict(ecfg, wseed))
+    sd = dict(synthetic_state_dict(cfg, wseed))
+    sd.update(synthetic_encode_tensors(cfg, wseed, ecfg.down_dim))
+    return ecfg, cfg, esd, sd, synthetic_audio(B, n, dseed), g
+
+
+@pytest.mark.parametrize("name,enc_preset,preset", ENC_AUDIO_CASES)
+def test_encoder_audio_oracle_matches_reference_golden(name, enc_preset, preset):
+    """oracle.encoder_oracle (log_mel, whisper_encoder, ...) against RedCodecInfer._encode_one_batch of the real reference."""
+    from oracle import encoder_oracle as EO
+    ecfg, cfg, esd, sd, audio, g = load_encoder_audio_case(name, enc_preset, preset)
+    taps = {}
+    vq = EO.encode_audio_features(esd, audio, ecfg, taps=taps)
+    assert np.abs(taps["mel"] - g["mel"]).max() < 2e-4 and O.snr_db(g["mel"], taps["mel"]) > 100.0
+    for k in ("ssl", "aco"):
+        assert taps[k].shape == g[k].shape
+        assert np.abs(taps[k] - g[k]).max() < 2e-5 and O.snr_db(g[k], taps[k]) > 100.0
+    assert np.abs(vq - g["vq_in"]).max() < 2e-5 and O.snr_db(g["vq_in"], vq) > 100.0
+
+
+def test_mel_filter_bank_and_positions_match_reference_formulas():
+    """The slaney bank and the sinusoidal table restated in oracle/ and fireredtts2_b200/: basic invariants (the golden
+    log-mel above pins the values)."""
+    from oracle import encoder_oracle as EO
+    from fireredtts2_b200.encoder import sinusoids
+    bank = EO.mel_filter_bank(201, 128)
+    assert bank.shape == (201, 128) and (bank >= 0).all() and (bank.max(axis=0) > 0).all()
+    assert bank[0].sum() == 0.0                       # DC belongs to no filter's interior
+    peaks = bank.argmax(axis=0)
+    assert (np.diff(peaks) >= 0).all()                # centres ascend
+    pos = sinusoids(1500, 1280)
+    assert pos.shape == (1500, 1280) and np.allclose(pos[0, :640], 0.0) and np.allclose(pos[0, 640:], 1.0)

@@ -26,12 +26,77 @@ def flops(cfg, M):
     return f
 
 
+def stack_flops(E, F, layers, M, T):
+    return layers * (2.0 * M * E * (4 * E + 2 * F) + 4.0 * E * T * M)
+
+
+def audio_bench(a):
+    """frt2_enc_audio_features + frt2_rvq_encode on `batch` 6 s chunks (the reference's _encode_one_batch, model.py:218-236)."""
+    from fireredtts2_b200.encoder import EC0F, synthetic_audio, synthetic_front_state_dict
+    dev = torch.device("cuda", 0)
+    cfg = EC0F
+    t0 = time.perf_counter()
+    esd = dict(synthetic_encoder_state_dict(cfg, 0))
+    esd.update(synthetic_front_state_dict(cfg, 0))
+    enc = CodecEncoderB200(cfg, esd, device="cuda:0")
+    del esd
+    sd = dict(synthetic_state_dict(C0, 0))
+    sd.update(synthetic_encode_tensors(C0, 0, cfg.down_dim))
+    codec = RedCodecB200(C0, sd, device="cuda:0", check_indices=False)
+    load_s = time.perf_counter() - t0
+    n = 96000
+    audio = torch.from_numpy(synthetic_audio(a.batch, n, 5)).to(dev)
+    for _ in range(2):
+        vq = enc.audio_features(audio)
+        codes = codec.rvq_encode_codes(vq.transpose(1, 2))
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    tf, tq = [], []
+    for _ in range(a.reps):
+        e[0].record()
+        vq = enc.audio_features(audio)
+        e[1].record()
+        codes = codec.rvq_encode_codes(vq.transpose(1, 2))
+        e[2].record()
+        torch.cuda.synchronize()
+        tf.append(e[0].elapsed_time(e[1]))
+        tq.append(e[1].elapsed_time(e[2]))
+    Tm, T = n // 160, n // 320
+    Mm, M = a.batch * Tm, a.batch * T
+    fl = 0.0
+    for E, F, L in ((cfg.ssl_in_dim, cfg.ssl_enc_ffn_dim or 4 * cfg.ssl_in_dim, cfg.ssl_enc_layers),
+                    (cfg.aco_dim, cfg.aco_ffn_dim or 4 * cfg.aco_dim, cfg.aco_layers)):
+        fl += 2.0 * Mm * 3 * cfg.num_mels * E + 2.0 * M * 3 * E * E + stack_flops(E, F, L, M, T)
+    fl += flops(cfg, M) + cfg.ssl_num_layers * 4.0 * cfg.ssl_embed_dim * T * M
+    ms_f, ms_q = float(np.median(tf)), float(np.median(tq))
+    pk = {}
+    try:
+        pk = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = pk.get("bf16_tflops_sustained") or 1400.0
+    audio_s = a.batch * 6.0
+    print(json.dumps({
+        "workload": f"whole encode path from the waveform: {a.batch} chunks x 6 s @16 kHz = {audio_s:.0f} audio-s per batch; "
+                    "log-mel, SSL encoder (whisper-large-v3 size: 32 x 1280, 20 heads), acoustic encoder (12 x 768, 8 heads, "
+                    "head_dim 96 padded to 128), ssl_adaptor, downsample, C0 RVQ; random weights",
+        "features_ms": ms_f, "rvq_encode_ms": ms_q, "total_ms": ms_f + ms_q, "audio_s_per_s": audio_s / ((ms_f + ms_q) * 1e-3),
+        "launches_features": enc.last_launches, "algorithmic_flops": fl,
+        "roofline": {"bound": "tensor", "achieved": fl / (ms_f * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                     "frac": fl / (ms_f * 1e-3) / 1e12 / peak},
+        "load_seconds": load_s, "codes_shape": list(codes.shape)}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=96)
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--audio", action="store_true", help="whole path from the 16 kHz waveform (EC0F: whisper-large-v3 "
+                    "sized SSL encoder + 12-layer acoustic encoder), 6 s chunks")
     a = ap.parse_args()
+    if a.audio:
+        return audio_bench(a)
     dev = torch.device("cuda", 0)
     esd = synthetic_encoder_state_dict(EC0, 0)
     enc = CodecEncoderB200(EC0, esd, device="cuda:0")
