@@ -17,25 +17,35 @@
 // tokens' activations broadcast from shared memory as float4.
 #include <math_constants.h>
 
+#include <cstdlib>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace frt2 {
 
 namespace {
 
-constexpr int RE_TM = 32;        // tokens per CTA
+constexpr int RE_TM_MAX = 32;    // tokens per CTA: 32, or 16 / 8 for small batches (more CTAs; a token's arithmetic does not depend on it)
 constexpr int RE_THREADS = 256;
 constexpr int RE_WARPS = RE_THREADS / 32;
 constexpr int RE_MAXCD = 256;    // codebook_dim limit (one thread per dim); also the k-chunk of the input projection
 
 // acc[m] += sum_k act[m][k] * W[k][col]   for k in [0, kn), act rows have pitch `ap` floats (16-byte aligned, kn % 4 == 0)
+template <int RE_TM>
 __device__ __forceinline__ void tile_fma(float (&acc)[RE_TM], const float* __restrict__ act, int ap,
                                          const float* __restrict__ Wcol, int wld, int kn) {
+  // the weights of the NEXT four k are requested before the 4 x RE_TM FMAs of this step: with one or two CTAs per SM the
+  // loop is otherwise a chain of L2 round trips
+  float w0 = __ldg(Wcol), w1 = __ldg(Wcol + wld), w2 = __ldg(Wcol + 2LL * wld), w3 = __ldg(Wcol + 3LL * wld);
   for (int k = 0; k < kn; k += 4) {
-    const float w0 = __ldg(Wcol + static_cast<long long>(k) * wld);
-    const float w1 = __ldg(Wcol + static_cast<long long>(k + 1) * wld);
-    const float w2 = __ldg(Wcol + static_cast<long long>(k + 2) * wld);
-    const float w3 = __ldg(Wcol + static_cast<long long>(k + 3) * wld);
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+    if (k + 4 < kn) {
+      n0 = __ldg(Wcol + static_cast<long long>(k + 4) * wld);
+      n1 = __ldg(Wcol + static_cast<long long>(k + 5) * wld);
+      n2 = __ldg(Wcol + static_cast<long long>(k + 6) * wld);
+      n3 = __ldg(Wcol + static_cast<long long>(k + 7) * wld);
+    }
 #pragma unroll
     for (int m = 0; m < RE_TM; ++m) {
       const float4 a = *reinterpret_cast<const float4*>(act + m * ap + k);   // same address in every lane: broadcast
@@ -44,9 +54,11 @@ __device__ __forceinline__ void tile_fma(float (&acc)[RE_TM], const float* __res
       acc[m] = fmaf(a.z, w2, acc[m]);
       acc[m] = fmaf(a.w, w3, acc[m]);
     }
+    w0 = n0; w1 = n1; w2 = n2; w3 = n3;
   }
 }
 
+template <int RE_TM>
 __global__ void __launch_bounds__(RE_THREADS) rvq_encode_kernel(RvqEncDesc d) {
   extern __shared__ __align__(16) uint8_t re_smem[];
   const int rp = d.rd + 4;                       // residual row pitch (floats): +4 keeps rows 16-byte aligned, de-phased
@@ -224,7 +236,7 @@ __global__ void __launch_bounds__(RE_THREADS) rvq_encode_kernel(RvqEncDesc d) {
   }
 }
 
-size_t re_smem_bytes(int rd) {
+size_t re_smem_bytes(int rd, int RE_TM) {
   return static_cast<size_t>(RE_TM) * (rd + 4) * 4 + static_cast<size_t>(RE_TM) * (RE_MAXCD + 4) * 4 + RE_TM * 4 * 3 +
          static_cast<size_t>(RE_WARPS) * RE_TM * 8;
 }
@@ -240,15 +252,30 @@ int rvq_encode(const RvqEncDesc& d, cudaStream_t stream) {
   FRT2_REQUIRE(d.WinT != nullptr || d.rd == d.cd, FRT2_ERR_BAD_ARG, "rvq_encode: Identity in_project needs rvq_dim == codebook_dim");
   const long long R = static_cast<long long>(d.B) * d.T;
   if (R == 0 || d.nq == 0) return FRT2_OK;
-  const size_t smem = re_smem_bytes(d.rd);
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(re_smem_bytes(2 * RE_THREADS)));
+    attr_err = cudaFuncSetAttribute(rvq_encode_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(re_smem_bytes(2 * RE_THREADS, 32)));
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rvq_encode_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(re_smem_bytes(2 * RE_THREADS, 16)));
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(rvq_encode_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(re_smem_bytes(2 * RE_THREADS, 8)));
   });
   FRT2_CUDA_OK(attr_err);
-  rvq_encode_kernel<<<static_cast<unsigned>((R + RE_TM - 1) / RE_TM), RE_THREADS, smem, stream>>>(d);
+  // tokens per CTA: the largest tile that still leaves one CTA per SM (measured at C0: 7200 tokens 9.5 ms with 32 per
+  // CTA, 13.6 ms with 16; 2400 tokens 9.8 ms with 32, 7.3 ms with 8 — smaller tiles re-stream the L2-resident tables)
+  static const int force_tm = getenv("FRT2_RVQ_ENC_TM") ? atoi(getenv("FRT2_RVQ_ENC_TM")) : 0;   // A/B
+  const long long sms = num_sms();
+  int tm = R >= 32 * sms ? 32 : (R >= 16 * sms ? 16 : 8);
+  if (force_tm == 8 || force_tm == 16 || force_tm == 32) tm = force_tm;
+  const unsigned grid = static_cast<unsigned>((R + tm - 1) / tm);
+  const size_t smem = re_smem_bytes(d.rd, tm);
+  if (tm == 32) rvq_encode_kernel<32><<<grid, RE_THREADS, smem, stream>>>(d);
+  else if (tm == 16) rvq_encode_kernel<16><<<grid, RE_THREADS, smem, stream>>>(d);
+  else rvq_encode_kernel<8><<<grid, RE_THREADS, smem, stream>>>(d);
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;
 }

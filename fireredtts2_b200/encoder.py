@@ -327,7 +327,8 @@ class CodecEncoderB200:
                       "aco": torch.empty((B, T, cfg.aco_dim), dtype=torch.float32, device=dev)}
             ptr = lambda k: C.c_void_p(tp[k].data_ptr()) if taps else None
             cnt = C.c_int64(0)
-            N.check(self._lib.frt2_enc_audio_features(self._e, C.c_void_p(audio16k.data_ptr()), audio16k.stride(0), B, n,
+            pitch = audio16k.stride(0) if B > 1 else n      # the stride of a size-1 dimension is arbitrary
+            N.check(self._lib.frt2_enc_audio_features(self._e, C.c_void_p(audio16k.data_ptr()), pitch, B, n,
                                                       C.c_void_p(out.data_ptr()), ptr("mel"), ptr("ssl"), ptr("aco"),
                                                       C.byref(cnt),
                                                       C.c_void_p(torch.cuda.current_stream(self.device_index).cuda_stream)))

@@ -65,6 +65,24 @@ def test_rvq_encode_c0_against_oracle_and_batch_independence():
     assert audio.shape == (4, 250 * cfg.samples_per_token) and bool(torch.isfinite(audio).all())
 
 
+def test_rvq_encode_tile_size_does_not_change_the_indices():
+    """The kernel picks 8, 16 or 32 tokens per CTA from the batch size (small batches: more, smaller tiles); a token's
+    arithmetic does not depend on the tile it sits in, so the three variants agree bit for bit."""
+    from fireredtts2_b200.config import SMALL
+    from fireredtts2_b200.weights import synthetic_encode_tensors, synthetic_state_dict
+    cfg = SMALL
+    sd = dict(synthetic_state_dict(cfg, 1))
+    sd.update(synthetic_encode_tensors(cfg, 1))
+    codec = build_codec(cfg, sd, check_indices=False)
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    T = 32 * sms + 13                                                   # >= 32 tokens per SM: 32 per CTA
+    z = torch.from_numpy(np.random.default_rng(8).standard_normal((1, cfg.embed_dim, T)).astype(np.float32)).cuda()
+    big = codec.rvq_encode_codes(z)
+    mid = codec.rvq_encode_codes(z[:, :, :20 * sms])                    # 16 per CTA
+    small = codec.rvq_encode_codes(z[:, :, :999])                       # 8 per CTA
+    assert torch.equal(mid, big[:, :, :20 * sms]) and torch.equal(small, big[:, :, :999])
+
+
 def test_rvq_encode_identity_first_code_is_exact():
     """Identity projections: z = codebook_0[idx] is reproduced exactly by the first quantizer (distance 0)."""
     from fireredtts2_b200.config import TINY_IDENT

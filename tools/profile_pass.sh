@@ -14,7 +14,7 @@ $STREAM > "$OUT/plain_stream.log" 2>&1 || { echo "plain stream failed"; exit 1; 
 ncu --metrics gpu__time_duration.sum --clock-control none -s 111 -c 111 --csv --log-file "$OUT/launches.csv" $BENCH > "$OUT/ncu_list.log" 2>&1
 echo "list=$?"
 # 2. one transformer layer of the step (row_stats, QKV, attention, out-proj, row_stats, fc1, fc2 ...) + the tail kernels
-ncu --set full --clock-control none -k regex:"gemm_tc|attention_t3|row_stats" -s 9 -c 9 -o "$OUT/prof_layer" -f $BENCH > "$OUT/ncu_layer.log" 2>&1
+ncu --set full --clock-control none -k regex:"gemm_tc|attention_t|row_stats" -s 9 -c 9 -o "$OUT/prof_layer" -f $BENCH > "$OUT/ncu_layer.log" 2>&1
 echo "layer=$?"
 ncu --set full --clock-control none -k regex:"overlap_add|layer_norm|rvq_gather" -c 4 -o "$OUT/prof_misc" -f $BENCH > "$OUT/ncu_misc.log" 2>&1
 echo "misc=$?"
