@@ -35,17 +35,11 @@ constexpr int RE_MAXCD = 256;    // codebook_dim limit (one thread per dim); als
 template <int RE_TM>
 __device__ __forceinline__ void tile_fma(float (&acc)[RE_TM], const float* __restrict__ act, int ap,
                                          const float* __restrict__ Wcol, int wld, int kn) {
-  // the weights of the NEXT four k are requested before the 4 x RE_TM FMAs of this step: with one or two CTAs per SM the
-  // loop is otherwise a chain of L2 round trips
-  float w0 = __ldg(Wcol), w1 = __ldg(Wcol + wld), w2 = __ldg(Wcol + 2LL * wld), w3 = __ldg(Wcol + 3LL * wld);
   for (int k = 0; k < kn; k += 4) {
-    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-    if (k + 4 < kn) {
-      n0 = __ldg(Wcol + static_cast<long long>(k + 4) * wld);
-      n1 = __ldg(Wcol + static_cast<long long>(k + 5) * wld);
-      n2 = __ldg(Wcol + static_cast<long long>(k + 6) * wld);
-      n3 = __ldg(Wcol + static_cast<long long>(k + 7) * wld);
-    }
+    const float w0 = __ldg(Wcol + static_cast<long long>(k) * wld);
+    const float w1 = __ldg(Wcol + static_cast<long long>(k + 1) * wld);
+    const float w2 = __ldg(Wcol + static_cast<long long>(k + 2) * wld);
+    const float w3 = __ldg(Wcol + static_cast<long long>(k + 3) * wld);
 #pragma unroll
     for (int m = 0; m < RE_TM; ++m) {
       const float4 a = *reinterpret_cast<const float4*>(act + m * ap + k);   // same address in every lane: broadcast
@@ -54,7 +48,6 @@ __device__ __forceinline__ void tile_fma(float (&acc)[RE_TM], const float* __res
       acc[m] = fmaf(a.z, w2, acc[m]);
       acc[m] = fmaf(a.w, w3, acc[m]);
     }
-    w0 = n0; w1 = n1; w2 = n2; w3 = n3;
   }
 }
 
@@ -265,11 +258,12 @@ int rvq_encode(const RvqEncDesc& d, cudaStream_t stream) {
                                       static_cast<int>(re_smem_bytes(2 * RE_THREADS, 8)));
   });
   FRT2_CUDA_OK(attr_err);
-  // tokens per CTA: the largest tile that still leaves one CTA per SM (measured at C0: 7200 tokens 9.5 ms with 32 per
-  // CTA, 13.6 ms with 16; 2400 tokens 9.8 ms with 32, 7.3 ms with 8 — smaller tiles re-stream the L2-resident tables)
+  // tokens per CTA: 32 once every SM gets a tile, else 8 (more, smaller tiles).  Measured at C0: 7200 tokens 9.5 ms with
+  // 32 per CTA, 13.6 ms with 16; 2400 tokens 9.8 / 8.1 / 7.3 ms with 32 / 16 / 8 (smaller tiles re-stream the L2-resident
+  // tables; a software prefetch of the next weights cost registers and time: 30.3 -> 33.3 ms at 24 000 tokens)
   static const int force_tm = getenv("FRT2_RVQ_ENC_TM") ? atoi(getenv("FRT2_RVQ_ENC_TM")) : 0;   // A/B
   const long long sms = num_sms();
-  int tm = R >= 32 * sms ? 32 : (R >= 16 * sms ? 16 : 8);
+  int tm = R >= 32 * sms ? 32 : 8;
   if (force_tm == 8 || force_tm == 16 || force_tm == 32) tm = force_tm;
   const unsigned grid = static_cast<unsigned>((R + tm - 1) / tm);
   const size_t smem = re_smem_bytes(d.rd, tm);

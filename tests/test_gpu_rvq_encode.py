@@ -66,8 +66,8 @@ def test_rvq_encode_c0_against_oracle_and_batch_independence():
 
 
 def test_rvq_encode_tile_size_does_not_change_the_indices():
-    """The kernel picks 8, 16 or 32 tokens per CTA from the batch size (small batches: more, smaller tiles); a token's
-    arithmetic does not depend on the tile it sits in, so the three variants agree bit for bit."""
+    """The kernel picks 32 or 8 tokens per CTA from the batch size (small batches: more, smaller tiles); a token's
+    arithmetic does not depend on the tile it sits in, so the variants agree bit for bit."""
     from fireredtts2_b200.config import SMALL
     from fireredtts2_b200.weights import synthetic_encode_tensors, synthetic_state_dict
     cfg = SMALL
@@ -78,7 +78,7 @@ def test_rvq_encode_tile_size_does_not_change_the_indices():
     T = 32 * sms + 13                                                   # >= 32 tokens per SM: 32 per CTA
     z = torch.from_numpy(np.random.default_rng(8).standard_normal((1, cfg.embed_dim, T)).astype(np.float32)).cuda()
     big = codec.rvq_encode_codes(z)
-    mid = codec.rvq_encode_codes(z[:, :, :20 * sms])                    # 16 per CTA
+    mid = codec.rvq_encode_codes(z[:, :, :20 * sms])                    # 8 per CTA, many tiles
     small = codec.rvq_encode_codes(z[:, :, :999])                       # 8 per CTA
     assert torch.equal(mid, big[:, :, :20 * sms]) and torch.equal(small, big[:, :, :999])
 

@@ -81,3 +81,15 @@ def test_token_step_kernels(sass):
     assert _count(_fn(sass, "state_roll_kernel"), "STG.E.128") >= 1 and _count(_fn(sass, "state_reset_kernel"), "STG.E.128") >= 1
     assert _count(_fn(sass, "overlap_add_vec4_kernel"), "STG.E.128") >= 1
     assert _count(_fn(sass, "rvq_encode_kernel"), "FFMA") >= 100
+
+
+def test_encode_side_kernels(sass):
+    """encoder.cu: the bandwidth kernels move 16-byte vectors, the log-mel kernel is an fp32 FMA loop; the encoders'
+    contractions and attention are the decode path's tcgen05 kernels (no kernel of their own)."""
+    assert _count(_fn(sass, "silu_mul_kernel"), "LDG.E.EF.128") >= 2 and _count(_fn(sass, "silu_mul_kernel"), "STG.E.128") >= 1
+    assert _count(_fn(sass, "cvt_rows_kernel"), "LDG.E.EF.128") >= 1      # streaming (evict-first) 16-byte loads
+    assert _count(_fn(sass, "add_pos_kernel"), "STG.E.128") >= 1
+    b = _fn(sass, "mel_power_kernel")
+    assert _count(b, "FFMA") >= 8 and _count(b, "HMMA") == 0
+    names = " ".join(sass)
+    assert "rvq_encode_kernelILi8" in names and "rvq_encode_kernelILi16" in names and "rvq_encode_kernelILi32" in names

@@ -24,3 +24,6 @@ echo "streamlist=$?"
 ncu --set full --clock-control none -k regex:"gemm_skinny_kernel|attention_warp" -s 100 -c 6 -o "$OUT/prof_stream" -f $STREAM > "$OUT/ncu_stream.log" 2>&1
 echo "stream=$?"
 ls -la "$OUT"
+# 4. DRAM bytes of every launch of the step (bench.py reports the GEMM's per-launch traffic from this: tools/dram_traffic.py)
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -s 111 -c 111 --csv --log-file "$OUT/launches_dram.csv" $BENCH > "$OUT/ncu_dram.log" 2>&1
+echo "dram=$?"
