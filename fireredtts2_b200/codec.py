@@ -145,7 +145,13 @@ class RedCodecB200(torch.nn.Module):
                           num_heads=num_heads or ad.num_heads, hop_length=ad.hop_length)
         if not getattr(ad, "causal", True):
             raise AssertionError("Only AcousticDecoder with causal=True supports forward_chunk method.")
-        return cls(cfg, ref.state_dict(), encoder=ref, **kw)
+        native_encode = kw.pop("native_encode", False)
+        codec = cls(cfg, ref.state_dict(), encoder=ref, **kw)
+        if native_encode:       # the whole encode path on the GPU library too; the reference stays unused
+            from .encoder import CodecEncoderB200, EncoderConfig
+            codec.attach_encoder(CodecEncoderB200(EncoderConfig.from_reference_module(ref), ref.state_dict(),
+                                                  device=str(codec.device)))
+        return codec
 
     @classmethod
     def from_pretrained(cls, conf_path: str, ckpt_path: str, **kw) -> "RedCodecB200":
@@ -349,8 +355,19 @@ class RedCodecB200(torch.nn.Module):
 
     resample = staticmethod(resample)   # torchaudio.functional.resample of the context loop, on the same device
 
+    def attach_encoder(self, native_encoder) -> None:
+        """Route ``encode`` through a ``CodecEncoderB200`` (fireredtts2_b200/encoder.py) instead of the reference module."""
+        self._native_encoder = native_encoder
+
     def encode(self, *args, **kwargs):
-        """Out of scope for this path: delegated to the wrapped reference module."""
+        """``RedCodecInfer.encode`` (model.py:243-305): through the attached ``CodecEncoderB200`` when there is one
+        (SURVEY.md §8f.3), else delegated to the wrapped reference module."""
+        ne = getattr(self, "_native_encoder", None)
+        if ne is not None:
+            audio16k = args[0] if args else kwargs["audio16k"]
+            length = args[1] if len(args) > 1 else kwargs.get("audio16k_length")
+            bs = args[2] if len(args) > 2 else kwargs.get("batch_size", 96)
+            return ne.encode(audio16k, length, self, bs)
         enc = self._encoder[0]
         if enc is None:
             raise NotImplementedError("encode() needs the reference RedCodecInfer (use RedCodecB200.from_reference)")

@@ -76,6 +76,25 @@ class EncoderConfig:
                    ssl_num_layers=a["num_layers"], ssl_num_heads=a["num_heads"], ssl_ffn_dim=a.get("ffn_dim") or 0,
                    aco_dim=aco, avg_pooler=d.get("avg_pooler", 4), **front)
 
+    @classmethod
+    def from_reference_module(cls, ref) -> "EncoderConfig":
+        """Read the encode-side architecture off a live reference ``RedCodec`` / ``RedCodecInfer`` (model.py:150-170)."""
+        a, d, ae, ssl = ref.ssl_adaptor, ref.downsample, ref.acoustic_encoder, ref.ssl
+
+        def ffn(stack, width):
+            f = stack.layers[0].fc1.out_features if len(stack.layers) else 0
+            return 0 if f == 4 * width else f
+
+        def heads(stack):
+            return stack.layers[0].self_attn.num_heads if len(stack.layers) else 1
+
+        return cls(ssl_in_dim=a.in_dim, ssl_embed_dim=a.embed_dim, ssl_out_dim=a.out_proj.out_features,
+                   ssl_num_layers=len(a.layers), ssl_num_heads=heads(a), ssl_ffn_dim=ffn(a, a.embed_dim),
+                   aco_dim=ae.embed_dim, avg_pooler=d.avg_pooler,
+                   ssl_enc_layers=len(ssl.layers), ssl_enc_heads=heads(ssl), ssl_enc_ffn_dim=ffn(ssl, ssl.embed_dim),
+                   aco_layers=len(ae.layers), aco_heads=heads(ae), aco_ffn_dim=ffn(ae, ae.embed_dim),
+                   num_mels=ae.in_dim, max_positions=ae.max_positions)
+
     def to_reference_dict(self) -> Dict[str, Any]:
         return {"ssl_adaptor": dict(in_dim=self.ssl_in_dim, embed_dim=self.ssl_embed_dim, out_dim=self.ssl_out_dim,
                                     num_layers=self.ssl_num_layers, num_heads=self.ssl_num_heads,
