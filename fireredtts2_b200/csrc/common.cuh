@@ -198,8 +198,19 @@ struct RvqEncDesc {
   const float* WoutT;        // (nq, cd, rd) out_project^T or null
   const float* bout;         // (nq, rd)
   long long* codes;          // (nq, B, T) int64
+  // tensor-core variant (rvq_encode_tc.cu): split-fp16 weights, rows [w_hi | w_lo*S | w_hi/S], or null
+  const __half* s_inp;       // (rd, 3*input_dim)
+  const __half* s_in;        // (nq, cd, 3*rd)
+  const __half* s_C;         // (nq, K, 3*cd)
+  const __half* s_out;       // (nq, rd, 3*cd)
+  const float* nbout;        // (nq, rd) = -bout
 };
-int rvq_encode(const RvqEncDesc& d, cudaStream_t stream);
+int rvq_encode(const RvqEncDesc& d, cudaStream_t stream);   // CUDA-core fp32 kernel (checker; any widths)
+// every contraction of the chain as a tcgen05 GEMM on split-fp16 operands (widths that are multiples of 64)
+bool rvq_encode_tc_applicable(const RvqEncDesc& d);
+size_t rvq_encode_tc_ws_bytes(const RvqEncDesc& d, long long R);
+int rvq_encode_tc(const RvqEncDesc& d, uint8_t* ws, cudaStream_t stream, long long* launches);
+void rvq_split_weight_host(const float* W, int64_t N, int64_t Kk, __half* out);
 int layer_norm_rows(const float* x, int64_t ldx, int rows, int C, const float* gamma, const float* beta, float eps,
                     int apply_silu, __half* out16, int64_t ld16, cudaStream_t stream);
 // Overlap-add of windowed frames + window-square envelope normalisation + "same" trimming.

@@ -226,7 +226,15 @@ struct Handle {
   bool enc_ready = false;
   int enc_input_dim = 0;
   float *enc_WinpT = nullptr, *enc_binp = nullptr, *enc_WinT = nullptr, *enc_bin = nullptr, *enc_CT = nullptr,
-        *enc_c2 = nullptr, *enc_WoutT = nullptr, *enc_bout = nullptr;
+        *enc_c2 = nullptr, *enc_WoutT = nullptr, *enc_bout = nullptr, *enc_nbout = nullptr;
+  __half *enc_s_inp = nullptr, *enc_s_in = nullptr, *enc_s_C = nullptr, *enc_s_out = nullptr;   // split-fp16 (rvq_encode_tc)
+  int upload_split(const std::vector<float>& W, int64_t N, int64_t Kk, __half** out) {
+    std::vector<__half> hb(static_cast<size_t>(N) * 3 * Kk);
+    rvq_split_weight_host(W.data(), N, Kk, hb.data());
+    FRT2_TRY(dev_alloc(reinterpret_cast<void**>(out), hb.size() * 2));
+    FRT2_CUDA_OK(cudaMemcpy(*out, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
+    return FRT2_OK;
+  }
   int build_rvq_encoder();
   __half* w_outproj = nullptr; float* b_outproj = nullptr;
   __half* w_up_in = nullptr;   float* b_up_in = nullptr;
@@ -534,10 +542,14 @@ int Handle::build_rvq_encoder() {
       for (int k = 0; k < enc_input_dim; ++k) WT[static_cast<size_t>(k) * rd + o] = W[static_cast<size_t>(o) * enc_input_dim + k];
     FRT2_TRY(upload_f32(WT, &enc_WinpT));
     FRT2_TRY(upload_f32(b->data, &enc_binp));
+    FRT2_TRY(upload_split(W, rd, enc_input_dim, &enc_s_inp));
   }
   std::vector<float> CT(static_cast<size_t>(nq) * cd * K), c2(static_cast<size_t>(nq) * K);
   std::vector<float> WinT, bin, WoutT, bout;
+  std::vector<float> Win_all, Wout_all, C_all(static_cast<size_t>(nq) * K * cd);   // (out, in) row-major, for the split copies
   if (has_out_project) {
+    Win_all.resize(static_cast<size_t>(nq) * cd * rd);
+    Wout_all.resize(static_cast<size_t>(nq) * rd * cd);
     WinT.resize(static_cast<size_t>(nq) * rd * cd);
     bin.resize(static_cast<size_t>(nq) * cd);
     WoutT.resize(static_cast<size_t>(nq) * cd * rd);
@@ -546,6 +558,7 @@ int Handle::build_rvq_encoder() {
   for (int i = 0; i < nq; ++i) {
     const std::string q = RVQ + "quantizers." + std::to_string(i);
     FRT2_TRY(need(q + ".codebook", &t, {K, cd}));
+    std::memcpy(&C_all[static_cast<size_t>(i) * K * cd], t->data.data(), static_cast<size_t>(K) * cd * 4);
     for (int64_t k = 0; k < K; ++k) {
       double ss = 0.0;
       for (int c = 0; c < cd; ++c) {
@@ -564,6 +577,7 @@ int Handle::build_rvq_encoder() {
       for (int o = 0; o < cd; ++o)
         for (int k = 0; k < rd; ++k) WinT[(static_cast<size_t>(i) * rd + k) * cd + o] = Wi[static_cast<size_t>(o) * rd + k];
       std::memcpy(&bin[static_cast<size_t>(i) * cd], b->data.data(), static_cast<size_t>(cd) * 4);
+      std::memcpy(&Win_all[static_cast<size_t>(i) * cd * rd], Wi.data(), Wi.size() * 4);
       FRT2_TRY(need(q + ".out_project.parametrizations.weight.original0", &g, {rd, 1, 1}));
       FRT2_TRY(need(q + ".out_project.parametrizations.weight.original1", &v, {rd, cd, 1}));
       FRT2_TRY(need(q + ".out_project.bias", &b, {rd}));
@@ -571,6 +585,7 @@ int Handle::build_rvq_encoder() {
       for (int o = 0; o < rd; ++o)
         for (int k = 0; k < cd; ++k) WoutT[(static_cast<size_t>(i) * cd + k) * rd + o] = Wo[static_cast<size_t>(o) * cd + k];
       std::memcpy(&bout[static_cast<size_t>(i) * rd], b->data.data(), static_cast<size_t>(rd) * 4);
+      std::memcpy(&Wout_all[static_cast<size_t>(i) * rd * cd], Wo.data(), Wo.size() * 4);
     }
   }
   FRT2_TRY(upload_f32(CT, &enc_CT));
@@ -580,6 +595,17 @@ int Handle::build_rvq_encoder() {
     FRT2_TRY(upload_f32(bin, &enc_bin));
     FRT2_TRY(upload_f32(WoutT, &enc_WoutT));
     FRT2_TRY(upload_f32(bout, &enc_bout));
+  }
+  // split-fp16 copies for the tensor-core chain (widths that are multiples of 64; the CUDA-core kernel serves the rest)
+  if (rd % 64 == 0 && cd % 64 == 0 && enc_input_dim % 64 == 0) {
+    FRT2_TRY(upload_split(C_all, static_cast<int64_t>(nq) * K, cd, &enc_s_C));
+    if (has_out_project) {
+      FRT2_TRY(upload_split(Win_all, static_cast<int64_t>(nq) * cd, rd, &enc_s_in));
+      FRT2_TRY(upload_split(Wout_all, static_cast<int64_t>(nq) * rd, cd, &enc_s_out));
+      std::vector<float> nb(bout.size());
+      for (size_t j = 0; j < nb.size(); ++j) nb[j] = -bout[j];
+      FRT2_TRY(upload_f32(nb, &enc_nbout));
+    }
   }
   enc_ready = true;
   return FRT2_OK;
@@ -1887,7 +1913,46 @@ int frt2_rvq_encode(frt2_handle* hh, const float* z, int64_t sB, int64_t sD, int
   d.WinpT = h.enc_WinpT; d.binp = h.enc_binp; d.WinT = h.enc_WinT; d.bin = h.enc_bin; d.CT = h.enc_CT; d.c2 = h.enc_c2;
   d.C = h.codebooks; d.WoutT = h.enc_WoutT; d.bout = h.enc_bout;
   d.codes = reinterpret_cast<long long*>(codes);
-  return rvq_encode(d, static_cast<cudaStream_t>(cuda_stream));
+  d.s_inp = h.enc_s_inp; d.s_in = h.enc_s_in; d.s_C = h.enc_s_C; d.s_out = h.enc_s_out; d.nbout = h.enc_nbout;
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  // product path: the chain on the tensor cores (split-fp16 GEMMs); FRT2_RVQ_ENC_SIMT=1 / DBG_GEMM_REF select the
+  // CUDA-core kernel (A/B, checker), which also serves widths that are not multiples of 64
+  static const bool force_simt = getenv("FRT2_RVQ_ENC_SIMT") != nullptr && atoi(getenv("FRT2_RVQ_ENC_SIMT")) != 0;
+  if (force_simt || (h.debug & DBG_GEMM_REF) || !rvq_encode_tc_applicable(d)) return rvq_encode(d, st);
+  std::lock_guard<std::mutex> lk(h.mu);
+  // slabs of tokens bound the score buffer (K floats per token)
+  const long long R = static_cast<long long>(B) * T;
+  if (R == 0) return FRT2_OK;
+  const long long SLAB = 32768;
+  if (R <= SLAB) {
+    FRT2_TRY(h.ensure_ws(rvq_encode_tc_ws_bytes(d, R)));
+    FRT2_TRY(h.ws_acquire(st));
+    long long n = 0;
+    FRT2_TRY(rvq_encode_tc(d, h.ws, st, &n));
+    h.launches += n;
+    return h.ws_release(st);
+  }
+  // larger inputs: item by item groups whose token count fits a slab (codes are (nq, B, T): a group is a B-slice,
+  // written through a temporary because its rows are not contiguous in the output)
+  const int per = static_cast<int>(std::max<long long>(1, SLAB / std::max(1, T)));
+  FRT2_REQUIRE(static_cast<long long>(T) <= SLAB, FRT2_ERR_BAD_ARG, "frt2_rvq_encode: more than 32768 frames per item");
+  FRT2_TRY(h.ensure_ws(rvq_encode_tc_ws_bytes(d, static_cast<long long>(per) * T) +
+                       static_cast<size_t>(nq) * per * T * sizeof(long long)));
+  FRT2_TRY(h.ws_acquire(st));
+  long long* tmp = reinterpret_cast<long long*>(h.ws + rvq_encode_tc_ws_bytes(d, static_cast<long long>(per) * T));
+  for (int b0 = 0; b0 < B; b0 += per) {
+    RvqEncDesc g = d;
+    g.B = std::min(per, B - b0);
+    g.z = z + static_cast<int64_t>(b0) * sB;
+    g.codes = tmp;
+    long long n = 0;
+    FRT2_TRY(rvq_encode_tc(g, h.ws, st, &n));
+    h.launches += n;
+    FRT2_CUDA_OK(cudaMemcpy2DAsync(d.codes + static_cast<long long>(b0) * T, static_cast<size_t>(B) * T * 8, tmp,
+                                   static_cast<size_t>(g.B) * T * 8, static_cast<size_t>(g.B) * T * 8, nq,
+                                   cudaMemcpyDeviceToDevice, st));
+  }
+  return h.ws_release(st);
 }
 
 // FIR bank of torchaudio's sinc_interp_hann resampler, computed in float32 in the same operation order as

@@ -65,6 +65,40 @@ def test_rvq_encode_c0_against_oracle_and_batch_independence():
     assert audio.shape == (4, 250 * cfg.samples_per_token) and bool(torch.isfinite(audio).all())
 
 
+def test_rvq_encode_tensor_core_chain_vs_cuda_core_kernel():
+    """The product path runs the chain as split-fp16 tcgen05 GEMMs (rvq_encode_tc.cu); the fp32 CUDA-core kernel
+    (DBG_GEMM_REF) is its checker: same indices wherever the oracle's top-2 margin exceeds the fp32 rounding scale, on
+    channel-major and time-major inputs, for prefixes of the quantizers and for more tokens than one slab."""
+    from fireredtts2_b200 import _native as N
+    from fireredtts2_b200.config import C0
+    from fireredtts2_b200.weights import synthetic_encode_tensors, synthetic_state_dict
+    cfg = C0
+    sd = dict(synthetic_state_dict(cfg, 0))
+    sd.update(synthetic_encode_tensors(cfg, 0))
+    codec = build_codec(cfg, sd, check_indices=False)
+    rng = np.random.default_rng(21)
+    z = rng.standard_normal((3, cfg.embed_dim, 333)).astype(np.float32)
+    ref, margin = O.rvq_encode_codes(sd, z)
+    zc = torch.from_numpy(z).cuda()
+    tc = codec.rvq_encode_codes(zc)
+    _compare("c0 3x333 tensor-core chain vs oracle", tc, ref, margin, 2e-4)
+    codec.set_debug(N.DBG_GEMM_REF)
+    simt = codec.rvq_encode_codes(zc)
+    codec.set_debug(0)
+    _compare("c0 3x333 cuda-core kernel vs oracle", simt, ref, margin, 2e-4)
+    same = float((tc == simt).float().mean())
+    print(f"[parity] tensor-core chain == cuda-core kernel on {same * 100:.2f} % of the indices")
+    assert same >= 0.995
+    zt = zc.transpose(1, 2).contiguous().transpose(1, 2)                 # time-major storage
+    assert torch.equal(codec.rvq_encode_codes(zt), tc)
+    assert torch.equal(codec.rvq_encode_codes(zc, nq=3), tc[:3])
+    # more than one slab of 32768 tokens: groups of items, same indices as item by item
+    zb = torch.from_numpy(rng.standard_normal((5, cfg.embed_dim, 9000)).astype(np.float32)).cuda()
+    big = codec.rvq_encode_codes(zb, nq=4)
+    for b in (0, 3, 4):
+        assert torch.equal(big[:, b], codec.rvq_encode_codes(zb[b:b + 1], nq=4)[:, 0])
+
+
 def test_rvq_encode_tile_size_does_not_change_the_indices():
     """The kernel picks 32 or 8 tokens per CTA from the batch size (small batches: more, smaller tiles); a token's
     arithmetic does not depend on the tile it sits in, so the variants agree bit for bit."""
@@ -74,6 +108,8 @@ def test_rvq_encode_tile_size_does_not_change_the_indices():
     sd = dict(synthetic_state_dict(cfg, 1))
     sd.update(synthetic_encode_tensors(cfg, 1))
     codec = build_codec(cfg, sd, check_indices=False)
+    from fireredtts2_b200 import _native as N
+    codec.set_debug(N.DBG_GEMM_REF)                                     # the CUDA-core kernel (the product path is the GEMM chain)
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     T = 32 * sms + 13                                                   # >= 32 tokens per SM: 32 per CTA
     z = torch.from_numpy(np.random.default_rng(8).standard_normal((1, cfg.embed_dim, T)).astype(np.float32)).cuda()
