@@ -608,6 +608,13 @@ def run_ours(args):
                    "note": "whole job per step: every rank uploads its tokens; the waveforms of all ranks are read to "
                            "pinned host memory" + (" by rank 0 after the gather" if world > 1 else "")},
            "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels, "parity": parity, "latency": lat}
+    if world == 1 and not args.no_extras:
+        try:
+            del codec
+            torch.cuda.empty_cache()
+            out["encode"] = encode_record(dev)
+        except Exception as e:      # noqa: BLE001 — an extra record must never cost the bench line
+            out["encode"] = {"unavailable": repr(e)}
     if world > 1:
         out["gather"] = {"mode": gather_mode, "bytes_into_rank0_per_step": int((world - 1) * B * n_samples * 4),
                          "check": gathered_ok,
@@ -735,6 +742,60 @@ def first_chunk_latency(codec, cfg, dev, reps=200):
                                  "126 MB L2); the step is a chain of ~90 dependent <= 16-row kernels, i.e. latency-bound"}}
 
 
+def encode_record(dev, batch=96, frames=300, reps=5):
+    """SURVEY 8f.3 sub-record: the codec ENCODE side behind the feature encoders at the reference's batch shape (96 chunks
+    of 6 s = 300 frames at 50 Hz each, model.py:247,262): SslAdaptor + cat + ResidualDownConv (frt2_enc_features) and the
+    RVQ search (frt2_rvq_encode, split-fp16 tensor-core chain), EC0 / C0 widths, random weights; one item checked against
+    the numpy oracle.  (The whole path from the waveform needs the 640 M-parameter SSL encoder: tools/encode_bench.py --audio.)"""
+    import torch
+    from fireredtts2_b200.codec import RedCodecB200
+    from fireredtts2_b200.config import C0
+    from fireredtts2_b200.encoder import EC0, CodecEncoderB200, synthetic_encoder_state_dict, synthetic_features
+    from fireredtts2_b200.weights import synthetic_encode_tensors, synthetic_state_dict
+    from oracle import codec_oracle as O
+    from oracle import encoder_oracle as EO
+    esd = synthetic_encoder_state_dict(EC0, 0)
+    enc = CodecEncoderB200(EC0, esd, device=str(dev))
+    sd = dict(synthetic_state_dict(C0, 0))
+    sd.update(synthetic_encode_tensors(C0, 0, EC0.down_dim))
+    rvq = RedCodecB200(C0, sd, device=str(dev), check_indices=False)
+    ssl_np, aco_np = synthetic_features(EC0, batch, frames, 3)
+    ssl, aco = torch.from_numpy(ssl_np).to(dev), torch.from_numpy(aco_np).to(dev)
+    for _ in range(2):
+        codes = enc.encode_features(ssl, aco, rvq)
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    tf, tq = [], []
+    for _ in range(reps):
+        ev[0].record()
+        vq = enc.features(ssl, aco)
+        ev[1].record()
+        codes = rvq.rvq_encode_codes(vq.transpose(1, 2))
+        ev[2].record()
+        torch.cuda.synchronize()
+        tf.append(ev[0].elapsed_time(ev[1]))
+        tq.append(ev[1].elapsed_time(ev[2]))
+    ref = EO.encode_features(esd, ssl_np[:1], aco_np[:1], EC0.ssl_num_heads, EC0.avg_pooler)
+    got = vq[:1].cpu().numpy()
+    ref_codes, margin = O.rvq_encode_codes(sd, np.ascontiguousarray(got.transpose(0, 2, 1)))
+    M = batch * frames
+    E, F, D, P = EC0.ssl_embed_dim, EC0.ffn_dim, EC0.down_dim, EC0.avg_pooler * EC0.down_dim
+    fl = (2.0 * M * EC0.ssl_in_dim * E + EC0.ssl_num_layers * (2.0 * M * E * (4 * E + 2 * F) + 4.0 * E * frames * M) +
+          2.0 * M * E * EC0.ssl_out_dim + (M / EC0.avg_pooler) * 2.0 * P * (3 * P + D))
+    ms_f, ms_q = statistics.median(tf), statistics.median(tq)
+    pk, _ = peaks()
+    peak = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    audio_s = batch * frames / 50.0
+    return {"workload": f"codec encode side behind the feature encoders: {batch} chunks x {frames} frames (50 Hz) = "
+                        f"{audio_s:.0f} audio-s per batch; EC0 ssl_adaptor / downsample + C0 RVQ, random weights",
+            "features_ms": ms_f, "rvq_search_ms": ms_q, "audio_s_per_s": audio_s / ((ms_f + ms_q) * 1e-3),
+            "launches": enc.last_launches,
+            "roofline": {"bound": "tensor", "achieved": fl / (ms_f * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                         "frac": fl / (ms_f * 1e-3) / 1e12 / peak if peak else None, "kernel": "frt2_enc_features (gemm_tc + attention_t4)"},
+            "parity": {"vq_in_feats_snr_db_vs_oracle": O.snr_db(ref, got), "gate_snr_db": 40.0,
+                       "indices_identical_to_oracle_on_gpu_features": float((codes[:, 0].cpu().numpy() == ref_codes[:, 0]).mean())}}
+
+
 def llm_overlap(codec, cfg, dev, frames=96, producer_ms=(4.0, 12.0)):
     """SURVEY 8f.1 — the codec half of the reference's ``generate_stream`` (fireredtts2.py:259-343) next to a SIMULATED
     frame producer.  The LLM is out of scope, so the producer is a stand-in with the same shape of work: per frame a
@@ -836,16 +897,18 @@ def llm_overlap(codec, cfg, dev, frames=96, producer_ms=(4.0, 12.0)):
                 return sorted(m.elapsed_time(r) for m, r in list(zip(marks, readies))[2:-1])
             return None
 
-        res = {}
-        for name, fn in (("producer_only", run_producer_only), ("serial", run_serial), ("overlapped", run_overlapped)):
+        # the three loops take turns (clock / power drift hits all of them alike); medians over 5 rounds
+        modes = (("producer_only", run_producer_only), ("serial", run_serial), ("overlapped", run_overlapped))
+        for _, fn in modes:
             fn()
-            ts = []
-            for _ in range(3):
+        samples = {name: [] for name, _ in modes}
+        for _ in range(5):
+            for name, fn in modes:
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 fn()
-                ts.append(1e3 * (time.perf_counter() - t0) / frames)
-            res[name] = min(ts)
+                samples[name].append(1e3 * (time.perf_counter() - t0) / frames)
+        res = {name: statistics.median(v) for name, v in samples.items()}
         rec = {"producer_ms_per_frame": res["producer_only"], "serial_ms_per_frame": res["serial"],
                "overlapped_ms_per_frame": res["overlapped"],
                "codec_cost_serial_ms": res["serial"] - res["producer_only"],
