@@ -21,6 +21,7 @@
 // statistics, exactly as on the decode side.  The result feeds frt2_rvq_encode.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -206,6 +207,74 @@ __global__ void __launch_bounds__(256) mel_power_kernel(const float* __restrict_
   if ((threadIdx.x & 31) == 0) atomicMax(item_max + b, __float_as_int(local_max));
 }
 
+// ---- the same front end with the DFT on the tensor cores (product path) ----
+// The 400-point real DFT of every frame is a GEMM: frames (rows) x [cos | sin] twiddles (2 x 201 columns), evaluated with
+// SPLIT fp16 operands like the RVQ chain (rvq_encode_tc.cu): x = x_hi + x_lo, three-term product in ONE GEMM over a
+// reduction of 3 * KP (KP = n_fft padded to a multiple of 64), fp32 accumulation — ~22 significant bits, the precision
+// of the reference's fp32 FFT — instead of 2 * 400 * 201 FMAs per frame on the CUDA cores (the direct kernel above took
+// 1.64 ms per 32 chunks, 8 % of the whole encode; it stays as the checker, FRT2_MEL_SIMT=1).
+constexpr float MEL_S = 256.0f;
+
+// reflect-padded, Hann-windowed frames -> split rows [hi | hi/S | lo*S] of KP columns each; one thread per (frame, column)
+__global__ void __launch_bounds__(256) mel_frames_kernel(const float* __restrict__ audio, long long audio_pitch, long long n,
+                                                         int T, int n_fft, int hop, int KP, const float* __restrict__ window,
+                                                         __half* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long per_item = static_cast<long long>(T) * KP;
+  const int b = blockIdx.y;
+  if (i >= per_item) return;
+  const int t = static_cast<int>(i / KP), j = static_cast<int>(i - static_cast<long long>(t) * KP);
+  float v = 0.f;
+  if (j < n_fft) {
+    long long k = static_cast<long long>(t) * hop - n_fft / 2 + j;
+    if (k < 0) k = -k;
+    if (k >= n) k = 2 * (n - 1) - k;
+    v = audio[static_cast<long long>(b) * audio_pitch + k] * __ldg(window + j);
+  }
+  const __half hi = to_half_sat(v);
+  const float h = __half2float(hi);
+  __half* o = out + (static_cast<long long>(b) * T + t) * 3 * KP + j;
+  o[0] = hi;
+  o[KP] = __float2half_rn(h * (1.0f / MEL_S));
+  o[2 * KP] = __float2half_rn((v - h) * MEL_S);
+}
+
+// spec (frames, ld) fp32 = [Re X_0..X_bins-1 | Im X_0..X_bins-1] -> power -> mel bank -> log10, per-item maximum
+__global__ void __launch_bounds__(256) mel_bank_kernel(const float* __restrict__ spec, long long ld, int T, int bins,
+                                                       const float* __restrict__ bank, int n_mels,
+                                                       float* __restrict__ logmel, int* __restrict__ item_max) {
+  extern __shared__ float mel_smem[];
+  float* s_pw = mel_smem;                  // [MEL_FR][bins]
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * MEL_FR;
+  for (int e = threadIdx.x; e < MEL_FR * bins; e += blockDim.x) {
+    const int f = e / bins, k = e - f * bins;
+    float pw = 0.f;
+    if (t0 + f < T) {
+      const float* row = spec + (static_cast<long long>(b) * T + t0 + f) * ld;
+      const float re = row[k], im = row[bins + k];
+      pw = re * re + im * im;
+    }
+    s_pw[e] = pw;
+  }
+  __syncthreads();
+  float local_max = 0.f;
+  for (int e = threadIdx.x; e < MEL_FR * n_mels; e += blockDim.x) {
+    const int f = e / n_mels, m = e - f * n_mels;
+    const int t = t0 + f;
+    if (t >= T) continue;
+    const float* pw = s_pw + f * bins;
+    float acc = 0.f;
+    for (int k = 0; k < bins; ++k) acc = fmaf(__ldg(bank + static_cast<long long>(k) * n_mels + m), pw[k], acc);
+    const float lg = log10f(fmaxf(acc, 1e-10f));
+    logmel[(static_cast<long long>(b) * T + t) * n_mels + m] = lg;
+    local_max = fmaxf(local_max, lg + 10.0f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) local_max = fmaxf(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(item_max + b, __float_as_int(local_max));
+}
+
 // log_spec = max(log_spec, item_max - 8); (log_spec + 4) / 4  (whisper.py:294-295) -> fp32 (parity hook) and fp16 (conv1's operand)
 __global__ void __launch_bounds__(256) mel_norm_kernel(const float* __restrict__ logmel, const int* __restrict__ item_max,
                                                        long long per_item, long long total, float* __restrict__ out32,
@@ -263,6 +332,8 @@ struct Encoder {
   EncStack ssl_stack, aco_stack;                     // ssl.layers / acoustic_encoder.layers
   EncFront ssl_front, aco_front;
   float *mel_window = nullptr, *mel_bank = nullptr;  // hann(n_fft); (n_fft/2+1, n_mels) slaney bank
+  __half* mel_dft_s = nullptr;                       // (2*bins, 3*KP) split-fp16 [cos | sin] twiddle rows
+  int mel_kp = 0;                                    // n_fft padded to a multiple of 64
   unsigned int* sched = nullptr;                     // item-scheduler words of the persistent attention kernel
   uint8_t* ws = nullptr;
   size_t ws_bytes = 0;
@@ -373,7 +444,7 @@ struct Encoder {
   int run_front(const EncFront& f, const EncStack& s, const __half* mel16, int B, int Tm, __half* c1, float* x32,
                 cudaStream_t st);
   int mel(const float* audio, int64_t pitch, int B, int64_t n, float* logmel, int* item_max, float* out32, __half* out16,
-          cudaStream_t st);
+          __half* fr_s, float* spec, cudaStream_t st);
   int downstream(const __half* ssl16, int64_t M, int B, int T, uint8_t* base, float* vq_in, cudaStream_t st,
                  const float* aco32);
   int features(const float* ssl, const float* aco_feats, int B, int T, float* vq_in, cudaStream_t st);
@@ -559,6 +630,19 @@ int Encoder::finalize() {
     }
     FRT2_TRY(up32(win, &mel_window));
     FRT2_TRY(up32(bank, &mel_bank));
+    // twiddles of the real DFT as GEMM weights: row k < bins = cos(2 pi k j / n_fft), row bins + k = sin(...), exact phase
+    mel_kp = (n_fft + 63) / 64 * 64;
+    std::vector<float> tw(static_cast<size_t>(2 * bins) * mel_kp, 0.f);
+    for (int k = 0; k < bins; ++k)
+      for (int j = 0; j < n_fft; ++j) {
+        const double ang = 2.0 * M_PI * static_cast<double>((static_cast<long long>(k) * j) % n_fft) / n_fft;
+        tw[static_cast<size_t>(k) * mel_kp + j] = static_cast<float>(std::cos(ang));
+        tw[static_cast<size_t>(bins + k) * mel_kp + j] = static_cast<float>(std::sin(ang));
+      }
+    std::vector<__half> tws(tw.size() * 3);
+    rvq_split_weight_host(tw.data(), 2 * bins, mel_kp, tws.data());
+    FRT2_TRY(dev_alloc(reinterpret_cast<void**>(&mel_dft_s), tws.size() * 2));
+    FRT2_CUDA_OK(cudaMemcpy(mel_dft_s, tws.data(), tws.size() * 2, cudaMemcpyHostToDevice));
   }
   FRT2_TRY(dev_alloc(reinterpret_cast<void**>(&sched), 16));
   FRT2_CUDA_OK(cudaMemset(sched, 0, 16));
@@ -622,19 +706,39 @@ int Encoder::run_front(const EncFront& f, const EncStack& s, const __half* mel16
 }
 
 int Encoder::mel(const float* audio, int64_t pitch, int B, int64_t n, float* logmel, int* item_max, float* out32,
-                 __half* out16, cudaStream_t st) {
+                 __half* out16, __half* fr_s, float* spec, cudaStream_t st) {
   const int T = static_cast<int>(n / hop);
   FRT2_CUDA_OK(cudaMemsetAsync(item_max, 0, static_cast<size_t>(B) * sizeof(int), st));
   const int bins = n_fft / 2 + 1;
-  const size_t smem = static_cast<size_t>(2 * n_fft + MEL_FR * n_fft + MEL_FR * bins) * sizeof(float);
-  mel_power_kernel<<<dim3((T + MEL_FR - 1) / MEL_FR, B), 256, smem, st>>>(audio, pitch, n, T, n_fft, hop, mel_window,
-                                                                        mel_bank, n_mels, logmel, item_max);
-  FRT2_CUDA_OK(cudaGetLastError());
+  static const bool simt = getenv("FRT2_MEL_SIMT") != nullptr && atoi(getenv("FRT2_MEL_SIMT")) != 0;   // checker / A-B
+  if (simt) {
+    const size_t smem = static_cast<size_t>(2 * n_fft + MEL_FR * n_fft + MEL_FR * bins) * sizeof(float);
+    mel_power_kernel<<<dim3((T + MEL_FR - 1) / MEL_FR, B), 256, smem, st>>>(audio, pitch, n, T, n_fft, hop, mel_window,
+                                                                          mel_bank, n_mels, logmel, item_max);
+    FRT2_CUDA_OK(cudaGetLastError());
+    launches += 1;
+  } else {
+    const int KP = mel_kp, ld = (2 * bins + 3) / 4 * 4;
+    const long long per_item = static_cast<long long>(T) * KP;
+    mel_frames_kernel<<<dim3(static_cast<unsigned>((per_item + 255) / 256), B), 256, 0, st>>>(audio, pitch, n, T, n_fft, hop,
+                                                                                            KP, mel_window, fr_s);
+    FRT2_CUDA_OK(cudaGetLastError());
+    GemmDesc g{};
+    const int64_t Mm = static_cast<int64_t>(B) * T;
+    g.A = fr_s; g.a_row_pitch = 3 * KP; g.rows_a = static_cast<int>(Mm); g.batches = 1; g.Kc = 3 * KP; g.ntaps = 1;
+    g.W = mel_dft_s; g.N = 2 * bins; g.rows_out = static_cast<int>(Mm); g.alpha = 1.0f; g.act = ACT_NONE;
+    g.out32 = spec; g.ld32 = ld;
+    FRT2_TRY(gemm_tc(g, st));
+    mel_bank_kernel<<<dim3((T + MEL_FR - 1) / MEL_FR, B), 256, static_cast<size_t>(MEL_FR) * bins * sizeof(float), st>>>(
+        spec, ld, T, bins, mel_bank, n_mels, logmel, item_max);
+    FRT2_CUDA_OK(cudaGetLastError());
+    launches += 3;
+  }
   const long long total = static_cast<long long>(B) * T * n_mels;
   mel_norm_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(logmel, item_max, static_cast<long long>(T) * n_mels,
                                                                             total, out32, out16);
   FRT2_CUDA_OK(cudaGetLastError());
-  launches += 2;
+  launches += 1;
   return FRT2_OK;
 }
 
@@ -711,9 +815,13 @@ int Encoder::audio_features(const float* audio, int64_t pitch, int B, int64_t n,
   size_t so_s[4], so_a[4];
   const size_t sb_s = stack_bytes(ssl_stack, M, so_s), sb_a = stack_bytes(aco_stack, M, so_a);
   const int Emax = std::max(ssl_stack.E, aco_stack.E);
+  // the split frame rows / DFT output of the log-mel front end are dead once mel16 exists: they share the bytes of the
+  // encoders' scratch (c1, x32, layer-stack buffers)
+  const int spec_ld = (n_fft + 2 + 3) / 4 * 4;
+  const size_t mel_tmp = al(Mm * 3 * static_cast<size_t>(mel_kp) * 2) + al(Mm * static_cast<size_t>(spec_ld) * 4);
   const size_t o_logmel = 0, o_imax = o_logmel + al(Mm * n_mels * 4), o_mel16 = o_imax + al(B * 4),
                o_c1 = o_mel16 + al(Mm * n_mels * 2), o_x32 = o_c1 + al(Mm * Emax * 2), o_stack = o_x32 + al(M * Emax * 4),
-               scratch = o_stack + std::max(sb_s, sb_a);
+               scratch = std::max(o_stack + std::max(sb_s, sb_a), o_c1 + mel_tmp);
   FRT2_TRY(ensure_ws(ssl_bytes + down_bytes + scratch));
   FRT2_TRY(begin(st));
   __half* ssl16 = reinterpret_cast<__half*>(ws);
@@ -727,7 +835,8 @@ int Encoder::audio_features(const float* audio, int64_t pitch, int B, int64_t n,
   uint8_t* sbase = sc + o_stack;
   float* cat32 = reinterpret_cast<float*>(down);                                // downstream()'s first two buffers
   __half* cat16 = reinterpret_cast<__half*>(down + al(M * D * 4));
-  FRT2_TRY(mel(audio, pitch, B, n, logmel, imax, mel_out, mel16, st));
+  FRT2_TRY(mel(audio, pitch, B, n, logmel, imax, mel_out, mel16, reinterpret_cast<__half*>(sc + o_c1),
+               reinterpret_cast<float*>(sc + o_c1 + al(Mm * 3 * static_cast<size_t>(mel_kp) * 2)), st));
   // semantic encoder: its final LayerNorm output is only ever a GEMM operand (ssl_adaptor.in_proj) -> fp16
   FRT2_TRY(run_front(ssl_front, ssl_stack, mel16, B, Tm, c1, x32, st));
   {
