@@ -155,11 +155,19 @@ class RedCodecB200(torch.nn.Module):
 
     @classmethod
     def from_pretrained(cls, conf_path: str, ckpt_path: str, **kw) -> "RedCodecB200":
-        """Same arguments as ``RedCodecInfer.from_pretrained`` (reference model.py:210-216); decode-only."""
+        """Same arguments as ``RedCodecInfer.from_pretrained`` (reference model.py:210-216); decode-only unless
+        ``native_encode=True`` (then ``encode`` runs on the library too, fireredtts2_b200/encoder.py)."""
+        native_encode = kw.pop("native_encode", False)
         with open(conf_path, "r") as f:
-            cfg = CodecConfig.from_reference_dict(json.load(f))
+            conf = json.load(f)
+        cfg = CodecConfig.from_reference_dict(conf)
         ckpt = torch.load(ckpt_path, map_location="cpu")["generator"]
-        return cls(cfg, ckpt, **kw)
+        codec = cls(cfg, ckpt, **kw)
+        if native_encode:       # encode() on the library as well: the checkpoint holds ssl.*, ssl_adaptor.*, acoustic_encoder.*, downsample.*
+            from .encoder import CodecEncoderB200, EncoderConfig
+            c = dict(conf.get("codec", conf), with_feature_encoders=True)
+            codec.attach_encoder(CodecEncoderB200(EncoderConfig.from_reference_dict(c), ckpt, device=str(codec.device)))
+        return codec
 
     # ------------------------------------------------------------------ nn.Module compatibility
     def to(self, *args, **kwargs):  # weights live in the native handle on self.device

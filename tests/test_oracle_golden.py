@@ -248,6 +248,12 @@ def test_encoder_config_roundtrip():
     with pytest.raises(ValueError):
         bad = dict(d, downsample=dict(d["downsample"], embed_dim=EC0.down_dim + 8))
         EncoderConfig.from_reference_dict(bad)
+    # with the feature encoders: the SSL encoder's shape is fixed by PretrainedWhisperEncoder.from_pretrained (whisper.py:359-369)
+    from fireredtts2_b200.encoder import EC0F, front_keys, synthetic_front_state_dict, ETINYF
+    df = EC0F.to_reference_dict()
+    df["with_feature_encoders"] = True
+    assert EncoderConfig.from_reference_dict({"codec": df}) == EC0F
+    assert sorted(synthetic_front_state_dict(ETINYF, 0)) == sorted(front_keys(ETINYF))
     sd = synthetic_encoder_state_dict(EC0, 0)
     assert sorted(sd) == sorted(encoder_keys(EC0))
     assert sd["downsample.gate_proj.weight"].shape == (4 * EC0.down_dim, EC0.down_dim, 4)
