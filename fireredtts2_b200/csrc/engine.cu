@@ -239,6 +239,7 @@ struct Handle {
   __half* w_outproj = nullptr; float* b_outproj = nullptr;
   __half* w_up_in = nullptr;   float* b_up_in = nullptr;
   __half* w_up_conv = nullptr;
+  __half* w_up_comp = nullptr; float* b_up_comp = nullptr;   // output_proj . in_proj . up_conv composed at load: (4E, rd)
   __half* w_us0 = nullptr;     float* b_us0 = nullptr;
   __half* w_us2 = nullptr;     float* b_us2 = nullptr;
   __half* w_inproj = nullptr;  float* b_inproj = nullptr;
@@ -678,6 +679,64 @@ int Handle::finalize() {
       for (int64_t c = 0; c < Cin; ++c) W[n * Cin + c] = wc->data[(c * E + o) * 4 + k];
     }
     FRT2_TRY(upload_f16(W, &w_up_conv));
+    // The RVQ output projection, UpConv.in_proj and the k = s = 4 transposed convolution are three linear maps in a row
+    // (rvq.py:163, model.py:142-148: no non-linearity between them), so they compose at load into ONE (4E x rd) matrix:
+    //   x50 = Wup (Win (Wo emb + bo) + bin) = (Wup Win Wo) emb + Wup (Win bo + bin)
+    // a tenth of the multiply-adds and one launch instead of three; one fp16 rounding of the composed weights instead of
+    // three weight roundings and two activation roundings.  fp32 on the host cores (rows in parallel, contiguous inner
+    // loops).  FRT2_NO_UPCOMP=1 / DBG_TAPS keep the three separate GEMMs (A/B; the "z" tap only exists there).
+    static const bool no_comp = (getenv("FRT2_NO_UPCOMP") != nullptr);
+    if (!no_comp) {
+      const int64_t E4 = 4 * E, Rd = has_output_proj ? rd : E;
+      std::vector<float> Wo_m;                       // (E, rd) or identity
+      const float* bo_p = nullptr;
+      if (has_output_proj) {
+        const HostTensor *g, *v, *bo;
+        FRT2_TRY(need(RVQ + "output_proj.parametrizations.weight.original0", &g, {E, 1, 1}));
+        FRT2_TRY(need(RVQ + "output_proj.parametrizations.weight.original1", &v, {E, rd, 1}));
+        FRT2_TRY(need(RVQ + "output_proj.bias", &bo, {E}));
+        Wo_m = weight_norm_host(*g, *v);
+        bo_p = bo->data.data();
+      }
+      // T1 = Win Wo : (4E, Rd);  hb = Win bo + bin : (4E)
+      std::vector<float> T1(static_cast<size_t>(E4) * Rd), hb(E4);
+#pragma omp parallel for schedule(static)
+      for (long long i = 0; i < E4; ++i) {
+        const float* wi = &w->data[i * E];
+        float* t = &T1[i * Rd];
+        double acc_b = b->data[i];
+        if (has_output_proj) {
+          for (int64_t j = 0; j < Rd; ++j) t[j] = 0.f;
+          for (int64_t k = 0; k < E; ++k) {
+            const float a = wi[k];
+            const float* wo = &Wo_m[k * Rd];
+            for (int64_t j = 0; j < Rd; ++j) t[j] += a * wo[j];
+            acc_b += static_cast<double>(a) * bo_p[k];
+          }
+        } else {
+          for (int64_t j = 0; j < Rd; ++j) t[j] = wi[j];
+        }
+        hb[i] = static_cast<float>(acc_b);
+      }
+      // Wc = Wup_flat T1 : (4E, Rd);  bc = Wup_flat hb
+      std::vector<float> Wc(static_cast<size_t>(E4) * Rd), bc(E4);
+#pragma omp parallel for schedule(static)
+      for (long long n = 0; n < E4; ++n) {
+        const float* wu = &W[n * Cin];
+        float* o = &Wc[n * Rd];
+        for (int64_t j = 0; j < Rd; ++j) o[j] = 0.f;
+        double acc_b = 0.0;
+        for (int64_t c = 0; c < Cin; ++c) {
+          const float a = wu[c];
+          const float* t = &T1[c * Rd];
+          for (int64_t j = 0; j < Rd; ++j) o[j] += a * t[j];
+          acc_b += static_cast<double>(a) * hb[c];
+        }
+        bc[n] = static_cast<float>(acc_b);
+      }
+      FRT2_TRY(upload_f16(Wc, &w_up_comp));
+      FRT2_TRY(upload_f32(bc, &b_up_comp));
+    }
   }
   // ---- upsample_conv (two ConvTranspose1d k=3) ----
   {
@@ -1034,6 +1093,16 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     }
   }
   FRT2_TRY(tap_f32("emb", emb32, R * rd, st));
+  if (w_up_comp != nullptr && !(debug & DBG_TAPS)) {
+    // ---- output projection + UpConv (Linear E->4E, ConvTranspose k=s=4) as ONE GEMM with the weights composed at load:
+    //      its (R, 4E) output is the (4R, E) 50 Hz sequence ----
+    GemmDesc g{};
+    g.A = emb16; g.a_row_pitch = rd; g.a_batch_pitch = static_cast<int64_t>(L) * rd; g.rows_a = L; g.batches = B;
+    g.Kc = rd; g.ntaps = 1; g.row_shift = 0; g.W = w_up_comp; g.N = 4 * E; g.rows_out = L;
+    g.alpha = 1.0f; g.bias = b_up_comp; g.act = ACT_NONE; g.resid = nullptr; g.out32 = nullptr; g.ld32 = 0; g.pitch32 = 0;
+    g.out16 = chunk_ptr(cb[0]); g.ld16 = 4 * E; g.pitch16 = cb[0].pitch;
+    FRT2_TRY(run_gemm(g, st));
+  } else {
   const __half* z = emb16;
   if (has_output_proj) {
     FRT2_TRY(flat_gemm(emb16, R, rd, w_outproj, E, b_outproj, ACT_NONE, nullptr, nullptr, z16, E));
@@ -1049,6 +1118,7 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
     g.alpha = 1.0f; g.bias = nullptr; g.act = ACT_NONE; g.resid = nullptr; g.out32 = nullptr; g.ld32 = 0; g.pitch32 = 0;
     g.out16 = chunk_ptr(cb[0]); g.ld16 = 4 * E; g.pitch16 = cb[0].pitch;
     FRT2_TRY(run_gemm(g, st));
+  }
   }
   if (!streaming) FRT2_TRY(tap_f16("x50", cb[0].p, E, R * 4, E, st));
   // ---- upsample_conv: ConvT(k3,s2)+GELU as a 2-tap conv with N=2E (even|odd phases), ConvT(k3,s1)+GELU 3-tap ----
