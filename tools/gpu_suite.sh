@@ -24,6 +24,9 @@ run decode_misc 900 tests/test_gpu_decode.py -k "rvq or index or varlen or pcm16
 run decode_stream 900 tests/test_gpu_decode.py -k "stream or graph"
 run decode_c0 900 tests/test_gpu_decode.py -k "c0"
 run pool 900 tests/test_gpu_pool.py
+run streams 900 tests/test_gpu_streams.py
+run rvq_encode 900 tests/test_gpu_rvq_encode.py
+run encoder 900 tests/test_gpu_encoder.py
 timeout 600 python __graft_entry__.py --smoke > "$OUT/smoke.log" 2>&1; echo "smoke exit=$?" | tee -a "$OUT/summary.txt"
 grep -h "\[parity\]\|^gemm\|^attention\|smoke:" "$OUT"/*.log > "$OUT/parity_lines.txt" 2>/dev/null
 cat "$OUT/summary.txt"
