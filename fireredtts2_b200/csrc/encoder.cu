@@ -291,6 +291,10 @@ struct EncLayer {
   __half *w_qkv = nullptr, *w_o = nullptr, *w_fc1 = nullptr, *w_fc2 = nullptr;
   float *b_qkv = nullptr, *b_o = nullptr, *b_fc1 = nullptr, *b_fc2 = nullptr;
   float *ln1_g = nullptr, *ln1_b = nullptr, *ln2_g = nullptr, *ln2_b = nullptr;
+  // LayerNorm folded across the GEMMs as on the decode side: LN(x) W^T = rstd (x (gamma.W)^T - mean colsum)
+  // + (b + W beta); the producer of the residual stream (out-projection, fc2) also writes its fp16 copy
+  __half *w_qkv_f = nullptr, *w_fc1_f = nullptr;
+  float *s_qkv = nullptr, *c_qkv = nullptr, *s_fc1 = nullptr, *c_fc1 = nullptr;
 };
 
 // N x WhisperEncoderLayer (whisper.py:121-163) + the LayerNorm behind them.  Head dims the attention kernels do not
@@ -401,8 +405,10 @@ struct Encoder {
   }
   // ---- building blocks (all asynchronous on `st`) ----
   int gemm(const __half* A, int64_t rows, int K, const __half* W, int N, const float* bias, int act, const float* resid,
-           float* out32, int64_t ld32, __half* out16, int64_t ld16, cudaStream_t st) {
+           float* out32, int64_t ld32, __half* out16, int64_t ld16, cudaStream_t st, __half* x16_copy = nullptr,
+           const float2* stats = nullptr, const float* colsum = nullptr) {
     GemmDesc g{};
+    g.x16_out = x16_copy; g.ld_x16 = N; g.stats_in = stats; g.colsum = colsum;
     g.A = A; g.a_row_pitch = K; g.a_batch_pitch = 0; g.rows_a = static_cast<int>(rows); g.batches = 1;
     g.Kc = K; g.ntaps = 1; g.row_shift = 0; g.W = W; g.N = N; g.rows_out = static_cast<int>(rows);
     g.alpha = 1.0f; g.bias = bias; g.act = act; g.resid = resid; g.out32 = out32; g.ld32 = ld32; g.out16 = out16;
@@ -430,15 +436,43 @@ struct Encoder {
     FRT2_CUDA_OK(cudaGetLastError());
     return FRT2_OK;
   }
-  struct StackBufs { __half *n16, *qkv16, *o16, *g16; };
-  static size_t stack_bytes(const EncStack& s, int64_t M, size_t (&o)[4]) {
+  struct StackBufs { __half *n16, *qkv16, *o16, *g16; float2* stats; };
+  static size_t stack_bytes(const EncStack& s, int64_t M, size_t (&o)[5]) {
     size_t off = 0;
     auto take = [&](size_t b) { const size_t at = off; off += (b + 255) & ~static_cast<size_t>(255); return at; };
     o[0] = take(M * s.E * 2);
     o[1] = take(M * 3 * s.H * s.hdp * 2);
     o[2] = take(M * s.H * s.hdp * 2);
     o[3] = take(M * s.F * 2);
+    o[4] = take(M * sizeof(float2));
     return off;
+  }
+  static StackBufs stack_bufs(uint8_t* base, const size_t (&o)[5]) {
+    return StackBufs{reinterpret_cast<__half*>(base + o[0]), reinterpret_cast<__half*>(base + o[1]),
+                     reinterpret_cast<__half*>(base + o[2]), reinterpret_cast<__half*>(base + o[3]),
+                     reinterpret_cast<float2*>(base + o[4])};
+  }
+  int fold_ln(const std::vector<float>& W, const std::vector<float>& bias, const std::vector<float>& gamma,
+              const std::vector<float>& beta, int64_t Nn, int64_t Kk, __half** w_f, float** colsum, float** bias_f) {
+    std::vector<float> Wf(static_cast<size_t>(Nn) * Kk), cs(Nn), bf(Nn);
+#pragma omp parallel for schedule(static)
+    for (long long n = 0; n < Nn; ++n) {
+      double sacc = 0.0, bacc = bias[n];
+      for (int64_t k = 0; k < Kk; ++k) {
+        const float w = W[n * Kk + k];
+        const float wf = w * gamma[k];
+        Wf[n * Kk + k] = wf;
+        // the column sum runs over the ROUNDED fp16 weights the tensor cores see
+        sacc += static_cast<double>(__half2float(__float2half_rn(std::min(65504.0f, std::max(-65504.0f, wf)))));
+        bacc += static_cast<double>(beta[k]) * w;
+      }
+      cs[n] = static_cast<float>(sacc);
+      bf[n] = static_cast<float>(bacc);
+    }
+    FRT2_TRY(up16(Wf, w_f));
+    FRT2_TRY(up32(cs, colsum));
+    FRT2_TRY(up32(bf, bias_f));
+    return FRT2_OK;
   }
   int run_stack(const EncStack& s, float* x32, int B, int T, const StackBufs& w, cudaStream_t st);
   int run_front(const EncFront& f, const EncStack& s, const __half* mel16, int B, int Tm, __half* c1, float* x32,
@@ -489,6 +523,12 @@ int Encoder::load_stack(const std::string& prefix, const std::string& ln_key, En
         }
     FRT2_TRY(up16(wqkv, &L.w_qkv));
     FRT2_TRY(up32(bqkv, &L.b_qkv));
+    {
+      const HostT *g1, *b1;
+      FRT2_TRY(need(p + "self_attn_layer_norm.weight", &g1, {E}));
+      FRT2_TRY(need(p + "self_attn_layer_norm.bias", &b1, {E}));
+      FRT2_TRY(fold_ln(wqkv, bqkv, g1->data, b1->data, 3 * EP, E, &L.w_qkv_f, &L.s_qkv, &L.c_qkv));
+    }
     FRT2_TRY(need(p + "self_attn.out_proj.weight", &w, {E, E}));
     FRT2_TRY(need(p + "self_attn.out_proj.bias", &b, {E}));
     std::vector<float> wo(static_cast<size_t>(E * EP), 0.f);
@@ -501,6 +541,12 @@ int Encoder::load_stack(const std::string& prefix, const std::string& ln_key, En
     FRT2_TRY(need(p + "fc1.bias", &b, {F}));
     FRT2_TRY(up16(w->data, &L.w_fc1));
     FRT2_TRY(up32(b->data, &L.b_fc1));
+    {
+      const HostT *g2, *b2;
+      FRT2_TRY(need(p + "final_layer_norm.weight", &g2, {E}));
+      FRT2_TRY(need(p + "final_layer_norm.bias", &b2, {E}));
+      FRT2_TRY(fold_ln(w->data, b->data, g2->data, b2->data, F, E, &L.w_fc1_f, &L.s_fc1, &L.c_fc1));
+    }
     FRT2_TRY(need(p + "fc2.weight", &w, {E, F}));
     FRT2_TRY(need(p + "fc2.bias", &b, {E}));
     FRT2_TRY(up16(w->data, &L.w_fc2));
@@ -652,12 +698,30 @@ int Encoder::finalize() {
   return FRT2_OK;
 }
 
-// x32 (B*T, E) fp32 residual stream, updated in place; leaves nothing else behind (the caller applies the final LayerNorm)
+// x32 (B*T, E) fp32 residual stream, updated in place; leaves nothing else behind (the caller applies the final LayerNorm).
+// LayerNorm is folded across the GEMMs like on the decode side: the out-projection and fc2 also write the fp16 copy of the
+// rows they produce, row_stats reads that copy (2 B per element instead of LayerNorm's 4 in + 2 out) and the q|k|v / fc1
+// GEMM finishes the normalisation in its epilogue.  Only the first LayerNorm of a stack (its rows come from a producer
+// without that copy) and the final one are kernels.  FRT2_ENC_NO_LNFOLD=1: every LayerNorm as a kernel (A/B).
 int Encoder::run_stack(const EncStack& s, float* x32, int B, int T, const StackBufs& w, cudaStream_t st) {
   const int64_t M = static_cast<int64_t>(B) * T, E = s.E, EP = static_cast<int64_t>(s.H) * s.hdp;
-  for (const EncLayer& L : s.layers) {
-    FRT2_TRY(ln16(x32, M, s.E, L.ln1_g, L.ln1_b, w.n16, st));
-    FRT2_TRY(gemm(w.n16, M, s.E, L.w_qkv, static_cast<int>(3 * EP), L.b_qkv, ACT_NONE, nullptr, nullptr, 0, w.qkv16, 3 * EP, st));
+  static const bool no_fold = getenv("FRT2_ENC_NO_LNFOLD") != nullptr && atoi(getenv("FRT2_ENC_NO_LNFOLD")) != 0;
+  const bool fold = !no_fold && s.E <= 2048;     // the same arithmetic whatever the batch (rows are never packed here)
+  auto stats = [&]() {
+    ++launches;
+    return row_stats(w.n16, E, M, s.E, 1e-5f, w.stats, st, nullptr);
+  };
+  const size_t nl = s.layers.size();
+  for (size_t i = 0; i < nl; ++i) {
+    const EncLayer& L = s.layers[i];
+    if (fold && i > 0) {     // n16 holds the fp16 copy fc2 of the previous layer wrote
+      FRT2_TRY(stats());
+      FRT2_TRY(gemm(w.n16, M, s.E, L.w_qkv_f, static_cast<int>(3 * EP), L.c_qkv, ACT_NONE, nullptr, nullptr, 0, w.qkv16,
+                    3 * EP, st, nullptr, w.stats, L.s_qkv));
+    } else {
+      FRT2_TRY(ln16(x32, M, s.E, L.ln1_g, L.ln1_b, w.n16, st));
+      FRT2_TRY(gemm(w.n16, M, s.E, L.w_qkv, static_cast<int>(3 * EP), L.b_qkv, ACT_NONE, nullptr, nullptr, 0, w.qkv16, 3 * EP, st));
+    }
     AttnDesc a{};
     a.B = B; a.H = s.H; a.hd = s.hdp; a.Tq = T; a.Tk = T; a.q_pos0 = 0; a.block_causal = 0;
     a.q = w.qkv16; a.q_row_pitch = 3 * EP; a.q_batch_pitch = static_cast<int64_t>(T) * 3 * EP;
@@ -668,10 +732,18 @@ int Encoder::run_stack(const EncStack& s, float* x32, int B, int T, const StackB
     ++launches;
     if ((s.hdp == 64 || s.hdp == 128) && T >= 32) FRT2_TRY(attention_tc(a, st));
     else FRT2_TRY(attention_warp(a, st));
-    FRT2_TRY(gemm(w.o16, M, static_cast<int>(EP), L.w_o, s.E, L.b_o, ACT_NONE, x32, x32, E, nullptr, 0, st));
-    FRT2_TRY(ln16(x32, M, s.E, L.ln2_g, L.ln2_b, w.n16, st));
-    FRT2_TRY(gemm(w.n16, M, s.E, L.w_fc1, s.F, L.b_fc1, ACT_GELU, nullptr, nullptr, 0, w.g16, s.F, st));
-    FRT2_TRY(gemm(w.g16, M, s.F, L.w_fc2, s.E, L.b_fc2, ACT_NONE, x32, x32, E, nullptr, 0, st));
+    FRT2_TRY(gemm(w.o16, M, static_cast<int>(EP), L.w_o, s.E, L.b_o, ACT_NONE, x32, x32, E, nullptr, 0, st,
+                  fold ? w.n16 : nullptr));
+    if (fold) {
+      FRT2_TRY(stats());
+      FRT2_TRY(gemm(w.n16, M, s.E, L.w_fc1_f, s.F, L.c_fc1, ACT_GELU, nullptr, nullptr, 0, w.g16, s.F, st, nullptr, w.stats,
+                    L.s_fc1));
+    } else {
+      FRT2_TRY(ln16(x32, M, s.E, L.ln2_g, L.ln2_b, w.n16, st));
+      FRT2_TRY(gemm(w.n16, M, s.E, L.w_fc1, s.F, L.b_fc1, ACT_GELU, nullptr, nullptr, 0, w.g16, s.F, st));
+    }
+    FRT2_TRY(gemm(w.g16, M, s.F, L.w_fc2, s.E, L.b_fc2, ACT_NONE, x32, x32, E, nullptr, 0, st,
+                  (fold && i + 1 < nl) ? w.n16 : nullptr));
   }
   return FRT2_OK;
 }
@@ -752,11 +824,10 @@ int Encoder::downstream(const __half* ssl16, int64_t M, int B, int T, uint8_t* b
   float* cat32 = reinterpret_cast<float*>(take(M * D * 4));      // FIRST: audio_features() pre-fills the acoustic half
   __half* cat16 = reinterpret_cast<__half*>(take(M * D * 2));
   float* x32 = reinterpret_cast<float*>(take(M * E * 4));
-  size_t so[4];
+  size_t so[5];
   const size_t sb = stack_bytes(ada, M, so);
   uint8_t* sbase = take(sb);
-  StackBufs w{reinterpret_cast<__half*>(sbase + so[0]), reinterpret_cast<__half*>(sbase + so[1]),
-              reinterpret_cast<__half*>(sbase + so[2]), reinterpret_cast<__half*>(sbase + so[3])};
+  StackBufs w = stack_bufs(sbase, so);
   __half* gu16 = reinterpret_cast<__half*>(take(M4 * 2 * P * 2));
   __half* act16 = reinterpret_cast<__half*>(take(M4 * P * 2));
   float* c32 = reinterpret_cast<float*>(take(M4 * P * 4));
@@ -786,7 +857,7 @@ int Encoder::downstream(const __half* ssl16, int64_t M, int B, int T, uint8_t* b
 
 static size_t downstream_bytes(const Encoder& e, int64_t M) {
   const int64_t M4 = M / e.pool, P = static_cast<int64_t>(e.pool) * e.D;
-  size_t so[4];
+  size_t so[5];
   auto al = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
   return al(M * e.D * 4) + al(M * e.D * 2) + al(M * e.ada.E * 4) + al(Encoder::stack_bytes(e.ada, M, so)) +
          al(M4 * 2 * P * 2) + al(M4 * P * 2) + al(M4 * P * 4) + al(M4 * P * 2);
@@ -812,7 +883,7 @@ int Encoder::audio_features(const float* audio, int64_t pitch, int B, int64_t n,
   auto al = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
   // layout: [ssl16 | downstream arena (cat32 first) | encoder scratch]
   const size_t ssl_bytes = al(M * ssl_in * 2), down_bytes = downstream_bytes(*this, M);
-  size_t so_s[4], so_a[4];
+  size_t so_s[5], so_a[5];
   const size_t sb_s = stack_bytes(ssl_stack, M, so_s), sb_a = stack_bytes(aco_stack, M, so_a);
   const int Emax = std::max(ssl_stack.E, aco_stack.E);
   // the split frame rows / DFT output of the log-mel front end are dead once mel16 exists: they share the bytes of the
@@ -840,16 +911,14 @@ int Encoder::audio_features(const float* audio, int64_t pitch, int B, int64_t n,
   // semantic encoder: its final LayerNorm output is only ever a GEMM operand (ssl_adaptor.in_proj) -> fp16
   FRT2_TRY(run_front(ssl_front, ssl_stack, mel16, B, Tm, c1, x32, st));
   {
-    StackBufs w{reinterpret_cast<__half*>(sbase + so_s[0]), reinterpret_cast<__half*>(sbase + so_s[1]),
-                reinterpret_cast<__half*>(sbase + so_s[2]), reinterpret_cast<__half*>(sbase + so_s[3])};
+    StackBufs w = stack_bufs(sbase, so_s);
     FRT2_TRY(run_stack(ssl_stack, x32, B, T, w, st));
     FRT2_TRY(ln32(x32, M, ssl_stack.E, ssl_stack.lnf_g, ssl_stack.lnf_b, ssl_out32, ssl_in, ssl16, ssl_in, st));
   }
   // acoustic encoder: its output is the right half of the concatenated features (fp32 residual + fp16 operand)
   FRT2_TRY(run_front(aco_front, aco_stack, mel16, B, Tm, c1, x32, st));
   {
-    StackBufs w{reinterpret_cast<__half*>(sbase + so_a[0]), reinterpret_cast<__half*>(sbase + so_a[1]),
-                reinterpret_cast<__half*>(sbase + so_a[2]), reinterpret_cast<__half*>(sbase + so_a[3])};
+    StackBufs w = stack_bufs(sbase, so_a);
     FRT2_TRY(run_stack(aco_stack, x32, B, T, w, st));
     FRT2_TRY(ln32(x32, M, aco_stack.E, aco_stack.lnf_g, aco_stack.lnf_b, cat32 + ssl_out, D, cat16 + ssl_out, D, st));
     if (aco_out32 != nullptr)
