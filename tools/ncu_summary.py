@@ -6,7 +6,7 @@ import collections, csv, io, json, subprocess, sys
 
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__shared_mem_per_block_dynamic", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
         "smsp__inst_executed.sum", "sm__cycles_elapsed.avg.per_second"]
@@ -81,7 +81,7 @@ def cmd_full(paths):
                     f"DRAM rd {rd / 1e6 if rd is not None else -1:9.1f} MB wr {wr / 1e6 if wr is not None else -1:9.1f} MB "
                     f"({vals.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', -1):5.1f}% of peak) | "
                     f"tensor pipe {vals.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', -1):5.1f}% | "
-                    f"issue {vals.get('smsp__issue_active.avg.pct', -1):5.1f}% | XU {vals.get('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', -1):5.1f}% | "
+                    f"issue {vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active", -1):5.1f}% | XU {vals.get('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active', -1):5.1f}% | "
                     f"warps {vals.get('sm__warps_active.avg.pct_of_peak_sustained_active', -1):5.1f}% | L2 hit {vals.get('lts__t_sector_hit_rate.pct', -1):5.1f}%")
             print(line)
             out.setdefault(name, []).append({"us": dur_us, "dram_read_bytes": rd, "dram_write_bytes": wr,
