@@ -39,7 +39,6 @@ def audio_bench(a):
     esd = dict(synthetic_encoder_state_dict(cfg, 0))
     esd.update(synthetic_front_state_dict(cfg, 0))
     enc = CodecEncoderB200(cfg, esd, device="cuda:0")
-    del esd
     sd = dict(synthetic_state_dict(C0, 0))
     sd.update(synthetic_encode_tensors(C0, 0, cfg.down_dim))
     codec = RedCodecB200(C0, sd, device="cuda:0", check_indices=False)
@@ -76,6 +75,24 @@ def audio_bench(a):
         pass
     peak = pk.get("bf16_tflops_sustained") or 1400.0
     audio_s = a.batch * 6.0
+    # parity at the full size: chunk 0 against the numpy oracle (log-mel, both encoders, RVQ input), indices from our
+    # features against the oracle's search on the same features
+    from oracle import codec_oracle as O
+    from oracle import encoder_oracle as EO
+    t0 = time.perf_counter()
+    taps = {}
+    a_np = audio[:1].cpu().numpy()
+    ref = EO.encode_audio_features(esd, a_np, cfg, taps=taps)
+    vq1, tp = enc.audio_features(audio[:1], taps=True)
+    got = vq1.cpu().numpy()
+    ref_codes, margin = O.rvq_encode_codes(sd, np.ascontiguousarray(got.transpose(0, 2, 1)))
+    codes1 = codec.rvq_encode_codes(vq1.transpose(1, 2)).cpu().numpy()
+    parity = {"chunk": 0, "log_mel_snr_db": O.snr_db(taps["mel"], tp["mel"].cpu().numpy()),
+              "ssl_encoder_snr_db": O.snr_db(taps["ssl"], tp["ssl"].cpu().numpy()),
+              "acoustic_encoder_snr_db": O.snr_db(taps["aco"], tp["aco"].cpu().numpy()),
+              "vq_in_feats_snr_db": O.snr_db(ref, got), "gate_snr_db": 40.0,
+              "indices_identical_to_oracle_on_gpu_features": float((codes1 == ref_codes).mean()),
+              "oracle_seconds": time.perf_counter() - t0}
     print(json.dumps({
         "workload": f"whole encode path from the waveform: {a.batch} chunks x 6 s @16 kHz = {audio_s:.0f} audio-s per batch; "
                     "log-mel, SSL encoder (whisper-large-v3 size: 32 x 1280, 20 heads), acoustic encoder (12 x 768, 8 heads, "
@@ -84,7 +101,7 @@ def audio_bench(a):
         "launches_features": enc.last_launches, "algorithmic_flops": fl,
         "roofline": {"bound": "tensor", "achieved": fl / (ms_f * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                      "frac": fl / (ms_f * 1e-3) / 1e12 / peak},
-        "load_seconds": load_s, "codes_shape": list(codes.shape)}))
+        "load_seconds": load_s, "codes_shape": list(codes.shape), "parity": parity}))
 
 
 def main():
