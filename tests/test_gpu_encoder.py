@@ -160,3 +160,20 @@ def test_encode_chunks_pads_and_reassembles_like_the_reference():
         assert (tok[i, :, 75 * (-(-n // 96000)):] == 0).all()
     with pytest.raises(ValueError):
         enc.audio_features(torch.zeros(1, 1000).cuda())
+
+
+def test_encoder_head_dim_32_runs_on_the_warp_kernel():
+    """head_dim 32 (embed 128 / 4 heads) is served by the CUDA-core attention kernel (8-query blocks: T % 8 == 0)."""
+    import dataclasses
+    from fireredtts2_b200.encoder import ETINY, synthetic_encoder_state_dict, synthetic_features
+    cfg = dataclasses.replace(ETINY, ssl_num_heads=4)
+    esd = synthetic_encoder_state_dict(cfg, 6)
+    enc = build_encoder(cfg, esd)
+    ssl, aco = synthetic_features(cfg, 2, 40, 4)
+    vq = enc.features(torch.from_numpy(ssl).cuda(), torch.from_numpy(aco).cuda())
+    ref = EO.encode_features(esd, ssl, aco, cfg.ssl_num_heads, cfg.avg_pooler)
+    _, snr = report("hd32 encoder features vs oracle", ref, vq.cpu().numpy())
+    assert snr >= SNR_GATE_DB
+    ssl, aco = synthetic_features(cfg, 1, 44, 4)                  # 44 % 8 != 0
+    with pytest.raises(ValueError):
+        enc.features(torch.from_numpy(ssl).cuda(), torch.from_numpy(aco).cuda())
