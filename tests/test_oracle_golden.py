@@ -307,3 +307,44 @@ def test_mel_filter_bank_and_positions_match_reference_formulas():
     assert (np.diff(peaks) >= 0).all()                # centres ascend
     pos = sinusoids(1500, 1280)
     assert pos.shape == (1500, 1280) and np.allclose(pos[0, :640], 0.0) and np.allclose(pos[0, 640:], 1.0)
+
+
+# ---- frame tail of the speech LM (oracle/frame_decoder_oracle.py; goldens from oracle/make_golden_frame_decoder.py) ----
+FD_CASES = [("fd_tiny", "FD_TINY"), ("fd_small", "FD_SMALL"), ("fd_small_b1", "FD_SMALL"), ("fd_200m", "FD_200M")]
+
+
+def load_fd_case(name, preset):
+    import os
+    from fireredtts2_b200.frame_decoder import FD_PRESETS, synthetic_frame_decoder_state_dict
+    from tests.helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    cfg = FD_PRESETS[preset]
+    B, wseed, dseed, topk = (int(v) for v in g["meta"])
+    return cfg, synthetic_frame_decoder_state_dict(cfg, wseed), g, topk, float(g["temperature"])
+
+
+@pytest.mark.parametrize("name,preset", FD_CASES)
+def test_frame_decoder_oracle_matches_reference_generate_frame(name, preset):
+    """oracle.frame_decoder_oracle.generate_codes against the reference's own Model.generate_frame (llm.py:272-334; Qwen2
+    blocks from Hugging Face transformers behind a torchtune shim): same codes, logits to fp32 summation order."""
+    from oracle import frame_decoder_oracle as FO
+    cfg, sd, g, topk, temperature = load_fd_case(name, preset)
+    codes, logits = FO.generate_codes(sd, cfg, g["last_h"], topk, temperature, g["noise"])
+    assert codes.shape == g["codes"].shape == (g["last_h"].shape[0], cfg.audio_num_codebooks)
+    assert np.array_equal(codes, g["codes"])
+    assert np.abs(logits - g["logits"]).max() < 1e-4 and O.snr_db(g["logits"], logits) > 100.0
+    # teacher forcing reproduces the same logits, and a given c0 skips the codebook-0 head
+    codes_f, logits_f = FO.generate_codes(sd, cfg, g["last_h"], topk, temperature, g["noise"], forced=g["codes"])
+    assert np.array_equal(codes_f, g["codes"]) and np.array_equal(logits_f, logits)
+    codes_c, logits_c = FO.generate_codes(sd, cfg, g["last_h"], topk, temperature, g["noise"], c0=g["codes"][:, 0])
+    assert np.array_equal(codes_c, g["codes"]) and not logits_c[:, 0].any()
+
+
+def test_sample_topk_oracle_edge_cases():
+    """ties at the k-th value stay in the candidate set (llm.py:43 uses `<`), topk = 1 is arg-max, topk = V keeps all."""
+    from oracle import frame_decoder_oracle as FO
+    logits = np.array([[0.0, 3.0, 3.0, 1.0, 3.0, -2.0]], np.float32)
+    q = np.array([[1.0, 9.0, 1.0, 1.0, 0.5, 1e-6]], np.float32)
+    assert FO.sample_topk(logits, 2, 1.0, q)[0] == 4            # three tied maxima survive topk = 2; the smallest q wins
+    assert FO.sample_topk(logits, 1, 0.5, np.ones_like(q))[0] == 1
+    assert FO.sample_topk(logits, 6, 1.0, q)[0] == 5            # nothing filtered: the tiny q of the last entry wins
