@@ -80,6 +80,12 @@ SIGNATURES = {
     "frt2_enc_destroy": (None, [_p]),
     "frt2_enc_features": (_i, [_p, _p, _p, _i, _i, _p, C.POINTER(_i64), _p]),
     "frt2_enc_audio_features": (_i, [_p, _p, _i64, _i, _i64, _p, _p, _p, _p, C.POINTER(_i64), _p]),
+    "frt2_fd_create": (_i, [_p, _i, C.POINTER(_p)]),
+    "frt2_fd_load_tensor": (_i, [_p, C.c_char_p, _p, _i, C.POINTER(_i64), _i]),
+    "frt2_fd_finalize": (_i, [_p]),
+    "frt2_fd_destroy": (None, [_p]),
+    "frt2_fd_generate": (_i, [_p, _p, _i, _p, _p, C.c_uint64, _i, _f, _p, _p, _p, C.POINTER(_i64), _p]),
+    "frt2_fd_check_error": (_i, [_p, _p]),
     "frt2_resample": (_i, [_i, _p, _i64, _i, _i64, _p, _i, _i, _p, _i64, C.POINTER(_i64), _p]),
     "frt2_rvq_gather": (_i, [_p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _p, _p]),
     "frt2_set_debug": (_i, [_p, _i]),
@@ -92,6 +98,7 @@ SIGNATURES = {
     "frt2_op_layer_norm": (_i, [_p, _i, _i, _p, _p, _f, _i, _p, _p]),
     "frt2_op_attention": (_i, [_i, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "frt2_op_attention_trace": (_i, [_p]),
+    "frt2_op_sample_topk": (_i, [_p, _i, _i, _i, _f, _p, C.c_uint64, _p, _p]),
     "frt2_op_overlap_add": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _p]),
     "frt2_last_error": (C.c_char_p, []),
     "frt2_version": (C.c_char_p, []),

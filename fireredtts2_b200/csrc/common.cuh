@@ -75,7 +75,9 @@ constexpr int CTRL_LAST = 1;    // this step is the item's last chunk (iSTFT kee
 constexpr int CTRL_ACTIVE = 2;  // 0: the slot is idle this step — no state update, no output
 
 // ---- GEMM (tcgen05) ----
-enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_POLAR = 2 };
+enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_POLAR = 2,
+                     ACT_SWIGLU = 3 };   // gemm_skinny only: weight rows interleaved (gate_j, up_j); column pair (2j, 2j+1)
+                                         // -> silu(gate) * up stored at column j of out16 (the frame decoder's SwiGLU)
 
 struct GemmDesc {
   // A operand: fp16, logical (batches, rows_a, Kc) with element pitches; K of the GEMM = ntaps*Kc.
@@ -133,6 +135,7 @@ struct GemmDesc {
   const float* ln_beta;
   float ln_eps;
   int ln_silu;
+  int ln_rms;             // 1: RMSNorm (no mean subtraction, no beta: ln_beta may be null) — the frame decoder's norms
 };
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start

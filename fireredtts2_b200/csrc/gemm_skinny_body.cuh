@@ -99,7 +99,7 @@ __device__ __forceinline__ void gemm_skinny_body(const GemmDesc& g, int mtot, in
   if (g.ln_gamma != nullptr) {   // gamma / beta -> shared memory, asynchronously: no round trip inside the LayerNorm
     for (int c = tid * 4; c < g.Kc; c += SK_WARPS * 32 * 4) {
       cp_async16(sGam + c, g.ln_gamma + c, true);
-      cp_async16(sBet + c, g.ln_beta + c, true);
+      cp_async16(sBet + c, g.ln_beta != nullptr ? g.ln_beta + c : g.ln_gamma, g.ln_beta != nullptr);   // RMSNorm: zeros
     }
   }
   if (PDL) {
@@ -171,7 +171,7 @@ __device__ __forceinline__ void gemm_skinny_body(const GemmDesc& g, int mtot, in
             if (lane + 32 * i < C4) s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          const float mean = s / static_cast<float>(g.Kc);
+          const float mean = g.ln_rms ? 0.f : s / static_cast<float>(g.Kc);
           float q = 0.f;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -194,7 +194,7 @@ __device__ __forceinline__ void gemm_skinny_body(const GemmDesc& g, int mtot, in
           }
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          const float mean = s / static_cast<float>(g.Kc);
+          const float mean = g.ln_rms ? 0.f : s / static_cast<float>(g.Kc);
           float q = 0.f;
           for (int c = lane; c < C4; c += 32) {
             const float4 v = xr[c];
@@ -294,6 +294,13 @@ __device__ __forceinline__ void gemm_skinny_body(const GemmDesc& g, int mtot, in
         float sn, cs;
         sincosf(ph, &sn, &cs);
         v = (c & 1) ? mag * sn : mag * cs;
+      } else if (g.act == ACT_SWIGLU) {   // (gate, up) pairs -> silu(gate) * up at column nn / 2 (exact expf: a handful per CTA)
+        if ((c & 1) == 0 && (nn ^ 1) < g.N) {
+          const float up = pre(c ^ 1);
+          g.out16[static_cast<long long>(m / g.rows_out) * g.pitch16 +
+                  static_cast<long long>(m % g.rows_out) * g.ld16 + (nn >> 1)] = to_half_sat(v / (1.0f + expf(-v)) * up);
+        }
+        return;
       }
       const int b = m / g.rows_out, r = m - b * g.rows_out;
       const int roff = ep_roff;

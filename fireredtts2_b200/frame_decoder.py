@@ -192,6 +192,12 @@ class FrameDecoderB200:
                                  audio_num_codebooks=model.config.audio_num_codebooks)
         return cls(cfg, sd, device)
 
+    def check_error(self):
+        """Synchronise and raise IndexError if a given code was outside ``[0, audio_vocab_size)`` since the last check (the
+        reference raises inside ``nn.Embedding``, llm.py:337-338)."""
+        import torch
+        N.check(self._lib.frt2_fd_check_error(self._h, C.c_void_p(torch.cuda.current_stream(self.device_index).cuda_stream)))
+
     def generate_codes(self, last_h, topk: int, temperature: float, c0=None, noise=None, seed: int = 0, forced=None,
                        return_logits: bool = False):
         """last_h ``(B, backbone_dim)`` fp32 = ``h[:, -1, :]`` of the backbone (llm.py:302).  ``c0`` ``(B,)`` int: codebook-0
@@ -235,3 +241,22 @@ class FrameDecoderB200:
                                                C.c_void_p(torch.cuda.current_stream(self.device_index).cuda_stream)))
             self.last_launches = int(cnt.value)
         return (codes, logits) if return_logits else codes
+
+
+def sample_topk(logits, topk: int, temperature: float, noise=None, seed: int = 0):
+    """``sample_topk`` of the reference (llm.py:39-49) on the library: logits ``(B, V)`` fp32 on a CUDA device, ``noise``
+    ``(B, V)`` = the Exp(1) draws (None: the library's generator) -> ``(B,)`` int32."""
+    import torch
+    lib = N.load()
+    logits = logits.to(dtype=torch.float32).contiguous()
+    B, V = logits.shape
+    if noise is not None:
+        noise = noise.to(device=logits.device, dtype=torch.float32).contiguous()
+        assert tuple(noise.shape) == (B, V)
+    with torch.cuda.device(logits.device):
+        codes = torch.empty((B,), dtype=torch.int32, device=logits.device)
+        N.check(lib.frt2_op_sample_topk(C.c_void_p(logits.data_ptr()), B, V, int(topk), C.c_float(temperature),
+                                        C.c_void_p(noise.data_ptr()) if noise is not None else None, C.c_uint64(seed),
+                                        C.c_void_p(codes.data_ptr()),
+                                        C.c_void_p(torch.cuda.current_stream(logits.device).cuda_stream)))
+    return codes

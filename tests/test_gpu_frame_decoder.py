@@ -1,0 +1,133 @@
+"""Frame tail of the speech LM on the library (csrc/frame_decoder.cu through the C ABI) against the oracle and the goldens
+recorded from the reference's own Model.generate_frame (llm.py:272-334)."""
+import numpy as np
+import pytest
+import torch
+
+from fireredtts2_b200.frame_decoder import (FD_PRESETS, FrameDecoderB200, sample_topk, synthetic_frame_decoder_state_dict,
+                                            synthetic_frame_inputs)
+from oracle import codec_oracle as O
+from oracle import frame_decoder_oracle as FO
+from tests.gpu_common import report, to_np
+from tests.test_oracle_golden import FD_CASES, load_fd_case
+
+pytestmark = pytest.mark.gpu
+
+SNR_GATE_DB = 40.0      # fp16 operands / fp32 accumulation against the fp32 reference (north_star tolerance)
+
+_cache = {}
+
+
+def build(preset, wseed):
+    key = (preset, wseed)
+    if key not in _cache:
+        cfg = FD_PRESETS[preset]
+        sd = synthetic_frame_decoder_state_dict(cfg, wseed)
+        _cache.clear()          # one set of full-size weights at a time
+        _cache[key] = (cfg, sd, FrameDecoderB200(cfg, sd))
+    return _cache[key]
+
+
+def cuda(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t.to(dtype) if dtype is not None else t
+
+
+@pytest.mark.parametrize("name,preset", FD_CASES)
+def test_frame_tail_vs_reference_golden(name, preset):
+    """Teacher-forced logits within the SNR gate of the reference's; the free-running frame reproduces the reference's codes
+    from the reference's own Exp(1) draws."""
+    cfg0, _, g, topk, temperature = load_fd_case(name, preset)
+    cfg, sd, fd = build(preset, int(g["meta"][1]))
+    last_h, noise = cuda(g["last_h"]), cuda(g["noise"])
+    codes_f, logits = fd.generate_codes(last_h, topk, temperature, noise=noise, forced=cuda(g["codes"]), return_logits=True)
+    assert np.array_equal(to_np(codes_f).astype(np.int32), g["codes"])
+    _, snr = report(f"{name} teacher-forced logits", g["logits"], to_np(logits))
+    assert snr >= SNR_GATE_DB
+    codes = fd.generate_codes(last_h, topk, temperature, noise=noise)
+    fd.check_error()
+    got = codes.cpu().numpy()
+    same = got == g["codes"]
+    print(f"[parity] {name}: free-running codes equal to the reference's: {int(same.sum())} / {same.size}")
+    assert same.all()
+    assert fd.last_launches == 1 + 1 + cfg.audio_num_codebooks * (2 + 5 * cfg.num_layers) + (cfg.audio_num_codebooks - 1)
+
+
+def test_given_c0_and_batch_independence():
+    """c0 from the caller skips the codebook-0 head (logits row 0 untouched = zeros here); an item's codes and logits do not
+    depend on its neighbours in the batch."""
+    cfg, sd, fd = build("FD_SMALL", 5)
+    last_h, noise = synthetic_frame_inputs(cfg, 4, seed=7)
+    c0 = np.array([3, 500, 17, 0], np.int32)
+    ref_codes, ref_logits = FO.generate_codes(sd, cfg, last_h, 25, 0.85, noise, c0=c0)
+    codes, logits = fd.generate_codes(cuda(last_h), 25, 0.85, c0=cuda(c0), noise=cuda(noise), return_logits=True)
+    assert np.array_equal(codes.cpu().numpy()[:, 0], c0)
+    assert np.array_equal(codes.cpu().numpy(), ref_codes)
+    _, snr = report("FD_SMALL given-c0 logits", ref_logits[:, 1:], to_np(logits)[:, 1:])
+    assert snr >= SNR_GATE_DB
+    for b in (0, 3):
+        cb, lb = fd.generate_codes(cuda(last_h[b:b + 1]), 25, 0.85, c0=cuda(c0[b:b + 1]), noise=cuda(noise[b:b + 1]),
+                                   return_logits=True)
+        assert torch.equal(cb[0], codes[b]) and torch.equal(lb[0, 1:], logits[b, 1:])
+
+
+def test_out_of_range_code_raises_index_error():
+    cfg, sd, fd = build("FD_TINY", 3)
+    last_h, noise = synthetic_frame_inputs(cfg, 2, seed=1)
+    forced = np.zeros((2, cfg.audio_num_codebooks), np.int32)
+    forced[1, 2] = cfg.audio_vocab_size       # nn.Embedding would raise IndexError (llm.py:337-338)
+    fd.generate_codes(cuda(last_h), 5, 1.0, noise=cuda(noise), forced=cuda(forced))
+    with pytest.raises(IndexError):
+        fd.check_error()
+    fd.generate_codes(cuda(last_h), 5, 1.0, noise=cuda(noise))
+    fd.check_error()                           # the word was cleared
+    with pytest.raises(ValueError):
+        fd.generate_codes(cuda(last_h[:, :-8]), 5, 1.0)
+    with pytest.raises(ValueError):
+        fd.generate_codes(cuda(last_h), 0, 1.0)
+
+
+def test_library_generator_is_counter_based():
+    """noise=None: Philox draws keyed by (seed, frame counter): a fresh handle with the same seed repeats the sequence of
+    frames, another seed does not; consecutive frames differ."""
+    cfg = FD_PRESETS["FD_TINY"]
+    sd = synthetic_frame_decoder_state_dict(cfg, 3)
+    last_h, _ = synthetic_frame_inputs(cfg, 2, seed=2)
+    runs = []
+    for seed in (11, 11, 12):
+        fd = FrameDecoderB200(cfg, sd)
+        runs.append(torch.stack([fd.generate_codes(cuda(last_h), cfg.audio_vocab_size, 1.5, seed=seed) for _ in range(6)]).cpu())
+    assert torch.equal(runs[0], runs[1])
+    assert not torch.equal(runs[0], runs[2])
+    assert not torch.equal(runs[0][0], runs[0][1])
+    assert int(runs[0].min()) >= 0 and int(runs[0].max()) < cfg.audio_vocab_size
+
+
+@pytest.mark.parametrize("V,topk,temperature", [(64, 8, 0.9), (2048, 10, 0.75), (2048, 30, 0.9), (2051, 50, 1.0), (512, 512, 1.3),
+                                                (2048, 1, 0.5)])
+def test_sample_topk_matches_oracle(V, topk, temperature):
+    """Index work: identical to the restated llm.py:33-49 on the same logits and draws, duplicates at the k-th value included."""
+    rng = np.random.default_rng(V + topk)
+    B = 64
+    logits = (2.0 * rng.standard_normal((B, V))).astype(np.float32)
+    logits[: B // 2] = np.round(logits[: B // 2] * 2) / 2          # many exact ties, also at the k-th value
+    noise = np.maximum(rng.exponential(1.0, (B, V)), 1e-30).astype(np.float32)
+    ref = FO.sample_topk(logits, topk, temperature, noise)
+    got = sample_topk(cuda(logits), topk, temperature, cuda(noise)).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+def test_sample_topk_library_draws_follow_the_distribution():
+    """noise=None: the sampled frequencies follow softmax(logits / T) restricted to the top k (chi-square-like bound)."""
+    V, topk, T, B = 64, 8, 0.8, 20000
+    rng = np.random.default_rng(5)
+    row = (1.5 * rng.standard_normal(V)).astype(np.float32)
+    logits = np.tile(row, (B, 1))
+    got = sample_topk(cuda(logits), topk, T, None, seed=99).cpu().numpy()
+    s = row / np.float32(T)
+    keep = s >= np.sort(s)[::-1][topk - 1]
+    p = np.where(keep, np.exp(s - s.max()), 0.0)
+    p /= p.sum()
+    freq = np.bincount(got, minlength=V) / B
+    assert freq[~keep].sum() == 0.0
+    assert np.abs(freq - p).max() < 4.0 * np.sqrt(0.25 / B)
