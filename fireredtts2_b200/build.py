@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfrt2_b200.so")
-SOURCES = ["engine.cu", "gemm_tc.cu", "gemm_skinny.cu", "attention.cu", "kernels_misc.cu", "rvq_encode.cu", "rvq_encode_tc.cu", "stream_state.cu", "encoder.cu", "frame_decoder.cu"]
+SOURCES = ["engine.cu", "gemm_tc.cu", "gemm_skinny.cu", "attention.cu", "kernels_misc.cu", "rvq_encode.cu", "rvq_encode_tc.cu", "stream_state.cu", "encoder.cu", "frame_decoder.cu", "gemm_stream.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC,-fopenmp,-O2", "--expt-relaxed-constexpr"]

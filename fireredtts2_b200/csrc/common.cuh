@@ -151,6 +151,30 @@ int gemm_skinny(const GemmDesc& g, cudaStream_t stream); // <= 16 rows in total:
 bool gemm_skinny_applicable(const GemmDesc& g);
 int gemm_skinny_init();
 
+// ---- persistent weight-streaming GEMM for <= 8 rows (gemm_stream.cu; the frame tail of the speech LM) ----
+struct StreamGemm {
+  const __half* Wt;       // weights in tile-blocked order [ceil(N/8)][K/32][8][32] (gemm_stream_pack_host)
+  int N, K, B;            // K a multiple of 32; B <= 8 rows
+  const __half* A;        // fp16 rows (B, K), pitch lda — or, when gamma != null, the rows are RMSNorm(x) * gamma:
+  int64_t lda;
+  const float* x;         // fp32 rows (B, K), pitch ldx
+  int64_t ldx;
+  const float* gamma;     // (K)
+  float eps;
+  const float* bias;      // (N) or null
+  int act;                // ACT_NONE / ACT_GELU / ACT_SWIGLU (interleaved gate/up rows -> out16 column n/2)
+  const float* resid;     // fp32 (B, ld32), may alias out32
+  float* out32;
+  int64_t ld32;
+  __half* out16;
+  int64_t ld16;
+};
+int gemm_stream(const StreamGemm& d, cudaStream_t stream);
+int gemm_stream_init();
+bool gemm_stream_applicable(int N, int K, int B);
+size_t gemm_stream_packed_elems(int64_t N, int64_t K);
+void gemm_stream_pack_host(const float* W, int64_t N, int64_t K, __half* out);
+
 // ---- attention ----
 struct AttnDesc {
   const __half* q;   // (B, Tq, *) rows, head h at column h*hd

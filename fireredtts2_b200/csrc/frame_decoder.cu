@@ -21,6 +21,7 @@
 // codes stay on the device (they are the token operand of frt2_decode_chunk).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -33,7 +34,7 @@ namespace frt2 {
 namespace {
 
 constexpr int FD_MAX_BATCH = 8;
-constexpr int FD_MAX_POS = 64;        // audio_num_codebooks limit (scores of one head live in registers)
+constexpr int FD_MAX_POS = 64;        // audio_num_codebooks limit (lane t of the attention warp owns positions t and t + 32)
 constexpr int FD_SAMPLE_THREADS = 256;
 
 // run-time parameters of a frame, written by fd_begin_kernel, read by the captured kernels
@@ -59,11 +60,16 @@ __global__ void fd_begin_kernel(const float* __restrict__ last_h, int B, int Db,
 // One position of one layer: rotary embedding of q and the new k, K/V append, attention over positions 0..pos.
 // grid (Hk, B); one warp per query head of the kv group.  qkv: (B, (H + 2 Hk) hd) fp32 = [q | k | v] with bias.
 // kc / vc: this layer's (B, npos, Hk, hd) fp32 state.  Scores are 1/sqrt(hd)-scaled dot products, softmax in fp32.
-template <int PAIRS>   // pairs (i, i + hd/2) per lane: hd <= 64 * PAIRS
+// Latency is all that matters here (a few KB of state between two weight streams): lane t owns position t — every lane
+// reads ITS key row in one batch of independent 16-byte loads (one round trip for all positions), the softmax is a pair
+// of warp reductions, and the value rows are read coalesced (lane = channel) with the weights broadcast by shuffles.
 __global__ void __launch_bounds__(256) fd_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kc,
                                                       float* __restrict__ vc, __half* __restrict__ out16,
                                                       const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
                                                       int H, int Hk, int hd, int npos, int pos, float scale) {
+  __shared__ __align__(16) float s_q[8][128];       // rotated query of each warp's head
+  __shared__ __align__(16) float s_k[8][128];       // rotated new key / new value (one copy per warp: no CTA barrier)
+  __shared__ __align__(16) float s_v[8][128];
   const int kvh = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rep = H / Hk, half = hd >> 1;
@@ -75,79 +81,69 @@ __global__ void __launch_bounds__(256) fd_attn_kernel(const float* __restrict__ 
   const long long row = static_cast<long long>(Hk) * hd;                      // one position of one item
   float* kcb = kc + (static_cast<long long>(b) * npos) * row + kvh * hd;
   float* vcb = vc + (static_cast<long long>(b) * npos) * row + kvh * hd;
-  float q1[PAIRS], q2[PAIRS], k1[PAIRS], k2[PAIRS], v1[PAIRS], v2[PAIRS];
-#pragma unroll
-  for (int j = 0; j < PAIRS; ++j) {
-    const int i = lane + 32 * j;
-    q1[j] = q2[j] = k1[j] = k2[j] = v1[j] = v2[j] = 0.f;
-    if (i < half) {
-      const float c = rope_cos[pos * half + i], s = rope_sin[pos * half + i];
-      const float a = qr[i], bq = qr[i + half];
-      q1[j] = a * c - bq * s;
-      q2[j] = bq * c + a * s;
-      const float ka = kr[i], kb = kr[i + half];
-      k1[j] = ka * c - kb * s;
-      k2[j] = kb * c + ka * s;
-      v1[j] = vr[i];
-      v2[j] = vr[i + half];
-      if (warp == 0) {
-        kcb[pos * row + i] = k1[j];
-        kcb[pos * row + i + half] = k2[j];
-        vcb[pos * row + i] = v1[j];
-        vcb[pos * row + i + half] = v2[j];
-      }
+  // the other positions' key rows do not depend on this kernel's input: request them first
+  const int t0 = lane, t1 = lane + 32;
+  const int nv4 = hd >> 2;
+  for (int i = lane; i < half; i += 32) {
+    const float c = rope_cos[pos * half + i], s = rope_sin[pos * half + i];
+    const float a = qr[i], bq = qr[i + half];
+    s_q[warp][i] = a * c - bq * s;
+    s_q[warp][i + half] = bq * c + a * s;
+    const float ka = kr[i], kb = kr[i + half];
+    const float k1 = ka * c - kb * s, k2 = kb * c + ka * s;
+    const float v1 = vr[i], v2 = vr[i + half];
+    s_k[warp][i] = k1;
+    s_k[warp][i + half] = k2;
+    s_v[warp][i] = v1;
+    s_v[warp][i + half] = v2;
+    if (warp == 0) {
+      kcb[pos * row + i] = k1;
+      kcb[pos * row + i + half] = k2;
+      vcb[pos * row + i] = v1;
+      vcb[pos * row + i + half] = v2;
     }
   }
-  float sc[FD_MAX_POS];
-  float mx = -INFINITY;
-#pragma unroll 1
-  for (int t = 0; t <= pos; ++t) {
-    float part = 0.f;
-#pragma unroll
-    for (int j = 0; j < PAIRS; ++j) {
-      const int i = lane + 32 * j;
-      if (i < half) {
-        const float a = (t == pos) ? k1[j] : kcb[t * row + i];
-        const float bb = (t == pos) ? k2[j] : kcb[t * row + i + half];
-        part += q1[j] * a + q2[j] * bb;
-      }
+  __syncwarp();
+  auto score = [&](int t) -> float {
+    if (t > pos) return -INFINITY;
+    const float4* kp = t == pos ? reinterpret_cast<const float4*>(s_k[warp]) : reinterpret_cast<const float4*>(kcb + t * row);
+    const float4* qp = reinterpret_cast<const float4*>(s_q[warp]);
+    float acc = 0.f;
+#pragma unroll 8
+    for (int i = 0; i < nv4; ++i) {
+      const float4 kv = kp[i], qv = qp[i];
+      acc += (kv.x * qv.x + kv.y * qv.y) + (kv.z * qv.z + kv.w * qv.w);
     }
+    return acc * scale;
+  };
+  float sc0 = score(t0), sc1 = pos >= 32 ? score(t1) : -INFINITY;
+  float mx = fmaxf(sc0, sc1);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    part *= scale;
-    // the scores of <= FD_MAX_POS positions stay in registers only when the loop is unrolled; a local array indexed by a
-    // run-time t lives in local memory (L1) — 16 floats per lane, irrelevant next to the weight streams around this kernel
-    sc[t] = part;
-    mx = fmaxf(mx, part);
-  }
-  float den = 0.f;
-  for (int t = 0; t <= pos; ++t) {
-    sc[t] = expf(sc[t] - mx);
-    den += sc[t];
-  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  sc0 = t0 <= pos ? expf(sc0 - mx) : 0.f;
+  sc1 = t1 <= pos ? expf(sc1 - mx) : 0.f;
+  float den = sc0 + sc1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
   const float inv = 1.0f / den;
-  float o1[PAIRS], o2[PAIRS];
-#pragma unroll
-  for (int j = 0; j < PAIRS; ++j) o1[j] = o2[j] = 0.f;
+  sc0 *= inv;
+  sc1 *= inv;
+  float o_acc[4] = {0.f, 0.f, 0.f, 0.f};              // channels lane, lane + 32, lane + 64, lane + 96
+#pragma unroll 4
   for (int t = 0; t <= pos; ++t) {
-    const float a = sc[t] * inv;
+    const float a = __shfl_sync(0xffffffffu, t < 32 ? sc0 : sc1, t & 31);
+    const float* vp = t == pos ? s_v[warp] : vcb + t * row;
 #pragma unroll
-    for (int j = 0; j < PAIRS; ++j) {
-      const int i = lane + 32 * j;
-      if (i < half) {
-        o1[j] += a * ((t == pos) ? v1[j] : vcb[t * row + i]);
-        o2[j] += a * ((t == pos) ? v2[j] : vcb[t * row + i + half]);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const int dch = lane + 32 * j;
+      if (dch < hd) o_acc[j] += a * vp[dch];
     }
   }
   __half* orow = out16 + static_cast<long long>(b) * H * hd + h * hd;
 #pragma unroll
-  for (int j = 0; j < PAIRS; ++j) {
-    const int i = lane + 32 * j;
-    if (i < half) {
-      orow[i] = to_half_sat(o1[j]);
-      orow[i + half] = to_half_sat(o2[j]);
-    }
+  for (int j = 0; j < 4; ++j) {
+    const int dch = lane + 32 * j;
+    if (dch < hd) orow[dch] = to_half_sat(o_acc[j]);
   }
 }
 
@@ -315,6 +311,7 @@ struct FrameDecoder {
   std::mutex mu;
   std::map<std::string, HostT> raw;
   bool finalized = false;
+  bool use_stream = true;        // gemm_stream (tile-blocked weights) for every GEMM; false: gemm_skinny (A/B, odd widths)
   frt2_fd_config cfg{};
   int hd = 0, qkv = 0;
   std::vector<void*> owned;
@@ -322,6 +319,7 @@ struct FrameDecoder {
   __half* w_proj = nullptr;      // (D, Db)
   __half* w_head0 = nullptr;     // (V, Db)
   __half* w_heads = nullptr;     // (ncb - 1, V, D): audio_head[i] transposed (K contiguous)
+  size_t head_stride = 0;        // elements between two heads
   __half* emb16 = nullptr;       // (ncb * V, Db)
   float* g_final = nullptr;
   float *rope_cos = nullptr, *rope_sin = nullptr;     // (ncb, hd / 2)
@@ -370,6 +368,15 @@ struct FrameDecoder {
     FRT2_CUDA_OK(cudaMemcpy(*out, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice));
     return FRT2_OK;
   }
+  // GEMM weight (N, K) fp32 -> fp16 in the layout of the kernel that will stream it
+  int up_w(const float* w, int64_t N, int64_t K, __half** out) {
+    if (!use_stream) return up16(std::vector<float>(w, w + N * K), out);
+    std::vector<__half> packed(gemm_stream_packed_elems(N, K));
+    gemm_stream_pack_host(w, N, K, packed.data());
+    FRT2_TRY(dev_alloc(out, packed.size()));
+    FRT2_CUDA_OK(cudaMemcpy(*out, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice));
+    return FRT2_OK;
+  }
   int need(const std::string& key, const HostT** out, std::initializer_list<int64_t> shape) {
     auto it = raw.find(key);
     if (it == raw.end()) {
@@ -396,13 +403,16 @@ struct FrameDecoder {
 int FrameDecoder::finalize() {
   FRT2_CUDA_OK(cudaSetDevice(device));
   FRT2_TRY(gemm_skinny_init());
+  FRT2_TRY(gemm_stream_init());
+  use_stream = getenv("FRT2_FD_SKINNY") == nullptr && gemm_stream_applicable(8, cfg.dim, 8) &&
+               gemm_stream_applicable(8, cfg.backbone_dim, 8) && gemm_stream_applicable(8, cfg.intermediate_dim, 8);
   const int D = cfg.dim, Db = cfg.backbone_dim, I = cfg.intermediate_dim, V = cfg.audio_vocab_size, n = cfg.audio_num_codebooks;
   const int H = cfg.num_heads, Hk = cfg.num_kv_heads;
   const HostT* t = nullptr;
   FRT2_TRY(need("projection.weight", &t, {D, Db}));
-  FRT2_TRY(up16(t->data, &w_proj));
+  FRT2_TRY(up_w(t->data.data(), D, Db, &w_proj));
   FRT2_TRY(need("codebook0_head.weight", &t, {V, Db}));
-  FRT2_TRY(up16(t->data, &w_head0));
+  FRT2_TRY(up_w(t->data.data(), V, Db, &w_head0));
   FRT2_TRY(need("audio_embeddings.weight", &t, {static_cast<int64_t>(V) * n, Db}));
   FRT2_TRY(up16(t->data, &emb16));
   FRT2_TRY(need("audio_head", &t, {n - 1, D, V}));
@@ -415,7 +425,17 @@ int FrameDecoder::finalize() {
       for (int v = 0; v < V; ++v)
         for (int d = 0; d < D; ++d) dst[static_cast<size_t>(v) * D + d] = src[static_cast<size_t>(d) * V + v];
     }
-    FRT2_TRY(up16(tr, &w_heads));
+    head_stride = use_stream ? gemm_stream_packed_elems(V, D) : static_cast<size_t>(V) * D;
+    std::vector<__half> all(head_stride * (n - 1));
+    FRT2_TRY(dev_alloc(&w_heads, all.size()));
+    for (int i = 0; i < n - 1; ++i) {
+      __half* one = nullptr;   // packed / converted one head at a time, copied into the common buffer
+      const size_t mark = owned.size();
+      FRT2_TRY(up_w(tr.data() + static_cast<size_t>(i) * D * V, V, D, &one));
+      FRT2_CUDA_OK(cudaMemcpy(w_heads + head_stride * i, one, head_stride * 2, cudaMemcpyDeviceToDevice));
+      cudaFree(one);
+      owned.resize(mark);
+    }
   }
   FRT2_TRY(need("decoder.norm.scale", &t, {D}));
   FRT2_TRY(up32(t->data.data(), D, &g_final));
@@ -437,10 +457,10 @@ int FrameDecoder::finalize() {
     std::copy(bq->data.begin(), bq->data.end(), bias.begin());
     std::copy(bk->data.begin(), bk->data.end(), bias.begin() + H * hd);
     std::copy(bv->data.begin(), bv->data.end(), bias.begin() + (H + Hk) * hd);
-    FRT2_TRY(up16(w, &L.w_qkv));
+    FRT2_TRY(up_w(w.data(), qkv, D, &L.w_qkv));
     FRT2_TRY(up32(bias.data(), bias.size(), &L.b_qkv));
     FRT2_TRY(need(p + "attn.output_proj.weight", &t, {D, H * hd}));
-    FRT2_TRY(up16(t->data, &L.w_o));
+    FRT2_TRY(up_w(t->data.data(), D, H * hd, &L.w_o));
     FRT2_TRY(need(p + "mlp.w1.weight", &w1, {I, D}));
     FRT2_TRY(need(p + "mlp.w3.weight", &w3, {I, D}));
     std::vector<float> gu(static_cast<size_t>(2) * I * D);
@@ -449,9 +469,9 @@ int FrameDecoder::finalize() {
       std::memcpy(gu.data() + static_cast<size_t>(2 * j) * D, w1->data.data() + static_cast<size_t>(j) * D, D * 4);
       std::memcpy(gu.data() + static_cast<size_t>(2 * j + 1) * D, w3->data.data() + static_cast<size_t>(j) * D, D * 4);
     }
-    FRT2_TRY(up16(gu, &L.w_gu));
+    FRT2_TRY(up_w(gu.data(), 2 * I, D, &L.w_gu));
     FRT2_TRY(need(p + "mlp.w2.weight", &t, {D, I}));
-    FRT2_TRY(up16(t->data, &L.w_down));
+    FRT2_TRY(up_w(t->data.data(), D, I, &L.w_down));
     FRT2_TRY(need(p + "sa_norm.scale", &t, {D}));
     FRT2_TRY(up32(t->data.data(), D, &L.g_sa));
     FRT2_TRY(need(p + "mlp_norm.scale", &t, {D}));
@@ -494,6 +514,13 @@ int FrameDecoder::finalize() {
 int FrameDecoder::skinny(const __half* A, int K, const __half* W, int N, const float* bias, int act, const float* resid,
                          float* out32, int64_t ld32, __half* out16, int64_t ld16, const float* ln_x,
                          const float* ln_gamma, int B, cudaStream_t st) {
+  ++launches;
+  if (use_stream) {
+    StreamGemm d{};
+    d.Wt = W; d.N = N; d.K = K; d.B = B; d.A = A; d.lda = K; d.x = ln_x; d.ldx = K; d.gamma = ln_gamma; d.eps = cfg.norm_eps;
+    d.bias = bias; d.act = act; d.resid = resid; d.out32 = out32; d.ld32 = ld32; d.out16 = out16; d.ld16 = ld16;
+    return gemm_stream(d, st);
+  }
   GemmDesc g{};
   g.A = A; g.a_row_pitch = K; g.a_batch_pitch = 0; g.rows_a = B; g.batches = 1; g.Kc = K; g.ntaps = 1; g.row_shift = 0;
   g.W = W; g.N = N; g.rows_out = B; g.alpha = 1.0f; g.bias = bias; g.act = act; g.resid = resid; g.out32 = out32;
@@ -501,7 +528,6 @@ int FrameDecoder::skinny(const __half* A, int K, const __half* W, int N, const f
   if (ln_gamma != nullptr) {
     g.ln_x = ln_x; g.ln_ldx = K; g.ln_gamma = ln_gamma; g.ln_beta = nullptr; g.ln_eps = cfg.norm_eps; g.ln_rms = 1;
   }
-  ++launches;
   return gemm_skinny(g, st);
 }
 
@@ -527,10 +553,7 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
       FRT2_TRY(skinny(nullptr, D, L.w_qkv, qkv, L.b_qkv, ACT_NONE, nullptr, qkv32, qkv, nullptr, 0, x32, L.g_sa, B, st));
       const dim3 grid(Hk, B);
       const int threads = 32 * (H / Hk);
-      if (hd <= 64)
-        fd_attn_kernel<1><<<grid, threads, 0, st>>>(qkv32, L.kc, L.vc, attn16, rope_cos, rope_sin, H, Hk, hd, n, pos, scale);
-      else
-        fd_attn_kernel<2><<<grid, threads, 0, st>>>(qkv32, L.kc, L.vc, attn16, rope_cos, rope_sin, H, Hk, hd, n, pos, scale);
+      fd_attn_kernel<<<grid, threads, 0, st>>>(qkv32, L.kc, L.vc, attn16, rope_cos, rope_sin, H, Hk, hd, n, pos, scale);
       FRT2_CUDA_OK(cudaGetLastError());
       ++launches;
       FRT2_TRY(skinny(attn16, H * hd, L.w_o, D, nullptr, ACT_NONE, x32, x32, D, nullptr, 0, nullptr, nullptr, B, st));
@@ -538,7 +561,7 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
       FRT2_TRY(skinny(h16, I, L.w_down, D, nullptr, ACT_NONE, x32, x32, D, nullptr, 0, nullptr, nullptr, B, st));
     }
     if (pos >= 1) {   // llm.py:322-326: final norm (inside the head GEMM), audio_head[pos-1], sampler, next embedding
-      FRT2_TRY(skinny(nullptr, D, w_heads + static_cast<size_t>(pos - 1) * V * D, V, nullptr, ACT_NONE, nullptr,
+      FRT2_TRY(skinny(nullptr, D, w_heads + head_stride * (pos - 1), V, nullptr, ACT_NONE, nullptr,
                       logits + static_cast<size_t>(pos) * V, ldl, nullptr, 0, x32, g_final, B, st));
       FRT2_CUDA_OK(sample(pos));
     }
@@ -588,7 +611,7 @@ int frt2_fd_create(const frt2_fd_config* cfg, int device, frt2_frame_decoder** o
                    cfg->num_heads % cfg->num_kv_heads == 0 && cfg->num_heads / cfg->num_kv_heads <= 8,
                FRT2_ERR_BAD_ARG, "frt2_fd_create: heads must divide dim, kv heads must divide heads (<= 8 per group)");
   const int hd = cfg->dim / cfg->num_heads;
-  FRT2_REQUIRE(hd % 2 == 0 && hd <= 128, FRT2_ERR_BAD_ARG, "frt2_fd_create: head_dim must be even and <= 128");
+  FRT2_REQUIRE(hd % 4 == 0 && hd <= 128, FRT2_ERR_BAD_ARG, "frt2_fd_create: head_dim must be a multiple of 4 and <= 128");
   FRT2_REQUIRE(cfg->audio_vocab_size > 0 && cfg->audio_vocab_size <= 24000 && cfg->audio_num_codebooks >= 2 &&
                    cfg->audio_num_codebooks <= FD_MAX_POS,
                FRT2_ERR_BAD_ARG, "frt2_fd_create: audio_vocab_size in [1, 24000], audio_num_codebooks in [2, 64]");
