@@ -615,6 +615,11 @@ def run_ours(args):
             out["encode"] = encode_record(dev)
         except Exception as e:      # noqa: BLE001 — an extra record must never cost the bench line
             out["encode"] = {"unavailable": repr(e)}
+        try:
+            torch.cuda.empty_cache()
+            out["frame_tail"] = frame_tail_record(dev)
+        except Exception as e:      # noqa: BLE001
+            out["frame_tail"] = {"unavailable": repr(e)}
     if world > 1:
         out["gather"] = {"mode": gather_mode, "bytes_into_rank0_per_step": int((world - 1) * B * n_samples * 4),
                          "check": gathered_ok,
@@ -794,6 +799,56 @@ def encode_record(dev, batch=96, frames=300, reps=5):
                          "frac": fl / (ms_f * 1e-3) / 1e12 / peak if peak else None, "kernel": "frt2_enc_features (gemm_tc + attention_t4)"},
             "parity": {"vq_in_feats_snr_db_vs_oracle": O.snr_db(ref, got), "gate_snr_db": 40.0,
                        "indices_identical_to_oracle_on_gpu_features": float((codes[:, 0].cpu().numpy() == ref_codes[:, 0]).mean())}}
+
+
+def frame_tail_record(dev, frames=40):
+    """SURVEY 8f.4 sub-record: the frame tail of the speech LM (llm.py:303-334 — codebook-0 head, 16 dependent passes of
+    the qwen-200m "decoder", samplers, embeddings) as one CUDA graph per frame (frt2_fd_generate), batch 1 and 8; HBM
+    roofline = the fp16 weights one frame streams; parity of one FD_200M frame (teacher-forced logits, free-running
+    codes) against the numpy oracle on the box, which is also the CPU baseline (one frame, all host cores through BLAS)."""
+    import torch
+    from fireredtts2_b200.frame_decoder import (FD_200M, FrameDecoderB200, synthetic_frame_decoder_state_dict,
+                                                synthetic_frame_inputs)
+    from oracle import codec_oracle as O
+    from oracle import frame_decoder_oracle as FO
+    cfg = FD_200M
+    sd = synthetic_frame_decoder_state_dict(cfg, 0)
+    fd = FrameDecoderB200(cfg, sd, device=str(dev))
+    pk, _ = peaks()
+    rec = {"workload": "frame tail of Model.generate_frame (llm.py:303-334): qwen-1.5b-wide backbone state -> 16 codes; "
+                       "decoder flavor qwen-200m (4 x 1536, 12 / 2 heads, 8960), V = 2048, random weights; topk 30, T 0.9",
+           "weight_bytes_per_frame": cfg.weight_bytes_per_frame()}
+    for B in (1, 8):
+        last_h, _ = synthetic_frame_inputs(cfg, B, 0)
+        h = torch.from_numpy(last_h).to(dev)
+        for _ in range(5):
+            fd.generate_codes(h, 30, 0.9, seed=1)
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(frames + 1)]
+        ev[0].record()
+        for i in range(frames):
+            fd.generate_codes(h, 30, 0.9, seed=1)
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        ms = statistics.median(ev[i].elapsed_time(ev[i + 1]) for i in range(frames))
+        gbs = cfg.weight_bytes_per_frame() / (ms * 1e-3) / 1e9
+        rec[f"batch{B}"] = {"ms_per_frame": ms, "frames_per_s": B * 1e3 / ms, "x_realtime_per_stream": 80.0 / ms,
+                            "launches_per_frame": fd.last_launches,
+                            "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk.get("hbm_gbs"), "unit": "GB/s",
+                                         "frac": gbs / pk["hbm_gbs"] if pk.get("hbm_gbs") else None,
+                                         "kernel": "gemm_stream_kernel (fp16 weights streamed once per decoder position)"}}
+    last_h, noise = synthetic_frame_inputs(cfg, 1, 3)
+    t0 = time.perf_counter()
+    ref_codes, ref_logits = FO.generate_codes(sd, cfg, last_h, 30, 0.9, noise)
+    cpu_s = time.perf_counter() - t0
+    h, nz = torch.from_numpy(last_h).to(dev), torch.from_numpy(noise).to(dev)
+    _, logits = fd.generate_codes(h, 30, 0.9, noise=nz, forced=torch.from_numpy(ref_codes).to(dev), return_logits=True)
+    codes = fd.generate_codes(h, 30, 0.9, noise=nz).cpu().numpy()
+    rec["parity"] = {"teacher_forced_logits_snr_db_vs_oracle": O.snr_db(ref_logits, logits.cpu().numpy()), "gate_snr_db": 40.0,
+                     "free_running_codes_identical_to_oracle": float((codes == ref_codes).mean())}
+    rec["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                           "sample": "one FD_200M frame (16 positions) by oracle/frame_decoder_oracle.py (numpy fp32, BLAS threads)"}
+    return rec
 
 
 def llm_overlap(codec, cfg, dev, frames=96, producer_ms=(4.0, 12.0)):

@@ -537,6 +537,8 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
   const int H = cfg.num_heads, Hk = cfg.num_kv_heads;
   const float scale = 1.0f / std::sqrt(static_cast<float>(hd));
   const int64_t ldl = static_cast<int64_t>(n) * V;
+  // timing experiments only (results are wrong with any bit set): marginal cost of a kernel class inside the graph
+  static const int skip = getenv("FRT2_FD_SKIP") != nullptr ? atoi(getenv("FRT2_FD_SKIP")) : 0;
   auto sample = [&](int s) {
     fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, s, V, n, params, given, codes, emb16, Db, in16,
                                                                 err_word);
@@ -550,17 +552,23 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
     FRT2_TRY(skinny(in16, Db, w_proj, D, nullptr, ACT_NONE, nullptr, x32, D, nullptr, 0, nullptr, nullptr, B, st));
     if (pos == 0) FRT2_CUDA_OK(sample(0));   // c0 and its embedding: in16 is free once the projection has read it
     for (FdLayer& L : layers) {
-      FRT2_TRY(skinny(nullptr, D, L.w_qkv, qkv, L.b_qkv, ACT_NONE, nullptr, qkv32, qkv, nullptr, 0, x32, L.g_sa, B, st));
+      if (!(skip & 8))
+        FRT2_TRY(skinny(nullptr, D, L.w_qkv, qkv, L.b_qkv, ACT_NONE, nullptr, qkv32, qkv, nullptr, 0, x32, L.g_sa, B, st));
       const dim3 grid(Hk, B);
       const int threads = 32 * (H / Hk);
-      fd_attn_kernel<<<grid, threads, 0, st>>>(qkv32, L.kc, L.vc, attn16, rope_cos, rope_sin, H, Hk, hd, n, pos, scale);
-      FRT2_CUDA_OK(cudaGetLastError());
-      ++launches;
-      FRT2_TRY(skinny(attn16, H * hd, L.w_o, D, nullptr, ACT_NONE, x32, x32, D, nullptr, 0, nullptr, nullptr, B, st));
-      FRT2_TRY(skinny(nullptr, D, L.w_gu, 2 * I, nullptr, ACT_SWIGLU, nullptr, nullptr, 0, h16, I, x32, L.g_mlp, B, st));
-      FRT2_TRY(skinny(h16, I, L.w_down, D, nullptr, ACT_NONE, x32, x32, D, nullptr, 0, nullptr, nullptr, B, st));
+      if (!(skip & 1)) {
+        fd_attn_kernel<<<grid, threads, 0, st>>>(qkv32, L.kc, L.vc, attn16, rope_cos, rope_sin, H, Hk, hd, n, pos, scale);
+        FRT2_CUDA_OK(cudaGetLastError());
+        ++launches;
+      }
+      if (!(skip & 16))
+        FRT2_TRY(skinny(attn16, H * hd, L.w_o, D, nullptr, ACT_NONE, x32, x32, D, nullptr, 0, nullptr, nullptr, B, st));
+      if (!(skip & 2))
+        FRT2_TRY(skinny(nullptr, D, L.w_gu, 2 * I, nullptr, ACT_SWIGLU, nullptr, nullptr, 0, h16, I, x32, L.g_mlp, B, st));
+      if (!(skip & 4))
+        FRT2_TRY(skinny(h16, I, L.w_down, D, nullptr, ACT_NONE, x32, x32, D, nullptr, 0, nullptr, nullptr, B, st));
     }
-    if (pos >= 1) {   // llm.py:322-326: final norm (inside the head GEMM), audio_head[pos-1], sampler, next embedding
+    if (pos >= 1 && !(skip & 32)) {   // llm.py:322-326: final norm (inside the head GEMM), audio_head[pos-1], sampler, next embedding
       FRT2_TRY(skinny(nullptr, D, w_heads + head_stride * (pos - 1), V, nullptr, ACT_NONE, nullptr,
                       logits + static_cast<size_t>(pos) * V, ldl, nullptr, 0, x32, g_final, B, st));
       FRT2_CUDA_OK(sample(pos));

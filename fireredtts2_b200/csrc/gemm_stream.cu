@@ -2,20 +2,22 @@
 //
 // out[m, n] = act(sum_k A[m, k] W[n, k] + bias[n]) (+ resid), m < B <= 8.  Every weight byte is used once, so the kernel is
 // an HBM stream with a little arithmetic attached.  Against gemm_skinny (one CTA per 8..32 columns, load -> wait -> MMA ->
-// reduce -> store per CTA; 164 registers, one CTA per SM and 3.8 waves on the 17920-column gate|up layer: 1.8 TB/s) it
-// changes three things:
-//   * ONE CTA per SM for the whole launch.  The activation rows are staged (and RMS-normalised) once per CTA, not once
-//     per column tile.
+// reduce -> store per CTA; 164 registers, one CTA per SM and 3.8 waves on the 17920-column gate|up layer: 1.8 TB/s):
+//   * ONE CTA of 16 warps per SM for the whole launch.  The activation rows are staged (and RMS-normalised) once per CTA,
+//     not once per column tile.
 //   * Weights are repacked at load into the order the warps consume them: tile-blocked [N/8][K/32][8 columns][32 k], so
-//     the 16-byte vector of lane (g, t) = W[8j+g][32b+8t..] sits at lane*16 bytes of a 512-byte block: every warp load is
-//     four full 128-byte lines, and a warp's whole job is ONE contiguous byte range.
-//   * Every warp keeps a RING of RING 16-byte vectors in flight and refills a slot the moment it is consumed: the stream
-//     never drains at tile boundaries, reductions or epilogues (8 warps x 16 x 512 B = 64 KB in flight per SM).
-// Work split: WIDE layers (tiles >= warps of the grid: gate|up) — a warp owns whole column tiles (all of K): no
-// reduction, the epilogue runs from the MMA accumulators.  NARROW layers (q|k|v, output / down projection, heads) — a CTA
-// owns column tiles round-robin and its 8 warps split K; partial sums meet in shared memory (fixed order: deterministic),
-// double-buffered so that one barrier per tile suffices.  Products on mma.sync.m16n8k16 (rows 8..15 unused) with the
-// k-permutation of gemm_skinny (a dot product does not care about the order of k inside a 32-block).
+//     the 16-byte vector of lane (g, t) = W[8j+g][32b+8t..] sits at lane*16 bytes of a 512-byte block: every warp request
+//     is four full 128-byte lines.
+//   * A CTA owns column tiles round-robin (tile j -> CTA j mod grid) and its 16 warps split the tile's K, so at any moment
+//     the whole GPU reads one compact window of the weight matrix; partial sums meet in shared memory (fixed order:
+//     deterministic), double-buffered so that one barrier per tile suffices.  (A layer with more tiles than warps in the
+//     grid lets every warp stream whole tiles instead: no reduction.)
+//   * Every lane keeps a RING of 8 16-byte vectors in flight in registers and refills a slot the moment it is consumed:
+//     the stream never drains at tile boundaries, reductions or epilogues (16 warps x 8 x 512 B = 64 KB in flight per SM).
+// Measured alternatives: 8 warps x ring 16 / 24 / 32, 16 x 16, a cp.async ring in shared memory (4..12 deep,
+// 64 registers, two co-resident CTAs), warp groups of 1..16 per tile with the epilogue operands prefetched — none faster.
+// Products on mma.sync.m16n8k16 (rows 8..15 unused) with the k-permutation of gemm_skinny (a dot product does not care
+// about the order of k inside a 32-block).
 #include <algorithm>
 #include <cstdlib>
 #include <vector>
@@ -26,10 +28,10 @@ namespace frt2 {
 
 namespace {
 
-constexpr int GS_WARPS = 8;
-constexpr int GS_RING = 16;
+constexpr int GS_WARPS = 16;
+constexpr int GS_RING = 8;
 #ifndef GS_MIN_CTAS
-#define GS_MIN_CTAS 2   // registers <= 128: the next kernel of the frame can become resident early (programmatic dependent launch)
+#define GS_MIN_CTAS 1
 #endif
 constexpr int GS_PAD = 32;     // halves between activation rows beyond K: rows g, g+1 land on disjoint banks
 

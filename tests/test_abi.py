@@ -49,6 +49,39 @@ def test_bad_arguments_are_rejected_without_touching_the_gpu(lib):
     assert lib.frt2_decode(None, None, 8, 0, 0, 0, 1, 1, 1, None, None, 0, None) == N.ERR_BAD_ARG
 
 
+def test_frame_decoder_arguments_are_validated_without_a_gpu(lib):
+    from fireredtts2_b200 import _native as N
+    from fireredtts2_b200.frame_decoder import Frt2FdConfig
+    h = C.c_void_p()
+    assert lib.frt2_fd_create(None, 0, C.byref(h)) == N.ERR_BAD_ARG
+    bad = Frt2FdConfig(1536, 1536, 4, 12, 5, 8960, 2048, 16, 1e6, 1e-6)        # kv heads do not divide heads
+    assert lib.frt2_fd_create(C.byref(bad), 0, C.byref(h)) == N.ERR_BAD_ARG
+    bad = Frt2FdConfig(1536, 1530, 4, 12, 2, 8960, 2048, 16, 1e6, 1e-6)        # dim not a multiple of 8
+    assert lib.frt2_fd_create(C.byref(bad), 0, C.byref(h)) == N.ERR_BAD_ARG
+    bad = Frt2FdConfig(1536, 1536, 4, 12, 2, 8960, 2048, 1, 1e6, 1e-6)         # fewer than two codebooks
+    assert lib.frt2_fd_create(C.byref(bad), 0, C.byref(h)) == N.ERR_BAD_ARG
+    assert lib.frt2_fd_finalize(None) == N.ERR_BAD_ARG
+    assert lib.frt2_fd_generate(None, None, 1, None, None, 0, 10, 1.0, None, None, None, None, None) == N.ERR_BAD_ARG
+    assert lib.frt2_op_sample_topk(None, 1, 8, 2, 1.0, None, 0, None, None) == N.ERR_BAD_ARG
+
+
+def test_frame_decoder_host_side():
+    """config presets mirror modules.py, the weight-byte count of the roofline, the synthetic state dict's key set."""
+    from fireredtts2_b200.frame_decoder import (FD_200M, FD_500M, FD_TINY, FrameDecoderConfig, frame_decoder_keys,
+                                                synthetic_frame_decoder_state_dict)
+    assert (FD_200M.dim, FD_200M.num_layers, FD_200M.num_heads, FD_200M.num_kv_heads, FD_200M.intermediate_dim) == \
+        (1536, 4, 12, 2, 8960)                                                    # modules.py:5-18
+    assert (FD_500M.dim, FD_500M.num_layers, FD_500M.num_heads, FD_500M.intermediate_dim) == (896, 24, 14, 4864)   # :21-34
+    assert FD_200M.head_dim == 128 and FD_200M.qkv_dim == 2048
+    per_layer = 1536 * 2048 + 1536 * 1536 + 3 * 1536 * 8960
+    assert FD_200M.weight_bytes_per_frame() == 2 * (16 * (1536 * 1536 + 4 * per_layer) + 15 * 1536 * 2048 + 2048 * 1536)
+    sd = synthetic_frame_decoder_state_dict(FD_TINY, 1)
+    assert sorted(sd) == sorted(frame_decoder_keys(FD_TINY))
+    assert sd["audio_head"].shape == (5, 64, 64) and sd["audio_embeddings.weight"].shape == (6 * 64, 96)
+    with pytest.raises(ValueError):
+        FrameDecoderConfig(dim=100, num_heads=3)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

@@ -131,3 +131,34 @@ def test_sample_topk_library_draws_follow_the_distribution():
     freq = np.bincount(got, minlength=V) / B
     assert freq[~keep].sum() == 0.0
     assert np.abs(freq - p).max() < 4.0 * np.sqrt(0.25 / B)
+
+
+def test_codes_feed_the_codec_step_on_the_device():
+    """generate_frame -> decode_one_token (fireredtts2.py:303-326 of generate_stream): the frame's codes go from the frame
+    decoder to the codec's streaming step as a strided int32 device view, frame after frame on one stream; the audio equals
+    the oracle's streaming decode of the same codes."""
+    from fireredtts2_b200.codec import RedCodecB200
+    from fireredtts2_b200.config import TINY
+    from fireredtts2_b200.weights import synthetic_state_dict
+    cfg, sd, fd = build("FD_TINY", 3)
+    csd = synthetic_state_dict(TINY, 0)
+    codec = RedCodecB200(TINY, csd, device="cuda:0")
+    nq = TINY.num_quantizers
+    assert cfg.audio_vocab_size == TINY.codebook_size and nq <= cfg.audio_num_codebooks
+    rng = np.random.default_rng(9)
+    cache, chunks, frames = {}, [], []
+    n_frames = 5
+    for i in range(n_frames):
+        last_h = cuda(rng.standard_normal((1, cfg.backbone_dim)).astype(np.float32))
+        codes = fd.generate_codes(last_h, 16, 1.0, seed=4)                       # (1, ncb) int32, stays on the device
+        audio, cache = codec.decode_one_token(codes[:, :nq].unsqueeze(-1), cache, i == n_frames - 1)
+        frames.append(codes)
+        chunks.append(audio)
+    fd.check_error()
+    tok = torch.stack(frames, dim=-1)[:, :nq].cpu().numpy().astype(np.int64)      # (1, nq, n_frames)
+    state, ref = None, []
+    for i in range(n_frames):
+        a, state = O.decode_chunk(csd, tok[:, :, i:i + 1], state, i == n_frames - 1, TINY.num_heads, TINY.hop_length)
+        ref.append(a)
+    _, snr = report("frame tail -> codec step audio", np.concatenate(ref, axis=1), to_np(torch.cat(chunks, dim=1)))
+    assert snr >= SNR_GATE_DB

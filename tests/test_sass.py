@@ -93,3 +93,17 @@ def test_encode_side_kernels(sass):
     assert _count(b, "FFMA") >= 8 and _count(b, "HMMA") == 0
     names = " ".join(sass)
     assert "rvq_encode_kernelILi8" in names and "rvq_encode_kernelILi16" in names and "rvq_encode_kernelILi32" in names
+
+
+def test_frame_tail_kernels(sass):
+    """gemm_stream.cu / frame_decoder.cu: the weight stream is 16-byte no-allocate loads feeding mma.sync (<= 8 rows: a
+    tcgen05 tile would be 94 % padding and the kernel is HBM-bound), one block barrier, no local-memory spills; the
+    sampler's selection rounds and the attention's reductions are warp shuffles."""
+    b = _fn(sass, "gemm_stream_kernel")
+    assert _count(b, "HMMA.16816.F32") >= 2 and _count(b, "LDG.E.128.CONSTANT") + _count(b, "LDG.E.128.NA.CONSTANT") + \
+        len(re.findall(r"LDG\.E\.[\w.]*128", b)) >= 8
+    assert _count(b, "UTCHMMA") == 0 and "STL" not in b and "LDL" not in b
+    for name in ("fd_sample_kernel", "fd_attn_kernel"):
+        k = _fn(sass, name)
+        assert _count(k, "SHFL.BFLY") >= 5, name
+    assert _count(_fn(sass, "fd_sample_kernel"), "MUFU.EX2") >= 1

@@ -27,6 +27,7 @@ run pool 900 tests/test_gpu_pool.py
 run streams 900 tests/test_gpu_streams.py
 run rvq_encode 900 tests/test_gpu_rvq_encode.py
 run encoder 900 tests/test_gpu_encoder.py
+run frame_decoder 900 tests/test_gpu_frame_decoder.py
 timeout 600 python __graft_entry__.py --smoke > "$OUT/smoke.log" 2>&1; echo "smoke exit=$?" | tee -a "$OUT/summary.txt"
 grep -h "\[parity\]\|^gemm\|^attention\|smoke:" "$OUT"/*.log > "$OUT/parity_lines.txt" 2>/dev/null
 cat "$OUT/summary.txt"
