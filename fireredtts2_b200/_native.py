@@ -87,6 +87,8 @@ SIGNATURES = {
     "frt2_fd_generate": (_i, [_p, _p, _i, _p, _p, C.c_uint64, _i, _f, _p, _p, _p, C.POINTER(_i64), _p]),
     "frt2_fd_check_error": (_i, [_p, _p]),
     "frt2_resample": (_i, [_i, _p, _i64, _i, _i64, _p, _i, _i, _p, _i64, C.POINTER(_i64), _p]),
+    "frt2_decode_resampled": (_i, [_p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _p, _i64, _i, _i, _p, _i64,
+                                   C.POINTER(_i64), _p]),
     "frt2_rvq_gather": (_i, [_p, _p, _i, _i64, _i64, _i64, _i, _i, _i, _p, _p, _p]),
     "frt2_set_debug": (_i, [_p, _i]),
     "frt2_get_tap": (_i, [_p, C.c_char_p, _p, _i64, C.POINTER(_i64), _p]),

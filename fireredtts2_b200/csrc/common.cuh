@@ -258,6 +258,9 @@ struct OlaDesc {
                              // and nothing is written past the item's own sample count (scatter into a shared buffer)
 };
 int istft_overlap_add(const OlaDesc& d, cudaStream_t stream);
+// overlap-add + rational resampler in one kernel (offline decode): d.audio (24 kHz, optional) and y (resampled)
+int istft_overlap_add_resample(const OlaDesc& d, const float* taps, int K, int width, int orig, int nnew, float* y,
+                               int64_t y_pitch, cudaStream_t stream);
 // mean_out: optional (rows) — the row means, left behind for the folded LayerNorm's shifted fp16 copy
 int layer_norm_rows_batched(const float* x, int64_t ldx, int64_t rows, int rows_per_batch, int C, const float* gamma,
                             const float* beta, float eps, int apply_silu, __half* out16, int64_t ld16,

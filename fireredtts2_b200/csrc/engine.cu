@@ -277,6 +277,11 @@ struct Handle {
 
   int16_t* pcm16_out = nullptr;  // set (under the mutex) by frt2_decode_pcm16 for the next pipeline run
   const long long* scatter_off = nullptr;  // set (under the mutex) by frt2_decode_scatter: per-item output offsets
+  // set (under the mutex) by frt2_decode_resampled: the overlap-add kernel also resamples (taps of the rate pair)
+  float* rs_out = nullptr;
+  int64_t rs_pitch = 0;
+  const float* rs_taps = nullptr;
+  int rs_K = 0, rs_width = 0, rs_orig = 0, rs_new = 0;
 
   // workspace arena (grow-only) of the offline decode and of streaming chunks that do not run as a captured step.
   // The arena is shared by every call on this handle, and calls are asynchronous: a call that arrives on another CUDA
@@ -1234,7 +1239,10 @@ int Handle::pipeline(const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, 
   }
   {
     const int id = prof_begin(FRT2_PROF_OLA, 0.0, static_cast<double>(M) * (n_fft + hop) * 4.0, st);
-    FRT2_TRY(istft_overlap_add(od, st));
+    if (rs_out != nullptr && !streaming)
+      FRT2_TRY(istft_overlap_add_resample(od, rs_taps, rs_K, rs_width, rs_orig, rs_new, rs_out, rs_pitch, st));
+    else
+      FRT2_TRY(istft_overlap_add(od, st));
     prof_end(id, st);
   }
   if (streaming) {
@@ -2098,6 +2106,34 @@ int frt2_resample(int device, const float* in, int64_t in_pitch, int B, int64_t 
   if (n_out) *n_out = n;
   return resample_rows(in, in_pitch, B, n_in, lengths, bank.taps, bank.K, bank.width, bank.orig, bank.nnew, out,
                        out_pitch, st);
+}
+
+int frt2_decode_resampled(frt2_handle* hh, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
+                          int nq, int L, const int32_t* lengths, float* audio, int64_t audio_pitch, int orig_freq,
+                          int new_freq, float* audio_rs, int64_t rs_pitch, int64_t* n_rs, void* cuda_stream) {
+  FRT2_REQUIRE(hh, FRT2_ERR_BAD_ARG, "null handle");
+  Handle& h = hh->h;
+  FRT2_TRY(check_decode_args(h, tokens, idx_bytes, B, nq, L, audio_rs));
+  FRT2_REQUIRE(orig_freq > 0 && new_freq > 0, FRT2_ERR_BAD_ARG,
+               "Original frequency and desired frequecy should be positive");   // torchaudio's message
+  FRT2_REQUIRE(orig_freq != new_freq, FRT2_ERR_BAD_ARG, "frt2_decode_resampled: equal rates (use frt2_decode)");
+  const int64_t n_in = static_cast<int64_t>(8) * h.hop * L;
+  FRT2_REQUIRE(audio == nullptr || audio_pitch >= n_in, FRT2_ERR_BAD_ARG, "audio_pitch too small");
+  ResampleBank bank;
+  FRT2_CUDA_OK(cudaSetDevice(h.device));
+  FRT2_TRY(get_resample_bank(h.device, orig_freq, new_freq, &bank));
+  FRT2_REQUIRE(bank.nnew <= 3, FRT2_ERR_BAD_ARG,
+               "frt2_decode_resampled: new_freq / gcd(orig_freq, new_freq) must be 1, 2 or 3 (decode, then frt2_resample)");
+  const int64_t n = (n_in * bank.nnew + bank.orig - 1) / bank.orig;
+  FRT2_REQUIRE(rs_pitch >= n, FRT2_ERR_BAD_ARG, "frt2_decode_resampled: rs_pitch too small");
+  if (n_rs) *n_rs = n;
+  std::lock_guard<std::mutex> lk(h.mu);
+  h.rs_out = audio_rs; h.rs_pitch = rs_pitch; h.rs_taps = bank.taps; h.rs_K = bank.K; h.rs_width = bank.width;
+  h.rs_orig = bank.orig; h.rs_new = bank.nnew;
+  const int rc = h.pipeline(tokens, idx_bytes, sB, sQ, sL, B, nq, L, lengths, audio, audio_pitch, nullptr, 1,
+                            static_cast<cudaStream_t>(cuda_stream));
+  h.rs_out = nullptr;
+  return rc;
 }
 
 int frt2_set_debug(frt2_handle* hh, int flags) {

@@ -419,6 +419,99 @@ int resample_rows(const float* x, int64_t x_pitch, int B, int64_t n_in, const in
   return FRT2_OK;
 }
 
+// K5c + K6 in one pass ("resample fused onto the decoder output"): the block that stages the input span of
+// its output frames does not READ the 24 kHz waveform — it computes those samples from the windowed iSTFT frames (the
+// gather-form overlap-add of overlap_add_vec4_kernel, same order of additions: bit-identical samples), optionally stores
+// its own part of them as the 24 kHz output, and resamples from shared memory with the FMA sequence of
+// resample_np_kernel (bit-identical to decode -> frt2_resample).  The waveform never makes an HBM round trip between the
+// two steps; every frame element is read once (plus the tile halo of 2 * width samples per fr * orig).
+// Offline decode only (first = last = 1, no carried tail).
+template <int NP>
+__global__ void __launch_bounds__(256) ola_resample_np_kernel(OlaDesc d, int start, const float* __restrict__ taps, int K,
+                                                              int width, int orig, int fr, float* __restrict__ y,
+                                                              long long y_pitch, long long n_out_max) {
+  extern __shared__ float s_in[];
+  const int span = (fr - 1) * orig + K;
+  float* s_taps = s_in + ((span + 3) & ~3);      // [K][NP]
+  const int b = blockIdx.y;
+  int TF = d.T;
+  if (d.lengths != nullptr) TF = min(TF, d.lengths[b] * d.len_mul);
+  const long long n_full = static_cast<long long>(d.T) * d.hop;     // samples of the longest item (row width)
+  const long long n = static_cast<long long>(TF) * d.hop;           // this item's samples
+  const long long n_out = (n * NP + orig - 1) / orig;
+  const long long m0 = static_cast<long long>(blockIdx.x) * fr;
+  const long long in0 = m0 * orig - width;
+  const float* fb = d.frames + static_cast<long long>(b) * d.frames_batch_pitch;
+  for (int i = threadIdx.x; i < span; i += blockDim.x) {
+    const long long g = in0 + i;
+    float v = 0.f;
+    if (g >= 0 && g < n) {
+      const int m = static_cast<int>(g) + start;
+      int t_hi = m / d.hop;
+      if (t_hi > TF - 1) t_hi = TF - 1;
+      int t_lo = (m - d.n_fft + d.hop) / d.hop;
+      if (m - d.n_fft + 1 <= 0) t_lo = 0;
+      float env = 0.f;
+      for (int t = t_lo; t <= t_hi; ++t) {
+        const int off = m - t * d.hop;
+        const float w = __ldg(d.window + off);
+        v += __ldcs(fb + static_cast<long long>(t) * d.n_fft + off);
+        env += w * w;
+      }
+      v /= env;
+    }
+    s_in[i] = v;
+    // this block owns the 24 kHz samples [m0 * orig, (m0 + fr) * orig): zeros behind the item's own length
+    if (d.audio != nullptr && i >= width && i < width + fr * orig && g < n_full)
+      d.audio[static_cast<long long>(b) * d.audio_pitch + g] = v;
+  }
+  for (int i = threadIdx.x; i < K * NP; i += blockDim.x) {
+    const int k = i / NP, p = i - k * NP;
+    s_taps[i] = __ldg(taps + static_cast<long long>(p) * K + k);
+  }
+  __syncthreads();
+  float* yb = y + b * y_pitch;
+  for (int m = threadIdx.x; m < fr; m += blockDim.x) {
+    const long long j0 = (m0 + m) * NP;
+    if (j0 >= n_out_max) break;
+    float acc[NP];
+#pragma unroll
+    for (int p = 0; p < NP; ++p) acc[p] = 0.f;
+    const float* xi = s_in + m * orig;
+    for (int k = 0; k < K; ++k) {
+      const float xv = xi[k];
+#pragma unroll
+      for (int p = 0; p < NP; ++p) acc[p] = fmaf(xv, s_taps[k * NP + p], acc[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p)
+      if (j0 + p < n_out_max) yb[j0 + p] = (j0 + p < n_out) ? acc[p] : 0.f;
+  }
+}
+
+int istft_overlap_add_resample(const OlaDesc& d, const float* taps, int K, int width, int orig, int nnew, float* y,
+                               int64_t y_pitch, cudaStream_t stream) {
+  FRT2_REQUIRE(d.n_fft % d.hop == 0 && d.T >= 1 && d.B >= 1 && d.first && d.last && d.tail == nullptr && d.ctrl == nullptr &&
+                   d.out_off == nullptr && d.pcm16 == nullptr,
+               FRT2_ERR_BAD_ARG, "overlap_add_resample: offline fp32 decode only");
+  FRT2_REQUIRE(nnew >= 1 && nnew <= 3, FRT2_ERR_BAD_ARG,
+               "overlap_add_resample: new_freq / gcd must be 1, 2 or 3 (24 kHz -> 16 / 8 / 12 kHz)");
+  const int pad = (d.n_fft - d.hop) / 2;
+  const int64_t n_in = static_cast<int64_t>(d.T) * d.hop;
+  const int64_t n_out_max = (n_in * nnew + orig - 1) / orig;
+  int fr = (8192 - K) / orig;
+  fr = std::max(1, std::min(fr, 256));
+  const int span = (fr - 1) * orig + K;
+  const int64_t frames = (n_out_max + nnew - 1) / nnew;
+  dim3 grid(static_cast<unsigned>((frames + fr - 1) / fr), d.B);
+  const size_t smem = (static_cast<size_t>((span + 3) & ~3) + static_cast<size_t>(K) * nnew) * 4;
+  if (nnew == 2) ola_resample_np_kernel<2><<<grid, 256, smem, stream>>>(d, pad, taps, K, width, orig, fr, y, y_pitch, n_out_max);
+  else if (nnew == 3) ola_resample_np_kernel<3><<<grid, 256, smem, stream>>>(d, pad, taps, K, width, orig, fr, y, y_pitch, n_out_max);
+  else ola_resample_np_kernel<1><<<grid, 256, smem, stream>>>(d, pad, taps, K, width, orig, fr, y, y_pitch, n_out_max);
+  FRT2_CUDA_OK(cudaGetLastError());
+  return FRT2_OK;
+}
+
 // =====================================================================================================
 // SIMT check GEMM (tests only): same contract as gemm_tc, one thread per output column pair.
 // =====================================================================================================

@@ -279,6 +279,16 @@ int frt2_fd_check_error(frt2_frame_decoder* f, void* cuda_stream);
 int frt2_resample(int device, const float* in, int64_t in_pitch, int B, int64_t n_in, const int32_t* lengths,
                   int orig_freq, int new_freq, float* out, int64_t out_pitch, int64_t* n_out, void* cuda_stream);
 
+/* frt2_decode with the resampler fused behind the overlap-add (the context loop's decode -> torchaudio resample,
+ * fireredtts2.py:386-391): ONE kernel computes the 24 kHz samples from the iSTFT frames, stores them to audio (optional:
+ * NULL = only the resampled waveform is wanted) and resamples them from shared memory into audio_rs (B, ceil(new * 1920 L
+ * / orig)), row pitch rs_pitch; *n_rs (host, optional) receives that length.  Both outputs are bit-identical to
+ * frt2_decode followed by frt2_resample (lengths: item b's outputs behind its own length are zero).  orig_freq is the
+ * codec's 24000; new_freq / gcd must be 1, 2 or 3 (16 kHz: 2). */
+int frt2_decode_resampled(frt2_handle* h, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
+                          int nq, int L, const int32_t* lengths, float* audio, int64_t audio_pitch, int orig_freq,
+                          int new_freq, float* audio_rs, int64_t rs_pitch, int64_t* n_rs, void* cuda_stream);
+
 /* ---- parity hooks ----
  * Raw codebook rows and their index-ordered fp32 sum, bit-exact with VectorQuantize.decode_code /
  * ResidualVQ.decode_codes for Identity projections (rvq.py:56-60,145-164).  rows (B,L,nq,cd) / sum (B,L,cd),

@@ -415,3 +415,33 @@ def test_long_utterance_against_oracle():
     a = to_np(codec.decode(torch.from_numpy(tok).cuda()))
     ref = O.decode(sd, tok, cfg.num_heads, cfg.hop_length)
     _gate("small_B2_L300/audio", ref, a)
+
+
+@pytest.mark.parametrize("new_freq", [16000, 8000, 12000])
+def test_decode_resampled_is_bit_identical_to_decode_then_resample(new_freq):
+    """frt2_decode_resampled (overlap-add + resampler in one kernel; the context loop's decode -> torchaudio resample,
+    fireredtts2.py:386-391): both outputs equal the two separate calls bit for bit, ragged lengths included, and the
+    resampled waveform matches the oracle's torchaudio restatement on the oracle's own decode."""
+    from fireredtts2_b200.codec import resample
+    case = cases("offline")[0]
+    cfg, sd, g = load_case(case)
+    codec = build_codec(cfg, sd)
+    tok = torch.from_numpy(g["tokens"]).cuda()
+    B, _, L = tok.shape
+    a24 = codec.decode(tok)
+    a_rs = resample(a24, 24000, new_freq)
+    f24, f_rs = codec.decode_resampled(tok, new_freq)
+    assert torch.equal(f24, a24) and torch.equal(f_rs, a_rs)
+    only24, only_rs = codec.decode_resampled(tok, new_freq, return_native=False)
+    assert only24 is None and torch.equal(only_rs, a_rs)
+    if B >= 2:
+        lens = torch.tensor([L] + [max(1, L - 3)] * (B - 1), dtype=torch.int32)
+        v24 = codec.decode(tok, lengths=lens)
+        v_rs = resample(v24, 24000, new_freq, lengths=(lens * cfg.samples_per_token))
+        w24, w_rs = codec.decode_resampled(tok, new_freq, lengths=lens)
+        assert torch.equal(w24, v24) and torch.equal(w_rs, v_rs)
+    ref = O.resample(O.decode(sd, g["tokens"], cfg.num_heads, cfg.hop_length), 24000, new_freq)
+    _, snr = report(f"decode_resampled {new_freq} Hz vs oracle", ref, to_np(f_rs))
+    assert f_rs.shape == ref.shape and snr >= 40.0
+    with pytest.raises(ValueError):
+        codec.decode_resampled(tok, 22050)        # 24000 -> 22050: 147 phases per frame, not served by the fused kernel
