@@ -610,6 +610,10 @@ def run_ours(args):
            "gpu_launches": int(launches), "clocks": clocks, "kernels": kernels, "parity": parity, "latency": lat}
     if world == 1 and not args.no_extras:
         try:
+            out["context_resample"] = context_resample_record(codec, tok_dev, B, L, n_samples)
+        except Exception as e:      # noqa: BLE001
+            out["context_resample"] = {"unavailable": repr(e)}
+        try:
             del codec
             torch.cuda.empty_cache()
             out["encode"] = encode_record(dev)
@@ -799,6 +803,47 @@ def encode_record(dev, batch=96, frames=300, reps=5):
                          "frac": fl / (ms_f * 1e-3) / 1e12 / peak if peak else None, "kernel": "frt2_enc_features (gemm_tc + attention_t4)"},
             "parity": {"vq_in_feats_snr_db_vs_oracle": O.snr_db(ref, got), "gate_snr_db": 40.0,
                        "indices_identical_to_oracle_on_gpu_features": float((codes[:, 0].cpu().numpy() == ref_codes[:, 0]).mean())}}
+
+
+def context_resample_record(codec, tok_dev, B, L, n_samples, reps=3):
+    """SURVEY 8f.4 sub-record: the context loop's decode -> 24 kHz -> 16 kHz resample (fireredtts2.py:386-391) on the
+    benchmark batch.  The last stage as two kernels (overlap-add, then frt2_resample re-reading the waveform) against the
+    fused kernel of frt2_decode_resampled; kernel times from the library's profile events (class overlap_add) and CUDA
+    events around the stand-alone resampler; outputs compared bit for bit."""
+    import torch
+    from fireredtts2_b200 import _native as N
+    from fireredtts2_b200.codec import resample
+    a24 = codec.decode(tok_dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    t_rs = []
+    for _ in range(reps):
+        ev[0].record()
+        a16 = resample(a24, 24000, 16000)
+        ev[1].record()
+        torch.cuda.synchronize()
+        t_rs.append(ev[0].elapsed_time(ev[1]))
+    t_ola, t_fused = [], []
+    for _ in range(reps):
+        codec.profile(True)
+        codec.decode(tok_dev)
+        torch.cuda.synchronize()
+        t_ola.append(codec.profile_get(N.PROF_OLA)["ms"])
+        codec.profile(True)
+        f24, f16 = codec.decode_resampled(tok_dev, 16000)
+        torch.cuda.synchronize()
+        t_fused.append(codec.profile_get(N.PROF_OLA)["ms"])
+    codec.profile(False)
+    pk, _ = peaks()
+    frames = B * L * 8
+    bytes_fused = frames * (960 * 4 + 240 * 4 + 160 * 4)          # frames in, 24 kHz out, 16 kHz out
+    ms_two, ms_fused = statistics.median(t_ola) + statistics.median(t_rs), statistics.median(t_fused)
+    return {"workload": f"last stage of decode + resample 24 -> 16 kHz on the benchmark batch ({B} x {L} tokens): both waveforms out",
+            "overlap_add_ms": statistics.median(t_ola), "resample_ms": statistics.median(t_rs), "two_kernels_ms": ms_two,
+            "fused_kernel_ms": ms_fused,
+            "roofline": {"bound": "hbm", "achieved": bytes_fused / (ms_fused * 1e-3) / 1e9, "peak": pk.get("hbm_gbs"),
+                         "unit": "GB/s", "frac": bytes_fused / (ms_fused * 1e-3) / 1e9 / pk["hbm_gbs"] if pk.get("hbm_gbs") else None,
+                         "kernel": "ola_resample_np_kernel<2>"},
+            "bit_identical_to_two_calls": bool(torch.equal(f24, a24) and torch.equal(f16, a16))}
 
 
 def frame_tail_record(dev, frames=40):
