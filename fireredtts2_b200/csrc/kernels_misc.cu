@@ -442,28 +442,47 @@ __global__ void __launch_bounds__(256) ola_resample_np_kernel(OlaDesc d, int sta
   const long long m0 = static_cast<long long>(blockIdx.x) * fr;
   const long long in0 = m0 * orig - width;
   const float* fb = d.frames + static_cast<long long>(b) * d.frames_batch_pitch;
-  for (int i = threadIdx.x; i < span; i += blockDim.x) {
-    const long long g = in0 + i;
-    float v = 0.f;
-    if (g >= 0 && g < n) {
+  // four consecutive samples per thread, aligned to a multiple of 4 of the sample index (hop, pad and n_fft are
+  // multiples of 4: the frames / window are read with 16-byte loads exactly as in overlap_add_vec4_kernel)
+  const long long g_first = in0 >= 0 ? (in0 & ~3LL) : -((-in0 + 3) & ~3LL);
+  const int quads = static_cast<int>((in0 + span - g_first + 3) >> 2);
+  for (int qd = threadIdx.x; qd < quads; qd += blockDim.x) {
+    const long long g = g_first + 4LL * qd;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (g >= 0 && g < n) {       // n is a multiple of 4: the quad is inside the item or outside it as a whole
       const int m = static_cast<int>(g) + start;
       int t_hi = m / d.hop;
       if (t_hi > TF - 1) t_hi = TF - 1;
       int t_lo = (m - d.n_fft + d.hop) / d.hop;
       if (m - d.n_fft + 1 <= 0) t_lo = 0;
-      float env = 0.f;
+      float4 env = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int t = t_lo; t <= t_hi; ++t) {
         const int off = m - t * d.hop;
-        const float w = __ldg(d.window + off);
-        v += __ldcs(fb + static_cast<long long>(t) * d.n_fft + off);
-        env += w * w;
+        const float4 w = __ldg(reinterpret_cast<const float4*>(d.window + off));
+        const float4 f = __ldcs(reinterpret_cast<const float4*>(fb + static_cast<long long>(t) * d.n_fft + off));
+        v.x += f.x; v.y += f.y; v.z += f.z; v.w += f.w;
+        env.x += w.x * w.x; env.y += w.y * w.y; env.z += w.z * w.z; env.w += w.w * w.w;
       }
-      v /= env;
+      v.x /= env.x; v.y /= env.y; v.z /= env.z; v.w /= env.w;
     }
-    s_in[i] = v;
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const long long i = g + e - in0;
+      if (i >= 0 && i < span) s_in[i] = vv[e];
+    }
     // this block owns the 24 kHz samples [m0 * orig, (m0 + fr) * orig): zeros behind the item's own length
-    if (d.audio != nullptr && i >= width && i < width + fr * orig && g < n_full)
-      d.audio[static_cast<long long>(b) * d.audio_pitch + g] = v;
+    if (d.audio != nullptr) {
+      const long long own0 = m0 * orig, own1 = own0 + static_cast<long long>(fr) * orig;
+      float* ap = d.audio + static_cast<long long>(b) * d.audio_pitch;
+      if (g >= own0 && g + 3 < own1 && g + 3 < n_full) {
+        *reinterpret_cast<float4*>(ap + g) = v;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (g + e >= own0 && g + e < own1 && g + e >= 0 && g + e < n_full) ap[g + e] = vv[e];
+      }
+    }
   }
   for (int i = threadIdx.x; i < K * NP; i += blockDim.x) {
     const int k = i / NP, p = i - k * NP;
@@ -496,6 +515,10 @@ int istft_overlap_add_resample(const OlaDesc& d, const float* taps, int K, int w
                FRT2_ERR_BAD_ARG, "overlap_add_resample: offline fp32 decode only");
   FRT2_REQUIRE(nnew >= 1 && nnew <= 3, FRT2_ERR_BAD_ARG,
                "overlap_add_resample: new_freq / gcd must be 1, 2 or 3 (24 kHz -> 16 / 8 / 12 kHz)");
+  FRT2_REQUIRE(d.hop % 4 == 0 && d.n_fft % 4 == 0 && ((d.n_fft - d.hop) / 2) % 4 == 0 && d.frames_batch_pitch % 4 == 0 &&
+                   (reinterpret_cast<uintptr_t>(d.frames) & 15) == 0 && (reinterpret_cast<uintptr_t>(d.window) & 15) == 0 &&
+                   (d.audio == nullptr || ((reinterpret_cast<uintptr_t>(d.audio) & 15) == 0 && d.audio_pitch % 4 == 0)),
+               FRT2_ERR_BAD_ARG, "overlap_add_resample: hop / n_fft / pitches must be multiples of 4, buffers 16-byte aligned");
   const int pad = (d.n_fft - d.hop) / 2;
   const int64_t n_in = static_cast<int64_t>(d.T) * d.hop;
   const int64_t n_out_max = (n_in * nnew + orig - 1) / orig;
