@@ -48,17 +48,19 @@ struct FdParams {
   int has_forced;          // teacher forcing: every code given
 };
 
-__global__ void fd_begin_kernel(const float* __restrict__ last_h, int B, int Db, __half* __restrict__ in16,
+// in_ld: halves between the rows last_h is staged to (2 Db when positions 0 and 1 run as one two-row pass)
+__global__ void fd_begin_kernel(const float* __restrict__ last_h, int B, int Db, __half* __restrict__ in16, int in_ld,
                                 const int* __restrict__ c0, const int* __restrict__ forced, int ncb, int* __restrict__ given,
                                 FdParams p, FdParams* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *dst = p;
   if (i < B * ncb) given[i] = forced != nullptr ? forced[i] : ((c0 != nullptr && i % ncb == 0) ? c0[i / ncb] : 0);
-  for (int e = i; e < B * Db; e += gridDim.x * blockDim.x) in16[e] = to_half_sat(last_h[e]);
+  for (int e = i; e < B * Db; e += gridDim.x * blockDim.x) in16[(e / Db) * in_ld + e % Db] = to_half_sat(last_h[e]);
 }
 
-// One position of one layer: rotary embedding of q and the new k, K/V append, attention over positions 0..pos.
-// grid (Hk, B); one warp per query head of the kv group.  qkv: (B, (H + 2 Hk) hd) fp32 = [q | k | v] with bias.
+// One position of one layer (or the first TWO, np = 2: rows 2b and 2b+1 of qkv / out16 are positions 0 and 1 of item b):
+// rotary embedding of q and the new k, K/V append, attention over positions 0..pos.
+// grid (Hk, B); one warp per query head of the kv group.  qkv: (B * np, (H + 2 Hk) hd) fp32 = [q | k | v] with bias.
 // kc / vc: this layer's (B, npos, Hk, hd) fp32 state.  Scores are 1/sqrt(hd)-scaled dot products, softmax in fp32.
 // Latency is all that matters here (a few KB of state between two weight streams): lane t owns position t — every lane
 // reads ITS key row in one batch of independent 16-byte loads (one round trip for all positions), the softmax is a pair
@@ -66,84 +68,94 @@ __global__ void fd_begin_kernel(const float* __restrict__ last_h, int B, int Db,
 __global__ void __launch_bounds__(256) fd_attn_kernel(const float* __restrict__ qkv, float* __restrict__ kc,
                                                       float* __restrict__ vc, __half* __restrict__ out16,
                                                       const float* __restrict__ rope_cos, const float* __restrict__ rope_sin,
-                                                      int H, int Hk, int hd, int npos, int pos, float scale) {
-  __shared__ __align__(16) float s_q[8][128];       // rotated query of each warp's head
-  __shared__ __align__(16) float s_k[8][128];       // rotated new key / new value (one copy per warp: no CTA barrier)
-  __shared__ __align__(16) float s_v[8][128];
+                                                      int H, int Hk, int hd, int npos, int pos0, int np, float scale) {
+  __shared__ __align__(16) float s_q[8][128];          // rotated query of each warp's head
+  __shared__ __align__(16) float s_k[8][2][128];       // rotated new keys / new values (one copy per warp: no CTA barrier)
+  __shared__ __align__(16) float s_v[8][2][128];
   const int kvh = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rep = H / Hk, half = hd >> 1;
   const int h = kvh * rep + warp;
   const int qkv_ld = (H + 2 * Hk) * hd;
-  const float* qr = qkv + static_cast<long long>(b) * qkv_ld + h * hd;
-  const float* kr = qkv + static_cast<long long>(b) * qkv_ld + (H + kvh) * hd;
-  const float* vr = qkv + static_cast<long long>(b) * qkv_ld + (H + Hk + kvh) * hd;
   const long long row = static_cast<long long>(Hk) * hd;                      // one position of one item
   float* kcb = kc + (static_cast<long long>(b) * npos) * row + kvh * hd;
   float* vcb = vc + (static_cast<long long>(b) * npos) * row + kvh * hd;
-  // the other positions' key rows do not depend on this kernel's input: request them first
-  const int t0 = lane, t1 = lane + 32;
   const int nv4 = hd >> 2;
-  for (int i = lane; i < half; i += 32) {
-    const float c = rope_cos[pos * half + i], s = rope_sin[pos * half + i];
-    const float a = qr[i], bq = qr[i + half];
-    s_q[warp][i] = a * c - bq * s;
-    s_q[warp][i + half] = bq * c + a * s;
-    const float ka = kr[i], kb = kr[i + half];
-    const float k1 = ka * c - kb * s, k2 = kb * c + ka * s;
-    const float v1 = vr[i], v2 = vr[i + half];
-    s_k[warp][i] = k1;
-    s_k[warp][i + half] = k2;
-    s_v[warp][i] = v1;
-    s_v[warp][i + half] = v2;
-    if (warp == 0) {
-      kcb[pos * row + i] = k1;
-      kcb[pos * row + i + half] = k2;
-      vcb[pos * row + i] = v1;
-      vcb[pos * row + i + half] = v2;
+  for (int j = 0; j < np; ++j) {
+    const int pos = pos0 + j;
+    const float* kr = qkv + static_cast<long long>(b * np + j) * qkv_ld + (H + kvh) * hd;
+    const float* vr = qkv + static_cast<long long>(b * np + j) * qkv_ld + (H + Hk + kvh) * hd;
+    for (int i = lane; i < half; i += 32) {
+      const float c = rope_cos[pos * half + i], s = rope_sin[pos * half + i];
+      const float ka = kr[i], kb = kr[i + half];
+      const float k1 = ka * c - kb * s, k2 = kb * c + ka * s;
+      const float v1 = vr[i], v2 = vr[i + half];
+      s_k[warp][j][i] = k1;
+      s_k[warp][j][i + half] = k2;
+      s_v[warp][j][i] = v1;
+      s_v[warp][j][i + half] = v2;
+      if (warp == 0) {
+        kcb[pos * row + i] = k1;
+        kcb[pos * row + i + half] = k2;
+        vcb[pos * row + i] = v1;
+        vcb[pos * row + i + half] = v2;
+      }
     }
   }
-  __syncwarp();
-  auto score = [&](int t) -> float {
-    if (t > pos) return -INFINITY;
-    const float4* kp = t == pos ? reinterpret_cast<const float4*>(s_k[warp]) : reinterpret_cast<const float4*>(kcb + t * row);
-    const float4* qp = reinterpret_cast<const float4*>(s_q[warp]);
-    float acc = 0.f;
+  for (int j = 0; j < np; ++j) {
+    const int pos = pos0 + j;
+    const float* qr = qkv + static_cast<long long>(b * np + j) * qkv_ld + h * hd;
+    __syncwarp();
+    for (int i = lane; i < half; i += 32) {
+      const float c = rope_cos[pos * half + i], s = rope_sin[pos * half + i];
+      const float a = qr[i], bq = qr[i + half];
+      s_q[warp][i] = a * c - bq * s;
+      s_q[warp][i + half] = bq * c + a * s;
+    }
+    __syncwarp();
+    auto score = [&](int t) -> float {
+      if (t > pos) return -INFINITY;
+      const float4* kp = t >= pos0 ? reinterpret_cast<const float4*>(s_k[warp][t - pos0])
+                                   : reinterpret_cast<const float4*>(kcb + t * row);
+      const float4* qp = reinterpret_cast<const float4*>(s_q[warp]);
+      float acc = 0.f;
 #pragma unroll 8
-    for (int i = 0; i < nv4; ++i) {
-      const float4 kv = kp[i], qv = qp[i];
-      acc += (kv.x * qv.x + kv.y * qv.y) + (kv.z * qv.z + kv.w * qv.w);
-    }
-    return acc * scale;
-  };
-  float sc0 = score(t0), sc1 = pos >= 32 ? score(t1) : -INFINITY;
-  float mx = fmaxf(sc0, sc1);
+      for (int i = 0; i < nv4; ++i) {
+        const float4 kv = kp[i], qv = qp[i];
+        acc += (kv.x * qv.x + kv.y * qv.y) + (kv.z * qv.z + kv.w * qv.w);
+      }
+      return acc * scale;
+    };
+    const int t0 = lane, t1 = lane + 32;
+    float sc0 = score(t0), sc1 = pos >= 32 ? score(t1) : -INFINITY;
+    float mx = fmaxf(sc0, sc1);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  sc0 = t0 <= pos ? expf(sc0 - mx) : 0.f;
-  sc1 = t1 <= pos ? expf(sc1 - mx) : 0.f;
-  float den = sc0 + sc1;
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    sc0 = t0 <= pos ? expf(sc0 - mx) : 0.f;
+    sc1 = t1 <= pos ? expf(sc1 - mx) : 0.f;
+    float den = sc0 + sc1;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
-  const float inv = 1.0f / den;
-  sc0 *= inv;
-  sc1 *= inv;
-  float o_acc[4] = {0.f, 0.f, 0.f, 0.f};              // channels lane, lane + 32, lane + 64, lane + 96
+    for (int o = 16; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+    const float inv = 1.0f / den;
+    sc0 *= inv;
+    sc1 *= inv;
+    float o_acc[4] = {0.f, 0.f, 0.f, 0.f};              // channels lane, lane + 32, lane + 64, lane + 96
 #pragma unroll 4
-  for (int t = 0; t <= pos; ++t) {
-    const float a = __shfl_sync(0xffffffffu, t < 32 ? sc0 : sc1, t & 31);
-    const float* vp = t == pos ? s_v[warp] : vcb + t * row;
+    for (int t = 0; t <= pos; ++t) {
+      const float a = __shfl_sync(0xffffffffu, t < 32 ? sc0 : sc1, t & 31);
+      const float* vp = t >= pos0 ? s_v[warp][t - pos0] : vcb + t * row;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int dch = lane + 32 * j;
-      if (dch < hd) o_acc[j] += a * vp[dch];
+      for (int jj = 0; jj < 4; ++jj) {
+        const int dch = lane + 32 * jj;
+        if (dch < hd) o_acc[jj] += a * vp[dch];
+      }
     }
-  }
-  __half* orow = out16 + static_cast<long long>(b) * H * hd + h * hd;
+    __half* orow = out16 + static_cast<long long>(b * np + j) * H * hd + h * hd;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int dch = lane + 32 * j;
-    if (dch < hd) orow[dch] = to_half_sat(o_acc[j]);
+    for (int jj = 0; jj < 4; ++jj) {
+      const int dch = lane + 32 * jj;
+      if (dch < hd) orow[dch] = to_half_sat(o_acc[jj]);
+    }
   }
 }
 
@@ -207,7 +219,7 @@ __device__ __forceinline__ float block_sum(float x, float* red) {
 //   arg-max.  Everything in fp32 in the reference's order of operations.
 __global__ void __launch_bounds__(FD_SAMPLE_THREADS) fd_sample_kernel(
     const float* __restrict__ logits, int s, int V, int ncb, const FdParams* __restrict__ pp, const int* __restrict__ given,
-    int* __restrict__ codes, const __half* __restrict__ emb16, int Db, __half* __restrict__ in16,
+    int* __restrict__ codes, const __half* __restrict__ emb16, int Db, __half* __restrict__ in16, int in_ld,
     unsigned int* __restrict__ err_word) {
   extern __shared__ float fd_smem[];
   float* val = fd_smem;          // scaled logits
@@ -285,7 +297,7 @@ __global__ void __launch_bounds__(FD_SAMPLE_THREADS) fd_sample_kernel(
   code = s_code;
   if (s + 1 < ncb) {
     const uint4* src = reinterpret_cast<const uint4*>(emb16 + (static_cast<long long>(s) * V + code) * Db);
-    uint4* dst = reinterpret_cast<uint4*>(in16 + static_cast<long long>(b) * Db);
+    uint4* dst = reinterpret_cast<uint4*>(in16 + static_cast<long long>(b) * in_ld);
     for (int i = tid; i < Db / 8; i += FD_SAMPLE_THREADS) dst[i] = src[i];
   }
 }
@@ -395,7 +407,8 @@ struct FrameDecoder {
   }
   int finalize();
   int skinny(const __half* A, int K, const __half* W, int N, const float* bias, int act, const float* resid, float* out32,
-             int64_t ld32, __half* out16, int64_t ld16, const float* ln_x, const float* ln_gamma, int B, cudaStream_t st);
+             int64_t ld32, __half* out16, int64_t ld16, const float* ln_x, const float* ln_gamma, int B, cudaStream_t st,
+             int64_t lda = 0, int64_t ldx = 0);
   int enqueue_frame(int B, cudaStream_t st);
   int graph_for(int B, cudaGraphExec_t* out);
 };
@@ -513,20 +526,22 @@ int FrameDecoder::finalize() {
 
 int FrameDecoder::skinny(const __half* A, int K, const __half* W, int N, const float* bias, int act, const float* resid,
                          float* out32, int64_t ld32, __half* out16, int64_t ld16, const float* ln_x,
-                         const float* ln_gamma, int B, cudaStream_t st) {
+                         const float* ln_gamma, int B, cudaStream_t st, int64_t lda, int64_t ldx) {
+  if (lda == 0) lda = K;     // row pitches of the fp16 / fp32 activation rows: every other row of a two-row-per-item buffer
+  if (ldx == 0) ldx = K;
   ++launches;
   if (use_stream) {
     StreamGemm d{};
-    d.Wt = W; d.N = N; d.K = K; d.B = B; d.A = A; d.lda = K; d.x = ln_x; d.ldx = K; d.gamma = ln_gamma; d.eps = cfg.norm_eps;
+    d.Wt = W; d.N = N; d.K = K; d.B = B; d.A = A; d.lda = lda; d.x = ln_x; d.ldx = ldx; d.gamma = ln_gamma; d.eps = cfg.norm_eps;
     d.bias = bias; d.act = act; d.resid = resid; d.out32 = out32; d.ld32 = ld32; d.out16 = out16; d.ld16 = ld16;
     return gemm_stream(d, st);
   }
   GemmDesc g{};
-  g.A = A; g.a_row_pitch = K; g.a_batch_pitch = 0; g.rows_a = B; g.batches = 1; g.Kc = K; g.ntaps = 1; g.row_shift = 0;
+  g.A = A; g.a_row_pitch = lda; g.a_batch_pitch = 0; g.rows_a = B; g.batches = 1; g.Kc = K; g.ntaps = 1; g.row_shift = 0;
   g.W = W; g.N = N; g.rows_out = B; g.alpha = 1.0f; g.bias = bias; g.act = act; g.resid = resid; g.out32 = out32;
   g.ld32 = ld32; g.out16 = out16; g.ld16 = ld16;
   if (ln_gamma != nullptr) {
-    g.ln_x = ln_x; g.ln_ldx = K; g.ln_gamma = ln_gamma; g.ln_beta = nullptr; g.ln_eps = cfg.norm_eps; g.ln_rms = 1;
+    g.ln_x = ln_x; g.ln_ldx = ldx; g.ln_gamma = ln_gamma; g.ln_beta = nullptr; g.ln_eps = cfg.norm_eps; g.ln_rms = 1;
   }
   return gemm_skinny(g, st);
 }
@@ -539,40 +554,69 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
   const int64_t ldl = static_cast<int64_t>(n) * V;
   // timing experiments only (results are wrong with any bit set): marginal cost of a kernel class inside the graph
   static const int skip = getenv("FRT2_FD_SKIP") != nullptr ? atoi(getenv("FRT2_FD_SKIP")) : 0;
-  auto sample = [&](int s) {
-    fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, s, V, n, params, given, codes, emb16, Db, in16,
+  // positions 0 and 1 as ONE two-row pass while 2 B rows fit the GEMM's 8 (the reference's first decoder call has these
+  // two positions too, llm.py:306-321): one weight stream less per frame.  Rows 2b / 2b+1 = position 0 / 1 of item b.
+  static const bool no_pair = getenv("FRT2_FD_NO_PAIR") != nullptr;
+  const bool pair = !no_pair && 2 * B <= FD_MAX_BATCH;
+  auto sample = [&](int s, __half* dst, int dst_ld) {
+    fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, s, V, n, params, given, codes, emb16, Db, dst, dst_ld,
                                                                 err_word);
     ++launches;
     return cudaGetLastError();
   };
-  // codebook 0: llm.py:303-304 (in16 holds last_h here)
-  FRT2_TRY(skinny(in16, Db, w_head0, V, nullptr, ACT_NONE, nullptr, logits, ldl, nullptr, 0, nullptr, nullptr, B, st));
-  for (int pos = 0; pos < n; ++pos) {
-    // projection of this position's input (last_h, then the embedding of the previous code): llm.py:320
-    FRT2_TRY(skinny(in16, Db, w_proj, D, nullptr, ACT_NONE, nullptr, x32, D, nullptr, 0, nullptr, nullptr, B, st));
-    if (pos == 0) FRT2_CUDA_OK(sample(0));   // c0 and its embedding: in16 is free once the projection has read it
+  // projection of a pass's inputs (last_h / the embedding of the previous code) into the residual rows: llm.py:320
+  auto project = [&](int rows) -> int {
+    return skinny(in16, Db, w_proj, D, nullptr, ACT_NONE, nullptr, x32, D, nullptr, 0, nullptr, nullptr, rows, st);
+  };
+  // the decoder's layers over `rows` residual rows holding `np` new positions per item, the first of them at pos0
+  auto layers_pass = [&](int rows, int pos0, int np) -> int {
     for (FdLayer& L : layers) {
       if (!(skip & 8))
-        FRT2_TRY(skinny(nullptr, D, L.w_qkv, qkv, L.b_qkv, ACT_NONE, nullptr, qkv32, qkv, nullptr, 0, x32, L.g_sa, B, st));
-      const dim3 grid(Hk, B);
-      const int threads = 32 * (H / Hk);
+        FRT2_TRY(skinny(nullptr, D, L.w_qkv, qkv, L.b_qkv, ACT_NONE, nullptr, qkv32, qkv, nullptr, 0, x32, L.g_sa, rows, st));
       if (!(skip & 1)) {
-        fd_attn_kernel<<<grid, threads, 0, st>>>(qkv32, L.kc, L.vc, attn16, rope_cos, rope_sin, H, Hk, hd, n, pos, scale);
+        fd_attn_kernel<<<dim3(Hk, B), 32 * (H / Hk), 0, st>>>(qkv32, L.kc, L.vc, attn16, rope_cos, rope_sin, H, Hk, hd, n,
+                                                               pos0, np, scale);
         FRT2_CUDA_OK(cudaGetLastError());
         ++launches;
       }
       if (!(skip & 16))
-        FRT2_TRY(skinny(attn16, H * hd, L.w_o, D, nullptr, ACT_NONE, x32, x32, D, nullptr, 0, nullptr, nullptr, B, st));
+        FRT2_TRY(skinny(attn16, H * hd, L.w_o, D, nullptr, ACT_NONE, x32, x32, D, nullptr, 0, nullptr, nullptr, rows, st));
       if (!(skip & 2))
-        FRT2_TRY(skinny(nullptr, D, L.w_gu, 2 * I, nullptr, ACT_SWIGLU, nullptr, nullptr, 0, h16, I, x32, L.g_mlp, B, st));
+        FRT2_TRY(skinny(nullptr, D, L.w_gu, 2 * I, nullptr, ACT_SWIGLU, nullptr, nullptr, 0, h16, I, x32, L.g_mlp, rows, st));
       if (!(skip & 4))
-        FRT2_TRY(skinny(h16, I, L.w_down, D, nullptr, ACT_NONE, x32, x32, D, nullptr, 0, nullptr, nullptr, B, st));
+        FRT2_TRY(skinny(h16, I, L.w_down, D, nullptr, ACT_NONE, x32, x32, D, nullptr, 0, nullptr, nullptr, rows, st));
     }
-    if (pos >= 1 && !(skip & 32)) {   // llm.py:322-326: final norm (inside the head GEMM), audio_head[pos-1], sampler, next embedding
-      FRT2_TRY(skinny(nullptr, D, w_heads + head_stride * (pos - 1), V, nullptr, ACT_NONE, nullptr,
-                      logits + static_cast<size_t>(pos) * V, ldl, nullptr, 0, x32, g_final, B, st));
-      FRT2_CUDA_OK(sample(pos));
-    }
+    return FRT2_OK;
+  };
+  // llm.py:322-326 for position `pos` (its residual row: x_rows + b * x_ld): final norm (inside the head GEMM),
+  // audio_head[pos-1], sampler, embedding of the next input into in16 row b
+  auto head_and_sample = [&](int pos, const float* x_rows, int64_t x_ld) -> int {
+    if (skip & 32) return FRT2_OK;
+    FRT2_TRY(skinny(nullptr, D, w_heads + head_stride * (pos - 1), V, nullptr, ACT_NONE, nullptr,
+                    logits + static_cast<size_t>(pos) * V, ldl, nullptr, 0, x_rows, g_final, B, st, 0, x_ld));
+    FRT2_CUDA_OK(sample(pos, in16, Db));
+    return FRT2_OK;
+  };
+  // codebook 0: llm.py:303-304 (last_h sits in in16 rows b, or 2b in the two-row layout)
+  FRT2_TRY(skinny(in16, Db, w_head0, V, nullptr, ACT_NONE, nullptr, logits, ldl, nullptr, 0, nullptr, nullptr, B, st,
+                  pair ? 2 * Db : Db));
+  int pos;
+  if (pair) {
+    FRT2_CUDA_OK(sample(0, in16 + Db, 2 * Db));     // c0 and its embedding -> rows 2b+1
+    FRT2_TRY(project(2 * B));
+    FRT2_TRY(layers_pass(2 * B, 0, 2));
+    FRT2_TRY(head_and_sample(1, x32 + D, 2 * D));
+    pos = 2;
+  } else {
+    FRT2_TRY(project(B));                            // position 0 = last_h ...
+    FRT2_CUDA_OK(sample(0, in16, Db));               // ... whose rows are free for c0's embedding once projected
+    FRT2_TRY(layers_pass(B, 0, 1));
+    pos = 1;
+  }
+  for (; pos < n; ++pos) {
+    FRT2_TRY(project(B));
+    FRT2_TRY(layers_pass(B, pos, 1));
+    FRT2_TRY(head_and_sample(pos, x32, D));
   }
   return FRT2_OK;
 }
@@ -692,7 +736,9 @@ int frt2_fd_generate(frt2_frame_decoder* f, const float* last_h, int B, const in
   FdParams p{};
   p.noise = noise; p.seed = seed; p.frame = d.frame++; p.topk = topk; p.temperature = temperature;
   p.has_c0 = c0 != nullptr; p.has_forced = forced != nullptr;
-  fd_begin_kernel<<<std::max(1, (B * Db + 255) / 256), 256, 0, st>>>(last_h, B, Db, d.in16, c0, forced, n, d.given, p, d.params);
+  static const bool no_pair = getenv("FRT2_FD_NO_PAIR") != nullptr;
+  const int in_ld = (!no_pair && 2 * B <= FD_MAX_BATCH) ? 2 * Db : Db;     // the layout enqueue_frame captured for this B
+  fd_begin_kernel<<<std::max(1, (B * Db + 255) / 256), 256, 0, st>>>(last_h, B, Db, d.in16, in_ld, c0, forced, n, d.given, p, d.params);
   FRT2_CUDA_OK(cudaGetLastError());
   FRT2_CUDA_OK(cudaGraphLaunch(exec, st));
   d.launches += 1 + d.graph_kernels[B];
@@ -739,7 +785,7 @@ int frt2_op_sample_topk(const float* logits, int B, int V, int topk, float tempe
   if (e == cudaSuccess) e = cudaFuncSetAttribute(fd_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * V * 4);
   if (e == cudaSuccess) {
     // ncb = 1, s = 0: item b reads logits[b * V ..], noise[b * V ..] and writes codes[b]; no embedding lookup
-    fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, 0, V, 1, dp, nullptr, codes, nullptr, 0, nullptr, nullptr);
+    fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, 0, V, 1, dp, nullptr, codes, nullptr, 0, nullptr, 0, nullptr);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
