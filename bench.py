@@ -893,6 +893,33 @@ def frame_tail_record(dev, frames=40):
                      "free_running_codes_identical_to_oracle": float((codes == ref_codes).mean())}
     rec["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
                            "sample": "one FD_200M frame (16 positions) by oracle/frame_decoder_oracle.py (numpy fp32, BLAS threads)"}
+    # the first-packet path behind the backbone (generate_stream, fireredtts2.py:303-326): host last_h -> frame tail ->
+    # codec step (the codes never leave the device) -> first 1560 samples on the host
+    try:
+        from fireredtts2_b200.codec import RedCodecB200
+        from fireredtts2_b200.config import C0
+        from fireredtts2_b200.weights import synthetic_state_dict
+        codec = RedCodecB200(C0, synthetic_state_dict(C0, 0), device=str(dev), check_indices=False)
+        h_host = torch.from_numpy(synthetic_frame_inputs(cfg, 1, 5)[0]).pin_memory()
+        out_host = torch.empty((1, 1560), dtype=torch.float32).pin_memory()
+        ts = []
+        for i in range(60):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            h = h_host.to(dev, non_blocking=True)
+            codes = fd.generate_codes(h, 30, 0.9, seed=2)
+            audio, _ = codec.decode_one_token(codes.unsqueeze(-1), {}, False)
+            out_host.copy_(audio, non_blocking=True)
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        ts = sorted(ts[10:])
+        rec["first_chunk_behind_backbone"] = {
+            "workload": "batch 1: pinned host last_h -> H2D -> frt2_fd_generate -> decode_one_token(codes, {}, False) on the "
+                        "C0 codec -> 1560 samples D2H -> sync (the backbone pass in front of it is out of scope)",
+            "p50_ms": ts[len(ts) // 2], "p99_ms": ts[min(len(ts) - 1, int(len(ts) * 0.99))], "reps": len(ts),
+            "finite": bool(torch.isfinite(out_host).all())}
+    except Exception as e:      # noqa: BLE001
+        rec["first_chunk_behind_backbone"] = {"unavailable": repr(e)}
     return rec
 
 

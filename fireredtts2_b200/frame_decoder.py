@@ -55,11 +55,13 @@ class FrameDecoderConfig:
         return (self.num_heads + 2 * self.num_kv_heads) * self.head_dim
 
     def weight_bytes_per_frame(self) -> int:
-        """fp16 weight bytes one frame streams (the HBM roofline of the batch-1 frame tail)."""
+        """Algorithmic fp16 weight bytes of one frame (the HBM roofline of the frame tail at small batch): the reference runs
+        ``audio_num_codebooks - 1`` decoder calls per frame (llm.py:317-321, the first over two positions), each streams the
+        projection and every layer once; plus the codebook-0 head and one ``audio_head`` slice per call."""
         D, Db, I, V, n = self.dim, self.backbone_dim, self.intermediate_dim, self.audio_vocab_size, self.audio_num_codebooks
         layer = D * self.qkv_dim + D * D + 3 * D * I
-        per_pos = Db * D + self.num_layers * layer
-        return 2 * (n * per_pos + (n - 1) * D * V + V * Db)
+        per_pass = Db * D + self.num_layers * layer
+        return 2 * ((n - 1) * per_pass + (n - 1) * D * V + V * Db)
 
 
 # decoder flavors of the reference (modules.py:5-35) next to the backbone width they are paired with

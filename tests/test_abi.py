@@ -74,7 +74,7 @@ def test_frame_decoder_host_side():
     assert (FD_500M.dim, FD_500M.num_layers, FD_500M.num_heads, FD_500M.intermediate_dim) == (896, 24, 14, 4864)   # :21-34
     assert FD_200M.head_dim == 128 and FD_200M.qkv_dim == 2048
     per_layer = 1536 * 2048 + 1536 * 1536 + 3 * 1536 * 8960
-    assert FD_200M.weight_bytes_per_frame() == 2 * (16 * (1536 * 1536 + 4 * per_layer) + 15 * 1536 * 2048 + 2048 * 1536)
+    assert FD_200M.weight_bytes_per_frame() == 2 * (15 * (1536 * 1536 + 4 * per_layer) + 15 * 1536 * 2048 + 2048 * 1536)
     sd = synthetic_frame_decoder_state_dict(FD_TINY, 1)
     assert sorted(sd) == sorted(frame_decoder_keys(FD_TINY))
     assert sd["audio_head"].shape == (5, 64, 64) and sd["audio_embeddings.weight"].shape == (6 * 64, 96)

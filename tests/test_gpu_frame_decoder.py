@@ -95,6 +95,20 @@ def test_two_row_first_pass_and_single_row_layout_agree():
     assert same.sum() >= 4          # a frame may leave the oracle's trajectory at an fp16-vs-fp32 near-tie of the sampler
 
 
+def test_qwen_500m_decoder_flavor():
+    """The flavor pair of the reference's own example (llm.py:356-357: qwen-3b backbone width, qwen-500m decoder: 24 layers
+    x 896, 14 / 2 heads of 64, 4864): 7 query heads per kv group, a 1817-kernel graph; against the oracle."""
+    cfg, sd, fd = build("FD_500M", 2)
+    last_h, noise = synthetic_frame_inputs(cfg, 1, seed=3)
+    ref_codes, ref_logits = FO.generate_codes(sd, cfg, last_h, 30, 0.9, noise)
+    _, logits = fd.generate_codes(cuda(last_h), 30, 0.9, noise=cuda(noise), forced=cuda(ref_codes), return_logits=True)
+    _, snr = report("FD_500M teacher-forced logits", ref_logits, to_np(logits))
+    assert snr >= SNR_GATE_DB
+    codes = fd.generate_codes(cuda(last_h), 30, 0.9, noise=cuda(noise)).cpu().numpy()
+    print(f"[parity] FD_500M: free-running codes equal to the oracle's: {int((codes == ref_codes).sum())} / {codes.size}")
+    assert (codes[:, :4] == ref_codes[:, :4]).all()
+
+
 def test_out_of_range_code_raises_index_error():
     cfg, sd, fd = build("FD_TINY", 3)
     last_h, noise = synthetic_frame_inputs(cfg, 2, seed=1)
