@@ -159,6 +159,41 @@ __global__ void __launch_bounds__(256) fd_attn_kernel(const float* __restrict__ 
   }
 }
 
+// Large-batch path (> 8 items per frame, tcgen05 GEMMs): RMSNorm rows fp32 -> fp16 (one warp per row, the row kept in
+// registers for widths <= 4096) and silu(gate) * up on the interleaved (gate_j, up_j) columns of the merged GEMM's output
+__global__ void __launch_bounds__(256) fd_rms_rows_kernel(const float* __restrict__ x, int rows, int C,
+                                                          const float* __restrict__ gamma, float eps,
+                                                          __half* __restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int C4 = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+  float q = 0.f;
+  for (int c = lane; c < C4; c += 32) {
+    const float4 v = xr[c];
+    q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / static_cast<float>(C) + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  __half* orow = out + static_cast<long long>(row) * C;
+  for (int c = lane; c < C4; c += 32) {
+    const float4 v = xr[c], gg = __ldg(g4 + c);
+    uint2 h;
+    h.x = pack_half2(v.x * rstd * gg.x, v.y * rstd * gg.y);
+    h.y = pack_half2(v.z * rstd * gg.z, v.w * rstd * gg.w);
+    *reinterpret_cast<uint2*>(orow + 4 * c) = h;
+  }
+}
+__global__ void __launch_bounds__(256) fd_swiglu_rows_kernel(const __half2* __restrict__ gu, long long n,
+                                                             __half* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float2 p = __half22float2(gu[i]);      // (gate_j, up_j)
+  out[i] = to_half_sat(p.x / (1.0f + expf(-p.x)) * p.y);
+}
+
 // Philox-4x32-10 (counter-based: the draw of (frame, item, codebook, entry) does not depend on launch geometry)
 __device__ __forceinline__ float fd_exp1_draw(unsigned long long seed, unsigned long long frame, int b, int s, int v) {
   uint32_t c0 = static_cast<uint32_t>(v), c1 = static_cast<uint32_t>(s) | (static_cast<uint32_t>(b) << 16);
@@ -312,6 +347,7 @@ struct FdLayer {
   __half* w_o = nullptr;                               // (D, H hd)
   __half* w_gu = nullptr;                              // (2 I, D): rows (gate_0, up_0, gate_1, up_1, ...)
   __half* w_down = nullptr;                            // (D, I)
+  __half *w_qkv_rm = nullptr, *w_o_rm = nullptr, *w_gu_rm = nullptr, *w_down_rm = nullptr;   // row-major copies (large batches)
   float *g_sa = nullptr, *g_mlp = nullptr;
   float *kc = nullptr, *vc = nullptr;                  // (MAX_BATCH, ncb, Hk, hd) fp32
 };
@@ -332,6 +368,10 @@ struct FrameDecoder {
   __half* w_head0 = nullptr;     // (V, Db)
   __half* w_heads = nullptr;     // (ncb - 1, V, D): audio_head[i] transposed (K contiguous)
   size_t head_stride = 0;        // elements between two heads
+  bool big = false;              // max_batch > 8: row-major weight copies + tcgen05 GEMMs for frames of 9 .. max_batch items
+  int mb = FD_MAX_BATCH;         // rows the activation buffers hold
+  __half *w_proj_rm = nullptr, *w_head0_rm = nullptr, *w_heads_rm = nullptr;
+  __half *n16 = nullptr, *gu16 = nullptr;
   __half* emb16 = nullptr;       // (ncb * V, Db)
   float* g_final = nullptr;
   float *rope_cos = nullptr, *rope_sin = nullptr;     // (ncb, hd / 2)
@@ -381,7 +421,8 @@ struct FrameDecoder {
     return FRT2_OK;
   }
   // GEMM weight (N, K) fp32 -> fp16 in the layout of the kernel that will stream it
-  int up_w(const float* w, int64_t N, int64_t K, __half** out) {
+  int up_w(const float* w, int64_t N, int64_t K, __half** out, __half** rm = nullptr) {
+    if (rm != nullptr && big) FRT2_TRY(up16(std::vector<float>(w, w + N * K), rm));
     if (!use_stream) return up16(std::vector<float>(w, w + N * K), out);
     std::vector<__half> packed(gemm_stream_packed_elems(N, K));
     gemm_stream_pack_host(w, N, K, packed.data());
@@ -410,6 +451,9 @@ struct FrameDecoder {
              int64_t ld32, __half* out16, int64_t ld16, const float* ln_x, const float* ln_gamma, int B, cudaStream_t st,
              int64_t lda = 0, int64_t ldx = 0);
   int enqueue_frame(int B, cudaStream_t st);
+  int enqueue_frame_big(int B, cudaStream_t st);
+  int tc(const __half* A, int K, const __half* W, int N, const float* bias, const float* resid, float* out32, int64_t ld32,
+         __half* out16, int64_t ld16, int rows, cudaStream_t st);
   int graph_for(int B, cudaGraphExec_t* out);
 };
 
@@ -421,11 +465,14 @@ int FrameDecoder::finalize() {
                gemm_stream_applicable(8, cfg.backbone_dim, 8) && gemm_stream_applicable(8, cfg.intermediate_dim, 8);
   const int D = cfg.dim, Db = cfg.backbone_dim, I = cfg.intermediate_dim, V = cfg.audio_vocab_size, n = cfg.audio_num_codebooks;
   const int H = cfg.num_heads, Hk = cfg.num_kv_heads;
+  big = cfg.max_batch > FD_MAX_BATCH;
+  mb = big ? cfg.max_batch : FD_MAX_BATCH;
+  if (big) FRT2_TRY(gemm_tc_init());
   const HostT* t = nullptr;
   FRT2_TRY(need("projection.weight", &t, {D, Db}));
-  FRT2_TRY(up_w(t->data.data(), D, Db, &w_proj));
+  FRT2_TRY(up_w(t->data.data(), D, Db, &w_proj, &w_proj_rm));
   FRT2_TRY(need("codebook0_head.weight", &t, {V, Db}));
-  FRT2_TRY(up_w(t->data.data(), V, Db, &w_head0));
+  FRT2_TRY(up_w(t->data.data(), V, Db, &w_head0, &w_head0_rm));
   FRT2_TRY(need("audio_embeddings.weight", &t, {static_cast<int64_t>(V) * n, Db}));
   FRT2_TRY(up16(t->data, &emb16));
   FRT2_TRY(need("audio_head", &t, {n - 1, D, V}));
@@ -438,6 +485,7 @@ int FrameDecoder::finalize() {
       for (int v = 0; v < V; ++v)
         for (int d = 0; d < D; ++d) dst[static_cast<size_t>(v) * D + d] = src[static_cast<size_t>(d) * V + v];
     }
+    if (big) FRT2_TRY(up16(tr, &w_heads_rm));        // (ncb - 1, V, D) row-major
     head_stride = use_stream ? gemm_stream_packed_elems(V, D) : static_cast<size_t>(V) * D;
     std::vector<__half> all(head_stride * (n - 1));
     FRT2_TRY(dev_alloc(&w_heads, all.size()));
@@ -470,10 +518,10 @@ int FrameDecoder::finalize() {
     std::copy(bq->data.begin(), bq->data.end(), bias.begin());
     std::copy(bk->data.begin(), bk->data.end(), bias.begin() + H * hd);
     std::copy(bv->data.begin(), bv->data.end(), bias.begin() + (H + Hk) * hd);
-    FRT2_TRY(up_w(w.data(), qkv, D, &L.w_qkv));
+    FRT2_TRY(up_w(w.data(), qkv, D, &L.w_qkv, &L.w_qkv_rm));
     FRT2_TRY(up32(bias.data(), bias.size(), &L.b_qkv));
     FRT2_TRY(need(p + "attn.output_proj.weight", &t, {D, H * hd}));
-    FRT2_TRY(up_w(t->data.data(), D, H * hd, &L.w_o));
+    FRT2_TRY(up_w(t->data.data(), D, H * hd, &L.w_o, &L.w_o_rm));
     FRT2_TRY(need(p + "mlp.w1.weight", &w1, {I, D}));
     FRT2_TRY(need(p + "mlp.w3.weight", &w3, {I, D}));
     std::vector<float> gu(static_cast<size_t>(2) * I * D);
@@ -482,15 +530,15 @@ int FrameDecoder::finalize() {
       std::memcpy(gu.data() + static_cast<size_t>(2 * j) * D, w1->data.data() + static_cast<size_t>(j) * D, D * 4);
       std::memcpy(gu.data() + static_cast<size_t>(2 * j + 1) * D, w3->data.data() + static_cast<size_t>(j) * D, D * 4);
     }
-    FRT2_TRY(up_w(gu.data(), 2 * I, D, &L.w_gu));
+    FRT2_TRY(up_w(gu.data(), 2 * I, D, &L.w_gu, &L.w_gu_rm));
     FRT2_TRY(need(p + "mlp.w2.weight", &t, {D, I}));
-    FRT2_TRY(up_w(t->data.data(), D, I, &L.w_down));
+    FRT2_TRY(up_w(t->data.data(), D, I, &L.w_down, &L.w_down_rm));
     FRT2_TRY(need(p + "sa_norm.scale", &t, {D}));
     FRT2_TRY(up32(t->data.data(), D, &L.g_sa));
     FRT2_TRY(need(p + "mlp_norm.scale", &t, {D}));
     FRT2_TRY(up32(t->data.data(), D, &L.g_mlp));
-    FRT2_TRY(dev_alloc(&L.kc, static_cast<size_t>(FD_MAX_BATCH) * n * Hk * hd));
-    FRT2_TRY(dev_alloc(&L.vc, static_cast<size_t>(FD_MAX_BATCH) * n * Hk * hd));
+    FRT2_TRY(dev_alloc(&L.kc, static_cast<size_t>(mb) * n * Hk * hd));
+    FRT2_TRY(dev_alloc(&L.vc, static_cast<size_t>(mb) * n * Hk * hd));
   }
   {  // rotary tables in double (Qwen2RotaryPositionalEmbeddings: theta_i = base^(-2i/hd), angle = pos * theta_i)
     const int half = hd / 2;
@@ -504,14 +552,18 @@ int FrameDecoder::finalize() {
     FRT2_TRY(up32(c.data(), c.size(), &rope_cos));
     FRT2_TRY(up32(s.data(), s.size(), &rope_sin));
   }
-  FRT2_TRY(dev_alloc(&in16, static_cast<size_t>(FD_MAX_BATCH) * Db));
-  FRT2_TRY(dev_alloc(&attn16, static_cast<size_t>(FD_MAX_BATCH) * H * hd));
-  FRT2_TRY(dev_alloc(&h16, static_cast<size_t>(FD_MAX_BATCH) * I));
-  FRT2_TRY(dev_alloc(&x32, static_cast<size_t>(FD_MAX_BATCH) * D));
-  FRT2_TRY(dev_alloc(&qkv32, static_cast<size_t>(FD_MAX_BATCH) * qkv));
-  FRT2_TRY(dev_alloc(&logits, static_cast<size_t>(FD_MAX_BATCH) * n * V));
-  FRT2_TRY(dev_alloc(&codes, static_cast<size_t>(FD_MAX_BATCH) * n));
-  FRT2_TRY(dev_alloc(&given, static_cast<size_t>(FD_MAX_BATCH) * n));
+  FRT2_TRY(dev_alloc(&in16, static_cast<size_t>(mb) * Db));
+  FRT2_TRY(dev_alloc(&attn16, static_cast<size_t>(mb) * H * hd));
+  FRT2_TRY(dev_alloc(&h16, static_cast<size_t>(mb) * I));
+  FRT2_TRY(dev_alloc(&x32, static_cast<size_t>(mb) * D));
+  FRT2_TRY(dev_alloc(&qkv32, static_cast<size_t>(mb) * qkv));
+  FRT2_TRY(dev_alloc(&logits, static_cast<size_t>(mb) * n * V));
+  FRT2_TRY(dev_alloc(&codes, static_cast<size_t>(mb) * n));
+  FRT2_TRY(dev_alloc(&given, static_cast<size_t>(mb) * n));
+  if (big) {
+    FRT2_TRY(dev_alloc(&n16, static_cast<size_t>(mb) * std::max(D, Db)));
+    FRT2_TRY(dev_alloc(&gu16, static_cast<size_t>(mb) * 2 * I));
+  }
   FRT2_TRY(dev_alloc(&params, 1));
   FRT2_TRY(dev_alloc(&err_word, 1));
   FRT2_CUDA_OK(cudaFuncSetAttribute(fd_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * V * 4));
@@ -621,6 +673,64 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
   return FRT2_OK;
 }
 
+// ---- frames of 9 .. max_batch items: the same sequence on the tcgen05 GEMM (128-row tiles; every weight is still
+//      streamed once per decoder pass, now shared by up to 128 rows per tile) with RMSNorm / SwiGLU as row kernels
+int FrameDecoder::tc(const __half* A, int K, const __half* W, int N, const float* bias, const float* resid, float* out32,
+                     int64_t ld32, __half* out16, int64_t ld16, int rows, cudaStream_t st) {
+  GemmDesc g{};
+  g.A = A; g.a_row_pitch = K; g.a_batch_pitch = 0; g.rows_a = rows; g.batches = 1; g.Kc = K; g.ntaps = 1; g.row_shift = 0;
+  g.W = W; g.N = N; g.rows_out = rows; g.alpha = 1.0f; g.bias = bias; g.act = ACT_NONE; g.resid = resid; g.out32 = out32;
+  g.ld32 = ld32; g.out16 = out16; g.ld16 = ld16;
+  ++launches;
+  return gemm_tc(g, st);
+}
+
+int FrameDecoder::enqueue_frame_big(int B, cudaStream_t st) {
+  const int D = cfg.dim, Db = cfg.backbone_dim, I = cfg.intermediate_dim, V = cfg.audio_vocab_size, n = cfg.audio_num_codebooks;
+  const int H = cfg.num_heads, Hk = cfg.num_kv_heads;
+  const float scale = 1.0f / std::sqrt(static_cast<float>(hd));
+  const int64_t ldl = static_cast<int64_t>(n) * V;
+  auto sample = [&](int s) {
+    fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, s, V, n, params, given, codes, emb16, Db, in16, Db,
+                                                                err_word);
+    ++launches;
+    return cudaGetLastError();
+  };
+  auto rms = [&](const float* g) {
+    fd_rms_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(x32, B, D, g, cfg.norm_eps, n16);
+    ++launches;
+    return cudaGetLastError();
+  };
+  FRT2_TRY(tc(in16, Db, w_head0_rm, V, nullptr, nullptr, logits, ldl, nullptr, 0, B, st));           // llm.py:303
+  for (int pos = 0; pos < n; ++pos) {
+    FRT2_TRY(tc(in16, Db, w_proj_rm, D, nullptr, nullptr, x32, D, nullptr, 0, B, st));                // llm.py:320
+    if (pos == 0) FRT2_CUDA_OK(sample(0));
+    for (FdLayer& L : layers) {
+      FRT2_CUDA_OK(rms(L.g_sa));
+      FRT2_TRY(tc(n16, D, L.w_qkv_rm, qkv, L.b_qkv, nullptr, qkv32, qkv, nullptr, 0, B, st));
+      fd_attn_kernel<<<dim3(Hk, B), 32 * (H / Hk), 0, st>>>(qkv32, L.kc, L.vc, attn16, rope_cos, rope_sin, H, Hk, hd, n, pos, 1,
+                                                             scale);
+      FRT2_CUDA_OK(cudaGetLastError());
+      ++launches;
+      FRT2_TRY(tc(attn16, H * hd, L.w_o_rm, D, nullptr, x32, x32, D, nullptr, 0, B, st));
+      FRT2_CUDA_OK(rms(L.g_mlp));
+      FRT2_TRY(tc(n16, D, L.w_gu_rm, 2 * I, nullptr, nullptr, nullptr, 0, gu16, 2 * I, B, st));
+      const long long ne = static_cast<long long>(B) * I;
+      fd_swiglu_rows_kernel<<<static_cast<unsigned>((ne + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half2*>(gu16), ne, h16);
+      FRT2_CUDA_OK(cudaGetLastError());
+      ++launches;
+      FRT2_TRY(tc(h16, I, L.w_down_rm, D, nullptr, x32, x32, D, nullptr, 0, B, st));
+    }
+    if (pos >= 1) {                                                                                    // llm.py:322-326
+      FRT2_CUDA_OK(rms(g_final));
+      FRT2_TRY(tc(n16, D, w_heads_rm + static_cast<size_t>(pos - 1) * V * D, V, nullptr, nullptr,
+                  logits + static_cast<size_t>(pos) * V, ldl, nullptr, 0, B, st));
+      FRT2_CUDA_OK(sample(pos));
+    }
+  }
+  return FRT2_OK;
+}
+
 int FrameDecoder::graph_for(int B, cudaGraphExec_t* out) {
   auto it = graphs.find(B);
   if (it != graphs.end()) {
@@ -629,7 +739,7 @@ int FrameDecoder::graph_for(int B, cudaGraphExec_t* out) {
   }
   const long long before = launches;
   FRT2_CUDA_OK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
-  const int rc = enqueue_frame(B, cap_stream);
+  const int rc = B > FD_MAX_BATCH ? enqueue_frame_big(B, cap_stream) : enqueue_frame(B, cap_stream);
   cudaGraph_t graph = nullptr;
   const cudaError_t ce = cudaStreamEndCapture(cap_stream, &graph);
   if (rc != FRT2_OK) {
@@ -667,6 +777,10 @@ int frt2_fd_create(const frt2_fd_config* cfg, int device, frt2_frame_decoder** o
   FRT2_REQUIRE(cfg->audio_vocab_size > 0 && cfg->audio_vocab_size <= 24000 && cfg->audio_num_codebooks >= 2 &&
                    cfg->audio_num_codebooks <= FD_MAX_POS,
                FRT2_ERR_BAD_ARG, "frt2_fd_create: audio_vocab_size in [1, 24000], audio_num_codebooks in [2, 64]");
+  FRT2_REQUIRE(cfg->max_batch >= 0 && cfg->max_batch <= 1024, FRT2_ERR_BAD_ARG, "frt2_fd_create: max_batch must be in [0, 1024]");
+  FRT2_REQUIRE(cfg->max_batch <= FD_MAX_BATCH ||
+                   (cfg->dim % 64 == 0 && cfg->backbone_dim % 64 == 0 && cfg->intermediate_dim % 64 == 0 && hd % 8 == 0),
+               FRT2_ERR_BAD_ARG, "frt2_fd_create: max_batch > 8 needs widths that are multiples of 64");
   int ndev = 0;
   FRT2_CUDA_OK(cudaGetDeviceCount(&ndev));
   FRT2_REQUIRE(device >= 0 && device < ndev, FRT2_ERR_BAD_ARG, "frt2_fd_create: bad device index");
@@ -723,7 +837,7 @@ int frt2_fd_generate(frt2_frame_decoder* f, const float* last_h, int B, const in
   FRT2_REQUIRE(f && last_h && codes, FRT2_ERR_BAD_ARG, "frt2_fd_generate: null argument");
   FrameDecoder& d = f->d;
   FRT2_REQUIRE(d.finalized, FRT2_ERR_NOT_FINALIZED, "frt2_fd_generate: call frt2_fd_finalize first");
-  FRT2_REQUIRE(B >= 1 && B <= FD_MAX_BATCH, FRT2_ERR_BAD_ARG, "frt2_fd_generate: batch must be in [1, 8]");
+  FRT2_REQUIRE(B >= 1 && B <= d.mb, FRT2_ERR_BAD_ARG, "frt2_fd_generate: batch must be in [1, max(8, max_batch)]");
   FRT2_REQUIRE(topk >= 1 && temperature > 0.f, FRT2_ERR_BAD_ARG, "frt2_fd_generate: topk >= 1 and temperature > 0 required");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   std::lock_guard<std::mutex> lk(d.mu);

@@ -28,8 +28,17 @@ namespace frt2 {
 
 namespace {
 
-constexpr int GS_WARPS = 16;
-constexpr int GS_RING = 8;
+#ifndef GS_WARPS_N
+#define GS_WARPS_N 16
+#endif
+#ifndef GS_RING_N
+#define GS_RING_N 8
+#endif
+#ifndef GS_CTAS_PER_SM
+#define GS_CTAS_PER_SM 1     // CTAs of ONE launch per SM (grid = this x SMs)
+#endif
+constexpr int GS_WARPS = GS_WARPS_N;
+constexpr int GS_RING = GS_RING_N;
 #ifndef GS_MIN_CTAS
 #define GS_MIN_CTAS 1
 #endif
@@ -95,8 +104,8 @@ __global__ void __launch_bounds__(GS_WARPS * 32, GS_MIN_CTAS) gemm_stream_kernel
   const int nb = d.K >> 5;                 // k32 blocks per column tile
   const int T = (d.N + 7) >> 3;            // column tiles
   const int pitch = d.K + GS_PAD;
-  __half* sA = reinterpret_cast<__half*>(gs_smem);                                            // [8][pitch]
-  float* sRed = reinterpret_cast<float*>(gs_smem + static_cast<size_t>(8) * pitch * 2);       // SPLIT: [2][GS_WARPS][64]
+  __half* sA = reinterpret_cast<__half*>(gs_smem);                                            // [B][pitch]
+  float* sRed = reinterpret_cast<float*>(gs_smem + static_cast<size_t>(d.B) * pitch * 2);     // SPLIT: [2][GS_WARPS][64]
 
   // ---- this warp's segments: (tile, blocks [kb0, kb1)); consecutive segments are `tstep` tiles apart
   int tile0, ntiles, tstep, kb0, kb1;
@@ -264,11 +273,15 @@ int gemm_stream(const StreamGemm& d, cudaStream_t stream) {
                "gemm_stream: activation operand missing or misaligned");
   static const int sms = num_sms();
   const int T = (d.N + 7) / 8;
-  const bool split = T < sms * GS_WARPS;          // fewer column tiles than warps in the grid: the CTA's warps split K
+  const size_t smem = static_cast<size_t>(d.B) * (d.K + GS_PAD) * 2 + 2 * GS_WARPS * 64 * 4;
+  // GS_CTAS_PER_SM CTAs per SM while their shared memory fits next to the same number of CTAs of the NEXT launch
+  const int per_sm = (GS_CTAS_PER_SM > 1 && smem * 2 * GS_CTAS_PER_SM <= 200 * 1024) ? GS_CTAS_PER_SM : 1;
+  const int ctas = sms * per_sm;
+  const bool split = T < ctas * GS_WARPS;         // fewer column tiles than warps in the grid: the CTA's warps split K
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(split ? std::min(sms, T) : sms);
+  cfg.gridDim = dim3(split ? std::min(ctas, T) : ctas);
   cfg.blockDim = dim3(GS_WARPS * 32);
-  cfg.dynamicSmemBytes = static_cast<size_t>(8) * (d.K + GS_PAD) * 2 + (split ? 2 * GS_WARPS * 64 * 4 : 0);
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

@@ -137,15 +137,16 @@ def synthetic_frame_inputs(cfg: FrameDecoderConfig, batch: int, seed: int = 0) -
 class Frt2FdConfig(C.Structure):
     _fields_ = [("backbone_dim", C.c_int32), ("dim", C.c_int32), ("num_layers", C.c_int32), ("num_heads", C.c_int32),
                 ("num_kv_heads", C.c_int32), ("intermediate_dim", C.c_int32), ("audio_vocab_size", C.c_int32),
-                ("audio_num_codebooks", C.c_int32), ("rope_base", C.c_float), ("norm_eps", C.c_float)]
+                ("audio_num_codebooks", C.c_int32), ("rope_base", C.c_float), ("norm_eps", C.c_float),
+                ("max_batch", C.c_int32)]
 
 
 class FrameDecoderB200:
     """``generate_codes(last_h, ...)`` -> ``(B, audio_num_codebooks)`` int32 codes of one frame (llm.py:303-334)."""
 
-    MAX_BATCH = 8
-
-    def __init__(self, cfg: FrameDecoderConfig, state_dict, device="cuda:0"):
+    def __init__(self, cfg: FrameDecoderConfig, state_dict, device="cuda:0", max_batch: int = 8):
+        """``max_batch`` > 8 also keeps row-major weight copies so that frames of up to ``max_batch`` items (a pool of
+        concurrent streams) run on the tcgen05 GEMM; batches <= 8 always use the weight-streaming kernels."""
         import torch
         self._lib = N.load()
         if not torch.cuda.is_available():
@@ -154,8 +155,9 @@ class FrameDecoderB200:
         self.device = torch.device(device)
         self.device_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._h = C.c_void_p()
+        self.max_batch = max(8, int(max_batch))
         c = Frt2FdConfig(cfg.backbone_dim, cfg.dim, cfg.num_layers, cfg.num_heads, cfg.num_kv_heads, cfg.intermediate_dim,
-                         cfg.audio_vocab_size, cfg.audio_num_codebooks, cfg.rope_base, cfg.norm_eps)
+                         cfg.audio_vocab_size, cfg.audio_num_codebooks, cfg.rope_base, cfg.norm_eps, int(max_batch))
         N.check(self._lib.frt2_fd_create(C.byref(c), self.device_index, C.byref(self._h)))
         for key in frame_decoder_keys(cfg):
             if key not in state_dict:
@@ -178,7 +180,7 @@ class FrameDecoderB200:
             pass
 
     @classmethod
-    def from_reference(cls, model, device="cuda:0") -> "FrameDecoderB200":
+    def from_reference(cls, model, device="cuda:0", max_batch: int = 8) -> "FrameDecoderB200":
         """Build from a live reference ``Model`` (llm.py:85): widths from its modules, tensors from its state_dict."""
         sd = {k: v for k, v in model.state_dict().items()}
         n_layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("decoder.layers."))
@@ -192,7 +194,7 @@ class FrameDecoderB200:
                                  num_kv_heads=kv_total // hd, intermediate_dim=sd["decoder.layers.0.mlp.w1.weight"].shape[0],
                                  audio_vocab_size=model.config.audio_vocab_size,
                                  audio_num_codebooks=model.config.audio_num_codebooks)
-        return cls(cfg, sd, device)
+        return cls(cfg, sd, device, max_batch)
 
     def check_error(self):
         """Synchronise and raise IndexError if a given code was outside ``[0, audio_vocab_size)`` since the last check (the
@@ -214,8 +216,8 @@ class FrameDecoderB200:
         if last_h.dim() != 2 or last_h.shape[1] != cfg.backbone_dim:
             raise ValueError(f"last_h must be (B, {cfg.backbone_dim}), got {tuple(last_h.shape)}")
         B = last_h.shape[0]
-        if not 1 <= B <= self.MAX_BATCH:
-            raise ValueError(f"batch {B} outside 1..{self.MAX_BATCH}")
+        if not 1 <= B <= self.max_batch:
+            raise ValueError(f"batch {B} outside 1..{self.max_batch} (max_batch of the constructor)")
         if topk < 1:
             raise ValueError("topk must be >= 1")
         last_h = last_h.to(device=dev, dtype=torch.float32).contiguous()

@@ -243,6 +243,9 @@ typedef struct {
   int32_t audio_num_codebooks;
   float rope_base;             /* 1e6 (modules.py:16) */
   float norm_eps;              /* 1e-6 (modules.py:15) */
+  int32_t max_batch;           /* 0 / <= 8: frames of up to 8 items (weight-streaming kernels only).  > 8 (<= 1024): also keeps
+                                  row-major weight copies and runs larger batches — a pool of concurrent streams — on the
+                                  tcgen05 GEMM (widths must be multiples of 64) */
 } frt2_fd_config;
 typedef struct frt2_frame_decoder frt2_frame_decoder;
 int frt2_fd_create(const frt2_fd_config* cfg, int device, frt2_frame_decoder** out);
@@ -254,7 +257,7 @@ int frt2_fd_load_tensor(frt2_frame_decoder* f, const char* key, const float* dat
                         int on_device);
 int frt2_fd_finalize(frt2_frame_decoder* f);
 void frt2_fd_destroy(frt2_frame_decoder* f);
-/* One frame for B <= 8 items.  last_h: device fp32 (B, backbone_dim) = h[:, -1, :] of the backbone (llm.py:302).
+/* One frame for B <= max(8, max_batch) items.  last_h: device fp32 (B, backbone_dim) = h[:, -1, :] of the backbone (llm.py:302).
  * c0: optional device int32 (B) codebook-0 codes sampled by the caller (NULL: sampled here with topk / temperature).
  * noise: optional device fp32 (B, ncb, V), the Exp(1) draws q of _multinomial_sample_one_no_sync (llm.py:34-36) per
  * codebook (parity tests feed the reference's own draws); NULL: counter-based Philox draws keyed by (seed, frame counter

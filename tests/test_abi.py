@@ -54,11 +54,11 @@ def test_frame_decoder_arguments_are_validated_without_a_gpu(lib):
     from fireredtts2_b200.frame_decoder import Frt2FdConfig
     h = C.c_void_p()
     assert lib.frt2_fd_create(None, 0, C.byref(h)) == N.ERR_BAD_ARG
-    bad = Frt2FdConfig(1536, 1536, 4, 12, 5, 8960, 2048, 16, 1e6, 1e-6)        # kv heads do not divide heads
+    bad = Frt2FdConfig(1536, 1536, 4, 12, 5, 8960, 2048, 16, 1e6, 1e-6, 0)        # kv heads do not divide heads
     assert lib.frt2_fd_create(C.byref(bad), 0, C.byref(h)) == N.ERR_BAD_ARG
-    bad = Frt2FdConfig(1536, 1530, 4, 12, 2, 8960, 2048, 16, 1e6, 1e-6)        # dim not a multiple of 8
+    bad = Frt2FdConfig(1536, 1530, 4, 12, 2, 8960, 2048, 16, 1e6, 1e-6, 0)        # dim not a multiple of 8
     assert lib.frt2_fd_create(C.byref(bad), 0, C.byref(h)) == N.ERR_BAD_ARG
-    bad = Frt2FdConfig(1536, 1536, 4, 12, 2, 8960, 2048, 1, 1e6, 1e-6)         # fewer than two codebooks
+    bad = Frt2FdConfig(1536, 1536, 4, 12, 2, 8960, 2048, 1, 1e6, 1e-6, 0)         # fewer than two codebooks
     assert lib.frt2_fd_create(C.byref(bad), 0, C.byref(h)) == N.ERR_BAD_ARG
     assert lib.frt2_fd_finalize(None) == N.ERR_BAD_ARG
     assert lib.frt2_fd_generate(None, None, 1, None, None, 0, 10, 1.0, None, None, None, None, None) == N.ERR_BAD_ARG

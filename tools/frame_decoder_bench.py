@@ -17,7 +17,7 @@ from fireredtts2_b200.frame_decoder import (FD_PRESETS, FrameDecoderB200, synthe
 
 def run(preset="FD_200M", batch=1, frames=50, warmup=5, peak_gbs=None):
     cfg = FD_PRESETS[preset]
-    fd = FrameDecoderB200(cfg, synthetic_frame_decoder_state_dict(cfg, 0))
+    fd = FrameDecoderB200(cfg, synthetic_frame_decoder_state_dict(cfg, 0), max_batch=max(8, batch))
     last_h, _ = synthetic_frame_inputs(cfg, batch, 0)
     last_h = torch.from_numpy(last_h).cuda()
     for _ in range(warmup):
