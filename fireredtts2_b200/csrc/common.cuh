@@ -135,6 +135,8 @@ struct GemmDesc {
   const float* ln_beta;
   float ln_eps;
   int ln_silu;
+  int narrow_tiles;       // gemm_tc hint: 128-column tiles unless 256-column tiles would already fill every SM (few-row,
+                          // weight-streaming-bound GEMMs of the frame tail's large-batch path)
   int ln_rms;             // 1: RMSNorm (no mean subtraction, no beta: ln_beta may be null) — the frame decoder's norms
 };
 

@@ -680,7 +680,7 @@ int FrameDecoder::tc(const __half* A, int K, const __half* W, int N, const float
   GemmDesc g{};
   g.A = A; g.a_row_pitch = K; g.a_batch_pitch = 0; g.rows_a = rows; g.batches = 1; g.Kc = K; g.ntaps = 1; g.row_shift = 0;
   g.W = W; g.N = N; g.rows_out = rows; g.alpha = 1.0f; g.bias = bias; g.act = ACT_NONE; g.resid = resid; g.out32 = out32;
-  g.ld32 = ld32; g.out16 = out16; g.ld16 = ld16;
+  g.ld32 = ld32; g.out16 = out16; g.ld16 = ld16; g.narrow_tiles = 1;
   ++launches;
   return gemm_tc(g, st);
 }

@@ -799,7 +799,8 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   const int groups = packed ? (g.batches + pack_items - 1) / pack_items : g.batches;
   // few row tiles (latency-bound steps): narrower N tiles put more SMs on the weight stream
   const long long row_tiles = packed ? groups : static_cast<long long>(g.batches) * ((g.rows_out + BM - 1) / BM);
-  const int BN = (g.N >= 512 && row_tiles * ((g.N + 255) / 256) >= 64) ? 256 : 128;
+  const long long tiles256 = row_tiles * ((g.N + 255) / 256);
+  const int BN = (g.N >= 512 && tiles256 >= (g.narrow_tiles ? num_sms() : 64)) ? 256 : 128;
   // CTA pairs (256 x 256 tiles) for the large GEMMs; FRT2_GEMM_1CTA=1 forces the single-CTA kernel (A/B testing)
   static const bool force_1cta = (getenv("FRT2_GEMM_1CTA") != nullptr);
   const bool pair = !force_1cta && BN == 256 && g.rows_out >= 256 && g.out_row_off == nullptr;
