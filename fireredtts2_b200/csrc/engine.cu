@@ -2221,6 +2221,32 @@ int frt2_op_gemm(int impl, const void* A16, const void* W16, int batches, int ro
     FRT2_TRY(gemm_skinny_init());
     return gemm_skinny(g, st);
   }
+  if (impl == 3) {   // K2w: the weights are repacked here (tile-blocked order), test-only convenience; synchronises
+    FRT2_REQUIRE(batches == 1 && ntaps == 1 && alpha == 1.0f && gemm_stream_applicable(N, Kc, rows_per_batch), FRT2_ERR_BAD_ARG,
+                 "frt2_op_gemm(impl 3): one batch of <= 8 rows, one tap, alpha 1, K a multiple of 32");
+    FRT2_TRY(gemm_stream_init());
+    const size_t nw = static_cast<size_t>(N) * Kc;
+    std::vector<__half> hw(nw);
+    FRT2_CUDA_OK(cudaMemcpy(hw.data(), W16, nw * 2, cudaMemcpyDeviceToHost));
+    std::vector<float> fw(nw);
+    for (size_t i = 0; i < nw; ++i) fw[i] = __half2float(hw[i]);
+    std::vector<__half> packed(gemm_stream_packed_elems(N, Kc));
+    gemm_stream_pack_host(fw.data(), N, Kc, packed.data());
+    __half* dw = nullptr;
+    FRT2_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&dw), packed.size() * 2));
+    cudaError_t e = cudaMemcpy(dw, packed.data(), packed.size() * 2, cudaMemcpyHostToDevice);
+    int rc = FRT2_OK;
+    if (e == cudaSuccess) {
+      StreamGemm d{};
+      d.Wt = dw; d.N = N; d.K = Kc; d.B = rows_per_batch; d.A = g.A; d.lda = Kc; d.bias = bias; d.act = act; d.resid = resid;
+      d.out32 = out32; d.ld32 = N; d.out16 = g.out16; d.ld16 = act == ACT_SWIGLU ? N / 2 : N;
+      rc = gemm_stream(d, st);
+      if (rc == FRT2_OK) e = cudaStreamSynchronize(st);
+    }
+    cudaFree(dw);
+    FRT2_CUDA_OK(e);
+    return rc;
+  }
   return impl == 0 ? gemm_tc(g, st) : gemm_ref(g, st);
 }
 

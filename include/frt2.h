@@ -320,7 +320,9 @@ int frt2_profile_get(frt2_handle* h, int cls, double* ms, int64_t* launches, dou
 
 /* ---- single-operator entry points (unit parity tests and per-kernel roofline benches) ---- */
 /* C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias) (+ resid); A,W fp16 device, fp32 accumulate.
- * impl 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT check kernel, 2 = skinny weight-streaming kernel (<= 16 rows).  ntaps > 1: causal conv over `batches` items of
+ * impl 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT check kernel, 2 = skinny weight-streaming kernel (<= 16 rows), 3 = the frame
+ * tail's persistent weight-streaming kernel (one batch of <= 8 rows, K a multiple of 32; act 3 = SwiGLU on interleaved
+ * (gate, up) weight rows: out16 is (rows, N/2); the weights are repacked inside the call, which synchronises).  ntaps > 1: causal conv over `batches` items of
  * rows_per_batch rows, K = ntaps*Kc, zero left padding. */
 int frt2_op_gemm(int impl, const void* A16, const void* W16, int batches, int rows_per_batch, int Kc, int ntaps,
                  int N, float alpha, const float* bias, int act, const float* resid, float* out32, void* out16,

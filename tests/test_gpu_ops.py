@@ -303,6 +303,48 @@ def test_gemm_skinny(lib, case):
     assert (o16.float() - ref).abs().max().item() / scale < 3e-3
 
 
+STREAM_CASES = [
+    # rows, K, N, bias, act (0 none, 1 GELU, 3 SwiGLU on interleaved gate/up rows), resid
+    (1, 1536, 2048, True, 0, False),
+    (1, 1536, 1536, False, 0, True),
+    (8, 1536, 17920, False, 3, False),      # every warp of the grid takes part: 2240 column tiles on 148 x 16 warps
+    (4, 8960, 1536, False, 0, True),        # 280 k-blocks per tile, 192 tiles on 148 CTAs
+    (3, 64, 70, True, 0, False),            # fewer k-blocks than warps, N not a multiple of 8
+    (8, 160, 64, True, 1, True),
+    (2, 32, 8, False, 0, False),
+    (5, 896, 9728, False, 3, False),
+]
+
+
+@pytest.mark.parametrize("case", STREAM_CASES, ids=lambda c: "m%d_k%d_n%d_b%d_a%d_r%d" % c)
+def test_gemm_stream(lib, case):
+    """K2w (gemm_stream.cu) against a torch fp32 reference of the same op on the same fp16-rounded operands."""
+    rows, K, Nn, use_bias, act, use_resid = case
+    g = torch.Generator(device="cuda").manual_seed(11)
+    A = torch.randn(1, rows, K, device="cuda", generator=g).half()
+    W = (torch.randn(Nn, K, device="cuda", generator=g) / math.sqrt(K)).half()
+    bias = torch.randn(Nn, device="cuda", generator=g) * 0.1 if use_bias else None
+    resid = torch.randn(1, rows, Nn, device="cuda", generator=g) if use_resid else None
+    n_out = Nn // 2 if act == 3 else Nn
+    o32 = torch.full((1, rows, Nn), float("nan"), device="cuda") if act != 3 else None
+    o16 = torch.full((1, rows, n_out), float("nan"), device="cuda", dtype=torch.half)
+    _check(lib, lib.frt2_op_gemm(3, _p(A), _p(W), 1, rows, K, 1, Nn, 1.0, _p(bias), act, _p(resid), _p(o32), _p(o16), _stream()))
+    torch.cuda.synchronize()
+    y = A.float() @ W.float().t()
+    if bias is not None:
+        y = y + bias
+    if act == 3:
+        ref = torch.nn.functional.silu(y[..., 0::2]) * y[..., 1::2]
+    else:
+        ref = torch.nn.functional.gelu(y) if act == 1 else y
+        if resid is not None:
+            ref = ref + resid
+    scale = ref.abs().max().item() + 1e-6
+    if o32 is not None:
+        assert (o32 - ref).abs().max().item() / scale < 2e-3
+    assert torch.isfinite(o16.float()).all() and (o16.float() - ref).abs().max().item() / scale < 3e-3
+
+
 def test_fp16_outputs_saturate_instead_of_overflowing(lib):
     """fp32 -> fp16 conversions saturate at +-65504 (F2FP.SATFINITE): no inf / NaN from an out-of-range activation."""
     M, K, Nn = 256, 64, 512
