@@ -82,6 +82,15 @@ def test_frame_decoder_host_side():
         FrameDecoderConfig(dim=100, num_heads=3)
 
 
+def test_frame_decoder_has_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from fireredtts2_b200.frame_decoder import FD_TINY, FrameDecoderB200, synthetic_frame_decoder_state_dict
+    with pytest.raises(RuntimeError):
+        FrameDecoderB200(FD_TINY, synthetic_frame_decoder_state_dict(FD_TINY, 0))
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
