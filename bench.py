@@ -863,7 +863,7 @@ def frame_tail_record(dev, frames=40):
     rec = {"workload": "frame tail of Model.generate_frame (llm.py:303-334): qwen-1.5b-wide backbone state -> 16 codes; "
                        "decoder flavor qwen-200m (4 x 1536, 12 / 2 heads, 8960), V = 2048, random weights; topk 30, T 0.9",
            "weight_bytes_per_frame": cfg.weight_bytes_per_frame()}
-    for B in (1, 8):
+    for B in (1, 8, 16):
         last_h, _ = synthetic_frame_inputs(cfg, B, 0)
         h = torch.from_numpy(last_h).to(dev)
         for _ in range(5):

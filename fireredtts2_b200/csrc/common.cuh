@@ -156,7 +156,7 @@ int gemm_skinny_init();
 // ---- persistent weight-streaming GEMM for <= 8 rows (gemm_stream.cu; the frame tail of the speech LM) ----
 struct StreamGemm {
   const __half* Wt;       // weights in tile-blocked order [ceil(N/8)][K/32][8][32] (gemm_stream_pack_host)
-  int N, K, B;            // K a multiple of 32; B <= 8 rows
+  int N, K, B;            // K a multiple of 32; B <= gemm_stream_max_rows(K) <= 16 rows
   const __half* A;        // fp16 rows (B, K), pitch lda — or, when gamma != null, the rows are RMSNorm(x) * gamma:
   int64_t lda;
   const float* x;         // fp32 rows (B, K), pitch ldx
@@ -174,6 +174,7 @@ struct StreamGemm {
 int gemm_stream(const StreamGemm& d, cudaStream_t stream);
 int gemm_stream_init();
 bool gemm_stream_applicable(int N, int K, int B);
+int gemm_stream_max_rows(int K);       // activation rows of width K one launch can take (<= 16)
 size_t gemm_stream_packed_elems(int64_t N, int64_t K);
 void gemm_stream_pack_host(const float* W, int64_t N, int64_t K, __half* out);
 

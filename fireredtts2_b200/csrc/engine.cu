@@ -2223,7 +2223,7 @@ int frt2_op_gemm(int impl, const void* A16, const void* W16, int batches, int ro
   }
   if (impl == 3) {   // K2w: the weights are repacked here (tile-blocked order), test-only convenience; synchronises
     FRT2_REQUIRE(batches == 1 && ntaps == 1 && alpha == 1.0f && gemm_stream_applicable(N, Kc, rows_per_batch), FRT2_ERR_BAD_ARG,
-                 "frt2_op_gemm(impl 3): one batch of <= 8 rows, one tap, alpha 1, K a multiple of 32");
+                 "frt2_op_gemm(impl 3): one batch of <= 16 rows that fit the kernel's activation tile, one tap, alpha 1, K a multiple of 32");
     FRT2_TRY(gemm_stream_init());
     const size_t nw = static_cast<size_t>(N) * Kc;
     std::vector<__half> hw(nw);

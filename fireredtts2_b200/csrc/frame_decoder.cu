@@ -33,7 +33,7 @@
 namespace frt2 {
 namespace {
 
-constexpr int FD_MAX_BATCH = 8;
+constexpr int FD_MAX_BATCH = 16;      // rows the weight-streaming path takes (the m16 of its MMA tile)
 constexpr int FD_MAX_POS = 64;        // audio_num_codebooks limit (lane t of the attention warp owns positions t and t + 32)
 constexpr int FD_SAMPLE_THREADS = 256;
 
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) fd_attn_kernel(const float* __restrict__ 
   }
 }
 
-// Large-batch path (> 8 items per frame, tcgen05 GEMMs): RMSNorm rows fp32 -> fp16 (one warp per row, the row kept in
+// Large-batch path (> 16 items per frame, tcgen05 GEMMs): RMSNorm rows fp32 -> fp16 (one warp per row, the row kept in
 // registers for widths <= 4096) and silu(gate) * up on the interleaved (gate_j, up_j) columns of the merged GEMM's output
 __global__ void __launch_bounds__(256) fd_rms_rows_kernel(const float* __restrict__ x, int rows, int C,
                                                           const float* __restrict__ gamma, float eps,
@@ -368,7 +368,7 @@ struct FrameDecoder {
   __half* w_head0 = nullptr;     // (V, Db)
   __half* w_heads = nullptr;     // (ncb - 1, V, D): audio_head[i] transposed (K contiguous)
   size_t head_stride = 0;        // elements between two heads
-  bool big = false;              // max_batch > 8: row-major weight copies + tcgen05 GEMMs for frames of 9 .. max_batch items
+  bool big = false;              // max_batch > 16: row-major weight copies + tcgen05 GEMMs for frames of 17 .. max_batch items
   int mb = FD_MAX_BATCH;         // rows the activation buffers hold
   __half *w_proj_rm = nullptr, *w_head0_rm = nullptr, *w_heads_rm = nullptr;
   __half *n16 = nullptr, *gu16 = nullptr;
@@ -462,7 +462,8 @@ int FrameDecoder::finalize() {
   FRT2_TRY(gemm_skinny_init());
   FRT2_TRY(gemm_stream_init());
   use_stream = getenv("FRT2_FD_SKINNY") == nullptr && gemm_stream_applicable(8, cfg.dim, 8) &&
-               gemm_stream_applicable(8, cfg.backbone_dim, 8) && gemm_stream_applicable(8, cfg.intermediate_dim, 8);
+               gemm_stream_applicable(8, cfg.backbone_dim, 8) && gemm_stream_applicable(8, cfg.intermediate_dim, 8) &&
+               gemm_stream_max_rows(cfg.dim) >= 16 && gemm_stream_max_rows(cfg.backbone_dim) >= 16;
   const int D = cfg.dim, Db = cfg.backbone_dim, I = cfg.intermediate_dim, V = cfg.audio_vocab_size, n = cfg.audio_num_codebooks;
   const int H = cfg.num_heads, Hk = cfg.num_kv_heads;
   big = cfg.max_batch > FD_MAX_BATCH;
@@ -583,10 +584,23 @@ int FrameDecoder::skinny(const __half* A, int K, const __half* W, int N, const f
   if (ldx == 0) ldx = K;
   ++launches;
   if (use_stream) {
-    StreamGemm d{};
-    d.Wt = W; d.N = N; d.K = K; d.B = B; d.A = A; d.lda = lda; d.x = ln_x; d.ldx = ldx; d.gamma = ln_gamma; d.eps = cfg.norm_eps;
-    d.bias = bias; d.act = act; d.resid = resid; d.out32 = out32; d.ld32 = ld32; d.out16 = out16; d.ld16 = ld16;
-    return gemm_stream(d, st);
+    // the activation tile of a launch lives in shared memory: K = 8960 leaves room for 10 rows, so a wider batch runs the
+    // layer in two row groups (each streams the weights once)
+    const int fit = gemm_stream_max_rows(K);
+    --launches;
+    for (int r0 = 0; r0 < B; r0 += fit) {
+      StreamGemm d{};
+      d.Wt = W; d.N = N; d.K = K; d.B = std::min(fit, B - r0); d.lda = lda; d.ldx = ldx; d.gamma = ln_gamma; d.eps = cfg.norm_eps;
+      d.A = A != nullptr ? A + r0 * lda : nullptr;
+      d.x = ln_x != nullptr ? ln_x + r0 * ldx : nullptr;
+      d.bias = bias; d.act = act; d.ld32 = ld32; d.ld16 = ld16;
+      d.resid = resid != nullptr ? resid + r0 * ld32 : nullptr;
+      d.out32 = out32 != nullptr ? out32 + r0 * ld32 : nullptr;
+      d.out16 = out16 != nullptr ? out16 + r0 * ld16 : nullptr;
+      ++launches;
+      FRT2_TRY(gemm_stream(d, st));
+    }
+    return FRT2_OK;
   }
   GemmDesc g{};
   g.A = A; g.a_row_pitch = lda; g.a_batch_pitch = 0; g.rows_a = B; g.batches = 1; g.Kc = K; g.ntaps = 1; g.row_shift = 0;
@@ -673,7 +687,7 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
   return FRT2_OK;
 }
 
-// ---- frames of 9 .. max_batch items: the same sequence on the tcgen05 GEMM (128-row tiles; every weight is still
+// ---- frames of 17 .. max_batch items: the same sequence on the tcgen05 GEMM (128-row tiles; every weight is still
 //      streamed once per decoder pass, now shared by up to 128 rows per tile) with RMSNorm / SwiGLU as row kernels
 int FrameDecoder::tc(const __half* A, int K, const __half* W, int N, const float* bias, const float* resid, float* out32,
                      int64_t ld32, __half* out16, int64_t ld16, int rows, cudaStream_t st) {
@@ -780,7 +794,7 @@ int frt2_fd_create(const frt2_fd_config* cfg, int device, frt2_frame_decoder** o
   FRT2_REQUIRE(cfg->max_batch >= 0 && cfg->max_batch <= 1024, FRT2_ERR_BAD_ARG, "frt2_fd_create: max_batch must be in [0, 1024]");
   FRT2_REQUIRE(cfg->max_batch <= FD_MAX_BATCH ||
                    (cfg->dim % 64 == 0 && cfg->backbone_dim % 64 == 0 && cfg->intermediate_dim % 64 == 0 && hd % 8 == 0),
-               FRT2_ERR_BAD_ARG, "frt2_fd_create: max_batch > 8 needs widths that are multiples of 64");
+               FRT2_ERR_BAD_ARG, "frt2_fd_create: max_batch > 16 needs widths that are multiples of 64");
   int ndev = 0;
   FRT2_CUDA_OK(cudaGetDeviceCount(&ndev));
   FRT2_REQUIRE(device >= 0 && device < ndev, FRT2_ERR_BAD_ARG, "frt2_fd_create: bad device index");
@@ -837,7 +851,7 @@ int frt2_fd_generate(frt2_frame_decoder* f, const float* last_h, int B, const in
   FRT2_REQUIRE(f && last_h && codes, FRT2_ERR_BAD_ARG, "frt2_fd_generate: null argument");
   FrameDecoder& d = f->d;
   FRT2_REQUIRE(d.finalized, FRT2_ERR_NOT_FINALIZED, "frt2_fd_generate: call frt2_fd_finalize first");
-  FRT2_REQUIRE(B >= 1 && B <= d.mb, FRT2_ERR_BAD_ARG, "frt2_fd_generate: batch must be in [1, max(8, max_batch)]");
+  FRT2_REQUIRE(B >= 1 && B <= d.mb, FRT2_ERR_BAD_ARG, "frt2_fd_generate: batch must be in [1, max(16, max_batch)]");
   FRT2_REQUIRE(topk >= 1 && temperature > 0.f, FRT2_ERR_BAD_ARG, "frt2_fd_generate: topk >= 1 and temperature > 0 required");
   cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
   std::lock_guard<std::mutex> lk(d.mu);

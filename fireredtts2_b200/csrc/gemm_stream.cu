@@ -51,11 +51,12 @@ __device__ __forceinline__ void gs_cp_async16(void* smem_dst, const void* gsrc) 
 __device__ __forceinline__ void gs_cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ void gs_mma16816(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
-  const uint32_t z = 0u;     // rows 8..15 of the m16 tile are not used
+// a0 / a2: rows 0..7 of the m16 tile, a1 / a3: rows 8..15 (zero when the launch has <= 8 rows)
+__device__ __forceinline__ void gs_mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                            uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-               : "r"(a0), "r"(z), "r"(a2), "r"(z), "r"(b0), "r"(b1));
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 // streaming load: the weights are read once per launch, keep them out of L1
 __device__ __forceinline__ uint4 gs_ldw(const uint4* p) {
@@ -96,7 +97,8 @@ __device__ __forceinline__ void gs_emit(const StreamGemm& d, int m, int n, float
   }
 }
 
-template <bool SPLIT>
+// MR = 8: up to 8 activation rows (rows 8..15 of the MMA tile idle); MR = 16: up to 16
+template <bool SPLIT, int MR>
 __global__ void __launch_bounds__(GS_WARPS * 32, GS_MIN_CTAS) gemm_stream_kernel(StreamGemm d) {
   extern __shared__ __align__(16) uint8_t gs_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(GS_WARPS * 32, GS_MIN_CTAS) gemm_stream_kernel
   const int T = (d.N + 7) >> 3;            // column tiles
   const int pitch = d.K + GS_PAD;
   __half* sA = reinterpret_cast<__half*>(gs_smem);                                            // [B][pitch]
-  float* sRed = reinterpret_cast<float*>(gs_smem + static_cast<size_t>(d.B) * pitch * 2);     // SPLIT: [2][GS_WARPS][64]
+  float* sRed = reinterpret_cast<float*>(gs_smem + static_cast<size_t>(d.B) * pitch * 2);     // SPLIT: [2][GS_WARPS][MR * 8]
 
   // ---- this warp's segments: (tile, blocks [kb0, kb1)); consecutive segments are `tstep` tiles apart
   int tile0, ntiles, tstep, kb0, kb1;
@@ -187,20 +189,23 @@ __global__ void __launch_bounds__(GS_WARPS * 32, GS_MIN_CTAS) gemm_stream_kernel
 
   // ---- the stream
   const __half* arow = sA + static_cast<size_t>(gq < d.B ? gq : 0) * pitch + tq * 8;   // rows >= B: results never stored
+  const __half* arow_hi = sA + static_cast<size_t>(gq + 8 < d.B ? gq + 8 : 0) * pitch + tq * 8;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  // end of segment c_seg: acc[0], acc[1] = row gq, columns 2tq, 2tq+1 of the tile (this warp's share of K when SPLIT)
+  // end of segment c_seg: acc[0], acc[1] = row gq, columns 2tq, 2tq+1 of the tile, acc[2], acc[3] = row gq + 8 (this
+  // warp's share of K when SPLIT)
   auto finish = [&](int c_seg) {
     const int tile = tile0 + c_seg * tstep;
     if (SPLIT) {
-      float* r = sRed + ((c_seg & 1) * GS_WARPS + warp) * 64;
+      float* r = sRed + ((c_seg & 1) * GS_WARPS + warp) * (MR * 8);
       *reinterpret_cast<float2*>(r + gq * 8 + 2 * tq) = make_float2(acc[0], acc[1]);
+      if (MR == 16) *reinterpret_cast<float2*>(r + (gq + 8) * 8 + 2 * tq) = make_float2(acc[2], acc[3]);
       __syncthreads();   // one barrier per tile: the buffer of tile i is rewritten for tile i+2, behind barrier i+1
-      if (tid < 32) {    // thread -> (row, column pair); fixed summation order over the warps
-        const float* rr = sRed + (c_seg & 1) * GS_WARPS * 64 + tid * 2;
+      if (tid < MR * 4) {    // thread -> (row, column pair); fixed summation order over the warps
+        const float* rr = sRed + (c_seg & 1) * GS_WARPS * (MR * 8) + tid * 2;
         float v0 = 0.f, v1 = 0.f;
 #pragma unroll
         for (int ww = 0; ww < GS_WARPS; ++ww) {
-          const float2 pv = *reinterpret_cast<const float2*>(rr + ww * 64);
+          const float2 pv = *reinterpret_cast<const float2*>(rr + ww * (MR * 8));
           v0 += pv.x;
           v1 += pv.y;
         }
@@ -208,6 +213,7 @@ __global__ void __launch_bounds__(GS_WARPS * 32, GS_MIN_CTAS) gemm_stream_kernel
       }
     } else {
       gs_emit(d, gq, tile * 8 + 2 * tq, acc[0], acc[1]);
+      if (MR == 16) gs_emit(d, gq + 8, tile * 8 + 2 * tq, acc[2], acc[3]);
     }
     acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
   };
@@ -224,8 +230,10 @@ __global__ void __launch_bounds__(GS_WARPS * 32, GS_MIN_CTAS) gemm_stream_kernel
         const uint4 w = ring[u];
         ring[u] = next_load();
         const uint4 x = *reinterpret_cast<const uint4*>(arow + c_kb * 32);
-        gs_mma16816(acc, x.x, x.y, w.x, w.y);
-        gs_mma16816(acc, x.z, x.w, w.z, w.w);
+        uint4 y = make_uint4(0u, 0u, 0u, 0u);
+        if (MR == 16) y = *reinterpret_cast<const uint4*>(arow_hi + c_kb * 32);
+        gs_mma16816(acc, x.x, y.x, x.y, y.y, w.x, w.y);
+        gs_mma16816(acc, x.z, y.z, x.w, y.w, w.z, w.w);
         ++done;
         if (++c_kb == kb1) {
           finish(c_seg);
@@ -257,23 +265,32 @@ void gemm_stream_pack_host(const float* W, int64_t N, int64_t K, __half* out) {
 
 size_t gemm_stream_packed_elems(int64_t N, int64_t K) { return static_cast<size_t>((N + 7) / 8) * 8 * K; }
 
+// rows of width K the activation tile can hold next to the reduction buffers (<= 16)
+int gemm_stream_max_rows(int K) {
+  const long long room = 200 * 1024 - 2 * GS_WARPS * 128 * 4;
+  return static_cast<int>(std::min<long long>(16, room / (static_cast<long long>(K + GS_PAD) * 2)));
+}
+
 bool gemm_stream_applicable(int N, int K, int B) {
-  return B >= 1 && B <= 8 && K % 32 == 0 && K >= 32 && static_cast<size_t>(8) * (K + GS_PAD) * 2 + 2 * GS_WARPS * 64 * 4 <= 200 * 1024;
+  return B >= 1 && K % 32 == 0 && K >= 32 && B <= gemm_stream_max_rows(K);
 }
 
 int gemm_stream_init() {
-  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_stream_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_stream_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_stream_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  FRT2_CUDA_OK(cudaFuncSetAttribute(gemm_stream_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return FRT2_OK;
 }
 
 int gemm_stream(const StreamGemm& d, cudaStream_t stream) {
-  FRT2_REQUIRE(gemm_stream_applicable(d.N, d.K, d.B), FRT2_ERR_BAD_ARG, "gemm_stream: B in [1, 8], K a multiple of 32 required");
+  FRT2_REQUIRE(gemm_stream_applicable(d.N, d.K, d.B), FRT2_ERR_BAD_ARG, "gemm_stream: K a multiple of 32 and at most gemm_stream_max_rows(K) <= 16 rows required");
   FRT2_REQUIRE(d.gamma != nullptr ? (d.x != nullptr && d.ldx % 4 == 0) : (d.A != nullptr && d.lda % 8 == 0), FRT2_ERR_BAD_ARG,
                "gemm_stream: activation operand missing or misaligned");
   static const int sms = num_sms();
   const int T = (d.N + 7) / 8;
-  const size_t smem = static_cast<size_t>(d.B) * (d.K + GS_PAD) * 2 + 2 * GS_WARPS * 64 * 4;
+  const int MR = d.B > 8 ? 16 : 8;
+  const size_t smem = static_cast<size_t>(d.B) * (d.K + GS_PAD) * 2 + 2 * GS_WARPS * (MR * 8) * 4;
   // GS_CTAS_PER_SM CTAs per SM while their shared memory fits next to the same number of CTAs of the NEXT launch
   const int per_sm = (GS_CTAS_PER_SM > 1 && smem * 2 * GS_CTAS_PER_SM <= 200 * 1024) ? GS_CTAS_PER_SM : 1;
   const int ctas = sms * per_sm;
@@ -289,8 +306,13 @@ int gemm_stream(const StreamGemm& d, cudaStream_t stream) {
   static const bool use_pdl = (getenv("FRT2_NO_PDL") == nullptr);
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  if (split) FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_stream_kernel<true>, d));
-  else FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_stream_kernel<false>, d));
+  if (MR == 8) {
+    if (split) FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_stream_kernel<true, 8>, d));
+    else FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_stream_kernel<false, 8>, d));
+  } else {
+    if (split) FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_stream_kernel<true, 16>, d));
+    else FRT2_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_stream_kernel<false, 16>, d));
+  }
   FRT2_CUDA_OK(cudaGetLastError());
   return FRT2_OK;
 }

@@ -145,8 +145,8 @@ class FrameDecoderB200:
     """``generate_codes(last_h, ...)`` -> ``(B, audio_num_codebooks)`` int32 codes of one frame (llm.py:303-334)."""
 
     def __init__(self, cfg: FrameDecoderConfig, state_dict, device="cuda:0", max_batch: int = 8):
-        """``max_batch`` > 8 also keeps row-major weight copies so that frames of up to ``max_batch`` items (a pool of
-        concurrent streams) run on the tcgen05 GEMM; batches <= 8 always use the weight-streaming kernels."""
+        """Frames of up to 16 items always run on the weight-streaming kernels; ``max_batch`` > 16 also keeps row-major weight
+        copies so that frames of up to ``max_batch`` items (a pool of concurrent streams) run on the tcgen05 GEMM."""
         import torch
         self._lib = N.load()
         if not torch.cuda.is_available():
@@ -155,7 +155,7 @@ class FrameDecoderB200:
         self.device = torch.device(device)
         self.device_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._h = C.c_void_p()
-        self.max_batch = max(8, int(max_batch))
+        self.max_batch = max(16, int(max_batch))
         c = Frt2FdConfig(cfg.backbone_dim, cfg.dim, cfg.num_layers, cfg.num_heads, cfg.num_kv_heads, cfg.intermediate_dim,
                          cfg.audio_vocab_size, cfg.audio_num_codebooks, cfg.rope_base, cfg.norm_eps, int(max_batch))
         N.check(self._lib.frt2_fd_create(C.byref(c), self.device_index, C.byref(self._h)))

@@ -243,7 +243,7 @@ typedef struct {
   int32_t audio_num_codebooks;
   float rope_base;             /* 1e6 (modules.py:16) */
   float norm_eps;              /* 1e-6 (modules.py:15) */
-  int32_t max_batch;           /* 0 / <= 8: frames of up to 8 items (weight-streaming kernels only).  > 8 (<= 1024): also keeps
+  int32_t max_batch;           /* 0 / <= 16: frames of up to 16 items (weight-streaming kernels only).  > 16 (<= 1024): also keeps
                                   row-major weight copies and runs larger batches — a pool of concurrent streams — on the
                                   tcgen05 GEMM (widths must be multiples of 64) */
 } frt2_fd_config;
@@ -257,7 +257,7 @@ int frt2_fd_load_tensor(frt2_frame_decoder* f, const char* key, const float* dat
                         int on_device);
 int frt2_fd_finalize(frt2_frame_decoder* f);
 void frt2_fd_destroy(frt2_frame_decoder* f);
-/* One frame for B <= max(8, max_batch) items.  last_h: device fp32 (B, backbone_dim) = h[:, -1, :] of the backbone (llm.py:302).
+/* One frame for B <= max(16, max_batch) items.  last_h: device fp32 (B, backbone_dim) = h[:, -1, :] of the backbone (llm.py:302).
  * c0: optional device int32 (B) codebook-0 codes sampled by the caller (NULL: sampled here with topk / temperature).
  * noise: optional device fp32 (B, ncb, V), the Exp(1) draws q of _multinomial_sample_one_no_sync (llm.py:34-36) per
  * codebook (parity tests feed the reference's own draws); NULL: counter-based Philox draws keyed by (seed, frame counter
@@ -321,7 +321,7 @@ int frt2_profile_get(frt2_handle* h, int cls, double* ms, int64_t* launches, dou
 /* ---- single-operator entry points (unit parity tests and per-kernel roofline benches) ---- */
 /* C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias) (+ resid); A,W fp16 device, fp32 accumulate.
  * impl 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT check kernel, 2 = skinny weight-streaming kernel (<= 16 rows), 3 = the frame
- * tail's persistent weight-streaming kernel (one batch of <= 8 rows, K a multiple of 32; act 3 = SwiGLU on interleaved
+ * tail's persistent weight-streaming kernel (one batch of <= 16 rows that fit its shared-memory tile, K a multiple of 32; act 3 = SwiGLU on interleaved
  * (gate, up) weight rows: out16 is (rows, N/2); the weights are repacked inside the call, which synchronises).  ntaps > 1: causal conv over `batches` items of
  * rows_per_batch rows, K = ntaps*Kc, zero left padding. */
 int frt2_op_gemm(int impl, const void* A16, const void* W16, int batches, int rows_per_batch, int Kc, int ntaps,

@@ -51,8 +51,8 @@ def test_frame_tail_vs_reference_golden(name, preset):
     print(f"[parity] {name}: free-running codes equal to the reference's: {int(same.sum())} / {same.size}")
     assert same.all()
     # staging + codebook-0 head + per decoder pass (projection, 5 kernels per layer) + sampler per codebook + head per
-    # codebook >= 1; positions 0 and 1 are ONE pass while 2 B rows fit the GEMM's 8
-    passes = cfg.audio_num_codebooks - (1 if 2 * last_h.shape[0] <= 8 else 0)
+    # codebook >= 1; positions 0 and 1 are ONE pass while 2 B rows fit the GEMM's 16
+    passes = cfg.audio_num_codebooks - (1 if 2 * last_h.shape[0] <= 16 else 0)
     assert fd.last_launches == 1 + 1 + passes * (1 + 5 * cfg.num_layers) + cfg.audio_num_codebooks + (cfg.audio_num_codebooks - 1)
 
 
@@ -75,24 +75,24 @@ def test_given_c0_and_batch_independence():
 
 
 def test_two_row_first_pass_and_single_row_layout_agree():
-    """Batch <= 4: positions 0 and 1 run as one two-row pass; batch > 4: one position per pass.  The single-row layout
-    against the oracle (teacher-forced), then the same items through both layouts: GEMM rows and attention queries are
-    independent, so codes and logits are identical bit for bit."""
+    """Batch <= 8: positions 0 and 1 run as one two-row pass (2 B rows fit the MMA tile's 16); batch 9..16: one position
+    per pass.  The single-row layout against the oracle (teacher-forced), then the same items through both layouts: GEMM
+    rows and attention queries are independent, so codes and logits are identical bit for bit."""
     cfg, sd, fd = build("FD_SMALL", 5)
-    last_h, noise = synthetic_frame_inputs(cfg, 6, seed=11)
+    last_h, noise = synthetic_frame_inputs(cfg, 11, seed=11)
     ref_codes, ref_logits = FO.generate_codes(sd, cfg, last_h, 20, 0.9, noise)
     n, L = cfg.audio_num_codebooks, cfg.num_layers
-    _, forced6 = fd.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise), forced=cuda(ref_codes), return_logits=True)
+    _, forced = fd.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise), forced=cuda(ref_codes), return_logits=True)
     assert fd.last_launches == 2 + n * (1 + 5 * L) + n + (n - 1)                 # one position per pass
-    _, snr = report("FD_SMALL batch 6 (one position per pass) logits", ref_logits, to_np(forced6))
+    _, snr = report("FD_SMALL batch 11 (one position per pass, 16-row MMA tiles) logits", ref_logits, to_np(forced))
     assert snr >= SNR_GATE_DB
-    codes6, logits6 = fd.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise), return_logits=True)
-    codes2, logits2 = fd.generate_codes(cuda(last_h[4:6]), 20, 0.9, noise=cuda(noise[4:6]), return_logits=True)
+    codes11, logits11 = fd.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise), return_logits=True)
+    codes3, logits3 = fd.generate_codes(cuda(last_h[8:11]), 20, 0.9, noise=cuda(noise[8:11]), return_logits=True)
     assert fd.last_launches == 2 + (n - 1) * (1 + 5 * L) + n + (n - 1)           # positions 0 and 1 in one pass
-    assert torch.equal(codes2, codes6[4:6]) and torch.equal(logits2, logits6[4:6])
-    same = (codes6.cpu().numpy() == ref_codes).all(axis=1)
-    print(f"[parity] FD_SMALL batch 6: free-running frames identical to the oracle's: {int(same.sum())} / {same.size}")
-    assert same.sum() >= 4          # a frame may leave the oracle's trajectory at an fp16-vs-fp32 near-tie of the sampler
+    assert torch.equal(codes3, codes11[8:11]) and torch.equal(logits3, logits11[8:11])
+    same = (codes11.cpu().numpy() == ref_codes).all(axis=1)
+    print(f"[parity] FD_SMALL batch 11: free-running frames identical to the oracle's: {int(same.sum())} / {same.size}")
+    assert same.sum() >= 8          # a frame may leave the oracle's trajectory at an fp16-vs-fp32 near-tie of the sampler
 
 
 def test_qwen_500m_decoder_flavor():
@@ -110,8 +110,8 @@ def test_qwen_500m_decoder_flavor():
 
 
 def test_large_batch_runs_on_the_tcgen05_gemm():
-    """max_batch > 8: frames of 9 .. max_batch items (a pool of concurrent streams) take the tcgen05 GEMM path (row-major
-    weight copies, RMSNorm / SwiGLU row kernels); against the oracle, and the same items through the <= 8 path."""
+    """max_batch > 16: frames of 17 .. max_batch items (a pool of concurrent streams) take the tcgen05 GEMM path (row-major
+    weight copies, RMSNorm / SwiGLU row kernels); against the oracle, and the same items through the <= 16 path."""
     cfg = FD_PRESETS["FD_SMALL"]
     sd = synthetic_frame_decoder_state_dict(cfg, 5)
     fd = FrameDecoderB200(cfg, sd, max_batch=40)

@@ -313,6 +313,10 @@ STREAM_CASES = [
     (8, 160, 64, True, 1, True),
     (2, 32, 8, False, 0, False),
     (5, 896, 9728, False, 3, False),
+    (16, 1536, 2048, True, 0, True),        # 9..16 rows: both halves of the m16 tile
+    (12, 1536, 17920, False, 3, False),
+    (10, 8960, 1536, False, 0, True),       # the widest activation tile that fits (10 rows of 8960)
+    (9, 64, 70, True, 1, False),
 ]
 
 
