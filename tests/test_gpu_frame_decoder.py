@@ -226,3 +226,35 @@ def test_codes_feed_the_codec_step_on_the_device():
         ref.append(a)
     _, snr = report("frame tail -> codec step audio", np.concatenate(ref, axis=1), to_np(torch.cat(chunks, dim=1)))
     assert snr >= SNR_GATE_DB
+
+
+def test_frame_tail_feeds_a_pool_of_concurrent_streams():
+    """One frame for all slots -> frt2_pool_step: every slot's chunks equal the oracle's streaming decode of that slot's
+    codes (continuous batching behind the frame tail, no host round trip of the codes)."""
+    from fireredtts2_b200 import _native as NN
+    from fireredtts2_b200.codec import RedCodecB200
+    from fireredtts2_b200.config import TINY
+    from fireredtts2_b200.weights import synthetic_state_dict
+    cfg, sd, fd = build("FD_TINY", 3)
+    csd = synthetic_state_dict(TINY, 0)
+    codec = RedCodecB200(TINY, csd, device="cuda:0")
+    nq, slots, steps = TINY.num_quantizers, 3, 4
+    pool = codec.new_pool(slots)
+    rng = np.random.default_rng(10)
+    frames, chunks = [], [[] for _ in range(slots)]
+    for i in range(steps):
+        last_h = cuda(rng.standard_normal((slots, cfg.backbone_dim)).astype(np.float32))
+        codes = fd.generate_codes(last_h, 16, 1.0, seed=5)
+        flags = [NN.SLOT_ACTIVE | (NN.SLOT_RESET if i == 0 else 0) | (NN.SLOT_LAST if i == steps - 1 else 0)] * slots
+        out, n = pool.step_dense(codes[:, :nq], flags)
+        frames.append(codes)
+        for s in range(slots):
+            chunks[s].append(out[s, :n[s]])
+    tok = torch.stack(frames, dim=-1)[:, :nq].cpu().numpy().astype(np.int64)       # (slots, nq, steps)
+    for s in range(slots):
+        state, ref = None, []
+        for i in range(steps):
+            a, state = O.decode_chunk(csd, tok[s:s + 1, :, i:i + 1], state, i == steps - 1, TINY.num_heads, TINY.hop_length)
+            ref.append(a)
+        _, snr = report(f"frame tail -> pool slot {s}", np.concatenate(ref, axis=1)[0], to_np(torch.cat(chunks[s])))
+        assert snr >= SNR_GATE_DB
