@@ -135,6 +135,9 @@ struct GemmDesc {
   const float* ln_beta;
   float ln_eps;
   int ln_silu;
+  int w_batch_k;          // gemm_tc (single-CTA tiles, no packing): batch item b multiplies with W[:, b * w_batch_k ...] — with
+                          // a_batch_pitch = Kc this turns `batches` into a split of the reduction (partial sums per batch
+                          // item at pitch32; the frame tail's large-batch down projection)
   int narrow_tiles;       // gemm_tc hint: 128-column tiles unless 256-column tiles would already fill every SM (few-row,
                           // weight-streaming-bound GEMMs of the frame tail's large-batch path)
   int ln_rms;             // 1: RMSNorm (no mean subtraction, no beta: ln_beta may be null) — the frame decoder's norms

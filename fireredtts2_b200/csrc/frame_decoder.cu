@@ -194,6 +194,19 @@ __global__ void __launch_bounds__(256) fd_swiglu_rows_kernel(const __half2* __re
   out[i] = to_half_sat(p.x / (1.0f + expf(-p.x)) * p.y);
 }
 
+// x[r][n] += sum_s part[s][r][n] in the order s = 0, 1, ... (deterministic); four elements per thread
+__global__ void __launch_bounds__(256) fd_splitk_reduce_kernel(const float4* __restrict__ part, long long n4, int S,
+                                                               float4* __restrict__ x) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 a = x[i];
+  for (int s = 0; s < S; ++s) {
+    const float4 v = part[s * n4 + i];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  x[i] = a;
+}
+
 // Philox-4x32-10 (counter-based: the draw of (frame, item, codebook, entry) does not depend on launch geometry)
 __device__ __forceinline__ float fd_exp1_draw(unsigned long long seed, unsigned long long frame, int b, int s, int v) {
   uint32_t c0 = static_cast<uint32_t>(v), c1 = static_cast<uint32_t>(s) | (static_cast<uint32_t>(b) << 16);
@@ -372,6 +385,20 @@ struct FrameDecoder {
   int mb = FD_MAX_BATCH;         // rows the activation buffers hold
   __half *w_proj_rm = nullptr, *w_head0_rm = nullptr, *w_heads_rm = nullptr;
   __half *n16 = nullptr, *gu16 = nullptr;
+  float* part32 = nullptr;       // partial sums of a GEMM whose reduction is split over CTAs (large batches, narrow N)
+  int down_split = 1;            // the largest split (batch <= 128)
+  // down projection of the large-batch path: (rows / 128) x (D / 128) tiles would leave most SMs idle on the longest
+  // reduction of the layer; split K over S = the largest divisor of its k-blocks that keeps >= 4 blocks per split and
+  // tiles * S <= SMs
+  int pick_down_split(int B) const {
+    const int I = cfg.intermediate_dim, D = cfg.dim;
+    if (getenv("FRT2_FD_NO_SPLITK") != nullptr || I < 4096) return 1;
+    const int kblocks = I / 64, tiles = ((B + 127) / 128) * ((D + 127) / 128);
+    int best = 1;
+    for (int sdiv = 1; sdiv <= kblocks; ++sdiv)
+      if (kblocks % sdiv == 0 && kblocks / sdiv >= 4 && tiles * sdiv <= num_sms()) best = sdiv;
+    return best;
+  }
   __half* emb16 = nullptr;       // (ncb * V, Db)
   float* g_final = nullptr;
   float *rope_cos = nullptr, *rope_sin = nullptr;     // (ncb, hd / 2)
@@ -564,6 +591,8 @@ int FrameDecoder::finalize() {
   if (big) {
     FRT2_TRY(dev_alloc(&n16, static_cast<size_t>(mb) * std::max(D, Db)));
     FRT2_TRY(dev_alloc(&gu16, static_cast<size_t>(mb) * 2 * I));
+    down_split = pick_down_split(1);     // the largest split any batch size uses sizes the partial-sum buffer
+    if (down_split > 1) FRT2_TRY(dev_alloc(&part32, static_cast<size_t>(down_split) * mb * D));
   }
   FRT2_TRY(dev_alloc(&params, 1));
   FRT2_TRY(dev_alloc(&err_word, 1));
@@ -733,7 +762,24 @@ int FrameDecoder::enqueue_frame_big(int B, cudaStream_t st) {
       fd_swiglu_rows_kernel<<<static_cast<unsigned>((ne + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half2*>(gu16), ne, h16);
       FRT2_CUDA_OK(cudaGetLastError());
       ++launches;
-      FRT2_TRY(tc(h16, I, L.w_down_rm, D, nullptr, x32, x32, D, nullptr, 0, B, st));
+      const int S = pick_down_split(B);
+      if (S > 1) {
+        // the reduction split over S batch items of ONE launch, partial sums added to x in a fixed order
+        GemmDesc g{};
+        const int Kc = I / S;
+        g.A = h16; g.a_row_pitch = I; g.a_batch_pitch = Kc; g.rows_a = B; g.batches = S; g.Kc = Kc; g.ntaps = 1;
+        g.W = L.w_down_rm; g.w_batch_k = Kc; g.N = D; g.rows_out = B; g.alpha = 1.0f; g.act = ACT_NONE;
+        g.out32 = part32; g.ld32 = D; g.pitch32 = static_cast<int64_t>(B) * D; g.narrow_tiles = 1;
+        ++launches;
+        FRT2_TRY(gemm_tc(g, st));
+        const long long n4 = static_cast<long long>(B) * D / 4;
+        fd_splitk_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(
+            reinterpret_cast<const float4*>(part32), n4, S, reinterpret_cast<float4*>(x32));
+        FRT2_CUDA_OK(cudaGetLastError());
+        ++launches;
+      } else {
+        FRT2_TRY(tc(h16, I, L.w_down_rm, D, nullptr, x32, x32, D, nullptr, 0, B, st));
+      }
     }
     if (pos >= 1) {                                                                                    // llm.py:322-326
       FRT2_CUDA_OK(rms(g_final));

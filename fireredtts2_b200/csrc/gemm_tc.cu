@@ -71,6 +71,7 @@ struct GemmKParams {
   int pack_items;
   int batches;
   int item_mul;        // first item of tile group g is g * item_mul (pack_items when packed, else 1)
+  int w_batch_k;       // k offset of batch item b in W (split of the reduction over the batch dimension), else 0
   int stage_tx_bytes;  // bytes one pipeline stage receives (A box + W box)
   // folded LayerNorm (see GemmDesc): producer side ...
   __half* x16_out;
@@ -500,7 +501,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int tap = kb / p.kblocks_per_tap;
           const int c0 = (kb - tap * p.kblocks_per_tap) * BK;
           ptx::tma_load_3d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], c0, m0 + tap + p.row_shift, b);
-          ptx::tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK, n_idx * BN);
+          ptx::tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * BK + b * p.w_batch_k, n_idx * BN);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -794,7 +795,7 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   // Packed-item tiles: a batch of items with few rows each (the 8 frames per token of a batch of streams / pool
   // slots) would otherwise get one mostly empty 128-row tile per item, each re-streaming the whole weight panel.
   static const bool no_pack = (getenv("FRT2_GEMM_NOPACK") != nullptr);   // A/B switch for measurements
-  const bool packed = !no_pack && g.batches > 1 && g.rows_out <= BM / 2;
+  const bool packed = !no_pack && g.batches > 1 && g.rows_out <= BM / 2 && g.w_batch_k == 0;
   const int pack_items = packed ? std::min(BM / g.rows_out, g.batches) : 0;
   const int groups = packed ? (g.batches + pack_items - 1) / pack_items : g.batches;
   // few row tiles (latency-bound steps): narrower N tiles put more SMs on the weight stream
@@ -803,7 +804,7 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   const int BN = (g.N >= 512 && tiles256 >= (g.narrow_tiles ? num_sms() : 64)) ? 256 : 128;
   // CTA pairs (256 x 256 tiles) for the large GEMMs; FRT2_GEMM_1CTA=1 forces the single-CTA kernel (A/B testing)
   static const bool force_1cta = (getenv("FRT2_GEMM_1CTA") != nullptr);
-  const bool pair = !force_1cta && BN == 256 && g.rows_out >= 256 && g.out_row_off == nullptr;
+  const bool pair = !force_1cta && BN == 256 && g.rows_out >= 256 && g.out_row_off == nullptr && g.w_batch_k == 0;
   const int BMT = pair ? 2 * BM : BM;           // rows per tile
   const int BNB = pair ? BN / 2 : BN;           // W rows per TMA box
   const uint64_t Ktot = static_cast<uint64_t>(g.ntaps) * g.Kc;
@@ -821,8 +822,9 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
     FRT2_TRY(tma_encode_fp16(&tmA, g.A, 3, dims, strides, box));
   }
   {
-    uint64_t dims[2] = {Ktot, static_cast<uint64_t>(g.N)};
-    uint64_t strides[1] = {Ktot * 2};
+    const uint64_t Kw = Ktot + static_cast<uint64_t>(g.batches - 1) * g.w_batch_k;    // W row length (all reduction splits)
+    uint64_t dims[2] = {Kw, static_cast<uint64_t>(g.N)};
+    uint64_t strides[1] = {Kw * 2};
     uint32_t box[2] = {BK, static_cast<uint32_t>(BNB)};
     FRT2_TRY(tma_encode_fp16(&tmB, g.W, 2, dims, strides, box));
   }
@@ -842,6 +844,7 @@ int gemm_tc(const GemmDesc& g, cudaStream_t stream) {
   p.pack_items = pack_items;
   p.batches = g.batches;
   p.item_mul = packed ? pack_items : 1;
+  p.w_batch_k = g.w_batch_k;
   p.stage_tx_bytes = (packed ? pack_items * g.rows_out * BK * 2 : A_STAGE_BYTES) + BN * BK * 2;
   p.alpha = g.alpha;
   p.bias = g.bias;
