@@ -194,17 +194,22 @@ __global__ void __launch_bounds__(256) fd_swiglu_rows_kernel(const __half2* __re
   out[i] = to_half_sat(p.x / (1.0f + expf(-p.x)) * p.y);
 }
 
-// x[r][n] += sum_s part[s][r][n] in the order s = 0, 1, ... (deterministic); four elements per thread
-__global__ void __launch_bounds__(256) fd_splitk_reduce_kernel(const float4* __restrict__ part, long long n4, int S,
-                                                               float4* __restrict__ x) {
+// dst[r][n] = (accumulate ? dst[r][n] : bias[n] or 0) + sum_s part[s][r][n] in the order s = 0, 1, ... (deterministic); four
+// elements per thread; part rows are N wide, dst rows ld_dst
+__global__ void __launch_bounds__(256) fd_splitk_reduce_kernel(const float4* __restrict__ part, int rows, int N4, int S,
+                                                               const float4* __restrict__ bias, int accumulate,
+                                                               float* __restrict__ dst, long long ld_dst) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n4 = static_cast<long long>(rows) * N4;
   if (i >= n4) return;
-  float4 a = x[i];
+  const int r = static_cast<int>(i / N4), c = static_cast<int>(i - static_cast<long long>(r) * N4);
+  float4* dp = reinterpret_cast<float4*>(dst + r * ld_dst) + c;
+  float4 a = accumulate ? *dp : (bias != nullptr ? __ldg(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f));
   for (int s = 0; s < S; ++s) {
     const float4 v = part[s * n4 + i];
     a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
   }
-  x[i] = a;
+  *dp = a;
 }
 
 // Philox-4x32-10 (counter-based: the draw of (frame, item, codebook, entry) does not depend on launch geometry)
@@ -386,14 +391,14 @@ struct FrameDecoder {
   __half *w_proj_rm = nullptr, *w_head0_rm = nullptr, *w_heads_rm = nullptr;
   __half *n16 = nullptr, *gu16 = nullptr;
   float* part32 = nullptr;       // partial sums of a GEMM whose reduction is split over CTAs (large batches, narrow N)
-  int down_split = 1;            // the largest split (batch <= 128)
-  // down projection of the large-batch path: (rows / 128) x (D / 128) tiles would leave most SMs idle on the longest
-  // reduction of the layer; split K over S = the largest divisor of its k-blocks that keeps >= 4 blocks per split and
-  // tiles * S <= SMs
-  int pick_down_split(int B) const {
-    const int I = cfg.intermediate_dim, D = cfg.dim;
-    if (getenv("FRT2_FD_NO_SPLITK") != nullptr || I < 4096) return 1;
-    const int kblocks = I / 64, tiles = ((B + 127) / 128) * ((D + 127) / 128);
+  // Large-batch path: a layer with N / 128 column tiles per 128 rows leaves most SMs idle (12 tiles for N = 1536); its
+  // reduction is then split over S batch items of ONE launch: S = the largest divisor of the k-blocks that keeps >= 4
+  // blocks per split and tiles * S <= SMs (1 = no split)
+  int pick_split(int rows, int N, int K) const {
+    static const bool off = getenv("FRT2_FD_NO_SPLITK") != nullptr;
+    static const int min_k = getenv("FRT2_FD_SPLITK_MIN_K") != nullptr ? atoi(getenv("FRT2_FD_SPLITK_MIN_K")) : 1024;
+    if (off || K < min_k || N % 4) return 1;
+    const int kblocks = K / 64, tiles = ((rows + 127) / 128) * ((N + 127) / 128);
     int best = 1;
     for (int sdiv = 1; sdiv <= kblocks; ++sdiv)
       if (kblocks % sdiv == 0 && kblocks / sdiv >= 4 && tiles * sdiv <= num_sms()) best = sdiv;
@@ -481,6 +486,8 @@ struct FrameDecoder {
   int enqueue_frame_big(int B, cudaStream_t st);
   int tc(const __half* A, int K, const __half* W, int N, const float* bias, const float* resid, float* out32, int64_t ld32,
          __half* out16, int64_t ld16, int rows, cudaStream_t st);
+  int tc32(const __half* A, int K, const __half* W, int N, const float* bias, bool accumulate, float* dst, int64_t ld_dst,
+           int rows, cudaStream_t st);
   int graph_for(int B, cudaGraphExec_t* out);
 };
 
@@ -591,8 +598,11 @@ int FrameDecoder::finalize() {
   if (big) {
     FRT2_TRY(dev_alloc(&n16, static_cast<size_t>(mb) * std::max(D, Db)));
     FRT2_TRY(dev_alloc(&gu16, static_cast<size_t>(mb) * 2 * I));
-    down_split = pick_down_split(1);     // the largest split any batch size uses sizes the partial-sum buffer
-    if (down_split > 1) FRT2_TRY(dev_alloc(&part32, static_cast<size_t>(down_split) * mb * D));
+    // partial sums: the largest (split x columns) any of the layers uses at any batch size
+    size_t part = 0;
+    const int nk[6][2] = {{D, I}, {D, H * hd}, {qkv, D}, {D, Db}, {V, D}, {V, Db}};
+    for (const auto& e : nk) part = std::max(part, static_cast<size_t>(pick_split(1, e[0], e[1])) * e[0]);
+    FRT2_TRY(dev_alloc(&part32, part * mb));
   }
   FRT2_TRY(dev_alloc(&params, 1));
   FRT2_TRY(dev_alloc(&err_word, 1));
@@ -728,6 +738,27 @@ int FrameDecoder::tc(const __half* A, int K, const __half* W, int N, const float
   return gemm_tc(g, st);
 }
 
+// fp32 result dst = (accumulate ? dst : bias) + A W^T, with the reduction split over CTAs when the layer has too few tiles
+int FrameDecoder::tc32(const __half* A, int K, const __half* W, int N, const float* bias, bool accumulate, float* dst,
+                       int64_t ld_dst, int rows, cudaStream_t st) {
+  const int S = pick_split(rows, N, K);
+  if (S == 1) return tc(A, K, W, N, bias, accumulate ? dst : nullptr, dst, ld_dst, nullptr, 0, rows, st);
+  GemmDesc g{};
+  const int Kc = K / S;
+  g.A = A; g.a_row_pitch = K; g.a_batch_pitch = Kc; g.rows_a = rows; g.batches = S; g.Kc = Kc; g.ntaps = 1;
+  g.W = W; g.w_batch_k = Kc; g.N = N; g.rows_out = rows; g.alpha = 1.0f; g.act = ACT_NONE;
+  g.out32 = part32; g.ld32 = N; g.pitch32 = static_cast<int64_t>(rows) * N; g.narrow_tiles = 1;
+  ++launches;
+  FRT2_TRY(gemm_tc(g, st));
+  const long long n4 = static_cast<long long>(rows) * N / 4;
+  fd_splitk_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(
+      reinterpret_cast<const float4*>(part32), rows, N / 4, S, reinterpret_cast<const float4*>(bias), accumulate ? 1 : 0, dst,
+      ld_dst);
+  FRT2_CUDA_OK(cudaGetLastError());
+  ++launches;
+  return FRT2_OK;
+}
+
 int FrameDecoder::enqueue_frame_big(int B, cudaStream_t st) {
   const int D = cfg.dim, Db = cfg.backbone_dim, I = cfg.intermediate_dim, V = cfg.audio_vocab_size, n = cfg.audio_num_codebooks;
   const int H = cfg.num_heads, Hk = cfg.num_kv_heads;
@@ -744,47 +775,30 @@ int FrameDecoder::enqueue_frame_big(int B, cudaStream_t st) {
     ++launches;
     return cudaGetLastError();
   };
-  FRT2_TRY(tc(in16, Db, w_head0_rm, V, nullptr, nullptr, logits, ldl, nullptr, 0, B, st));           // llm.py:303
+  FRT2_TRY(tc32(in16, Db, w_head0_rm, V, nullptr, false, logits, ldl, B, st));                        // llm.py:303
   for (int pos = 0; pos < n; ++pos) {
-    FRT2_TRY(tc(in16, Db, w_proj_rm, D, nullptr, nullptr, x32, D, nullptr, 0, B, st));                // llm.py:320
+    FRT2_TRY(tc32(in16, Db, w_proj_rm, D, nullptr, false, x32, D, B, st));                             // llm.py:320
     if (pos == 0) FRT2_CUDA_OK(sample(0));
     for (FdLayer& L : layers) {
       FRT2_CUDA_OK(rms(L.g_sa));
-      FRT2_TRY(tc(n16, D, L.w_qkv_rm, qkv, L.b_qkv, nullptr, qkv32, qkv, nullptr, 0, B, st));
+      FRT2_TRY(tc32(n16, D, L.w_qkv_rm, qkv, L.b_qkv, false, qkv32, qkv, B, st));
       fd_attn_kernel<<<dim3(Hk, B), 32 * (H / Hk), 0, st>>>(qkv32, L.kc, L.vc, attn16, rope_cos, rope_sin, H, Hk, hd, n, pos, 1,
                                                              scale);
       FRT2_CUDA_OK(cudaGetLastError());
       ++launches;
-      FRT2_TRY(tc(attn16, H * hd, L.w_o_rm, D, nullptr, x32, x32, D, nullptr, 0, B, st));
+      FRT2_TRY(tc32(attn16, H * hd, L.w_o_rm, D, nullptr, true, x32, D, B, st));
       FRT2_CUDA_OK(rms(L.g_mlp));
       FRT2_TRY(tc(n16, D, L.w_gu_rm, 2 * I, nullptr, nullptr, nullptr, 0, gu16, 2 * I, B, st));
       const long long ne = static_cast<long long>(B) * I;
       fd_swiglu_rows_kernel<<<static_cast<unsigned>((ne + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half2*>(gu16), ne, h16);
       FRT2_CUDA_OK(cudaGetLastError());
       ++launches;
-      const int S = pick_down_split(B);
-      if (S > 1) {
-        // the reduction split over S batch items of ONE launch, partial sums added to x in a fixed order
-        GemmDesc g{};
-        const int Kc = I / S;
-        g.A = h16; g.a_row_pitch = I; g.a_batch_pitch = Kc; g.rows_a = B; g.batches = S; g.Kc = Kc; g.ntaps = 1;
-        g.W = L.w_down_rm; g.w_batch_k = Kc; g.N = D; g.rows_out = B; g.alpha = 1.0f; g.act = ACT_NONE;
-        g.out32 = part32; g.ld32 = D; g.pitch32 = static_cast<int64_t>(B) * D; g.narrow_tiles = 1;
-        ++launches;
-        FRT2_TRY(gemm_tc(g, st));
-        const long long n4 = static_cast<long long>(B) * D / 4;
-        fd_splitk_reduce_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(
-            reinterpret_cast<const float4*>(part32), n4, S, reinterpret_cast<float4*>(x32));
-        FRT2_CUDA_OK(cudaGetLastError());
-        ++launches;
-      } else {
-        FRT2_TRY(tc(h16, I, L.w_down_rm, D, nullptr, x32, x32, D, nullptr, 0, B, st));
-      }
+      FRT2_TRY(tc32(h16, I, L.w_down_rm, D, nullptr, true, x32, D, B, st));
     }
     if (pos >= 1) {                                                                                    // llm.py:322-326
       FRT2_CUDA_OK(rms(g_final));
-      FRT2_TRY(tc(n16, D, w_heads_rm + static_cast<size_t>(pos - 1) * V * D, V, nullptr, nullptr,
-                  logits + static_cast<size_t>(pos) * V, ldl, nullptr, 0, B, st));
+      FRT2_TRY(tc32(n16, D, w_heads_rm + static_cast<size_t>(pos - 1) * V * D, V, nullptr, false,
+                    logits + static_cast<size_t>(pos) * V, ldl, B, st));
       FRT2_CUDA_OK(sample(pos));
     }
   }
