@@ -161,13 +161,13 @@ __global__ void __launch_bounds__(256) fd_attn_kernel(const float* __restrict__ 
 
 // Large-batch path (> 16 items per frame, tcgen05 GEMMs): RMSNorm rows fp32 -> fp16 (one warp per row, the row kept in
 // registers for widths <= 4096) and silu(gate) * up on the interleaved (gate_j, up_j) columns of the merged GEMM's output
-__global__ void __launch_bounds__(256) fd_rms_rows_kernel(const float* __restrict__ x, int rows, int C,
+__global__ void __launch_bounds__(256) fd_rms_rows_kernel(const float* __restrict__ x, long long ldx, int rows, int C,
                                                           const float* __restrict__ gamma, float eps,
                                                           __half* __restrict__ out) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int C4 = C >> 2;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * C);
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<long long>(row) * ldx);
   float q = 0.f;
   for (int c = lane; c < C4; c += 32) {
     const float4 v = xr[c];
@@ -478,6 +478,11 @@ struct FrameDecoder {
     *out = &it->second;
     return FRT2_OK;
   }
+  // positions 0 and 1 as one two-row pass: while 2 B rows fit the weight-streaming kernel's 16, and on the tcgen05 path
+  bool pair_layout(int B) const {
+    static const bool no_pair = getenv("FRT2_FD_NO_PAIR") != nullptr;
+    return !no_pair && (2 * B <= FD_MAX_BATCH || B > FD_MAX_BATCH);
+  }
   int finalize();
   int skinny(const __half* A, int K, const __half* W, int N, const float* bias, int act, const float* resid, float* out32,
              int64_t ld32, __half* out16, int64_t ld16, const float* ln_x, const float* ln_gamma, int B, cudaStream_t st,
@@ -485,9 +490,9 @@ struct FrameDecoder {
   int enqueue_frame(int B, cudaStream_t st);
   int enqueue_frame_big(int B, cudaStream_t st);
   int tc(const __half* A, int K, const __half* W, int N, const float* bias, const float* resid, float* out32, int64_t ld32,
-         __half* out16, int64_t ld16, int rows, cudaStream_t st);
+         __half* out16, int64_t ld16, int rows, cudaStream_t st, int64_t lda = 0);
   int tc32(const __half* A, int K, const __half* W, int N, const float* bias, bool accumulate, float* dst, int64_t ld_dst,
-           int rows, cudaStream_t st);
+           int rows, cudaStream_t st, int64_t lda = 0);
   int graph_for(int B, cudaGraphExec_t* out);
 };
 
@@ -502,6 +507,7 @@ int FrameDecoder::finalize() {
   const int H = cfg.num_heads, Hk = cfg.num_kv_heads;
   big = cfg.max_batch > FD_MAX_BATCH;
   mb = big ? cfg.max_batch : FD_MAX_BATCH;
+  const size_t act_rows = big ? 2 * static_cast<size_t>(mb) : mb;   // the two-row first pass of a large batch
   if (big) FRT2_TRY(gemm_tc_init());
   const HostT* t = nullptr;
   FRT2_TRY(need("projection.weight", &t, {D, Db}));
@@ -587,22 +593,22 @@ int FrameDecoder::finalize() {
     FRT2_TRY(up32(c.data(), c.size(), &rope_cos));
     FRT2_TRY(up32(s.data(), s.size(), &rope_sin));
   }
-  FRT2_TRY(dev_alloc(&in16, static_cast<size_t>(mb) * Db));
-  FRT2_TRY(dev_alloc(&attn16, static_cast<size_t>(mb) * H * hd));
-  FRT2_TRY(dev_alloc(&h16, static_cast<size_t>(mb) * I));
-  FRT2_TRY(dev_alloc(&x32, static_cast<size_t>(mb) * D));
-  FRT2_TRY(dev_alloc(&qkv32, static_cast<size_t>(mb) * qkv));
+  FRT2_TRY(dev_alloc(&in16, static_cast<size_t>(act_rows) * Db));
+  FRT2_TRY(dev_alloc(&attn16, static_cast<size_t>(act_rows) * H * hd));
+  FRT2_TRY(dev_alloc(&h16, static_cast<size_t>(act_rows) * I));
+  FRT2_TRY(dev_alloc(&x32, static_cast<size_t>(act_rows) * D));
+  FRT2_TRY(dev_alloc(&qkv32, static_cast<size_t>(act_rows) * qkv));
   FRT2_TRY(dev_alloc(&logits, static_cast<size_t>(mb) * n * V));
   FRT2_TRY(dev_alloc(&codes, static_cast<size_t>(mb) * n));
   FRT2_TRY(dev_alloc(&given, static_cast<size_t>(mb) * n));
   if (big) {
-    FRT2_TRY(dev_alloc(&n16, static_cast<size_t>(mb) * std::max(D, Db)));
-    FRT2_TRY(dev_alloc(&gu16, static_cast<size_t>(mb) * 2 * I));
+    FRT2_TRY(dev_alloc(&n16, static_cast<size_t>(act_rows) * std::max(D, Db)));
+    FRT2_TRY(dev_alloc(&gu16, static_cast<size_t>(act_rows) * 2 * I));
     // partial sums: the largest (split x columns) any of the layers uses at any batch size
     size_t part = 0;
     const int nk[6][2] = {{D, I}, {D, H * hd}, {qkv, D}, {D, Db}, {V, D}, {V, Db}};
     for (const auto& e : nk) part = std::max(part, static_cast<size_t>(pick_split(1, e[0], e[1])) * e[0]);
-    FRT2_TRY(dev_alloc(&part32, part * mb));
+    FRT2_TRY(dev_alloc(&part32, part * act_rows));
   }
   FRT2_TRY(dev_alloc(&params, 1));
   FRT2_TRY(dev_alloc(&err_word, 1));
@@ -661,8 +667,7 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
   static const int skip = getenv("FRT2_FD_SKIP") != nullptr ? atoi(getenv("FRT2_FD_SKIP")) : 0;
   // positions 0 and 1 as ONE two-row pass while 2 B rows fit the GEMM's 8 (the reference's first decoder call has these
   // two positions too, llm.py:306-321): one weight stream less per frame.  Rows 2b / 2b+1 = position 0 / 1 of item b.
-  static const bool no_pair = getenv("FRT2_FD_NO_PAIR") != nullptr;
-  const bool pair = !no_pair && 2 * B <= FD_MAX_BATCH;
+  const bool pair = pair_layout(B);
   auto sample = [&](int s, __half* dst, int dst_ld) {
     fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, s, V, n, params, given, codes, emb16, Db, dst, dst_ld,
                                                                 err_word);
@@ -729,9 +734,9 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
 // ---- frames of 17 .. max_batch items: the same sequence on the tcgen05 GEMM (128-row tiles; every weight is still
 //      streamed once per decoder pass, now shared by up to 128 rows per tile) with RMSNorm / SwiGLU as row kernels
 int FrameDecoder::tc(const __half* A, int K, const __half* W, int N, const float* bias, const float* resid, float* out32,
-                     int64_t ld32, __half* out16, int64_t ld16, int rows, cudaStream_t st) {
+                     int64_t ld32, __half* out16, int64_t ld16, int rows, cudaStream_t st, int64_t lda) {
   GemmDesc g{};
-  g.A = A; g.a_row_pitch = K; g.a_batch_pitch = 0; g.rows_a = rows; g.batches = 1; g.Kc = K; g.ntaps = 1; g.row_shift = 0;
+  g.A = A; g.a_row_pitch = lda ? lda : K; g.a_batch_pitch = 0; g.rows_a = rows; g.batches = 1; g.Kc = K; g.ntaps = 1; g.row_shift = 0;
   g.W = W; g.N = N; g.rows_out = rows; g.alpha = 1.0f; g.bias = bias; g.act = ACT_NONE; g.resid = resid; g.out32 = out32;
   g.ld32 = ld32; g.out16 = out16; g.ld16 = ld16; g.narrow_tiles = 1;
   ++launches;
@@ -740,12 +745,12 @@ int FrameDecoder::tc(const __half* A, int K, const __half* W, int N, const float
 
 // fp32 result dst = (accumulate ? dst : bias) + A W^T, with the reduction split over CTAs when the layer has too few tiles
 int FrameDecoder::tc32(const __half* A, int K, const __half* W, int N, const float* bias, bool accumulate, float* dst,
-                       int64_t ld_dst, int rows, cudaStream_t st) {
+                       int64_t ld_dst, int rows, cudaStream_t st, int64_t lda) {
   const int S = pick_split(rows, N, K);
-  if (S == 1) return tc(A, K, W, N, bias, accumulate ? dst : nullptr, dst, ld_dst, nullptr, 0, rows, st);
+  if (S == 1) return tc(A, K, W, N, bias, accumulate ? dst : nullptr, dst, ld_dst, nullptr, 0, rows, st, lda);
   GemmDesc g{};
   const int Kc = K / S;
-  g.A = A; g.a_row_pitch = K; g.a_batch_pitch = Kc; g.rows_a = rows; g.batches = S; g.Kc = Kc; g.ntaps = 1;
+  g.A = A; g.a_row_pitch = lda ? lda : K; g.a_batch_pitch = Kc; g.rows_a = rows; g.batches = S; g.Kc = Kc; g.ntaps = 1;
   g.W = W; g.w_batch_k = Kc; g.N = N; g.rows_out = rows; g.alpha = 1.0f; g.act = ACT_NONE;
   g.out32 = part32; g.ld32 = N; g.pitch32 = static_cast<int64_t>(rows) * N; g.narrow_tiles = 1;
   ++launches;
@@ -764,43 +769,62 @@ int FrameDecoder::enqueue_frame_big(int B, cudaStream_t st) {
   const int H = cfg.num_heads, Hk = cfg.num_kv_heads;
   const float scale = 1.0f / std::sqrt(static_cast<float>(hd));
   const int64_t ldl = static_cast<int64_t>(n) * V;
-  auto sample = [&](int s) {
-    fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, s, V, n, params, given, codes, emb16, Db, in16, Db,
+  const bool pair = pair_layout(B);       // rows 2b / 2b+1 = positions 0 / 1 of item b in the first pass
+  auto sample = [&](int s, __half* dst, int dst_ld) {
+    fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, s, V, n, params, given, codes, emb16, Db, dst, dst_ld,
                                                                 err_word);
     ++launches;
     return cudaGetLastError();
   };
-  auto rms = [&](const float* g) {
-    fd_rms_rows_kernel<<<(B + 7) / 8, 256, 0, st>>>(x32, B, D, g, cfg.norm_eps, n16);
+  auto rms = [&](const float* xrows, int64_t ldx, int rows, const float* g) {
+    fd_rms_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(xrows, ldx, rows, D, g, cfg.norm_eps, n16);
     ++launches;
     return cudaGetLastError();
   };
-  FRT2_TRY(tc32(in16, Db, w_head0_rm, V, nullptr, false, logits, ldl, B, st));                        // llm.py:303
-  for (int pos = 0; pos < n; ++pos) {
-    FRT2_TRY(tc32(in16, Db, w_proj_rm, D, nullptr, false, x32, D, B, st));                             // llm.py:320
-    if (pos == 0) FRT2_CUDA_OK(sample(0));
+  auto layers_pass = [&](int rows, int pos0, int np) -> int {
     for (FdLayer& L : layers) {
-      FRT2_CUDA_OK(rms(L.g_sa));
-      FRT2_TRY(tc32(n16, D, L.w_qkv_rm, qkv, L.b_qkv, false, qkv32, qkv, B, st));
-      fd_attn_kernel<<<dim3(Hk, B), 32 * (H / Hk), 0, st>>>(qkv32, L.kc, L.vc, attn16, rope_cos, rope_sin, H, Hk, hd, n, pos, 1,
+      FRT2_CUDA_OK(rms(x32, D, rows, L.g_sa));
+      FRT2_TRY(tc32(n16, D, L.w_qkv_rm, qkv, L.b_qkv, false, qkv32, qkv, rows, st));
+      fd_attn_kernel<<<dim3(Hk, B), 32 * (H / Hk), 0, st>>>(qkv32, L.kc, L.vc, attn16, rope_cos, rope_sin, H, Hk, hd, n, pos0, np,
                                                              scale);
       FRT2_CUDA_OK(cudaGetLastError());
       ++launches;
-      FRT2_TRY(tc32(attn16, H * hd, L.w_o_rm, D, nullptr, true, x32, D, B, st));
-      FRT2_CUDA_OK(rms(L.g_mlp));
-      FRT2_TRY(tc(n16, D, L.w_gu_rm, 2 * I, nullptr, nullptr, nullptr, 0, gu16, 2 * I, B, st));
-      const long long ne = static_cast<long long>(B) * I;
+      FRT2_TRY(tc32(attn16, H * hd, L.w_o_rm, D, nullptr, true, x32, D, rows, st));
+      FRT2_CUDA_OK(rms(x32, D, rows, L.g_mlp));
+      FRT2_TRY(tc(n16, D, L.w_gu_rm, 2 * I, nullptr, nullptr, nullptr, 0, gu16, 2 * I, rows, st));
+      const long long ne = static_cast<long long>(rows) * I;
       fd_swiglu_rows_kernel<<<static_cast<unsigned>((ne + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __half2*>(gu16), ne, h16);
       FRT2_CUDA_OK(cudaGetLastError());
       ++launches;
-      FRT2_TRY(tc32(h16, I, L.w_down_rm, D, nullptr, true, x32, D, B, st));
+      FRT2_TRY(tc32(h16, I, L.w_down_rm, D, nullptr, true, x32, D, rows, st));
     }
-    if (pos >= 1) {                                                                                    // llm.py:322-326
-      FRT2_CUDA_OK(rms(g_final));
-      FRT2_TRY(tc32(n16, D, w_heads_rm + static_cast<size_t>(pos - 1) * V * D, V, nullptr, false,
-                    logits + static_cast<size_t>(pos) * V, ldl, B, st));
-      FRT2_CUDA_OK(sample(pos));
-    }
+    return FRT2_OK;
+  };
+  auto head_and_sample = [&](int pos, const float* xrows, int64_t ldx) -> int {                      // llm.py:322-326
+    FRT2_CUDA_OK(rms(xrows, ldx, B, g_final));
+    FRT2_TRY(tc32(n16, D, w_heads_rm + static_cast<size_t>(pos - 1) * V * D, V, nullptr, false,
+                  logits + static_cast<size_t>(pos) * V, ldl, B, st));
+    FRT2_CUDA_OK(sample(pos, in16, Db));
+    return FRT2_OK;
+  };
+  FRT2_TRY(tc32(in16, Db, w_head0_rm, V, nullptr, false, logits, ldl, B, st, pair ? 2 * Db : Db));    // llm.py:303
+  int pos;
+  if (pair) {
+    FRT2_CUDA_OK(sample(0, in16 + Db, 2 * Db));
+    FRT2_TRY(tc32(in16, Db, w_proj_rm, D, nullptr, false, x32, D, 2 * B, st));                         // llm.py:320
+    FRT2_TRY(layers_pass(2 * B, 0, 2));
+    FRT2_TRY(head_and_sample(1, x32 + D, 2 * D));
+    pos = 2;
+  } else {
+    FRT2_TRY(tc32(in16, Db, w_proj_rm, D, nullptr, false, x32, D, B, st));
+    FRT2_CUDA_OK(sample(0, in16, Db));
+    FRT2_TRY(layers_pass(B, 0, 1));
+    pos = 1;
+  }
+  for (; pos < n; ++pos) {
+    FRT2_TRY(tc32(in16, Db, w_proj_rm, D, nullptr, false, x32, D, B, st));
+    FRT2_TRY(layers_pass(B, pos, 1));
+    FRT2_TRY(head_and_sample(pos, x32, D));
   }
   return FRT2_OK;
 }
@@ -924,8 +948,7 @@ int frt2_fd_generate(frt2_frame_decoder* f, const float* last_h, int B, const in
   FdParams p{};
   p.noise = noise; p.seed = seed; p.frame = d.frame++; p.topk = topk; p.temperature = temperature;
   p.has_c0 = c0 != nullptr; p.has_forced = forced != nullptr;
-  static const bool no_pair = getenv("FRT2_FD_NO_PAIR") != nullptr;
-  const int in_ld = (!no_pair && 2 * B <= FD_MAX_BATCH) ? 2 * Db : Db;     // the layout enqueue_frame captured for this B
+  const int in_ld = d.pair_layout(B) ? 2 * Db : Db;     // the layout enqueue_frame captured for this B
   fd_begin_kernel<<<std::max(1, (B * Db + 255) / 256), 256, 0, st>>>(last_h, B, Db, d.in16, in_ld, c0, forced, n, d.given, p, d.params);
   FRT2_CUDA_OK(cudaGetLastError());
   FRT2_CUDA_OK(cudaGraphLaunch(exec, st));

@@ -122,8 +122,8 @@ def test_large_batch_runs_on_the_tcgen05_gemm(preset, wseed, B, per_layer):
     ref_codes, ref_logits = FO.generate_codes(sd, cfg, last_h, 20, 0.9, noise)
     _, logits = fd.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise), forced=cuda(ref_codes), return_logits=True)
     n, L = cfg.audio_num_codebooks, cfg.num_layers
-    if per_layer is not None:
-        assert fd.last_launches == 2 + n * (1 + per_layer * L) + n + 2 * (n - 1)
+    if per_layer is not None:      # positions 0 and 1 in one pass on this path too: n - 1 decoder passes
+        assert fd.last_launches == 2 + (n - 1) * (1 + per_layer * L) + n + 2 * (n - 1)
     _, snr = report(f"{preset} batch {B} (tcgen05 GEMM path) teacher-forced logits", ref_logits, to_np(logits))
     assert snr >= SNR_GATE_DB
     codes = fd.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise))
