@@ -138,6 +138,25 @@ def test_large_batch_runs_on_the_tcgen05_gemm(preset, wseed, B, per_layer):
         fd.generate_codes(cuda(np.zeros((41, cfg.backbone_dim), np.float32)), 20, 0.9)
 
 
+def test_gemm_skinny_fallback_for_widths_the_stream_kernel_does_not_take(monkeypatch):
+    """Widths that are not multiples of 32 (or FRT2_FD_SKINNY=1, used here) run every GEMM of the frame on gemm_skinny with
+    its fused RMSNorm / SwiGLU modes (row-major weights): same parity, and 60+ dB against the stream-kernel instance."""
+    cfg = FD_PRESETS["FD_SMALL"]
+    sd = synthetic_frame_decoder_state_dict(cfg, 5)
+    last_h, noise = synthetic_frame_inputs(cfg, 3, seed=17)
+    ref_codes, ref_logits = FO.generate_codes(sd, cfg, last_h, 20, 0.9, noise)
+    monkeypatch.setenv("FRT2_FD_SKINNY", "1")
+    fb = FrameDecoderB200(cfg, sd)
+    monkeypatch.delenv("FRT2_FD_SKINNY")
+    _, lg_fb = fb.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise), forced=cuda(ref_codes), return_logits=True)
+    _, snr = report("FD_SMALL on the gemm_skinny fallback", ref_logits, to_np(lg_fb))
+    assert snr >= SNR_GATE_DB
+    _, _, fd = build("FD_SMALL", 5)
+    _, lg = fd.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise), forced=cuda(ref_codes), return_logits=True)
+    _, snr = report("fallback vs stream kernel", to_np(lg), to_np(lg_fb))
+    assert snr >= 60.0
+
+
 def test_out_of_range_code_raises_index_error():
     cfg, sd, fd = build("FD_TINY", 3)
     last_h, noise = synthetic_frame_inputs(cfg, 2, seed=1)
