@@ -48,14 +48,13 @@ struct FdParams {
   int has_forced;          // teacher forcing: every code given
 };
 
-// in_ld: halves between the rows last_h is staged to (2 Db when positions 0 and 1 run as one two-row pass)
-__global__ void fd_begin_kernel(const float* __restrict__ last_h, int B, int Db, __half* __restrict__ in16, int in_ld,
+__global__ void fd_begin_kernel(const float* __restrict__ last_h, int B, int Db, __half* __restrict__ in16,
                                 const int* __restrict__ c0, const int* __restrict__ forced, int ncb, int* __restrict__ given,
                                 FdParams p, FdParams* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) *dst = p;
   if (i < B * ncb) given[i] = forced != nullptr ? forced[i] : ((c0 != nullptr && i % ncb == 0) ? c0[i / ncb] : 0);
-  for (int e = i; e < B * Db; e += gridDim.x * blockDim.x) in16[(e / Db) * in_ld + e % Db] = to_half_sat(last_h[e]);
+  for (int e = i; e < B * Db; e += gridDim.x * blockDim.x) in16[e] = to_half_sat(last_h[e]);
 }
 
 // One position of one layer (or the first TWO, np = 2: rows 2b and 2b+1 of qkv / out16 are positions 0 and 1 of item b):
@@ -266,13 +265,14 @@ __device__ __forceinline__ float block_sum(float x, float* red) {
 }
 
 // sample_topk + _multinomial_sample_one_no_sync (llm.py:33-49) for codebook s of item blockIdx.x, then the embedding row
-// of the next decoder input (llm.py:305,325-326: audio_embeddings[code + s * V]) as the fp16 operand of `projection`.
+// of the next decoder input, already projected (llm.py:305,320,325-326: projection(audio_embeddings[code + s * V]), a
+// table composed at load), as the next position's residual row.
 //   logits / temperature; k-th largest value by k rounds of "remove the first maximum" (multiplicity counted like
 //   torch.topk); entries < k-th are dropped (ties at the k-th value stay, llm.py:43); log_softmax, softmax, p / q, first
 //   arg-max.  Everything in fp32 in the reference's order of operations.
 __global__ void __launch_bounds__(FD_SAMPLE_THREADS) fd_sample_kernel(
     const float* __restrict__ logits, int s, int V, int ncb, const FdParams* __restrict__ pp, const int* __restrict__ given,
-    int* __restrict__ codes, const __half* __restrict__ emb16, int Db, __half* __restrict__ in16, int in_ld,
+    int* __restrict__ codes, const float* __restrict__ table, int D, float* __restrict__ x_next, int x_ld,
     unsigned int* __restrict__ err_word) {
   extern __shared__ float fd_smem[];
   float* val = fd_smem;          // scaled logits
@@ -349,9 +349,10 @@ __global__ void __launch_bounds__(FD_SAMPLE_THREADS) fd_sample_kernel(
   __syncthreads();
   code = s_code;
   if (s + 1 < ncb) {
-    const uint4* src = reinterpret_cast<const uint4*>(emb16 + (static_cast<long long>(s) * V + code) * Db);
-    uint4* dst = reinterpret_cast<uint4*>(in16 + static_cast<long long>(b) * in_ld);
-    for (int i = tid; i < Db / 8; i += FD_SAMPLE_THREADS) dst[i] = src[i];
+    // projection(audio_embeddings[code + s V]) from the table composed at load: the residual row of the next position
+    const float4* src = reinterpret_cast<const float4*>(table + (static_cast<long long>(s) * V + code) * D);
+    float4* dst = reinterpret_cast<float4*>(x_next + static_cast<long long>(b) * x_ld);
+    for (int i = tid; i < D / 4; i += FD_SAMPLE_THREADS) dst[i] = __ldg(src + i);
   }
 }
 
@@ -404,7 +405,10 @@ struct FrameDecoder {
       if (kblocks % sdiv == 0 && kblocks / sdiv >= 4 && tiles * sdiv <= num_sms()) best = sdiv;
     return best;
   }
-  __half* emb16 = nullptr;       // (ncb * V, Db)
+  __half* emb16 = nullptr;       // (ncb * V, Db): only until the table below is built
+  float* proj_table = nullptr;   // (ncb * V, D) fp32 = projection(audio_embeddings): what a sampled code contributes to the
+                                 // next position (composed at load with the frame's own GEMM kernel: the same bits as
+                                 // embedding lookup + projection GEMM per position, 15 launches fewer per frame)
   float* g_final = nullptr;
   float *rope_cos = nullptr, *rope_sin = nullptr;     // (ncb, hd / 2)
   // activations of a frame (MAX_BATCH rows)
@@ -617,6 +621,21 @@ int FrameDecoder::finalize() {
   FRT2_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   FRT2_CUDA_OK(cudaStreamCreateWithPriority(&cap_stream, cudaStreamNonBlocking, hi));
   FRT2_CUDA_OK(cudaEventCreateWithFlags(&ws_event, cudaEventDisableTiming));
+  {  // projection(audio_embeddings) row by row through the kernel the frame itself would have used (16 rows per launch)
+    const long long total = static_cast<long long>(n) * V;
+    FRT2_TRY(dev_alloc(&proj_table, static_cast<size_t>(total) * D));
+    const long long before = launches;
+    for (long long r0 = 0; r0 < total; r0 += FD_MAX_BATCH) {
+      const int rows = static_cast<int>(std::min<long long>(FD_MAX_BATCH, total - r0));
+      FRT2_TRY(skinny(emb16 + r0 * Db, Db, w_proj, D, nullptr, ACT_NONE, nullptr, proj_table + r0 * D, D, nullptr, 0, nullptr,
+                      nullptr, rows, nullptr));
+    }
+    launches = before;
+    FRT2_CUDA_OK(cudaDeviceSynchronize());
+    owned.erase(std::find(owned.begin(), owned.end(), static_cast<void*>(emb16)));
+    cudaFree(emb16);
+    emb16 = nullptr;
+  }
   raw.clear();
   finalized = true;
   return FRT2_OK;
@@ -668,15 +687,12 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
   // positions 0 and 1 as ONE two-row pass while 2 B rows fit the GEMM's 8 (the reference's first decoder call has these
   // two positions too, llm.py:306-321): one weight stream less per frame.  Rows 2b / 2b+1 = position 0 / 1 of item b.
   const bool pair = pair_layout(B);
-  auto sample = [&](int s, __half* dst, int dst_ld) {
-    fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, s, V, n, params, given, codes, emb16, Db, dst, dst_ld,
+  // sampler of codebook s; the projected embedding of its code becomes the residual row of the next position
+  auto sample = [&](int s, float* x_next, int x_ld) {
+    fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, s, V, n, params, given, codes, proj_table, D, x_next, x_ld,
                                                                 err_word);
     ++launches;
     return cudaGetLastError();
-  };
-  // projection of a pass's inputs (last_h / the embedding of the previous code) into the residual rows: llm.py:320
-  auto project = [&](int rows) -> int {
-    return skinny(in16, Db, w_proj, D, nullptr, ACT_NONE, nullptr, x32, D, nullptr, 0, nullptr, nullptr, rows, st);
   };
   // the decoder's layers over `rows` residual rows holding `np` new positions per item, the first of them at pos0
   auto layers_pass = [&](int rows, int pos0, int np) -> int {
@@ -699,32 +715,30 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
     return FRT2_OK;
   };
   // llm.py:322-326 for position `pos` (its residual row: x_rows + b * x_ld): final norm (inside the head GEMM),
-  // audio_head[pos-1], sampler, embedding of the next input into in16 row b
+  // audio_head[pos-1], sampler, the next position's residual row b
   auto head_and_sample = [&](int pos, const float* x_rows, int64_t x_ld) -> int {
     if (skip & 32) return FRT2_OK;
     FRT2_TRY(skinny(nullptr, D, w_heads + head_stride * (pos - 1), V, nullptr, ACT_NONE, nullptr,
                     logits + static_cast<size_t>(pos) * V, ldl, nullptr, 0, x_rows, g_final, B, st, 0, x_ld));
-    FRT2_CUDA_OK(sample(pos, in16, Db));
+    FRT2_CUDA_OK(sample(pos, x32, D));
     return FRT2_OK;
   };
-  // codebook 0: llm.py:303-304 (last_h sits in in16 rows b, or 2b in the two-row layout)
-  FRT2_TRY(skinny(in16, Db, w_head0, V, nullptr, ACT_NONE, nullptr, logits, ldl, nullptr, 0, nullptr, nullptr, B, st,
-                  pair ? 2 * Db : Db));
+  // codebook 0 and the projection of last_h (position 0; in16 holds last_h): llm.py:303-304,320
+  FRT2_TRY(skinny(in16, Db, w_head0, V, nullptr, ACT_NONE, nullptr, logits, ldl, nullptr, 0, nullptr, nullptr, B, st));
   int pos;
   if (pair) {
-    FRT2_CUDA_OK(sample(0, in16 + Db, 2 * Db));     // c0 and its embedding -> rows 2b+1
-    FRT2_TRY(project(2 * B));
+    FRT2_TRY(skinny(in16, Db, w_proj, D, nullptr, ACT_NONE, nullptr, x32, 2 * D, nullptr, 0, nullptr, nullptr, B, st));   // rows 2b
+    FRT2_CUDA_OK(sample(0, x32 + D, 2 * D));         // c0 -> rows 2b+1
     FRT2_TRY(layers_pass(2 * B, 0, 2));
     FRT2_TRY(head_and_sample(1, x32 + D, 2 * D));
     pos = 2;
   } else {
-    FRT2_TRY(project(B));                            // position 0 = last_h ...
-    FRT2_CUDA_OK(sample(0, in16, Db));               // ... whose rows are free for c0's embedding once projected
+    FRT2_TRY(skinny(in16, Db, w_proj, D, nullptr, ACT_NONE, nullptr, x32, D, nullptr, 0, nullptr, nullptr, B, st));
     FRT2_TRY(layers_pass(B, 0, 1));
+    FRT2_CUDA_OK(sample(0, x32, D));                 // c0 -> position 1's rows, free once position 0 has run
     pos = 1;
   }
   for (; pos < n; ++pos) {
-    FRT2_TRY(project(B));
     FRT2_TRY(layers_pass(B, pos, 1));
     FRT2_TRY(head_and_sample(pos, x32, D));
   }
@@ -770,8 +784,8 @@ int FrameDecoder::enqueue_frame_big(int B, cudaStream_t st) {
   const float scale = 1.0f / std::sqrt(static_cast<float>(hd));
   const int64_t ldl = static_cast<int64_t>(n) * V;
   const bool pair = pair_layout(B);       // rows 2b / 2b+1 = positions 0 / 1 of item b in the first pass
-  auto sample = [&](int s, __half* dst, int dst_ld) {
-    fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, s, V, n, params, given, codes, emb16, Db, dst, dst_ld,
+  auto sample = [&](int s, float* x_next, int x_ld) {
+    fd_sample_kernel<<<B, FD_SAMPLE_THREADS, 2 * V * 4, st>>>(logits, s, V, n, params, given, codes, proj_table, D, x_next, x_ld,
                                                                 err_word);
     ++launches;
     return cudaGetLastError();
@@ -804,25 +818,24 @@ int FrameDecoder::enqueue_frame_big(int B, cudaStream_t st) {
     FRT2_CUDA_OK(rms(xrows, ldx, B, g_final));
     FRT2_TRY(tc32(n16, D, w_heads_rm + static_cast<size_t>(pos - 1) * V * D, V, nullptr, false,
                   logits + static_cast<size_t>(pos) * V, ldl, B, st));
-    FRT2_CUDA_OK(sample(pos, in16, Db));
+    FRT2_CUDA_OK(sample(pos, x32, D));
     return FRT2_OK;
   };
-  FRT2_TRY(tc32(in16, Db, w_head0_rm, V, nullptr, false, logits, ldl, B, st, pair ? 2 * Db : Db));    // llm.py:303
+  FRT2_TRY(tc32(in16, Db, w_head0_rm, V, nullptr, false, logits, ldl, B, st));                        // llm.py:303
   int pos;
   if (pair) {
-    FRT2_CUDA_OK(sample(0, in16 + Db, 2 * Db));
-    FRT2_TRY(tc32(in16, Db, w_proj_rm, D, nullptr, false, x32, D, 2 * B, st));                         // llm.py:320
+    FRT2_TRY(tc32(in16, Db, w_proj_rm, D, nullptr, false, x32, 2 * D, B, st));                         // llm.py:320, rows 2b
+    FRT2_CUDA_OK(sample(0, x32 + D, 2 * D));                                                           // c0 -> rows 2b+1
     FRT2_TRY(layers_pass(2 * B, 0, 2));
     FRT2_TRY(head_and_sample(1, x32 + D, 2 * D));
     pos = 2;
   } else {
     FRT2_TRY(tc32(in16, Db, w_proj_rm, D, nullptr, false, x32, D, B, st));
-    FRT2_CUDA_OK(sample(0, in16, Db));
     FRT2_TRY(layers_pass(B, 0, 1));
+    FRT2_CUDA_OK(sample(0, x32, D));
     pos = 1;
   }
   for (; pos < n; ++pos) {
-    FRT2_TRY(tc32(in16, Db, w_proj_rm, D, nullptr, false, x32, D, B, st));
     FRT2_TRY(layers_pass(B, pos, 1));
     FRT2_TRY(head_and_sample(pos, x32, D));
   }
@@ -948,8 +961,7 @@ int frt2_fd_generate(frt2_frame_decoder* f, const float* last_h, int B, const in
   FdParams p{};
   p.noise = noise; p.seed = seed; p.frame = d.frame++; p.topk = topk; p.temperature = temperature;
   p.has_c0 = c0 != nullptr; p.has_forced = forced != nullptr;
-  const int in_ld = d.pair_layout(B) ? 2 * Db : Db;     // the layout enqueue_frame captured for this B
-  fd_begin_kernel<<<std::max(1, (B * Db + 255) / 256), 256, 0, st>>>(last_h, B, Db, d.in16, in_ld, c0, forced, n, d.given, p, d.params);
+  fd_begin_kernel<<<std::max(1, (B * Db + 255) / 256), 256, 0, st>>>(last_h, B, Db, d.in16, c0, forced, n, d.given, p, d.params);
   FRT2_CUDA_OK(cudaGetLastError());
   FRT2_CUDA_OK(cudaGraphLaunch(exec, st));
   d.launches += 1 + d.graph_kernels[B];

@@ -50,10 +50,10 @@ def test_frame_tail_vs_reference_golden(name, preset):
     same = got == g["codes"]
     print(f"[parity] {name}: free-running codes equal to the reference's: {int(same.sum())} / {same.size}")
     assert same.all()
-    # staging + codebook-0 head + per decoder pass (projection, 5 kernels per layer) + sampler per codebook + head per
-    # codebook >= 1; positions 0 and 1 are ONE pass while 2 B rows fit the GEMM's 16
+    # staging + codebook-0 head + projection of last_h + per decoder pass 5 kernels per layer + sampler per codebook (it
+    # also writes the next position's projected embedding row) + head per codebook >= 1; positions 0 and 1 are ONE pass while 2 B rows fit the GEMM's 16
     passes = cfg.audio_num_codebooks - (1 if 2 * last_h.shape[0] <= 16 else 0)
-    assert fd.last_launches == 1 + 1 + passes * (1 + 5 * cfg.num_layers) + cfg.audio_num_codebooks + (cfg.audio_num_codebooks - 1)
+    assert fd.last_launches == 3 + passes * 5 * cfg.num_layers + cfg.audio_num_codebooks + (cfg.audio_num_codebooks - 1)
 
 
 def test_given_c0_and_batch_independence():
@@ -83,12 +83,12 @@ def test_two_row_first_pass_and_single_row_layout_agree():
     ref_codes, ref_logits = FO.generate_codes(sd, cfg, last_h, 20, 0.9, noise)
     n, L = cfg.audio_num_codebooks, cfg.num_layers
     _, forced = fd.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise), forced=cuda(ref_codes), return_logits=True)
-    assert fd.last_launches == 2 + n * (1 + 5 * L) + n + (n - 1)                 # one position per pass
+    assert fd.last_launches == 3 + n * 5 * L + n + (n - 1)                       # one position per pass
     _, snr = report("FD_SMALL batch 11 (one position per pass, 16-row MMA tiles) logits", ref_logits, to_np(forced))
     assert snr >= SNR_GATE_DB
     codes11, logits11 = fd.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise), return_logits=True)
     codes3, logits3 = fd.generate_codes(cuda(last_h[8:11]), 20, 0.9, noise=cuda(noise[8:11]), return_logits=True)
-    assert fd.last_launches == 2 + (n - 1) * (1 + 5 * L) + n + (n - 1)           # positions 0 and 1 in one pass
+    assert fd.last_launches == 3 + (n - 1) * 5 * L + n + (n - 1)                 # positions 0 and 1 in one pass
     assert torch.equal(codes3, codes11[8:11]) and torch.equal(logits3, logits11[8:11])
     same = (codes11.cpu().numpy() == ref_codes).all(axis=1)
     print(f"[parity] FD_SMALL batch 11: free-running frames identical to the oracle's: {int(same.sum())} / {same.size}")
@@ -123,7 +123,7 @@ def test_large_batch_runs_on_the_tcgen05_gemm(preset, wseed, B, per_layer):
     _, logits = fd.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise), forced=cuda(ref_codes), return_logits=True)
     n, L = cfg.audio_num_codebooks, cfg.num_layers
     if per_layer is not None:      # positions 0 and 1 in one pass on this path too: n - 1 decoder passes
-        assert fd.last_launches == 2 + (n - 1) * (1 + per_layer * L) + n + 2 * (n - 1)
+        assert fd.last_launches == 3 + (n - 1) * per_layer * L + n + 2 * (n - 1)
     _, snr = report(f"{preset} batch {B} (tcgen05 GEMM path) teacher-forced logits", ref_logits, to_np(logits))
     assert snr >= SNR_GATE_DB
     codes = fd.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise))
