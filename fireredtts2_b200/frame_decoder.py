@@ -179,21 +179,26 @@ class FrameDecoderB200:
         except Exception:
             pass
 
-    @classmethod
-    def from_reference(cls, model, device="cuda:0", max_batch: int = 8) -> "FrameDecoderB200":
-        """Build from a live reference ``Model`` (llm.py:85): widths from its modules, tensors from its state_dict."""
+    @staticmethod
+    def config_from_reference(model) -> Tuple[FrameDecoderConfig, dict]:
+        """Widths of a live reference ``Model`` (llm.py:85) read off its modules / state_dict (torchtune parameter names)."""
         sd = {k: v for k, v in model.state_dict().items()}
         n_layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("decoder.layers."))
         D = sd["decoder.norm.scale"].shape[0]
         hd_total = sd["decoder.layers.0.attn.q_proj.weight"].shape[0]
         kv_total = sd["decoder.layers.0.attn.k_proj.weight"].shape[0]
-        attn = model.decoder.layers[0].attn
-        H = int(attn.num_heads)
+        H = int(model.decoder.layers[0].attn.num_heads)
         hd = hd_total // H
         cfg = FrameDecoderConfig(backbone_dim=sd["projection.weight"].shape[1], dim=D, num_layers=n_layers, num_heads=H,
                                  num_kv_heads=kv_total // hd, intermediate_dim=sd["decoder.layers.0.mlp.w1.weight"].shape[0],
                                  audio_vocab_size=model.config.audio_vocab_size,
                                  audio_num_codebooks=model.config.audio_num_codebooks)
+        return cfg, sd
+
+    @classmethod
+    def from_reference(cls, model, device="cuda:0", max_batch: int = 8) -> "FrameDecoderB200":
+        """Build from a live reference ``Model`` (llm.py:85): widths from its modules, tensors from its state_dict."""
+        cfg, sd = cls.config_from_reference(model)
         return cls(cfg, sd, device, max_batch)
 
     def check_error(self):

@@ -82,6 +82,45 @@ def test_frame_decoder_host_side():
         FrameDecoderConfig(dim=100, num_heads=3)
 
 
+def test_frame_decoder_config_from_a_reference_shaped_model():
+    """config_from_reference reads the widths off a module tree with the reference's names (Model.projection /
+    audio_embeddings / codebook0_head / audio_head / decoder.layers[i].attn ... with torchtune parameter names)."""
+    import torch
+    from fireredtts2_b200.frame_decoder import FD_TINY, FrameDecoderB200, frame_decoder_keys, synthetic_frame_decoder_state_dict
+
+    cfg = FD_TINY
+    sd = synthetic_frame_decoder_state_dict(cfg, 2)
+
+    class Holder(torch.nn.Module):
+        pass
+
+    def grow(root, dotted, tensor):
+        *path, leaf = dotted.split(".")
+        m = root
+        for p in path:
+            if not hasattr(m, p):
+                setattr(m, p, Holder())
+            m = getattr(m, p)
+        setattr(m, leaf, torch.nn.Parameter(torch.from_numpy(tensor)))
+
+    model = Holder()
+    layers = torch.nn.ModuleList([Holder() for _ in range(cfg.num_layers)])
+    model.decoder = Holder()
+    model.decoder.layers = layers
+    for k, v in sd.items():
+        if k.startswith("decoder.layers."):
+            _, _, i, rest = k.split(".", 3)
+            grow(layers[int(i)], rest, v)
+        else:
+            grow(model, k, v)
+    for l in layers:
+        l.attn.num_heads = cfg.num_heads
+    model.config = type("Cfg", (), {"audio_vocab_size": cfg.audio_vocab_size, "audio_num_codebooks": cfg.audio_num_codebooks})()
+    got, got_sd = FrameDecoderB200.config_from_reference(model)
+    assert got == cfg
+    assert sorted(got_sd) == sorted(frame_decoder_keys(cfg))
+
+
 def test_frame_decoder_has_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
