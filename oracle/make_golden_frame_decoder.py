@@ -179,8 +179,52 @@ def run_case(cfg, B, wseed, dseed, topk, temperature):
             "meta": np.array([B, wseed, dseed, topk], dtype=np.int64), "temperature": np.float32(temperature)}
 
 
+# V, topk, temperature, rows — sample_topk of the reference on its own (llm.py:39-49), exact ties at the k-th value included
+SAMPLER_CASES = [(64, 8, 0.9, 64), (2048, 10, 0.75, 32), (2048, 30, 0.9, 32), (2051, 50, 1.0, 24), (512, 512, 1.3, 16),
+                 (2048, 1, 0.5, 16)]
+
+
+def sampler_golden():
+    """The reference's ``sample_topk`` / ``_multinomial_sample_one_no_sync`` on seeded logits; the Exp(1) draws it makes
+    are recorded by wrapping ``Tensor.exponential_``."""
+    out = {}
+    real_exp = torch.Tensor.exponential_
+    for i, (V, topk, temp, rows) in enumerate(SAMPLER_CASES):
+        g = torch.Generator().manual_seed(100 + i)
+        logits = 2.0 * torch.randn(rows, V, generator=g)
+        logits[: rows // 2] = torch.round(logits[: rows // 2] * 2) / 2        # many exact ties
+        drawn = []
+
+        def exp_spy(self, *a, **kw):
+            r = real_exp(self, *a, **kw)
+            drawn.append(r.detach().clone())
+            return r
+
+        torch.Tensor.exponential_ = exp_spy
+        try:
+            torch.manual_seed(200 + i)
+            codes = ref_llm.sample_topk(logits, topk, temp)
+        finally:
+            torch.Tensor.exponential_ = real_exp
+        assert len(drawn) == 1
+        out[f"c{i}_logits"] = logits.numpy()
+        out[f"c{i}_q"] = drawn[0].numpy()
+        out[f"c{i}_codes"] = codes.numpy().astype(np.int32).reshape(-1)
+        out[f"c{i}_meta"] = np.array([V, topk, rows], dtype=np.int64)
+        out[f"c{i}_temperature"] = np.float32(temp)
+    out["n_cases"] = np.int64(len(SAMPLER_CASES))
+    return out
+
+
 def main():
     torch.set_num_threads(os.cpu_count() or 1)
+    from oracle import frame_decoder_oracle as FO_
+    sg = sampler_golden()
+    np.savez_compressed(os.path.join(GOLDEN, "fd_sampler.npz"), **sg)
+    for i in range(int(sg["n_cases"])):
+        V, topk, rows = (int(v) for v in sg[f"c{i}_meta"])
+        got = FO_.sample_topk(sg[f"c{i}_logits"], topk, float(sg[f"c{i}_temperature"]), sg[f"c{i}_q"])
+        print("sampler case", i, (V, topk, rows), "oracle == reference:", bool((got == sg[f"c{i}_codes"]).all()))
     from oracle import frame_decoder_oracle as FO
     for name, preset, B, wseed, dseed, topk, temperature in CASES:
         cfg = FD_PRESETS[preset]

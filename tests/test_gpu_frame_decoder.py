@@ -203,6 +203,17 @@ def test_sample_topk_matches_oracle(V, topk, temperature):
     assert np.array_equal(got, ref)
 
 
+def test_sample_topk_matches_the_reference_sampler_golden():
+    """fd_sample_kernel against decisions of the reference's own sample_topk (llm.py:39-49) with the draws it made."""
+    import os
+    from tests.helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "fd_sampler.npz"))
+    for i in range(int(g["n_cases"])):
+        V, topk, rows = (int(v) for v in g[f"c{i}_meta"])
+        got = sample_topk(cuda(g[f"c{i}_logits"]), topk, float(g[f"c{i}_temperature"]), cuda(g[f"c{i}_q"])).cpu().numpy()
+        assert np.array_equal(got, g[f"c{i}_codes"]), (i, V, topk)
+
+
 def test_sample_topk_library_draws_follow_the_distribution():
     """noise=None: the sampled frequencies follow softmax(logits / T) restricted to the top k (chi-square-like bound)."""
     V, topk, T, B = 64, 8, 0.8, 20000

@@ -348,3 +348,16 @@ def test_sample_topk_oracle_edge_cases():
     assert FO.sample_topk(logits, 2, 1.0, q)[0] == 4            # three tied maxima survive topk = 2; the smallest q wins
     assert FO.sample_topk(logits, 1, 0.5, np.ones_like(q))[0] == 1
     assert FO.sample_topk(logits, 6, 1.0, q)[0] == 5            # nothing filtered: the tiny q of the last entry wins
+
+
+def test_sample_topk_oracle_matches_the_reference_sampler():
+    """oracle.sample_topk against the reference's own sample_topk / _multinomial_sample_one_no_sync (llm.py:33-49) on seeded
+    logits with exact ties at the k-th value; the Exp(1) draws are the ones the reference made (tests/golden/fd_sampler.npz)."""
+    import os
+    from oracle import frame_decoder_oracle as FO
+    from tests.helpers import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "fd_sampler.npz"))
+    for i in range(int(g["n_cases"])):
+        V, topk, rows = (int(v) for v in g[f"c{i}_meta"])
+        got = FO.sample_topk(g[f"c{i}_logits"], topk, float(g[f"c{i}_temperature"]), g[f"c{i}_q"])
+        assert got.shape == (rows,) and np.array_equal(got, g[f"c{i}_codes"]), (i, V, topk)
