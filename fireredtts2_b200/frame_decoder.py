@@ -125,6 +125,22 @@ def synthetic_frame_decoder_state_dict(cfg: FrameDecoderConfig, seed: int = 0) -
     return sd
 
 
+def adversarial_frame_decoder_state_dict(cfg: FrameDecoderConfig, seed: int = 0, outlier: float = 50.0) -> Dict[str, np.ndarray]:
+    """Weights that stress fp16 operands the way trained LMs do: four residual channels carry values ``outlier`` times the
+    others ("massive activations": the projection's rows of those channels are scaled), RMSNorm scales between 0.1 and 5,
+    gate / up projections three times wider (SwiGLU products in the hundreds)."""
+    sd = synthetic_frame_decoder_state_dict(cfg, seed)
+    rng = np.random.default_rng(7000 + seed)
+    ch = rng.choice(cfg.dim, size=4, replace=False)
+    sd["projection.weight"][ch] *= outlier
+    for k in list(sd):
+        if k.endswith("norm.scale"):
+            sd[k] = rng.uniform(0.1, 5.0, sd[k].shape).astype(np.float32)
+        if k.endswith("mlp.w1.weight") or k.endswith("mlp.w3.weight"):
+            sd[k] = (sd[k] * 3.0).astype(np.float32)
+    return sd
+
+
 def synthetic_frame_inputs(cfg: FrameDecoderConfig, batch: int, seed: int = 0) -> Tuple[np.ndarray, np.ndarray]:
     """-> ``last_h (B, backbone_dim)`` fp32 and Exp(1) draws ``noise (B, ncb, V)`` (what ``exponential_(1)`` produces in
     ``_multinomial_sample_one_no_sync``, llm.py:34-36)."""

@@ -157,6 +157,21 @@ def test_gemm_skinny_fallback_for_widths_the_stream_kernel_does_not_take(monkeyp
     assert snr >= 60.0
 
 
+def test_adversarial_weights_keep_the_gate():
+    """Massive residual channels (x 50), RMSNorm scales in [0.1, 5], wide SwiGLU products: teacher-forced logits of the
+    fp16-operand path stay within the gate of the fp32 oracle."""
+    from fireredtts2_b200.frame_decoder import adversarial_frame_decoder_state_dict
+    cfg = FD_PRESETS["FD_SMALL"]
+    sd = adversarial_frame_decoder_state_dict(cfg, 1)
+    _cache.clear()
+    fd = FrameDecoderB200(cfg, sd)
+    last_h, noise = synthetic_frame_inputs(cfg, 2, seed=19)
+    ref_codes, ref_logits = FO.generate_codes(sd, cfg, last_h, 20, 0.9, noise)
+    _, logits = fd.generate_codes(cuda(last_h), 20, 0.9, noise=cuda(noise), forced=cuda(ref_codes), return_logits=True)
+    _, snr = report("FD_SMALL adversarial weights, teacher-forced logits", ref_logits[:, 1:], to_np(logits)[:, 1:])
+    assert snr >= SNR_GATE_DB
+
+
 def test_out_of_range_code_raises_index_error():
     cfg, sd, fd = build("FD_TINY", 3)
     last_h, noise = synthetic_frame_inputs(cfg, 2, seed=1)
