@@ -847,7 +847,7 @@ def context_resample_record(codec, tok_dev, B, L, n_samples, reps=3):
 
 
 def frame_tail_record(dev, frames=40):
-    """SURVEY 8f.4 sub-record: the frame tail of the speech LM (llm.py:303-334 — codebook-0 head, 16 dependent passes of
+    """SURVEY 8f.4 sub-record: the frame tail of the speech LM (llm.py:304-330 — codebook-0 head, 16 dependent passes of
     the qwen-200m "decoder", samplers, embeddings) as one CUDA graph per frame (frt2_fd_generate), batch 1 and 8; HBM
     roofline = the fp16 weights one frame streams; parity of one FD_200M frame (teacher-forced logits, free-running
     codes) against the numpy oracle on the box, which is also the CPU baseline (one frame, all host cores through BLAS)."""
@@ -860,7 +860,7 @@ def frame_tail_record(dev, frames=40):
     sd = synthetic_frame_decoder_state_dict(cfg, 0)
     fd = FrameDecoderB200(cfg, sd, device=str(dev))
     pk, _ = peaks()
-    rec = {"workload": "frame tail of Model.generate_frame (llm.py:303-334): qwen-1.5b-wide backbone state -> 16 codes; "
+    rec = {"workload": "frame tail of Model.generate_frame (llm.py:304-330): qwen-1.5b-wide backbone state -> 16 codes; "
                        "decoder flavor qwen-200m (4 x 1536, 12 / 2 heads, 8960), V = 2048, random weights; topk 30, T 0.9",
            "weight_bytes_per_frame": cfg.weight_bytes_per_frame()}
     for B in (1, 8, 16):

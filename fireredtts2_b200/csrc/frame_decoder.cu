@@ -1,10 +1,10 @@
-// Frame tail of the speech LM: what `Model.generate_frame` (reference fireredtts2/llm/llm.py:272-334)
+// Frame tail of the speech LM: what `Model.generate_frame` (reference fireredtts2/llm/llm.py:274-330)
 // runs after the backbone —
 //
-//   c0_logits = codebook0_head(last_h); c0 = sample_topk(c0_logits, topk, temperature)          llm.py:303-304
-//   decoder K/V state reset; positions 0 (projection(last_h)) and 1 (projection(embed(0, c0)))   llm.py:305-321
+//   c0_logits = codebook0_head(last_h); c0 = sample_topk(c0_logits, topk, temperature)          llm.py:305-306
+//   decoder K/V state reset; positions 0 (projection(last_h)) and 1 (projection(embed(0, c0)))   llm.py:307-322
 //   for i = 1 .. ncb-1:  h = decoder(projection(curr))[:, -1]; logits = h @ audio_head[i-1];
-//                        c_i = sample_topk(logits, 10, 0.75); curr = embed(i, c_i)                llm.py:317-328
+//                        c_i = sample_topk(logits, 10, 0.75); curr = embed(i, c_i)                llm.py:318-328
 //
 // `decoder` is torchtune's qwen2 (modules.py:5-82): RMSNorm (eps 1e-6) -> q|k|v projections with bias -> rotary positions
 // on the halves of every head -> grouped-query attention over the frame's <= ncb positions -> output projection ->
@@ -42,7 +42,7 @@ struct FdParams {
   const float* noise;      // (B, ncb, V) Exp(1) draws or null -> counter-based generator
   unsigned long long seed;
   unsigned long long frame;
-  int topk;                // codebook 0 (llm.py:304); codebooks >= 1 use 10 / 0.75 (llm.py:323)
+  int topk;                // codebook 0 (llm.py:306); codebooks >= 1 use 10 / 0.75 (llm.py:324)
   float temperature;
   int has_c0;              // codebook-0 code given by the caller
   int has_forced;          // teacher forcing: every code given
@@ -264,8 +264,8 @@ __device__ __forceinline__ float block_sum(float x, float* red) {
   return r;
 }
 
-// sample_topk + _multinomial_sample_one_no_sync (llm.py:33-49) for codebook s of item blockIdx.x, then the embedding row
-// of the next decoder input, already projected (llm.py:305,320,325-326: projection(audio_embeddings[code + s * V]), a
+// sample_topk + _multinomial_sample_one_no_sync (llm.py:34-49) for codebook s of item blockIdx.x, then the embedding row
+// of the next decoder input, already projected (llm.py:307,321,325-326: projection(audio_embeddings[code + s * V]), a
 // table composed at load), as the next position's residual row.
 //   logits / temperature; k-th largest value by k rounds of "remove the first maximum" (multiplicity counted like
 //   torch.topk); entries < k-th are dropped (ties at the k-th value stay, llm.py:43); log_softmax, softmax, p / q, first
@@ -685,7 +685,7 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
   // timing experiments only (results are wrong with any bit set): marginal cost of a kernel class inside the graph
   static const int skip = getenv("FRT2_FD_SKIP") != nullptr ? atoi(getenv("FRT2_FD_SKIP")) : 0;
   // positions 0 and 1 as ONE two-row pass while 2 B rows fit the GEMM's 8 (the reference's first decoder call has these
-  // two positions too, llm.py:306-321): one weight stream less per frame.  Rows 2b / 2b+1 = position 0 / 1 of item b.
+  // two positions too, llm.py:308-322): one weight stream less per frame.  Rows 2b / 2b+1 = position 0 / 1 of item b.
   const bool pair = pair_layout(B);
   // sampler of codebook s; the projected embedding of its code becomes the residual row of the next position
   auto sample = [&](int s, float* x_next, int x_ld) {
@@ -714,7 +714,7 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
     }
     return FRT2_OK;
   };
-  // llm.py:322-326 for position `pos` (its residual row: x_rows + b * x_ld): final norm (inside the head GEMM),
+  // llm.py:323-326 for position `pos` (its residual row: x_rows + b * x_ld): final norm (inside the head GEMM),
   // audio_head[pos-1], sampler, the next position's residual row b
   auto head_and_sample = [&](int pos, const float* x_rows, int64_t x_ld) -> int {
     if (skip & 32) return FRT2_OK;
@@ -723,7 +723,7 @@ int FrameDecoder::enqueue_frame(int B, cudaStream_t st) {
     FRT2_CUDA_OK(sample(pos, x32, D));
     return FRT2_OK;
   };
-  // codebook 0 and the projection of last_h (position 0; in16 holds last_h): llm.py:303-304,320
+  // codebook 0 and the projection of last_h (position 0; in16 holds last_h): llm.py:305-306,321
   FRT2_TRY(skinny(in16, Db, w_head0, V, nullptr, ACT_NONE, nullptr, logits, ldl, nullptr, 0, nullptr, nullptr, B, st));
   int pos;
   if (pair) {
@@ -814,17 +814,17 @@ int FrameDecoder::enqueue_frame_big(int B, cudaStream_t st) {
     }
     return FRT2_OK;
   };
-  auto head_and_sample = [&](int pos, const float* xrows, int64_t ldx) -> int {                      // llm.py:322-326
+  auto head_and_sample = [&](int pos, const float* xrows, int64_t ldx) -> int {                      // llm.py:323-326
     FRT2_CUDA_OK(rms(xrows, ldx, B, g_final));
     FRT2_TRY(tc32(n16, D, w_heads_rm + static_cast<size_t>(pos - 1) * V * D, V, nullptr, false,
                   logits + static_cast<size_t>(pos) * V, ldl, B, st));
     FRT2_CUDA_OK(sample(pos, x32, D));
     return FRT2_OK;
   };
-  FRT2_TRY(tc32(in16, Db, w_head0_rm, V, nullptr, false, logits, ldl, B, st));                        // llm.py:303
+  FRT2_TRY(tc32(in16, Db, w_head0_rm, V, nullptr, false, logits, ldl, B, st));                        // llm.py:305
   int pos;
   if (pair) {
-    FRT2_TRY(tc32(in16, Db, w_proj_rm, D, nullptr, false, x32, 2 * D, B, st));                         // llm.py:320, rows 2b
+    FRT2_TRY(tc32(in16, Db, w_proj_rm, D, nullptr, false, x32, 2 * D, B, st));                         // llm.py:321, rows 2b
     FRT2_CUDA_OK(sample(0, x32 + D, 2 * D));                                                           // c0 -> rows 2b+1
     FRT2_TRY(layers_pass(2 * B, 0, 2));
     FRT2_TRY(head_and_sample(1, x32 + D, 2 * D));
@@ -994,7 +994,7 @@ int frt2_fd_check_error(frt2_frame_decoder* f, void* cuda_stream) {
   return FRT2_OK;
 }
 
-// single-operator parity hook: sample_topk + _multinomial_sample_one_no_sync (llm.py:33-49) on given logits
+// single-operator parity hook: sample_topk + _multinomial_sample_one_no_sync (llm.py:34-49) on given logits
 int frt2_op_sample_topk(const float* logits, int B, int V, int topk, float temperature, const float* noise, uint64_t seed,
                         int32_t* codes, void* cuda_stream) {
   FRT2_REQUIRE(logits && codes && B >= 1 && V >= 1 && V <= 24000 && topk >= 1 && temperature > 0.f, FRT2_ERR_BAD_ARG,

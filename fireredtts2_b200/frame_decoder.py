@@ -1,4 +1,4 @@
-"""Frame decoder + sampler of the speech LM on the library (reference ``fireredtts2/llm/llm.py:303-334``).
+"""Frame decoder + sampler of the speech LM on the library (reference ``fireredtts2/llm/llm.py:304-330``).
 
 ``Model.generate_frame`` ends with the part that turns the backbone's last hidden state into the frame's
 ``audio_num_codebooks`` codes: ``codebook0_head`` + ``sample_topk`` for codebook 0, then fifteen dependent passes of the
@@ -56,7 +56,7 @@ class FrameDecoderConfig:
 
     def weight_bytes_per_frame(self) -> int:
         """Algorithmic fp16 weight bytes of one frame (the HBM roofline of the frame tail at small batch): the reference runs
-        ``audio_num_codebooks - 1`` decoder calls per frame (llm.py:317-321, the first over two positions), each streams the
+        ``audio_num_codebooks - 1`` decoder calls per frame (llm.py:318-322, the first over two positions), each streams the
         projection and every layer once; plus the codebook-0 head and one ``audio_head`` slice per call."""
         D, Db, I, V, n = self.dim, self.backbone_dim, self.intermediate_dim, self.audio_vocab_size, self.audio_num_codebooks
         layer = D * self.qkv_dim + D * D + 3 * D * I
@@ -158,7 +158,7 @@ class Frt2FdConfig(C.Structure):
 
 
 class FrameDecoderB200:
-    """``generate_codes(last_h, ...)`` -> ``(B, audio_num_codebooks)`` int32 codes of one frame (llm.py:303-334)."""
+    """``generate_codes(last_h, ...)`` -> ``(B, audio_num_codebooks)`` int32 codes of one frame (llm.py:304-330)."""
 
     def __init__(self, cfg: FrameDecoderConfig, state_dict, device="cuda:0", max_batch: int = 8):
         """Frames of up to 16 items always run on the weight-streaming kernels; ``max_batch`` > 16 also keeps row-major weight
@@ -219,15 +219,15 @@ class FrameDecoderB200:
 
     def check_error(self):
         """Synchronise and raise IndexError if a given code was outside ``[0, audio_vocab_size)`` since the last check (the
-        reference raises inside ``nn.Embedding``, llm.py:337-338)."""
+        reference raises inside ``nn.Embedding``, llm.py:336-337)."""
         import torch
         N.check(self._lib.frt2_fd_check_error(self._h, C.c_void_p(torch.cuda.current_stream(self.device_index).cuda_stream)))
 
     def generate_codes(self, last_h, topk: int, temperature: float, c0=None, noise=None, seed: int = 0, forced=None,
                        return_logits: bool = False):
-        """last_h ``(B, backbone_dim)`` fp32 = ``h[:, -1, :]`` of the backbone (llm.py:302).  ``c0`` ``(B,)`` int: codebook-0
+        """last_h ``(B, backbone_dim)`` fp32 = ``h[:, -1, :]`` of the backbone (llm.py:304).  ``c0`` ``(B,)`` int: codebook-0
         codes already sampled by the caller (else ``codebook0_head`` + ``sample_topk(topk, temperature)`` run here,
-        llm.py:303-304).  ``noise`` ``(B, ncb, V)`` fp32: the Exp(1) draws ``q`` of ``_multinomial_sample_one_no_sync`` per
+        llm.py:305-306).  ``noise`` ``(B, ncb, V)`` fp32: the Exp(1) draws ``q`` of ``_multinomial_sample_one_no_sync`` per
         codebook (parity tests); ``None`` -> the library's counter-based generator keyed by ``seed``.  ``forced``
         ``(B, ncb)`` int: teacher forcing — the returned codes are these, the logits are still computed from them.
         -> codes ``(B, ncb)`` int32 on the device [, logits ``(B, ncb, V)`` fp32]."""

@@ -228,10 +228,10 @@ int frt2_enc_audio_features(frt2_encoder* e, const float* audio16k, int64_t audi
                             float* mel_out, float* ssl_out, float* aco_out, int64_t* launches, void* cuda_stream);
 
 /* ---- frame tail of the speech LM: replaces the part of Model.generate_frame behind the backbone ----
- * fireredtts2/llm/llm.py:303-334: codebook0_head + sample_topk (llm.py:303-304), the per-frame reset of the decoder's
- * K/V state (llm.py:316), and for i = 1 .. ncb-1 decoder(projection(curr_h)) -> audio_head[i-1] -> sample_topk(., 10,
- * 0.75) -> _embed_audio(i, .) (llm.py:317-328).  `decoder` = torchtune qwen2 (llm/modules.py:5-82).  One CUDA graph per
- * frame; the backbone (llm.py:292-301) stays with the caller. */
+ * fireredtts2/llm/llm.py:304-330: codebook0_head + sample_topk (llm.py:305-306), the per-frame reset of the decoder's
+ * K/V state (llm.py:317), and for i = 1 .. ncb-1 decoder(projection(curr_h)) -> audio_head[i-1] -> sample_topk(., 10,
+ * 0.75) -> _embed_audio(i, .) (llm.py:318-328).  `decoder` = torchtune qwen2 (llm/modules.py:5-82).  One CUDA graph per
+ * frame; the backbone (llm.py:292-302) stays with the caller. */
 typedef struct {
   int32_t backbone_dim;        /* FLAVORS[backbone_flavor] embed_dim = width of last_h / audio_embeddings (llm.py:98-104) */
   int32_t dim;                 /* decoder flavor: embed_dim, num_layers, num_heads, num_kv_heads, intermediate_dim */
@@ -257,12 +257,12 @@ int frt2_fd_load_tensor(frt2_frame_decoder* f, const char* key, const float* dat
                         int on_device);
 int frt2_fd_finalize(frt2_frame_decoder* f);
 void frt2_fd_destroy(frt2_frame_decoder* f);
-/* One frame for B <= max(16, max_batch) items.  last_h: device fp32 (B, backbone_dim) = h[:, -1, :] of the backbone (llm.py:302).
+/* One frame for B <= max(16, max_batch) items.  last_h: device fp32 (B, backbone_dim) = h[:, -1, :] of the backbone (llm.py:304).
  * c0: optional device int32 (B) codebook-0 codes sampled by the caller (NULL: sampled here with topk / temperature).
  * noise: optional device fp32 (B, ncb, V), the Exp(1) draws q of _multinomial_sample_one_no_sync (llm.py:34-36) per
  * codebook (parity tests feed the reference's own draws); NULL: counter-based Philox draws keyed by (seed, frame counter
  * of the handle, item, codebook, entry).  forced: optional device int32 (B, ncb): teacher forcing (every code given; the
- * logits are those of the forced history).  codes: device int32 (B, ncb) — the curr_sample of llm.py:334 (the codec's
+ * logits are those of the forced history).  codes: device int32 (B, ncb) — the curr_sample of llm.py:330 (the codec's
  * token operand: frt2_decode_chunk(tokens = codes, idx_bytes 4, sB = ncb, sQ = 1, sL = 1)).  logits: optional device fp32
  * (B, ncb, V): c0_logits at [:, 0] (only when c0 == NULL), ci_logits at [:, i].  Asynchronous on the stream; a given code
  * outside [0, V) is reported by frt2_fd_check_error (the reference raises IndexError in nn.Embedding). */
@@ -335,7 +335,7 @@ int frt2_op_attention(int impl, const void* q16, const void* k16, const void* v1
 /* debug: while dev_buf (16*128*8 uint32, device) is set, CTA 0 of the persistent tcgen05 attention kernel writes
  * clock64 stamps of its softmax / MMA-issue phases there (tools/attn_trace.py); NULL switches it off. */
 int frt2_op_attention_trace(void* dev_buf);
-/* sample_topk + _multinomial_sample_one_no_sync (llm.py:33-49): logits (B, V) device fp32, noise (B, V) Exp(1) draws or NULL
+/* sample_topk + _multinomial_sample_one_no_sync (llm.py:34-49): logits (B, V) device fp32, noise (B, V) Exp(1) draws or NULL
  * (Philox draws keyed by seed, item, entry), codes (B) device int32.  Synchronises the stream. */
 int frt2_op_sample_topk(const float* logits, int B, int V, int topk, float temperature, const float* noise, uint64_t seed,
                         int32_t* codes, void* cuda_stream);

@@ -3,8 +3,8 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s checker legs may import this module; the product path
 (``fireredtts2_b200/``) never does.
 
-What is restated: ``fireredtts2/llm/llm.py:303-334`` (codebook-0 head, ``sample_topk``, the fifteen dependent decoder
-passes with ``projection`` / ``audio_head`` / ``_embed_audio``) and ``llm.py:33-49`` (``_multinomial_sample_one_no_sync``,
+What is restated: ``fireredtts2/llm/llm.py:304-330`` (codebook-0 head, ``sample_topk``, the fifteen dependent decoder
+passes with ``projection`` / ``audio_head`` / ``_embed_audio``) and ``llm.py:34-49`` (``_multinomial_sample_one_no_sync``,
 ``sample_topk``).  The transformer inside (``self.decoder``) is NOT in /root/reference: it is ``torchtune.models.qwen2.
 qwen2`` (requirements.txt:1 ``torchtune``, unpinned, absent from this image) — the published Qwen2 decoder block: RMSNorm
 (eps 1e-6, fp32), grouped-query attention with biased q/k/v projections and an unbiased output projection, rotary
@@ -95,7 +95,7 @@ def sample_topk(logits, topk, temperature, q):
 
 
 def generate_codes(sd, cfg, last_h, topk, temperature, noise, c0=None, forced=None):
-    """llm.py:302-334 from ``last_h`` on.  noise (B, ncb, V) = the draws q of codebook i at [:, i].  ``forced`` (B, ncb)
+    """llm.py:304-330 from ``last_h`` on.  noise (B, ncb, V) = the draws q of codebook i at [:, i].  ``forced`` (B, ncb)
     replaces every sampled code (teacher forcing; the logits are still those of the forced history).
     -> codes (B, ncb) int32, logits (B, ncb, V) fp32 (row 0 = c0_logits; zeros when c0 is given)."""
     sd = {k: np.asarray(v, dtype=F32) for k, v in sd.items()}
@@ -105,17 +105,17 @@ def generate_codes(sd, cfg, last_h, topk, temperature, noise, c0=None, forced=No
     codes = np.zeros((B, n), np.int32)
     last_h = last_h.astype(F32)
     if c0 is None:
-        logits[:, 0] = last_h @ sd["codebook0_head.weight"].T                          # llm.py:303
-        c0 = sample_topk(logits[:, 0], topk, temperature, noise[:, 0])                 # llm.py:304
+        logits[:, 0] = last_h @ sd["codebook0_head.weight"].T                          # llm.py:305
+        c0 = sample_topk(logits[:, 0], topk, temperature, noise[:, 0])                 # llm.py:306
     codes[:, 0] = forced[:, 0] if forced is not None else c0
-    kc = [np.zeros((B, 0, cfg.num_kv_heads, cfg.head_dim), F32) for _ in range(cfg.num_layers)]   # llm.py:316 reset_caches
+    kc = [np.zeros((B, 0, cfg.num_kv_heads, cfg.head_dim), F32) for _ in range(cfg.num_layers)]   # llm.py:317 reset_caches
     vc = [np.zeros((B, 0, cfg.num_kv_heads, cfg.head_dim), F32) for _ in range(cfg.num_layers)]
     P = sd["projection.weight"].T
-    decoder_position(sd, cfg, last_h @ P, 0, kc, vc)                                   # position 0 of llm.py:306,319-321
+    decoder_position(sd, cfg, last_h @ P, 0, kc, vc)                                   # position 0 of llm.py:308,320-322
     for i in range(1, n):
-        emb = sd["audio_embeddings.weight"][codes[:, i - 1] + (i - 1) * V]             # llm.py:305,325 (_embed_audio)
+        emb = sd["audio_embeddings.weight"][codes[:, i - 1] + (i - 1) * V]             # llm.py:307,325 (_embed_audio)
         h = decoder_position(sd, cfg, emb @ P, i, kc, vc)
-        logits[:, i] = h @ sd["audio_head"][i - 1]                                     # llm.py:322
-        ci = sample_topk(logits[:, i], 10, 0.75, noise[:, i])                          # llm.py:323
+        logits[:, i] = h @ sd["audio_head"][i - 1]                                     # llm.py:323
+        ci = sample_topk(logits[:, i], 10, 0.75, noise[:, i])                          # llm.py:324
         codes[:, i] = forced[:, i] if forced is not None else ci
     return codes, logits

@@ -2,7 +2,7 @@
 
     python oracle/make_golden_frame_decoder.py     # writes tests/golden/fd_*.npz
 
-``fireredtts2/llm/llm.py`` is imported UNMODIFIED from /root/reference and ``Model.generate_frame`` (llm.py:272-334) runs as
+``fireredtts2/llm/llm.py`` is imported UNMODIFIED from /root/reference and ``Model.generate_frame`` (llm.py:274-330) runs as
 it is.  Its transformer blocks come from ``torchtune`` (requirements.txt:1), which is not in this image and cannot be
 installed (no network); a ``torchtune`` shim registered in ``sys.modules`` below provides ``qwen2(...)`` /
 ``TransformerDecoder`` with exactly the surface the reference touches (``tok_embeddings``, ``output``, ``max_seq_len``,
@@ -169,7 +169,7 @@ def run_case(cfg, B, wseed, dseed, topk, temperature):
     try:
         torch.manual_seed(dseed)
         with torch.inference_mode():
-            codes = model.generate_frame(tokens, tokens_mask, input_pos, temperature, topk)     # llm.py:272-334
+            codes = model.generate_frame(tokens, tokens_mask, input_pos, temperature, topk)     # llm.py:274-330
     finally:
         ref_llm.sample_topk, torch.Tensor.exponential_ = real_sample, real_exp
         hook.remove()

@@ -1,5 +1,5 @@
 """Frame tail of the speech LM on the library (csrc/frame_decoder.cu through the C ABI) against the oracle and the goldens
-recorded from the reference's own Model.generate_frame (llm.py:272-334)."""
+recorded from the reference's own Model.generate_frame (llm.py:274-330)."""
 import numpy as np
 import pytest
 import torch
@@ -176,7 +176,7 @@ def test_out_of_range_code_raises_index_error():
     cfg, sd, fd = build("FD_TINY", 3)
     last_h, noise = synthetic_frame_inputs(cfg, 2, seed=1)
     forced = np.zeros((2, cfg.audio_num_codebooks), np.int32)
-    forced[1, 2] = cfg.audio_vocab_size       # nn.Embedding would raise IndexError (llm.py:337-338)
+    forced[1, 2] = cfg.audio_vocab_size       # nn.Embedding would raise IndexError (llm.py:336-337)
     fd.generate_codes(cuda(last_h), 5, 1.0, noise=cuda(noise), forced=cuda(forced))
     with pytest.raises(IndexError):
         fd.check_error()
@@ -207,7 +207,7 @@ def test_library_generator_is_counter_based():
 @pytest.mark.parametrize("V,topk,temperature", [(64, 8, 0.9), (2048, 10, 0.75), (2048, 30, 0.9), (2051, 50, 1.0), (512, 512, 1.3),
                                                 (2048, 1, 0.5)])
 def test_sample_topk_matches_oracle(V, topk, temperature):
-    """Index work: identical to the restated llm.py:33-49 on the same logits and draws, duplicates at the k-th value included."""
+    """Index work: identical to the restated llm.py:34-49 on the same logits and draws, duplicates at the k-th value included."""
     rng = np.random.default_rng(V + topk)
     B = 64
     logits = (2.0 * rng.standard_normal((B, V))).astype(np.float32)

@@ -325,7 +325,7 @@ def load_fd_case(name, preset):
 
 @pytest.mark.parametrize("name,preset", FD_CASES)
 def test_frame_decoder_oracle_matches_reference_generate_frame(name, preset):
-    """oracle.frame_decoder_oracle.generate_codes against the reference's own Model.generate_frame (llm.py:272-334; Qwen2
+    """oracle.frame_decoder_oracle.generate_codes against the reference's own Model.generate_frame (llm.py:274-330; Qwen2
     blocks from Hugging Face transformers behind a torchtune shim): same codes, logits to fp32 summation order."""
     from oracle import frame_decoder_oracle as FO
     cfg, sd, g, topk, temperature = load_fd_case(name, preset)
@@ -351,7 +351,7 @@ def test_sample_topk_oracle_edge_cases():
 
 
 def test_sample_topk_oracle_matches_the_reference_sampler():
-    """oracle.sample_topk against the reference's own sample_topk / _multinomial_sample_one_no_sync (llm.py:33-49) on seeded
+    """oracle.sample_topk against the reference's own sample_topk / _multinomial_sample_one_no_sync (llm.py:34-49) on seeded
     logits with exact ties at the k-th value; the Exp(1) draws are the ones the reference made (tests/golden/fd_sampler.npz)."""
     import os
     from oracle import frame_decoder_oracle as FO
