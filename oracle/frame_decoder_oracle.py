@@ -50,7 +50,7 @@ def silu(x):
 
 
 def decoder_position(sd, cfg, x, pos, kc, vc):
-    """One position of ``self.decoder`` (tok_embeddings / output are Identity, llm.py:10-14).  x (B, dim); kc / vc are
+    """One position of ``self.decoder`` (tok_embeddings / output are Identity, llm.py:9-13).  x (B, dim); kc / vc are
     per-layer lists of (B, pos, Hk, hd) arrays holding positions < pos, extended in place.  -> (B, dim) after ``norm``."""
     H, Hk, hd = cfg.num_heads, cfg.num_kv_heads, cfg.head_dim
     cos, sin = rope_tables(hd, pos + 1, cfg.rope_base)
