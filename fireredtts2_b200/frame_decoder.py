@@ -268,6 +268,62 @@ class FrameDecoderB200:
         return (codes, logits) if return_logits else codes
 
 
+class GenerateFrameB200:
+    """Drop-in for the bound method ``Model.generate_frame`` (llm.py:274-330): the same five arguments, the same
+    ``(batch_size, audio_num_codebooks)`` int32 result, so ``FireRedTTS2``'s frame loops (``fireredtts2.py:173-192,
+    228-247``) run unchanged after ``GenerateFrameB200.install(model)``.
+
+    Lines 292-302 — the causal-mask lookup, the masked sum of the text / audio token embeddings, the backbone and its K/V
+    state — stay the reference's OWN modules, called exactly as the reference calls them (the backbone is outside SURVEY
+    §8).  Everything behind ``last_h = h[:, -1, :]`` (llm.py:304-330) is one ``FrameDecoderB200.generate_codes`` call, i.e.
+    one captured CUDA graph on the library; ``self.decoder`` of the reference is never run (its per-frame
+    ``reset_caches()`` at llm.py:317 has nothing left to reset: the library owns the frame's K/V rows).
+
+    Random draws: the reference draws ``q ~ Exp(1)`` from torch's global generator (llm.py:34-36); here the library's
+    counter-based generator is keyed by ``seed`` and its own frame counter, so a seeded run is reproducible and
+    independent of torch's generator state.  ``noise`` (tests) feeds given draws instead.
+    """
+
+    def __init__(self, model, tail: Optional["FrameDecoderB200"] = None, device=None, max_batch: int = 8, seed: int = 0):
+        self.model = model
+        if tail is None:
+            if device is None:
+                device = next(model.parameters()).device
+            tail = FrameDecoderB200.from_reference(model, device, max_batch)
+        self.tail = tail
+        self.seed = int(seed)
+        self.noise = None       # (B, audio_num_codebooks, audio_vocab_size) Exp(1) draws for the NEXT call only (parity tests)
+
+    @classmethod
+    def install(cls, model, **kw) -> "GenerateFrameB200":
+        """``model.generate_frame`` becomes this object (an instance attribute shadowing the class's method);
+        ``uninstall()`` gives the reference's method back."""
+        g = cls(model, **kw)
+        model.__dict__["generate_frame"] = g
+        return g
+
+    def uninstall(self) -> None:
+        if self.model.__dict__.get("generate_frame") is self:
+            del self.model.__dict__["generate_frame"]
+
+    def __call__(self, tokens, tokens_mask, input_pos, temperature: float, topk: int):
+        import torch
+        m = self.model
+        dtype = next(m.parameters()).dtype                                             # llm.py:292
+        assert m.backbone.caches_are_enabled(), "backbone caches are not enabled"      # llm.py:295
+        curr_backbone_mask = m.backbone_causal_mask[input_pos, :]                      # _index_causal_mask, llm.py:20-31,296
+        embeds = m._embed_tokens(tokens)                                               # llm.py:297, 339-352
+        h = (embeds * tokens_mask.unsqueeze(-1)).sum(dim=2)                            # llm.py:298-299
+        h = m.backbone(h, input_pos=input_pos, mask=curr_backbone_mask).to(dtype=dtype)  # llm.py:300-302
+        last_h = h[:, -1, :]                                                           # llm.py:304
+        noise, self.noise = self.noise, None
+        codes = self.tail.generate_codes(last_h.detach().to(torch.float32), int(topk), float(temperature), noise=noise,
+                                         seed=self.seed)                               # llm.py:305-330
+        return codes.to(device=tokens.device)
+
+    generate_frame = __call__
+
+
 def sample_topk(logits, topk: int, temperature: float, noise=None, seed: int = 0):
     """``sample_topk`` of the reference (llm.py:39-49) on the library: logits ``(B, V)`` fp32 on a CUDA device, ``noise``
     ``(B, V)`` = the Exp(1) draws (None: the library's generator) -> ``(B,)`` int32."""

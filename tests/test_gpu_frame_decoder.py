@@ -306,3 +306,108 @@ def test_frame_tail_feeds_a_pool_of_concurrent_streams():
             ref.append(a)
         _, snr = report(f"frame tail -> pool slot {s}", np.concatenate(ref, axis=1)[0], to_np(torch.cat(chunks[s])))
         assert snr >= SNR_GATE_DB
+
+
+def test_generate_frame_drop_in_on_a_reference_shaped_model():
+    """GenerateFrameB200.install(model) on a module tree with the reference's names (Model.projection / audio_embeddings /
+    codebook0_head / audio_head / decoder.layers[i], torchtune parameter names) living on the GPU: the tail is built by
+    from_reference from the live tensors, ``model.generate_frame(tokens, tokens_mask, input_pos, temperature, topk)``
+    (llm.py:274-330's signature) runs the model's own embedding sum and backbone and hands ``h[:, -1, :]`` to the library.
+    The backbone is a stand-in (out of scope); the codes must equal, bit for bit, those of the library called directly on
+    the same last_h, and the oracle's.  (The same host logic against the REAL generate_frame: tests/test_host.py.)"""
+    from fireredtts2_b200.frame_decoder import GenerateFrameB200
+    cfg, sd, fd = build("FD_TINY", 3)
+    n, V, D = cfg.audio_num_codebooks, cfg.audio_vocab_size, cfg.backbone_dim
+    dev = torch.device("cuda:0")
+
+    class Holder(torch.nn.Module):
+        pass
+
+    def grow(root, dotted, tensor):
+        *path, leaf = dotted.split(".")
+        m = root
+        for p in path:
+            if not hasattr(m, p):
+                setattr(m, p, Holder())
+            m = getattr(m, p)
+        setattr(m, leaf, torch.nn.Parameter(torch.from_numpy(np.ascontiguousarray(tensor))))
+
+    class Backbone(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(11)
+            self.w = torch.nn.Parameter(torch.randn(D, D, generator=g) / D ** 0.5)
+            self.enabled, self.seen = True, []
+
+        def caches_are_enabled(self):
+            return self.enabled
+
+        def forward(self, h, input_pos=None, mask=None):
+            self.seen.append((tuple(h.shape), tuple(mask.shape)))
+            return torch.tanh(h @ self.w) + 0.01 * input_pos.unsqueeze(-1).to(h.dtype)
+
+    class Model(Holder):
+        def _embed_tokens(self, tokens):                                   # llm.py:339-352
+            text = torch.nn.functional.embedding(tokens[:, :, -1], self.text_embeddings.weight).unsqueeze(-2)
+            idx = tokens[:, :, :-1] + V * torch.arange(n, device=tokens.device)
+            audio = torch.nn.functional.embedding(idx.reshape(-1), self.audio_embeddings.weight).reshape(
+                tokens.size(0), tokens.size(1), n, -1)
+            return torch.cat([audio, text], dim=-2)
+
+    model = Model()
+    model.decoder = Holder()
+    model.decoder.layers = torch.nn.ModuleList([Holder() for _ in range(cfg.num_layers)])
+    for k, v in sd.items():
+        if k.startswith("decoder.layers."):
+            _, _, i, rest = k.split(".", 3)
+            grow(model.decoder.layers[int(i)], rest, v)
+        else:
+            grow(model, k, v)
+    for l in model.decoder.layers:
+        l.attn.num_heads = cfg.num_heads
+    model.config = type("Cfg", (), {"audio_vocab_size": V, "audio_num_codebooks": n})()
+    model.backbone = Backbone()
+    g = torch.Generator().manual_seed(12)
+    grow(model, "text_embeddings.weight", torch.randn(32, D, generator=g).numpy())
+    model.register_buffer("backbone_causal_mask", torch.tril(torch.ones(64, 64, dtype=torch.bool)))
+    model = model.to(dev)
+
+    gen = GenerateFrameB200.install(model, seed=5)
+    assert model.generate_frame is gen and gen.tail.cfg == cfg
+
+    B, S = 2, 5
+    tokens = torch.zeros(B, S, n + 1, dtype=torch.long)
+    tokens[:, :, :n] = torch.randint(0, V, (B, S, n), generator=g)
+    tokens[:, :, n] = torch.randint(0, 32, (B, S), generator=g)
+    mask = torch.ones(B, S, n + 1, dtype=torch.bool)
+    tokens, mask = tokens.to(dev), mask.to(dev)
+    pos = torch.arange(S, device=dev)[None].repeat(B, 1)
+    rng = np.random.default_rng(13)
+    for f in range(3):
+        noise = rng.exponential(1.0, (B, n, V)).astype(np.float32)
+        with torch.inference_mode():
+            h = (model._embed_tokens(tokens) * mask.unsqueeze(-1)).sum(dim=2)
+            last_h = (torch.tanh(h @ model.backbone.w) + 0.01 * pos.unsqueeze(-1).float())[:, -1, :]
+            gen.noise = cuda(noise)
+            sample = model.generate_frame(tokens, mask, pos, 0.9, 8)
+        assert sample.dtype == torch.int32 and tuple(sample.shape) == (B, n) and sample.device == tokens.device
+        direct = fd.generate_codes(last_h, 8, 0.9, noise=cuda(noise))
+        assert torch.equal(sample, direct)
+        ref_codes, _ = FO.generate_codes(sd, cfg, to_np(last_h), 8, 0.9, noise)
+        same = to_np(sample) == ref_codes
+        print(f"[parity] generate_frame drop-in, frame {f}: codes equal to the oracle's: {int(same.sum())} / {same.size}")
+        assert same.mean() >= 0.9
+        tokens = torch.cat([sample, torch.zeros(B, 1, device=dev).long()], dim=1).unsqueeze(1)          # fireredtts2.py:183-191
+        mask = torch.cat([torch.ones_like(sample).bool(), torch.zeros(B, 1, device=dev).bool()], dim=1).unsqueeze(1)
+        pos = pos[:, -1:] + 1
+    assert model.backbone.seen[0] == ((B, S, D), (B, S, 64)) and model.backbone.seen[-1] == ((B, 1, D), (B, 1, 64))
+    # library draws: reproducible for a seed, the frame counter advances them
+    a = model.generate_frame(tokens, mask, pos, 0.9, 8)
+    b = model.generate_frame(tokens, mask, pos, 0.9, 8)
+    assert a.shape == b.shape and not torch.equal(a, b)
+    gen.tail.check_error()
+    model.backbone.enabled = False
+    with pytest.raises(AssertionError):
+        model.generate_frame(tokens, mask, pos, 0.9, 8)
+    gen.uninstall()
+    assert "generate_frame" not in model.__dict__
