@@ -53,7 +53,9 @@ int frt2_create(const frt2_config* cfg, int device, frt2_handle** out);
 /* Hand over one tensor of the reference state_dict by its reference key (e.g.
  * "acoustic_decoder.backbone.transformers.3.fc1.weight", "rvq.quantizers.0.codebook",
  * "rvq.output_proj.parametrizations.weight.original0").  fp32, reference layout, contiguous;
- * host pointer (on_device = 0) or device pointer.  Keys the decode path does not use are ignored. */
+ * host pointer (on_device = 0) or device pointer.  Keys the decode path does not use are ignored.  Replaces
+ * codec.load_state_dict(ckpt) (model.py:214-215); the weight-norm pairs original0 / original1 are materialised as
+ * rvq.py:8-13 does on every forward. */
 int frt2_load_tensor(frt2_handle* h, const char* key, const float* data, int ndim, const int64_t* shape,
                      int on_device);
 /* One-time repack on the GPU: weight-norm materialisation (rvq.py:8-13), folded RVQ tables, tap-major
@@ -103,7 +105,8 @@ int frt2_peer_free(int device, void* ptr);
  * The stream object owns what the reference keeps in cache_dict (up_conv_cache, bb_conv_cache1/2, bb_kv_cache,
  * is_cache) in HBM, updated in place. */
 int frt2_stream_create(frt2_handle* h, int B, int max_tokens, frt2_stream** out);
-/* Back to "no token consumed".  Stream-ordered: nothing runs here; the state is cleared by a kernel on the CUDA stream
+/* Back to "no token consumed" — the reference's fresh cache_dict = {} of a new utterance (model.py:346-355 take the
+ * "cache is None" branches).  Stream-ordered: nothing runs here; the state is cleared by a kernel on the CUDA stream
  * of the next decode call, after everything the state's previous user enqueued (no device synchronisation). */
 int frt2_stream_reset(frt2_stream* s);
 /* The reference's call pattern is decode_one_token(token, {}, last) with a fresh cache_dict per utterance
@@ -157,7 +160,8 @@ int frt2_pool_step(frt2_handle* h, frt2_stream* pool, const void* tokens, int id
 /* tokens consumed so far by one slot of a pool */
 int frt2_pool_slot_tokens(const frt2_stream* pool, int slot);
 
-/* Export / import the state in the reference's cache_dict layouts (fp32, contiguous, device):
+/* Export / import the state in the reference's cache_dict layouts (model.py:346-375; the five tensors are produced at
+ * decoder.py:624-655 [up_conv_cache], :275-320 [bb_conv_cache1/2, bb_kv_cache], :407-468 [is_cache]) — fp32, contiguous, device:
  * up_conv_cache (B,E,3), bb_conv_cache1 (B,E,6), bb_conv_cache2 (B,8E,2), bb_kv_cache (B,layers,H,T,2*hd)
  * with T = 8*frt2_stream_tokens(s), is_cache (B,n_fft,3).  Any pointer may be NULL (skipped). */
 int frt2_export_state(frt2_handle* h, const frt2_stream* s, float* up_conv_cache, float* bb_conv_cache1,
@@ -298,13 +302,18 @@ int frt2_decode_resampled(frt2_handle* h, const void* tokens, int idx_bytes, int
  * either may be NULL. */
 int frt2_rvq_gather(frt2_handle* h, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
                     int nq, int L, float* rows, float* sum, void* cuda_stream);
-/* Copy an intermediate of the most recent frt2_decode into out (device fp32, time-major (B,T,C)):
+/* Copy an intermediate of the most recent frt2_decode into out (device fp32, time-major (B,T,C)) — the values the
+ * reference holds inside ResidualVQ.decode_codes (rvq.py:145-164: "emb" before, "z" after output_proj), after UpConv
+ * (model.py:142-148: "x50"), after the upsample convs (decoder.py:610-616: "up"), inside CausalVocosBackbone.forward
+ * (decoder.py:258-273: "prior" after prior_net :260, "layer0" / "layers" after the first / last layer :267-268, "final"
+ * after final_norm :273), and in the iSTFT head (decoder.py:503-518: "spec"; :380-381: "frames" = windowed irfft):
  * "emb" (B,L,rvq_dim), "z" (B,L,E), "x50" (B,4L,E), "up" (B,8L,E), "prior", "layer0", "layers", "final",
  * "spec" (B,8L,2*n_bins interleaved re,im), "frames" (B,8L,n_fft).  Requires frt2_set_debug(h, 1) before
  * the decode.  Returns the number of floats written through *n. */
 int frt2_set_debug(frt2_handle* h, int flags);
 int frt2_get_tap(frt2_handle* h, const char* name, float* out, int64_t capacity, int64_t* n, void* cuda_stream);
-/* Synchronise the stream and translate the handle's device-side error word (out-of-range code index of an OFFLINE decode /
+/* Synchronise the stream and translate the handle's device-side error word (out-of-range code index of an OFFLINE decode —
+ * the reference raises IndexError inside F.embedding, rvq.py:58 — /
  * frt2_rvq_gather since the last check) into a status.  Streams and pools have their own words: frt2_stream_check_error. */
 int frt2_check_error(frt2_handle* h, void* cuda_stream);
 
@@ -318,8 +327,10 @@ enum { FRT2_PROF_GEMM = 0, FRT2_PROF_ATTN_TC = 1, FRT2_PROF_ATTN_WARP = 2, FRT2_
 int frt2_profile(frt2_handle* h, int enable);
 int frt2_profile_get(frt2_handle* h, int cls, double* ms, int64_t* launches, double* flops, double* bytes);
 
-/* ---- single-operator entry points (unit parity tests and per-kernel roofline benches) ---- */
-/* C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias) (+ resid); A,W fp16 device, fp32 accumulate.
+/* ---- single-operator entry points (unit parity tests and per-kernel roofline benches) ----
+ * Each is one kernel of the path on its own, checked against the torch fp32 op the reference calls there. */
+/* The nn.Linear / Conv1d / ConvTranspose1d contractions of the path (model.py:142-148, decoder.py:78-101,571-589,
+ * whisper.py:37-40,137-138, decoder.py:503): C[M,N] = act(alpha * A[M,K] * W[N,K]^T + bias) (+ resid); A,W fp16 device, fp32 accumulate.
  * impl 0 = tcgen05/TMEM/TMA kernel, 1 = SIMT check kernel, 2 = skinny weight-streaming kernel (<= 16 rows), 3 = the frame
  * tail's persistent weight-streaming kernel (one batch of <= 16 rows that fit its shared-memory tile, K a multiple of 32; act 3 = SwiGLU on interleaved
  * (gate, up) weight rows: out16 is (rows, N/2); the weights are repacked inside the call, which synchronises).  ntaps > 1: causal conv over `batches` items of
@@ -327,9 +338,12 @@ int frt2_profile_get(frt2_handle* h, int cls, double* ms, int64_t* launches, dou
 int frt2_op_gemm(int impl, const void* A16, const void* W16, int batches, int rows_per_batch, int Kc, int ntaps,
                  int N, float alpha, const float* bias, int act, const float* resid, float* out32, void* out16,
                  void* cuda_stream);
+/* nn.LayerNorm over channels (+ the nn.SiLU behind it in CausalResnetBlock): decoder.py:119-121,127-129,246; whisper.py:134,140. */
 int frt2_op_layer_norm(const float* x, int rows, int C, const float* gamma, const float* beta, float eps,
                        int apply_silu, void* out16, void* cuda_stream);
-/* q,k,v,out: fp16 (B,T,H*hd) contiguous.  impl 0 = tcgen05 flash kernel, 1 = warp kernel. */
+/* F.scaled_dot_product_attention of WhisperSdpaAttention (whisper.py:49-79 with the block-causal mask of utils.py:19-38:
+ * key j visible to query i iff j <= (i | 7); whisper.py:81-118 chunked: Tq new queries at q_pos0 over Tk keys, no mask).
+ * q,k,v,out: fp16 (B,T,H*hd) contiguous.  impl 0 = tcgen05 flash kernel, 1 = warp kernel. */
 int frt2_op_attention(int impl, const void* q16, const void* k16, const void* v16, void* out16, int B, int H,
                       int hd, int Tq, int Tk, int q_pos0, int block_causal, void* cuda_stream);
 /* debug: while dev_buf (16*128*8 uint32, device) is set, CTA 0 of the persistent tcgen05 attention kernel writes
@@ -339,6 +353,8 @@ int frt2_op_attention_trace(void* dev_buf);
  * (Philox draws keyed by seed, item, entry), codes (B) device int32.  Synchronises the stream. */
 int frt2_op_sample_topk(const float* logits, int B, int V, int topk, float temperature, const float* noise, uint64_t seed,
                         int32_t* codes, void* cuda_stream);
+/* ISTFT's window / fold / envelope division / trim (decoder.py:380-405 offline; :407-468 chunked with the three cached
+ * windowed frames `tail` and the first / last trimming rules). */
 int frt2_op_overlap_add(const float* frames, const float* tail, const float* window, const int32_t* lengths,
                         float* audio, int64_t audio_pitch, int B, int T, int n_fft, int hop, int first, int last,
                         void* cuda_stream);
