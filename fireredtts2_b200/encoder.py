@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import dataclasses
-from typing import Any, Dict, Iterable, List, Optional
+from typing import Any, Dict, List, Optional
 
 import numpy as np
 import torch

@@ -8,7 +8,6 @@ the box's host cores.  /root/reference cannot travel to the GPU box; this port (
 """
 from __future__ import annotations
 
-import math
 from typing import Dict
 
 import numpy as np

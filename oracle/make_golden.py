@@ -19,7 +19,6 @@ import sys
 
 import numpy as np
 import torch
-import torch.nn as nn
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)

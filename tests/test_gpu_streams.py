@@ -10,7 +10,6 @@ import numpy as np
 import pytest
 import torch
 
-from fireredtts2_b200 import _native as N
 from fireredtts2_b200.codec import StreamDecoder, StreamPoolIndexError
 from fireredtts2_b200.config import SMALL, TINY
 from fireredtts2_b200.weights import synthetic_state_dict, synthetic_tokens

@@ -1,7 +1,7 @@
 """ncu csv (--metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum over the launches of one decode
 step) -> the per-kernel DRAM traffic JSON bench.py reads for `roofline.traffic` (profiles/rNN_dram_traffic.json).
 usage: python tools/dram_traffic.py launches_dram.csv "source description" > profiles/r02_dram_traffic.json"""
-import collections, csv, io, json, sys
+import collections, json, sys
 
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.abspath(__file__)))
 from ncu_summary import rows_of, short  # noqa: E402

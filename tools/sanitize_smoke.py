@@ -13,7 +13,6 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-import numpy as np
 import torch
 
 from fireredtts2_b200.codec import RedCodecB200, StreamDecoder
