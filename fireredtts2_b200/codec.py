@@ -204,7 +204,8 @@ class RedCodecB200(torch.nn.Module):
     @torch.inference_mode()
     def decode(self, tokens: torch.Tensor, lengths: Optional[torch.Tensor] = None, pcm16: bool = False) -> torch.Tensor:
         """RedCodecInfer.decode (reference model.py:307-324).  Extensions: ``lengths`` (B,) int32 token counts for
-        ragged batches (item b equals a standalone decode of its first lengths[b] tokens); ``pcm16=True`` returns
+        ragged batches (item b equals a standalone decode of its first lengths[b] tokens — within the parity tolerance where the
+        two batch shapes are served by different kernels; a count <= 0 gives zeros, one beyond L is L); ``pcm16=True`` returns
         the int16 PCM of the reference's wire format, ``(audio * 32767).astype(int16)``, straight from the kernel."""
         tokens = self._prep_tokens(tokens)
         B, nq, L = tokens.shape

@@ -67,7 +67,8 @@ void frt2_destroy(frt2_handle* h);
  * tokens: device, (B,nq,L) integers of idx_bytes (4 or 8) with ELEMENT strides sB,sQ,sL (any strides: the
  * production caller passes a permuted int32 view, fireredtts2.py:196).  audio: device fp32 (B, 8*hop*L) with
  * row pitch audio_pitch elements.  lengths: optional device int32 (B) of per-item token counts L_b <= L
- * (extension; item b then equals a standalone decode of its first L_b tokens, remaining samples are 0);
+ * (extension; item b then equals a standalone decode of its first L_b tokens — bit for bit when the same kernels serve
+ * both batch shapes, within the parity tolerance otherwise — remaining samples are 0; L_b <= 0: all zeros, L_b > L: L);
  * NULL reproduces the reference (every item has L tokens). */
 int frt2_decode(frt2_handle* h, const void* tokens, int idx_bytes, int64_t sB, int64_t sQ, int64_t sL, int B,
                 int nq, int L, const int32_t* lengths, float* audio, int64_t audio_pitch, void* cuda_stream);

@@ -222,6 +222,38 @@ def test_varlen_lengths_extension():
     assert np.all(a[1, (L - 4) * spt:] == 0)
 
 
+def test_varlen_lengths_edge_values():
+    """Ragged batches at the edges of the ``lengths`` extension: an item of zero tokens (an empty turn) and a negative
+    count decode to all zeros, a count beyond L is clamped to L; the neighbours are bit-identical to their padded-batch
+    decode, for the fp32 and the int16 form and for decode + resample; a shortened item matches its standalone decode."""
+    from fireredtts2_b200.config import SMALL
+    from fireredtts2_b200.weights import synthetic_state_dict, synthetic_tokens
+    cfg = SMALL
+    codec = build_codec(cfg, synthetic_state_dict(cfg, 9))
+    L = 11
+    tok = torch.from_numpy(synthetic_tokens(cfg, 5, L, 4)).cuda()
+    lens = torch.tensor([L, 0, L + 5, -3, 4], dtype=torch.int32)
+    full = codec.decode(tok)
+    spt = cfg.samples_per_token
+    for pcm16 in (False, True):
+        ref = codec.decode(tok, pcm16=True) if pcm16 else full
+        a = codec.decode(tok, lengths=lens, pcm16=pcm16)
+        assert torch.equal(a[0], ref[0]) and torch.equal(a[2], ref[2])
+        assert not bool(a[1].any()) and not bool(a[3].any())
+        assert not bool(a[4, 4 * spt:].any()) and bool(a[4, :4 * spt].any())
+    # against the standalone decode of the same 4 tokens: another batch shape, so other kernels may serve it (32 rows here)
+    # — equal within the parity tolerance, not necessarily bit for bit
+    short = codec.decode(tok[4:5, :, :4])
+    _, snr = report("ragged item vs standalone decode", to_np(short[0]), to_np(codec.decode(tok, lengths=lens)[4, :4 * spt]))
+    assert snr >= 40.0
+    a24, a16 = codec.decode_resampled(tok, 16000, lengths=lens)
+    assert torch.equal(a24, codec.decode(tok, lengths=lens))
+    assert not bool(a16[1].any()) and not bool(a16[3].any()) and bool(a16[0].any())
+    # every item empty
+    z = codec.decode(tok, lengths=torch.zeros(5, dtype=torch.int32))
+    assert z.shape == full.shape and not bool(z.any())
+
+
 def test_c0_multi_wave_batch_items_are_independent():
     """A batch large enough that every GEMM of the step runs several waves of tiles over the 148 SMs (12 x 159 tokens
     at C0 = 15 264 frames): identical items must decode to bit-identical waveforms, equal to the standalone decode of
