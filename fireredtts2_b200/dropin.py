@@ -17,6 +17,8 @@ from __future__ import annotations
 import dataclasses
 from typing import Any, Optional
 
+import torch
+
 
 @dataclasses.dataclass
 class Installed:
@@ -45,3 +47,60 @@ def install(tts, native_encode: bool = False, frame_tail: bool = True, max_batch
     tts._audio_tokenizer = codec
     gen = GenerateFrameB200.install(tts._model, tail=tail, seed=seed) if frame_tail else None
     return Installed(tts, ref_codec, codec, gen)
+
+
+@torch.inference_mode()      # on a generator function torch enters the mode around every resumption, not across yields
+def generate_stream(tts, text: str, speaker: str, context, max_audio_length_ms: float = 90_000, temperature: float = 0.9,
+                    topk: int = 50, pcm16: bool = True, decoder_factory=None):
+    """The reference's commented-out ``FireRedTTS2.generate_stream`` (fireredtts2.py:259-343) revived on the library
+    (SURVEY §8f.1): same arguments, same prompt assembly through the object's own ``_tokenize_segment`` /
+    ``_tokenize_text_segment``, same frame loop and stopping rule — and one chunk per generated frame, delivered with the
+    same one-frame delay (the chunk of frame *i* is yielded once frame *i+1* exists, the last one with ``last_token=True``).
+
+    What differs from the commented-out code: the codec step does not run between two LLM frames on the caller's stream
+    (``decode_one_token`` at fireredtts2.py:317-321, 338-342) but on ``StreamDecoder``'s side stream — one captured graph replay
+    straight to int16 PCM in pinned host memory — so it overlaps ``generate_frame`` of the next frame; what is yielded is a
+    ``StreamChunk`` (``.samples`` (1, n) pinned host tensor, n = 1560 first / 1920 / 2280 last at hop 240; ``.ready`` the
+    CUDA event to wait on before reading; ``.index``) instead of a device tensor.  ``pcm16=False`` gives fp32 samples.
+    ``tts._audio_tokenizer`` must be a ``RedCodecB200`` (``dropin.install(tts)``); an immediate end-of-speech frame yields
+    nothing (the commented-out code would fail on ``prev_sample.unsqueeze``)."""
+    from .codec import RedCodecB200, StreamDecoder
+    max_generation_len = int(max_audio_length_ms / 80)                                  # fireredtts2.py:271
+    if decoder_factory is None:
+        codec = tts._audio_tokenizer
+        if not isinstance(codec, RedCodecB200):
+            raise TypeError("generate_stream needs the library's codec behind tts._audio_tokenizer: call dropin.install(tts) first")
+        decoder_factory = lambda: StreamDecoder(codec, batch=1, pcm16=pcm16, max_tokens=max(max_generation_len, 1))  # noqa: E731
+    tts._model.reset_caches()                                                       # fireredtts2.py:269
+    tokens, tokens_mask = [], []
+    for segment in context:                                                         # fireredtts2.py:273-276
+        segment_tokens, segment_tokens_mask = tts._tokenize_segment(segment)
+        tokens.append(segment_tokens)
+        tokens_mask.append(segment_tokens_mask)
+    gen_segment_tokens, gen_segment_tokens_mask = tts._tokenize_text_segment(text, speaker)   # fireredtts2.py:278-282
+    tokens.append(gen_segment_tokens)
+    tokens_mask.append(gen_segment_tokens_mask)
+    prompt_tokens = torch.cat(tokens, dim=0).long().to(tts.device)
+    prompt_tokens_mask = torch.cat(tokens_mask, dim=0).bool().to(tts.device)
+    curr_tokens = prompt_tokens.unsqueeze(0)
+    curr_tokens_mask = prompt_tokens_mask.unsqueeze(0)
+    curr_pos = torch.arange(0, prompt_tokens.size(0)).unsqueeze(0).long().to(tts.device)
+    max_seq_len = 3100                                                              # fireredtts2.py:294-299
+    max_context_len = max_seq_len - max_generation_len
+    if curr_tokens.size(1) >= max_context_len:
+        raise ValueError(f"Inputs too long, must be below max_seq_len - max_generation_len: {max_context_len}")
+    dec = decoder_factory()
+    for _ in range(max_generation_len):                                             # fireredtts2.py:305-336
+        sample = tts._model.generate_frame(curr_tokens, curr_tokens_mask, curr_pos, temperature, topk)
+        if torch.all(sample == 0):                                                  # eos
+            break
+        chunk = dec.push(sample)            # codec step of the PREVIOUS frame, on the side stream
+        if chunk is not None:
+            yield chunk
+        curr_tokens = torch.cat([sample, torch.zeros(1, 1).long().to(tts.device)], dim=1).unsqueeze(1)
+        curr_tokens_mask = torch.cat([torch.ones_like(sample).bool(), torch.zeros(1, 1).bool().to(tts.device)],
+                                     dim=1).unsqueeze(1)
+        curr_pos = curr_pos[:, -1:] + 1
+    last = dec.finish()                                                             # last_token=True, fireredtts2.py:338-343
+    if last is not None:
+        yield last

@@ -207,3 +207,66 @@ def test_decode_stream_front_matches_offline_and_wire_format():
     assert dec.finish() is None
     with pytest.raises(ValueError):
         dec.push(frames[2])
+
+
+def test_generate_stream_revived_on_the_library():
+    """dropin.generate_stream (fireredtts2.py:259-343) on a FireRedTTS2-shaped object whose ``_audio_tokenizer`` is the
+    library's codec and whose LM is a stand-in emitting given frames on the device, then an all-zero frame: one chunk per
+    frame, one frame late, int16 PCM in pinned host memory — bit-identical to ``decode_stream`` over the same frames, and
+    the fp32 form within the gate of the oracle's offline decode."""
+    from fireredtts2_b200 import dropin
+    cfg = TINY
+    sd = synthetic_state_dict(cfg, 17)
+    codec = build_codec(cfg, sd, stream_max_tokens=16)
+    nq, n = cfg.num_quantizers, 6
+    tok = synthetic_tokens(cfg, 1, n, 8)
+    tok[0, :, :] = np.maximum(tok[0, :, :], 1)                      # no all-zero frame before the end
+    frames = [torch.from_numpy(tok[0, :, i].astype(np.int32)).cuda().unsqueeze(0) for i in range(n)]
+
+    class Model:
+        def __init__(self):
+            self.n = 0
+
+        def reset_caches(self):
+            self.n = 0
+
+        def generate_frame(self, tokens, mask, pos, temperature, topk):
+            assert tokens.shape[-1] == nq + 1 and tokens.is_cuda
+            self.n += 1
+            return frames[self.n - 1] if self.n <= n else torch.zeros(1, nq, dtype=torch.int32, device="cuda")
+
+    class TTS:
+        device = "cuda:0"
+
+        def __init__(self):
+            self._model, self._audio_tokenizer = Model(), codec
+
+        def _tokenize_segment(self, seg):
+            return torch.zeros(3, nq + 1), torch.ones(3, nq + 1)
+
+        def _tokenize_text_segment(self, text, speaker):
+            return torch.zeros(2, nq + 1), torch.ones(2, nq + 1)
+
+    tts = TTS()
+    spt, pad = cfg.samples_per_token, cfg.istft_pad
+    got = {}
+    for pcm16 in (True, False):
+        chunks = list(dropin.generate_stream(tts, "hi", "[S1]", [None], max_audio_length_ms=1600, pcm16=pcm16))
+        assert tts._model.n == n + 1 and [c.index for c in chunks] == list(range(n))
+        assert [c.samples.shape[1] for c in chunks] == [spt - pad] + [spt] * (n - 2) + [spt + pad]
+        for c in chunks:
+            c.ready.synchronize()
+            assert c.samples.is_pinned()
+        got[pcm16] = np.concatenate([c.samples.numpy()[0].copy() for c in chunks])
+        ref_chunks = list(codec.decode_stream((f[0] for f in frames), pcm16=pcm16))
+        for c in ref_chunks:
+            c.ready.synchronize()
+        assert np.array_equal(got[pcm16], np.concatenate([c.samples.numpy()[0] for c in ref_chunks]))
+    assert got[True].dtype == np.int16 and np.array_equal(got[True], (got[False] * 32767).astype(np.int16))
+    ref = O.decode(sd, tok, cfg.num_heads, cfg.hop_length)[0]
+    _, snr = report("generate_stream/fp32 vs the oracle's offline decode", ref, got[False])
+    assert snr >= SNR_GATE_DB
+    # the generation budget ends the stream too: 3 frames at 240 ms, the third flushed with last_token
+    tts._model = Model()
+    short = list(dropin.generate_stream(tts, "hi", "[S1]", [], max_audio_length_ms=240))
+    assert [c.samples.shape[1] for c in short] == [spt - pad, spt, spt + pad]
