@@ -9,6 +9,11 @@ What is swapped — and nothing else:
     run on the library; without the flag ``encode`` stays delegated to the wrapped reference module;
   * ``tts._model.generate_frame`` (llm.py:274-330) -> ``GenerateFrameB200``: the backbone stays the reference's, everything
     behind ``last_h`` is one ``frt2_fd_generate`` call.
+  * the name ``torchaudio`` inside the reference's module (``fireredtts2.py:5``) -> a pass-through proxy whose
+    ``functional.resample`` sends float CUDA waveforms to the library's resampler: the 24 kHz -> 16 kHz conversion of
+    every generated turn in ``generate_dialogue`` (fireredtts2.py:389-391) stays on the device; CPU tensors (the prompt
+    audio, fireredtts2.py:65) and every other torchaudio attribute go to torchaudio itself.  Only that module's binding
+    changes, ``torchaudio`` as imported anywhere else is untouched.
 The text tokenizer, prompt preparation, the LLM backbone and the dialogue loop are the reference's own code.  There is no
 CPU fallback: on a machine without the library / a CUDA device the constructors raise and the object is left untouched.
 """
@@ -20,6 +25,32 @@ from typing import Any, Optional
 import torch
 
 
+class _FunctionalProxy:
+    """``torchaudio.functional`` as the reference's module sees it after ``install``."""
+
+    def __init__(self, real, resample_fn):
+        self._real, self._resample = real, resample_fn
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+    def resample(self, waveform, orig_freq, new_freq, *args, **kw):
+        """The call at fireredtts2.py:389-391 (positional rates, torchaudio's defaults).  Anything else — a CPU tensor,
+        non-default filter arguments, an integer waveform — is torchaudio's."""
+        if not args and not kw and getattr(waveform, "is_cuda", False) and waveform.is_floating_point():
+            return self._resample(waveform, int(orig_freq), int(new_freq))
+        return self._real.resample(waveform, orig_freq, new_freq, *args, **kw)
+
+
+class _TorchaudioProxy:
+    def __init__(self, real, resample_fn):
+        self._real = real
+        self.functional = _FunctionalProxy(real.functional, resample_fn)
+
+    def __getattr__(self, name):
+        return getattr(self._real, name)
+
+
 @dataclasses.dataclass
 class Installed:
     """What ``install`` replaced; ``uninstall()`` puts the reference's objects back."""
@@ -27,17 +58,23 @@ class Installed:
     reference_codec: Any
     codec: Any
     generate_frame: Optional[Any]
+    module: Optional[Any] = None            # the reference module whose ``torchaudio`` binding was swapped
+    reference_torchaudio: Optional[Any] = None
 
     def uninstall(self) -> None:
         if self.tts._audio_tokenizer is self.codec:
             self.tts._audio_tokenizer = self.reference_codec
         if self.generate_frame is not None:
             self.generate_frame.uninstall()
+        if self.module is not None and isinstance(getattr(self.module, "torchaudio", None), _TorchaudioProxy):
+            self.module.torchaudio = self.reference_torchaudio
 
 
 def install(tts, native_encode: bool = False, frame_tail: bool = True, max_batch: int = 8, seed: int = 0,
-            num_heads: Optional[int] = None) -> Installed:
+            num_heads: Optional[int] = None, resample: bool = True) -> Installed:
     """Both objects are built BEFORE anything is assigned, so a failure (no GPU, unsupported widths) leaves ``tts`` as it was."""
+    import sys
+    from . import codec as codec_mod
     from .codec import RedCodecB200
     from .frame_decoder import FrameDecoderB200, GenerateFrameB200
     device = getattr(tts, "device", "cuda:0")
@@ -46,7 +83,13 @@ def install(tts, native_encode: bool = False, frame_tail: bool = True, max_batch
     tail = FrameDecoderB200.from_reference(tts._model, device=str(device), max_batch=max_batch) if frame_tail else None
     tts._audio_tokenizer = codec
     gen = GenerateFrameB200.install(tts._model, tail=tail, seed=seed) if frame_tail else None
-    return Installed(tts, ref_codec, codec, gen)
+    module = sys.modules.get(type(tts).__module__) if resample else None
+    real_ta = getattr(module, "torchaudio", None) if module is not None else None
+    if real_ta is None or isinstance(real_ta, _TorchaudioProxy) or not hasattr(real_ta, "functional"):
+        module = real_ta = None                 # nothing to swap (or already swapped by an earlier install)
+    else:
+        module.torchaudio = _TorchaudioProxy(real_ta, lambda w, o, n: codec_mod.resample(w, o, n))
+    return Installed(tts, ref_codec, codec, gen, module, real_ta)
 
 
 @torch.inference_mode()      # on a generator function torch enters the mode around every resumption, not across yields
