@@ -92,6 +92,17 @@ def install(tts, native_encode: bool = False, frame_tail: bool = True, max_batch
     return Installed(tts, ref_codec, codec, gen, module, real_ta)
 
 
+def _feed_back(sample, pos):
+    """The next frame's LM input from the frame just sampled (fireredtts2.py:326-336, the live loop's :183-192): one row
+    ``[code_0 .. code_{nq-1}, 0]`` with the text column masked out, at the next position."""
+    b, nq = sample.shape
+    tokens = torch.zeros((b, 1, nq + 1), dtype=torch.long, device=sample.device)
+    tokens[:, 0, :nq] = sample
+    mask = torch.ones((b, 1, nq + 1), dtype=torch.bool, device=sample.device)
+    mask[:, 0, nq] = False
+    return tokens, mask, pos[:, -1:] + 1
+
+
 @torch.inference_mode()      # on a generator function torch enters the mode around every resumption, not across yields
 def generate_stream(tts, text: str, speaker: str, context, max_audio_length_ms: float = 90_000, temperature: float = 0.9,
                     topk: int = 50, pcm16: bool = True, decoder_factory=None):
@@ -140,10 +151,7 @@ def generate_stream(tts, text: str, speaker: str, context, max_audio_length_ms: 
         chunk = dec.push(sample)            # codec step of the PREVIOUS frame, on the side stream
         if chunk is not None:
             yield chunk
-        curr_tokens = torch.cat([sample, torch.zeros(1, 1).long().to(tts.device)], dim=1).unsqueeze(1)
-        curr_tokens_mask = torch.cat([torch.ones_like(sample).bool(), torch.zeros(1, 1).bool().to(tts.device)],
-                                     dim=1).unsqueeze(1)
-        curr_pos = curr_pos[:, -1:] + 1
+        curr_tokens, curr_tokens_mask, curr_pos = _feed_back(sample, curr_pos)
     last = dec.finish()                                                             # last_token=True, fireredtts2.py:338-343
     if last is not None:
         yield last
