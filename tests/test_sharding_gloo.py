@@ -121,3 +121,41 @@ def test_unit_offsets_is_the_concatenation_layout():
     offs = unit_offsets(lens)
     assert offs[0] == 0 and offs[-1] == 1920 * 2250 and len(offs) == len(lens) + 1
     assert all(offs[i + 1] - offs[i] == 1920 * lens[i] for i in range(len(lens)))
+
+
+def test_partition_and_batches_properties():
+    """Property tests of the host-side planning (hypothesis): every unit is owned exactly once, the plan is deterministic
+    (every rank computes it without communicating), the greedy bound holds (max load <= mean load + longest unit), batches
+    respect both limits, keep every unit, and are ordered longest first."""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    from fireredtts2_b200.sharding import unit_offsets
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(1, 375), min_size=0, max_size=60), st.integers(1, 8))
+    def plan_props(lens, world):
+        plan = partition_units(lens, world)
+        assert plan == partition_units(list(lens), world) and len(plan) == world
+        assert sorted(i for p in plan for i in p) == list(range(len(lens)))
+        assert all(p == sorted(p) for p in plan)
+        loads = [sum(lens[i] for i in p) for p in plan]
+        if lens:
+            assert max(loads) <= sum(lens) / world + max(lens)
+            assert max(loads) - min(loads) <= max(lens)
+        offs = unit_offsets(lens, 8)
+        assert len(offs) == len(lens) + 1 and offs[0] == 0 and offs[-1] == 8 * sum(lens)
+        assert all(b - a == 8 * n for a, b, n in zip(offs, offs[1:], lens))
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(1, 375), min_size=1, max_size=60), st.integers(1, 64), st.integers(1, 64 * 375))
+    def batch_props(lens, max_batch, max_tokens):
+        bs = make_batches(range(len(lens)), lens, max_batch, max_tokens)
+        assert sorted(i for b in bs for i in b) == list(range(len(lens)))
+        flat = [lens[i] for b in bs for i in b]
+        assert flat == sorted(flat, reverse=True)                       # longest first, across and inside the batches
+        for b in bs:
+            padded = len(b) * max(lens[i] for i in b)
+            assert 1 <= len(b) <= max_batch and (padded <= max_tokens or len(b) == 1)
+
+    plan_props()
+    batch_props()
