@@ -172,3 +172,12 @@ def test_header_is_plain_c(tmp_path):
                         "-Wl,--unresolved-symbols=ignore-in-shared-libs"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_every_entry_point_is_documented_for_integrators():
+    """INTEGRATION.md names every function include/frt2.h declares (the reference-side binding document stays complete)."""
+    hdr = open(os.path.join(ROOT, "include", "frt2.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    names = sorted(set(re.findall(r"\b(frt2_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 50
+    assert [n for n in names if n not in doc] == []
